@@ -1,0 +1,1104 @@
+// deb_core.cuh -- per-mode Einstein-Boltzmann integrator, one WARP per k-mode.
+//
+// The algorithm is the reference's (Rodas5Transformed + diffrax PID loop, see include/discoeb_b200.h
+// for the file:line map) but organised for a Blackwell SM:
+//   * 32 lanes own the n state variables cyclically (element e -> lane e%32); the 7 stage vectors
+//     k_1..k_7 live in registers, the stage state / right-hand side in shared memory;
+//   * the Jacobian is never formed: W = I/(gamma dt) - J is split into
+//       - the scale-factor column (row 0 is closed, so x_0 is solved first and moved to the rhs),
+//       - 3+nq tri-diagonal hierarchy tails (l >= 3) eliminated by a pivot-free continued-fraction
+//         sweep whose Schur complement touches one diagonal entry of the head per chain,
+//       - a dense "head" (metric, fluids, l <= 2 of every hierarchy, a h') of 17+3nq <= 32 unknowns
+//         factored by LU with partial pivoting, one lane per row;
+//   * d f/d a comes from a forward-dual evaluation of the same RHS code (what jax.jacfwd does).
+//
+// This header compiles for the device (nvcc) and, with -DDEB_CPU_EMU, as plain C++ in which the
+// 32 lanes are executed by loops.  The emulation build is TEST INFRASTRUCTURE only (tests/emu):
+// it lets the CPU test-suite run the very same source against the oracle; the Python package
+// never loads it.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#ifdef DEB_CPU_EMU
+#define DEB_DEV inline
+#define DEB_HD inline
+#define DEB_LDG(p) (*(p))
+#define DEB_LANES_BEGIN for (int lane = 0; lane < 32; ++lane) {
+#define DEB_LANES_END }
+#define DEB_LANE0_BEGIN {
+#define DEB_LANE0_END }
+#define DEB_SYNC()
+#define DEB_REGS(type, name, dims) type name##_all[32] dims
+#define DEB_USE(name) auto& name = name##_all[lane]
+#define DEB_SHFL(name, src) (name##_all[(src)])
+#define DEB_ANY(name) ([&]() { int a_ = 0; for (int l_ = 0; l_ < 32; ++l_) a_ |= (name##_all[l_] != 0); return a_; }())
+#else
+#define DEB_DEV __device__ __forceinline__
+#define DEB_HD __host__ __device__ __forceinline__
+#define DEB_LDG(p) __ldg(p)
+#define DEB_LANES_BEGIN {
+#define DEB_LANES_END } __syncwarp();
+#define DEB_LANE0_BEGIN if (lane == 0) {
+#define DEB_LANE0_END } __syncwarp();
+#define DEB_SYNC() __syncwarp()
+#define DEB_REGS(type, name, dims) type name dims
+#define DEB_USE(name)
+#define DEB_SHFL(name, src) __shfl_sync(0xffffffffu, name, (src))
+#define DEB_ANY(name) __any_sync(0xffffffffu, name)
+#endif
+
+namespace deb {
+
+constexpr int NSCAL = 24;
+enum { S_OMEGAM = 0, S_OMEGAB, S_OMEGADE, S_OMEGAK, S_GRHOM, S_GRHOG, S_GRHOR, S_NEFF, S_NMNU, S_AMNU,
+       S_W0, S_WA, S_CS2DE, S_YHE, S_H0, S_TAUMIN, S_AS, S_NS, S_KP };
+enum { T_CS2A = 0, T_XE, T_LRHONU, T_LPNU, T_A_OF_TAU, T_XE_OF_TAU, T_TAU_OF_A, NSPLINE };
+
+constexpr int NQMAX = 5;          // head must fit one lane per row: 17 + 3 nq <= 32
+constexpr int NHMAX = 32;
+constexpr int NCHMAX = 3 + NQMAX;
+constexpr int LMAXCAP = 96;
+constexpr int LDH = 33;           // odd leading dimension: conflict-free column access
+
+// row types (element descriptors)
+enum RowType : int { R_A = 0, R_AHP, R_ETA, R_DC, R_TC, R_DB, R_TB, R_F0, R_F1, R_F2, R_G0, R_G1, R_G2,
+                     R_N0, R_N1, R_N2, R_P0, R_P1, R_P2, R_DQ, R_TQ, R_GEN, R_TRUNC };
+
+// Rodas5 coefficients, transformed form (ode_integrators_stiff.py:622-687)
+#define RD_GAMMA 0.19
+#define RD_A21 2.0
+#define RD_A31 3.040894194418781
+#define RD_A32 1.041747909077569
+#define RD_A41 2.576417536461461
+#define RD_A42 1.622083060776640
+#define RD_A43 -0.9089668560264532
+#define RD_A51 2.760842080225597
+#define RD_A52 1.446624659844071
+#define RD_A53 -0.3036980084553738
+#define RD_A54 0.2877498600325443
+#define RD_A61 -14.09640773051259
+#define RD_A62 6.925207756232704
+#define RD_A63 -41.47510893210728
+#define RD_A64 2.343771018586405
+#define RD_A65 24.13215229196062
+#define RD_C21 -10.31323885133993
+#define RD_C31 -21.04823117650003
+#define RD_C32 -7.234992135176716
+#define RD_C41 32.22751541853323
+#define RD_C42 -4.943732386540191
+#define RD_C43 19.44922031041879
+#define RD_C51 -20.69865579590063
+#define RD_C52 -8.816374604402768
+#define RD_C53 1.260436877740897
+#define RD_C54 -0.7495647613787146
+#define RD_C61 -46.22004352711257
+#define RD_C62 -17.49534862857472
+#define RD_C63 -289.6389582892057
+#define RD_C64 93.60855400400906
+#define RD_C65 318.3822534212147
+#define RD_C71 34.20013733472935
+#define RD_C72 -14.15535402717690
+#define RD_C73 57.82335640988400
+#define RD_C74 25.83362985412365
+#define RD_C75 1.408950972071624
+#define RD_C76 -6.551835421242162
+#define RD_C81 42.57076742291101
+#define RD_C82 -13.80770672017997
+#define RD_C83 93.98938432427124
+#define RD_C84 18.77919633714503
+#define RD_C85 -31.58359187223370
+#define RD_C86 -6.685968952921985
+#define RD_C87 -5.810979938412932
+#define RD_CT2 0.38
+#define RD_CT3 0.3878509998321533
+#define RD_CT4 0.4839718937873840
+#define RD_CT5 0.4570477008819580
+#define RD_D1 0.19
+#define RD_D2 -0.1823079225333714636
+#define RD_D3 -0.319231832186874912
+#define RD_D4 0.3449828624725343
+#define RD_D5 -0.377417564392089818
+
+#define AKTHOM_RHS 2.3038921003709498e-9   // perturbations.py:215
+#define AKTHOM_START 2.3048e-9             // perturbations.py:648
+
+// ---------------------------------------------------------------------------------------------
+// forward dual number (value, d/da): the seed is the scale factor y[0]
+// ---------------------------------------------------------------------------------------------
+struct Dual { double v, d; };
+DEB_DEV Dual mk(double v, double d) { Dual r; r.v = v; r.d = d; return r; }
+DEB_DEV Dual operator+(Dual a, Dual b) { return mk(a.v + b.v, a.d + b.d); }
+DEB_DEV Dual operator-(Dual a, Dual b) { return mk(a.v - b.v, a.d - b.d); }
+DEB_DEV Dual operator*(Dual a, Dual b) { return mk(a.v * b.v, a.d * b.v + a.v * b.d); }
+DEB_DEV Dual operator/(Dual a, Dual b) { double q = a.v / b.v; return mk(q, (a.d - q * b.d) / b.v); }
+DEB_DEV Dual operator+(Dual a, double b) { return mk(a.v + b, a.d); }
+DEB_DEV Dual operator+(double b, Dual a) { return mk(a.v + b, a.d); }
+DEB_DEV Dual operator-(Dual a, double b) { return mk(a.v - b, a.d); }
+DEB_DEV Dual operator-(double b, Dual a) { return mk(b - a.v, -a.d); }
+DEB_DEV Dual operator-(Dual a) { return mk(-a.v, -a.d); }
+DEB_DEV Dual operator*(Dual a, double b) { return mk(a.v * b, a.d * b); }
+DEB_DEV Dual operator*(double b, Dual a) { return mk(a.v * b, a.d * b); }
+DEB_DEV Dual operator/(Dual a, double b) { return mk(a.v / b, a.d / b); }
+DEB_DEV Dual operator/(double b, Dual a) { double q = b / a.v; return mk(q, -q * a.d / a.v); }
+DEB_DEV Dual dsqrt(Dual a) { double s = sqrt(a.v); return mk(s, 0.5 * a.d / s); }
+DEB_DEV Dual dexp(Dual a) { double e = exp(a.v); return mk(e, e * a.d); }
+DEB_DEV Dual dlog(Dual a) { return mk(log(a.v), a.d / a.v); }
+DEB_DEV double dsqrt(double a) { return sqrt(a); }
+DEB_DEV double dexp(double a) { return exp(a); }
+DEB_DEV double dlog(double a) { return log(a); }
+DEB_DEV double val(double a) { return a; }
+DEB_DEV double val(Dual a) { return a.v; }
+DEB_DEV double der(double) { return 0.0; }
+DEB_DEV double der(Dual a) { return a.d; }
+
+// ---------------------------------------------------------------------------------------------
+// natural cubic spline lookup (spline_interpolation.py:130-153)
+// ---------------------------------------------------------------------------------------------
+struct Spl { const double* x; const double* y; const double* S; int n; };
+
+// idx = clip(searchsorted_left(x, xn) - 1, 0, n-2); `hint` (>=0) makes it a local walk
+DEB_DEV int spl_locate(const double* x, int n, double xn, int hint) {
+  int i;
+  if (hint < 0) {
+    int lo = 0, hi = n;               // first index with x[idx] >= xn
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (DEB_LDG(x + mid) < xn) lo = mid + 1; else hi = mid; }
+    i = lo - 1;
+    if (i < 0) i = 0;
+    if (i > n - 2) i = n - 2;
+    return i;
+  }
+  i = hint;
+  if (i > n - 2) i = n - 2;
+  while (i < n - 2 && DEB_LDG(x + i + 1) < xn) ++i;
+  while (i > 0 && DEB_LDG(x + i) >= xn) --i;
+  return i;
+}
+
+DEB_DEV double spl_eval_at(const Spl& s, int i, double xn) {
+  double x0 = DEB_LDG(s.x + i), x1 = DEB_LDG(s.x + i + 1);
+  double h = x1 - x0;
+  double t = (xn - x0) / h;
+  double A = 1.0 - t, B = t;
+  return A * DEB_LDG(s.y + i) + B * DEB_LDG(s.y + i + 1)
+       + ((A * A * A - A) * DEB_LDG(s.S + i) + (B * B * B - B) * DEB_LDG(s.S + i + 1)) * (h * h) / 6.0;
+}
+DEB_DEV Dual spl_eval_at(const Spl& s, int i, Dual xn) {
+  double x0 = DEB_LDG(s.x + i), x1 = DEB_LDG(s.x + i + 1);
+  double h = x1 - x0;
+  double t = (xn.v - x0) / h;
+  double A = 1.0 - t, B = t;
+  double y0 = DEB_LDG(s.y + i), y1 = DEB_LDG(s.y + i + 1), S0 = DEB_LDG(s.S + i), S1 = DEB_LDG(s.S + i + 1);
+  double v = A * y0 + B * y1 + ((A * A * A - A) * S0 + (B * B * B - B) * S1) * (h * h) / 6.0;
+  double dvdt = (y1 - y0) + (-(3.0 * A * A - 1.0) * S0 + (3.0 * B * B - 1.0) * S1) * (h * h) / 6.0;
+  return mk(v, dvdt / h * xn.d);
+}
+DEB_DEV double spl_eval(const Spl& s, double xn) { return spl_eval_at(s, spl_locate(s.x, s.n, xn, -1), xn); }
+
+// ---------------------------------------------------------------------------------------------
+// launch-wide problem description
+// ---------------------------------------------------------------------------------------------
+struct Problem {
+  int ncosmo, nk, nout, n, nh, nch, np;          // np: n rounded up to even (smem vector stride)
+  int lmaxg, lmaxgp, lmaxr, lmaxnu, nq, nth, nnu;
+  int max_steps, return_full, k_per_cosmo, power_idx;
+  int ig, igp, ir, iq0;
+  double rtol, atol, c1, c2, c3, factormax, factormin, safety;
+  const double* scalars; const double* tables; const double* kmodes; const double* aexp_out;
+  const double* tau_out;                         // [ncosmo, nout] (filled by the tau_out pre-kernel)
+  double* y_out; double* pk_out;
+  int* status; int* nsteps; int* naccept;
+  // debug single-step mode
+  const double* dbg_t0; const double* dbg_t1; const double* dbg_y0; double* dbg_y1; double* dbg_err;
+  double* dbg_tau_start; double* dbg_ics;
+  // debug replay mode: follow a prescribed step sequence (oracle trace) instead of the controller
+  const double* rp_tnext; const int* rp_keep; const int* rp_n; int rp_stride;
+  int mode;                                      // 0 evolve, 1 single step, 2 prologue only, 3 replay
+  unsigned int* ticket;                          // work-queue counter
+};
+
+// momentum bins (background.py:27-38); weights already divided by 7 pi^4/120
+struct NuBins { double q[NQMAX], w[NQMAX], dl[NQMAX]; };
+
+// launch-constant tables placed in shared memory once per CTA
+struct CtaConst {
+  double cl[LMAXCAP];     // l/(2l+1)
+  double ch[LMAXCAP];     // (l+1)/(2l+1)
+  NuBins nu;
+  int hidx[NHMAX];        // head position -> state index
+  int htype[NHMAX];       // head position -> row type
+  int hbin[NHMAX];        // head position -> momentum bin (P rows)
+  int ch_base[NCHMAX];    // chain -> state index of its l=0 element
+  int ch_stride[NCHMAX];
+  int ch_lmax[NCHMAX];
+  int ch_h2[NCHMAX];      // chain -> head position of its l=2 element
+  const int* desc;        // element -> type | ell<<8 | chain<<16   [np] (dynamic shared memory)
+};
+
+DEB_DEV Spl get_spline(const Problem& P, int cosmo, int which) {
+  size_t tl = 3 * (size_t)(5 * P.nth + 2 * P.nnu);
+  const double* base = P.tables + (size_t)cosmo * tl;
+  size_t off = 0;
+  for (int s = 0; s < which; ++s) off += 3 * (size_t)((s == T_LRHONU || s == T_LPNU) ? P.nnu : P.nth);
+  int n = (which == T_LRHONU || which == T_LPNU) ? P.nnu : P.nth;
+  Spl r; r.x = base + off; r.y = r.x + n; r.S = r.y + n; r.n = n;
+  return r;
+}
+
+// element descriptor: type | ell << 8 | chain << 16
+DEB_DEV int elem_desc(const Problem& P, int e) {
+  const int nq = P.nq;
+  if (e >= P.n) return -1;
+  if (e == 0) return R_A;
+  if (e == 1) return R_AHP;
+  if (e == 2) return R_ETA;
+  if (e == 3) return R_DC;
+  if (e == 4) return R_TC;
+  if (e == 5) return R_DB;
+  if (e == 6) return R_TB;
+  if (e == P.n - 2) return R_DQ;
+  if (e == P.n - 1) return R_TQ;
+  int chain, l, L;
+  if (e < P.igp) { chain = 0; l = e - P.ig; L = P.lmaxg; }
+  else if (e < P.ir) { chain = 1; l = e - P.igp; L = P.lmaxgp; }
+  else if (e < P.iq0) { chain = 2; l = e - P.ir; L = P.lmaxr; }
+  else { int o = e - P.iq0; l = o / nq; chain = 3 + (o - l * nq); L = P.lmaxnu; }
+  int type;
+  if (l == L) type = R_TRUNC;
+  else if (l >= 3) type = R_GEN;
+  else if (chain == 0) type = R_F0 + l;
+  else if (chain == 1) type = R_G0 + l;
+  else if (chain == 2) type = R_N0 + l;
+  else type = R_P0 + l;
+  return type | (l << 8) | (chain << 16);
+}
+
+DEB_DEV void init_cta_const(const Problem& P, CtaConst& C, int* desc, int tid, int nthreads) {
+  for (int e = tid; e < P.np; e += nthreads) desc[e] = elem_desc(P, e);
+  for (int l = tid; l < LMAXCAP; l += nthreads) {
+    C.cl[l] = (double)l / (double)(2 * l + 1);
+    C.ch[l] = (double)(l + 1) / (double)(2 * l + 1);
+  }
+  if (tid == 0) {
+    C.desc = desc;
+    const int nq = P.nq;
+    const double q3[3] = {0.913201, 3.37517, 7.79184}, k3[3] = {0.0687359, 3.31435, 2.29911};
+    const double q4[4] = {0.7, 2.62814, 5.90428, 12.0}, k4[4] = {0.0200251, 1.84539, 3.52736, 0.289427};
+    const double q5[5] = {0.583165, 2.0, 4.0, 7.26582, 13.0}, k5[5] = {0.0081201, 0.689407, 2.8063, 2.05156, 0.12681};
+    for (int i = 0; i < nq; ++i) {
+      double q = nq == 3 ? q3[i] : (nq == 4 ? q4[i] : q5[i]);
+      double kw = nq == 3 ? k3[i] : (nq == 4 ? k4[i] : k5[i]);
+      double dl = -q / (1.0 + exp(-q));
+      C.nu.q[i] = q; C.nu.dl[i] = dl;
+      C.nu.w[i] = kw / (-0.25 * dl) / 5.682196976983475;
+    }
+    int h = 0;
+    auto put = [&](int e, int type, int bin) { C.hidx[h] = e; C.htype[h] = type; C.hbin[h] = bin; ++h; };
+    put(2, R_ETA, 0); put(3, R_DC, 0); put(4, R_TC, 0); put(5, R_DB, 0); put(6, R_TB, 0);
+    for (int l = 0; l < 3; ++l) put(P.ig + l, R_F0 + l, 0);
+    C.ch_h2[0] = h - 1;
+    for (int l = 0; l < 3; ++l) put(P.igp + l, R_G0 + l, 0);
+    C.ch_h2[1] = h - 1;
+    for (int l = 0; l < 3; ++l) put(P.ir + l, R_N0 + l, 0);
+    C.ch_h2[2] = h - 1;
+    for (int l = 0; l < 3; ++l)
+      for (int i = 0; i < nq; ++i) { put(P.iq0 + l * nq + i, R_P0 + l, i); if (l == 2) C.ch_h2[3 + i] = h - 1; }
+    put(P.n - 2, R_DQ, 0); put(P.n - 1, R_TQ, 0); put(1, R_AHP, 0);
+    C.ch_base[0] = P.ig;  C.ch_stride[0] = 1; C.ch_lmax[0] = P.lmaxg;
+    C.ch_base[1] = P.igp; C.ch_stride[1] = 1; C.ch_lmax[1] = P.lmaxgp;
+    C.ch_base[2] = P.ir;  C.ch_stride[2] = 1; C.ch_lmax[2] = P.lmaxr;
+    for (int i = 0; i < nq; ++i) { C.ch_base[3 + i] = P.iq0 + i; C.ch_stride[3 + i] = nq; C.ch_lmax[3 + i] = P.lmaxnu; }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-warp shared-memory workspace (carved out of dynamic shared memory by the kernel)
+// ---------------------------------------------------------------------------------------------
+struct WarpWs {
+  double* y;    // accepted state at tprev                         [np]
+  double* u;    // stage state                                     [np]
+  double* r;    // stage right-hand side, solved in place -> k_i   [np]
+  double* m;    // tail backward multipliers W_{l,l+1}/e_{l+1}     [np]
+  double* ie;   // tail inverse pivots 1/e_l                       [np]
+  double* g;    // tail forward multipliers -W_{l,l-1}/e_l         [np]
+  double* ja;   // d f / d a at (t0, y0)                           [np]
+  double* lu;   // head LU                                         [NHMAX*LDH]
+  double* gh;   // d h'/d y_c over head columns                    [NHMAX]
+  double* ge;   // d eta'/d y_c                                    [NHMAX]
+  double* j1;   // d f_1/d y_c  (the a h' row)                     [NHMAX]
+  double* kc;   // chain wavenumber k or k v_i (value, d/da)       [2*NCHMAX]
+  double* kap;  // chain damping opac or 0 (value, d/da)           [2*NCHMAX]
+  int* perm;    // pivot row of elimination step j                 [NHMAX]
+};
+DEB_HD size_t warp_ws_doubles(int np) { return (size_t)7 * np + NHMAX * LDH + 3 * NHMAX + 4 * NCHMAX + NHMAX / 2 + 2; }
+DEB_DEV void carve(WarpWs& W, double* base, int np) {
+  W.y = base; W.u = W.y + np; W.r = W.u + np; W.m = W.r + np; W.ie = W.m + np; W.g = W.ie + np; W.ja = W.g + np;
+  W.lu = W.ja + np; W.gh = W.lu + NHMAX * LDH; W.ge = W.gh + NHMAX; W.j1 = W.ge + NHMAX;
+  W.kc = W.j1 + NHMAX; W.kap = W.kc + 2 * NCHMAX; W.perm = (int*)(W.kap + 2 * NCHMAX);
+}
+
+// per-mode constants
+struct Cosmo {
+  double Omegam, Omegab, OmegaDE, Omegak, grhom, grhog, grhor, Neff, Nmnu, amnu, w0, wa, cs2de, YHe, H0, taumin;
+  double As, ns, kp;
+  double Omegac, akthom, rq_exp;
+  Spl cs2a, xe, lrn, lpn, a_of_tau, xe_of_tau, tau_of_a;
+};
+DEB_DEV Cosmo load_cosmo(const Problem& P, int c) {
+  const double* s = P.scalars + (size_t)c * NSCAL;
+  Cosmo o;
+  o.Omegam = DEB_LDG(s + S_OMEGAM); o.Omegab = DEB_LDG(s + S_OMEGAB); o.OmegaDE = DEB_LDG(s + S_OMEGADE);
+  o.Omegak = DEB_LDG(s + S_OMEGAK); o.grhom = DEB_LDG(s + S_GRHOM); o.grhog = DEB_LDG(s + S_GRHOG);
+  o.grhor = DEB_LDG(s + S_GRHOR); o.Neff = DEB_LDG(s + S_NEFF); o.Nmnu = DEB_LDG(s + S_NMNU);
+  o.amnu = DEB_LDG(s + S_AMNU); o.w0 = DEB_LDG(s + S_W0); o.wa = DEB_LDG(s + S_WA); o.cs2de = DEB_LDG(s + S_CS2DE);
+  o.YHe = DEB_LDG(s + S_YHE); o.H0 = DEB_LDG(s + S_H0); o.taumin = DEB_LDG(s + S_TAUMIN);
+  o.As = DEB_LDG(s + S_AS); o.ns = DEB_LDG(s + S_NS); o.kp = DEB_LDG(s + S_KP);
+  o.Omegac = o.Omegam - o.Omegab;
+  o.akthom = AKTHOM_RHS * (1.0 - o.YHe) * o.Omegab * o.H0 * o.H0;
+  o.rq_exp = -3.0 * (1.0 + o.w0 + o.wa);
+  o.cs2a = get_spline(P, c, T_CS2A); o.xe = get_spline(P, c, T_XE); o.lrn = get_spline(P, c, T_LRHONU);
+  o.lpn = get_spline(P, c, T_LPNU); o.a_of_tau = get_spline(P, c, T_A_OF_TAU);
+  o.xe_of_tau = get_spline(P, c, T_XE_OF_TAU); o.tau_of_a = get_spline(P, c, T_TAU_OF_A);
+  return o;
+}
+
+// background coefficients at scale factor a (perturbations.py:176-218, background.py:110-121)
+template <class T> struct Bg {
+  T a, H, opac, cs2, pbo, wq1, wq, ca2;
+  T gc, gb, gg, gr, gnu, gq;      // grhom Oc/a, grhom Ob/a, grhog/a^2, grhor Neff/a^2, grhor Nmnu/a^2, grhom ODE rhoQ a^2
+  T v[NQMAX];
+};
+struct Hints { int th, nu; };
+
+template <class T>
+DEB_DEV void compute_bg(const Cosmo& c, const NuBins& nb, int nq, T a, Hints& hint, Bg<T>& b) {
+  T loga = dlog(a);
+  hint.th = spl_locate(c.cs2a.x, c.cs2a.n, val(loga), hint.th);
+  hint.nu = spl_locate(c.lrn.x, c.lrn.n, val(loga), hint.nu);
+  T inva = 1.0 / a;
+  T inva2 = inva * inva;
+  b.a = a;
+  b.cs2 = spl_eval_at(c.cs2a, hint.th, loga) * inva;
+  T xe = spl_eval_at(c.xe, hint.th, loga);
+  T rhonu = dexp(spl_eval_at(c.lrn, hint.nu, loga));
+  T rhoq = dexp(c.rq_exp * loga + 3.0 * c.wa * (a - 1.0));
+  b.wq = c.w0 + c.wa * (1.0 - a);
+  b.wq1 = 1.0 + b.wq;
+  b.gc = (c.grhom * c.Omegac) * inva;
+  b.gb = (c.grhom * c.Omegab) * inva;
+  b.gg = c.grhog * inva2;
+  b.gr = (c.grhor * c.Neff) * inva2;
+  b.gnu = (c.grhor * c.Nmnu) * inva2;
+  b.gq = (c.grhom * c.OmegaDE) * rhoq * (a * a);
+  T grho = (c.grhom * c.Omegam) * inva + (c.grhog + c.grhor * (c.Neff + c.Nmnu * rhonu)) * inva2
+         + b.gq + c.grhom * c.Omegak;
+  b.H = dsqrt(grho / 3.0);
+  T wqp = -c.wa * b.H * a;
+  b.ca2 = b.wq - wqp / 3.0 / (b.wq1 + 1e-6) / b.H;
+  b.opac = xe * c.akthom * inva2;
+  b.pbo = (4.0 / 3.0 * c.grhog / (c.grhom * c.Omegab)) * inva * b.opac;
+  for (int i = 0; i < nq; ++i) {
+    T aq = a * (c.amnu / nb.q[i]);
+    b.v[i] = 1.0 / dsqrt(1.0 + aq * aq);
+  }
+}
+
+// metric sources and the three constraint quantities (perturbations.py:229-261)
+template <class T> struct Metric { T hp, ep, al, f1; };
+
+template <class T>
+DEB_DEV void compute_metric(const Problem& P, const Cosmo& c, const NuBins& nb, const Bg<T>& b, const double* u,
+                            double k, Metric<T>& mt) {
+  const int nq = P.nq, iq0 = P.iq0, n = P.n;
+  double eta = u[2], dc = u[3], tc = u[4], db = u[5], tb = u[6], dg = u[7], tg = u[8];
+  double dr = u[P.ir], tr = u[P.ir + 1], dq = u[n - 2], tq = u[n - 1];
+  T drhonu = 0.0 * b.a, dpnu = 0.0 * b.a;
+  double fnu = 0.0;
+  for (int i = 0; i < nq; ++i) {
+    double p0 = u[iq0 + i];
+    drhonu = drhonu + (nb.w[i] * p0) / b.v[i];
+    dpnu = dpnu + (nb.w[i] * p0) * b.v[i];
+    fnu += nb.w[i] * u[iq0 + nq + i];
+  }
+  dpnu = dpnu / 3.0;
+  double k2 = k * k;
+  T rpt = b.wq1 * b.gq * tq;
+  T dgrho = b.gc * dc + b.gb * db + b.gg * dg + b.gr * dr + b.gnu * drhonu + b.gq * dq;
+  T dgpres = (b.gg * dg + b.gr * dr) / 3.0 + b.gnu * dpnu + c.cs2de * (b.gq * dq)
+           + (c.cs2de - b.ca2) * (3.0 * b.H * rpt / k2);
+  T dgtheta = b.gc * tc + b.gb * tb + 4.0 / 3.0 * (b.gg * tg + b.gr * tr) + b.gnu * (k * fnu) + rpt;
+  mt.f1 = -(dgrho + 3.0 * dgpres) * b.a;
+  mt.hp = (2.0 * k2 * eta + dgrho) / b.H;
+  mt.ep = 0.5 * dgtheta / k2;
+  mt.al = (mt.hp + 6.0 * mt.ep) / 2.0 / k2;
+}
+
+// one row of the right-hand side (perturbations.py:226-369).  kc/kap are the chain arrays with
+// layout [value x NCHMAX | d/da x NCHMAX]; the dual instantiation returns d f_e / d a in .d
+template <class T> DEB_DEV T pick(const double* arr, int i);
+template <> DEB_DEV double pick<double>(const double* arr, int i) { return arr[i]; }
+template <> DEB_DEV Dual pick<Dual>(const double* arr, int i) { return mk(arr[i], arr[NCHMAX + i]); }
+
+template <class T>
+DEB_DEV T rhs_row(const Problem& P, const Cosmo& c, const CtaConst& C, const Bg<T>& b, const Metric<T>& mt,
+                  const double* kcA, const double* kapA, const double* u, int e, int desc, double k, double invtau) {
+  const int type = desc & 0xff, l = (desc >> 8) & 0xff, chain = desc >> 16;
+  const double k2 = k * k;
+  switch (type) {
+    case R_A: return b.H * b.a;
+    case R_AHP: return mt.f1;
+    case R_ETA: return mt.ep;
+    case R_DC: return -0.5 * mt.hp - u[4];
+    case R_TC: return -(b.H * u[4]);
+    case R_DB: return -0.5 * mt.hp - u[6];
+    case R_TB: return -(b.H * u[6]) + (k2 * u[5]) * b.cs2 + b.pbo * (u[8] - u[6]);
+    case R_F0: return -2.0 / 3.0 * mt.hp - 4.0 / 3.0 * u[8];
+    case R_F1: return -(b.opac * (u[8] - u[6])) + k2 * (0.25 * u[7] - 0.5 * u[9]);
+    case R_F2: {
+      double polter = u[9] + u[P.igp] + u[P.igp + 2];
+      return 8.0 / 15.0 * (k2 * mt.al) - b.opac * (u[9] - 0.1 * polter) + (8.0 / 15.0 * u[8] - 0.6 * k * u[10]);
+    }
+    case R_N0: return -2.0 / 3.0 * mt.hp - 4.0 / 3.0 * u[P.ir + 1];
+    case R_N1: { T z = 0.0 * b.a; return z + k2 * (0.25 * u[P.ir] - 0.5 * u[P.ir + 2]); }
+    case R_N2: return 8.0 / 15.0 * (k2 * mt.al) + (8.0 / 15.0 * u[P.ir + 1] - 0.6 * k * u[P.ir + 3]);
+    case R_DQ: {
+      double dq = u[P.n - 2], tq = u[P.n - 1];
+      return -(b.wq1 * (tq + 0.5 * mt.hp)) - 3.0 * (c.cs2de - b.wq) * b.H * dq
+           - 9.0 * b.wq1 * (c.cs2de - b.ca2) * (b.H * b.H) * (tq / k2);
+    }
+    case R_TQ: {
+      double dq = u[P.n - 2], tq = u[P.n - 1];
+      return -((1.0 - 3.0 * c.cs2de) * tq) * b.H + (c.cs2de * k2 * dq) / b.wq1;
+    }
+    default: break;
+  }
+  // hierarchy rows: generic three-term recurrence (+ extras for l = 0, 2 of G and psi)
+  const int s = C.ch_stride[chain];
+  T kcv = pick<T>(kcA, chain), kpv = pick<T>(kapA, chain);
+  if (type == R_TRUNC) {
+    int L = C.ch_lmax[chain];
+    return kcv * u[e - s] - (kpv + (double)(L + 1) * invtau) * u[e];
+  }
+  double lin = C.cl[l] * (l > 0 ? u[e - s] : 0.0) - C.ch[l] * u[e + s];
+  T f = kcv * lin - kpv * u[e];
+  if (type == R_G0 || type == R_G2) {
+    double polter = u[9] + u[P.igp] + u[P.igp + 2];
+    f = f + b.opac * (polter * (type == R_G0 ? 0.5 : 0.1));
+  } else if (type == R_P0) {
+    f = f + mt.hp * (C.nu.dl[chain - 3] / 6.0);
+  } else if (type == R_P2) {
+    f = f - (mt.hp / 15.0 + 0.4 * mt.ep) * C.nu.dl[chain - 3];
+  }
+  return f;
+}
+
+// fill the per-chain wavenumber / damping arrays for the current background
+template <class T>
+DEB_DEV void fill_chain_coeffs(const Problem& P, const Bg<T>& b, double k, double* kcA, double* kapA) {
+  for (int ch = 0; ch < P.nch; ++ch) {
+    T kc = ch < 3 ? (0.0 * b.a + k) : b.v[ch - 3] * k;
+    T kp = ch < 2 ? b.opac : 0.0 * b.a;
+    kcA[ch] = val(kc); kcA[NCHMAX + ch] = der(kc);
+    kapA[ch] = val(kp); kapA[NCHMAX + ch] = der(kp);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// prologue: start time (perturbations.py:630-681, util.py:365-396)
+// ---------------------------------------------------------------------------------------------
+DEB_DEV double aprimeoa_plain(const Cosmo& c, double a) {
+  double loga = log(a);
+  double rhonu = exp(spl_eval(c.lrn, loga));
+  double rhoq = exp(c.rq_exp * loga + 3.0 * c.wa * (a - 1.0));
+  double grho = c.grhom * c.Omegam / a + (c.grhog + c.grhor * (c.Neff + c.Nmnu * rhonu)) / (a * a)
+              + c.grhom * c.OmegaDE * rhoq * (a * a) + c.grhom * c.Omegak;
+  return sqrt(grho / 3.0);
+}
+DEB_DEV double cond_small_k(const Cosmo& c, double lt) {
+  double tau = exp(lt);
+  double akthom = AKTHOM_START * (1.0 - c.YHe) * c.Omegab * c.H0 * c.H0;
+  double xe = spl_eval(c.xe_of_tau, tau);
+  double a = spl_eval(c.a_of_tau, tau);
+  double opac = xe * akthom / (a * a);
+  double H = aprimeoa_plain(c, a);
+  return (1.0 / opac) / (1.0 / H) / 0.0004 - 1.0;
+}
+DEB_DEV double cond_large_k(const Cosmo& c, double lt, double k) {
+  double a = spl_eval(c.a_of_tau, exp(lt));
+  return (1.0 / aprimeoa_plain(c, a)) / (1.0 / k) / 0.07 - 1.0;
+}
+DEB_DEV double start_time(const Cosmo& c, double k) {
+  double l0 = log(c.taumin), l1 = log(spl_eval(c.tau_of_a, 0.1));
+  double xl = l0, xr = l1;
+  for (int it = 0; it < 7; ++it) {
+    double xm = 0.5 * (xl + xr);
+    if (cond_large_k(c, xm, k) * cond_large_k(c, xl, k) > 0) xl = xm; else xr = xm;
+  }
+  double lt_large = 0.5 * (xl + xr);
+  xl = l0; xr = l1;
+  for (int it = 0; it < 7; ++it) {
+    double xm = 0.5 * (xl + xr);
+    if (cond_small_k(c, xm) * cond_small_k(c, xl) > 0) xl = xm; else xr = xm;
+  }
+  double lt_small = 0.5 * (xl + xr);
+  return exp(fmin(lt_small, lt_large));
+}
+
+// adiabatic initial conditions (perturbations.py:526-627): value of element e
+struct IcScalars { double a, deltag, thetag, deltar, thetar, shearr, deltaq, thetaq, eta; };
+DEB_DEV IcScalars ic_scalars(const Cosmo& c, double tau, double k) {
+  IcScalars s;
+  double a = spl_eval(c.a_of_tau, tau);
+  double rn = exp(spl_eval(c.lrn, log(a)));
+  double a2 = a * a, a4 = a2 * a2;
+  double rhom = c.grhom * c.Omegam / (a2 * a);
+  double rhor = (c.grhog + c.grhor * (c.Neff + c.Nmnu * rn)) / a4;
+  double rhonu = c.grhor * (c.Neff + c.Nmnu * rn) / a4;
+  double fracb = c.Omegab / c.Omegam, fracnu = rhonu / rhor;
+  double om = a * rhom / sqrt(rhor);
+  const double ci = -1.0;
+  double kt = k * tau, kt2 = kt * kt;
+  s.a = a;
+  s.deltag = -kt2 / 3.0 * (1.0 - om * tau / 5.0) * ci;
+  s.thetag = -(kt2 * kt) / tau / 36.0 * (1.0 - 3.0 * (1.0 + 5.0 * fracb - fracnu) / 20.0 / (1.0 - fracnu) * om * tau) * ci;
+  s.deltar = s.deltag;
+  s.thetar = -(kt2 * kt2) / tau / 36.0 / (4.0 * fracnu + 15.0)
+           * (4.0 * fracnu + 11.0 + 12.0 - 3.0 * (8.0 * fracnu * fracnu + 50.0 * fracnu + 275.0) / 20.0 / (2.0 * fracnu + 15.0) * tau * om) * ci;
+  s.shearr = kt2 / (45.0 + 12.0 * fracnu) * 2.0 * (1.0 + (4.0 * fracnu - 5.0) / 4.0 / (2.0 * fracnu + 15.0) * tau * om) * ci;
+  double wq = c.w0 + c.wa * (1.0 - a);
+  s.deltaq = kt2 / 4.0 * (1.0 + wq) * (4.0 - 3.0 * c.cs2de) / (4.0 - 6.0 * wq + 3.0 * c.cs2de) * ci;
+  s.thetaq = (kt2 * kt2) / tau / 4.0 * c.cs2de / (4.0 - 6.0 * wq + 3.0 * c.cs2de) * ci;
+  s.eta = ci * (1.0 - kt2 / 12.0 / (15.0 + 4.0 * fracnu)
+                * (5.0 + 4.0 * fracnu - (16.0 * fracnu * fracnu + 280.0 * fracnu + 325.0) / 10.0 / (2.0 * fracnu + 15.0) * tau * om));
+  return s;
+}
+DEB_DEV double ic_value(const Problem& P, const Cosmo& c, const NuBins& nb, const IcScalars& s, int desc, double k) {
+  const int type = desc & 0xff, chain = desc >> 16;
+  switch (type) {
+    case R_A: return s.a;
+    case R_ETA: return s.eta;
+    case R_DC: case R_DB: return 0.75 * s.deltag;
+    case R_TB: case R_F1: return s.thetag;
+    case R_F0: return s.deltag;
+    case R_N0: return s.deltar;
+    case R_N1: return s.thetar;
+    case R_N2: return s.shearr * 2.0;
+    case R_DQ: return s.deltaq;
+    case R_TQ: return s.thetaq;
+    case R_P0: case R_P1: case R_P2: {
+      int i = chain - 3;
+      double aq = s.a * c.amnu / nb.q[i];
+      double v = 1.0 / sqrt(1.0 + aq * aq);
+      double dl = nb.dl[i];
+      if (type == R_P0) return -0.25 * dl * s.deltar;
+      if (type == R_P1) return -dl * s.thetar / v / k / 3.0;
+      return -0.5 * dl * s.shearr;
+    }
+    default: return 0.0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// epilogue: state -> 20 output fields (perturbations.py:374-523), executed by one lane
+// ---------------------------------------------------------------------------------------------
+DEB_DEV void convert_outputs(const Problem& P, const Cosmo& c, const NuBins& nb, const double* y, double k, double* out) {
+  const int nq = P.nq, iq0 = P.iq0, n = P.n;
+  double a = y[0], eta = y[2], dc = y[3], tc = y[4], db = y[5], tb = y[6], dg = y[7], tg = y[8];
+  double dr = y[P.ir], tr = y[P.ir + 1], dq = y[n - 2], tq = y[n - 1];
+  double la = log(a);
+  double rhonu = exp(spl_eval(c.lrn, la)), pnu = exp(spl_eval(c.lpn, la));
+  double drhonu = 0.0, fnu = 0.0;
+  for (int i = 0; i < nq; ++i) {
+    double aq = a * c.amnu / nb.q[i];
+    double v = 1.0 / sqrt(1.0 + aq * aq);
+    drhonu += nb.w[i] * y[iq0 + i] / v;
+    fnu += nb.w[i] * y[iq0 + nq + i];
+  }
+  double deltanu = drhonu / rhonu, thetanu = k * fnu / (rhonu + pnu);
+  double wq = c.w0 + c.wa * (1.0 - a);
+  double rhoq = pow(a, c.rq_exp) * exp(3.0 * (a - 1.0) * c.wa);
+  double a2 = a * a;
+  double rpt = (1.0 + wq) * rhoq * c.grhom * c.OmegaDE * tq * a2;
+  double grho = c.grhom * c.Omegam / a + (c.grhog + c.grhor * (c.Neff + c.Nmnu * rhonu)) / a2
+              + c.grhom * c.OmegaDE * rhoq * a2 + c.grhom * c.Omegak;
+  double H = sqrt(grho / 3.0);
+  double mat = c.grhom * (c.Omegac * dc + c.Omegab * db) / a;
+  double matth = c.grhom * (c.Omegac * tc + c.Omegab * tb) / a;
+  double dgrho = mat + (c.grhog * dg + c.grhor * (c.Neff * dr + c.Nmnu * drhonu)) / a2 + c.grhom * c.OmegaDE * dq * rhoq * a2;
+  double dgtheta = matth + 4.0 / 3.0 * (c.grhog * tg + c.Neff * c.grhor * tr) / a2 + c.Nmnu * c.grhor * k * fnu / a2 + rpt;
+  double k2 = k * k;
+  double hp = (2.0 * k2 * eta + dgrho) / H, ep = 0.5 * dgtheta / k2, al = (hp + 6.0 * ep) / 2.0 / k2;
+  double deltam = (mat + (c.grhor * c.Nmnu * drhonu) / a2) / (c.grhom * c.Omegam / a + (c.grhor * c.Nmnu * rhonu) / a2);
+  double thetam = (matth + c.Nmnu * c.grhor * k * fnu / a2) / (3.0 * (c.grhom * c.Omegam / a + c.grhor * c.Nmnu * rhonu / a2));
+  double deltabc = mat / (c.grhom * c.Omegam / a);
+  double thetabc = matth / (3.0 * (c.grhom * c.Omegam / a) / a2);
+  thetam += al * k2; thetabc += al * k2;
+  out[0] = eta; out[1] = ep; out[2] = hp; out[3] = al;
+  out[4] = deltam; out[5] = thetam / H; out[6] = deltabc; out[7] = thetabc / H;
+  out[8] = dc; out[9] = tc / H; out[10] = db; out[11] = tb / H; out[12] = dg; out[13] = tg / H;
+  out[14] = dr; out[15] = tr / H; out[16] = deltanu; out[17] = thetanu / H; out[18] = dq; out[19] = tq / H;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the integrator: one call = one (cosmology, k) mode, executed by one warp
+// ---------------------------------------------------------------------------------------------
+#ifdef DEB_CPU_EMU
+#define DEB_LANE_PARAM
+#else
+#define DEB_LANE_PARAM , const int lane
+#endif
+
+template <int NE>
+DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int mode DEB_LANE_PARAM) {
+  const int n = P.n, nh = P.nh, nch = P.nch, nq = P.nq;
+  const int cosmo = mode / P.nk, kidx = mode - cosmo * P.nk;
+  const double k = DEB_LDG(P.kmodes + (P.k_per_cosmo ? (size_t)cosmo * P.nk + kidx : (size_t)kidx));
+  const double k2 = k * k;
+  const Cosmo c = load_cosmo(P, cosmo);
+  const NuBins& nb = C.nu;
+  const double* tout = P.tau_out + (size_t)cosmo * P.nout;
+
+  DEB_REGS(double, ks, [7][NE]);
+  DEB_REGS(double, hb, );          // head solve: this lane's right-hand side / solution entry
+  DEB_REGS(int, nanflag, );
+  const int* desc = C.desc;
+
+  // ---- prologue ----
+  double t1 = DEB_LDG(tout);
+  double tmin_out = t1;
+  for (int j = 1; j < P.nout; ++j) { double tj = DEB_LDG(tout + j); t1 = fmax(t1, tj); tmin_out = fmin(tmin_out, tj); }
+  double t, tnext;
+  if (P.mode == 1) {
+    t = DEB_LDG(P.dbg_t0 + mode); tnext = DEB_LDG(P.dbg_t1 + mode); t1 = tnext;
+    DEB_LANES_BEGIN
+      for (int e = lane; e < n; e += 32) W.y[e] = DEB_LDG(P.dbg_y0 + (size_t)mode * n + e);
+    DEB_LANES_END
+  } else {
+    double tau_start = 0.99 * fmin(tmin_out, start_time(c, k));
+    IcScalars ics = ic_scalars(c, tau_start, k);
+    DEB_LANES_BEGIN
+      for (int e = lane; e < n; e += 32) W.y[e] = ic_value(P, c, nb, ics, desc[e], k);
+    DEB_LANES_END
+    if (P.mode == 2) {
+      DEB_LANES_BEGIN
+        if (lane == 0) P.dbg_tau_start[mode] = tau_start;
+        for (int e = lane; e < n; e += 32) P.dbg_ics[(size_t)mode * n + e] = W.y[e];
+      DEB_LANES_END
+      return;
+    }
+    t = tau_start;
+    tnext = t + fmin(t / 4.0, 0.5 * (t1 - t));          // dt0 (perturbations.py:756)
+    if (tnext > t1 - 1e-10) tnext = t1;
+  }
+
+  double inv_prev = 1.0, inv_pprev = 1.0;
+  int nsteps = 0, nacc = 0, save_idx = 0, status = 0;
+  Hints hint; hint.th = -1; hint.nu = -1;
+
+  while (t < t1 && nsteps < P.max_steps && status == 0) {
+    if (P.mode == 3) {
+      if (nsteps >= DEB_LDG(P.rp_n + mode)) break;
+      tnext = DEB_LDG(P.rp_tnext + (size_t)mode * P.rp_stride + nsteps);
+    }
+    const double dt = tnext - t;
+    const double invdt = 1.0 / dt;
+    const double idg = 1.0 / (dt * RD_GAMMA);      // diagonal of W = I/(gamma dt) - J
+    const double invt0 = 1.0 / t;
+
+    // ================= Jacobian pieces at (t, y) =================
+    double x0piv;      // W_00 = 1/(gamma dt) - d(H a)/da
+    {
+      Bg<Dual> bd;
+      compute_bg<Dual>(c, nb, nq, mk(W.y[0], 1.0), hint, bd);
+      Metric<Dual> md;
+      compute_metric<Dual>(P, c, nb, bd, W.y, k, md);
+      DEB_LANE0_BEGIN
+        fill_chain_coeffs<Dual>(P, bd, k, W.kc, W.kap);
+      DEB_LANE0_END
+      // f(t,y) -> r (stage-1 right-hand side incl. dt d1 dT), d f/d a -> ja
+      DEB_LANES_BEGIN
+#pragma unroll 1
+        for (int e = lane; e < n; e += 32) {
+          const int de = desc[e];
+          Dual f = rhs_row<Dual>(P, c, C, bd, md, W.kc, W.kap, W.y, e, de, k, invt0);
+          double fv = f.v;
+          if ((de & 0xff) == R_TRUNC) {
+            int L = C.ch_lmax[de >> 16];
+            fv += (dt * RD_D1) * ((double)(L + 1) * invt0 * invt0 * W.y[e]);
+          }
+          W.r[e] = fv; W.ja[e] = f.d;
+        }
+      DEB_LANES_END
+      x0piv = idg - W.ja[0];
+
+      // head-column gradients of h', eta' and of row 1 (value parts only)
+      const double H = bd.H.v, a = bd.a.v;
+      DEB_LANES_BEGIN
+        if (lane < nh) {
+          int ty = C.htype[lane], bin = C.hbin[lane];
+          double wr = 0.0, wp = 0.0, wt = 0.0, extra = 0.0;
+          switch (ty) {
+            case R_ETA: extra = 2.0 * k2 / H; break;
+            case R_DC: wr = bd.gc.v; break;
+            case R_TC: wt = bd.gc.v; break;
+            case R_DB: wr = bd.gb.v; break;
+            case R_TB: wt = bd.gb.v; break;
+            case R_F0: wr = bd.gg.v; wp = bd.gg.v / 3.0; break;
+            case R_F1: wt = 4.0 / 3.0 * bd.gg.v; break;
+            case R_N0: wr = bd.gr.v; wp = bd.gr.v / 3.0; break;
+            case R_N1: wt = 4.0 / 3.0 * bd.gr.v; break;
+            case R_P0: wr = bd.gnu.v * nb.w[bin] / bd.v[bin].v; wp = bd.gnu.v * nb.w[bin] * bd.v[bin].v / 3.0; break;
+            case R_P1: wt = bd.gnu.v * k * nb.w[bin]; break;
+            case R_DQ: wr = bd.gq.v; wp = c.cs2de * bd.gq.v; break;
+            case R_TQ: wt = bd.wq1.v * bd.gq.v; wp = (c.cs2de - bd.ca2.v) * 3.0 * H * wt / k2; break;
+            default: break;
+          }
+          W.gh[lane] = wr / H + extra;
+          W.ge[lane] = 0.5 * wt / k2;
+          W.j1[lane] = -(wr + 3.0 * wp) * a;
+        }
+      DEB_LANES_END
+
+      // ---- tails: pivot-free backward elimination l = L .. 3 (one lane per chain) ----
+      DEB_LANES_BEGIN
+        if (lane < nch) {
+          const int base = C.ch_base[lane], s = C.ch_stride[lane], L = C.ch_lmax[lane];
+          const double kc = W.kc[lane], kp = W.kap[lane];
+          // row L (truncation): diag = idg + kap + (L+1)/tau, lower = -kc
+          double e = idg + kp + (double)(L + 1) * invt0;
+          double ie = 1.0 / e;
+          int idx = base + L * s;
+          W.ie[idx] = ie;
+          W.g[idx] = kc * ie;                      // -W_{L,L-1}/e_L
+          double lower_next = -kc;                 // W_{l+1,l}
+          for (int l = L - 1; l >= 2; --l) {
+            idx -= s;
+            double up = kc * C.ch[l];              // W_{l,l+1}
+            double mm = up * ie;                   // uses 1/e_{l+1}
+            W.m[idx] = mm;
+            if (l >= 3) {
+              e = idg + kp - mm * lower_next;
+              ie = 1.0 / e;
+              W.ie[idx] = ie;
+              lower_next = -kc * C.cl[l];
+              W.g[idx] = -lower_next * ie;
+            } else {
+              W.ie[idx] = -mm * lower_next;        // Schur increment for head diagonal (l=2 row)
+            }
+          }
+        }
+      DEB_LANES_END
+
+      // ---- head matrix  W_h = I/(gamma dt) - J_h  (one lane per row) ----
+      DEB_LANES_BEGIN
+        if (lane < nh) {
+          const int ty = C.htype[lane], bin = C.hbin[lane];
+          double* row = W.lu + lane * LDH;
+          double chh = 0.0, cee = 0.0;
+          switch (ty) {
+            case R_ETA: cee = 1.0; break;
+            case R_DC: case R_DB: chh = -0.5; break;
+            case R_F0: case R_N0: chh = -2.0 / 3.0; break;
+            case R_F2: case R_N2: chh = 4.0 / 15.0; cee = 1.6; break;
+            case R_P0: chh = nb.dl[bin] / 6.0; break;
+            case R_P2: chh = -nb.dl[bin] / 15.0; cee = -0.4 * nb.dl[bin]; break;
+            case R_DQ: chh = -0.5 * bd.wq1.v; break;
+            default: break;
+          }
+          if (ty == R_AHP) { for (int cc = 0; cc < nh; ++cc) row[cc] = -W.j1[cc]; }
+          else { for (int cc = 0; cc < nh; ++cc) row[cc] = -(chh * W.gh[cc] + cee * W.ge[cc]); }
+          row[lane] += idg;
+          // local couplings; head positions: 0 eta,1 dc,2 tc,3 db,4 tb,5-7 F,8-10 G,11-13 N,14.. psi, then dq,tq,ahp
+          const double op = bd.opac.v, pbo = bd.pbo.v;
+          const int hF = 5, hG = 8, hN = 11, hP = 14, hQ = 14 + 3 * nq;
+          switch (ty) {
+            case R_DC: row[2] -= -1.0; break;
+            case R_TC: row[2] -= -H; break;
+            case R_DB: row[4] -= -1.0; break;
+            case R_TB: row[4] -= -H - pbo; row[3] -= k2 * bd.cs2.v; row[hF + 1] -= pbo; break;
+            case R_F0: row[hF + 1] -= -4.0 / 3.0; break;
+            case R_F1: row[hF] -= 0.25 * k2; row[hF + 2] -= -0.5 * k2; row[hF + 1] -= -op; row[4] -= op; break;
+            case R_F2: row[hF + 1] -= 8.0 / 15.0; row[hF + 2] -= -0.9 * op; row[hG] -= 0.1 * op; row[hG + 2] -= 0.1 * op; break;
+            case R_G0: row[hG + 1] -= -k; row[hG] -= -0.5 * op; row[hF + 2] -= 0.5 * op; row[hG + 2] -= 0.5 * op; break;
+            case R_G1: row[hG] -= k / 3.0; row[hG + 2] -= -2.0 * k / 3.0; row[hG + 1] -= -op; break;
+            case R_G2: row[hG + 1] -= 0.4 * k; row[hG + 2] -= -0.9 * op; row[hF + 2] -= 0.1 * op; row[hG] -= 0.1 * op; break;
+            case R_N0: row[hN + 1] -= -4.0 / 3.0; break;
+            case R_N1: row[hN] -= 0.25 * k2; row[hN + 2] -= -0.5 * k2; break;
+            case R_N2: row[hN + 1] -= 8.0 / 15.0; break;
+            case R_P0: row[hP + nq + bin] -= -k * bd.v[bin].v; break;
+            case R_P1: row[hP + bin] -= k * bd.v[bin].v / 3.0; row[hP + 2 * nq + bin] -= -2.0 * k * bd.v[bin].v / 3.0; break;
+            case R_P2: row[hP + nq + bin] -= 0.4 * k * bd.v[bin].v; break;
+            case R_DQ: row[hQ + 1] -= -bd.wq1.v - 9.0 * bd.wq1.v * (c.cs2de - bd.ca2.v) * H * H / k2;
+                       row[hQ] -= -3.0 * (c.cs2de - bd.wq.v) * H; break;
+            case R_TQ: row[hQ + 1] -= -(1.0 - 3.0 * c.cs2de) * H; row[hQ] -= c.cs2de * k2 / bd.wq1.v; break;
+            default: break;
+          }
+          // Schur complement of the chain tail on the l=2 diagonal
+          if (ty == R_F2 || ty == R_G2 || ty == R_N2 || ty == R_P2) {
+            int chain = ty == R_F2 ? 0 : (ty == R_G2 ? 1 : (ty == R_N2 ? 2 : 3 + bin));
+            row[lane] += W.ie[C.ch_base[chain] + 2 * C.ch_stride[chain]];
+          }
+        }
+      DEB_LANES_END
+    }
+
+    // ---- head LU with partial pivoting (rows stay in place; perm[j] = pivot row of step j) ----
+    {
+      DEB_REGS(int, pivoted, );
+      DEB_LANES_BEGIN
+        DEB_USE(pivoted);
+        pivoted = (lane < nh) ? 0 : 1;
+      DEB_LANES_END
+      for (int j = 0; j < nh; ++j) {
+        // pivot search: every lane scans column j (rows not yet pivoted)
+        int piv = -1; double best = -1.0;
+        for (int rr = 0; rr < nh; ++rr) {
+          int pv = DEB_SHFL(pivoted, rr);
+          double av = fabs(W.lu[rr * LDH + j]);
+          if (!pv && (piv < 0 || av > best)) { best = av; piv = rr; }
+        }
+        const double ipv = 1.0 / W.lu[piv * LDH + j];
+        DEB_LANES_BEGIN
+          DEB_USE(pivoted);
+          if (lane == piv) { pivoted = 1; W.perm[j] = piv; }
+          if (!pivoted) {
+            double* row = W.lu + lane * LDH;
+            const double* prow = W.lu + piv * LDH;
+            double lm = row[j] * ipv;
+            row[j] = lm;
+            for (int cc = j + 1; cc < nh; ++cc) row[cc] -= lm * prow[cc];
+          }
+        DEB_LANES_END
+      }
+    }
+
+    // ================= 8 stages =================
+    double errnorm2 = 0.0;
+#pragma unroll 1
+    for (int st = 1; st <= 8; ++st) {
+      if (st > 1) {
+        // ---- stage state u and evaluation time ----
+        const double ts = st == 2 ? t + RD_CT2 * dt : st == 3 ? t + RD_CT3 * dt : st == 4 ? t + RD_CT4 * dt
+                        : st == 5 ? t + RD_CT5 * dt : t + dt;
+        const double dtd = st == 2 ? dt * RD_D2 : st == 3 ? dt * RD_D3 : st == 4 ? dt * RD_D4 : st == 5 ? dt * RD_D5 : 0.0;
+        DEB_LANES_BEGIN
+          DEB_USE(ks);
+#pragma unroll
+          for (int j = 0; j < NE; ++j) {
+            int e = lane + 32 * j;
+            if (e < n) {
+              double uu;
+              switch (st) {
+                case 2: uu = W.y[e] + RD_A21 * ks[0][j]; break;
+                case 3: uu = W.y[e] + RD_A31 * ks[0][j] + RD_A32 * ks[1][j]; break;
+                case 4: uu = W.y[e] + RD_A41 * ks[0][j] + RD_A42 * ks[1][j] + RD_A43 * ks[2][j]; break;
+                case 5: uu = W.y[e] + RD_A51 * ks[0][j] + RD_A52 * ks[1][j] + RD_A53 * ks[2][j] + RD_A54 * ks[3][j]; break;
+                case 6: uu = W.y[e] + RD_A61 * ks[0][j] + RD_A62 * ks[1][j] + RD_A63 * ks[2][j] + RD_A64 * ks[3][j] + RD_A65 * ks[4][j]; break;
+                case 7: uu = W.u[e] + ks[5][j]; break;
+                default: uu = W.u[e] + ks[6][j]; break;
+              }
+              W.u[e] = uu;
+            }
+          }
+        DEB_LANES_END
+        // ---- f(ts, u) + dt d_i dT + sum_j C_ij/dt k_j  -> r ----
+        Bg<double> b;
+        compute_bg<double>(c, nb, nq, W.u[0], hint, b);
+        Metric<double> mt;
+        compute_metric<double>(P, c, nb, b, W.u, k, mt);
+        const double invts = 1.0 / ts;
+        DEB_LANE0_BEGIN
+          // value halves only; the d/da halves written at factor time are not used by the stages
+          for (int ch = 0; ch < nch; ++ch) { W.kc[ch] = ch < 3 ? k : b.v[ch - 3] * k; W.kap[ch] = ch < 2 ? b.opac : 0.0; }
+        DEB_LANE0_END
+        DEB_LANES_BEGIN
+          DEB_USE(ks);
+#pragma unroll
+          for (int j = 0; j < NE; ++j) {
+            int e = lane + 32 * j;
+            if (e < n) {
+              double cc;
+              switch (st) {
+                case 2: cc = RD_C21 * ks[0][j]; break;
+                case 3: cc = RD_C31 * ks[0][j] + RD_C32 * ks[1][j]; break;
+                case 4: cc = RD_C41 * ks[0][j] + RD_C42 * ks[1][j] + RD_C43 * ks[2][j]; break;
+                case 5: cc = RD_C51 * ks[0][j] + RD_C52 * ks[1][j] + RD_C53 * ks[2][j] + RD_C54 * ks[3][j]; break;
+                case 6: cc = RD_C61 * ks[0][j] + RD_C62 * ks[1][j] + RD_C63 * ks[2][j] + RD_C64 * ks[3][j] + RD_C65 * ks[4][j]; break;
+                case 7: cc = RD_C71 * ks[0][j] + RD_C72 * ks[1][j] + RD_C73 * ks[2][j] + RD_C74 * ks[3][j] + RD_C75 * ks[4][j] + RD_C76 * ks[5][j]; break;
+                default: cc = RD_C81 * ks[0][j] + RD_C82 * ks[1][j] + RD_C83 * ks[2][j] + RD_C84 * ks[3][j] + RD_C85 * ks[4][j] + RD_C86 * ks[5][j] + RD_C87 * ks[6][j]; break;
+              }
+              W.r[e] = cc * invdt;
+            }
+          }
+#pragma unroll 1
+          for (int e = lane; e < n; e += 32) {
+            const int de = desc[e];
+            double f = rhs_row<double>(P, c, C, b, mt, W.kc, W.kap, W.u, e, de, k, invts);
+            if (dtd != 0.0 && (de & 0xff) == R_TRUNC) {
+              int L = C.ch_lmax[de >> 16];
+              f += dtd * ((double)(L + 1) * invt0 * invt0 * W.y[e]);
+            }
+            W.r[e] += f;
+          }
+        DEB_LANES_END
+      }
+
+      // ---- solve W x = r in place ----
+      const double x0 = W.r[0] / x0piv;
+      DEB_LANES_BEGIN
+        for (int e = lane; e < n; e += 32) W.r[e] = (e == 0) ? x0 : W.r[e] + W.ja[e] * x0;
+      DEB_LANES_END
+      DEB_LANES_BEGIN
+        if (lane < nch) {          // backward sweep: b'_l = b_l - m_l b'_{l+1}, l = L-1 .. 2
+          const int base = C.ch_base[lane], s = C.ch_stride[lane], L = C.ch_lmax[lane];
+          int idx = base + L * s;
+          double bp = W.r[idx];
+          for (int l = L - 1; l >= 2; --l) { idx -= s; bp = W.r[idx] - W.m[idx] * bp; W.r[idx] = bp; }
+        }
+      DEB_LANES_END
+      // head: forward substitution (unit lower), then backward, rows in pivot order
+      DEB_LANES_BEGIN
+        DEB_USE(hb);
+        hb = lane < nh ? W.r[C.hidx[lane]] : 0.0;
+      DEB_LANES_END
+      {
+        DEB_REGS(int, done, );
+        DEB_LANES_BEGIN
+          DEB_USE(done);
+          done = 0;
+        DEB_LANES_END
+        for (int j = 0; j < nh; ++j) {
+          const int pr = W.perm[j];
+          const double yj = DEB_SHFL(hb, pr);
+          DEB_LANES_BEGIN
+            DEB_USE(hb); DEB_USE(done);
+            if (lane == pr) done = 1;
+            else if (!done && lane < nh) hb -= W.lu[lane * LDH + j] * yj;
+          DEB_LANES_END
+        }
+        for (int j = nh - 1; j >= 0; --j) {
+          const int pr = W.perm[j];
+          const double xj = DEB_SHFL(hb, pr) / W.lu[pr * LDH + j];
+          DEB_LANES_BEGIN
+            DEB_USE(hb); DEB_USE(done);
+            if (lane == pr) { done = 0; W.r[C.hidx[j]] = xj; }
+            else if (done && lane < nh) hb -= W.lu[lane * LDH + j] * xj;
+          DEB_LANES_END
+        }
+      }
+      DEB_LANES_BEGIN
+        if (lane < nch) {          // forward sweep: x_l = b'_l/e_l + g_l x_{l-1}, l = 3 .. L
+          const int base = C.ch_base[lane], s = C.ch_stride[lane], L = C.ch_lmax[lane];
+          int idx = base + 2 * s;
+          double x = W.r[idx];
+          for (int l = 3; l <= L; ++l) { idx += s; x = W.r[idx] * W.ie[idx] + W.g[idx] * x; W.r[idx] = x; }
+        }
+      DEB_LANES_END
+      // ---- keep k_st in registers ----
+      if (st < 8) {
+        DEB_LANES_BEGIN
+          DEB_USE(ks);
+#pragma unroll
+          for (int j = 0; j < NE; ++j) {
+            int e = lane + 32 * j;
+            double kv = e < n ? W.r[e] : 0.0;
+            switch (st) {
+              case 1: ks[0][j] = kv; break;
+              case 2: ks[1][j] = kv; break;
+              case 3: ks[2][j] = kv; break;
+              case 4: ks[3][j] = kv; break;
+              case 5: ks[4][j] = kv; break;
+              case 6: ks[5][j] = kv; break;
+              default: ks[6][j] = kv; break;
+            }
+          }
+        DEB_LANES_END
+      }
+    }
+    // y1 = u + k8 -> u ; err = k8 = r
+    DEB_LANES_BEGIN
+      DEB_USE(nanflag);
+      nanflag = 0;
+      for (int e = lane; e < n; e += 32) { double y1v = W.u[e] + W.r[e]; W.u[e] = y1v; nanflag |= (y1v != y1v); }
+    DEB_LANES_END
+
+    if (P.mode == 1) {
+      DEB_LANES_BEGIN
+        for (int e = lane; e < n; e += 32) { P.dbg_y1[(size_t)mode * n + e] = W.u[e]; P.dbg_err[(size_t)mode * n + e] = W.r[e]; }
+      DEB_LANES_END
+      return;
+    }
+
+    // ================= error norm, PID controller (diffrax semantics) =================
+    {
+      const int idx6[6] = {0, 2, 3, 5, 6, 7};
+      const double w6[6] = {1.0, k2, 1.0, 1.0, 1.0 / k2, 1.0};
+      const bool anynan = DEB_ANY(nanflag) != 0;
+      for (int q = 0; q < 6; ++q) {
+        int e = idx6[q];
+        double y0v = W.y[e], y1v = anynan ? y0v : W.u[e], ev = W.r[e];
+        if (ev != ev) ev = INFINITY;
+        double sc = ev / (P.atol + fmax(fabs(y0v), fabs(y1v)) * P.rtol) * w6[q];
+        errnorm2 += sc * sc;
+      }
+    }
+    const double E = sqrt(errnorm2 / 6.0);
+    const bool keep = (P.mode == 3) ? (DEB_LDG(P.rp_keep + (size_t)mode * P.rp_stride + nsteps) != 0) : (E < 1.0);
+    double inv = 1.0 / E;
+    double f1 = P.c1 != 0.0 ? pow(inv, P.c1) : 1.0;
+    double f2 = P.c2 != 0.0 ? pow(inv_prev, P.c2) : 1.0;
+    double f3 = P.c3 != 0.0 ? pow(inv_pprev, P.c3) : 1.0;
+    double fac = fmin(fmax(P.safety * f1 * f2 * f3, keep ? 1.0 : P.factormin), P.factormax);
+    if (!(fac == fac)) fac = NAN;
+    const double dtn = dt * fac;
+#ifdef DEB_CPU_EMU_TRACE
+    fprintf(stderr, "TRACE %d %d %.17g %.17g %.17g %d\n", mode, nsteps, t, dt, E, (int)keep);
+#endif
+    if (inv == 0.0 || isinf(inv)) inv = 1.0;
+    ++nsteps;
+    if (keep) {
+      ++nacc;
+      // SaveAt(ts): linear interpolation inside the accepted step
+      while (save_idx < P.nout && DEB_LDG(tout + save_idx) <= tnext) {
+        const double tt = DEB_LDG(tout + save_idx);
+        const double coeff = (tnext == t) ? 0.0 : (tt - t) / (tnext - t);
+        const size_t obase = ((size_t)mode * P.nout + save_idx);
+        if (P.return_full) {
+          DEB_LANES_BEGIN
+            for (int e = lane; e < n; e += 32) P.y_out[obase * n + e] = W.y[e] + coeff * (W.u[e] - W.y[e]);
+          DEB_LANES_END
+        } else {
+          DEB_LANES_BEGIN
+            for (int e = lane; e < n; e += 32) W.r[e] = W.y[e] + coeff * (W.u[e] - W.y[e]);
+          DEB_LANES_END
+          DEB_LANE0_BEGIN
+            double o20[20];
+            convert_outputs(P, c, nb, W.r, k, o20);
+            for (int q = 0; q < 20; ++q) P.y_out[obase * 20 + q] = o20[q];
+            if (P.pk_out && P.power_idx >= 0) {
+              double yv = o20[P.power_idx];
+              P.pk_out[obase] = 2.0 * 9.869604401089358 * c.As * pow(k / c.kp, c.ns - 1.0) * pow(k, -3.0) * yv * yv;
+            }
+          DEB_LANE0_END
+        }
+        ++save_idx;
+      }
+      DEB_LANES_BEGIN
+        for (int e = lane; e < n; e += 32) W.y[e] = W.u[e];
+      DEB_LANES_END
+      inv_pprev = inv_prev; inv_prev = inv;
+      t = fmin(tnext, t1);
+    }
+    double tn = t + dtn;
+    if (tn > t1 - 1e-10) tn = keep ? t1 : t + 0.5 * (t1 - t);
+    tnext = tn;
+    if (!(tnext == tnext) || isinf(tnext)) status = 2;
+  }
+  if (status == 0 && t < t1) status = 1;
+  DEB_LANE0_BEGIN
+    P.status[mode] = status; P.nsteps[mode] = nsteps;
+    if (P.naccept) P.naccept[mode] = nacc;
+  DEB_LANE0_END
+}
+
+}  // namespace deb

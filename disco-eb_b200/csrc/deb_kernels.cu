@@ -1,0 +1,316 @@
+// deb_kernels.cu -- sm_100a kernels and the C-ABI of include/discoeb_b200.h.
+//
+// Launch geometry: one warp integrates one (cosmology, k) mode from start time to the last output
+// (prologue, adaptive Rodas5 loop, output sampling and conversion fused in one kernel).  A CTA is a
+// single warp, so up to 8 modes are resident per SM (bounded by the 255-register budget that holds
+// the 7 stage vectors, and by ~19 KB of shared-memory workspace per mode at n=265).  Warps pull
+// modes from a global ticket counter, largest k first (cost grows steeply with k), so SMs that
+// finish early keep working: a persistent grid sized to the device, not to the batch.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <vector>
+#include "../../include/discoeb_b200.h"
+#include "deb_core.cuh"
+#include "deb_host.inl"
+
+using namespace deb;
+
+#define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
+  fprintf(stderr, "[discoeb_b200] CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return DEB_E_CUDA; } } while (0)
+
+// tau_out[c, j] = tau_of_a_spline(aexp_out[j])   (perturbations.py:975)
+__global__ void k_tau_out(Problem P, double* tau_out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.ncosmo * P.nout) return;
+  int c = i / P.nout, j = i - c * P.nout;
+  Spl s = get_spline(P, c, T_TAU_OF_A);
+  tau_out[i] = spl_eval(s, P.aexp_out[j]);
+}
+
+static __host__ __device__ size_t cta_smem_bytes(int np) {
+  size_t b = sizeof(CtaConst);
+  b = (b + 15) & ~(size_t)15;
+  b += (size_t)np * sizeof(int);
+  b = (b + 15) & ~(size_t)15;
+  b += warp_ws_doubles(np) * sizeof(double);
+  return b;
+}
+
+template <int NE>
+__global__ void __launch_bounds__(32, 1) k_evolve(const __grid_constant__ Problem P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  CtaConst* C = reinterpret_cast<CtaConst*>(smem_raw);
+  size_t off = (sizeof(CtaConst) + 15) & ~(size_t)15;
+  int* desc = reinterpret_cast<int*>(smem_raw + off);
+  off = (off + (size_t)P.np * sizeof(int) + 15) & ~(size_t)15;
+  double* wsb = reinterpret_cast<double*>(smem_raw + off);
+  const int lane = threadIdx.x & 31;
+  init_cta_const(P, *C, desc, lane, 32);
+  __syncwarp();
+  WarpWs W;
+  carve(W, wsb, P.np);
+  const int total = P.ncosmo * P.nk;
+  for (;;) {
+    unsigned int tk = 0;
+    if (lane == 0) tk = atomicAdd(P.ticket, 1u);
+    tk = __shfl_sync(0xffffffffu, tk, 0);
+    if (tk >= (unsigned int)total) break;
+    // largest k first, cosmologies interleaved
+    const int kd = tk / P.ncosmo, cs = tk - kd * P.ncosmo;
+    const int mode = cs * P.nk + (P.nk - 1 - kd);
+    integrate_mode<NE>(P, *C, W, mode, lane);
+    __syncwarp();
+  }
+}
+
+typedef void (*evolve_kernel_t)(const Problem);
+static evolve_kernel_t pick_kernel(int n) {
+  int ne = (n + 31) / 32;
+  if (ne <= 3) return k_evolve<3>;
+  if (ne <= 4) return k_evolve<4>;
+  if (ne <= 6) return k_evolve<6>;
+  if (ne <= 9) return k_evolve<9>;
+  if (ne <= 12) return k_evolve<12>;
+  return nullptr;
+}
+
+static int launch_evolve(const Problem& P, cudaStream_t st) {
+  evolve_kernel_t kern = pick_kernel(P.n);
+  if (!kern) return DEB_E_UNSUPPORTED;
+  size_t smem = cta_smem_bytes(P.np);
+  CUDA_TRY(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, nsm = 0, occ = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)kern, 32, smem));
+  if (occ < 1) return DEB_E_UNSUPPORTED;
+  long total = (long)P.ncosmo * P.nk;
+  long grid = (long)nsm * occ;
+  if (grid > total) grid = total;
+  CUDA_TRY(cudaMemsetAsync(P.ticket, 0, sizeof(unsigned int), st));
+  kern<<<(unsigned)grid, 32, smem, st>>>(P);
+  CUDA_TRY(cudaGetLastError());
+  return DEB_OK;
+}
+
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  int alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 8) == cudaSuccess ? 0 : -1; }
+  template <class T> T* as() { return (T*)p; }
+};
+
+extern "C" {
+
+int32_t deb_nvar(const deb_dims* d) { return d ? deb_nvar_impl(d) : 0; }
+size_t deb_table_len(const deb_dims* d) { return d ? 3 * (size_t)(5 * d->nth + 2 * d->nnu) : 0; }
+size_t deb_workspace_bytes(const deb_dims* d) { (void)d; return 256; }
+const char* deb_strerror(int code) { return deb_strerror_impl(code); }
+int32_t deb_abi_version(void) { return DEB_ABI_VERSION; }
+int32_t deb_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
+
+int deb_evolve_f64(const deb_dims* dims, const deb_ctrl* ctrl, const double* scalars, const double* tables,
+                   const double* kmodes, const double* aexp_out, double* y_out, double* pk_out, double* tau_out,
+                   int32_t* status, int32_t* nsteps, int32_t* naccept, void* workspace, size_t workspace_bytes,
+                   void* stream) {
+  Problem P;
+  int rc = fill_problem(dims, ctrl, &P);
+  if (rc) return rc;
+  if (!scalars || !tables || !kmodes || !aexp_out || !y_out || !tau_out || !status || !nsteps || !workspace) return DEB_E_ARG;
+  if (workspace_bytes < deb_workspace_bytes(dims)) return DEB_E_WORKSPACE;
+  if (dims->power_idx >= 0 && !pk_out) return DEB_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  P.scalars = scalars; P.tables = tables; P.kmodes = kmodes; P.aexp_out = aexp_out;
+  P.y_out = y_out; P.pk_out = dims->power_idx >= 0 ? pk_out : nullptr; P.tau_out = tau_out;
+  P.status = status; P.nsteps = nsteps; P.naccept = naccept;
+  P.ticket = (unsigned int*)workspace;
+  P.mode = 0;
+  int nt = P.ncosmo * P.nout;
+  k_tau_out<<<(nt + 127) / 128, 128, 0, st>>>(P, tau_out);
+  CUDA_TRY(cudaGetLastError());
+  return launch_evolve(P, st);
+}
+
+// ---- host-pointer conveniences -------------------------------------------------------------
+
+int deb_evolve_host_f64(const deb_dims* dims, const deb_ctrl* ctrl, const double* scalars, const double* tables,
+                        const double* kmodes, const double* aexp_out, double* y_out, double* pk_out, double* tau_out,
+                        int32_t* status, int32_t* nsteps, int32_t* naccept, int32_t device, float* kernel_ms) {
+  Problem P0;
+  int rc = fill_problem(dims, ctrl, &P0);
+  if (rc) return rc;
+  if (deb_device_count() < 1) return DEB_E_NODEVICE;
+  CUDA_TRY(cudaSetDevice(device));
+  const size_t nc = dims->ncosmo, nk = dims->nk, nout = dims->nout;
+  const size_t nf = dims->return_full ? (size_t)P0.n : 20;
+  const size_t tl = deb_table_len(dims);
+  const size_t nkm = dims->k_per_cosmo ? nc * nk : nk;
+  const bool pk = dims->power_idx >= 0 && pk_out;
+  DevBuf d_sc, d_tb, d_k, d_a, d_y, d_pk, d_tau, d_st, d_ns, d_na, d_ws;
+  if (d_sc.alloc(nc * DEB_NSCAL * 8) || d_tb.alloc(nc * tl * 8) || d_k.alloc(nkm * 8) || d_a.alloc(nout * 8) ||
+      d_y.alloc(nc * nk * nout * nf * 8) || d_pk.alloc(pk ? nc * nk * nout * 8 : 8) || d_tau.alloc(nc * nout * 8) ||
+      d_st.alloc(nc * nk * 4) || d_ns.alloc(nc * nk * 4) || d_na.alloc(nc * nk * 4) || d_ws.alloc(256))
+    return DEB_E_CUDA;
+  cudaStream_t st;
+  CUDA_TRY(cudaStreamCreate(&st));
+  CUDA_TRY(cudaMemcpyAsync(d_sc.p, scalars, nc * DEB_NSCAL * 8, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(d_tb.p, tables, nc * tl * 8, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(d_k.p, kmodes, nkm * 8, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(d_a.p, aexp_out, nout * 8, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemsetAsync(d_y.p, 0, nc * nk * nout * nf * 8, st));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  CUDA_TRY(cudaEventRecord(e0, st));
+  deb_dims d2 = *dims;
+  if (!pk) d2.power_idx = -1;
+  rc = deb_evolve_f64(&d2, ctrl, d_sc.as<double>(), d_tb.as<double>(), d_k.as<double>(), d_a.as<double>(),
+                      d_y.as<double>(), d_pk.as<double>(), d_tau.as<double>(), d_st.as<int32_t>(), d_ns.as<int32_t>(),
+                      d_na.as<int32_t>(), d_ws.p, 256, (void*)st);
+  if (rc == DEB_OK) {
+    CUDA_TRY(cudaEventRecord(e1, st));
+    CUDA_TRY(cudaMemcpyAsync(y_out, d_y.p, nc * nk * nout * nf * 8, cudaMemcpyDeviceToHost, st));
+    if (pk) CUDA_TRY(cudaMemcpyAsync(pk_out, d_pk.p, nc * nk * nout * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(tau_out, d_tau.p, nc * nout * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(status, d_st.p, nc * nk * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(nsteps, d_ns.p, nc * nk * 4, cudaMemcpyDeviceToHost, st));
+    if (naccept) CUDA_TRY(cudaMemcpyAsync(naccept, d_na.p, nc * nk * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (kernel_ms) CUDA_TRY(cudaEventElapsedTime(kernel_ms, e0, e1));
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaStreamDestroy(st);
+  return rc;
+}
+
+static int debug_common(const deb_dims* dims, const deb_ctrl* ctrl, const double* scalars, const double* tables,
+                        const double* kmodes, const double* aexp_out, int32_t device, int mode, size_t nper,
+                        const double* in_t0, const double* in_t1, const double* in_y0, double* out_a, double* out_b,
+                        const double* rp_tnext, const int32_t* rp_keep, const int32_t* rp_n, int rp_stride,
+                        double* y_out, int32_t* nsteps_out) {
+  Problem P;
+  int rc = fill_problem(dims, ctrl, &P);
+  if (rc) return rc;
+  if (deb_device_count() < 1) return DEB_E_NODEVICE;
+  CUDA_TRY(cudaSetDevice(device));
+  const size_t nc = dims->ncosmo, nk = dims->nk, nout = dims->nout, total = nc * nk, n = P.n;
+  const size_t tl = deb_table_len(dims);
+  const size_t nkm = dims->k_per_cosmo ? nc * nk : nk;
+  const size_t nf = dims->return_full ? n : 20;
+  DevBuf d_sc, d_tb, d_k, d_a, d_tau, d_st, d_ns, d_ws, d_t0, d_t1, d_y0, d_oa, d_ob, d_rt, d_rk, d_rn, d_y;
+  if (d_sc.alloc(nc * DEB_NSCAL * 8) || d_tb.alloc(nc * tl * 8) || d_k.alloc(nkm * 8) || d_a.alloc(nout * 8) ||
+      d_tau.alloc(nc * nout * 8) || d_st.alloc(total * 4) || d_ns.alloc(total * 4) || d_ws.alloc(256) ||
+      d_t0.alloc(total * 8) || d_t1.alloc(total * 8) || d_y0.alloc(total * n * 8) || d_oa.alloc(total * nper * 8) ||
+      d_ob.alloc(total * n * 8) || d_rt.alloc(total * (size_t)rp_stride * 8 + 8) || d_rk.alloc(total * (size_t)rp_stride * 4 + 8) ||
+      d_rn.alloc(total * 4) || d_y.alloc(total * nout * nf * 8))
+    return DEB_E_CUDA;
+  CUDA_TRY(cudaMemcpy(d_sc.p, scalars, nc * DEB_NSCAL * 8, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(d_tb.p, tables, nc * tl * 8, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(d_k.p, kmodes, nkm * 8, cudaMemcpyHostToDevice));
+  P.scalars = d_sc.as<double>(); P.tables = d_tb.as<double>(); P.kmodes = d_k.as<double>();
+  P.tau_out = d_tau.as<double>(); P.status = d_st.as<int>(); P.nsteps = d_ns.as<int>(); P.naccept = nullptr;
+  P.ticket = (unsigned int*)d_ws.p; P.mode = mode; P.y_out = d_y.as<double>();
+  if (aexp_out) {
+    CUDA_TRY(cudaMemcpy(d_a.p, aexp_out, nout * 8, cudaMemcpyHostToDevice));
+    P.aexp_out = d_a.as<double>();
+    int nt = P.ncosmo * P.nout;
+    k_tau_out<<<(nt + 127) / 128, 128>>>(P, d_tau.as<double>());
+    CUDA_TRY(cudaGetLastError());
+  } else {
+    std::vector<double> ones(nc * nout, 1.0);
+    CUDA_TRY(cudaMemcpy(d_tau.p, ones.data(), nc * nout * 8, cudaMemcpyHostToDevice));
+  }
+  if (mode == 1) {
+    CUDA_TRY(cudaMemcpy(d_t0.p, in_t0, total * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_t1.p, in_t1, total * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_y0.p, in_y0, total * n * 8, cudaMemcpyHostToDevice));
+    P.dbg_t0 = d_t0.as<double>(); P.dbg_t1 = d_t1.as<double>(); P.dbg_y0 = d_y0.as<double>();
+    P.dbg_y1 = d_oa.as<double>(); P.dbg_err = d_ob.as<double>();
+  } else if (mode == 2) {
+    P.dbg_tau_start = d_oa.as<double>(); P.dbg_ics = d_ob.as<double>();
+  } else if (mode == 3) {
+    CUDA_TRY(cudaMemcpy(d_rt.p, rp_tnext, total * (size_t)rp_stride * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_rk.p, rp_keep, total * (size_t)rp_stride * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_rn.p, rp_n, total * 4, cudaMemcpyHostToDevice));
+    P.rp_tnext = d_rt.as<double>(); P.rp_keep = d_rk.as<int>(); P.rp_n = d_rn.as<int>(); P.rp_stride = rp_stride;
+  }
+  rc = launch_evolve(P, 0);
+  if (rc) return rc;
+  CUDA_TRY(cudaDeviceSynchronize());
+  if (mode == 1 || mode == 2) {
+    CUDA_TRY(cudaMemcpy(out_a, d_oa.p, total * nper * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(out_b, d_ob.p, total * n * 8, cudaMemcpyDeviceToHost));
+  } else {
+    CUDA_TRY(cudaMemcpy(y_out, d_y.p, total * nout * nf * 8, cudaMemcpyDeviceToHost));
+    if (nsteps_out) CUDA_TRY(cudaMemcpy(nsteps_out, d_ns.p, total * 4, cudaMemcpyDeviceToHost));
+  }
+  return DEB_OK;
+}
+
+int deb_debug_step_host_f64(const deb_dims* dims, const double* scalars, const double* tables, const double* kmodes,
+                            const double* t0, const double* t1, const double* y0, double* y1, double* yerr,
+                            int32_t device) {
+  deb_ctrl ctrl = {1e-4, 1e-4, 0.25, 0.8, 0.0, 20.0, 0.3, 0.9};
+  deb_dims d = *dims;
+  d.nout = 1;
+  return debug_common(&d, &ctrl, scalars, tables, kmodes, nullptr, device, 1, (size_t)deb_nvar(&d), t0, t1, y0, y1, yerr,
+                      nullptr, nullptr, nullptr, 0, nullptr, nullptr);
+}
+
+int deb_debug_ics_host_f64(const deb_dims* dims, const double* scalars, const double* tables, const double* kmodes,
+                           const double* aexp_out, double* tau_start, double* y0, int32_t device) {
+  deb_ctrl ctrl = {1e-4, 1e-4, 0.25, 0.8, 0.0, 20.0, 0.3, 0.9};
+  return debug_common(dims, &ctrl, scalars, tables, kmodes, aexp_out, device, 2, 1, nullptr, nullptr, nullptr, tau_start, y0,
+                      nullptr, nullptr, nullptr, 0, nullptr, nullptr);
+}
+
+int deb_debug_replay_host_f64(const deb_dims* dims, const deb_ctrl* ctrl, const double* scalars, const double* tables,
+                              const double* kmodes, const double* aexp_out, const double* rp_tnext,
+                              const int32_t* rp_keep, const int32_t* rp_n, int32_t rp_stride, double* y_out,
+                              int32_t* nsteps, int32_t device) {
+  return debug_common(dims, ctrl, scalars, tables, kmodes, aexp_out, device, 3, 1, nullptr, nullptr, nullptr, nullptr, nullptr,
+                      rp_tnext, rp_keep, rp_n, rp_stride, y_out, nsteps);
+}
+
+// ---- FP64 FMA peak probe (roofline denominator) ---------------------------------------------
+__global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double seed) {
+  double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+int deb_fp64_peak_tflops(int32_t device, double* tflops, float* sm_clock_mhz) {
+  if (deb_device_count() < 1) return DEB_E_NODEVICE;
+  CUDA_TRY(cudaSetDevice(device));
+  int nsm = 0, khz = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
+  CUDA_TRY(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device));
+  const int blocks = nsm * 8, threads = 256, iters = 1 << 16;
+  DevBuf buf;
+  if (buf.alloc((size_t)blocks * threads * 8)) return DEB_E_CUDA;
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    CUDA_TRY(cudaEventRecord(e0));
+    k_dfma_peak<<<blocks, threads>>>(buf.as<double>(), iters, 1.0);
+    CUDA_TRY(cudaEventRecord(e1));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  double flops = (double)blocks * threads * 8.0 * 2.0 * iters;
+  if (tflops) *tflops = flops / (best * 1e-3) / 1e12;
+  if (sm_clock_mhz) *sm_clock_mhz = khz / 1000.0f;
+  return DEB_OK;
+}
+
+}  // extern "C"

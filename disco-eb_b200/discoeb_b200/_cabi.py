@@ -1,0 +1,173 @@
+"""ctypes binding of the C-ABI declared in ``include/discoeb_b200.h``.
+
+The library is built in-tree by ``__graft_entry__.build()`` (``disco-eb_b200/csrc/Makefile``) as
+``disco-eb_b200/discoeb_b200/libdiscoeb_b200.so``.  There is NO fallback: if the shared library
+or a CUDA device is missing, loading/calling raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdiscoeb_b200.so")
+
+
+class DebDims(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "ncosmo", "nk", "nout", "ntan", "lmaxg", "lmaxgp", "lmaxr", "lmaxnu", "nqmax", "nth", "nnu",
+        "max_steps", "return_full", "k_per_cosmo", "power_idx", "reserved")]
+
+
+class DebCtrl(C.Structure):
+    _fields_ = [(n, C.c_double) for n in (
+        "rtol", "atol", "pcoeff", "icoeff", "dcoeff", "factormax", "factormin", "safety")]
+
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+
+
+def _d(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return None if a is None else a.ctypes.data_as(_ip)
+
+
+class DiscoEBError(RuntimeError):
+    pass
+
+
+class Library:
+    """One loaded shared library exposing the ``deb_*`` (or, in the CPU test-suite, ``emu_*``) symbols."""
+
+    def __init__(self, path: str = LIB_PATH, prefix: str = "deb_"):
+        if not os.path.exists(path):
+            raise DiscoEBError(
+                f"{path} not found: build the CUDA library first (python -c 'import __graft_entry__ as g; g.build()'). "
+                "discoeb_b200 has no CPU fallback.")
+        self.path, self.prefix = path, prefix
+        self.lib = C.CDLL(path)
+        f = getattr(self.lib, prefix + "evolve_host_f64")
+        base = [C.POINTER(DebDims), C.POINTER(DebCtrl), _dp, _dp, _dp, _dp, _dp, _dp, _dp, _ip, _ip, _ip]
+        f.argtypes = base + ([C.c_int32, C.POINTER(C.c_float)] if prefix == "deb_" else [])
+        f.restype = C.c_int
+        self._evolve_host = f
+        g = getattr(self.lib, prefix + "debug_step_host_f64")
+        g.argtypes = [C.POINTER(DebDims), _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp] + ([C.c_int32] if prefix == "deb_" else [])
+        g.restype = C.c_int
+        self._debug_step = g
+        h = getattr(self.lib, prefix + "debug_ics_host_f64")
+        h.argtypes = [C.POINTER(DebDims), _dp, _dp, _dp, _dp, _dp, _dp] + ([C.c_int32] if prefix == "deb_" else [])
+        h.restype = C.c_int
+        self._debug_ics = h
+        if prefix == "deb_":
+            self.lib.deb_strerror.restype = C.c_char_p
+            self.lib.deb_strerror.argtypes = [C.c_int]
+            self.lib.deb_workspace_bytes.restype = C.c_size_t
+            self.lib.deb_workspace_bytes.argtypes = [C.POINTER(DebDims)]
+            self.lib.deb_table_len.restype = C.c_size_t
+            self.lib.deb_table_len.argtypes = [C.POINTER(DebDims)]
+            self.lib.deb_nvar.restype = C.c_int32
+            self.lib.deb_nvar.argtypes = [C.POINTER(DebDims)]
+            self.lib.deb_device_count.restype = C.c_int32
+            self.lib.deb_abi_version.restype = C.c_int32
+            self.lib.deb_fp64_peak_tflops.restype = C.c_int
+            self.lib.deb_fp64_peak_tflops.argtypes = [C.c_int32, _dp, C.POINTER(C.c_float)]
+            self.lib.deb_evolve_f64.restype = C.c_int
+            self.lib.deb_evolve_f64.argtypes = [C.POINTER(DebDims), C.POINTER(DebCtrl)] + [C.c_void_p] * 10 + \
+                [C.c_void_p, C.c_size_t, C.c_void_p]
+
+    # ------------------------------------------------------------------------------------------
+    def strerror(self, code: int) -> str:
+        if self.prefix == "deb_":
+            return self.lib.deb_strerror(code).decode()
+        return f"error {code}"
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise DiscoEBError(f"{what} failed: {self.strerror(rc)} (code {rc})")
+
+    @staticmethod
+    def nvar(lmaxg, lmaxgp, lmaxr, lmaxnu, nqmax):
+        return 7 + (lmaxg + 1) + (lmaxgp + 1) + (lmaxr + 1) + nqmax * (lmaxnu + 1) + 2
+
+    def evolve_host(self, dims: DebDims, ctrl: DebCtrl, scalars, tables, kmodes, aexp_out, device: int = 0,
+                    want_pk: bool = False):
+        """numpy in -> dict of numpy out (y, pk, tau_out, status, nsteps, naccept, kernel_ms)."""
+        nc, nk, nout = dims.ncosmo, dims.nk, dims.nout
+        nf = self.nvar(dims.lmaxg, dims.lmaxgp, dims.lmaxr, dims.lmaxnu, dims.nqmax) if dims.return_full else 20
+        scalars = np.ascontiguousarray(scalars, dtype=np.float64)
+        tables = np.ascontiguousarray(tables, dtype=np.float64)
+        kmodes = np.ascontiguousarray(kmodes, dtype=np.float64)
+        aexp_out = np.ascontiguousarray(aexp_out, dtype=np.float64)
+        y = np.zeros((nc, nk, nout, nf), dtype=np.float64)
+        pk = np.zeros((nc, nk, nout), dtype=np.float64) if want_pk else None
+        tau_out = np.zeros((nc, nout), dtype=np.float64)
+        status = np.zeros((nc, nk), dtype=np.int32)
+        nsteps = np.zeros((nc, nk), dtype=np.int32)
+        nacc = np.zeros((nc, nk), dtype=np.int32)
+        args = [C.byref(dims), C.byref(ctrl), _d(scalars), _d(tables), _d(kmodes), _d(aexp_out), _d(y), _d(pk),
+                _d(tau_out), _i(status), _i(nsteps), _i(nacc)]
+        kms = C.c_float(0.0)
+        if self.prefix == "deb_":
+            args += [C.c_int32(device), C.byref(kms)]
+        self._check(self._evolve_host(*args), "evolve_host_f64")
+        return dict(y=y, pk=pk, tau_out=tau_out, status=status, nsteps=nsteps, naccept=nacc, kernel_ms=kms.value)
+
+    def debug_step(self, dims: DebDims, scalars, tables, kmodes, t0, t1, y0, device: int = 0):
+        y0 = np.ascontiguousarray(y0, dtype=np.float64)
+        y1 = np.zeros_like(y0)
+        err = np.zeros_like(y0)
+        t0 = np.ascontiguousarray(t0, dtype=np.float64)
+        t1 = np.ascontiguousarray(t1, dtype=np.float64)
+        args = [C.byref(dims), _d(np.ascontiguousarray(scalars)), _d(np.ascontiguousarray(tables)),
+                _d(np.ascontiguousarray(kmodes, dtype=np.float64)), _d(t0), _d(t1), _d(y0), _d(y1), _d(err)]
+        if self.prefix == "deb_":
+            args.append(C.c_int32(device))
+        self._check(self._debug_step(*args), "debug_step_host_f64")
+        return y1, err
+
+    def debug_ics(self, dims: DebDims, scalars, tables, kmodes, aexp_out, device: int = 0):
+        n = self.nvar(dims.lmaxg, dims.lmaxgp, dims.lmaxr, dims.lmaxnu, dims.nqmax)
+        ts = np.zeros((dims.ncosmo, dims.nk), dtype=np.float64)
+        y0 = np.zeros((dims.ncosmo, dims.nk, n), dtype=np.float64)
+        args = [C.byref(dims), _d(np.ascontiguousarray(scalars)), _d(np.ascontiguousarray(tables)),
+                _d(np.ascontiguousarray(kmodes, dtype=np.float64)), _d(np.ascontiguousarray(aexp_out, dtype=np.float64)),
+                _d(ts), _d(y0)]
+        if self.prefix == "deb_":
+            args.append(C.c_int32(device))
+        self._check(self._debug_ics(*args), "debug_ics_host_f64")
+        return ts, y0
+
+    def fp64_peak_tflops(self, device: int = 0):
+        t = C.c_double(0.0)
+        mhz = C.c_float(0.0)
+        self._check(self.lib.deb_fp64_peak_tflops(device, C.byref(t), C.byref(mhz)), "fp64_peak_tflops")
+        return t.value, mhz.value
+
+
+_default = None
+
+
+def default_library() -> Library:
+    global _default
+    if _default is None:
+        _default = Library()
+    return _default
+
+
+def make_dims(*, ncosmo, nk, nout, lmaxg, lmaxgp, lmaxr, lmaxnu, nqmax, nth, nnu, max_steps, return_full=False,
+              k_per_cosmo=False, power_idx=-1) -> DebDims:
+    return DebDims(ncosmo=ncosmo, nk=nk, nout=nout, ntan=0, lmaxg=lmaxg, lmaxgp=lmaxgp, lmaxr=lmaxr, lmaxnu=lmaxnu,
+                   nqmax=nqmax, nth=nth, nnu=nnu, max_steps=max_steps, return_full=int(bool(return_full)),
+                   k_per_cosmo=int(bool(k_per_cosmo)), power_idx=power_idx, reserved=0)
+
+
+def make_ctrl(*, rtol, atol, pcoeff=0.25, icoeff=0.8, dcoeff=0.0, factormax=20.0, factormin=0.3, safety=0.9) -> DebCtrl:
+    return DebCtrl(rtol=rtol, atol=atol, pcoeff=pcoeff, icoeff=icoeff, dcoeff=dcoeff, factormax=factormax,
+                   factormin=factormin, safety=safety)

@@ -1,0 +1,146 @@
+"""Drop-in host API of the Einstein-Boltzmann hot path, backed by the sm_100a CUDA library.
+
+Mirrors the reference's keyword API on the ``param`` dict
+(``/root/reference/src/discoeb/perturbations.py``):
+
+* ``evolve_perturbations``          -> :926-997   returns ``(y, kmodes, param)``
+* ``evolve_perturbations_batched``  -> :1000-1061 returns ``(y, kmodes)``
+* ``get_power``                     -> :1101-1123
+
+Same argument names, defaults, return shapes, ``param`` side effects (:989-995) and failure
+behaviour (diffrax raises when ``max_steps`` is exhausted; so does this).  The arithmetic runs in
+``libdiscoeb_b200.so`` through the C-ABI of ``include/discoeb_b200.h``; there is no CPU path.
+
+Documented deviation: ``evolve_perturbations_batched`` integrates every mode with its own step
+sequence (the reference's batched solver shares one step size per batch, which changes results
+at O(rtol)).  ``batch_size`` only has to divide ``num_k`` as in the
+reference (:830).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _cabi
+from ._pack import pack_param, pack_params
+
+__all__ = ["evolve_perturbations", "evolve_perturbations_batched", "evolve_perturbations_multi", "get_power"]
+
+
+class MaxStepsReached(RuntimeError):
+    """Same condition diffrax reports as ``RESULTS.max_steps_reached``."""
+
+
+def _kgrid(kmin, kmax, num_k, dologk):
+    # jnp.geomspace / jnp.linspace (perturbations.py:967-970)
+    return np.geomspace(kmin, kmax, num_k) if dologk else np.linspace(kmin, kmax, num_k)
+
+
+def _check_status(status, nsteps, max_steps, throw):
+    if not throw:
+        return
+    bad = np.argwhere(status != 0)
+    if bad.size:
+        kinds = sorted(set(int(s) for s in status[status != 0]))
+        msg = (f"{bad.shape[0]} of {status.size} modes did not complete (status codes {kinds}; 1 = the maximum "
+               f"number of solver steps ({max_steps}) was reached, 2 = non-finite step). Try increasing max_steps.")
+        raise MaxStepsReached(msg)
+
+
+def _solve(params, kmodes, aexp_out, *, lmaxg, lmaxgp, lmaxr, lmaxnu, nqmax, rtol, atol, pcoeff, icoeff, dcoeff,
+           factormax, factormin, max_steps, return_full, device, power_idx=-1, lib=None, k_per_cosmo=False):
+    lib = lib or _cabi.default_library()
+    scalars, tables, nth, nnu = pack_params(params)
+    aexp_out = np.atleast_1d(np.asarray(aexp_out, dtype=np.float64))
+    if aexp_out.ndim != 1 or aexp_out.size < 1:
+        raise ValueError("aexp_out must be a scalar or 1-d array")
+    if np.any(np.diff(aexp_out) < 0):
+        raise ValueError("aexp_out must be ascending (diffrax SaveAt(ts) requires increasing ts)")
+    nk = kmodes.shape[-1]
+    dims = _cabi.make_dims(ncosmo=len(params), nk=nk, nout=aexp_out.size, lmaxg=lmaxg, lmaxgp=lmaxgp, lmaxr=lmaxr,
+                           lmaxnu=lmaxnu, nqmax=nqmax, nth=nth, nnu=nnu, max_steps=max_steps,
+                           return_full=return_full, k_per_cosmo=k_per_cosmo, power_idx=power_idx)
+    ctrl = _cabi.make_ctrl(rtol=rtol, atol=atol, pcoeff=pcoeff, icoeff=icoeff, dcoeff=dcoeff, factormax=factormax,
+                           factormin=factormin)
+    return lib.evolve_host(dims, ctrl, scalars, tables, kmodes, aexp_out, device=device, want_pk=power_idx >= 0)
+
+
+def evolve_perturbations(*, param, aexp_out, kmin: float, kmax: float, num_k: int,
+                         lmaxg: int = 11, lmaxgp: int = 11, lmaxr: int = 11, lmaxnu: int = 8,
+                         nqmax: int = 3, rtol: float = 1e-4, atol: float = 1e-4,
+                         pcoeff: float = 0.25, icoeff: float = 0.80, dcoeff: float = 0.0,
+                         factormax: float = 20.0, factormin: float = 0.3, max_steps: int = 2048,
+                         return_full: bool = False, dologk: bool = True, device: int = 0, throw: bool = True,
+                         return_info: bool = False):
+    """Evolve the linear perturbations of every k-mode in the synchronous gauge.
+
+    Arguments, defaults and return value follow ``perturbations.py:926-997``:
+    ``(y[num_k, nout, 20 | n], kmodes[num_k], param)`` with ``lmaxg, lmaxgp, lmaxr, lmaxnu, nqmax,
+    nout, tau_out`` written into ``param``.  Extra keyword-only knobs (not in the reference):
+    ``device`` (CUDA ordinal), ``throw`` (False: return instead of raising on exhausted
+    ``max_steps``) and ``return_info`` (append a dict with per-mode ``status``, ``nsteps``,
+    ``naccept`` and the kernel time).
+    """
+    kmodes = _kgrid(kmin, kmax, num_k, dologk)
+    out = _solve([param], kmodes, aexp_out, lmaxg=lmaxg, lmaxgp=lmaxgp, lmaxr=lmaxr, lmaxnu=lmaxnu, nqmax=nqmax,
+                 rtol=rtol, atol=atol, pcoeff=pcoeff, icoeff=icoeff, dcoeff=dcoeff, factormax=factormax,
+                 factormin=factormin, max_steps=max_steps, return_full=return_full, device=device)
+    _check_status(out["status"], out["nsteps"], max_steps, throw)
+    param["lmaxg"] = lmaxg
+    param["lmaxgp"] = lmaxgp
+    param["lmaxr"] = lmaxr
+    param["lmaxnu"] = lmaxnu
+    param["nqmax"] = nqmax
+    param["nout"] = out["tau_out"].shape[1]
+    param["tau_out"] = out["tau_out"][0]
+    if return_info:
+        info = dict(status=out["status"][0], nsteps=out["nsteps"][0], naccept=out["naccept"][0],
+                    kernel_ms=out["kernel_ms"])
+        return out["y"][0], kmodes, param, info
+    return out["y"][0], kmodes, param
+
+
+def evolve_perturbations_batched(*, param, aexp_out, kmin: float, kmax: float, num_k: int,
+                                 lmaxg: int = 11, lmaxgp: int = 11, lmaxr: int = 11, lmaxnu: int = 8,
+                                 nqmax: int = 3, rtol: float = 1e-4, atol: float = 1e-4,
+                                 pcoeff: float = 0.25, icoeff: float = 0.80, dcoeff: float = 0.0,
+                                 factormax: float = 20.0, factormin: float = 0.3, max_steps: int = 2048,
+                                 batch_size: int = 16, device: int = 0, throw: bool = True):
+    """API-compatible with ``perturbations.py:1000-1061``: returns ``(y, kmodes)``.  Per-mode
+    stepping (see module docstring)."""
+    if num_k % batch_size != 0:
+        raise ValueError("num_k must be divisible by batch_size (jnp.split at perturbations.py:830)")
+    kmodes = np.geomspace(kmin, kmax, num_k)
+    out = _solve([param], kmodes, aexp_out, lmaxg=lmaxg, lmaxgp=lmaxgp, lmaxr=lmaxr, lmaxnu=lmaxnu, nqmax=nqmax,
+                 rtol=rtol, atol=atol, pcoeff=pcoeff, icoeff=icoeff, dcoeff=dcoeff, factormax=factormax,
+                 factormin=factormin, max_steps=max_steps, return_full=False, device=device)
+    _check_status(out["status"], out["nsteps"], max_steps, throw)
+    param["nout"] = out["tau_out"].shape[1]
+    return out["y"][0], kmodes
+
+
+def evolve_perturbations_multi(*, params, aexp_out, kmin: float, kmax: float, num_k: int,
+                               lmaxg: int = 11, lmaxgp: int = 11, lmaxr: int = 11, lmaxnu: int = 8,
+                               nqmax: int = 3, rtol: float = 1e-4, atol: float = 1e-4,
+                               pcoeff: float = 0.25, icoeff: float = 0.80, dcoeff: float = 0.0,
+                               factormax: float = 20.0, factormin: float = 0.3, max_steps: int = 2048,
+                               return_full: bool = False, dologk: bool = True, device: int = 0, throw: bool = True,
+                               power_idx: int = -1):
+    """Batch of cosmologies in ONE launch (what ``jax.vmap(evolve_perturbations)`` over a stack of
+    ``param`` dicts does in the reference's emulator/MCMC use).  Returns
+    ``(y[ncosmo, num_k, nout, 20|n], kmodes, info)``; ``info['pk']`` holds ``get_power`` of field
+    ``power_idx`` when requested (fused epilogue)."""
+    kmodes = _kgrid(kmin, kmax, num_k, dologk)
+    out = _solve(list(params), kmodes, aexp_out, lmaxg=lmaxg, lmaxgp=lmaxgp, lmaxr=lmaxr, lmaxnu=lmaxnu, nqmax=nqmax,
+                 rtol=rtol, atol=atol, pcoeff=pcoeff, icoeff=icoeff, dcoeff=dcoeff, factormax=factormax,
+                 factormin=factormin, max_steps=max_steps, return_full=return_full, device=device,
+                 power_idx=power_idx)
+    _check_status(out["status"], out["nsteps"], max_steps, throw)
+    return out["y"], kmodes, out
+
+
+def get_power(*, k, y, idx: int, param):
+    """``2 pi^2 A_s (k/k_p)^(n_s-1) k^-3 y[..., idx]^2`` (perturbations.py:1101-1123); pure array
+    math on the solver output, kept on the host like in the reference."""
+    k = np.asarray(k)
+    y = np.asarray(y)
+    return 2 * np.pi ** 2 * param["A_s"] * (k / param["k_p"]) ** (param["n_s"] - 1) * k ** (-3) * y[..., idx] ** 2

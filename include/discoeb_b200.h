@@ -1,0 +1,147 @@
+/* discoeb_b200.h -- C-ABI of the B200-native Einstein-Boltzmann hot path.
+ *
+ * One entry point replaces the reference's per-mode solve
+ *   evolve_perturbations -> jax.vmap(evolve_one_mode) -> diffrax.diffeqsolve(Rodas5Transformed)
+ *   (/root/reference/src/discoeb/perturbations.py:926-997, :728-781;
+ *    ode_integrators_stiff.py:694-843)
+ * for every (cosmology, k) pair of a batch, including the prologue (start time :630-681,
+ * adiabatic initial conditions :526-627) and the epilogue (output conversion :374-523,
+ * get_power :1101-1123).  The reference has no FFI of its own: its seam is the Python
+ * keyword API on the `param` dict, mirrored by disco-eb_b200/discoeb_b200/perturbations.py,
+ * which binds this library with ctypes (INTEGRATION.md shows the jax.ffi binding).
+ *
+ * Conventions: plain pointers and sizes, float64 everywhere, row-major, no allocation and no
+ * synchronisation inside the *_f64 device entry (asynchronous on `stream`), re-entrant, no
+ * global state.  Return value 0 or a negative deb_status code; per-mode solver outcomes go to
+ * status[] (0 ok, 1 max_steps exhausted, 2 non-finite), mirroring diffrax's RESULTS.
+ */
+#ifndef DISCOEB_B200_H
+#define DISCOEB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DEB_ABI_VERSION 1
+#define DEB_NSCAL 24        /* doubles per cosmology in `scalars` */
+#define DEB_NSPLINE 7       /* splines per cosmology in `tables`  */
+#define DEB_NFIELD 20       /* output fields (perturbations.py:511-521) */
+
+/* index of each scalar inside one cosmology's DEB_NSCAL block */
+enum deb_scalar {
+  DEB_S_OMEGAM = 0, DEB_S_OMEGAB, DEB_S_OMEGADE, DEB_S_OMEGAK,
+  DEB_S_GRHOM, DEB_S_GRHOG, DEB_S_GRHOR, DEB_S_NEFF, DEB_S_NMNU, DEB_S_AMNU,
+  DEB_S_W0, DEB_S_WA, DEB_S_CS2DE, DEB_S_YHE, DEB_S_H0, DEB_S_TAUMIN,
+  DEB_S_AS, DEB_S_NS, DEB_S_KP
+};
+
+/* order of the splines inside one cosmology's table block.  Every spline is stored as
+ * x[n], y[n], S[n] (knots, values, second derivatives -- spline_interpolation.py:111-113).
+ * Splines 0,1 and 4,5,6 have nth knots, splines 2,3 have nnu knots; 0 and 1 must share
+ * their knots (they do in the reference, background.py:254-255).
+ * Block length = 3*(5*nth + 2*nnu) doubles. */
+enum deb_spline {
+  DEB_T_CS2A_OF_LOGA = 0, DEB_T_XE_OF_LOGA, DEB_T_LOGRHONU_OF_LOGA, DEB_T_LOGPNU_OF_LOGA,
+  DEB_T_A_OF_TAU, DEB_T_XE_OF_TAU, DEB_T_TAU_OF_A
+};
+
+typedef struct deb_dims {
+  int32_t ncosmo;        /* cosmologies in the batch                                  */
+  int32_t nk;            /* k-modes per cosmology                                     */
+  int32_t nout;          /* output times (ascending aexp_out)                         */
+  int32_t ntan;          /* forward tangents (0 in this ABI version)                  */
+  int32_t lmaxg, lmaxgp, lmaxr, lmaxnu;   /* hierarchy cut-offs, each >= 3            */
+  int32_t nqmax;         /* massive-neutrino momentum bins (3,4,5)                    */
+  int32_t nth, nnu;      /* knots of the thermo / neutrino splines                    */
+  int32_t max_steps;     /* attempted (accepted+rejected) step budget per mode        */
+  int32_t return_full;   /* 0: 20 output fields, 1: raw state vector (return_full)    */
+  int32_t k_per_cosmo;   /* 0: kmodes[nk] shared, 1: kmodes[ncosmo*nk]                */
+  int32_t power_idx;     /* >=0: also write P(k) of this field to pk_out (get_power)  */
+  int32_t reserved;
+} deb_dims;
+
+typedef struct deb_ctrl {
+  double rtol, atol;
+  double pcoeff, icoeff, dcoeff;
+  double factormax, factormin;
+  double safety;         /* diffrax default 0.9 */
+} deb_ctrl;
+
+enum deb_status {
+  DEB_OK = 0, DEB_E_ARG = -1, DEB_E_UNSUPPORTED = -2, DEB_E_WORKSPACE = -3,
+  DEB_E_CUDA = -4, DEB_E_NODEVICE = -5
+};
+
+/* number of state variables n = 7+(lg+1)+(lp+1)+(lr+1)+nq*(lnu+1)+2 (perturbations.py:739) */
+int32_t deb_nvar(const deb_dims* dims);
+/* doubles per cosmology in `tables` */
+size_t deb_table_len(const deb_dims* dims);
+/* bytes of device scratch deb_evolve_f64 needs */
+size_t deb_workspace_bytes(const deb_dims* dims);
+const char* deb_strerror(int code);
+int32_t deb_abi_version(void);
+int32_t deb_device_count(void);
+
+/* Device-pointer entry.  All array arguments are DEVICE pointers.
+ *   scalars   [ncosmo, DEB_NSCAL]
+ *   tables    [ncosmo, deb_table_len]
+ *   kmodes    [nk] or [ncosmo, nk]
+ *   aexp_out  [nout]                      ascending
+ *   y_out     [ncosmo, nk, nout, 20|n]
+ *   pk_out    [ncosmo, nk, nout] or NULL  (requires power_idx >= 0)
+ *   tau_out   [ncosmo, nout]              tau_of_a(aexp_out), returned like param['tau_out']
+ *   status    [ncosmo, nk]   nsteps [ncosmo, nk] attempted steps   naccept [ncosmo,nk] or NULL
+ *   stream    a cudaStream_t passed as void* (NULL = default stream)
+ */
+int deb_evolve_f64(const deb_dims* dims, const deb_ctrl* ctrl,
+                   const double* scalars, const double* tables, const double* kmodes,
+                   const double* aexp_out,
+                   double* y_out, double* pk_out, double* tau_out,
+                   int32_t* status, int32_t* nsteps, int32_t* naccept,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* Host-pointer entry: same arguments with HOST buffers; copies inputs to device `device`,
+ * runs deb_evolve_f64, copies results back and synchronises.  If kernel_ms is non-NULL it
+ * receives the device time of the solve kernel alone (CUDA events). */
+int deb_evolve_host_f64(const deb_dims* dims, const deb_ctrl* ctrl,
+                        const double* scalars, const double* tables, const double* kmodes,
+                        const double* aexp_out,
+                        double* y_out, double* pk_out, double* tau_out,
+                        int32_t* status, int32_t* nsteps, int32_t* naccept,
+                        int32_t device, float* kernel_ms);
+
+/* Debug/validation entry (host pointers): ONE attempted Rodas5 step per mode from a given
+ * state.  t0[nmodes], t1[nmodes], y0[nmodes, n] -> y1[nmodes, n], yerr[nmodes, n].
+ * Modes index (cosmology, k) like deb_evolve_f64.  Used by the parity tests to compare the
+ * structured solve with the oracle's dense LU stage by stage. */
+int deb_debug_step_host_f64(const deb_dims* dims, const double* scalars, const double* tables,
+                            const double* kmodes, const double* t0, const double* t1,
+                            const double* y0, double* y1, double* yerr, int32_t device);
+
+/* Debug/validation entry (host pointers): prologue only.  tau_start[ncosmo,nk] and the
+ * adiabatic initial state y0[ncosmo,nk,n]. */
+int deb_debug_ics_host_f64(const deb_dims* dims, const double* scalars, const double* tables,
+                           const double* kmodes, const double* aexp_out,
+                           double* tau_start, double* y0, int32_t device);
+
+/* Debug/validation entry (host pointers): integrate every mode along a PRESCRIBED step sequence
+ * (rp_tnext[mode, s] = end of attempted step s, rp_keep[mode, s] = accepted?, rp_n[mode] steps;
+ * rp_stride = row length) instead of the PID controller.  The adaptive step sequence of the
+ * reference algorithm is chaotic under round-off (DESIGN.md "Parity"), so the parity tests replay
+ * the oracle's own sequence to compare whole trajectories at round-off level. */
+int deb_debug_replay_host_f64(const deb_dims* dims, const deb_ctrl* ctrl, const double* scalars,
+                              const double* tables, const double* kmodes, const double* aexp_out,
+                              const double* rp_tnext, const int32_t* rp_keep, const int32_t* rp_n,
+                              int32_t rp_stride, double* y_out, int32_t* nsteps, int32_t device);
+
+/* Measures the FP64 FMA peak of `device` (dependent-free DFMA streams on every SM) and
+ * returns it in TFLOP/s; the roofline denominator bench.py reports against. */
+int deb_fp64_peak_tflops(int32_t device, double* tflops, float* sm_clock_mhz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DISCOEB_B200_H */

@@ -1,0 +1,116 @@
+// deb_emu.cpp -- TEST INFRASTRUCTURE: compiles the CUDA kernel source (deb_core.cuh) as plain C++
+// with the 32 lanes of a warp executed by loops, so that the CPU test-suite (-m "not gpu") can run
+// the very same per-mode integrator against the oracle.  It is built on demand by tests/conftest.py
+// into tests/emu/_build/, is never imported by the discoeb_b200 package and is not a fallback:
+// the product path fails loudly when the CUDA library is missing.
+#define DEB_CPU_EMU 1
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "../../include/discoeb_b200.h"
+#include "../../disco-eb_b200/csrc/deb_core.cuh"
+#include "../../disco-eb_b200/csrc/deb_host.inl"
+
+using namespace deb;
+
+static void tau_out_host(const Problem& P, double* tau_out) {
+  for (int c = 0; c < P.ncosmo; ++c) {
+    Spl s = get_spline(P, c, T_TAU_OF_A);
+    for (int j = 0; j < P.nout; ++j) tau_out[(size_t)c * P.nout + j] = spl_eval(s, P.aexp_out[j]);
+  }
+}
+
+template <int NE>
+static void run_all(const Problem& P) {
+  CtaConst C;
+  std::vector<int> desc(P.np);
+  for (int t = 0; t < 32; ++t) init_cta_const(P, C, desc.data(), t, 32);
+  std::vector<double> ws(warp_ws_doubles(P.np));
+  const int total = P.ncosmo * P.nk;
+#pragma omp parallel for schedule(dynamic, 1) firstprivate(ws)
+  for (int m = 0; m < total; ++m) {
+    WarpWs W;
+    carve(W, ws.data(), P.np);
+    integrate_mode<NE>(P, C, W, total - 1 - m);
+  }
+}
+
+static int dispatch(const Problem& P) {
+  int ne = (P.n + 31) / 32;
+  if (ne <= 3) run_all<3>(P);
+  else if (ne <= 4) run_all<4>(P);
+  else if (ne <= 6) run_all<6>(P);
+  else if (ne <= 9) run_all<9>(P);
+  else if (ne <= 12) run_all<12>(P);
+  else return DEB_E_UNSUPPORTED;
+  return DEB_OK;
+}
+
+extern "C" int emu_evolve_host_f64(const deb_dims* dims, const deb_ctrl* ctrl, const double* scalars,
+                                   const double* tables, const double* kmodes, const double* aexp_out,
+                                   double* y_out, double* pk_out, double* tau_out, int32_t* status,
+                                   int32_t* nsteps, int32_t* naccept) {
+  Problem P;
+  int rc = fill_problem(dims, ctrl, &P);
+  if (rc) return rc;
+  P.scalars = scalars; P.tables = tables; P.kmodes = kmodes; P.aexp_out = aexp_out;
+  P.y_out = y_out; P.pk_out = pk_out; P.status = status; P.nsteps = nsteps; P.naccept = naccept;
+  tau_out_host(P, tau_out);
+  P.tau_out = tau_out;
+  P.mode = 0;
+  return dispatch(P);
+}
+
+extern "C" int emu_debug_step_host_f64(const deb_dims* dims, const double* scalars, const double* tables,
+                                       const double* kmodes, const double* t0, const double* t1,
+                                       const double* y0, double* y1, double* yerr) {
+  Problem P;
+  deb_ctrl ctrl = {1e-4, 1e-4, 0.25, 0.8, 0.0, 20.0, 0.3, 0.9};
+  deb_dims d = *dims;
+  d.nout = 1;
+  int rc = fill_problem(&d, &ctrl, &P);
+  if (rc) return rc;
+  const int total = P.ncosmo * P.nk;
+  std::vector<double> tau_out(P.ncosmo, 1.0);
+  std::vector<int32_t> st(total), ns(total);
+  P.scalars = scalars; P.tables = tables; P.kmodes = kmodes; P.aexp_out = nullptr;
+  P.tau_out = tau_out.data(); P.status = st.data(); P.nsteps = ns.data(); P.naccept = nullptr;
+  P.dbg_t0 = t0; P.dbg_t1 = t1; P.dbg_y0 = y0; P.dbg_y1 = y1; P.dbg_err = yerr;
+  P.mode = 1;
+  return dispatch(P);
+}
+
+extern "C" int emu_debug_ics_host_f64(const deb_dims* dims, const double* scalars, const double* tables,
+                                      const double* kmodes, const double* aexp_out, double* tau_start, double* y0) {
+  Problem P;
+  deb_ctrl ctrl = {1e-4, 1e-4, 0.25, 0.8, 0.0, 20.0, 0.3, 0.9};
+  int rc = fill_problem(dims, &ctrl, &P);
+  if (rc) return rc;
+  const int total = P.ncosmo * P.nk;
+  std::vector<double> tau_out((size_t)P.ncosmo * P.nout);
+  std::vector<int32_t> st(total), ns(total);
+  P.scalars = scalars; P.tables = tables; P.kmodes = kmodes; P.aexp_out = aexp_out;
+  tau_out_host(P, tau_out.data());
+  P.tau_out = tau_out.data(); P.status = st.data(); P.nsteps = ns.data(); P.naccept = nullptr;
+  P.dbg_tau_start = tau_start; P.dbg_ics = y0;
+  P.mode = 2;
+  return dispatch(P);
+}
+
+extern "C" int emu_debug_replay_host_f64(const deb_dims* dims, const deb_ctrl* ctrl, const double* scalars,
+                                         const double* tables, const double* kmodes, const double* aexp_out,
+                                         const double* rp_tnext, const int32_t* rp_keep, const int32_t* rp_n,
+                                         int32_t rp_stride, double* y_out, int32_t* nsteps) {
+  Problem P;
+  int rc = fill_problem(dims, ctrl, &P);
+  if (rc) return rc;
+  const int total = P.ncosmo * P.nk;
+  std::vector<double> tau_out((size_t)P.ncosmo * P.nout);
+  std::vector<int32_t> st(total);
+  P.scalars = scalars; P.tables = tables; P.kmodes = kmodes; P.aexp_out = aexp_out;
+  tau_out_host(P, tau_out.data());
+  P.tau_out = tau_out.data(); P.status = st.data(); P.nsteps = nsteps; P.naccept = nullptr; P.y_out = y_out;
+  P.rp_tnext = rp_tnext; P.rp_keep = rp_keep; P.rp_n = rp_n; P.rp_stride = rp_stride;
+  P.mode = 3;
+  return dispatch(P);
+}
