@@ -65,6 +65,11 @@ class Library:
         h.argtypes = [C.POINTER(DebDims), _dp, _dp, _dp, _dp, _dp, _dp] + ([C.c_int32] if prefix == "deb_" else [])
         h.restype = C.c_int
         self._debug_ics = h
+        r = getattr(self.lib, prefix + "debug_replay_host_f64")
+        r.argtypes = [C.POINTER(DebDims), C.POINTER(DebCtrl), _dp, _dp, _dp, _dp, _dp, _ip, _ip, C.c_int32, _dp, _ip] + \
+            ([C.c_int32] if prefix == "deb_" else [])
+        r.restype = C.c_int
+        self._debug_replay = r
         if prefix == "deb_":
             self.lib.deb_strerror.restype = C.c_char_p
             self.lib.deb_strerror.argtypes = [C.c_int]
@@ -143,6 +148,23 @@ class Library:
             args.append(C.c_int32(device))
         self._check(self._debug_ics(*args), "debug_ics_host_f64")
         return ts, y0
+
+    def debug_replay(self, dims: DebDims, ctrl: DebCtrl, scalars, tables, kmodes, aexp_out, rp_tnext, rp_keep, rp_n,
+                     device: int = 0):
+        """Integrate along a prescribed step sequence (see include/discoeb_b200.h)."""
+        nf = self.nvar(dims.lmaxg, dims.lmaxgp, dims.lmaxr, dims.lmaxnu, dims.nqmax) if dims.return_full else 20
+        rp_tnext = np.ascontiguousarray(rp_tnext, dtype=np.float64)
+        rp_keep = np.ascontiguousarray(rp_keep, dtype=np.int32)
+        rp_n = np.ascontiguousarray(rp_n, dtype=np.int32)
+        y = np.zeros((dims.ncosmo, dims.nk, dims.nout, nf), dtype=np.float64)
+        ns = np.zeros((dims.ncosmo, dims.nk), dtype=np.int32)
+        args = [C.byref(dims), C.byref(ctrl), _d(np.ascontiguousarray(scalars)), _d(np.ascontiguousarray(tables)),
+                _d(np.ascontiguousarray(kmodes, dtype=np.float64)), _d(np.ascontiguousarray(aexp_out, dtype=np.float64)),
+                _d(rp_tnext), _i(rp_keep), _i(rp_n), C.c_int32(rp_tnext.shape[-1]), _d(y), _i(ns)]
+        if self.prefix == "deb_":
+            args.append(C.c_int32(device))
+        self._check(self._debug_replay(*args), "debug_replay_host_f64")
+        return y, ns
 
     def fp64_peak_tflops(self, device: int = 0):
         t = C.c_double(0.0)

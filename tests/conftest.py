@@ -1,0 +1,50 @@
+"""Shared fixtures.  GPU tests are marked ``gpu`` (run on a B200 through the C-ABI); everything
+else runs on CPU: the oracle against the reference's golden curves, the host logic, the C-ABI
+symbol table, and the kernel SOURCE compiled for the CPU (tests/emu) against the oracle."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "disco-eb_b200"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "slow: takes more than ~30 s on CPU")
+
+
+@pytest.fixture(scope="session")
+def emu_lib():
+    """The kernel source compiled as plain C++ (lanes as loops).  Test infrastructure only."""
+    from discoeb_b200 import _cabi
+    src = os.path.join(ROOT, "tests", "emu", "deb_emu.cpp")
+    out = os.path.join(ROOT, "tests", "emu", "_build", "libdeb_emu.so")
+    deps = [src, os.path.join(ROOT, "disco-eb_b200", "csrc", "deb_core.cuh"),
+            os.path.join(ROOT, "disco-eb_b200", "csrc", "deb_host.inl"), os.path.join(ROOT, "include", "discoeb_b200.h")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.check_call(["g++", "-O2", "-fopenmp", "-shared", "-fPIC", "-std=c++17", "-o", out, src])
+    return _cabi.Library(out, prefix="emu_")
+
+
+@pytest.fixture(scope="session")
+def gpu_lib():
+    from discoeb_b200 import _cabi
+    lib = _cabi.default_library()
+    if lib.lib.deb_device_count() < 1:
+        pytest.fail("no CUDA device visible: GPU tests must run on the B200 box")
+    return lib
+
+
+@pytest.fixture(scope="session")
+def tables():
+    import helpers
+    return {name: helpers.load_tables(name) for name in ("fiducial", "w0wa", "massless")}

@@ -1,0 +1,56 @@
+"""Test helpers: fixtures on disk -> packed tables / oracle-style ``param`` dicts."""
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+from oracle.background import Spline  # noqa: E402
+from discoeb_b200._pack import SCALAR_KEYS, SPLINE_KEYS  # noqa: E402
+
+
+class Tables:
+    def __init__(self, scalars, tables, nth, nnu):
+        self.scalars, self.tables, self.nth, self.nnu = scalars, tables, int(nth), int(nnu)
+
+    def param(self):
+        """Rebuild the dict the oracle consumes (splines carry the stored second derivatives)."""
+        p = {k: float(self.scalars[i]) for i, k in enumerate(SCALAR_KEYS)}
+        off = 0
+        for j, key in enumerate(SPLINE_KEYS):
+            n = self.nnu if j in (2, 3) else self.nth
+            sp = Spline.__new__(Spline)
+            sp.x = self.tables[off:off + n].copy()
+            sp.y = self.tables[off + n:off + 2 * n].copy()
+            sp.S = self.tables[off + 2 * n:off + 3 * n].copy()
+            p[key] = sp
+            off += 3 * n
+        return p
+
+
+def load_tables(name):
+    z = np.load(os.path.join(GOLD, f"tables_{name}.npz"))
+    return Tables(z["scalars"], z["tables"], z["nth"], z["nnu"])
+
+
+def load_case(name):
+    z = np.load(os.path.join(GOLD, f"oracle_{name}.npz"), allow_pickle=False)
+    return {k: z[k] for k in z.files}
+
+
+CASES = ("default_n72", "config1_n111", "config2_n265", "w0wa_n72", "odd_dims_n43")
+
+
+def field_scaled_diff(a, b):
+    """max |a-b| per output field, relative to the largest magnitude that field takes over the
+    compared set (fields such as theta_c are identically ~0, so a plain relative error is
+    meaningless for them)."""
+    sc = np.maximum(np.abs(b).max(axis=tuple(range(b.ndim - 1))), 1e-300)
+    # theta_c is identically zero in synchronous gauge (perturbations.py:269): it only carries
+    # round-off, so it is measured against the baryon velocity that sits next to it
+    if b.shape[-1] == 20:
+        sc[9] = max(sc[9], sc[11])
+    else:
+        sc[4] = max(sc[4], sc[6])
+    return np.abs(a - b).max(axis=tuple(range(b.ndim - 1))) / sc

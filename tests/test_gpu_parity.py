@@ -1,0 +1,146 @@
+"""GPU suite (pytest -m gpu, on a B200): the CUDA library through its C-ABI against the oracle's
+committed golden vectors and against the oracle itself.  Tolerances are stated in
+tests/parity_checks.py.  Nothing here reads /root/reference."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+import parity_checks as pc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", helpers.CASES)
+def test_prologue_matches_oracle(gpu_lib, tables, name):
+    pc.check_prologue(gpu_lib, tables, name)
+
+
+@pytest.mark.parametrize("name", helpers.CASES)
+def test_single_step_matches_dense_lu_oracle(gpu_lib, tables, name):
+    pc.check_single_step(gpu_lib, tables, name)
+
+
+@pytest.mark.parametrize("name", helpers.CASES)
+def test_replay_of_oracle_step_sequence(gpu_lib, tables, name):
+    pc.check_replay(gpu_lib, tables, name)
+
+
+@pytest.mark.parametrize("name", helpers.CASES)
+def test_adaptive_solve_against_oracle(gpu_lib, tables, name):
+    pc.check_adaptive(gpu_lib, tables, name)
+
+
+def test_gpu_matches_cpu_build_of_same_source(gpu_lib, emu_lib, tables):
+    """Same source, two compilers: any difference beyond round-off is a GPU-only defect
+    (missing __syncwarp, shuffle misuse, shared-memory race)."""
+    case = helpers.load_case("config2_n265")
+    tab = tables["fiducial"]
+    ks, aout = case["kmodes"], case["aexp_out"]
+    from discoeb_b200 import _cabi
+    ctrl = _cabi.make_ctrl(rtol=1e-4, atol=1e-4)
+    dims = pc.dims_for(case, tab, len(ks), len(aout), return_full=True)
+    a, na = gpu_lib.debug_replay(dims, ctrl, tab.scalars, tab.tables, ks, aout, case["rp_tnext"], case["rp_keep"], case["nsteps"])
+    b, nb = emu_lib.debug_replay(dims, ctrl, tab.scalars, tab.tables, ks, aout, case["rp_tnext"], case["rp_keep"], case["nsteps"])
+    for m in range(len(ks)):
+        assert helpers.field_scaled_diff(a[0, m], b[0, m]).max() < 1e-8
+
+
+def test_class_golden_curve_full_size(gpu_lib, tables):
+    """Reference acceptance test at its full size (512 modes, lmax=31, nq=5, z=99):
+    P_bc within 0.5 % of CLASS for k <= 10/Mpc (tests/test_perturbations.py:95-109)."""
+    from discoeb_b200 import _cabi
+    tab = tables["fiducial"]
+    g = json.load(open(os.path.join(helpers.GOLD, "CLASS_data.json")))
+    kc, Pc = np.array(g["k"]), np.array(g["Pkbc"])
+    nk = 512
+    ks = np.geomspace(1e-5, 10.0, nk)
+    dims = _cabi.make_dims(ncosmo=1, nk=nk, nout=1, lmaxg=31, lmaxgp=31, lmaxr=31, lmaxnu=31, nqmax=5, nth=tab.nth,
+                           nnu=tab.nnu, max_steps=2048, power_idx=6)
+    out = gpu_lib.evolve_host(dims, _cabi.make_ctrl(rtol=1e-4, atol=1e-4), tab.scalars[None], tab.tables[None], ks,
+                              np.array([0.01]), want_pk=True)
+    assert np.all(out["status"] == 0)
+    m = (kc >= 1e-5) & (kc <= 10.0)
+    np.testing.assert_allclose(np.interp(kc[m], ks, out["pk"][0, :, 0]), Pc[m], rtol=0.005)
+
+
+def test_full_size_properties_config2(gpu_lib, emu_lib, tables):
+    """BASELINE config 2 at full size (512 modes, n=265, z=0): size-independent properties.
+    (i) every mode completes; (ii) results do not depend on which warp/SM ran the mode: a
+    permuted k order gives bit-identical per-mode output; (iii) linearity of the epilogue:
+    pk == get_power(y); (iv) the statistical agreement with the CPU build of the same source:
+    median relative deviation of delta_m at round-off level, every mode within 50 rtol."""
+    from discoeb_b200 import _cabi
+    tab = tables["fiducial"]
+    nk = 512
+    ks = np.geomspace(1e-4, 10.0, nk)
+    dims = _cabi.make_dims(ncosmo=1, nk=nk, nout=1, lmaxg=31, lmaxgp=31, lmaxr=31, lmaxnu=31, nqmax=5, nth=tab.nth,
+                           nnu=tab.nnu, max_steps=2048, power_idx=4)
+    ctrl = _cabi.make_ctrl(rtol=1e-4, atol=1e-4)
+    out = gpu_lib.evolve_host(dims, ctrl, tab.scalars[None], tab.tables[None], ks, np.array([1.0]), want_pk=True)
+    assert np.all(out["status"] == 0)
+    perm = np.random.default_rng(3).permutation(nk)
+    outp = gpu_lib.evolve_host(dims, ctrl, tab.scalars[None], tab.tables[None], ks[perm], np.array([1.0]), want_pk=True)
+    assert np.array_equal(outp["y"][0], out["y"][0][perm])
+    assert np.array_equal(outp["nsteps"][0], out["nsteps"][0][perm])
+    p = tab.param()
+    Pk = 2 * np.pi ** 2 * p["A_s"] * (ks / p["k_p"]) ** (p["n_s"] - 1) * ks ** (-3) * out["y"][0, :, 0, 4] ** 2
+    np.testing.assert_allclose(out["pk"][0, :, 0], Pk, rtol=1e-13)
+    ref = emu_lib.evolve_host(dims, ctrl, tab.scalars[None], tab.tables[None], ks, np.array([1.0]))
+    rel = np.abs(out["y"][0, :, 0, 4] / ref["y"][0, :, 0, 4] - 1)
+    assert np.median(rel) < 1e-9
+    assert rel.max() < 50 * 1e-4
+
+
+def test_tight_tolerance_meets_1e5(gpu_lib, tables):
+    """At rtol=atol=1e-7 the free-running solve agrees with the oracle within the 1e-5 of
+    north_star on the matter transfer functions, whatever the step sequences do."""
+    from discoeb_b200 import _cabi
+    import oracle.discoeb_oracle as O
+    tab = tables["fiducial"]
+    p = tab.param()
+    ks = np.array([1e-3, 0.05, 0.5])
+    y, k, _ = O.evolve_perturbations(param=p, aexp_out=[1.0], kmin=0, kmax=0, num_k=3, kmodes=ks, rtol=1e-7, atol=1e-7,
+                                     max_steps=20000)
+    dims = _cabi.make_dims(ncosmo=1, nk=3, nout=1, lmaxg=11, lmaxgp=11, lmaxr=11, lmaxnu=8, nqmax=3, nth=tab.nth,
+                           nnu=tab.nnu, max_steps=20000)
+    out = gpu_lib.evolve_host(dims, _cabi.make_ctrl(rtol=1e-7, atol=1e-7), tab.scalars[None], tab.tables[None], ks, np.array([1.0]))
+    assert np.all(out["status"] == 0)
+    rel = np.abs(out["y"][0, :, 0, :][:, pc.MATTER_FIELDS] / y[:, 0, :][:, pc.MATTER_FIELDS] - 1)
+    assert rel.max() < 1e-5
+
+
+def test_host_api_drop_in(gpu_lib, tables):
+    """The reference-shaped Python API: 3-tuple, param side effects, get_power, failure mode."""
+    from discoeb_b200.perturbations import evolve_perturbations, evolve_perturbations_batched, get_power, MaxStepsReached
+    case = helpers.load_case("default_n72")
+    p = tables["fiducial"].param()
+    y, k, pout = evolve_perturbations(param=p, aexp_out=case["aexp_out"], kmin=1e-4, kmax=10.0, num_k=8)
+    assert y.shape == (8, 3, 20) and pout is p
+    np.testing.assert_allclose(k, case["kmodes"], rtol=1e-15)
+    assert (p["lmaxg"], p["lmaxgp"], p["lmaxr"], p["lmaxnu"], p["nqmax"], p["nout"]) == (11, 11, 11, 8, 3, 3)
+    np.testing.assert_allclose(p["tau_out"], case["tau_out"], rtol=1e-14)
+    rel = np.abs(y[..., pc.MATTER_FIELDS] / case["y"][..., pc.MATTER_FIELDS] - 1)
+    assert rel.max() < 50 * 1e-4
+    Pk = get_power(k=k, y=y[:, -1, :], idx=4, param=p)
+    assert Pk.shape == (8,) and np.all(Pk > 0)
+    yf, _, _ = evolve_perturbations(param=p, aexp_out=[1.0], kmin=1e-3, kmax=1.0, num_k=4, return_full=True)
+    assert yf.shape == (4, 1, 72)
+    yb, kb = evolve_perturbations_batched(param=p, aexp_out=[1.0], kmin=1e-3, kmax=1.0, num_k=4, batch_size=2)
+    assert yb.shape == (4, 1, 20)
+    with pytest.raises(ValueError):
+        evolve_perturbations_batched(param=p, aexp_out=[1.0], kmin=1e-3, kmax=1.0, num_k=5, batch_size=2)
+    with pytest.raises(MaxStepsReached):
+        evolve_perturbations(param=p, aexp_out=[1.0], kmin=1e-3, kmax=1.0, num_k=4, max_steps=30)
+
+
+def test_batch_of_cosmologies(gpu_lib, tables):
+    from discoeb_b200.perturbations import evolve_perturbations, evolve_perturbations_multi
+    ps = [tables["fiducial"].param(), tables["w0wa"].param(), tables["massless"].param()]
+    y, k, info = evolve_perturbations_multi(params=ps, aexp_out=[0.5, 1.0], kmin=1e-3, kmax=1.0, num_k=16, power_idx=4)
+    assert y.shape == (3, 16, 2, 20) and info["pk"].shape == (3, 16, 2)
+    for i, p in enumerate(ps):
+        yi, _, _ = evolve_perturbations(param=p, aexp_out=[0.5, 1.0], kmin=1e-3, kmax=1.0, num_k=16)
+        assert np.array_equal(yi, y[i])
