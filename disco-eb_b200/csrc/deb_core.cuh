@@ -699,6 +699,8 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
     if (P.mode == 3) {
       if (nsteps >= DEB_LDG(P.rp_n + mode)) break;
       tnext = DEB_LDG(P.rp_tnext + (size_t)mode * P.rp_stride + nsteps);
+      // the prescribed end time comes from another evaluation of tau_of_a(aexp_out): snap it onto ours
+      if (fabs(tnext - t1) <= 1e-12 * fabs(t1)) tnext = t1;
     }
     const double dt = tnext - t;
     const double invdt = 1.0 / dt;

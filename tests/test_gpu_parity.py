@@ -45,7 +45,7 @@ def test_gpu_matches_cpu_build_of_same_source(gpu_lib, emu_lib, tables):
     a, na = gpu_lib.debug_replay(dims, ctrl, tab.scalars, tab.tables, ks, aout, case["rp_tnext"], case["rp_keep"], case["nsteps"])
     b, nb = emu_lib.debug_replay(dims, ctrl, tab.scalars, tab.tables, ks, aout, case["rp_tnext"], case["rp_keep"], case["nsteps"])
     for m in range(len(ks)):
-        assert helpers.field_scaled_diff(a[0, m], b[0, m]).max() < 1e-8
+        assert helpers.field_scaled_diff(a[0, m], b[0, m]).max() < 1e-6
 
 
 def test_class_golden_curve_full_size(gpu_lib, tables):
