@@ -19,6 +19,7 @@
 #pragma once
 #include <stdint.h>
 #include <math.h>
+#include <string.h>
 
 #ifdef DEB_CPU_EMU
 #define DEB_DEV inline
@@ -33,6 +34,9 @@
 #define DEB_USE(name) auto& name = name##_all[lane]
 #define DEB_SHFL(name, src) (name##_all[(src)])
 #define DEB_ANY(name) ([&]() { int a_ = 0; for (int l_ = 0; l_ < 32; ++l_) a_ |= (name##_all[l_] != 0); return a_; }())
+// lane holding the largest 32-bit key (lowest lane among ties)
+#define DEB_ARGMAX_U32(name) ([&]() { unsigned m_ = name##_all[0]; int a_ = 0; for (int l_ = 1; l_ < 32; ++l_) if (name##_all[l_] > m_) { m_ = name##_all[l_]; a_ = l_; } return a_; }())
+#define DEB_RSQRT(x) (1.0 / sqrt(x))
 #else
 #define DEB_DEV __device__ __forceinline__
 #define DEB_HD __host__ __device__ __forceinline__
@@ -46,6 +50,8 @@
 #define DEB_USE(name)
 #define DEB_SHFL(name, src) __shfl_sync(0xffffffffu, name, (src))
 #define DEB_ANY(name) __any_sync(0xffffffffu, name)
+#define DEB_ARGMAX_U32(name) (__ffs(__ballot_sync(0xffffffffu, (name) == __reduce_max_sync(0xffffffffu, (name)))) - 1)
+#define DEB_RSQRT(x) rsqrt(x)
 #endif
 
 namespace deb {
@@ -151,6 +157,16 @@ DEB_DEV double val(double a) { return a; }
 DEB_DEV double val(Dual a) { return a.v; }
 DEB_DEV double der(double) { return 0.0; }
 DEB_DEV double der(Dual a) { return a.d; }
+// upper 32 bits of |x|: a monotone integer key for pivot selection (ties within 2^-20 are equivalent pivots)
+DEB_DEV unsigned hi32abs(double x) {
+#ifdef DEB_CPU_EMU
+  unsigned long long b; double ax = fabs(x); memcpy(&b, &ax, 8); return (unsigned)(b >> 32);
+#else
+  return (unsigned)__double2hiint(fabs(x));
+#endif
+}
+DEB_DEV Dual drsqrt(Dual a) { double r = DEB_RSQRT(a.v); return mk(r, -0.5 * r * a.d / a.v); }
+DEB_DEV double drsqrt(double a) { return DEB_RSQRT(a); }
 
 // ---------------------------------------------------------------------------------------------
 // natural cubic spline lookup (spline_interpolation.py:130-153)
@@ -233,6 +249,8 @@ struct CtaConst {
   int ch_lmax[NCHMAX];
   int ch_h2[NCHMAX];      // chain -> head position of its l=2 element
   const int* desc;        // element -> type | ell<<8 | chain<<16   [np] (dynamic shared memory)
+  const int* tail;        // tail entry -> element | chain<<12 | ell<<16, elements ascending   [np]
+  int ntail;              // number of hierarchy rows with l >= 3
 };
 
 DEB_DEV Spl get_spline(const Problem& P, int cosmo, int which) {
@@ -273,8 +291,16 @@ DEB_DEV int elem_desc(const Problem& P, int e) {
   return type | (l << 8) | (chain << 16);
 }
 
-DEB_DEV void init_cta_const(const Problem& P, CtaConst& C, int* desc, int tid, int nthreads) {
+DEB_DEV void init_cta_const(const Problem& P, CtaConst& C, int* desc, int* tail, int tid, int nthreads) {
   for (int e = tid; e < P.np; e += nthreads) desc[e] = elem_desc(P, e);
+  if (tid == 0) {
+    int nt = 0;
+    for (int e = 0; e < P.n; ++e) {
+      const int d = elem_desc(P, e), ty = d & 0xff;
+      if (ty == R_GEN || ty == R_TRUNC) tail[nt++] = e | ((d >> 16) << 12) | (((d >> 8) & 0xff) << 16);
+    }
+    C.ntail = nt; C.tail = tail;
+  }
   for (int l = tid; l < LMAXCAP; l += nthreads) {
     C.cl[l] = (double)l / (double)(2 * l + 1);
     C.ch[l] = (double)(l + 1) / (double)(2 * l + 1);
@@ -311,32 +337,6 @@ DEB_DEV void init_cta_const(const Problem& P, CtaConst& C, int* desc, int tid, i
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// per-warp shared-memory workspace (carved out of dynamic shared memory by the kernel)
-// ---------------------------------------------------------------------------------------------
-struct WarpWs {
-  double* y;    // accepted state at tprev                         [np]
-  double* u;    // stage state                                     [np]
-  double* r;    // stage right-hand side, solved in place -> k_i   [np]
-  double* m;    // tail backward multipliers W_{l,l+1}/e_{l+1}     [np]
-  double* ie;   // tail inverse pivots 1/e_l                       [np]
-  double* g;    // tail forward multipliers -W_{l,l-1}/e_l         [np]
-  double* ja;   // d f / d a at (t0, y0)                           [np]
-  double* lu;   // head LU                                         [NHMAX*LDH]
-  double* gh;   // d h'/d y_c over head columns                    [NHMAX]
-  double* ge;   // d eta'/d y_c                                    [NHMAX]
-  double* j1;   // d f_1/d y_c  (the a h' row)                     [NHMAX]
-  double* kc;   // chain wavenumber k or k v_i (value, d/da)       [2*NCHMAX]
-  double* kap;  // chain damping opac or 0 (value, d/da)           [2*NCHMAX]
-  int* perm;    // pivot row of elimination step j                 [NHMAX]
-};
-DEB_HD size_t warp_ws_doubles(int np) { return (size_t)7 * np + NHMAX * LDH + 3 * NHMAX + 4 * NCHMAX + NHMAX / 2 + 2; }
-DEB_DEV void carve(WarpWs& W, double* base, int np) {
-  W.y = base; W.u = W.y + np; W.r = W.u + np; W.m = W.r + np; W.ie = W.m + np; W.g = W.ie + np; W.ja = W.g + np;
-  W.lu = W.ja + np; W.gh = W.lu + NHMAX * LDH; W.ge = W.gh + NHMAX; W.j1 = W.ge + NHMAX;
-  W.kc = W.j1 + NHMAX; W.kap = W.kc + 2 * NCHMAX; W.perm = (int*)(W.kap + 2 * NCHMAX);
-}
-
 // per-mode constants
 struct Cosmo {
   double Omegam, Omegab, OmegaDE, Omegak, grhom, grhog, grhor, Neff, Nmnu, amnu, w0, wa, cs2de, YHe, H0, taumin;
@@ -362,25 +362,77 @@ DEB_DEV Cosmo load_cosmo(const Problem& P, int c) {
   return o;
 }
 
+// ---------------------------------------------------------------------------------------------
+// per-warp shared-memory workspace (carved out of dynamic shared memory by the kernel)
+// ---------------------------------------------------------------------------------------------
+struct WarpWs {
+  double* y;    // accepted state at tprev                         [np]
+  double* u;    // stage state                                     [np]
+  double* r;    // stage right-hand side, solved in place -> k_i   [np]
+  double* m;    // tail backward multipliers W_{l,l+1}/e_{l+1}     [np]
+  double* ie;   // tail inverse pivots 1/e_l                       [np]
+  double* g;    // tail forward multipliers -W_{l,l-1}/e_l         [np]
+  double* ja;   // d f / d a at (t0, y0)                           [np]
+  double* lu;   // head LU                                         [NHMAX*LDH]
+  double* gh;   // d h'/d y_c over head columns                    [NHMAX]
+  double* ge;   // d eta'/d y_c                                    [NHMAX]
+  double* j1;   // d f_1/d y_c  (the a h' row)                     [NHMAX]
+  double* kc;   // chain wavenumber k or k v_i (value, d/da)       [2*NCHMAX]
+  double* kap;  // chain damping opac or 0 (value, d/da)           [2*NCHMAX]
+  int* perm;    // pivot row of elimination step j                 [NHMAX]
+  Cosmo* cosmo; // per-mode constants and table pointers
+};
+DEB_HD size_t warp_ws_doubles(int np) {
+  return (size_t)7 * np + NHMAX * LDH + 3 * NHMAX + 4 * NCHMAX + NHMAX / 2 + 2 + (sizeof(Cosmo) + 7) / 8;
+}
+DEB_DEV void carve(WarpWs& W, double* base, int np) {
+  W.y = base; W.u = W.y + np; W.r = W.u + np; W.m = W.r + np; W.ie = W.m + np; W.g = W.ie + np; W.ja = W.g + np;
+  W.lu = W.ja + np; W.gh = W.lu + NHMAX * LDH; W.ge = W.gh + NHMAX; W.j1 = W.ge + NHMAX;
+  W.kc = W.j1 + NHMAX; W.kap = W.kc + 2 * NCHMAX; W.perm = (int*)(W.kap + 2 * NCHMAX);
+  W.cosmo = (Cosmo*)(W.kap + 2 * NCHMAX + NHMAX / 2 + 2);
+}
+
 // background coefficients at scale factor a (perturbations.py:176-218, background.py:110-121)
 template <class T> struct Bg {
   T a, H, opac, cs2, pbo, wq1, wq, ca2;
   T gc, gb, gg, gr, gnu, gq;      // grhom Oc/a, grhom Ob/a, grhog/a^2, grhor Neff/a^2, grhor Nmnu/a^2, grhom ODE rhoQ a^2
-  T v[NQMAX];
 };
 struct Hints { int th, nu; };
+
+// value and x-derivative factors of the cubic on interval i, shared by splines on the same knots
+struct SplPos { double h, A, B, cA, cB, dA, dB; };
+DEB_DEV SplPos spl_pos(const double* x, int i, double xn) {
+  SplPos p;
+  const double x0 = DEB_LDG(x + i), x1 = DEB_LDG(x + i + 1);
+  p.h = x1 - x0;
+  const double t = (xn - x0) / p.h;
+  p.A = 1.0 - t; p.B = t;
+  const double h26 = (p.h * p.h) / 6.0;
+  p.cA = (p.A * p.A * p.A - p.A) * h26; p.cB = (p.B * p.B * p.B - p.B) * h26;
+  p.dA = -(3.0 * p.A * p.A - 1.0) * h26; p.dB = (3.0 * p.B * p.B - 1.0) * h26;
+  return p;
+}
+DEB_DEV double spl_at(const Spl& s, int i, const SplPos& p, double) {
+  return p.A * DEB_LDG(s.y + i) + p.B * DEB_LDG(s.y + i + 1) + (p.cA * DEB_LDG(s.S + i) + p.cB * DEB_LDG(s.S + i + 1));
+}
+DEB_DEV Dual spl_at(const Spl& s, int i, const SplPos& p, Dual xn) {
+  const double y0 = DEB_LDG(s.y + i), y1 = DEB_LDG(s.y + i + 1), S0 = DEB_LDG(s.S + i), S1 = DEB_LDG(s.S + i + 1);
+  return mk(p.A * y0 + p.B * y1 + (p.cA * S0 + p.cB * S1), ((y1 - y0) + (p.dA * S0 + p.dB * S1)) / p.h * xn.d);
+}
 
 template <class T>
 DEB_DEV void compute_bg(const Cosmo& c, const NuBins& nb, int nq, T a, Hints& hint, Bg<T>& b) {
   T loga = dlog(a);
   hint.th = spl_locate(c.cs2a.x, c.cs2a.n, val(loga), hint.th);
   hint.nu = spl_locate(c.lrn.x, c.lrn.n, val(loga), hint.nu);
+  const SplPos pth = spl_pos(c.cs2a.x, hint.th, val(loga));     // cs2a and xe share their knots
+  const SplPos pnu = spl_pos(c.lrn.x, hint.nu, val(loga));
   T inva = 1.0 / a;
   T inva2 = inva * inva;
   b.a = a;
-  b.cs2 = spl_eval_at(c.cs2a, hint.th, loga) * inva;
-  T xe = spl_eval_at(c.xe, hint.th, loga);
-  T rhonu = dexp(spl_eval_at(c.lrn, hint.nu, loga));
+  b.cs2 = spl_at(c.cs2a, hint.th, pth, loga) * inva;
+  T xe = spl_at(c.xe, hint.th, pth, loga);
+  T rhonu = dexp(spl_at(c.lrn, hint.nu, pnu, loga));
   T rhoq = dexp(c.rq_exp * loga + 3.0 * c.wa * (a - 1.0));
   b.wq = c.w0 + c.wa * (1.0 - a);
   b.wq1 = 1.0 + b.wq;
@@ -392,23 +444,37 @@ DEB_DEV void compute_bg(const Cosmo& c, const NuBins& nb, int nq, T a, Hints& hi
   b.gq = (c.grhom * c.OmegaDE) * rhoq * (a * a);
   T grho = (c.grhom * c.Omegam) * inva + (c.grhog + c.grhor * (c.Neff + c.Nmnu * rhonu)) * inva2
          + b.gq + c.grhom * c.Omegak;
-  b.H = dsqrt(grho / 3.0);
-  T wqp = -c.wa * b.H * a;
-  b.ca2 = b.wq - wqp / 3.0 / (b.wq1 + 1e-6) / b.H;
+  b.H = dsqrt(grho * (1.0 / 3.0));
+  // c_a^2 = w - w'/(3 (1+w+1e-6) H) with w' = -wa H a: the Hubble rate cancels (perturbations.py:211-212)
+  b.ca2 = b.wq + (c.wa * a) / (3.0 * (b.wq1 + 1e-6));
   b.opac = xe * c.akthom * inva2;
   b.pbo = (4.0 / 3.0 * c.grhog / (c.grhom * c.Omegab)) * inva * b.opac;
-  for (int i = 0; i < nq; ++i) {
-    T aq = a * (c.amnu / nb.q[i]);
-    b.v[i] = 1.0 / dsqrt(1.0 + aq * aq);
-  }
 }
+
+// per-chain wavenumber k_c (k, or k v_i with v_i = 1/sqrt(1+(a amnu/q_i)^2)) and damping (opacity for the
+// photon chains); executed by lane `ch` < nch.  Layout [value x NCHMAX | d/da x NCHMAX].
+template <class T>
+DEB_DEV void chain_coeffs_lane(const Cosmo& c, const NuBins& nb, const Bg<T>& b, double k, int ch, double* kcA, double* kapA) {
+  T kc = 0.0 * b.a + k;
+  if (ch >= 3) {
+    T aq = b.a * (c.amnu / nb.q[ch - 3]);
+    kc = drsqrt(1.0 + aq * aq) * k;
+  }
+  T kp = ch < 2 ? b.opac : 0.0 * b.a;
+  kcA[ch] = val(kc); kcA[NCHMAX + ch] = der(kc);
+  kapA[ch] = val(kp); kapA[NCHMAX + ch] = der(kp);
+}
+
+template <class T> DEB_DEV T pick(const double* arr, int i);
+template <> DEB_DEV double pick<double>(const double* arr, int i) { return arr[i]; }
+template <> DEB_DEV Dual pick<Dual>(const double* arr, int i) { return mk(arr[i], arr[NCHMAX + i]); }
 
 // metric sources and the three constraint quantities (perturbations.py:229-261)
 template <class T> struct Metric { T hp, ep, al, f1; };
 
 template <class T>
 DEB_DEV void compute_metric(const Problem& P, const Cosmo& c, const NuBins& nb, const Bg<T>& b, const double* u,
-                            double k, Metric<T>& mt) {
+                            double k, const double* kcA, Metric<T>& mt) {
   const int nq = P.nq, iq0 = P.iq0, n = P.n;
   double eta = u[2], dc = u[3], tc = u[4], db = u[5], tb = u[6], dg = u[7], tg = u[8];
   double dr = u[P.ir], tr = u[P.ir + 1], dq = u[n - 2], tq = u[n - 1];
@@ -416,8 +482,9 @@ DEB_DEV void compute_metric(const Problem& P, const Cosmo& c, const NuBins& nb, 
   double fnu = 0.0;
   for (int i = 0; i < nq; ++i) {
     double p0 = u[iq0 + i];
-    drhonu = drhonu + (nb.w[i] * p0) / b.v[i];
-    dpnu = dpnu + (nb.w[i] * p0) * b.v[i];
+    T v = pick<T>(kcA, 3 + i) * (1.0 / k);
+    drhonu = drhonu + (nb.w[i] * p0) / v;
+    dpnu = dpnu + (nb.w[i] * p0) * v;
     fnu += nb.w[i] * u[iq0 + nq + i];
   }
   dpnu = dpnu / 3.0;
@@ -435,9 +502,6 @@ DEB_DEV void compute_metric(const Problem& P, const Cosmo& c, const NuBins& nb, 
 
 // one row of the right-hand side (perturbations.py:226-369).  kc/kap are the chain arrays with
 // layout [value x NCHMAX | d/da x NCHMAX]; the dual instantiation returns d f_e / d a in .d
-template <class T> DEB_DEV T pick(const double* arr, int i);
-template <> DEB_DEV double pick<double>(const double* arr, int i) { return arr[i]; }
-template <> DEB_DEV Dual pick<Dual>(const double* arr, int i) { return mk(arr[i], arr[NCHMAX + i]); }
 
 template <class T>
 DEB_DEV T rhs_row(const Problem& P, const Cosmo& c, const CtaConst& C, const Bg<T>& b, const Metric<T>& mt,
@@ -492,15 +556,20 @@ DEB_DEV T rhs_row(const Problem& P, const Cosmo& c, const CtaConst& C, const Bg<
   return f;
 }
 
-// fill the per-chain wavenumber / damping arrays for the current background
+// hierarchy rows with l >= 3 (perturbations.py:300-303, :307-312, :323-327, :346-360), branch-free: the
+// truncation row is the generic recurrence with (cl, ch) = (1, 0) and (lmax+1)/tau added to the damping
 template <class T>
-DEB_DEV void fill_chain_coeffs(const Problem& P, const Bg<T>& b, double k, double* kcA, double* kapA) {
-  for (int ch = 0; ch < P.nch; ++ch) {
-    T kc = ch < 3 ? (0.0 * b.a + k) : b.v[ch - 3] * k;
-    T kp = ch < 2 ? b.opac : 0.0 * b.a;
-    kcA[ch] = val(kc); kcA[NCHMAX + ch] = der(kc);
-    kapA[ch] = val(kp); kapA[NCHMAX + ch] = der(kp);
-  }
+DEB_DEV T tail_row(const CtaConst& C, const double* kcA, const double* kapA, const double* u, int info, double invtau,
+                   int* e_out, double* trunc_out) {
+  const int e = info & 0xfff, chain = (info >> 12) & 0xf, l = info >> 16;
+  const int s = C.ch_stride[chain], L = C.ch_lmax[chain];
+  const bool isT = (l == L);
+  const double clv = isT ? 1.0 : C.cl[l], chv = isT ? 0.0 : C.ch[l];
+  const double tr = isT ? (double)(L + 1) : 0.0;
+  const double lin = clv * u[e - s] - chv * u[isT ? e : e + s];
+  T kcv = pick<T>(kcA, chain), kpv = pick<T>(kapA, chain);
+  *e_out = e; *trunc_out = tr;
+  return kcv * lin - (kpv + tr * invtau) * u[e];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -654,12 +723,17 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
   const int cosmo = mode / P.nk, kidx = mode - cosmo * P.nk;
   const double k = DEB_LDG(P.kmodes + (P.k_per_cosmo ? (size_t)cosmo * P.nk + kidx : (size_t)kidx));
   const double k2 = k * k;
-  const Cosmo c = load_cosmo(P, cosmo);
+  DEB_LANE0_BEGIN
+    *W.cosmo = load_cosmo(P, cosmo);
+  DEB_LANE0_END
+  const Cosmo& c = *W.cosmo;
   const NuBins& nb = C.nu;
   const double* tout = P.tau_out + (size_t)cosmo * P.nout;
 
   DEB_REGS(double, ks, [7][NE]);
-  DEB_REGS(double, hb, );          // head solve: this lane's right-hand side / solution entry
+  DEB_REGS(int, pcol, );           // head inverse: pivot column of this lane's row
+  DEB_REGS(double, rscale, );      // head inverse: 1/pivot of this lane's row
+  DEB_REGS(unsigned, pkey, );
   DEB_REGS(int, nanflag, );
   const int* desc = C.desc;
 
@@ -712,23 +786,25 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
     {
       Bg<Dual> bd;
       compute_bg<Dual>(c, nb, nq, mk(W.y[0], 1.0), hint, bd);
+      DEB_LANES_BEGIN
+        if (lane < nch) chain_coeffs_lane<Dual>(c, nb, bd, k, lane, W.kc, W.kap);
+      DEB_LANES_END
       Metric<Dual> md;
-      compute_metric<Dual>(P, c, nb, bd, W.y, k, md);
-      DEB_LANE0_BEGIN
-        fill_chain_coeffs<Dual>(P, bd, k, W.kc, W.kap);
-      DEB_LANE0_END
+      compute_metric<Dual>(P, c, nb, bd, W.y, k, W.kc, md);
       // f(t,y) -> r (stage-1 right-hand side incl. dt d1 dT), d f/d a -> ja
       DEB_LANES_BEGIN
-#pragma unroll 1
-        for (int e = lane; e < n; e += 32) {
-          const int de = desc[e];
-          Dual f = rhs_row<Dual>(P, c, C, bd, md, W.kc, W.kap, W.y, e, de, k, invt0);
-          double fv = f.v;
-          if ((de & 0xff) == R_TRUNC) {
-            int L = C.ch_lmax[de >> 16];
-            fv += (dt * RD_D1) * ((double)(L + 1) * invt0 * invt0 * W.y[e]);
-          }
-          W.r[e] = fv; W.ja[e] = f.d;
+        if (lane < nh) {                      // head rows: one lane per row
+          const int e = C.hidx[lane];
+          Dual f = rhs_row<Dual>(P, c, C, bd, md, W.kc, W.kap, W.y, e, desc[e], k, invt0);
+          W.r[e] = f.v; W.ja[e] = f.d;
+        }
+        if (lane == 0) { Dual f = bd.H * bd.a; W.r[0] = f.v; W.ja[0] = f.d; }
+        const double d1t = (dt * RD_D1) * invt0 * invt0;
+#pragma unroll 2
+        for (int tt = lane; tt < C.ntail; tt += 32) {
+          int e; double tr;
+          Dual f = tail_row<Dual>(C, W.kc, W.kap, W.y, C.tail[tt], invt0, &e, &tr);
+          W.r[e] = f.v + d1t * tr * W.y[e]; W.ja[e] = f.d;
         }
       DEB_LANES_END
       x0piv = idg - W.ja[0];
@@ -749,7 +825,7 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
             case R_F1: wt = 4.0 / 3.0 * bd.gg.v; break;
             case R_N0: wr = bd.gr.v; wp = bd.gr.v / 3.0; break;
             case R_N1: wt = 4.0 / 3.0 * bd.gr.v; break;
-            case R_P0: wr = bd.gnu.v * nb.w[bin] / bd.v[bin].v; wp = bd.gnu.v * nb.w[bin] * bd.v[bin].v / 3.0; break;
+            case R_P0: { const double vb = W.kc[3 + bin] / k; wr = bd.gnu.v * nb.w[bin] / vb; wp = bd.gnu.v * nb.w[bin] * vb / 3.0; } break;
             case R_P1: wt = bd.gnu.v * k * nb.w[bin]; break;
             case R_DQ: wr = bd.gq.v; wp = c.cs2de * bd.gq.v; break;
             case R_TQ: wt = bd.wq1.v * bd.gq.v; wp = (c.cs2de - bd.ca2.v) * 3.0 * H * wt / k2; break;
@@ -827,9 +903,9 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
             case R_N0: row[hN + 1] -= -4.0 / 3.0; break;
             case R_N1: row[hN] -= 0.25 * k2; row[hN + 2] -= -0.5 * k2; break;
             case R_N2: row[hN + 1] -= 8.0 / 15.0; break;
-            case R_P0: row[hP + nq + bin] -= -k * bd.v[bin].v; break;
-            case R_P1: row[hP + bin] -= k * bd.v[bin].v / 3.0; row[hP + 2 * nq + bin] -= -2.0 * k * bd.v[bin].v / 3.0; break;
-            case R_P2: row[hP + nq + bin] -= 0.4 * k * bd.v[bin].v; break;
+            case R_P0: row[hP + nq + bin] -= -W.kc[3 + bin]; break;
+            case R_P1: row[hP + bin] -= W.kc[3 + bin] / 3.0; row[hP + 2 * nq + bin] -= -2.0 * W.kc[3 + bin] / 3.0; break;
+            case R_P2: row[hP + nq + bin] -= 0.4 * W.kc[3 + bin]; break;
             case R_DQ: row[hQ + 1] -= -bd.wq1.v - 9.0 * bd.wq1.v * (c.cs2de - bd.ca2.v) * H * H / k2;
                        row[hQ] -= -3.0 * (c.cs2de - bd.wq.v) * H; break;
             case R_TQ: row[hQ + 1] -= -(1.0 - 3.0 * c.cs2de) * H; row[hQ] -= c.cs2de * k2 / bd.wq1.v; break;
@@ -844,35 +920,39 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
       DEB_LANES_END
     }
 
-    // ---- head LU with partial pivoting (rows stay in place; perm[j] = pivot row of step j) ----
-    {
-      DEB_REGS(int, pivoted, );
+    // ---- head: in-place Gauss-Jordan inverse with implicit partial pivoting, one lane per row ----
+    // Rows stay in place; the pivot row of step j (perm[j]) is left unscaled until the end, which makes
+    // every elimination step a single race-free phase.  Afterwards S[:, j] holds column perm[j] of the
+    // accumulated row operations E (E W_h = Pi), so x_j = (S b_perm)[perm[j]] with b_perm[j] = b[perm[j]].
+    DEB_LANES_BEGIN
+      DEB_USE(pcol); DEB_USE(rscale);
+      pcol = -1; rscale = 1.0;
+    DEB_LANES_END
+    for (int j = 0; j < nh; ++j) {
       DEB_LANES_BEGIN
-        DEB_USE(pivoted);
-        pivoted = (lane < nh) ? 0 : 1;
+        DEB_USE(pcol); DEB_USE(pkey);
+        pkey = (lane < nh && pcol < 0) ? hi32abs(W.lu[lane * LDH + j]) + 1u : 0u;
       DEB_LANES_END
-      for (int j = 0; j < nh; ++j) {
-        // pivot search: every lane scans column j (rows not yet pivoted)
-        int piv = -1; double best = -1.0;
-        for (int rr = 0; rr < nh; ++rr) {
-          int pv = DEB_SHFL(pivoted, rr);
-          double av = fabs(W.lu[rr * LDH + j]);
-          if (!pv && (piv < 0 || av > best)) { best = av; piv = rr; }
+      const int piv = DEB_ARGMAX_U32(pkey);
+      const double ipv = 1.0 / W.lu[piv * LDH + j];
+      DEB_SYNC();
+      DEB_LANES_BEGIN
+        DEB_USE(pcol); DEB_USE(rscale);
+        double* row = W.lu + lane * LDH;
+        if (lane == piv) { pcol = j; rscale = ipv; W.perm[j] = piv; row[j] = 1.0; }
+        else if (lane < nh) {
+          const double* prow = W.lu + piv * LDH;
+          const double f = row[j] * ipv;
+          for (int cc = 0; cc < j; ++cc) row[cc] -= f * prow[cc];
+          for (int cc = j + 1; cc < nh; ++cc) row[cc] -= f * prow[cc];
+          row[j] = -f;
         }
-        const double ipv = 1.0 / W.lu[piv * LDH + j];
-        DEB_LANES_BEGIN
-          DEB_USE(pivoted);
-          if (lane == piv) { pivoted = 1; W.perm[j] = piv; }
-          if (!pivoted) {
-            double* row = W.lu + lane * LDH;
-            const double* prow = W.lu + piv * LDH;
-            double lm = row[j] * ipv;
-            row[j] = lm;
-            for (int cc = j + 1; cc < nh; ++cc) row[cc] -= lm * prow[cc];
-          }
-        DEB_LANES_END
-      }
+      DEB_LANES_END
     }
+    DEB_LANES_BEGIN
+      DEB_USE(rscale);
+      if (lane < nh) { double* row = W.lu + lane * LDH; for (int cc = 0; cc < nh; ++cc) row[cc] *= rscale; }
+    DEB_LANES_END
 
     // ================= 8 stages =================
     double errnorm2 = 0.0;
@@ -906,13 +986,12 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
         // ---- f(ts, u) + dt d_i dT + sum_j C_ij/dt k_j  -> r ----
         Bg<double> b;
         compute_bg<double>(c, nb, nq, W.u[0], hint, b);
+        DEB_LANES_BEGIN
+          if (lane < nch) chain_coeffs_lane<double>(c, nb, b, k, lane, W.kc, W.kap);
+        DEB_LANES_END
         Metric<double> mt;
-        compute_metric<double>(P, c, nb, b, W.u, k, mt);
+        compute_metric<double>(P, c, nb, b, W.u, k, W.kc, mt);
         const double invts = 1.0 / ts;
-        DEB_LANE0_BEGIN
-          // value halves only; the d/da halves written at factor time are not used by the stages
-          for (int ch = 0; ch < nch; ++ch) { W.kc[ch] = ch < 3 ? k : b.v[ch - 3] * k; W.kap[ch] = ch < 2 ? b.opac : 0.0; }
-        DEB_LANE0_END
         DEB_LANES_BEGIN
           DEB_USE(ks);
 #pragma unroll
@@ -932,15 +1011,19 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
               W.r[e] = cc * invdt;
             }
           }
-#pragma unroll 1
-          for (int e = lane; e < n; e += 32) {
-            const int de = desc[e];
-            double f = rhs_row<double>(P, c, C, b, mt, W.kc, W.kap, W.u, e, de, k, invts);
-            if (dtd != 0.0 && (de & 0xff) == R_TRUNC) {
-              int L = C.ch_lmax[de >> 16];
-              f += dtd * ((double)(L + 1) * invt0 * invt0 * W.y[e]);
-            }
-            W.r[e] += f;
+        DEB_LANES_END
+        DEB_LANES_BEGIN      // rows are distributed differently from the register-resident k's: new phase
+          if (lane < nh) {
+            const int e = C.hidx[lane];
+            W.r[e] += rhs_row<double>(P, c, C, b, mt, W.kc, W.kap, W.u, e, desc[e], k, invts);
+          }
+          if (lane == 0) W.r[0] += b.H * b.a;
+          const double dtt = dtd * invt0 * invt0;
+#pragma unroll 2
+          for (int tt = lane; tt < C.ntail; tt += 32) {
+            int e; double tr;
+            const double f = tail_row<double>(C, W.kc, W.kap, W.u, C.tail[tt], invts, &e, &tr);
+            W.r[e] += f + dtt * tr * W.y[e];
           }
         DEB_LANES_END
       }
@@ -951,49 +1034,54 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
         for (int e = lane; e < n; e += 32) W.r[e] = (e == 0) ? x0 : W.r[e] + W.ja[e] * x0;
       DEB_LANES_END
       DEB_LANES_BEGIN
-        if (lane < nch) {          // backward sweep: b'_l = b_l - m_l b'_{l+1}, l = L-1 .. 2
-          const int base = C.ch_base[lane], s = C.ch_stride[lane], L = C.ch_lmax[lane];
-          int idx = base + L * s;
+        if (lane < nch) {          // backward sweep: b'_l = b_l - m_l b'_{l+1}, l = L-1 .. 2 (loads run one step ahead)
+          const int s = C.ch_stride[lane], L = C.ch_lmax[lane];
+          int idx = C.ch_base[lane] + L * s;
           double bp = W.r[idx];
-          for (int l = L - 1; l >= 2; --l) { idx -= s; bp = W.r[idx] - W.m[idx] * bp; W.r[idx] = bp; }
+          idx -= s;
+          double rn = W.r[idx], mn = W.m[idx];
+          for (int l = L - 1; l > 2; --l) {
+            const double rc = rn, mc = mn;
+            rn = W.r[idx - s]; mn = W.m[idx - s];
+            bp = rc - mc * bp;
+            W.r[idx] = bp;
+            idx -= s;
+          }
+          W.r[idx] = rn - mn * bp;
         }
       DEB_LANES_END
-      // head: forward substitution (unit lower), then backward, rows in pivot order
+      // head: x_h = S (P b) with the explicit inverse; lane j gathers b[perm[j]], lane r forms row r of S b
       DEB_LANES_BEGIN
-        DEB_USE(hb);
-        hb = lane < nh ? W.r[C.hidx[lane]] : 0.0;
+        if (lane < nh) W.gh[lane] = W.r[C.hidx[W.perm[lane]]];
       DEB_LANES_END
-      {
-        DEB_REGS(int, done, );
-        DEB_LANES_BEGIN
-          DEB_USE(done);
-          done = 0;
-        DEB_LANES_END
-        for (int j = 0; j < nh; ++j) {
-          const int pr = W.perm[j];
-          const double yj = DEB_SHFL(hb, pr);
-          DEB_LANES_BEGIN
-            DEB_USE(hb); DEB_USE(done);
-            if (lane == pr) done = 1;
-            else if (!done && lane < nh) hb -= W.lu[lane * LDH + j] * yj;
-          DEB_LANES_END
+      DEB_LANES_BEGIN
+        DEB_USE(pcol);
+        if (lane < nh) {
+          const double* row = W.lu + lane * LDH;
+          double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+          int j = 0;
+          for (; j + 3 < nh; j += 4) {
+            a0 += row[j] * W.gh[j]; a1 += row[j + 1] * W.gh[j + 1]; a2 += row[j + 2] * W.gh[j + 2]; a3 += row[j + 3] * W.gh[j + 3];
+          }
+          for (; j < nh; ++j) a0 += row[j] * W.gh[j];
+          W.r[C.hidx[pcol]] = (a0 + a1) + (a2 + a3);
         }
-        for (int j = nh - 1; j >= 0; --j) {
-          const int pr = W.perm[j];
-          const double xj = DEB_SHFL(hb, pr) / W.lu[pr * LDH + j];
-          DEB_LANES_BEGIN
-            DEB_USE(hb); DEB_USE(done);
-            if (lane == pr) { done = 0; W.r[C.hidx[j]] = xj; }
-            else if (done && lane < nh) hb -= W.lu[lane * LDH + j] * xj;
-          DEB_LANES_END
-        }
-      }
+      DEB_LANES_END
       DEB_LANES_BEGIN
         if (lane < nch) {          // forward sweep: x_l = b'_l/e_l + g_l x_{l-1}, l = 3 .. L
-          const int base = C.ch_base[lane], s = C.ch_stride[lane], L = C.ch_lmax[lane];
-          int idx = base + 2 * s;
+          const int s = C.ch_stride[lane], L = C.ch_lmax[lane];
+          int idx = C.ch_base[lane] + 2 * s;
           double x = W.r[idx];
-          for (int l = 3; l <= L; ++l) { idx += s; x = W.r[idx] * W.ie[idx] + W.g[idx] * x; W.r[idx] = x; }
+          idx += s;
+          double cn = W.r[idx] * W.ie[idx], gn = W.g[idx];
+          for (int l = 3; l < L; ++l) {
+            const double cc = cn, gc = gn;
+            cn = W.r[idx + s] * W.ie[idx + s]; gn = W.g[idx + s];
+            x = cc + gc * x;
+            W.r[idx] = x;
+            idx += s;
+          }
+          W.r[idx] = cn + gn * x;
         }
       DEB_LANES_END
       // ---- keep k_st in registers ----
@@ -1033,23 +1121,20 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
 
     // ================= error norm, PID controller (diffrax semantics) =================
     {
-      const int idx6[6] = {0, 2, 3, 5, 6, 7};
-      const double w6[6] = {1.0, k2, 1.0, 1.0, 1.0 / k2, 1.0};
       const bool anynan = DEB_ANY(nanflag) != 0;
-      for (int q = 0; q < 6; ++q) {
-        int e = idx6[q];
-        double y0v = W.y[e], y1v = anynan ? y0v : W.u[e], ev = W.r[e];
-        if (ev != ev) ev = INFINITY;
-        double sc = ev / (P.atol + fmax(fabs(y0v), fabs(y1v)) * P.rtol) * w6[q];
-        errnorm2 += sc * sc;
-      }
+      const double ik2 = 1.0 / k2;
+#define DEB_ERRC(e, w) { double y0v = W.y[e], y1v = anynan ? y0v : W.u[e], ev = W.r[e]; if (ev != ev) ev = INFINITY; \
+        double sc = ev / (P.atol + fmax(fabs(y0v), fabs(y1v)) * P.rtol) * (w); errnorm2 += sc * sc; }
+      DEB_ERRC(0, 1.0) DEB_ERRC(2, k2) DEB_ERRC(3, 1.0) DEB_ERRC(5, 1.0) DEB_ERRC(6, ik2) DEB_ERRC(7, 1.0)
+#undef DEB_ERRC
     }
     const double E = sqrt(errnorm2 / 6.0);
     const bool keep = (P.mode == 3) ? (DEB_LDG(P.rp_keep + (size_t)mode * P.rp_stride + nsteps) != 0) : (E < 1.0);
     double inv = 1.0 / E;
-    double f1 = P.c1 != 0.0 ? pow(inv, P.c1) : 1.0;
-    double f2 = P.c2 != 0.0 ? pow(inv_prev, P.c2) : 1.0;
-    double f3 = P.c3 != 0.0 ? pow(inv_pprev, P.c3) : 1.0;
+    // inv^c1 * inv_prev^c2 * inv_pprev^c3 (PID law) through one exp; E = 0 or inf keep their limits
+    double f1 = P.c1 != 0.0 ? ((inv > 0.0 && !isinf(inv)) ? exp(P.c1 * log(inv)) : pow(inv, P.c1)) : 1.0;
+    double f2 = P.c2 != 0.0 ? exp(P.c2 * log(inv_prev)) : 1.0;
+    double f3 = P.c3 != 0.0 ? exp(P.c3 * log(inv_pprev)) : 1.0;
     double fac = fmin(fmax(P.safety * f1 * f2 * f3, keep ? 1.0 : P.factormin), P.factormax);
     if (!(fac == fac)) fac = NAN;
     const double dtn = dt * fac;

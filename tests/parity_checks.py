@@ -13,7 +13,8 @@ Tolerances (float64; north_star asks for 1e-5 relative on transfer functions / P
 * free-running adaptive solve: the step-size controller of the reference algorithm is chaotic
   under round-off once a mode takes more than ~100 steps (DESIGN.md "Parity"): two correct
   implementations diverge in their accept/reject sequence and then differ by O(10 rtol).  Hence
-  modes whose attempted-step count equals the oracle's must agree to 1e-6; the others to
+  modes of at most 100 steps whose attempted/accepted counts equal the oracle's must agree to 1e-5 (the
+  error estimate itself carries ~1e-6 of round-off, which moves dt at the 1e-5 level); the others to
   50*rtol on the matter transfer functions, and at least half of all modes must be of the
   first kind.
 """
@@ -92,6 +93,6 @@ def check_adaptive(lib, tables, name):
     for m in range(len(ks)):
         rel = np.abs(y[m][:, MATTER_FIELDS] / ref[m][:, MATTER_FIELDS] - 1).max()
         if same[m] and np.array_equal(out["naccept"][0][m:m + 1], case["naccept"][m:m + 1]) and case["nsteps"][m] <= 100:
-            assert helpers.field_scaled_diff(y[m], ref[m]).max() < 1e-6, (name, m)
+            assert helpers.field_scaled_diff(y[m], ref[m]).max() < 1e-5, (name, m)
         assert rel < 50 * rtol, (name, m, rel)
     return out
