@@ -366,30 +366,50 @@ DEB_DEV Cosmo load_cosmo(const Problem& P, int c) {
 // per-warp shared-memory workspace (carved out of dynamic shared memory by the kernel)
 // ---------------------------------------------------------------------------------------------
 struct WarpWs {
-  double* y;    // accepted state at tprev                         [np]
-  double* u;    // stage state                                     [np]
-  double* r;    // stage right-hand side, solved in place -> k_i   [np]
-  double* m;    // tail backward multipliers W_{l,l+1}/e_{l+1}     [np]
-  double* ie;   // tail inverse pivots 1/e_l                       [np]
-  double* g;    // tail forward multipliers -W_{l,l-1}/e_l         [np]
-  double* ja;   // d f / d a at (t0, y0)                           [np]
-  double* lu;   // head LU                                         [NHMAX*LDH]
-  double* gh;   // d h'/d y_c over head columns                    [NHMAX]
-  double* ge;   // d eta'/d y_c                                    [NHMAX]
-  double* j1;   // d f_1/d y_c  (the a h' row)                     [NHMAX]
-  double* kc;   // chain wavenumber k or k v_i (value, d/da)       [2*NCHMAX]
-  double* kap;  // chain damping opac or 0 (value, d/da)           [2*NCHMAX]
-  int* perm;    // pivot row of elimination step j                 [NHMAX]
-  Cosmo* cosmo; // per-mode constants and table pointers
+  double* y_;   // accepted state at tprev [np]
+  double* u_;   // stage state [np]
+  double* r_;   // stage right-hand side, solved in place -> k_i [np]
+  double* m_;   // tail backward multipliers W_{l,l+1}/e_{l+1} [np]
+  double* ie_;   // tail inverse pivots 1/e_l [np]
+  double* g_;   // tail forward multipliers -W_{l,l-1}/e_l [np]
+  double* ja_;   // d f / d a at (t0, y0) [np]
+  double* lu_;   // head matrix -> its inverse [NHMAX*LDH]
+  double* gh_;   // d h'/d y_c over head columns [NHMAX]
+  double* ge_;   // d eta'/d y_c [NHMAX]
+  double* j1_;   // d f_1/d y_c (the a h' row) [NHMAX]
+  double* kc_;   // chain wavenumber k or k v_i (value, d/da) [2*NCHMAX]
+  double* kap_;   // chain damping opac or 0 (value, d/da) [2*NCHMAX]
+  double* nur_;   // w_i psi0_i / v_i (value, d/da) [2*NQMAX]
+  double* nup_;   // w_i psi0_i v_i (value, d/da) [2*NQMAX]
+  int* perm_;    // pivot row of elimination step j [NHMAX]
+  Cosmo* cosmo_; // per-mode constants and table pointers
+  DEB_DEV double* y() const { return y_; }
+  DEB_DEV double* u() const { return u_; }
+  DEB_DEV double* r() const { return r_; }
+  DEB_DEV double* m() const { return m_; }
+  DEB_DEV double* ie() const { return ie_; }
+  DEB_DEV double* g() const { return g_; }
+  DEB_DEV double* ja() const { return ja_; }
+  DEB_DEV double* lu() const { return lu_; }
+  DEB_DEV double* gh() const { return gh_; }
+  DEB_DEV double* ge() const { return ge_; }
+  DEB_DEV double* j1() const { return j1_; }
+  DEB_DEV double* kc() const { return kc_; }
+  DEB_DEV double* kap() const { return kap_; }
+  DEB_DEV double* nur() const { return nur_; }
+  DEB_DEV double* nup() const { return nup_; }
+  DEB_DEV int* perm() const { return perm_; }
+  DEB_DEV Cosmo* cosmo() const { return cosmo_; }
 };
 DEB_HD size_t warp_ws_doubles(int np) {
-  return (size_t)7 * np + NHMAX * LDH + 3 * NHMAX + 4 * NCHMAX + NHMAX / 2 + 2 + (sizeof(Cosmo) + 7) / 8;
+  return (size_t)7 * np + NHMAX * LDH + 3 * NHMAX + 4 * NCHMAX + 4 * NQMAX + NHMAX / 2 + 2 + (sizeof(Cosmo) + 7) / 8;
 }
 DEB_DEV void carve(WarpWs& W, double* base, int np) {
-  W.y = base; W.u = W.y + np; W.r = W.u + np; W.m = W.r + np; W.ie = W.m + np; W.g = W.ie + np; W.ja = W.g + np;
-  W.lu = W.ja + np; W.gh = W.lu + NHMAX * LDH; W.ge = W.gh + NHMAX; W.j1 = W.ge + NHMAX;
-  W.kc = W.j1 + NHMAX; W.kap = W.kc + 2 * NCHMAX; W.perm = (int*)(W.kap + 2 * NCHMAX);
-  W.cosmo = (Cosmo*)(W.kap + 2 * NCHMAX + NHMAX / 2 + 2);
+  W.y_ = base; W.u_ = W.y_ + np; W.r_ = W.u_ + np; W.m_ = W.r_ + np; W.ie_ = W.m_ + np; W.g_ = W.ie_ + np; W.ja_ = W.g_ + np;
+  W.lu_ = W.ja_ + np; W.gh_ = W.lu_ + NHMAX * LDH; W.ge_ = W.gh_ + NHMAX; W.j1_ = W.ge_ + NHMAX;
+  W.kc_ = W.j1_ + NHMAX; W.kap_ = W.kc_ + 2 * NCHMAX; W.nur_ = W.kap_ + 2 * NCHMAX; W.nup_ = W.nur_ + 2 * NQMAX;
+  W.perm_ = (int*)(W.nup_ + 2 * NQMAX);
+  W.cosmo_ = (Cosmo*)(W.nup_ + 2 * NQMAX + NHMAX / 2 + 2);
 }
 
 // background coefficients at scale factor a (perturbations.py:176-218, background.py:110-121)
@@ -454,11 +474,20 @@ DEB_DEV void compute_bg(const Cosmo& c, const NuBins& nb, int nq, T a, Hints& hi
 // per-chain wavenumber k_c (k, or k v_i with v_i = 1/sqrt(1+(a amnu/q_i)^2)) and damping (opacity for the
 // photon chains); executed by lane `ch` < nch.  Layout [value x NCHMAX | d/da x NCHMAX].
 template <class T>
-DEB_DEV void chain_coeffs_lane(const Cosmo& c, const NuBins& nb, const Bg<T>& b, double k, int ch, double* kcA, double* kapA) {
+DEB_DEV void chain_coeffs_lane(const Cosmo& c, const NuBins& nb, const Bg<T>& b, double k, int ch, const double* u, int iq0,
+                               double* kcA, double* kapA, double* nurA, double* nupA) {
   T kc = 0.0 * b.a + k;
   if (ch >= 3) {
-    T aq = b.a * (c.amnu / nb.q[ch - 3]);
-    kc = drsqrt(1.0 + aq * aq) * k;
+    const int i = ch - 3;
+    T aq = b.a * (c.amnu / nb.q[i]);
+    T s2 = 1.0 + aq * aq;
+    T v = drsqrt(s2);            // v_i
+    T iv = s2 * v;               // 1/v_i without a division
+    kc = v * k;
+    const double wp0 = nb.w[i] * u[iq0 + i];
+    T tr = iv * wp0, tp = v * wp0;            // terms of drhonu and 3 dpnu (nu_perturb, perturbations.py:45-46)
+    nurA[i] = val(tr); nurA[NQMAX + i] = der(tr);
+    nupA[i] = val(tp); nupA[NQMAX + i] = der(tp);
   }
   T kp = ch < 2 ? b.opac : 0.0 * b.a;
   kcA[ch] = val(kc); kcA[NCHMAX + ch] = der(kc);
@@ -468,36 +497,37 @@ DEB_DEV void chain_coeffs_lane(const Cosmo& c, const NuBins& nb, const Bg<T>& b,
 template <class T> DEB_DEV T pick(const double* arr, int i);
 template <> DEB_DEV double pick<double>(const double* arr, int i) { return arr[i]; }
 template <> DEB_DEV Dual pick<Dual>(const double* arr, int i) { return mk(arr[i], arr[NCHMAX + i]); }
+template <class T> DEB_DEV T pickq(const double* arr, int i);
+template <> DEB_DEV double pickq<double>(const double* arr, int i) { return arr[i]; }
+template <> DEB_DEV Dual pickq<Dual>(const double* arr, int i) { return mk(arr[i], arr[NQMAX + i]); }
 
 // metric sources and the three constraint quantities (perturbations.py:229-261)
 template <class T> struct Metric { T hp, ep, al, f1; };
 
 template <class T>
 DEB_DEV void compute_metric(const Problem& P, const Cosmo& c, const NuBins& nb, const Bg<T>& b, const double* u,
-                            double k, const double* kcA, Metric<T>& mt) {
+                            double k, const double* nurA, const double* nupA, Metric<T>& mt) {
   const int nq = P.nq, iq0 = P.iq0, n = P.n;
   double eta = u[2], dc = u[3], tc = u[4], db = u[5], tb = u[6], dg = u[7], tg = u[8];
   double dr = u[P.ir], tr = u[P.ir + 1], dq = u[n - 2], tq = u[n - 1];
   T drhonu = 0.0 * b.a, dpnu = 0.0 * b.a;
   double fnu = 0.0;
   for (int i = 0; i < nq; ++i) {
-    double p0 = u[iq0 + i];
-    T v = pick<T>(kcA, 3 + i) * (1.0 / k);
-    drhonu = drhonu + (nb.w[i] * p0) / v;
-    dpnu = dpnu + (nb.w[i] * p0) * v;
+    drhonu = drhonu + pickq<T>(nurA, i);
+    dpnu = dpnu + pickq<T>(nupA, i);
     fnu += nb.w[i] * u[iq0 + nq + i];
   }
-  dpnu = dpnu / 3.0;
-  double k2 = k * k;
+  const double k2 = k * k, ik2 = 1.0 / k2;
   T rpt = b.wq1 * b.gq * tq;
   T dgrho = b.gc * dc + b.gb * db + b.gg * dg + b.gr * dr + b.gnu * drhonu + b.gq * dq;
-  T dgpres = (b.gg * dg + b.gr * dr) / 3.0 + b.gnu * dpnu + c.cs2de * (b.gq * dq)
-           + (c.cs2de - b.ca2) * (3.0 * b.H * rpt / k2);
+  // 3 dgpres: the 1/3 of the radiation and neutrino pressure cancels against the 3 of (dgrho + 3 dgpres)
+  T dgpres3 = (b.gg * dg + b.gr * dr) + b.gnu * dpnu + 3.0 * (c.cs2de * (b.gq * dq))
+            + (c.cs2de - b.ca2) * (9.0 * ik2 * (b.H * rpt));
   T dgtheta = b.gc * tc + b.gb * tb + 4.0 / 3.0 * (b.gg * tg + b.gr * tr) + b.gnu * (k * fnu) + rpt;
-  mt.f1 = -(dgrho + 3.0 * dgpres) * b.a;
+  mt.f1 = -(dgrho + dgpres3) * b.a;
   mt.hp = (2.0 * k2 * eta + dgrho) / b.H;
-  mt.ep = 0.5 * dgtheta / k2;
-  mt.al = (mt.hp + 6.0 * mt.ep) / 2.0 / k2;
+  mt.ep = (0.5 * ik2) * dgtheta;
+  mt.al = (mt.hp + 6.0 * mt.ep) * (0.5 * ik2);
 }
 
 // one row of the right-hand side (perturbations.py:226-369).  kc/kap are the chain arrays with
@@ -724,13 +754,12 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
   const double k = DEB_LDG(P.kmodes + (P.k_per_cosmo ? (size_t)cosmo * P.nk + kidx : (size_t)kidx));
   const double k2 = k * k;
   DEB_LANE0_BEGIN
-    *W.cosmo = load_cosmo(P, cosmo);
+    *W.cosmo() = load_cosmo(P, cosmo);
   DEB_LANE0_END
-  const Cosmo& c = *W.cosmo;
+  const Cosmo& c = *W.cosmo();
   const NuBins& nb = C.nu;
   const double* tout = P.tau_out + (size_t)cosmo * P.nout;
 
-  DEB_REGS(double, ks, [7][NE]);
   DEB_REGS(int, pcol, );           // head inverse: pivot column of this lane's row
   DEB_REGS(double, rscale, );      // head inverse: 1/pivot of this lane's row
   DEB_REGS(unsigned, pkey, );
@@ -745,18 +774,18 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
   if (P.mode == 1) {
     t = DEB_LDG(P.dbg_t0 + mode); tnext = DEB_LDG(P.dbg_t1 + mode); t1 = tnext;
     DEB_LANES_BEGIN
-      for (int e = lane; e < n; e += 32) W.y[e] = DEB_LDG(P.dbg_y0 + (size_t)mode * n + e);
+      for (int e = lane; e < n; e += 32) W.y()[e] = DEB_LDG(P.dbg_y0 + (size_t)mode * n + e);
     DEB_LANES_END
   } else {
     double tau_start = 0.99 * fmin(tmin_out, start_time(c, k));
     IcScalars ics = ic_scalars(c, tau_start, k);
     DEB_LANES_BEGIN
-      for (int e = lane; e < n; e += 32) W.y[e] = ic_value(P, c, nb, ics, desc[e], k);
+      for (int e = lane; e < n; e += 32) W.y()[e] = ic_value(P, c, nb, ics, desc[e], k);
     DEB_LANES_END
     if (P.mode == 2) {
       DEB_LANES_BEGIN
         if (lane == 0) P.dbg_tau_start[mode] = tau_start;
-        for (int e = lane; e < n; e += 32) P.dbg_ics[(size_t)mode * n + e] = W.y[e];
+        for (int e = lane; e < n; e += 32) P.dbg_ics[(size_t)mode * n + e] = W.y()[e];
       DEB_LANES_END
       return;
     }
@@ -776,6 +805,7 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
       // the prescribed end time comes from another evaluation of tau_of_a(aexp_out): snap it onto ours
       if (fabs(tnext - t1) <= 1e-12 * fabs(t1)) tnext = t1;
     }
+    DEB_REGS(double, ks, [7][NE]);    // stage vectors k_1..k_7: registers, scoped to one step (dead while W is factored)
     const double dt = tnext - t;
     const double invdt = 1.0 / dt;
     const double idg = 1.0 / (dt * RD_GAMMA);      // diagonal of W = I/(gamma dt) - J
@@ -785,29 +815,29 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
     double x0piv;      // W_00 = 1/(gamma dt) - d(H a)/da
     {
       Bg<Dual> bd;
-      compute_bg<Dual>(c, nb, nq, mk(W.y[0], 1.0), hint, bd);
+      compute_bg<Dual>(c, nb, nq, mk(W.y()[0], 1.0), hint, bd);
       DEB_LANES_BEGIN
-        if (lane < nch) chain_coeffs_lane<Dual>(c, nb, bd, k, lane, W.kc, W.kap);
+        if (lane < nch) chain_coeffs_lane<Dual>(c, nb, bd, k, lane, W.y(), P.iq0, W.kc(), W.kap(), W.nur(), W.nup());
       DEB_LANES_END
       Metric<Dual> md;
-      compute_metric<Dual>(P, c, nb, bd, W.y, k, W.kc, md);
+      compute_metric<Dual>(P, c, nb, bd, W.y(), k, W.nur(), W.nup(), md);
       // f(t,y) -> r (stage-1 right-hand side incl. dt d1 dT), d f/d a -> ja
       DEB_LANES_BEGIN
         if (lane < nh) {                      // head rows: one lane per row
           const int e = C.hidx[lane];
-          Dual f = rhs_row<Dual>(P, c, C, bd, md, W.kc, W.kap, W.y, e, desc[e], k, invt0);
-          W.r[e] = f.v; W.ja[e] = f.d;
+          Dual f = rhs_row<Dual>(P, c, C, bd, md, W.kc(), W.kap(), W.y(), e, desc[e], k, invt0);
+          W.r()[e] = f.v; W.ja()[e] = f.d;
         }
-        if (lane == 0) { Dual f = bd.H * bd.a; W.r[0] = f.v; W.ja[0] = f.d; }
+        if (lane == 0) { Dual f = bd.H * bd.a; W.r()[0] = f.v; W.ja()[0] = f.d; }
         const double d1t = (dt * RD_D1) * invt0 * invt0;
 #pragma unroll 2
         for (int tt = lane; tt < C.ntail; tt += 32) {
           int e; double tr;
-          Dual f = tail_row<Dual>(C, W.kc, W.kap, W.y, C.tail[tt], invt0, &e, &tr);
-          W.r[e] = f.v + d1t * tr * W.y[e]; W.ja[e] = f.d;
+          Dual f = tail_row<Dual>(C, W.kc(), W.kap(), W.y(), C.tail[tt], invt0, &e, &tr);
+          W.r()[e] = f.v + d1t * tr * W.y()[e]; W.ja()[e] = f.d;
         }
       DEB_LANES_END
-      x0piv = idg - W.ja[0];
+      x0piv = idg - W.ja()[0];
 
       // head-column gradients of h', eta' and of row 1 (value parts only)
       const double H = bd.H.v, a = bd.a.v;
@@ -825,15 +855,15 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
             case R_F1: wt = 4.0 / 3.0 * bd.gg.v; break;
             case R_N0: wr = bd.gr.v; wp = bd.gr.v / 3.0; break;
             case R_N1: wt = 4.0 / 3.0 * bd.gr.v; break;
-            case R_P0: { const double vb = W.kc[3 + bin] / k; wr = bd.gnu.v * nb.w[bin] / vb; wp = bd.gnu.v * nb.w[bin] * vb / 3.0; } break;
+            case R_P0: { const double vb = W.kc()[3 + bin] / k; wr = bd.gnu.v * nb.w[bin] / vb; wp = bd.gnu.v * nb.w[bin] * vb / 3.0; } break;
             case R_P1: wt = bd.gnu.v * k * nb.w[bin]; break;
             case R_DQ: wr = bd.gq.v; wp = c.cs2de * bd.gq.v; break;
             case R_TQ: wt = bd.wq1.v * bd.gq.v; wp = (c.cs2de - bd.ca2.v) * 3.0 * H * wt / k2; break;
             default: break;
           }
-          W.gh[lane] = wr / H + extra;
-          W.ge[lane] = 0.5 * wt / k2;
-          W.j1[lane] = -(wr + 3.0 * wp) * a;
+          W.gh()[lane] = wr / H + extra;
+          W.ge()[lane] = 0.5 * wt / k2;
+          W.j1()[lane] = -(wr + 3.0 * wp) * a;
         }
       DEB_LANES_END
 
@@ -841,27 +871,27 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
       DEB_LANES_BEGIN
         if (lane < nch) {
           const int base = C.ch_base[lane], s = C.ch_stride[lane], L = C.ch_lmax[lane];
-          const double kc = W.kc[lane], kp = W.kap[lane];
+          const double kc = W.kc()[lane], kp = W.kap()[lane];
           // row L (truncation): diag = idg + kap + (L+1)/tau, lower = -kc
           double e = idg + kp + (double)(L + 1) * invt0;
           double ie = 1.0 / e;
           int idx = base + L * s;
-          W.ie[idx] = ie;
-          W.g[idx] = kc * ie;                      // -W_{L,L-1}/e_L
+          W.ie()[idx] = ie;
+          W.g()[idx] = kc * ie;                      // -W_{L,L-1}/e_L
           double lower_next = -kc;                 // W_{l+1,l}
           for (int l = L - 1; l >= 2; --l) {
             idx -= s;
             double up = kc * C.ch[l];              // W_{l,l+1}
             double mm = up * ie;                   // uses 1/e_{l+1}
-            W.m[idx] = mm;
+            W.m()[idx] = mm;
             if (l >= 3) {
               e = idg + kp - mm * lower_next;
               ie = 1.0 / e;
-              W.ie[idx] = ie;
+              W.ie()[idx] = ie;
               lower_next = -kc * C.cl[l];
-              W.g[idx] = -lower_next * ie;
+              W.g()[idx] = -lower_next * ie;
             } else {
-              W.ie[idx] = -mm * lower_next;        // Schur increment for head diagonal (l=2 row)
+              W.ie()[idx] = -mm * lower_next;        // Schur increment for head diagonal (l=2 row)
             }
           }
         }
@@ -871,7 +901,7 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
       DEB_LANES_BEGIN
         if (lane < nh) {
           const int ty = C.htype[lane], bin = C.hbin[lane];
-          double* row = W.lu + lane * LDH;
+          double* row = W.lu() + lane * LDH;
           double chh = 0.0, cee = 0.0;
           switch (ty) {
             case R_ETA: cee = 1.0; break;
@@ -883,8 +913,13 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
             case R_DQ: chh = -0.5 * bd.wq1.v; break;
             default: break;
           }
-          if (ty == R_AHP) { for (int cc = 0; cc < nh; ++cc) row[cc] = -W.j1[cc]; }
-          else { for (int cc = 0; cc < nh; ++cc) row[cc] = -(chh * W.gh[cc] + cee * W.ge[cc]); }
+          for (int c0 = 0; c0 < nh; c0 += 8) {
+            double ga[8], gb[8], gc[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { ga[i] = W.gh()[c0 + i]; gb[i] = W.ge()[c0 + i]; gc[i] = W.j1()[c0 + i]; }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) row[c0 + i] = (ty == R_AHP) ? -gc[i] : -(chh * ga[i] + cee * gb[i]);
+          }
           row[lane] += idg;
           // local couplings; head positions: 0 eta,1 dc,2 tc,3 db,4 tb,5-7 F,8-10 G,11-13 N,14.. psi, then dq,tq,ahp
           const double op = bd.opac.v, pbo = bd.pbo.v;
@@ -903,9 +938,9 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
             case R_N0: row[hN + 1] -= -4.0 / 3.0; break;
             case R_N1: row[hN] -= 0.25 * k2; row[hN + 2] -= -0.5 * k2; break;
             case R_N2: row[hN + 1] -= 8.0 / 15.0; break;
-            case R_P0: row[hP + nq + bin] -= -W.kc[3 + bin]; break;
-            case R_P1: row[hP + bin] -= W.kc[3 + bin] / 3.0; row[hP + 2 * nq + bin] -= -2.0 * W.kc[3 + bin] / 3.0; break;
-            case R_P2: row[hP + nq + bin] -= 0.4 * W.kc[3 + bin]; break;
+            case R_P0: row[hP + nq + bin] -= -W.kc()[3 + bin]; break;
+            case R_P1: row[hP + bin] -= W.kc()[3 + bin] / 3.0; row[hP + 2 * nq + bin] -= -2.0 * W.kc()[3 + bin] / 3.0; break;
+            case R_P2: row[hP + nq + bin] -= 0.4 * W.kc()[3 + bin]; break;
             case R_DQ: row[hQ + 1] -= -bd.wq1.v - 9.0 * bd.wq1.v * (c.cs2de - bd.ca2.v) * H * H / k2;
                        row[hQ] -= -3.0 * (c.cs2de - bd.wq.v) * H; break;
             case R_TQ: row[hQ + 1] -= -(1.0 - 3.0 * c.cs2de) * H; row[hQ] -= c.cs2de * k2 / bd.wq1.v; break;
@@ -914,7 +949,7 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
           // Schur complement of the chain tail on the l=2 diagonal
           if (ty == R_F2 || ty == R_G2 || ty == R_N2 || ty == R_P2) {
             int chain = ty == R_F2 ? 0 : (ty == R_G2 ? 1 : (ty == R_N2 ? 2 : 3 + bin));
-            row[lane] += W.ie[C.ch_base[chain] + 2 * C.ch_stride[chain]];
+            row[lane] += W.ie()[C.ch_base[chain] + 2 * C.ch_stride[chain]];
           }
         }
       DEB_LANES_END
@@ -931,27 +966,42 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
     for (int j = 0; j < nh; ++j) {
       DEB_LANES_BEGIN
         DEB_USE(pcol); DEB_USE(pkey);
-        pkey = (lane < nh && pcol < 0) ? hi32abs(W.lu[lane * LDH + j]) + 1u : 0u;
+        pkey = (lane < nh && pcol < 0) ? hi32abs(W.lu()[lane * LDH + j]) + 1u : 0u;
       DEB_LANES_END
       const int piv = DEB_ARGMAX_U32(pkey);
-      const double ipv = 1.0 / W.lu[piv * LDH + j];
+      const double ipv = 1.0 / W.lu()[piv * LDH + j];
       DEB_SYNC();
       DEB_LANES_BEGIN
         DEB_USE(pcol); DEB_USE(rscale);
-        double* row = W.lu + lane * LDH;
-        if (lane == piv) { pcol = j; rscale = ipv; W.perm[j] = piv; row[j] = 1.0; }
+        double* row = W.lu() + lane * LDH;
+        if (lane == piv) { pcol = j; rscale = ipv; W.perm()[j] = piv; row[j] = 1.0; }
         else if (lane < nh) {
-          const double* prow = W.lu + piv * LDH;
+          const double* prow = W.lu() + piv * LDH;
           const double f = row[j] * ipv;
-          for (int cc = 0; cc < j; ++cc) row[cc] -= f * prow[cc];
-          for (int cc = j + 1; cc < nh; ++cc) row[cc] -= f * prow[cc];
+          double* rp = row;
+          for (int c0 = 0; c0 < nh; c0 += 8, rp += 8, prow += 8) {   // 8 columns per trip: loads, then FMAs, then stores
+            double ra[8], pa[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { ra[i] = rp[i]; pa[i] = prow[i]; }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) rp[i] = ra[i] - f * pa[i];
+          }
           row[j] = -f;
         }
       DEB_LANES_END
     }
     DEB_LANES_BEGIN
       DEB_USE(rscale);
-      if (lane < nh) { double* row = W.lu + lane * LDH; for (int cc = 0; cc < nh; ++cc) row[cc] *= rscale; }
+      if (lane < nh) {
+        double* row = W.lu() + lane * LDH;
+        for (int c0 = 0; c0 < nh; c0 += 8) {
+          double ra[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) ra[i] = row[c0 + i];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) row[c0 + i] = ra[i] * rscale;
+        }
+      }
     DEB_LANES_END
 
     // ================= 8 stages =================
@@ -963,144 +1013,132 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
         const double ts = st == 2 ? t + RD_CT2 * dt : st == 3 ? t + RD_CT3 * dt : st == 4 ? t + RD_CT4 * dt
                         : st == 5 ? t + RD_CT5 * dt : t + dt;
         const double dtd = st == 2 ? dt * RD_D2 : st == 3 ? dt * RD_D3 : st == 4 ? dt * RD_D4 : st == 5 ? dt * RD_D5 : 0.0;
+        // (the switch sits outside the element loops so that every k_j keeps a fixed register)
+#define DEB_FOR_OWN(body) _Pragma("unroll") for (int j = 0; j < NE; ++j) { const int e = lane + 32 * j; if (e < n) { body } }
         DEB_LANES_BEGIN
           DEB_USE(ks);
-#pragma unroll
-          for (int j = 0; j < NE; ++j) {
-            int e = lane + 32 * j;
-            if (e < n) {
-              double uu;
-              switch (st) {
-                case 2: uu = W.y[e] + RD_A21 * ks[0][j]; break;
-                case 3: uu = W.y[e] + RD_A31 * ks[0][j] + RD_A32 * ks[1][j]; break;
-                case 4: uu = W.y[e] + RD_A41 * ks[0][j] + RD_A42 * ks[1][j] + RD_A43 * ks[2][j]; break;
-                case 5: uu = W.y[e] + RD_A51 * ks[0][j] + RD_A52 * ks[1][j] + RD_A53 * ks[2][j] + RD_A54 * ks[3][j]; break;
-                case 6: uu = W.y[e] + RD_A61 * ks[0][j] + RD_A62 * ks[1][j] + RD_A63 * ks[2][j] + RD_A64 * ks[3][j] + RD_A65 * ks[4][j]; break;
-                case 7: uu = W.u[e] + ks[5][j]; break;
-                default: uu = W.u[e] + ks[6][j]; break;
-              }
-              W.u[e] = uu;
-            }
+          switch (st) {
+            case 2: DEB_FOR_OWN(W.u()[e] = W.y()[e] + RD_A21 * ks[0][j];) break;
+            case 3: DEB_FOR_OWN(W.u()[e] = W.y()[e] + RD_A31 * ks[0][j] + RD_A32 * ks[1][j];) break;
+            case 4: DEB_FOR_OWN(W.u()[e] = W.y()[e] + RD_A41 * ks[0][j] + RD_A42 * ks[1][j] + RD_A43 * ks[2][j];) break;
+            case 5: DEB_FOR_OWN(W.u()[e] = W.y()[e] + RD_A51 * ks[0][j] + RD_A52 * ks[1][j] + RD_A53 * ks[2][j] + RD_A54 * ks[3][j];) break;
+            case 6: DEB_FOR_OWN(W.u()[e] = W.y()[e] + RD_A61 * ks[0][j] + RD_A62 * ks[1][j] + RD_A63 * ks[2][j] + RD_A64 * ks[3][j] + RD_A65 * ks[4][j];) break;
+            case 7: DEB_FOR_OWN(W.u()[e] = W.u()[e] + ks[5][j];) break;
+            default: DEB_FOR_OWN(W.u()[e] = W.u()[e] + ks[6][j];) break;
           }
         DEB_LANES_END
         // ---- f(ts, u) + dt d_i dT + sum_j C_ij/dt k_j  -> r ----
         Bg<double> b;
-        compute_bg<double>(c, nb, nq, W.u[0], hint, b);
+        compute_bg<double>(c, nb, nq, W.u()[0], hint, b);
         DEB_LANES_BEGIN
-          if (lane < nch) chain_coeffs_lane<double>(c, nb, b, k, lane, W.kc, W.kap);
+          if (lane < nch) chain_coeffs_lane<double>(c, nb, b, k, lane, W.u(), P.iq0, W.kc(), W.kap(), W.nur(), W.nup());
         DEB_LANES_END
         Metric<double> mt;
-        compute_metric<double>(P, c, nb, b, W.u, k, W.kc, mt);
+        compute_metric<double>(P, c, nb, b, W.u(), k, W.nur(), W.nup(), mt);
         const double invts = 1.0 / ts;
         DEB_LANES_BEGIN
           DEB_USE(ks);
-#pragma unroll
-          for (int j = 0; j < NE; ++j) {
-            int e = lane + 32 * j;
-            if (e < n) {
-              double cc;
-              switch (st) {
-                case 2: cc = RD_C21 * ks[0][j]; break;
-                case 3: cc = RD_C31 * ks[0][j] + RD_C32 * ks[1][j]; break;
-                case 4: cc = RD_C41 * ks[0][j] + RD_C42 * ks[1][j] + RD_C43 * ks[2][j]; break;
-                case 5: cc = RD_C51 * ks[0][j] + RD_C52 * ks[1][j] + RD_C53 * ks[2][j] + RD_C54 * ks[3][j]; break;
-                case 6: cc = RD_C61 * ks[0][j] + RD_C62 * ks[1][j] + RD_C63 * ks[2][j] + RD_C64 * ks[3][j] + RD_C65 * ks[4][j]; break;
-                case 7: cc = RD_C71 * ks[0][j] + RD_C72 * ks[1][j] + RD_C73 * ks[2][j] + RD_C74 * ks[3][j] + RD_C75 * ks[4][j] + RD_C76 * ks[5][j]; break;
-                default: cc = RD_C81 * ks[0][j] + RD_C82 * ks[1][j] + RD_C83 * ks[2][j] + RD_C84 * ks[3][j] + RD_C85 * ks[4][j] + RD_C86 * ks[5][j] + RD_C87 * ks[6][j]; break;
-              }
-              W.r[e] = cc * invdt;
-            }
+          switch (st) {
+            case 2: DEB_FOR_OWN(W.r()[e] = invdt * (RD_C21 * ks[0][j]);) break;
+            case 3: DEB_FOR_OWN(W.r()[e] = invdt * (RD_C31 * ks[0][j] + RD_C32 * ks[1][j]);) break;
+            case 4: DEB_FOR_OWN(W.r()[e] = invdt * (RD_C41 * ks[0][j] + RD_C42 * ks[1][j] + RD_C43 * ks[2][j]);) break;
+            case 5: DEB_FOR_OWN(W.r()[e] = invdt * (RD_C51 * ks[0][j] + RD_C52 * ks[1][j] + RD_C53 * ks[2][j] + RD_C54 * ks[3][j]);) break;
+            case 6: DEB_FOR_OWN(W.r()[e] = invdt * (RD_C61 * ks[0][j] + RD_C62 * ks[1][j] + RD_C63 * ks[2][j] + RD_C64 * ks[3][j] + RD_C65 * ks[4][j]);) break;
+            case 7: DEB_FOR_OWN(W.r()[e] = invdt * (RD_C71 * ks[0][j] + RD_C72 * ks[1][j] + RD_C73 * ks[2][j] + RD_C74 * ks[3][j] + RD_C75 * ks[4][j] + RD_C76 * ks[5][j]);) break;
+            default: DEB_FOR_OWN(W.r()[e] = invdt * (RD_C81 * ks[0][j] + RD_C82 * ks[1][j] + RD_C83 * ks[2][j] + RD_C84 * ks[3][j] + RD_C85 * ks[4][j] + RD_C86 * ks[5][j] + RD_C87 * ks[6][j]);) break;
           }
         DEB_LANES_END
         DEB_LANES_BEGIN      // rows are distributed differently from the register-resident k's: new phase
           if (lane < nh) {
             const int e = C.hidx[lane];
-            W.r[e] += rhs_row<double>(P, c, C, b, mt, W.kc, W.kap, W.u, e, desc[e], k, invts);
+            W.r()[e] += rhs_row<double>(P, c, C, b, mt, W.kc(), W.kap(), W.u(), e, desc[e], k, invts);
           }
-          if (lane == 0) W.r[0] += b.H * b.a;
+          if (lane == 0) W.r()[0] += b.H * b.a;
           const double dtt = dtd * invt0 * invt0;
-#pragma unroll 2
-          for (int tt = lane; tt < C.ntail; tt += 32) {
-            int e; double tr;
-            const double f = tail_row<double>(C, W.kc, W.kap, W.u, C.tail[tt], invts, &e, &tr);
-            W.r[e] += f + dtt * tr * W.y[e];
+          for (int tt = lane; tt < C.ntail; tt += 64) {      // two rows per trip: both evaluated before either store
+            int e0, e1 = 0; double tr0, tr1 = 0.0, f1 = 0.0, r1 = 0.0, y1 = 0.0;
+            const bool two = tt + 32 < C.ntail;
+            const double f0 = tail_row<double>(C, W.kc(), W.kap(), W.u(), C.tail[tt], invts, &e0, &tr0);
+            const double r0 = W.r()[e0], y0 = W.y()[e0];
+            if (two) { f1 = tail_row<double>(C, W.kc(), W.kap(), W.u(), C.tail[tt + 32], invts, &e1, &tr1); r1 = W.r()[e1]; y1 = W.y()[e1]; }
+            W.r()[e0] = r0 + f0 + dtt * tr0 * y0;
+            if (two) W.r()[e1] = r1 + f1 + dtt * tr1 * y1;
           }
         DEB_LANES_END
       }
 
       // ---- solve W x = r in place ----
-      const double x0 = W.r[0] / x0piv;
+      const double x0 = W.r()[0] / x0piv;
       DEB_LANES_BEGIN
-        for (int e = lane; e < n; e += 32) W.r[e] = (e == 0) ? x0 : W.r[e] + W.ja[e] * x0;
+        DEB_FOR_OWN(W.r()[e] = (e == 0) ? x0 : W.r()[e] + W.ja()[e] * x0;)
       DEB_LANES_END
       DEB_LANES_BEGIN
         if (lane < nch) {          // backward sweep: b'_l = b_l - m_l b'_{l+1}, l = L-1 .. 2 (loads run one step ahead)
           const int s = C.ch_stride[lane], L = C.ch_lmax[lane];
-          int idx = C.ch_base[lane] + L * s;
-          double bp = W.r[idx];
-          idx -= s;
-          double rn = W.r[idx], mn = W.m[idx];
+          double* rp = W.r() + (C.ch_base[lane] + L * s);
+          const double* mp = W.m() + (C.ch_base[lane] + L * s);
+          double bp = *rp;
+          rp -= s; mp -= s;
+          double rn = *rp, mn = *mp;
           for (int l = L - 1; l > 2; --l) {
             const double rc = rn, mc = mn;
-            rn = W.r[idx - s]; mn = W.m[idx - s];
+            rn = *(rp - s); mn = *(mp - s);
             bp = rc - mc * bp;
-            W.r[idx] = bp;
-            idx -= s;
+            *rp = bp;
+            rp -= s; mp -= s;
           }
-          W.r[idx] = rn - mn * bp;
+          *rp = rn - mn * bp;
         }
       DEB_LANES_END
       // head: x_h = S (P b) with the explicit inverse; lane j gathers b[perm[j]], lane r forms row r of S b
       DEB_LANES_BEGIN
-        if (lane < nh) W.gh[lane] = W.r[C.hidx[W.perm[lane]]];
+        if (lane < nh) W.gh()[lane] = W.r()[C.hidx[W.perm()[lane]]];
       DEB_LANES_END
       DEB_LANES_BEGIN
         DEB_USE(pcol);
         if (lane < nh) {
-          const double* row = W.lu + lane * LDH;
+          const double* row = W.lu() + lane * LDH;
           double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
           int j = 0;
           for (; j + 3 < nh; j += 4) {
-            a0 += row[j] * W.gh[j]; a1 += row[j + 1] * W.gh[j + 1]; a2 += row[j + 2] * W.gh[j + 2]; a3 += row[j + 3] * W.gh[j + 3];
+            a0 += row[j] * W.gh()[j]; a1 += row[j + 1] * W.gh()[j + 1]; a2 += row[j + 2] * W.gh()[j + 2]; a3 += row[j + 3] * W.gh()[j + 3];
           }
-          for (; j < nh; ++j) a0 += row[j] * W.gh[j];
-          W.r[C.hidx[pcol]] = (a0 + a1) + (a2 + a3);
+          for (; j < nh; ++j) a0 += row[j] * W.gh()[j];
+          W.r()[C.hidx[pcol]] = (a0 + a1) + (a2 + a3);
         }
       DEB_LANES_END
       DEB_LANES_BEGIN
         if (lane < nch) {          // forward sweep: x_l = b'_l/e_l + g_l x_{l-1}, l = 3 .. L
           const int s = C.ch_stride[lane], L = C.ch_lmax[lane];
-          int idx = C.ch_base[lane] + 2 * s;
-          double x = W.r[idx];
-          idx += s;
-          double cn = W.r[idx] * W.ie[idx], gn = W.g[idx];
+          const int i0 = C.ch_base[lane] + 2 * s;
+          double* rp = W.r() + i0;
+          const double* ip = W.ie() + i0;
+          const double* gp = W.g() + i0;
+          double x = *rp;
+          rp += s; ip += s; gp += s;
+          double cn = *rp * *ip, gn = *gp;
           for (int l = 3; l < L; ++l) {
             const double cc = cn, gc = gn;
-            cn = W.r[idx + s] * W.ie[idx + s]; gn = W.g[idx + s];
+            cn = *(rp + s) * *(ip + s); gn = *(gp + s);
             x = cc + gc * x;
-            W.r[idx] = x;
-            idx += s;
+            *rp = x;
+            rp += s; ip += s; gp += s;
           }
-          W.r[idx] = cn + gn * x;
+          *rp = cn + gn * x;
         }
       DEB_LANES_END
       // ---- keep k_st in registers ----
       if (st < 8) {
         DEB_LANES_BEGIN
           DEB_USE(ks);
-#pragma unroll
-          for (int j = 0; j < NE; ++j) {
-            int e = lane + 32 * j;
-            double kv = e < n ? W.r[e] : 0.0;
-            switch (st) {
-              case 1: ks[0][j] = kv; break;
-              case 2: ks[1][j] = kv; break;
-              case 3: ks[2][j] = kv; break;
-              case 4: ks[3][j] = kv; break;
-              case 5: ks[4][j] = kv; break;
-              case 6: ks[5][j] = kv; break;
-              default: ks[6][j] = kv; break;
-            }
+          switch (st) {
+            case 1: DEB_FOR_OWN(ks[0][j] = W.r()[e];) break;
+            case 2: DEB_FOR_OWN(ks[1][j] = W.r()[e];) break;
+            case 3: DEB_FOR_OWN(ks[2][j] = W.r()[e];) break;
+            case 4: DEB_FOR_OWN(ks[3][j] = W.r()[e];) break;
+            case 5: DEB_FOR_OWN(ks[4][j] = W.r()[e];) break;
+            case 6: DEB_FOR_OWN(ks[5][j] = W.r()[e];) break;
+            default: DEB_FOR_OWN(ks[6][j] = W.r()[e];) break;
           }
         DEB_LANES_END
       }
@@ -1109,12 +1147,12 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
     DEB_LANES_BEGIN
       DEB_USE(nanflag);
       nanflag = 0;
-      for (int e = lane; e < n; e += 32) { double y1v = W.u[e] + W.r[e]; W.u[e] = y1v; nanflag |= (y1v != y1v); }
+      DEB_FOR_OWN(const double y1v = W.u()[e] + W.r()[e]; W.u()[e] = y1v; nanflag |= (y1v != y1v);)
     DEB_LANES_END
 
     if (P.mode == 1) {
       DEB_LANES_BEGIN
-        for (int e = lane; e < n; e += 32) { P.dbg_y1[(size_t)mode * n + e] = W.u[e]; P.dbg_err[(size_t)mode * n + e] = W.r[e]; }
+        for (int e = lane; e < n; e += 32) { P.dbg_y1[(size_t)mode * n + e] = W.u()[e]; P.dbg_err[(size_t)mode * n + e] = W.r()[e]; }
       DEB_LANES_END
       return;
     }
@@ -1123,7 +1161,7 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
     {
       const bool anynan = DEB_ANY(nanflag) != 0;
       const double ik2 = 1.0 / k2;
-#define DEB_ERRC(e, w) { double y0v = W.y[e], y1v = anynan ? y0v : W.u[e], ev = W.r[e]; if (ev != ev) ev = INFINITY; \
+#define DEB_ERRC(e, w) { double y0v = W.y()[e], y1v = anynan ? y0v : W.u()[e], ev = W.r()[e]; if (ev != ev) ev = INFINITY; \
         double sc = ev / (P.atol + fmax(fabs(y0v), fabs(y1v)) * P.rtol) * (w); errnorm2 += sc * sc; }
       DEB_ERRC(0, 1.0) DEB_ERRC(2, k2) DEB_ERRC(3, 1.0) DEB_ERRC(5, 1.0) DEB_ERRC(6, ik2) DEB_ERRC(7, 1.0)
 #undef DEB_ERRC
@@ -1152,15 +1190,15 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
         const size_t obase = ((size_t)mode * P.nout + save_idx);
         if (P.return_full) {
           DEB_LANES_BEGIN
-            for (int e = lane; e < n; e += 32) P.y_out[obase * n + e] = W.y[e] + coeff * (W.u[e] - W.y[e]);
+            for (int e = lane; e < n; e += 32) P.y_out[obase * n + e] = W.y()[e] + coeff * (W.u()[e] - W.y()[e]);
           DEB_LANES_END
         } else {
           DEB_LANES_BEGIN
-            for (int e = lane; e < n; e += 32) W.r[e] = W.y[e] + coeff * (W.u[e] - W.y[e]);
+            for (int e = lane; e < n; e += 32) W.r()[e] = W.y()[e] + coeff * (W.u()[e] - W.y()[e]);
           DEB_LANES_END
           DEB_LANE0_BEGIN
             double o20[20];
-            convert_outputs(P, c, nb, W.r, k, o20);
+            convert_outputs(P, c, nb, W.r(), k, o20);
             for (int q = 0; q < 20; ++q) P.y_out[obase * 20 + q] = o20[q];
             if (P.pk_out && P.power_idx >= 0) {
               double yv = o20[P.power_idx];
@@ -1171,7 +1209,7 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
         ++save_idx;
       }
       DEB_LANES_BEGIN
-        for (int e = lane; e < n; e += 32) W.y[e] = W.u[e];
+        DEB_FOR_OWN(W.y()[e] = W.u()[e];)
       DEB_LANES_END
       inv_pprev = inv_prev; inv_prev = inv;
       t = fmin(tnext, t1);

@@ -37,8 +37,11 @@ static __host__ __device__ size_t cta_smem_bytes(int np) {
   return b;
 }
 
+// resident warps per SM the register allocation must allow: the 7 stage vectors take 14 NE registers per lane
+template <int NE> struct MinBlocks { static constexpr int v = 1; };   // 255 registers: tighter bounds spill the Jacobian phase (measured slower)
+
 template <int NE>
-__global__ void __launch_bounds__(32, 1) k_evolve(const __grid_constant__ Problem P) {
+__global__ void __launch_bounds__(32, MinBlocks<NE>::v) k_evolve(const __grid_constant__ Problem P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CtaConst* C = reinterpret_cast<CtaConst*>(smem_raw);
   size_t off = (sizeof(CtaConst) + 15) & ~(size_t)15;
