@@ -64,12 +64,18 @@ enum { T_CS2A = 0, T_XE, T_LRHONU, T_LPNU, T_A_OF_TAU, T_XE_OF_TAU, T_TAU_OF_A, 
 constexpr int NQMAX = 5;          // head must fit one lane per row: 17 + 3 nq <= 32
 constexpr int NHMAX = 32;
 constexpr int NCHMAX = 3 + NQMAX;
-constexpr int LMAXCAP = 96;
+constexpr int LMAXCAP = 64;
+constexpr int HOP_NT = 5;        // local couplings per head row (max: F2, G2)
+constexpr int NSLOT = 12 + NQMAX; // background scalars the head rows are built from (see HeadOp)
 constexpr int LDH = 33;           // odd leading dimension: conflict-free column access
 
 // row types (element descriptors)
 enum RowType : int { R_A = 0, R_AHP, R_ETA, R_DC, R_TC, R_DB, R_TB, R_F0, R_F1, R_F2, R_G0, R_G1, R_G2,
                      R_N0, R_N1, R_N2, R_P0, R_P1, R_P2, R_DQ, R_TQ, R_GEN, R_TRUNC };
+
+// background-scalar slots of the head operator
+enum Slot : int { SL_ONE = 0, SL_H, SL_OPAC, SL_PBO, SL_K2CS2, SL_WQ1, SL_DQD, SL_DQT, SL_TQD, SL_TQT, SL_K, SL_K2, SL_KV0 };
+// SL_DQD = (cs2_Q - w_Q) H   SL_DQT = (1+w_Q)(cs2_Q - ca2_Q) H^2/k^2   SL_TQD = cs2_Q k^2/(1+w_Q)   SL_TQT = (1 - 3 cs2_Q) H
 
 // Rodas5 coefficients, transformed form (ode_integrators_stiff.py:622-687)
 #define RD_GAMMA 0.19
@@ -248,7 +254,13 @@ struct CtaConst {
   int ch_stride[NCHMAX];
   int ch_lmax[NCHMAX];
   int ch_h2[NCHMAX];      // chain -> head position of its l=2 element
-  const int* desc;        // element -> type | ell<<8 | chain<<16   [np] (dynamic shared memory)
+  // head operator: row r of the RHS restricted to the head is
+  //   f_r = sum_t hop_c[t][r] * S[hop_slot] * y[hop_col]  +  hop_chc[r] * S[hop_chs[r]] * h'  +  hop_cec[r] * eta'
+  // with S the per-evaluation background scalars (slots below); the same table assembles W_h.
+  double hop_c[HOP_NT][NHMAX];
+  double hop_chc[NHMAX], hop_cec[NHMAX];
+  int hop_meta[HOP_NT][NHMAX];   // slot | state index << 8 | (head column + 1) << 20   (0 = unused term)
+  int hop_chs[NHMAX];
   const int* tail;        // tail entry -> element | chain<<12 | ell<<16, elements ascending   [np]
   int ntail;              // number of hierarchy rows with l >= 3
 };
@@ -291,8 +303,7 @@ DEB_DEV int elem_desc(const Problem& P, int e) {
   return type | (l << 8) | (chain << 16);
 }
 
-DEB_DEV void init_cta_const(const Problem& P, CtaConst& C, int* desc, int* tail, int tid, int nthreads) {
-  for (int e = tid; e < P.np; e += nthreads) desc[e] = elem_desc(P, e);
+DEB_DEV void init_cta_const(const Problem& P, CtaConst& C, int* tail, int tid, int nthreads) {
   if (tid == 0) {
     int nt = 0;
     for (int e = 0; e < P.n; ++e) {
@@ -306,7 +317,6 @@ DEB_DEV void init_cta_const(const Problem& P, CtaConst& C, int* desc, int* tail,
     C.ch[l] = (double)(l + 1) / (double)(2 * l + 1);
   }
   if (tid == 0) {
-    C.desc = desc;
     const int nq = P.nq;
     const double q3[3] = {0.913201, 3.37517, 7.79184}, k3[3] = {0.0687359, 3.31435, 2.29911};
     const double q4[4] = {0.7, 2.62814, 5.90428, 12.0}, k4[4] = {0.0200251, 1.84539, 3.52736, 0.289427};
@@ -330,6 +340,46 @@ DEB_DEV void init_cta_const(const Problem& P, CtaConst& C, int* desc, int* tail,
     for (int l = 0; l < 3; ++l)
       for (int i = 0; i < nq; ++i) { put(P.iq0 + l * nq + i, R_P0 + l, i); if (l == 2) C.ch_h2[3 + i] = h - 1; }
     put(P.n - 2, R_DQ, 0); put(P.n - 1, R_TQ, 0); put(1, R_AHP, 0);
+    // ---- head operator (perturbations.py:259-369 restricted to the l <= 2 rows) ----
+    for (int r = 0; r < NHMAX; ++r) {
+      for (int t = 0; t < HOP_NT; ++t) { C.hop_c[t][r] = 0.0; C.hop_meta[t][r] = 0; }
+      C.hop_chc[r] = 0.0; C.hop_cec[r] = 0.0; C.hop_chs[r] = SL_ONE;
+    }
+    auto hpos = [&](int e) { for (int q = 0; q < h; ++q) if (C.hidx[q] == e) return q; return -1; };
+    for (int r = 0; r < h; ++r) {
+      int nt = 0;
+      auto term = [&](double cst, int slot, int e) {
+        C.hop_c[nt][r] = cst; C.hop_meta[nt][r] = slot | (e << 8) | ((hpos(e) + 1) << 20); ++nt;
+      };
+      const int e = C.hidx[r], ty = C.htype[r], bin = C.hbin[r];
+      const int ig = P.ig, igp = P.igp, ir = P.ir;
+      switch (ty) {
+        case R_ETA: C.hop_cec[r] = 1.0; break;
+        case R_DC: term(-1.0, SL_ONE, 4); C.hop_chc[r] = -0.5; break;
+        case R_TC: term(-1.0, SL_H, 4); break;
+        case R_DB: term(-1.0, SL_ONE, 6); C.hop_chc[r] = -0.5; break;
+        case R_TB: term(-1.0, SL_H, 6); term(1.0, SL_K2CS2, 5); term(1.0, SL_PBO, 8); term(-1.0, SL_PBO, 6); break;
+        case R_F0: term(-4.0 / 3.0, SL_ONE, ig + 1); C.hop_chc[r] = -2.0 / 3.0; break;
+        case R_F1: term(0.25, SL_K2, ig); term(-0.5, SL_K2, ig + 2); term(-1.0, SL_OPAC, ig + 1); term(1.0, SL_OPAC, 6); break;
+        case R_F2: term(8.0 / 15.0, SL_ONE, ig + 1); term(-0.6, SL_K, ig + 3); term(-0.9, SL_OPAC, ig + 2);
+                   term(0.1, SL_OPAC, igp); term(0.1, SL_OPAC, igp + 2); C.hop_chc[r] = 4.0 / 15.0; C.hop_cec[r] = 1.6; break;
+        case R_G0: term(-1.0, SL_K, igp + 1); term(-0.5, SL_OPAC, igp); term(0.5, SL_OPAC, ig + 2); term(0.5, SL_OPAC, igp + 2); break;
+        case R_G1: term(1.0 / 3.0, SL_K, igp); term(-2.0 / 3.0, SL_K, igp + 2); term(-1.0, SL_OPAC, igp + 1); break;
+        case R_G2: term(0.4, SL_K, igp + 1); term(-0.6, SL_K, igp + 3); term(-0.9, SL_OPAC, igp + 2);
+                   term(0.1, SL_OPAC, ig + 2); term(0.1, SL_OPAC, igp); break;
+        case R_N0: term(-4.0 / 3.0, SL_ONE, ir + 1); C.hop_chc[r] = -2.0 / 3.0; break;
+        case R_N1: term(0.25, SL_K2, ir); term(-0.5, SL_K2, ir + 2); break;
+        case R_N2: term(8.0 / 15.0, SL_ONE, ir + 1); term(-0.6, SL_K, ir + 3); C.hop_chc[r] = 4.0 / 15.0; C.hop_cec[r] = 1.6; break;
+        case R_P0: term(-1.0, SL_KV0 + bin, e + nq); C.hop_chc[r] = C.nu.dl[bin] / 6.0; break;
+        case R_P1: term(1.0 / 3.0, SL_KV0 + bin, e - nq); term(-2.0 / 3.0, SL_KV0 + bin, e + nq); break;
+        case R_P2: term(0.4, SL_KV0 + bin, e - nq); term(-0.6, SL_KV0 + bin, e + nq);
+                   C.hop_chc[r] = -C.nu.dl[bin] / 15.0; C.hop_cec[r] = -0.4 * C.nu.dl[bin]; break;
+        case R_DQ: term(-1.0, SL_WQ1, P.n - 1); term(-3.0, SL_DQD, P.n - 2); term(-9.0, SL_DQT, P.n - 1);
+                   C.hop_chc[r] = -0.5; C.hop_chs[r] = SL_WQ1; break;
+        case R_TQ: term(-1.0, SL_TQT, P.n - 1); term(1.0, SL_TQD, P.n - 2); break;
+        default: break;      // R_AHP: f = mt.f1, dense Jacobian row j1
+      }
+    }
     C.ch_base[0] = P.ig;  C.ch_stride[0] = 1; C.ch_lmax[0] = P.lmaxg;
     C.ch_base[1] = P.igp; C.ch_stride[1] = 1; C.ch_lmax[1] = P.lmaxgp;
     C.ch_base[2] = P.ir;  C.ch_stride[2] = 1; C.ch_lmax[2] = P.lmaxr;
@@ -381,6 +431,7 @@ struct WarpWs {
   double* kap_;   // chain damping opac or 0 (value, d/da) [2*NCHMAX]
   double* nur_;   // w_i psi0_i / v_i (value, d/da) [2*NQMAX]
   double* nup_;   // w_i psi0_i v_i (value, d/da) [2*NQMAX]
+  double* sl_;   // background-scalar slots of the head operator (value, d/da) [2*NSLOT]
   int* perm_;    // pivot row of elimination step j [NHMAX]
   Cosmo* cosmo_; // per-mode constants and table pointers
   DEB_DEV double* y() const { return y_; }
@@ -398,18 +449,20 @@ struct WarpWs {
   DEB_DEV double* kap() const { return kap_; }
   DEB_DEV double* nur() const { return nur_; }
   DEB_DEV double* nup() const { return nup_; }
+  DEB_DEV double* sl() const { return sl_; }
   DEB_DEV int* perm() const { return perm_; }
   DEB_DEV Cosmo* cosmo() const { return cosmo_; }
 };
 DEB_HD size_t warp_ws_doubles(int np) {
-  return (size_t)7 * np + NHMAX * LDH + 3 * NHMAX + 4 * NCHMAX + 4 * NQMAX + NHMAX / 2 + 2 + (sizeof(Cosmo) + 7) / 8;
+  return (size_t)7 * np + NHMAX * LDH + 3 * NHMAX + 4 * NCHMAX + 4 * NQMAX + 2 * NSLOT + NHMAX / 2 + 2 + (sizeof(Cosmo) + 7) / 8;
 }
 DEB_DEV void carve(WarpWs& W, double* base, int np) {
   W.y_ = base; W.u_ = W.y_ + np; W.r_ = W.u_ + np; W.m_ = W.r_ + np; W.ie_ = W.m_ + np; W.g_ = W.ie_ + np; W.ja_ = W.g_ + np;
   W.lu_ = W.ja_ + np; W.gh_ = W.lu_ + NHMAX * LDH; W.ge_ = W.gh_ + NHMAX; W.j1_ = W.ge_ + NHMAX;
   W.kc_ = W.j1_ + NHMAX; W.kap_ = W.kc_ + 2 * NCHMAX; W.nur_ = W.kap_ + 2 * NCHMAX; W.nup_ = W.nur_ + 2 * NQMAX;
-  W.perm_ = (int*)(W.nup_ + 2 * NQMAX);
-  W.cosmo_ = (Cosmo*)(W.nup_ + 2 * NQMAX + NHMAX / 2 + 2);
+  W.sl_ = W.nup_ + 2 * NQMAX;
+  W.perm_ = (int*)(W.sl_ + 2 * NSLOT);
+  W.cosmo_ = (Cosmo*)(W.sl_ + 2 * NSLOT + NHMAX / 2 + 2);
 }
 
 // background coefficients at scale factor a (perturbations.py:176-218, background.py:110-121)
@@ -475,7 +528,7 @@ DEB_DEV void compute_bg(const Cosmo& c, const NuBins& nb, int nq, T a, Hints& hi
 // photon chains); executed by lane `ch` < nch.  Layout [value x NCHMAX | d/da x NCHMAX].
 template <class T>
 DEB_DEV void chain_coeffs_lane(const Cosmo& c, const NuBins& nb, const Bg<T>& b, double k, int ch, const double* u, int iq0,
-                               double* kcA, double* kapA, double* nurA, double* nupA) {
+                               double* kcA, double* kapA, double* nurA, double* nupA, double* sl) {
   T kc = 0.0 * b.a + k;
   if (ch >= 3) {
     const int i = ch - 3;
@@ -488,6 +541,7 @@ DEB_DEV void chain_coeffs_lane(const Cosmo& c, const NuBins& nb, const Bg<T>& b,
     T tr = iv * wp0, tp = v * wp0;            // terms of drhonu and 3 dpnu (nu_perturb, perturbations.py:45-46)
     nurA[i] = val(tr); nurA[NQMAX + i] = der(tr);
     nupA[i] = val(tp); nupA[NQMAX + i] = der(tp);
+    sl[SL_KV0 + i] = val(kc); sl[NSLOT + SL_KV0 + i] = der(kc);
   }
   T kp = ch < 2 ? b.opac : 0.0 * b.a;
   kcA[ch] = val(kc); kcA[NCHMAX + ch] = der(kc);
@@ -530,60 +584,35 @@ DEB_DEV void compute_metric(const Problem& P, const Cosmo& c, const NuBins& nb, 
   mt.al = (mt.hp + 6.0 * mt.ep) * (0.5 * ik2);
 }
 
-// one row of the right-hand side (perturbations.py:226-369).  kc/kap are the chain arrays with
-// layout [value x NCHMAX | d/da x NCHMAX]; the dual instantiation returns d f_e / d a in .d
-
+// background-scalar slots (lane 0) -- what the head rows and the head matrix are built from
 template <class T>
-DEB_DEV T rhs_row(const Problem& P, const Cosmo& c, const CtaConst& C, const Bg<T>& b, const Metric<T>& mt,
-                  const double* kcA, const double* kapA, const double* u, int e, int desc, double k, double invtau) {
-  const int type = desc & 0xff, l = (desc >> 8) & 0xff, chain = desc >> 16;
+DEB_DEV void fill_slots(const Cosmo& c, const Bg<T>& b, double k, double* sl) {
   const double k2 = k * k;
-  switch (type) {
-    case R_A: return b.H * b.a;
-    case R_AHP: return mt.f1;
-    case R_ETA: return mt.ep;
-    case R_DC: return -0.5 * mt.hp - u[4];
-    case R_TC: return -(b.H * u[4]);
-    case R_DB: return -0.5 * mt.hp - u[6];
-    case R_TB: return -(b.H * u[6]) + (k2 * u[5]) * b.cs2 + b.pbo * (u[8] - u[6]);
-    case R_F0: return -2.0 / 3.0 * mt.hp - 4.0 / 3.0 * u[8];
-    case R_F1: return -(b.opac * (u[8] - u[6])) + k2 * (0.25 * u[7] - 0.5 * u[9]);
-    case R_F2: {
-      double polter = u[9] + u[P.igp] + u[P.igp + 2];
-      return 8.0 / 15.0 * (k2 * mt.al) - b.opac * (u[9] - 0.1 * polter) + (8.0 / 15.0 * u[8] - 0.6 * k * u[10]);
-    }
-    case R_N0: return -2.0 / 3.0 * mt.hp - 4.0 / 3.0 * u[P.ir + 1];
-    case R_N1: { T z = 0.0 * b.a; return z + k2 * (0.25 * u[P.ir] - 0.5 * u[P.ir + 2]); }
-    case R_N2: return 8.0 / 15.0 * (k2 * mt.al) + (8.0 / 15.0 * u[P.ir + 1] - 0.6 * k * u[P.ir + 3]);
-    case R_DQ: {
-      double dq = u[P.n - 2], tq = u[P.n - 1];
-      return -(b.wq1 * (tq + 0.5 * mt.hp)) - 3.0 * (c.cs2de - b.wq) * b.H * dq
-           - 9.0 * b.wq1 * (c.cs2de - b.ca2) * (b.H * b.H) * (tq / k2);
-    }
-    case R_TQ: {
-      double dq = u[P.n - 2], tq = u[P.n - 1];
-      return -((1.0 - 3.0 * c.cs2de) * tq) * b.H + (c.cs2de * k2 * dq) / b.wq1;
-    }
-    default: break;
+  T one = 0.0 * b.a + 1.0;
+  T s[SL_KV0];
+  s[SL_ONE] = one; s[SL_H] = b.H; s[SL_OPAC] = b.opac; s[SL_PBO] = b.pbo; s[SL_K2CS2] = k2 * b.cs2; s[SL_WQ1] = b.wq1;
+  s[SL_DQD] = (c.cs2de - b.wq) * b.H;
+  s[SL_DQT] = b.wq1 * (c.cs2de - b.ca2) * (b.H * b.H) * (1.0 / k2);
+  s[SL_TQD] = (c.cs2de * k2) / b.wq1;
+  s[SL_TQT] = (1.0 - 3.0 * c.cs2de) * b.H;
+  s[SL_K] = one * k; s[SL_K2] = one * k2;
+#pragma unroll
+  for (int i = 0; i < SL_KV0; ++i) { sl[i] = val(s[i]); sl[NSLOT + i] = der(s[i]); }
+}
+template <class T> DEB_DEV T picks(const double* sl, int i);
+template <> DEB_DEV double picks<double>(const double* sl, int i) { return sl[i]; }
+template <> DEB_DEV Dual picks<Dual>(const double* sl, int i) { return mk(sl[i], sl[NSLOT + i]); }
+
+// head row r of the right-hand side from the operator table (branch-free, one lane per row)
+template <class T>
+DEB_DEV T head_row(const CtaConst& C, const double* sl, const double* u, int r, const Metric<T>& mt) {
+  T f = (C.hop_chc[r] * picks<T>(sl, C.hop_chs[r])) * mt.hp + C.hop_cec[r] * mt.ep;
+#pragma unroll
+  for (int t = 0; t < HOP_NT; ++t) {
+    const int m = C.hop_meta[t][r];
+    f = f + (C.hop_c[t][r] * u[(m >> 8) & 0xfff]) * picks<T>(sl, m & 0xff);
   }
-  // hierarchy rows: generic three-term recurrence (+ extras for l = 0, 2 of G and psi)
-  const int s = C.ch_stride[chain];
-  T kcv = pick<T>(kcA, chain), kpv = pick<T>(kapA, chain);
-  if (type == R_TRUNC) {
-    int L = C.ch_lmax[chain];
-    return kcv * u[e - s] - (kpv + (double)(L + 1) * invtau) * u[e];
-  }
-  double lin = C.cl[l] * (l > 0 ? u[e - s] : 0.0) - C.ch[l] * u[e + s];
-  T f = kcv * lin - kpv * u[e];
-  if (type == R_G0 || type == R_G2) {
-    double polter = u[9] + u[P.igp] + u[P.igp + 2];
-    f = f + b.opac * (polter * (type == R_G0 ? 0.5 : 0.1));
-  } else if (type == R_P0) {
-    f = f + mt.hp * (C.nu.dl[chain - 3] / 6.0);
-  } else if (type == R_P2) {
-    f = f - (mt.hp / 15.0 + 0.4 * mt.ep) * C.nu.dl[chain - 3];
-  }
-  return f;
+  return C.htype[r] == R_AHP ? mt.f1 : f;
 }
 
 // hierarchy rows with l >= 3 (perturbations.py:300-303, :307-312, :323-327, :346-360), branch-free: the
@@ -764,7 +793,6 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
   DEB_REGS(double, rscale, );      // head inverse: 1/pivot of this lane's row
   DEB_REGS(unsigned, pkey, );
   DEB_REGS(int, nanflag, );
-  const int* desc = C.desc;
 
   // ---- prologue ----
   double t1 = DEB_LDG(tout);
@@ -780,7 +808,7 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
     double tau_start = 0.99 * fmin(tmin_out, start_time(c, k));
     IcScalars ics = ic_scalars(c, tau_start, k);
     DEB_LANES_BEGIN
-      for (int e = lane; e < n; e += 32) W.y()[e] = ic_value(P, c, nb, ics, desc[e], k);
+      for (int e = lane; e < n; e += 32) W.y()[e] = ic_value(P, c, nb, ics, elem_desc(P, e), k);
     DEB_LANES_END
     if (P.mode == 2) {
       DEB_LANES_BEGIN
@@ -817,7 +845,8 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
       Bg<Dual> bd;
       compute_bg<Dual>(c, nb, nq, mk(W.y()[0], 1.0), hint, bd);
       DEB_LANES_BEGIN
-        if (lane < nch) chain_coeffs_lane<Dual>(c, nb, bd, k, lane, W.y(), P.iq0, W.kc(), W.kap(), W.nur(), W.nup());
+        if (lane < nch) chain_coeffs_lane<Dual>(c, nb, bd, k, lane, W.y(), P.iq0, W.kc(), W.kap(), W.nur(), W.nup(), W.sl());
+        if (lane == 0) fill_slots<Dual>(c, bd, k, W.sl());
       DEB_LANES_END
       Metric<Dual> md;
       compute_metric<Dual>(P, c, nb, bd, W.y(), k, W.nur(), W.nup(), md);
@@ -825,7 +854,7 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
       DEB_LANES_BEGIN
         if (lane < nh) {                      // head rows: one lane per row
           const int e = C.hidx[lane];
-          Dual f = rhs_row<Dual>(P, c, C, bd, md, W.kc(), W.kap(), W.y(), e, desc[e], k, invt0);
+          Dual f = head_row<Dual>(C, W.sl(), W.y(), lane, md);
           W.r()[e] = f.v; W.ja()[e] = f.d;
         }
         if (lane == 0) { Dual f = bd.H * bd.a; W.r()[0] = f.v; W.ja()[0] = f.d; }
@@ -897,22 +926,12 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
         }
       DEB_LANES_END
 
-      // ---- head matrix  W_h = I/(gamma dt) - J_h  (one lane per row) ----
+      // ---- head matrix  W_h = I/(gamma dt) - J_h  (one lane per row, from the operator table) ----
       DEB_LANES_BEGIN
         if (lane < nh) {
-          const int ty = C.htype[lane], bin = C.hbin[lane];
+          const int ty = C.htype[lane];
           double* row = W.lu() + lane * LDH;
-          double chh = 0.0, cee = 0.0;
-          switch (ty) {
-            case R_ETA: cee = 1.0; break;
-            case R_DC: case R_DB: chh = -0.5; break;
-            case R_F0: case R_N0: chh = -2.0 / 3.0; break;
-            case R_F2: case R_N2: chh = 4.0 / 15.0; cee = 1.6; break;
-            case R_P0: chh = nb.dl[bin] / 6.0; break;
-            case R_P2: chh = -nb.dl[bin] / 15.0; cee = -0.4 * nb.dl[bin]; break;
-            case R_DQ: chh = -0.5 * bd.wq1.v; break;
-            default: break;
-          }
+          const double chh = C.hop_chc[lane] * W.sl()[C.hop_chs[lane]], cee = C.hop_cec[lane];
           for (int c0 = 0; c0 < nh; c0 += 8) {
             double ga[8], gb[8], gc[8];
 #pragma unroll
@@ -920,36 +939,17 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
 #pragma unroll
             for (int i = 0; i < 8; ++i) row[c0 + i] = (ty == R_AHP) ? -gc[i] : -(chh * ga[i] + cee * gb[i]);
           }
-          row[lane] += idg;
-          // local couplings; head positions: 0 eta,1 dc,2 tc,3 db,4 tb,5-7 F,8-10 G,11-13 N,14.. psi, then dq,tq,ahp
-          const double op = bd.opac.v, pbo = bd.pbo.v;
-          const int hF = 5, hG = 8, hN = 11, hP = 14, hQ = 14 + 3 * nq;
-          switch (ty) {
-            case R_DC: row[2] -= -1.0; break;
-            case R_TC: row[2] -= -H; break;
-            case R_DB: row[4] -= -1.0; break;
-            case R_TB: row[4] -= -H - pbo; row[3] -= k2 * bd.cs2.v; row[hF + 1] -= pbo; break;
-            case R_F0: row[hF + 1] -= -4.0 / 3.0; break;
-            case R_F1: row[hF] -= 0.25 * k2; row[hF + 2] -= -0.5 * k2; row[hF + 1] -= -op; row[4] -= op; break;
-            case R_F2: row[hF + 1] -= 8.0 / 15.0; row[hF + 2] -= -0.9 * op; row[hG] -= 0.1 * op; row[hG + 2] -= 0.1 * op; break;
-            case R_G0: row[hG + 1] -= -k; row[hG] -= -0.5 * op; row[hF + 2] -= 0.5 * op; row[hG + 2] -= 0.5 * op; break;
-            case R_G1: row[hG] -= k / 3.0; row[hG + 2] -= -2.0 * k / 3.0; row[hG + 1] -= -op; break;
-            case R_G2: row[hG + 1] -= 0.4 * k; row[hG + 2] -= -0.9 * op; row[hF + 2] -= 0.1 * op; row[hG] -= 0.1 * op; break;
-            case R_N0: row[hN + 1] -= -4.0 / 3.0; break;
-            case R_N1: row[hN] -= 0.25 * k2; row[hN + 2] -= -0.5 * k2; break;
-            case R_N2: row[hN + 1] -= 8.0 / 15.0; break;
-            case R_P0: row[hP + nq + bin] -= -W.kc()[3 + bin]; break;
-            case R_P1: row[hP + bin] -= W.kc()[3 + bin] / 3.0; row[hP + 2 * nq + bin] -= -2.0 * W.kc()[3 + bin] / 3.0; break;
-            case R_P2: row[hP + nq + bin] -= 0.4 * W.kc()[3 + bin]; break;
-            case R_DQ: row[hQ + 1] -= -bd.wq1.v - 9.0 * bd.wq1.v * (c.cs2de - bd.ca2.v) * H * H / k2;
-                       row[hQ] -= -3.0 * (c.cs2de - bd.wq.v) * H; break;
-            case R_TQ: row[hQ + 1] -= -(1.0 - 3.0 * c.cs2de) * H; row[hQ] -= c.cs2de * k2 / bd.wq1.v; break;
-            default: break;
-          }
+          double diag = idg;
           // Schur complement of the chain tail on the l=2 diagonal
           if (ty == R_F2 || ty == R_G2 || ty == R_N2 || ty == R_P2) {
-            int chain = ty == R_F2 ? 0 : (ty == R_G2 ? 1 : (ty == R_N2 ? 2 : 3 + bin));
-            row[lane] += W.ie()[C.ch_base[chain] + 2 * C.ch_stride[chain]];
+            const int chain = ty == R_F2 ? 0 : (ty == R_G2 ? 1 : (ty == R_N2 ? 2 : 3 + C.hbin[lane]));
+            diag += W.ie()[C.ch_base[chain] + 2 * C.ch_stride[chain]];
+          }
+          row[lane] += diag;
+#pragma unroll
+          for (int t = 0; t < HOP_NT; ++t) {             // local couplings (columns inside the head)
+            const int m = C.hop_meta[t][lane], hc = (m >> 20) - 1;
+            if (hc >= 0) row[hc] -= C.hop_c[t][lane] * W.sl()[m & 0xff];
           }
         }
       DEB_LANES_END
@@ -1031,7 +1031,8 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
         Bg<double> b;
         compute_bg<double>(c, nb, nq, W.u()[0], hint, b);
         DEB_LANES_BEGIN
-          if (lane < nch) chain_coeffs_lane<double>(c, nb, b, k, lane, W.u(), P.iq0, W.kc(), W.kap(), W.nur(), W.nup());
+          if (lane < nch) chain_coeffs_lane<double>(c, nb, b, k, lane, W.u(), P.iq0, W.kc(), W.kap(), W.nur(), W.nup(), W.sl());
+          if (lane == 0) fill_slots<double>(c, b, k, W.sl());
         DEB_LANES_END
         Metric<double> mt;
         compute_metric<double>(P, c, nb, b, W.u(), k, W.nur(), W.nup(), mt);
@@ -1051,7 +1052,7 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
         DEB_LANES_BEGIN      // rows are distributed differently from the register-resident k's: new phase
           if (lane < nh) {
             const int e = C.hidx[lane];
-            W.r()[e] += rhs_row<double>(P, c, C, b, mt, W.kc(), W.kap(), W.u(), e, desc[e], k, invts);
+            W.r()[e] += head_row<double>(C, W.sl(), W.u(), lane, mt);
           }
           if (lane == 0) W.r()[0] += b.H * b.a;
           const double dtt = dtd * invt0 * invt0;
@@ -1080,6 +1081,7 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
           double bp = *rp;
           rp -= s; mp -= s;
           double rn = *rp, mn = *mp;
+#pragma unroll 4
           for (int l = L - 1; l > 2; --l) {
             const double rc = rn, mc = mn;
             rn = *(rp - s); mn = *(mp - s);
@@ -1117,6 +1119,7 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
           double x = *rp;
           rp += s; ip += s; gp += s;
           double cn = *rp * *ip, gn = *gp;
+#pragma unroll 4
           for (int l = 3; l < L; ++l) {
             const double cc = cn, gc = gn;
             cn = *(rp + s) * *(ip + s); gn = *(gp + s);

@@ -31,7 +31,7 @@ __global__ void k_tau_out(Problem P, double* tau_out) {
 static __host__ __device__ size_t cta_smem_bytes(int np) {
   size_t b = sizeof(CtaConst);
   b = (b + 15) & ~(size_t)15;
-  b += (size_t)2 * np * sizeof(int);
+  b += (size_t)np * sizeof(int);
   b = (b + 15) & ~(size_t)15;
   b += warp_ws_doubles(np) * sizeof(double);
   return b;
@@ -45,12 +45,11 @@ __global__ void __launch_bounds__(32, MinBlocks<NE>::v) k_evolve(const __grid_co
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CtaConst* C = reinterpret_cast<CtaConst*>(smem_raw);
   size_t off = (sizeof(CtaConst) + 15) & ~(size_t)15;
-  int* desc = reinterpret_cast<int*>(smem_raw + off);
-  int* tail = desc + P.np;
-  off = (off + (size_t)2 * P.np * sizeof(int) + 15) & ~(size_t)15;
+  int* tail = reinterpret_cast<int*>(smem_raw + off);
+  off = (off + (size_t)P.np * sizeof(int) + 15) & ~(size_t)15;
   double* wsb = reinterpret_cast<double*>(smem_raw + off);
   const int lane = threadIdx.x & 31;
-  init_cta_const(P, *C, desc, tail, lane, 32);
+  init_cta_const(P, *C, tail, lane, 32);
   __syncwarp();
   WarpWs W;
   carve(W, wsb, P.np);

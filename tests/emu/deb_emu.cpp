@@ -23,8 +23,8 @@ static void tau_out_host(const Problem& P, double* tau_out) {
 template <int NE>
 static void run_all(const Problem& P) {
   CtaConst C;
-  std::vector<int> desc(P.np), tail(P.np);
-  for (int t = 0; t < 32; ++t) init_cta_const(P, C, desc.data(), tail.data(), t, 32);
+  std::vector<int> tail(P.np);
+  for (int t = 0; t < 32; ++t) init_cta_const(P, C, tail.data(), t, 32);
   std::vector<double> ws(warp_ws_doubles(P.np));
   const int total = P.ncosmo * P.nk;
 #pragma omp parallel for schedule(dynamic, 1) firstprivate(ws)
