@@ -67,7 +67,7 @@ constexpr int NCHMAX = 3 + NQMAX;
 constexpr int LMAXCAP = 64;
 constexpr int HOP_NT = 5;        // local couplings per head row (max: F2, G2)
 constexpr int NSLOT = 12 + NQMAX; // background scalars the head rows are built from (see HeadOp)
-constexpr int LDH = 33;           // odd leading dimension: conflict-free column access
+constexpr int LDH = 34;           // 16-byte aligned rows; 128-bit row accesses are conflict-free per quarter-warp
 
 // row types (element descriptors)
 enum RowType : int { R_A = 0, R_AHP, R_ETA, R_DC, R_TC, R_DB, R_TB, R_F0, R_F1, R_F2, R_G0, R_G1, R_G2,
@@ -138,6 +138,7 @@ enum Slot : int { SL_ONE = 0, SL_H, SL_OPAC, SL_PBO, SL_K2CS2, SL_WQ1, SL_DQD, S
 // ---------------------------------------------------------------------------------------------
 // forward dual number (value, d/da): the seed is the scale factor y[0]
 // ---------------------------------------------------------------------------------------------
+struct alignas(16) D2 { double x, y; };   // one 128-bit shared-memory access
 struct Dual { double v, d; };
 DEB_DEV Dual mk(double v, double d) { Dual r; r.v = v; r.d = d; return r; }
 DEB_DEV Dual operator+(Dual a, Dual b) { return mk(a.v + b.v, a.d + b.d); }
@@ -937,7 +938,7 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
 #pragma unroll
             for (int i = 0; i < 8; ++i) { ga[i] = W.gh()[c0 + i]; gb[i] = W.ge()[c0 + i]; gc[i] = W.j1()[c0 + i]; }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) row[c0 + i] = (ty == R_AHP) ? -gc[i] : -(chh * ga[i] + cee * gb[i]);
+            for (int i = 0; i < 8; ++i) row[c0 + i] = (c0 + i >= nh) ? 0.0 : ((ty == R_AHP) ? -gc[i] : -(chh * ga[i] + cee * gb[i]));
           }
           double diag = idg;
           // Schur complement of the chain tail on the l=2 diagonal
@@ -976,15 +977,15 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
         double* row = W.lu() + lane * LDH;
         if (lane == piv) { pcol = j; rscale = ipv; W.perm()[j] = piv; row[j] = 1.0; }
         else if (lane < nh) {
-          const double* prow = W.lu() + piv * LDH;
+          const D2* prow = reinterpret_cast<const D2*>(W.lu() + piv * LDH);
           const double f = row[j] * ipv;
-          double* rp = row;
-          for (int c0 = 0; c0 < nh; c0 += 8, rp += 8, prow += 8) {   // 8 columns per trip: loads, then FMAs, then stores
-            double ra[8], pa[8];
+          D2* rp = reinterpret_cast<D2*>(row);
+          for (int c0 = 0; c0 < nh; c0 += 8, rp += 4, prow += 4) {   // 8 columns per trip as four 128-bit accesses
+            D2 ra[4], pa[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { ra[i] = rp[i]; pa[i] = prow[i]; }
+            for (int i = 0; i < 4; ++i) { ra[i] = rp[i]; pa[i] = prow[i]; }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) rp[i] = ra[i] - f * pa[i];
+            for (int i = 0; i < 4; ++i) { ra[i].x -= f * pa[i].x; ra[i].y -= f * pa[i].y; rp[i] = ra[i]; }
           }
           row[j] = -f;
         }
@@ -993,13 +994,13 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
     DEB_LANES_BEGIN
       DEB_USE(rscale);
       if (lane < nh) {
-        double* row = W.lu() + lane * LDH;
-        for (int c0 = 0; c0 < nh; c0 += 8) {
-          double ra[8];
+        D2* rp = reinterpret_cast<D2*>(W.lu() + lane * LDH);
+        for (int c0 = 0; c0 < nh; c0 += 8, rp += 4) {
+          D2 ra[4];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) ra[i] = row[c0 + i];
+          for (int i = 0; i < 4; ++i) ra[i] = rp[i];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) row[c0 + i] = ra[i] * rscale;
+          for (int i = 0; i < 4; ++i) { ra[i].x *= rscale; ra[i].y *= rscale; rp[i] = ra[i]; }
         }
       }
     DEB_LANES_END
@@ -1094,18 +1095,21 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
       DEB_LANES_END
       // head: x_h = S (P b) with the explicit inverse; lane j gathers b[perm[j]], lane r forms row r of S b
       DEB_LANES_BEGIN
-        if (lane < nh) W.gh()[lane] = W.r()[C.hidx[W.perm()[lane]]];
+        W.gh()[lane] = lane < nh ? W.r()[C.hidx[W.perm()[lane]]] : 0.0;
       DEB_LANES_END
       DEB_LANES_BEGIN
         DEB_USE(pcol);
         if (lane < nh) {
-          const double* row = W.lu() + lane * LDH;
+          const D2* row = reinterpret_cast<const D2*>(W.lu() + lane * LDH);
+          const D2* xb = reinterpret_cast<const D2*>(W.gh());
           double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-          int j = 0;
-          for (; j + 3 < nh; j += 4) {
-            a0 += row[j] * W.gh()[j]; a1 += row[j + 1] * W.gh()[j + 1]; a2 += row[j + 2] * W.gh()[j + 2]; a3 += row[j + 3] * W.gh()[j + 3];
+          for (int j = 0; j < nh; j += 8, row += 4, xb += 4) {      // columns >= nh hold zeros
+            D2 ra[4], xa[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { ra[i] = row[i]; xa[i] = xb[i]; }
+            a0 += ra[0].x * xa[0].x; a1 += ra[0].y * xa[0].y; a2 += ra[1].x * xa[1].x; a3 += ra[1].y * xa[1].y;
+            a0 += ra[2].x * xa[2].x; a1 += ra[2].y * xa[2].y; a2 += ra[3].x * xa[3].x; a3 += ra[3].y * xa[3].y;
           }
-          for (; j < nh; ++j) a0 += row[j] * W.gh()[j];
           W.r()[C.hidx[pcol]] = (a0 + a1) + (a2 + a3);
         }
       DEB_LANES_END
