@@ -37,6 +37,9 @@
 // lane holding the largest 32-bit key (lowest lane among ties)
 #define DEB_ARGMAX_U32(name) ([&]() { unsigned m_ = name##_all[0]; int a_ = 0; for (int l_ = 1; l_ < 32; ++l_) if (name##_all[l_] > m_) { m_ = name##_all[l_]; a_ = l_; } return a_; }())
 #define DEB_RSQRT(x) (1.0 / sqrt(x))
+// argmax restricted to the lanes of `mask` (every lane passes the mask of its own group)
+#define DEB_ARGMAX_U32_IN(name, mask) ([&]() { unsigned m_ = 0; int a_ = -1; for (int l_ = 0; l_ < 32; ++l_) if (((mask) >> l_) & 1u) { if (a_ < 0 || name##_all[l_] > m_) { m_ = name##_all[l_]; a_ = l_; } } return a_; }())
+#define DEB_WARP_SUM(name) ([&]() { double s_ = 0.0; for (int l_ = 0; l_ < 32; ++l_) s_ += name##_all[l_]; return s_; }())
 #else
 #define DEB_DEV __device__ __forceinline__
 #define DEB_HD __host__ __device__ __forceinline__
@@ -52,6 +55,8 @@
 #define DEB_ANY(name) __any_sync(0xffffffffu, name)
 #define DEB_ARGMAX_U32(name) (__ffs(__ballot_sync(0xffffffffu, (name) == __reduce_max_sync(0xffffffffu, (name)))) - 1)
 #define DEB_RSQRT(x) rsqrt(x)
+#define DEB_ARGMAX_U32_IN(name, mask) (__ffs(__ballot_sync(0xffffffffu, (name) == __reduce_max_sync((mask), (name))) & (mask)) - 1)
+#define DEB_WARP_SUM(name) deb::warp_sum(name)
 #endif
 
 namespace deb {
@@ -172,6 +177,13 @@ DEB_DEV unsigned hi32abs(double x) {
   return (unsigned)__double2hiint(fabs(x));
 #endif
 }
+#ifndef DEB_CPU_EMU
+DEB_DEV double warp_sum(double v) {      // xor butterfly: every lane ends with the same bits
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+#endif
 DEB_DEV Dual drsqrt(Dual a) { double r = DEB_RSQRT(a.v); return mk(r, -0.5 * r * a.d / a.v); }
 DEB_DEV double drsqrt(double a) { return DEB_RSQRT(a); }
 
@@ -255,6 +267,7 @@ struct CtaConst {
   int ch_stride[NCHMAX];
   int ch_lmax[NCHMAX];
   int ch_h2[NCHMAX];      // chain -> head position of its l=2 element
+  int blo[NHMAX], bhi[NHMAX];   // head position -> [lo, hi) of its diagonal block (AHP: empty)
   // head operator: row r of the RHS restricted to the head is
   //   f_r = sum_t hop_c[t][r] * S[hop_slot] * y[hop_col]  +  hop_chc[r] * S[hop_chs[r]] * h'  +  hop_cec[r] * eta'
   // with S the per-evaluation background scalars (slots below); the same table assembles W_h.
@@ -331,16 +344,26 @@ DEB_DEV void init_cta_const(const Problem& P, CtaConst& C, int* tail, int tid, i
     }
     int h = 0;
     auto put = [&](int e, int type, int bin) { C.hidx[h] = e; C.htype[h] = type; C.hbin[h] = bin; ++h; };
-    put(2, R_ETA, 0); put(3, R_DC, 0); put(4, R_TC, 0); put(5, R_DB, 0); put(6, R_TB, 0);
+    // Head order = the diagonal blocks of the local Jacobian: everything else couples only through the two
+    // metric scalars h' and eta' (a rank-2 term) -- {eta} {dc,tc} {db,tb,F0-2,G0-2} {N0-2} {psi0-2}_i {dq,tq}, a h'
+    int b0;
+    auto blk = [&](int lo, int hi) { for (int q = lo; q < hi; ++q) { C.blo[q] = lo; C.bhi[q] = hi; } };
+    for (int q = 0; q < NHMAX; ++q) { C.blo[q] = 0; C.bhi[q] = 0; }
+    b0 = h; put(2, R_ETA, 0); blk(b0, h);
+    b0 = h; put(3, R_DC, 0); put(4, R_TC, 0); blk(b0, h);
+    b0 = h; put(5, R_DB, 0); put(6, R_TB, 0);
     for (int l = 0; l < 3; ++l) put(P.ig + l, R_F0 + l, 0);
     C.ch_h2[0] = h - 1;
     for (int l = 0; l < 3; ++l) put(P.igp + l, R_G0 + l, 0);
-    C.ch_h2[1] = h - 1;
-    for (int l = 0; l < 3; ++l) put(P.ir + l, R_N0 + l, 0);
-    C.ch_h2[2] = h - 1;
-    for (int l = 0; l < 3; ++l)
-      for (int i = 0; i < nq; ++i) { put(P.iq0 + l * nq + i, R_P0 + l, i); if (l == 2) C.ch_h2[3 + i] = h - 1; }
-    put(P.n - 2, R_DQ, 0); put(P.n - 1, R_TQ, 0); put(1, R_AHP, 0);
+    C.ch_h2[1] = h - 1; blk(b0, h);
+    b0 = h; for (int l = 0; l < 3; ++l) put(P.ir + l, R_N0 + l, 0);
+    C.ch_h2[2] = h - 1; blk(b0, h);
+    for (int i = 0; i < nq; ++i) {
+      b0 = h; for (int l = 0; l < 3; ++l) put(P.iq0 + l * nq + i, R_P0 + l, i);
+      C.ch_h2[3 + i] = h - 1; blk(b0, h);
+    }
+    b0 = h; put(P.n - 2, R_DQ, 0); put(P.n - 1, R_TQ, 0); blk(b0, h);
+    put(1, R_AHP, 0);
     // ---- head operator (perturbations.py:259-369 restricted to the l <= 2 rows) ----
     for (int r = 0; r < NHMAX; ++r) {
       for (int t = 0; t < HOP_NT; ++t) { C.hop_c[t][r] = 0.0; C.hop_meta[t][r] = 0; }
@@ -428,6 +451,9 @@ struct WarpWs {
   double* gh_;   // d h'/d y_c over head columns [NHMAX]
   double* ge_;   // d eta'/d y_c [NHMAX]
   double* j1_;   // d f_1/d y_c (the a h' row) [NHMAX]
+  double* qh_;   // D^-1 (coefficient of h' per row) [NHMAX]
+  double* qe_;   // D^-1 (coefficient of eta' per row) [NHMAX]
+  double* xb_;   // gather buffer of the head solve [NHMAX]
   double* kc_;   // chain wavenumber k or k v_i (value, d/da) [2*NCHMAX]
   double* kap_;   // chain damping opac or 0 (value, d/da) [2*NCHMAX]
   double* nur_;   // w_i psi0_i / v_i (value, d/da) [2*NQMAX]
@@ -446,6 +472,9 @@ struct WarpWs {
   DEB_DEV double* gh() const { return gh_; }
   DEB_DEV double* ge() const { return ge_; }
   DEB_DEV double* j1() const { return j1_; }
+  DEB_DEV double* qh() const { return qh_; }
+  DEB_DEV double* qe() const { return qe_; }
+  DEB_DEV double* xb() const { return xb_; }
   DEB_DEV double* kc() const { return kc_; }
   DEB_DEV double* kap() const { return kap_; }
   DEB_DEV double* nur() const { return nur_; }
@@ -455,12 +484,13 @@ struct WarpWs {
   DEB_DEV Cosmo* cosmo() const { return cosmo_; }
 };
 DEB_HD size_t warp_ws_doubles(int np) {
-  return (size_t)7 * np + NHMAX * LDH + 3 * NHMAX + 4 * NCHMAX + 4 * NQMAX + 2 * NSLOT + NHMAX / 2 + 2 + (sizeof(Cosmo) + 7) / 8;
+  return (size_t)7 * np + NHMAX * LDH + 6 * NHMAX + 4 * NCHMAX + 4 * NQMAX + 2 * NSLOT + NHMAX / 2 + 2 + (sizeof(Cosmo) + 7) / 8;
 }
 DEB_DEV void carve(WarpWs& W, double* base, int np) {
   W.y_ = base; W.u_ = W.y_ + np; W.r_ = W.u_ + np; W.m_ = W.r_ + np; W.ie_ = W.m_ + np; W.g_ = W.ie_ + np; W.ja_ = W.g_ + np;
   W.lu_ = W.ja_ + np; W.gh_ = W.lu_ + NHMAX * LDH; W.ge_ = W.gh_ + NHMAX; W.j1_ = W.ge_ + NHMAX;
-  W.kc_ = W.j1_ + NHMAX; W.kap_ = W.kc_ + 2 * NCHMAX; W.nur_ = W.kap_ + 2 * NCHMAX; W.nup_ = W.nur_ + 2 * NQMAX;
+  W.qh_ = W.j1_ + NHMAX; W.qe_ = W.qh_ + NHMAX; W.xb_ = W.qe_ + NHMAX;
+  W.kc_ = W.xb_ + NHMAX; W.kap_ = W.kc_ + 2 * NCHMAX; W.nur_ = W.kap_ + 2 * NCHMAX; W.nup_ = W.nur_ + 2 * NQMAX;
   W.sl_ = W.nup_ + 2 * NQMAX;
   W.perm_ = (int*)(W.sl_ + 2 * NSLOT);
   W.cosmo_ = (Cosmo*)(W.sl_ + 2 * NSLOT + NHMAX / 2 + 2);
@@ -780,6 +810,7 @@ DEB_DEV void convert_outputs(const Problem& P, const Cosmo& c, const NuBins& nb,
 template <int NE>
 DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int mode DEB_LANE_PARAM) {
   const int n = P.n, nh = P.nh, nch = P.nch, nq = P.nq;
+  const int nhb = nh - 1;            // head unknowns inside diagonal blocks (the last head row is a h')
   const int cosmo = mode / P.nk, kidx = mode - cosmo * P.nk;
   const double k = DEB_LDG(P.kmodes + (P.k_per_cosmo ? (size_t)cosmo * P.nk + kidx : (size_t)kidx));
   const double k2 = k * k;
@@ -793,6 +824,10 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
   DEB_REGS(int, pcol, );           // head inverse: pivot column of this lane's row
   DEB_REGS(double, rscale, );      // head inverse: 1/pivot of this lane's row
   DEB_REGS(unsigned, pkey, );
+  DEB_REGS(int, pivl, );
+  DEB_REGS(double, fmul, );
+  DEB_REGS(double, pval, );
+  DEB_REGS(double, s1, ); DEB_REGS(double, s2, ); DEB_REGS(double, s3, ); DEB_REGS(double, s4, );
   DEB_REGS(int, nanflag, );
 
   // ---- prologue ----
@@ -927,28 +962,23 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
         }
       DEB_LANES_END
 
-      // ---- head matrix  W_h = I/(gamma dt) - J_h  (one lane per row, from the operator table) ----
+      // ---- head:  W_h = D - chv gh^T - cev ge^T  (+ the a h' row).  D = I/(gamma dt) - J_local is block diagonal
+      //      (blocks of size 1, 2, 8, 3, 3 x nq, 2), the metric coupling is rank 2  ->  block inverses + Woodbury.
       DEB_LANES_BEGIN
-        if (lane < nh) {
-          const int ty = C.htype[lane];
+        DEB_USE(pcol); DEB_USE(rscale);
+        pcol = -1; rscale = 1.0;
+        if (lane < nhb) {
+          const int ty = C.htype[lane], lo = C.blo[lane], hi = C.bhi[lane];
           double* row = W.lu() + lane * LDH;
-          const double chh = C.hop_chc[lane] * W.sl()[C.hop_chs[lane]], cee = C.hop_cec[lane];
-          for (int c0 = 0; c0 < nh; c0 += 8) {
-            double ga[8], gb[8], gc[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { ga[i] = W.gh()[c0 + i]; gb[i] = W.ge()[c0 + i]; gc[i] = W.j1()[c0 + i]; }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) row[c0 + i] = (c0 + i >= nh) ? 0.0 : ((ty == R_AHP) ? -gc[i] : -(chh * ga[i] + cee * gb[i]));
-          }
+          for (int cc = lo; cc < hi; ++cc) row[cc] = 0.0;
           double diag = idg;
-          // Schur complement of the chain tail on the l=2 diagonal
-          if (ty == R_F2 || ty == R_G2 || ty == R_N2 || ty == R_P2) {
+          if (ty == R_F2 || ty == R_G2 || ty == R_N2 || ty == R_P2) {      // Schur complement of the chain tail
             const int chain = ty == R_F2 ? 0 : (ty == R_G2 ? 1 : (ty == R_N2 ? 2 : 3 + C.hbin[lane]));
             diag += W.ie()[C.ch_base[chain] + 2 * C.ch_stride[chain]];
           }
-          row[lane] += diag;
+          row[lane] = diag;
 #pragma unroll
-          for (int t = 0; t < HOP_NT; ++t) {             // local couplings (columns inside the head)
+          for (int t = 0; t < HOP_NT; ++t) {             // local couplings (all inside the block)
             const int m = C.hop_meta[t][lane], hc = (m >> 20) - 1;
             if (hc >= 0) row[hc] -= C.hop_c[t][lane] * W.sl()[m & 0xff];
           }
@@ -956,54 +986,84 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
       DEB_LANES_END
     }
 
-    // ---- head: in-place Gauss-Jordan inverse with implicit partial pivoting, one lane per row ----
-    // Rows stay in place; the pivot row of step j (perm[j]) is left unscaled until the end, which makes
-    // every elimination step a single race-free phase.  Afterwards S[:, j] holds column perm[j] of the
-    // accumulated row operations E (E W_h = Pi), so x_j = (S b_perm)[perm[j]] with b_perm[j] = b[perm[j]].
-    DEB_LANES_BEGIN
-      DEB_USE(pcol); DEB_USE(rscale);
-      pcol = -1; rscale = 1.0;
-    DEB_LANES_END
-    for (int j = 0; j < nh; ++j) {
+    // ---- block inverses: in-place Gauss-Jordan with partial pivoting inside every block, all blocks at once
+    //      (step t eliminates the t-th column of each block; lanes = rows; pivot search is a masked warp max).
+    //      The pivot row is left unscaled until the end, so each step is one race-free phase; afterwards
+    //      S[:, j] is column perm[j] of the accumulated row operations: x_j = (S b_perm)[perm[j]].
+    for (int t = 0; t < 8; ++t) {
       DEB_LANES_BEGIN
         DEB_USE(pcol); DEB_USE(pkey);
-        pkey = (lane < nh && pcol < 0) ? hi32abs(W.lu()[lane * LDH + j]) + 1u : 0u;
+        const int lo = C.blo[lane], hi = C.bhi[lane];
+        pkey = (lane < nhb && lo + t < hi && pcol < 0) ? hi32abs(W.lu()[lane * LDH + lo + t]) + 1u : 0u;
       DEB_LANES_END
-      const int piv = DEB_ARGMAX_U32(pkey);
-      const double ipv = 1.0 / W.lu()[piv * LDH + j];
-      DEB_SYNC();
       DEB_LANES_BEGIN
-        DEB_USE(pcol); DEB_USE(rscale);
-        double* row = W.lu() + lane * LDH;
-        if (lane == piv) { pcol = j; rscale = ipv; W.perm()[j] = piv; row[j] = 1.0; }
-        else if (lane < nh) {
-          const D2* prow = reinterpret_cast<const D2*>(W.lu() + piv * LDH);
-          const double f = row[j] * ipv;
-          D2* rp = reinterpret_cast<D2*>(row);
-          for (int c0 = 0; c0 < nh; c0 += 8, rp += 4, prow += 4) {   // 8 columns per trip as four 128-bit accesses
-            D2 ra[4], pa[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { ra[i] = rp[i]; pa[i] = prow[i]; }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { ra[i].x -= f * pa[i].x; ra[i].y -= f * pa[i].y; rp[i] = ra[i]; }
+        DEB_USE(pcol); DEB_USE(rscale); DEB_USE(pkey); DEB_USE(pivl); DEB_USE(fmul);
+        const int lo = C.blo[lane], hi = C.bhi[lane], j = lo + t;
+        const unsigned bmask = (hi > lo) ? ((hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u)) : (1u << lane);
+        const int piv = DEB_ARGMAX_U32_IN(pkey, bmask);
+        pivl = piv; fmul = 0.0;
+        if (lane < nhb && j < hi) {
+          const double ipv = 1.0 / W.lu()[piv * LDH + j];
+          if (lane == piv) { pcol = j; rscale = ipv; W.perm()[j] = piv; }
+          else fmul = W.lu()[lane * LDH + j] * ipv;
+        }
+      DEB_LANES_END
+      DEB_LANES_BEGIN
+        DEB_USE(pivl); DEB_USE(fmul);
+        const int lo = C.blo[lane], hi = C.bhi[lane], j = lo + t;
+        if (lane < nhb && j < hi) {
+          double* row = W.lu() + lane * LDH;
+          if (lane == pivl) row[j] = 1.0;
+          else {
+            const double* prow = W.lu() + pivl * LDH;
+            const double f = fmul;
+            for (int cc = lo; cc < hi; ++cc) if (cc != j) row[cc] -= f * prow[cc];
+            row[j] = -f;
           }
-          row[j] = -f;
         }
       DEB_LANES_END
     }
+    // scale rows; Woodbury pieces: qh = D^-1 chv, qe = D^-1 cev, capacitance C = I - [gh ge]^T [qh qe]
     DEB_LANES_BEGIN
       DEB_USE(rscale);
-      if (lane < nh) {
-        D2* rp = reinterpret_cast<D2*>(W.lu() + lane * LDH);
-        for (int c0 = 0; c0 < nh; c0 += 8, rp += 4) {
-          D2 ra[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) ra[i] = rp[i];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) { ra[i].x *= rscale; ra[i].y *= rscale; rp[i] = ra[i]; }
+      if (lane < nhb) {
+        double* row = W.lu() + lane * LDH;
+        for (int cc = C.blo[lane]; cc < C.bhi[lane]; ++cc) row[cc] *= rscale;
+      }
+      // right-hand sides of the two Woodbury solves, gathered in pivot order
+      W.xb()[lane] = 0.0;
+    DEB_LANES_END
+    DEB_LANES_BEGIN
+      DEB_USE(pcol); DEB_USE(s1); DEB_USE(s2); DEB_USE(s3); DEB_USE(s4);
+      s1 = s2 = s3 = s4 = 0.0;
+      if (lane < nhb) {
+        const int lo = C.blo[lane], hi = C.bhi[lane];
+        const double* row = W.lu() + lane * LDH;
+        double ah = 0.0, ae = 0.0;
+        for (int cc = lo; cc < hi; ++cc) {
+          const int pr = W.perm()[cc];
+          ah += row[cc] * (C.hop_chc[pr] * W.sl()[C.hop_chs[pr]]);
+          ae += row[cc] * C.hop_cec[pr];
         }
+        W.qh()[pcol] = ah; W.qe()[pcol] = ae;
+        const double ghc = W.gh()[pcol], gec = W.ge()[pcol], j1c = W.j1()[pcol];
+        s1 = ghc * ah; s2 = ghc * ae; s3 = gec * ah; s4 = gec * ae;
+        W.xb()[lane] = j1c;           // parked for the next phase (lane-private slot)
       }
     DEB_LANES_END
+    double ci_hh, ci_he, ci_eh, ci_ee, jq_h, jq_e;     // inverse capacitance; a h' row applied to qh, qe
+    {
+      const double c_hh = 1.0 - DEB_WARP_SUM(s1), c_he = -DEB_WARP_SUM(s2), c_eh = -DEB_WARP_SUM(s3), c_ee = 1.0 - DEB_WARP_SUM(s4);
+      const double idet = 1.0 / (c_hh * c_ee - c_he * c_eh);
+      ci_hh = c_ee * idet; ci_he = -c_he * idet; ci_eh = -c_eh * idet; ci_ee = c_hh * idet;
+      DEB_LANES_BEGIN
+        DEB_USE(pcol); DEB_USE(s1); DEB_USE(s2);
+        s1 = s2 = 0.0;
+        if (lane < nhb) { const double j1c = W.xb()[lane]; s1 = j1c * W.qh()[pcol]; s2 = j1c * W.qe()[pcol]; }
+      DEB_LANES_END
+      jq_h = DEB_WARP_SUM(s1); jq_e = DEB_WARP_SUM(s2);
+    }
+    const double gdt = dt * RD_GAMMA;      // 1 / idg
 
     // ================= 8 stages =================
     double errnorm2 = 0.0;
@@ -1093,26 +1153,30 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
           *rp = rn - mn * bp;
         }
       DEB_LANES_END
-      // head: x_h = S (P b) with the explicit inverse; lane j gathers b[perm[j]], lane r forms row r of S b
+      // head: p = D^-1 b (block inverses), then the rank-2 Woodbury correction and the a h' row
       DEB_LANES_BEGIN
-        W.gh()[lane] = lane < nh ? W.r()[C.hidx[W.perm()[lane]]] : 0.0;
+        W.xb()[lane] = lane < nhb ? W.r()[C.hidx[W.perm()[lane]]] : 0.0;
       DEB_LANES_END
       DEB_LANES_BEGIN
-        DEB_USE(pcol);
-        if (lane < nh) {
-          const D2* row = reinterpret_cast<const D2*>(W.lu() + lane * LDH);
-          const D2* xb = reinterpret_cast<const D2*>(W.gh());
-          double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-          for (int j = 0; j < nh; j += 8, row += 4, xb += 4) {      // columns >= nh hold zeros
-            D2 ra[4], xa[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { ra[i] = row[i]; xa[i] = xb[i]; }
-            a0 += ra[0].x * xa[0].x; a1 += ra[0].y * xa[0].y; a2 += ra[1].x * xa[1].x; a3 += ra[1].y * xa[1].y;
-            a0 += ra[2].x * xa[2].x; a1 += ra[2].y * xa[2].y; a2 += ra[3].x * xa[3].x; a3 += ra[3].y * xa[3].y;
-          }
-          W.r()[C.hidx[pcol]] = (a0 + a1) + (a2 + a3);
+        DEB_USE(pcol); DEB_USE(s1); DEB_USE(s2); DEB_USE(s3); DEB_USE(pval);
+        s1 = s2 = s3 = 0.0; pval = 0.0;
+        if (lane < nhb) {
+          const double* row = W.lu() + lane * LDH;
+          double acc = 0.0;
+          for (int cc = C.blo[lane]; cc < C.bhi[lane]; ++cc) acc += row[cc] * W.xb()[cc];
+          pval = acc;                       // p_c for the column c = pcol this lane's row became
+          s1 = W.gh()[pcol] * acc; s2 = W.ge()[pcol] * acc; s3 = W.j1()[pcol] * acc;
         }
       DEB_LANES_END
+      {
+        const double th = DEB_WARP_SUM(s1), te = DEB_WARP_SUM(s2), ta = DEB_WARP_SUM(s3);
+        const double sh = ci_hh * th + ci_he * te, se = ci_eh * th + ci_ee * te;
+        DEB_LANES_BEGIN
+          DEB_USE(pcol); DEB_USE(pval);
+          if (lane < nhb) W.r()[C.hidx[pcol]] = pval + W.qh()[pcol] * sh + W.qe()[pcol] * se;
+          else if (lane == nhb) W.r()[1] = (W.r()[1] + ta + jq_h * sh + jq_e * se) * gdt;     // a h' (state 1): closed row
+        DEB_LANES_END
+      }
       DEB_LANES_BEGIN
         if (lane < nch) {          // forward sweep: x_l = b'_l/e_l + g_l x_{l-1}, l = 3 .. L
           const int s = C.ch_stride[lane], L = C.ch_lmax[lane];
