@@ -999,8 +999,14 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
       DEB_LANES_BEGIN
         DEB_USE(pcol); DEB_USE(rscale); DEB_USE(pkey); DEB_USE(pivl); DEB_USE(fmul);
         const int lo = C.blo[lane], hi = C.bhi[lane], j = lo + t;
-        const unsigned bmask = (hi > lo) ? ((hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u)) : (1u << lane);
-        const int piv = DEB_ARGMAX_U32_IN(pkey, bmask);
+        // pivot = first row of the block holding the largest key: a scan of the (at most 8) block rows by shuffles
+        int piv = lane; unsigned best = 0u;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int src = (lo + i < hi) ? lo + i : lane;
+          const unsigned kk = DEB_SHFL(pkey, src);
+          if (lo + i < hi && kk > best) { best = kk; piv = lo + i; }
+        }
         pivl = piv; fmul = 0.0;
         if (lane < nhb && j < hi) {
           const double ipv = 1.0 / W.lu()[piv * LDH + j];
