@@ -72,7 +72,7 @@ constexpr int NCHMAX = 3 + NQMAX;
 constexpr int LMAXCAP = 64;
 constexpr int HOP_NT = 5;        // local couplings per head row (max: F2, G2)
 constexpr int NSLOT = 12 + NQMAX; // background scalars the head rows are built from (see HeadOp)
-constexpr int LDH = 34;           // 16-byte aligned rows; 128-bit row accesses are conflict-free per quarter-warp
+constexpr int LDB = 9;            // head block rows: at most 8 entries (largest block), odd stride = conflict-free across lanes
 
 // row types (element descriptors)
 enum RowType : int { R_A = 0, R_AHP, R_ETA, R_DC, R_TC, R_DB, R_TB, R_F0, R_F1, R_F2, R_G0, R_G1, R_G2,
@@ -447,7 +447,7 @@ struct WarpWs {
   double* ie_;   // tail inverse pivots 1/e_l [np]
   double* g_;   // tail forward multipliers -W_{l,l-1}/e_l [np]
   double* ja_;   // d f / d a at (t0, y0) [np]
-  double* lu_;   // head matrix -> its inverse [NHMAX*LDH]
+  double* lu_;   // head matrix -> its inverse [NHMAX*LDB], row r holds its block's columns lo..hi-1
   double* gh_;   // d h'/d y_c over head columns [NHMAX]
   double* ge_;   // d eta'/d y_c [NHMAX]
   double* j1_;   // d f_1/d y_c (the a h' row) [NHMAX]
@@ -484,17 +484,20 @@ struct WarpWs {
   DEB_DEV Cosmo* cosmo() const { return cosmo_; }
 };
 DEB_HD size_t warp_ws_doubles(int np) {
-  return (size_t)7 * np + NHMAX * LDH + 6 * NHMAX + 4 * NCHMAX + 4 * NQMAX + 2 * NSLOT + NHMAX / 2 + 2 + (sizeof(Cosmo) + 7) / 8;
+  return (size_t)7 * np + NHMAX * LDB + 6 * NHMAX + 4 * NCHMAX + 4 * NQMAX + 2 * NSLOT + NHMAX / 2 + 2 + (sizeof(Cosmo) + 7) / 8;
 }
 DEB_DEV void carve(WarpWs& W, double* base, int np) {
   W.y_ = base; W.u_ = W.y_ + np; W.r_ = W.u_ + np; W.m_ = W.r_ + np; W.ie_ = W.m_ + np; W.g_ = W.ie_ + np; W.ja_ = W.g_ + np;
-  W.lu_ = W.ja_ + np; W.gh_ = W.lu_ + NHMAX * LDH; W.ge_ = W.gh_ + NHMAX; W.j1_ = W.ge_ + NHMAX;
+  W.lu_ = W.ja_ + np; W.gh_ = W.lu_ + NHMAX * LDB; W.ge_ = W.gh_ + NHMAX; W.j1_ = W.ge_ + NHMAX;
   W.qh_ = W.j1_ + NHMAX; W.qe_ = W.qh_ + NHMAX; W.xb_ = W.qe_ + NHMAX;
   W.kc_ = W.xb_ + NHMAX; W.kap_ = W.kc_ + 2 * NCHMAX; W.nur_ = W.kap_ + 2 * NCHMAX; W.nup_ = W.nur_ + 2 * NQMAX;
   W.sl_ = W.nup_ + 2 * NQMAX;
   W.perm_ = (int*)(W.sl_ + 2 * NSLOT);
   W.cosmo_ = (Cosmo*)(W.sl_ + 2 * NSLOT + NHMAX / 2 + 2);
 }
+
+// row r of the block-diagonal head matrix, addressable by ABSOLUTE head column lo <= c < hi
+DEB_DEV double* hrow(const WarpWs& W, int r, int lo) { return W.lu() + (r * LDB - lo); }
 
 // background coefficients at scale factor a (perturbations.py:176-218, background.py:110-121)
 template <class T> struct Bg {
@@ -969,7 +972,7 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
         pcol = -1; rscale = 1.0;
         if (lane < nhb) {
           const int ty = C.htype[lane], lo = C.blo[lane], hi = C.bhi[lane];
-          double* row = W.lu() + lane * LDH;
+          double* row = hrow(W, lane, lo);
           for (int cc = lo; cc < hi; ++cc) row[cc] = 0.0;
           double diag = idg;
           if (ty == R_F2 || ty == R_G2 || ty == R_N2 || ty == R_P2) {      // Schur complement of the chain tail
@@ -994,7 +997,7 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
       DEB_LANES_BEGIN
         DEB_USE(pcol); DEB_USE(pkey);
         const int lo = C.blo[lane], hi = C.bhi[lane];
-        pkey = (lane < nhb && lo + t < hi && pcol < 0) ? hi32abs(W.lu()[lane * LDH + lo + t]) + 1u : 0u;
+        pkey = (lane < nhb && lo + t < hi && pcol < 0) ? hi32abs(hrow(W, lane, lo)[lo + t]) + 1u : 0u;
       DEB_LANES_END
       DEB_LANES_BEGIN
         DEB_USE(pcol); DEB_USE(rscale); DEB_USE(pkey); DEB_USE(pivl); DEB_USE(fmul);
@@ -1009,19 +1012,19 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
         }
         pivl = piv; fmul = 0.0;
         if (lane < nhb && j < hi) {
-          const double ipv = 1.0 / W.lu()[piv * LDH + j];
+          const double ipv = 1.0 / hrow(W, piv, lo)[j];
           if (lane == piv) { pcol = j; rscale = ipv; W.perm()[j] = piv; }
-          else fmul = W.lu()[lane * LDH + j] * ipv;
+          else fmul = hrow(W, lane, lo)[j] * ipv;
         }
       DEB_LANES_END
       DEB_LANES_BEGIN
         DEB_USE(pivl); DEB_USE(fmul);
         const int lo = C.blo[lane], hi = C.bhi[lane], j = lo + t;
         if (lane < nhb && j < hi) {
-          double* row = W.lu() + lane * LDH;
+          double* row = hrow(W, lane, lo);
           if (lane == pivl) row[j] = 1.0;
           else {
-            const double* prow = W.lu() + pivl * LDH;
+            const double* prow = hrow(W, pivl, lo);
             const double f = fmul;
             for (int cc = lo; cc < hi; ++cc) if (cc != j) row[cc] -= f * prow[cc];
             row[j] = -f;
@@ -1033,7 +1036,7 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
     DEB_LANES_BEGIN
       DEB_USE(rscale);
       if (lane < nhb) {
-        double* row = W.lu() + lane * LDH;
+        double* row = hrow(W, lane, C.blo[lane]);
         for (int cc = C.blo[lane]; cc < C.bhi[lane]; ++cc) row[cc] *= rscale;
       }
       // right-hand sides of the two Woodbury solves, gathered in pivot order
@@ -1044,7 +1047,7 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
       s1 = s2 = s3 = s4 = 0.0;
       if (lane < nhb) {
         const int lo = C.blo[lane], hi = C.bhi[lane];
-        const double* row = W.lu() + lane * LDH;
+        const double* row = hrow(W, lane, lo);
         double ah = 0.0, ae = 0.0;
         for (int cc = lo; cc < hi; ++cc) {
           const int pr = W.perm()[cc];
@@ -1167,9 +1170,10 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
         DEB_USE(pcol); DEB_USE(s1); DEB_USE(s2); DEB_USE(s3); DEB_USE(pval);
         s1 = s2 = s3 = 0.0; pval = 0.0;
         if (lane < nhb) {
-          const double* row = W.lu() + lane * LDH;
+          const int lo = C.blo[lane];
+          const double* row = hrow(W, lane, lo);
           double acc = 0.0;
-          for (int cc = C.blo[lane]; cc < C.bhi[lane]; ++cc) acc += row[cc] * W.xb()[cc];
+          for (int cc = lo; cc < C.bhi[lane]; ++cc) acc += row[cc] * W.xb()[cc];
           pval = acc;                       // p_c for the column c = pcol this lane's row became
           s1 = W.gh()[pcol] * acc; s2 = W.ge()[pcol] * acc; s3 = W.j1()[pcol] * acc;
         }
