@@ -981,9 +981,9 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
           }
           row[lane] = diag;
 #pragma unroll
-          for (int t = 0; t < HOP_NT; ++t) {             // local couplings (all inside the block)
-            const int m = C.hop_meta[t][lane], hc = (m >> 20) - 1;
-            if (hc >= 0) row[hc] -= C.hop_c[t][lane] * W.sl()[m & 0xff];
+          for (int q = 0; q < HOP_NT; ++q) {             // local couplings (all inside the block)
+            const int m = C.hop_meta[q][lane], hc = (m >> 20) - 1;
+            if (hc >= 0) row[hc] -= C.hop_c[q][lane] * W.sl()[m & 0xff];
           }
         }
       DEB_LANES_END
@@ -993,15 +993,15 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
     //      (step t eliminates the t-th column of each block; lanes = rows; pivot search is a masked warp max).
     //      The pivot row is left unscaled until the end, so each step is one race-free phase; afterwards
     //      S[:, j] is column perm[j] of the accumulated row operations: x_j = (S b_perm)[perm[j]].
-    for (int t = 0; t < 8; ++t) {
+    for (int bt = 0; bt < 8; ++bt) {
       DEB_LANES_BEGIN
         DEB_USE(pcol); DEB_USE(pkey);
         const int lo = C.blo[lane], hi = C.bhi[lane];
-        pkey = (lane < nhb && lo + t < hi && pcol < 0) ? hi32abs(hrow(W, lane, lo)[lo + t]) + 1u : 0u;
+        pkey = (lane < nhb && lo + bt < hi && pcol < 0) ? hi32abs(hrow(W, lane, lo)[lo + bt]) + 1u : 0u;
       DEB_LANES_END
       DEB_LANES_BEGIN
         DEB_USE(pcol); DEB_USE(rscale); DEB_USE(pkey); DEB_USE(pivl); DEB_USE(fmul);
-        const int lo = C.blo[lane], hi = C.bhi[lane], j = lo + t;
+        const int lo = C.blo[lane], hi = C.bhi[lane], j = lo + bt;
         // pivot = first row of the block holding the largest key: a scan of the (at most 8) block rows by shuffles
         int piv = lane; unsigned best = 0u;
 #pragma unroll
@@ -1019,7 +1019,7 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
       DEB_LANES_END
       DEB_LANES_BEGIN
         DEB_USE(pivl); DEB_USE(fmul);
-        const int lo = C.blo[lane], hi = C.bhi[lane], j = lo + t;
+        const int lo = C.blo[lane], hi = C.bhi[lane], j = lo + bt;
         if (lane < nhb && j < hi) {
           double* row = hrow(W, lane, lo);
           if (lane == pivl) row[j] = 1.0;
