@@ -37,6 +37,7 @@
 // lane holding the largest 32-bit key (lowest lane among ties)
 #define DEB_ARGMAX_U32(name) ([&]() { unsigned m_ = name##_all[0]; int a_ = 0; for (int l_ = 1; l_ < 32; ++l_) if (name##_all[l_] > m_) { m_ = name##_all[l_]; a_ = l_; } return a_; }())
 #define DEB_RSQRT(x) (1.0 / sqrt(x))
+#define DEB_RCP(x) (1.0 / (x))
 // argmax restricted to the lanes of `mask` (every lane passes the mask of its own group)
 #define DEB_ARGMAX_U32_IN(name, mask) ([&]() { unsigned m_ = 0; int a_ = -1; for (int l_ = 0; l_ < 32; ++l_) if (((mask) >> l_) & 1u) { if (a_ < 0 || name##_all[l_] > m_) { m_ = name##_all[l_]; a_ = l_; } } return a_; }())
 #define DEB_WARP_SUM(name) ([&]() { double s_ = 0.0; for (int l_ = 0; l_ < 32; ++l_) s_ += name##_all[l_]; return s_; }())
@@ -55,6 +56,7 @@
 #define DEB_ANY(name) __any_sync(0xffffffffu, name)
 #define DEB_ARGMAX_U32(name) (__ffs(__ballot_sync(0xffffffffu, (name) == __reduce_max_sync(0xffffffffu, (name)))) - 1)
 #define DEB_RSQRT(x) rsqrt(x)
+#define DEB_RCP(x) __drcp_rn(x)      // correctly rounded reciprocal: same bits as 1.0/x, shorter sequence
 #define DEB_ARGMAX_U32_IN(name, mask) (__ffs(__ballot_sync(0xffffffffu, (name) == __reduce_max_sync((mask), (name))) & (mask)) - 1)
 #define DEB_WARP_SUM(name) deb::warp_sum(name)
 #endif
@@ -71,6 +73,7 @@ constexpr int NHMAX = 32;
 constexpr int NCHMAX = 3 + NQMAX;
 constexpr int LMAXCAP = 64;
 constexpr int HOP_NT = 5;        // local couplings per head row (max: F2, G2)
+constexpr int ICACHE = 20;        // doubles of the per-mode spline interval cache
 constexpr int NSLOT = 12 + NQMAX; // background scalars the head rows are built from (see HeadOp)
 constexpr int LDB = 9;            // head block rows: at most 8 entries (largest block), odd stride = conflict-free across lanes
 
@@ -158,7 +161,7 @@ DEB_DEV Dual operator-(Dual a) { return mk(-a.v, -a.d); }
 DEB_DEV Dual operator*(Dual a, double b) { return mk(a.v * b, a.d * b); }
 DEB_DEV Dual operator*(double b, Dual a) { return mk(a.v * b, a.d * b); }
 DEB_DEV Dual operator/(Dual a, double b) { return mk(a.v / b, a.d / b); }
-DEB_DEV Dual operator/(double b, Dual a) { double q = b / a.v; return mk(q, -q * a.d / a.v); }
+DEB_DEV Dual operator/(double b, Dual a) { double ia = DEB_RCP(a.v), q = b * ia; return mk(q, -q * a.d * ia); }
 DEB_DEV Dual dsqrt(Dual a) { double s = sqrt(a.v); return mk(s, 0.5 * a.d / s); }
 DEB_DEV Dual dexp(Dual a) { double e = exp(a.v); return mk(e, e * a.d); }
 DEB_DEV Dual dlog(Dual a) { return mk(log(a.v), a.d / a.v); }
@@ -459,6 +462,7 @@ struct WarpWs {
   double* nur_;   // w_i psi0_i / v_i (value, d/da) [2*NQMAX]
   double* nup_;   // w_i psi0_i v_i (value, d/da) [2*NQMAX]
   double* sl_;   // background-scalar slots of the head operator (value, d/da) [2*NSLOT]
+  double* ic_;   // spline interval cache [ICACHE]
   int* perm_;    // pivot row of elimination step j [NHMAX]
   Cosmo* cosmo_; // per-mode constants and table pointers
   DEB_DEV double* y() const { return y_; }
@@ -480,11 +484,12 @@ struct WarpWs {
   DEB_DEV double* nur() const { return nur_; }
   DEB_DEV double* nup() const { return nup_; }
   DEB_DEV double* sl() const { return sl_; }
+  DEB_DEV double* ic() const { return ic_; }
   DEB_DEV int* perm() const { return perm_; }
   DEB_DEV Cosmo* cosmo() const { return cosmo_; }
 };
 DEB_HD size_t warp_ws_doubles(int np) {
-  return (size_t)7 * np + NHMAX * LDB + 6 * NHMAX + 4 * NCHMAX + 4 * NQMAX + 2 * NSLOT + NHMAX / 2 + 2 + (sizeof(Cosmo) + 7) / 8;
+  return (size_t)7 * np + NHMAX * LDB + 6 * NHMAX + 4 * NCHMAX + 4 * NQMAX + 2 * NSLOT + ICACHE + NHMAX / 2 + 2 + (sizeof(Cosmo) + 7) / 8;
 }
 DEB_DEV void carve(WarpWs& W, double* base, int np) {
   W.y_ = base; W.u_ = W.y_ + np; W.r_ = W.u_ + np; W.m_ = W.r_ + np; W.ie_ = W.m_ + np; W.g_ = W.ie_ + np; W.ja_ = W.g_ + np;
@@ -492,8 +497,9 @@ DEB_DEV void carve(WarpWs& W, double* base, int np) {
   W.qh_ = W.j1_ + NHMAX; W.qe_ = W.qh_ + NHMAX; W.xb_ = W.qe_ + NHMAX;
   W.kc_ = W.xb_ + NHMAX; W.kap_ = W.kc_ + 2 * NCHMAX; W.nur_ = W.kap_ + 2 * NCHMAX; W.nup_ = W.nur_ + 2 * NQMAX;
   W.sl_ = W.nup_ + 2 * NQMAX;
-  W.perm_ = (int*)(W.sl_ + 2 * NSLOT);
-  W.cosmo_ = (Cosmo*)(W.sl_ + 2 * NSLOT + NHMAX / 2 + 2);
+  W.ic_ = W.sl_ + 2 * NSLOT;
+  W.perm_ = (int*)(W.ic_ + ICACHE);
+  W.cosmo_ = (Cosmo*)(W.ic_ + ICACHE + NHMAX / 2 + 2);
 }
 
 // row r of the block-diagonal head matrix, addressable by ABSOLUTE head column lo <= c < hi
@@ -506,40 +512,59 @@ template <class T> struct Bg {
 };
 struct Hints { int th, nu; };
 
-// value and x-derivative factors of the cubic on interval i, shared by splines on the same knots
-struct SplPos { double h, A, B, cA, cB, dA, dB; };
-DEB_DEV SplPos spl_pos(const double* x, int i, double xn) {
+// The RHS reads three splines of log a (cs2a and xe on one knot set, log rho_nu on another).  a(tau) is
+// monotone, so the active interval changes every few dozen evaluations: its knot data, 1/h and h^2/6 are
+// cached per mode in shared memory and refreshed only when log a leaves the interval.
+//   thermo: [0] x0 [1] x1 [2] 1/h [3] h^2/6 [4..7] cs2a y0 y1 S0 S1 [8..11] xe y0 y1 S0 S1
+//   nu    : [12] x0 [13] x1 [14] 1/h [15] h^2/6 [16..19] log rho_nu y0 y1 S0 S1
+struct SplPos { double invh, A, B, cA, cB, dA, dB; };
+DEB_DEV void icache_fill(double* ic, const Spl& s0, const Spl* s1, int i) {
+  const double x0 = DEB_LDG(s0.x + i), x1 = DEB_LDG(s0.x + i + 1), h = x1 - x0;
+  ic[0] = x0; ic[1] = x1; ic[2] = DEB_RCP(h); ic[3] = (h * h) / 6.0;
+  ic[4] = DEB_LDG(s0.y + i); ic[5] = DEB_LDG(s0.y + i + 1); ic[6] = DEB_LDG(s0.S + i); ic[7] = DEB_LDG(s0.S + i + 1);
+  if (s1) { ic[8] = DEB_LDG(s1->y + i); ic[9] = DEB_LDG(s1->y + i + 1); ic[10] = DEB_LDG(s1->S + i); ic[11] = DEB_LDG(s1->S + i + 1); }
+}
+// true when interval `i` (already located) still brackets xn under the reference's clip rule
+DEB_DEV bool icache_hit(const double* ic, int i, int n, double xn) {
+  return i >= 0 && (ic[0] < xn || i == 0) && (xn <= ic[1] || i == n - 2);
+}
+DEB_DEV SplPos spl_pos(const double* ic, double xn) {
   SplPos p;
-  const double x0 = DEB_LDG(x + i), x1 = DEB_LDG(x + i + 1);
-  p.h = x1 - x0;
-  const double t = (xn - x0) / p.h;
+  p.invh = ic[2];
+  const double t = (xn - ic[0]) * ic[2];
   p.A = 1.0 - t; p.B = t;
-  const double h26 = (p.h * p.h) / 6.0;
+  const double h26 = ic[3];
   p.cA = (p.A * p.A * p.A - p.A) * h26; p.cB = (p.B * p.B * p.B - p.B) * h26;
   p.dA = -(3.0 * p.A * p.A - 1.0) * h26; p.dB = (3.0 * p.B * p.B - 1.0) * h26;
   return p;
 }
-DEB_DEV double spl_at(const Spl& s, int i, const SplPos& p, double) {
-  return p.A * DEB_LDG(s.y + i) + p.B * DEB_LDG(s.y + i + 1) + (p.cA * DEB_LDG(s.S + i) + p.cB * DEB_LDG(s.S + i + 1));
+DEB_DEV double spl_at(const double* v, const SplPos& p, double) {       // v = {y0, y1, S0, S1}
+  return p.A * v[0] + p.B * v[1] + (p.cA * v[2] + p.cB * v[3]);
 }
-DEB_DEV Dual spl_at(const Spl& s, int i, const SplPos& p, Dual xn) {
-  const double y0 = DEB_LDG(s.y + i), y1 = DEB_LDG(s.y + i + 1), S0 = DEB_LDG(s.S + i), S1 = DEB_LDG(s.S + i + 1);
-  return mk(p.A * y0 + p.B * y1 + (p.cA * S0 + p.cB * S1), ((y1 - y0) + (p.dA * S0 + p.dB * S1)) / p.h * xn.d);
+DEB_DEV Dual spl_at(const double* v, const SplPos& p, Dual xn) {
+  return mk(p.A * v[0] + p.B * v[1] + (p.cA * v[2] + p.cB * v[3]), ((v[1] - v[0]) + (p.dA * v[2] + p.dB * v[3])) * p.invh * xn.d);
 }
 
 template <class T>
-DEB_DEV void compute_bg(const Cosmo& c, const NuBins& nb, int nq, T a, Hints& hint, Bg<T>& b) {
+DEB_DEV void compute_bg(const Cosmo& c, const NuBins& nb, int nq, T a, Hints& hint, double* ic, Bg<T>& b) {
   T loga = dlog(a);
-  hint.th = spl_locate(c.cs2a.x, c.cs2a.n, val(loga), hint.th);
-  hint.nu = spl_locate(c.lrn.x, c.lrn.n, val(loga), hint.nu);
-  const SplPos pth = spl_pos(c.cs2a.x, hint.th, val(loga));     // cs2a and xe share their knots
-  const SplPos pnu = spl_pos(c.lrn.x, hint.nu, val(loga));
+  const double lg = val(loga);
+  if (!icache_hit(ic, hint.th, c.cs2a.n, lg)) {
+    hint.th = spl_locate(c.cs2a.x, c.cs2a.n, lg, hint.th);
+    icache_fill(ic, c.cs2a, &c.xe, hint.th);                   // cs2a and xe share their knots
+  }
+  if (!icache_hit(ic + 12, hint.nu, c.lrn.n, lg)) {
+    hint.nu = spl_locate(c.lrn.x, c.lrn.n, lg, hint.nu);
+    icache_fill(ic + 12, c.lrn, nullptr, hint.nu);
+  }
+  const SplPos pth = spl_pos(ic, lg);
+  const SplPos pnu = spl_pos(ic + 12, lg);
   T inva = 1.0 / a;
   T inva2 = inva * inva;
   b.a = a;
-  b.cs2 = spl_at(c.cs2a, hint.th, pth, loga) * inva;
-  T xe = spl_at(c.xe, hint.th, pth, loga);
-  T rhonu = dexp(spl_at(c.lrn, hint.nu, pnu, loga));
+  b.cs2 = spl_at(ic + 4, pth, loga) * inva;
+  T xe = spl_at(ic + 8, pth, loga);
+  T rhonu = dexp(spl_at(ic + 16, pnu, loga));
   T rhoq = dexp(c.rq_exp * loga + 3.0 * c.wa * (a - 1.0));
   b.wq = c.w0 + c.wa * (1.0 - a);
   b.wq1 = 1.0 + b.wq;
@@ -605,7 +630,7 @@ DEB_DEV void compute_metric(const Problem& P, const Cosmo& c, const NuBins& nb, 
     dpnu = dpnu + pickq<T>(nupA, i);
     fnu += nb.w[i] * u[iq0 + nq + i];
   }
-  const double k2 = k * k, ik2 = 1.0 / k2;
+  const double k2 = k * k, ik2 = DEB_RCP(k2);
   T rpt = b.wq1 * b.gq * tq;
   T dgrho = b.gc * dc + b.gb * db + b.gg * dg + b.gr * dr + b.gnu * drhonu + b.gq * dq;
   // 3 dgpres: the 1/3 of the radiation and neutrino pressure cancels against the 3 of (dgrho + 3 dgpres)
@@ -874,15 +899,15 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
     }
     DEB_REGS(double, ks, [7][NE]);    // stage vectors k_1..k_7: registers, scoped to one step (dead while W is factored)
     const double dt = tnext - t;
-    const double invdt = 1.0 / dt;
-    const double idg = 1.0 / (dt * RD_GAMMA);      // diagonal of W = I/(gamma dt) - J
-    const double invt0 = 1.0 / t;
+    const double invdt = DEB_RCP(dt);
+    const double idg = DEB_RCP(dt * RD_GAMMA);      // diagonal of W = I/(gamma dt) - J
+    const double invt0 = DEB_RCP(t);
 
     // ================= Jacobian pieces at (t, y) =================
     double x0piv;      // W_00 = 1/(gamma dt) - d(H a)/da
     {
       Bg<Dual> bd;
-      compute_bg<Dual>(c, nb, nq, mk(W.y()[0], 1.0), hint, bd);
+      compute_bg<Dual>(c, nb, nq, mk(W.y()[0], 1.0), hint, W.ic(), bd);
       DEB_LANES_BEGIN
         if (lane < nch) chain_coeffs_lane<Dual>(c, nb, bd, k, lane, W.y(), P.iq0, W.kc(), W.kap(), W.nur(), W.nup(), W.sl());
         if (lane == 0) fill_slots<Dual>(c, bd, k, W.sl());
@@ -942,7 +967,7 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
           const double kc = W.kc()[lane], kp = W.kap()[lane];
           // row L (truncation): diag = idg + kap + (L+1)/tau, lower = -kc
           double e = idg + kp + (double)(L + 1) * invt0;
-          double ie = 1.0 / e;
+          double ie = DEB_RCP(e);
           int idx = base + L * s;
           W.ie()[idx] = ie;
           W.g()[idx] = kc * ie;                      // -W_{L,L-1}/e_L
@@ -954,7 +979,7 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
             W.m()[idx] = mm;
             if (l >= 3) {
               e = idg + kp - mm * lower_next;
-              ie = 1.0 / e;
+              ie = DEB_RCP(e);
               W.ie()[idx] = ie;
               lower_next = -kc * C.cl[l];
               W.g()[idx] = -lower_next * ie;
@@ -1012,7 +1037,7 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
         }
         pivl = piv; fmul = 0.0;
         if (lane < nhb && j < hi) {
-          const double ipv = 1.0 / hrow(W, piv, lo)[j];
+          const double ipv = DEB_RCP(hrow(W, piv, lo)[j]);
           if (lane == piv) { pcol = j; rscale = ipv; W.perm()[j] = piv; }
           else fmul = hrow(W, lane, lo)[j] * ipv;
         }
@@ -1063,7 +1088,7 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
     double ci_hh, ci_he, ci_eh, ci_ee, jq_h, jq_e;     // inverse capacitance; a h' row applied to qh, qe
     {
       const double c_hh = 1.0 - DEB_WARP_SUM(s1), c_he = -DEB_WARP_SUM(s2), c_eh = -DEB_WARP_SUM(s3), c_ee = 1.0 - DEB_WARP_SUM(s4);
-      const double idet = 1.0 / (c_hh * c_ee - c_he * c_eh);
+      const double idet = DEB_RCP(c_hh * c_ee - c_he * c_eh);
       ci_hh = c_ee * idet; ci_he = -c_he * idet; ci_eh = -c_eh * idet; ci_ee = c_hh * idet;
       DEB_LANES_BEGIN
         DEB_USE(pcol); DEB_USE(s1); DEB_USE(s2);
@@ -1099,14 +1124,14 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
         DEB_LANES_END
         // ---- f(ts, u) + dt d_i dT + sum_j C_ij/dt k_j  -> r ----
         Bg<double> b;
-        compute_bg<double>(c, nb, nq, W.u()[0], hint, b);
+        compute_bg<double>(c, nb, nq, W.u()[0], hint, W.ic(), b);
         DEB_LANES_BEGIN
           if (lane < nch) chain_coeffs_lane<double>(c, nb, b, k, lane, W.u(), P.iq0, W.kc(), W.kap(), W.nur(), W.nup(), W.sl());
           if (lane == 0) fill_slots<double>(c, b, k, W.sl());
         DEB_LANES_END
         Metric<double> mt;
         compute_metric<double>(P, c, nb, b, W.u(), k, W.nur(), W.nup(), mt);
-        const double invts = 1.0 / ts;
+        const double invts = DEB_RCP(ts);
         DEB_LANES_BEGIN
           DEB_USE(ks);
           switch (st) {
@@ -1241,7 +1266,7 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
     // ================= error norm, PID controller (diffrax semantics) =================
     {
       const bool anynan = DEB_ANY(nanflag) != 0;
-      const double ik2 = 1.0 / k2;
+      const double ik2 = DEB_RCP(k2);
 #define DEB_ERRC(e, w) { double y0v = W.y()[e], y1v = anynan ? y0v : W.u()[e], ev = W.r()[e]; if (ev != ev) ev = INFINITY; \
         double sc = ev / (P.atol + fmax(fabs(y0v), fabs(y1v)) * P.rtol) * (w); errnorm2 += sc * sc; }
       DEB_ERRC(0, 1.0) DEB_ERRC(2, k2) DEB_ERRC(3, 1.0) DEB_ERRC(5, 1.0) DEB_ERRC(6, ik2) DEB_ERRC(7, 1.0)

@@ -28,29 +28,30 @@ __global__ void k_tau_out(Problem P, double* tau_out) {
   tau_out[i] = spl_eval(s, P.aexp_out[j]);
 }
 
-static __host__ __device__ size_t cta_smem_bytes(int np) {
+static __host__ __device__ size_t warp_ws_bytes(int np) { return ((warp_ws_doubles(np) * sizeof(double)) + 15) & ~(size_t)15; }
+static __host__ __device__ size_t cta_smem_bytes(int np, int warps) {
   size_t b = sizeof(CtaConst);
   b = (b + 15) & ~(size_t)15;
   b += (size_t)np * sizeof(int);
   b = (b + 15) & ~(size_t)15;
-  b += warp_ws_doubles(np) * sizeof(double);
+  b += warps * warp_ws_bytes(np);
   return b;
 }
 
 // MINB = resident CTAs per SM the register allocation must allow.  1 -> 255 registers (lowest latency per
 // mode); 12 -> 168 registers, which at n <= 128 (14 NE registers hold the stage vectors) raises the
 // number of modes in flight per SM from 8 to 12: +33 % throughput on large batches, -4 % on small ones.
-template <int NE, int MINB>
-__global__ void __launch_bounds__(32, MINB) k_evolve(const __grid_constant__ Problem P) {
+template <int NE, int MINB, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS, MINB) k_evolve(const __grid_constant__ Problem P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CtaConst* C = reinterpret_cast<CtaConst*>(smem_raw);
   size_t off = (sizeof(CtaConst) + 15) & ~(size_t)15;
   int* tail = reinterpret_cast<int*>(smem_raw + off);
   off = (off + (size_t)P.np * sizeof(int) + 15) & ~(size_t)15;
-  double* wsb = reinterpret_cast<double*>(smem_raw + off);
-  const int lane = threadIdx.x & 31;
-  init_cta_const(P, *C, tail, lane, 32);
-  __syncwarp();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* wsb = reinterpret_cast<double*>(smem_raw + off + warp * warp_ws_bytes(P.np));
+  init_cta_const(P, *C, tail, threadIdx.x, 32 * WARPS);
+  if (WARPS > 1) __syncthreads(); else __syncwarp();
   WarpWs W;
   carve(W, wsb, P.np);
   const int total = P.ncosmo * P.nk;
@@ -68,13 +69,17 @@ __global__ void __launch_bounds__(32, MINB) k_evolve(const __grid_constant__ Pro
 }
 
 typedef void (*evolve_kernel_t)(const Problem);
-static evolve_kernel_t pick_kernel(int n, bool many_modes) {
+static evolve_kernel_t pick_kernel(int n, bool many_modes, int* warps) {
   int ne = (n + 31) / 32;
-  if (ne <= 3) return many_modes ? k_evolve<3, 12> : k_evolve<3, 1>;
-  if (ne <= 4) return many_modes ? k_evolve<4, 12> : k_evolve<4, 1>;
-  if (ne <= 6) return k_evolve<6, 1>;
-  if (ne <= 9) return k_evolve<9, 1>;
-  if (ne <= 12) return k_evolve<12, 1>;
+  *warps = 1;
+  if (ne <= 3) return many_modes ? k_evolve<3, 12, 1> : k_evolve<3, 1, 1>;
+  if (ne <= 4) return many_modes ? k_evolve<4, 12, 1> : k_evolve<4, 1, 1>;
+  if (ne <= 6) return k_evolve<6, 1, 1>;
+  // large batches at n <= 288: 4 warps share one CTA's constant tables (same 8 modes per SM, 255 registers;
+  // 10 or 9 modes per SM at 204 / 227 registers spill and measured 1.3-1.5x slower)
+  if (ne <= 9 && many_modes) { *warps = 4; return k_evolve<9, 2, 4>; }
+  if (ne <= 9) return k_evolve<9, 1, 1>;
+  if (ne <= 12) return k_evolve<12, 1, 1>;
   return nullptr;
 }
 
@@ -82,17 +87,18 @@ static int launch_evolve(const Problem& P, cudaStream_t st) {
   int dev = 0, nsm = 0, occ = 0;
   CUDA_TRY(cudaGetDevice(&dev));
   CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-  evolve_kernel_t kern = pick_kernel(P.n, (long)P.ncosmo * P.nk > (long)nsm * 8);
+  int warps = 1;
+  evolve_kernel_t kern = pick_kernel(P.n, (long)P.ncosmo * P.nk > (long)nsm * 8, &warps);
   if (!kern) return DEB_E_UNSUPPORTED;
-  size_t smem = cta_smem_bytes(P.np);
+  size_t smem = cta_smem_bytes(P.np, warps);
   CUDA_TRY(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)kern, 32, smem));
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)kern, 32 * warps, smem));
   if (occ < 1) return DEB_E_UNSUPPORTED;
   long total = (long)P.ncosmo * P.nk;
   long grid = (long)nsm * occ;
-  if (grid > total) grid = total;
+  if (grid * warps > total) grid = (total + warps - 1) / warps;
   CUDA_TRY(cudaMemsetAsync(P.ticket, 0, sizeof(unsigned int), st));
-  kern<<<(unsigned)grid, 32, smem, st>>>(P);
+  kern<<<(unsigned)grid, 32 * warps, smem, st>>>(P);
   CUDA_TRY(cudaGetLastError());
   return DEB_OK;
 }
