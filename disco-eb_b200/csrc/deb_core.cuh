@@ -549,13 +549,14 @@ template <class T>
 DEB_DEV void compute_bg(const Cosmo& c, const NuBins& nb, int nq, T a, Hints& hint, double* ic, Bg<T>& b) {
   T loga = dlog(a);
   const double lg = val(loga);
-  if (!icache_hit(ic, hint.th, c.cs2a.n, lg)) {
-    hint.th = spl_locate(c.cs2a.x, c.cs2a.n, lg, hint.th);
-    icache_fill(ic, c.cs2a, &c.xe, hint.th);                   // cs2a and xe share their knots
-  }
-  if (!icache_hit(ic + 12, hint.nu, c.lrn.n, lg)) {
-    hint.nu = spl_locate(c.lrn.x, c.lrn.n, lg, hint.nu);
-    icache_fill(ic + 12, c.lrn, nullptr, hint.nu);
+  // (all lanes take the same branch: the test reads the cache before anyone refills it; the refill writes the
+  //  same values from every lane, fenced on both sides)
+  const bool miss_th = !icache_hit(ic, hint.th, c.cs2a.n, lg), miss_nu = !icache_hit(ic + 12, hint.nu, c.lrn.n, lg);
+  if (miss_th || miss_nu) {
+    DEB_SYNC();
+    if (miss_th) { hint.th = spl_locate(c.cs2a.x, c.cs2a.n, lg, hint.th); icache_fill(ic, c.cs2a, &c.xe, hint.th); }   // cs2a, xe share knots
+    if (miss_nu) { hint.nu = spl_locate(c.lrn.x, c.lrn.n, lg, hint.nu); icache_fill(ic + 12, c.lrn, nullptr, hint.nu); }
+    DEB_SYNC();
   }
   const SplPos pth = spl_pos(ic, lg);
   const SplPos pnu = spl_pos(ic + 12, lg);
@@ -1165,6 +1166,7 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
 
       // ---- solve W x = r in place ----
       const double x0 = W.r()[0] / x0piv;
+      DEB_SYNC();          // every lane has read r[0] before lane 0 overwrites it with x0
       DEB_LANES_BEGIN
         DEB_FOR_OWN(W.r()[e] = (e == 0) ? x0 : W.r()[e] + W.ja()[e] * x0;)
       DEB_LANES_END
@@ -1271,6 +1273,7 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
         double sc = ev / (P.atol + fmax(fabs(y0v), fabs(y1v)) * P.rtol) * (w); errnorm2 += sc * sc; }
       DEB_ERRC(0, 1.0) DEB_ERRC(2, k2) DEB_ERRC(3, 1.0) DEB_ERRC(5, 1.0) DEB_ERRC(6, ik2) DEB_ERRC(7, 1.0)
 #undef DEB_ERRC
+      DEB_SYNC();          // y, u, r are rewritten below (output sampling, accepted state)
     }
     const double E = sqrt(errnorm2 / 6.0);
     const bool keep = (P.mode == 3) ? (DEB_LDG(P.rp_keep + (size_t)mode * P.rp_stride + nsteps) != 0) : (E < 1.0);

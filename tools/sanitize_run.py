@@ -1,0 +1,15 @@
+"""Tiny workload for compute-sanitizer (memcheck / racecheck / synccheck)."""
+import os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "disco-eb_b200")); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import helpers
+from discoeb_b200 import _cabi
+lib = _cabi.default_library()
+tab = helpers.load_tables("fiducial")
+for dm, nk in (((11, 11, 11, 8, 3), 6), ((31, 31, 31, 31, 5), 4)):
+    lg, lp, lr, ln, nq = dm
+    ks = np.geomspace(1e-3, 0.05, nk)
+    dims = _cabi.make_dims(ncosmo=1, nk=nk, nout=2, lmaxg=lg, lmaxgp=lp, lmaxr=lr, lmaxnu=ln, nqmax=nq, nth=tab.nth, nnu=tab.nnu, max_steps=60, power_idx=4)
+    out = lib.evolve_host(dims, _cabi.make_ctrl(rtol=1e-3, atol=1e-3), tab.scalars[None], tab.tables[None], ks, np.array([0.001, 0.002]), want_pk=True)
+    print("n", lib.nvar(*dm), "status", out["status"][0], "steps", out["nsteps"][0])
