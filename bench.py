@@ -45,6 +45,9 @@ WORKLOAD = dict(name="config2: LCDM + 1 massive nu, lmax=31 (32 multipoles), nq=
 METRIC = "k-modes/sec (ms per P(k), N_k=512, in ms_per_step)"
 
 
+NCU_DRAM_BYTES_PER_LAUNCH = 935680 + 29184     # ncu --set full, k_evolve<9>, 512 modes (profiles/r1_v6_k_evolve9_ncu_summary.txt)
+
+
 def f_step(n):
     return 370.0 * n + 3000.0
 
@@ -236,17 +239,21 @@ def run_ours(args, rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_dev, e2e = float(t[0]), float(t[1])
     if rank == 0:
-        peak, _ = lib.fp64_peak_tflops(local)
-        flops = total_steps * f_step(n)
+        peak1, _ = lib.fp64_peak_tflops(local)
+        peak = peak1 * world
+        flops = world * total_steps * f_step(n)          # every rank integrates the same number of steps
         achieved = flops / (ms_dev * 1e-3) / 1e12
         line = dict(metric=METRIC, value=world * nk / (ms_dev * 1e-3), unit="k-modes/s", n_gpus=world, steps=args.steps,
                     warmup=max(args.warmup, 3), ms_per_step=ms_dev, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype="f64", data="synthetic",
                     config=dict(workload=WORKLOAD["name"], modes_per_gpu=nk, attempted_steps_per_pass=total_steps,
                                 l2="flushed between timed iterations (256 MB write)", parallelism=f"k-modes x{world} (independent batches, all-gather of y)"),
-                    roofline=dict(bound="fp64", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=None,
-                                  note="FP64 FMA pipe; peak measured on this GPU by deb_fp64_peak_tflops (dependent-free DFMA streams); "
-                                       "algorithmic flops = (370 n + 3000) x attempted steps, n=265"),
+                    roofline=dict(bound="fp64", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak,
+                                  traffic=NCU_DRAM_BYTES_PER_LAUNCH,
+                                  note="FP64 FMA pipe (the path is neither HBM- nor tensor-bound); peak measured on this GPU by "
+                                       "deb_fp64_peak_tflops (dependent-free DFMA streams) x n_gpus; algorithmic flops = "
+                                       "(370 n + 3000) x attempted steps, n=265; traffic = dram bytes read+written per k_evolve "
+                                       "launch from profiles/r1_v6_k_evolve9_ncu_summary.txt (0.96 MB: HBM is idle)"),
                     e2e=dict(value=world * nk / (e2e * 1e-3), unit="k-modes/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
                              ms_per_step=e2e),
                     gpu_launches=2 * args.steps, clocks=clocks)

@@ -39,7 +39,7 @@ def load_case(name):
     return {k: z[k] for k in z.files}
 
 
-CASES = ("default_n72", "config1_n111", "config2_n265", "w0wa_n72", "odd_dims_n43")
+CASES = ("default_n72", "config1_n111", "config2_n265", "w0wa_n72", "odd_dims_n43", "min_dims_n33", "many_out_n72")
 
 
 def field_scaled_diff(a, b):

@@ -80,3 +80,17 @@ def test_two_cosmologies_in_one_call(emu_lib, tables):
     assert np.array_equal(both["y"][0], one_a["y"][0])
     assert np.array_equal(both["y"][1], one_b["y"][0])
     assert not np.allclose(both["y"][0], both["y"][1], rtol=1e-6)
+
+
+def test_per_cosmology_k_grids(emu_lib, tables):
+    """k_per_cosmo=1: every cosmology of a batch brings its own k grid (what a caller that scales
+    kmin/kmax by h needs)."""
+    from discoeb_b200 import _cabi
+    a, b = tables["fiducial"], tables["w0wa"]
+    k2 = np.stack([np.geomspace(1e-3, 0.5, 4), np.geomspace(2e-3, 1.0, 4)])
+    mk = lambda nc, kp: _cabi.make_dims(ncosmo=nc, nk=4, nout=1, lmaxg=11, lmaxgp=11, lmaxr=11, lmaxnu=8, nqmax=3,
+                                        nth=a.nth, nnu=a.nnu, max_steps=4096, k_per_cosmo=kp)
+    ctrl = _cabi.make_ctrl(rtol=1e-4, atol=1e-4)
+    both = emu_lib.evolve_host(mk(2, True), ctrl, np.stack([a.scalars, b.scalars]), np.stack([a.tables, b.tables]), k2, np.array([1.0]))
+    one_b = emu_lib.evolve_host(mk(1, False), ctrl, b.scalars[None], b.tables[None], k2[1], np.array([1.0]))
+    assert np.array_equal(both["y"][1], one_b["y"][0])

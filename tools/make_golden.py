@@ -38,7 +38,16 @@ CASES = {
     "config2_n265": ("fiducial", (31, 31, 31, 31, 5), np.array([1e-3, 0.03, 0.3, 3.0]), [0.01, 1.0], 1e-4),
     "w0wa_n72": ("w0wa", (11, 11, 11, 8, 3), np.array([1e-3, 0.1, 1.0]), [0.5, 1.0], 1e-5),
     "odd_dims_n43": ("fiducial", (5, 4, 6, 3, 4), np.array([2e-3, 0.2]), [0.1], 1e-3),
+    "min_dims_n33": ("fiducial", (3, 3, 3, 3, 3), np.array([0.01, 0.3]), [0.05, 0.2, 1.0], 1e-4),       # tails of length 1
+    "many_out_n72": ("w0wa", (11, 11, 11, 8, 3), np.array([1e-3, 0.05]), list(np.geomspace(1e-3, 1.0, 8)), 1e-5),
 }
+
+
+def helpers_param(name):
+    """Rebuild the oracle param dict from the committed tables (keeps existing fixtures bit-stable)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    return helpers.load_tables(name).param()
 
 
 def make_tables():
@@ -79,8 +88,11 @@ def run_case(p, dims, ks, aout, rtol, max_steps=4096):
 
 
 def main():
-    params = make_tables()
+    only = sys.argv[1:]
+    params = make_tables() if not only else {c: helpers_param(c) for c in COSMOLOGIES}
     for name, (cos, dims, ks, aout, rtol) in CASES.items():
+        if only and name not in only:
+            continue
         t = time.time()
         out = run_case(params[cos], dims, np.asarray(ks, dtype=np.float64), aout, rtol)
         np.savez_compressed(os.path.join(GOLD, f"oracle_{name}.npz"), cosmology=cos, **out)
