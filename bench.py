@@ -183,7 +183,7 @@ def run_ours(args, rank, world):
     d_st = torch.zeros((1, nk), dtype=torch.int32, device=dev)
     d_ns = torch.zeros((1, nk), dtype=torch.int32, device=dev)
     d_na = torch.zeros((1, nk), dtype=torch.int32, device=dev)
-    d_ws = torch.zeros(64, dtype=torch.int32, device=dev)
+    d_ws = torch.zeros(1024, dtype=torch.int32, device=dev)       # >= deb_workspace_bytes(dims) = 256 + 8 ncosmo
     gathered = torch.zeros((world, nk, nout, 20), **f64) if world > 1 else None
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)      # > 126 MB L2
 
@@ -191,7 +191,7 @@ def run_ours(args, rank, world):
         st = torch.cuda.current_stream().cuda_stream
         rc = lib.lib.deb_evolve_f64(C.byref(dims), C.byref(ctrl), d_sc.data_ptr(), d_tb.data_ptr(), d_k.data_ptr(), d_a.data_ptr(),
                                     d_y.data_ptr(), d_pk.data_ptr(), d_tau.data_ptr(), d_st.data_ptr(), d_ns.data_ptr(),
-                                    d_na.data_ptr(), d_ws.data_ptr(), C.c_size_t(256), C.c_void_p(st))
+                                    d_na.data_ptr(), d_ws.data_ptr(), C.c_size_t(4096), C.c_void_p(st))
         if rc != 0:
             raise RuntimeError(lib.strerror(rc))
         if world > 1:

@@ -244,6 +244,7 @@ struct Problem {
   double rtol, atol, c1, c2, c3, factormax, factormin, safety;
   const double* scalars; const double* tables; const double* kmodes; const double* aexp_out;
   const double* tau_out;                         // [ncosmo, nout] (filled by the tau_out pre-kernel)
+  const double* lt_small;                        // [ncosmo] log tau of the k-independent start-time root (pre-kernel)
   double* y_out; double* pk_out;
   int* status; int* nsteps; int* naccept;
   // debug single-step mode
@@ -456,7 +457,7 @@ struct WarpWs {
   double* j1_;   // d f_1/d y_c (the a h' row) [NHMAX]
   double* qh_;   // D^-1 (coefficient of h' per row) [NHMAX]
   double* qe_;   // D^-1 (coefficient of eta' per row) [NHMAX]
-  double* xb_;   // gather buffer of the head solve [NHMAX]
+  double* xb_;   // gather buffer of the head solve [NHMAX + 8], the last 8 stay zero
   double* kc_;   // chain wavenumber k or k v_i (value, d/da) [2*NCHMAX]
   double* kap_;   // chain damping opac or 0 (value, d/da) [2*NCHMAX]
   double* nur_;   // w_i psi0_i / v_i (value, d/da) [2*NQMAX]
@@ -489,13 +490,13 @@ struct WarpWs {
   DEB_DEV Cosmo* cosmo() const { return cosmo_; }
 };
 DEB_HD size_t warp_ws_doubles(int np) {
-  return (size_t)7 * np + NHMAX * LDB + 6 * NHMAX + 4 * NCHMAX + 4 * NQMAX + 2 * NSLOT + ICACHE + NHMAX / 2 + 2 + (sizeof(Cosmo) + 7) / 8;
+  return (size_t)7 * np + NHMAX * LDB + 6 * NHMAX + 8 + 4 * NCHMAX + 4 * NQMAX + 2 * NSLOT + ICACHE + NHMAX / 2 + 2 + (sizeof(Cosmo) + 7) / 8;
 }
 DEB_DEV void carve(WarpWs& W, double* base, int np) {
   W.y_ = base; W.u_ = W.y_ + np; W.r_ = W.u_ + np; W.m_ = W.r_ + np; W.ie_ = W.m_ + np; W.g_ = W.ie_ + np; W.ja_ = W.g_ + np;
   W.lu_ = W.ja_ + np; W.gh_ = W.lu_ + NHMAX * LDB; W.ge_ = W.gh_ + NHMAX; W.j1_ = W.ge_ + NHMAX;
   W.qh_ = W.j1_ + NHMAX; W.qe_ = W.qh_ + NHMAX; W.xb_ = W.qe_ + NHMAX;
-  W.kc_ = W.xb_ + NHMAX; W.kap_ = W.kc_ + 2 * NCHMAX; W.nur_ = W.kap_ + 2 * NCHMAX; W.nup_ = W.nur_ + 2 * NQMAX;
+  W.kc_ = W.xb_ + NHMAX + 8; W.kap_ = W.kc_ + 2 * NCHMAX; W.nur_ = W.kap_ + 2 * NCHMAX; W.nup_ = W.nur_ + 2 * NQMAX;
   W.sl_ = W.nup_ + 2 * NQMAX;
   W.ic_ = W.sl_ + 2 * NSLOT;
   W.perm_ = (int*)(W.ic_ + ICACHE);
@@ -715,20 +716,25 @@ DEB_DEV double cond_large_k(const Cosmo& c, double lt, double k) {
   double a = spl_eval(c.a_of_tau, exp(lt));
   return (1.0 / aprimeoa_plain(c, a)) / (1.0 / k) / 0.07 - 1.0;
 }
-DEB_DEV double start_time(const Cosmo& c, double k) {
-  double l0 = log(c.taumin), l1 = log(spl_eval(c.tau_of_a, 0.1));
-  double xl = l0, xr = l1;
+// util.py:365-396 keeps [mid, right] when f(mid) f(left) > 0.  f(left) is carried along instead of being
+// re-evaluated (same function at the same point: identical value), which halves the spline lookups.
+DEB_DEV double start_small_k(const Cosmo& c) {          // k-independent root: once per cosmology
+  double xl = log(c.taumin), xr = log(spl_eval(c.tau_of_a, 0.1));
+  double fl = cond_small_k(c, xl);
   for (int it = 0; it < 7; ++it) {
-    double xm = 0.5 * (xl + xr);
-    if (cond_large_k(c, xm, k) * cond_large_k(c, xl, k) > 0) xl = xm; else xr = xm;
+    const double xm = 0.5 * (xl + xr), fm = cond_small_k(c, xm);
+    if (fm * fl > 0) { xl = xm; fl = fm; } else xr = xm;
   }
-  double lt_large = 0.5 * (xl + xr);
-  xl = l0; xr = l1;
+  return 0.5 * (xl + xr);
+}
+DEB_DEV double start_time(const Cosmo& c, double k, double lt_small) {
+  double xl = log(c.taumin), xr = log(spl_eval(c.tau_of_a, 0.1));
+  double fl = cond_large_k(c, xl, k);
   for (int it = 0; it < 7; ++it) {
-    double xm = 0.5 * (xl + xr);
-    if (cond_small_k(c, xm) * cond_small_k(c, xl) > 0) xl = xm; else xr = xm;
+    const double xm = 0.5 * (xl + xr), fm = cond_large_k(c, xm, k);
+    if (fm * fl > 0) { xl = xm; fl = fm; } else xr = xm;
   }
-  double lt_small = 0.5 * (xl + xr);
+  const double lt_large = 0.5 * (xl + xr);
   return exp(fmin(lt_small, lt_large));
 }
 
@@ -870,7 +876,7 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
       for (int e = lane; e < n; e += 32) W.y()[e] = DEB_LDG(P.dbg_y0 + (size_t)mode * n + e);
     DEB_LANES_END
   } else {
-    double tau_start = 0.99 * fmin(tmin_out, start_time(c, k));
+    double tau_start = 0.99 * fmin(tmin_out, start_time(c, k, DEB_LDG(P.lt_small + cosmo)));
     IcScalars ics = ic_scalars(c, tau_start, k);
     DEB_LANES_BEGIN
       for (int e = lane; e < n; e += 32) W.y()[e] = ic_value(P, c, nb, ics, elem_desc(P, e), k);
@@ -999,7 +1005,8 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
         if (lane < nhb) {
           const int ty = C.htype[lane], lo = C.blo[lane], hi = C.bhi[lane];
           double* row = hrow(W, lane, lo);
-          for (int cc = lo; cc < hi; ++cc) row[cc] = 0.0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) row[lo + i] = 0.0;        // all 8 slots: the unused ones stay zero for the fixed-length loops
           double diag = idg;
           if (ty == R_F2 || ty == R_G2 || ty == R_N2 || ty == R_P2) {      // Schur complement of the chain tail
             const int chain = ty == R_F2 ? 0 : (ty == R_G2 ? 1 : (ty == R_N2 ? 2 : 3 + C.hbin[lane]));
@@ -1050,10 +1057,14 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
           double* row = hrow(W, lane, lo);
           if (lane == pivl) row[j] = 1.0;
           else {
-            const double* prow = hrow(W, pivl, lo);
+            const double* rb = row + lo;
+            const double* pb = hrow(W, pivl, lo) + lo;
             const double f = fmul;
-            for (int cc = lo; cc < hi; ++cc) if (cc != j) row[cc] -= f * prow[cc];
-            row[j] = -f;
+            double ra[8], pa[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { ra[i] = rb[i]; pa[i] = pb[i]; }     // slots beyond the block hold zeros
+#pragma unroll
+            for (int i = 0; i < 8; ++i) row[lo + i] = (i == bt) ? -f : ra[i] - f * pa[i];
           }
         }
       DEB_LANES_END
@@ -1062,8 +1073,12 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
     DEB_LANES_BEGIN
       DEB_USE(rscale);
       if (lane < nhb) {
-        double* row = hrow(W, lane, C.blo[lane]);
-        for (int cc = C.blo[lane]; cc < C.bhi[lane]; ++cc) row[cc] *= rscale;
+        double* rb = hrow(W, lane, C.blo[lane]) + C.blo[lane];
+        double ra[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ra[i] = rb[i];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rb[i] = ra[i] * rscale;
       }
       // right-hand sides of the two Woodbury solves, gathered in pivot order
       W.xb()[lane] = 0.0;
@@ -1192,15 +1207,20 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
       // head: p = D^-1 b (block inverses), then the rank-2 Woodbury correction and the a h' row
       DEB_LANES_BEGIN
         W.xb()[lane] = lane < nhb ? W.r()[C.hidx[W.perm()[lane]]] : 0.0;
+        if (lane < 8) W.xb()[NHMAX + lane] = 0.0;
       DEB_LANES_END
       DEB_LANES_BEGIN
         DEB_USE(pcol); DEB_USE(s1); DEB_USE(s2); DEB_USE(s3); DEB_USE(pval);
         s1 = s2 = s3 = 0.0; pval = 0.0;
         if (lane < nhb) {
           const int lo = C.blo[lane];
-          const double* row = hrow(W, lane, lo);
-          double acc = 0.0;
-          for (int cc = lo; cc < C.bhi[lane]; ++cc) acc += row[cc] * W.xb()[cc];
+          const double* rb = hrow(W, lane, lo) + lo;
+          const double* xb = W.xb() + lo;
+          double ra[8], xa[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { ra[i] = rb[i]; xa[i] = xb[i]; }      // zero slots x finite padding
+          const double acc = ((ra[0] * xa[0] + ra[1] * xa[1]) + (ra[2] * xa[2] + ra[3] * xa[3]))
+                           + ((ra[4] * xa[4] + ra[5] * xa[5]) + (ra[6] * xa[6] + ra[7] * xa[7]));
           pval = acc;                       // p_c for the column c = pcol this lane's row became
           s1 = W.gh()[pcol] * acc; s2 = W.ge()[pcol] * acc; s3 = W.j1()[pcol] * acc;
         }

@@ -20,12 +20,14 @@ using namespace deb;
   fprintf(stderr, "[discoeb_b200] CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return DEB_E_CUDA; } } while (0)
 
 // tau_out[c, j] = tau_of_a_spline(aexp_out[j])   (perturbations.py:975)
-__global__ void k_tau_out(Problem P, double* tau_out) {
+// ... and, once per cosmology, the k-independent root of the start-time search (perturbations.py:679)
+__global__ void k_tau_out(Problem P, double* tau_out, double* lt_small) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P.ncosmo * P.nout) return;
   int c = i / P.nout, j = i - c * P.nout;
   Spl s = get_spline(P, c, T_TAU_OF_A);
-  tau_out[i] = spl_eval(s, P.aexp_out[j]);
+  if (P.aexp_out) tau_out[i] = spl_eval(s, P.aexp_out[j]);
+  if (j == 0) { Cosmo cs = load_cosmo(P, c); lt_small[c] = start_small_k(cs); }
 }
 
 static __host__ __device__ size_t warp_ws_bytes(int np) { return ((warp_ws_doubles(np) * sizeof(double)) + 15) & ~(size_t)15; }
@@ -114,7 +116,7 @@ extern "C" {
 
 int32_t deb_nvar(const deb_dims* d) { return d ? deb_nvar_impl(d) : 0; }
 size_t deb_table_len(const deb_dims* d) { return d ? 3 * (size_t)(5 * d->nth + 2 * d->nnu) : 0; }
-size_t deb_workspace_bytes(const deb_dims* d) { (void)d; return 256; }
+size_t deb_workspace_bytes(const deb_dims* d) { return 256 + 8 * (size_t)(d ? d->ncosmo : 0); }
 const char* deb_strerror(int code) { return deb_strerror_impl(code); }
 int32_t deb_abi_version(void) { return DEB_ABI_VERSION; }
 int32_t deb_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
@@ -134,9 +136,11 @@ int deb_evolve_f64(const deb_dims* dims, const deb_ctrl* ctrl, const double* sca
   P.y_out = y_out; P.pk_out = dims->power_idx >= 0 ? pk_out : nullptr; P.tau_out = tau_out;
   P.status = status; P.nsteps = nsteps; P.naccept = naccept;
   P.ticket = (unsigned int*)workspace;
+  double* lt_small = (double*)((char*)workspace + 256);
+  P.lt_small = lt_small;
   P.mode = 0;
   int nt = P.ncosmo * P.nout;
-  k_tau_out<<<(nt + 127) / 128, 128, 0, st>>>(P, tau_out);
+  k_tau_out<<<(nt + 127) / 128, 128, 0, st>>>(P, tau_out, lt_small);
   CUDA_TRY(cudaGetLastError());
   return launch_evolve(P, st);
 }
@@ -159,7 +163,7 @@ int deb_evolve_host_f64(const deb_dims* dims, const deb_ctrl* ctrl, const double
   DevBuf d_sc, d_tb, d_k, d_a, d_y, d_pk, d_tau, d_st, d_ns, d_na, d_ws;
   if (d_sc.alloc(nc * DEB_NSCAL * 8) || d_tb.alloc(nc * tl * 8) || d_k.alloc(nkm * 8) || d_a.alloc(nout * 8) ||
       d_y.alloc(nc * nk * nout * nf * 8) || d_pk.alloc(pk ? nc * nk * nout * 8 : 8) || d_tau.alloc(nc * nout * 8) ||
-      d_st.alloc(nc * nk * 4) || d_ns.alloc(nc * nk * 4) || d_na.alloc(nc * nk * 4) || d_ws.alloc(256))
+      d_st.alloc(nc * nk * 4) || d_ns.alloc(nc * nk * 4) || d_na.alloc(nc * nk * 4) || d_ws.alloc(deb_workspace_bytes(dims)))
     return DEB_E_CUDA;
   cudaStream_t st;
   CUDA_TRY(cudaStreamCreate(&st));
@@ -176,7 +180,7 @@ int deb_evolve_host_f64(const deb_dims* dims, const deb_ctrl* ctrl, const double
   if (!pk) d2.power_idx = -1;
   rc = deb_evolve_f64(&d2, ctrl, d_sc.as<double>(), d_tb.as<double>(), d_k.as<double>(), d_a.as<double>(),
                       d_y.as<double>(), d_pk.as<double>(), d_tau.as<double>(), d_st.as<int32_t>(), d_ns.as<int32_t>(),
-                      d_na.as<int32_t>(), d_ws.p, 256, (void*)st);
+                      d_na.as<int32_t>(), d_ws.p, deb_workspace_bytes(dims), (void*)st);
   if (rc == DEB_OK) {
     CUDA_TRY(cudaEventRecord(e1, st));
     CUDA_TRY(cudaMemcpyAsync(y_out, d_y.p, nc * nk * nout * nf * 8, cudaMemcpyDeviceToHost, st));
@@ -209,7 +213,7 @@ static int debug_common(const deb_dims* dims, const deb_ctrl* ctrl, const double
   const size_t nf = dims->return_full ? n : 20;
   DevBuf d_sc, d_tb, d_k, d_a, d_tau, d_st, d_ns, d_ws, d_t0, d_t1, d_y0, d_oa, d_ob, d_rt, d_rk, d_rn, d_y;
   if (d_sc.alloc(nc * DEB_NSCAL * 8) || d_tb.alloc(nc * tl * 8) || d_k.alloc(nkm * 8) || d_a.alloc(nout * 8) ||
-      d_tau.alloc(nc * nout * 8) || d_st.alloc(total * 4) || d_ns.alloc(total * 4) || d_ws.alloc(256) ||
+      d_tau.alloc(nc * nout * 8) || d_st.alloc(total * 4) || d_ns.alloc(total * 4) || d_ws.alloc(deb_workspace_bytes(dims)) ||
       d_t0.alloc(total * 8) || d_t1.alloc(total * 8) || d_y0.alloc(total * n * 8) || d_oa.alloc(total * nper * 8) ||
       d_ob.alloc(total * n * 8) || d_rt.alloc(total * (size_t)rp_stride * 8 + 8) || d_rk.alloc(total * (size_t)rp_stride * 4 + 8) ||
       d_rn.alloc(total * 4) || d_y.alloc(total * nout * nf * 8))
@@ -220,15 +224,19 @@ static int debug_common(const deb_dims* dims, const deb_ctrl* ctrl, const double
   P.scalars = d_sc.as<double>(); P.tables = d_tb.as<double>(); P.kmodes = d_k.as<double>();
   P.tau_out = d_tau.as<double>(); P.status = d_st.as<int>(); P.nsteps = d_ns.as<int>(); P.naccept = nullptr;
   P.ticket = (unsigned int*)d_ws.p; P.mode = mode; P.y_out = d_y.as<double>();
+  double* lt_small = (double*)((char*)d_ws.p + 256);
+  P.lt_small = lt_small;
   if (aexp_out) {
     CUDA_TRY(cudaMemcpy(d_a.p, aexp_out, nout * 8, cudaMemcpyHostToDevice));
     P.aexp_out = d_a.as<double>();
-    int nt = P.ncosmo * P.nout;
-    k_tau_out<<<(nt + 127) / 128, 128>>>(P, d_tau.as<double>());
-    CUDA_TRY(cudaGetLastError());
   } else {
     std::vector<double> ones(nc * nout, 1.0);
     CUDA_TRY(cudaMemcpy(d_tau.p, ones.data(), nc * nout * 8, cudaMemcpyHostToDevice));
+  }
+  {
+    int nt = P.ncosmo * P.nout;
+    k_tau_out<<<(nt + 127) / 128, 128>>>(P, d_tau.as<double>(), lt_small);
+    CUDA_TRY(cudaGetLastError());
   }
   if (mode == 1) {
     CUDA_TRY(cudaMemcpy(d_t0.p, in_t0, total * 8, cudaMemcpyHostToDevice));

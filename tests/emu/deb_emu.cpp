@@ -13,11 +13,16 @@
 
 using namespace deb;
 
-static void tau_out_host(const Problem& P, double* tau_out) {
+static std::vector<double> g_lt_small;       // per call; the harness is single-caller
+static void tau_out_host(Problem& P, double* tau_out) {
+  g_lt_small.assign(P.ncosmo, 0.0);
   for (int c = 0; c < P.ncosmo; ++c) {
     Spl s = get_spline(P, c, T_TAU_OF_A);
-    for (int j = 0; j < P.nout; ++j) tau_out[(size_t)c * P.nout + j] = spl_eval(s, P.aexp_out[j]);
+    if (P.aexp_out) for (int j = 0; j < P.nout; ++j) tau_out[(size_t)c * P.nout + j] = spl_eval(s, P.aexp_out[j]);
+    Cosmo cs = load_cosmo(P, c);
+    g_lt_small[c] = start_small_k(cs);
   }
+  P.lt_small = g_lt_small.data();
 }
 
 template <int NE>
@@ -74,6 +79,7 @@ extern "C" int emu_debug_step_host_f64(const deb_dims* dims, const double* scala
   std::vector<double> tau_out(P.ncosmo, 1.0);
   std::vector<int32_t> st(total), ns(total);
   P.scalars = scalars; P.tables = tables; P.kmodes = kmodes; P.aexp_out = nullptr;
+  tau_out_host(P, tau_out.data());
   P.tau_out = tau_out.data(); P.status = st.data(); P.nsteps = ns.data(); P.naccept = nullptr;
   P.dbg_t0 = t0; P.dbg_t1 = t1; P.dbg_y0 = y0; P.dbg_y1 = y1; P.dbg_err = yerr;
   P.mode = 1;
