@@ -38,6 +38,8 @@
 #define DEB_ARGMAX_U32(name) ([&]() { unsigned m_ = name##_all[0]; int a_ = 0; for (int l_ = 1; l_ < 32; ++l_) if (name##_all[l_] > m_) { m_ = name##_all[l_]; a_ = l_; } return a_; }())
 #define DEB_RSQRT(x) (1.0 / sqrt(x))
 #define DEB_RCP(x) (1.0 / (x))
+#define DEB_BAR_ARRIVE(id)
+#define DEB_BAR_SYNC(id)
 // argmax restricted to the lanes of `mask` (every lane passes the mask of its own group)
 #define DEB_ARGMAX_U32_IN(name, mask) ([&]() { unsigned m_ = 0; int a_ = -1; for (int l_ = 0; l_ < 32; ++l_) if (((mask) >> l_) & 1u) { if (a_ < 0 || name##_all[l_] > m_) { m_ = name##_all[l_]; a_ = l_; } } return a_; }())
 #define DEB_WARP_SUM(name) ([&]() { double s_ = 0.0; for (int l_ = 0; l_ < 32; ++l_) s_ += name##_all[l_]; return s_; }())
@@ -57,6 +59,9 @@
 #define DEB_ARGMAX_U32(name) (__ffs(__ballot_sync(0xffffffffu, (name) == __reduce_max_sync(0xffffffffu, (name)))) - 1)
 #define DEB_RSQRT(x) rsqrt(x)
 #define DEB_RCP(x) __drcp_rn(x)      // correctly rounded reciprocal: same bits as 1.0/x, shorter sequence
+// named barriers of the two-warp (main + helper) variant: 64 threads, producer arrives, consumer syncs
+#define DEB_BAR_ARRIVE(id) asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory")
+#define DEB_BAR_SYNC(id) asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory")
 #define DEB_ARGMAX_U32_IN(name, mask) (__ffs(__ballot_sync(0xffffffffu, (name) == __reduce_max_sync((mask), (name))) & (mask)) - 1)
 #define DEB_WARP_SUM(name) deb::warp_sum(name)
 #endif
@@ -609,6 +614,41 @@ DEB_DEV void chain_coeffs_lane(const Cosmo& c, const NuBins& nb, const Bg<T>& b,
   kapA[ch] = val(kp); kapA[NCHMAX + ch] = der(kp);
 }
 
+// Mailbox of the two-warp variant: the main warp posts the scale factor of the NEXT stage as soon as it is
+// known (x0 is the first thing a solve produces); the helper warp evaluates everything that depends on a alone
+// while the main warp runs the sweeps of the current stage.
+struct HelpBox {
+  double a_req, k;
+  int cmd, seq;                 // cmd: 0 = evaluate, 1 = exit;  seq: bumped per mode (helper resets its cache)
+  double bgs[10];               // H, gc, gb, gg, gr, gnu, gq, wq1, ca2, wq
+  double vv[2 * NQMAX];         // v_i, 1/v_i
+  double ic2[ICACHE];           // the helper's own spline interval cache
+};
+enum { BAR_REQ = 1, BAR_RDY = 2 };
+
+// the a-only half of chain_coeffs_lane (helper warp) ...
+DEB_DEV void chain_a_lane(const Cosmo& c, const NuBins& nb, const Bg<double>& b, double k, int ch, double* kcA, double* kapA,
+                          double* vv, double* sl) {
+  double kc = k;
+  if (ch >= 3) {
+    const int i = ch - 3;
+    const double aq = b.a * (c.amnu / nb.q[i]);
+    const double s2 = 1.0 + aq * aq;
+    const double v = DEB_RSQRT(s2);
+    vv[i] = v; vv[NQMAX + i] = s2 * v;
+    kc = v * k;
+    sl[SL_KV0 + i] = kc;
+  }
+  kcA[ch] = kc;
+  kapA[ch] = ch < 2 ? b.opac : 0.0;
+}
+// ... and the half that needs the stage state (main warp)
+DEB_DEV void nu_moments_lane(const NuBins& nb, const double* vv, const double* u, int iq0, int i, double* nurA, double* nupA) {
+  const double wp0 = nb.w[i] * u[iq0 + i];
+  nurA[i] = vv[NQMAX + i] * wp0;
+  nupA[i] = vv[i] * wp0;
+}
+
 template <class T> DEB_DEV T pick(const double* arr, int i);
 template <> DEB_DEV double pick<double>(const double* arr, int i) { return arr[i]; }
 template <> DEB_DEV Dual pick<Dual>(const double* arr, int i) { return mk(arr[i], arr[NCHMAX + i]); }
@@ -842,8 +882,41 @@ DEB_DEV void convert_outputs(const Problem& P, const Cosmo& c, const NuBins& nb,
 #define DEB_LANE_PARAM , const int lane
 #endif
 
-template <int NE>
-DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int mode DEB_LANE_PARAM) {
+// One evaluation by the helper warp: background at box.a_req -> chain coefficients, operator slots, and the
+// scalars the main warp's metric sources need.
+DEB_DEV void helper_compute(const Problem& P, const CtaConst& C, WarpWs& W, HelpBox& box, Hints& hint2 DEB_LANE_PARAM) {
+  const Cosmo& c = *W.cosmo();
+  const double k = box.k;
+  Bg<double> b;
+  compute_bg<double>(c, C.nu, P.nq, box.a_req, hint2, box.ic2, b);
+  DEB_LANES_BEGIN
+    if (lane < P.nch) chain_a_lane(c, C.nu, b, k, lane, W.kc(), W.kap(), box.vv, W.sl());
+    if (lane == 0) {
+      fill_slots<double>(c, b, k, W.sl());
+      box.bgs[0] = b.H; box.bgs[1] = b.gc; box.bgs[2] = b.gb; box.bgs[3] = b.gg; box.bgs[4] = b.gr; box.bgs[5] = b.gnu;
+      box.bgs[6] = b.gq; box.bgs[7] = b.wq1; box.bgs[8] = b.ca2; box.bgs[9] = b.wq;
+    }
+  DEB_LANES_END
+}
+
+#ifndef DEB_CPU_EMU
+// helper warp of the two-warp variant: serves requests until told to exit
+DEB_DEV void helper_loop(const Problem& P, const CtaConst& C, WarpWs& W, HelpBox& box, const int lane) {
+  Hints hint2; hint2.th = -1; hint2.nu = -1;
+  int seq = -1;
+  for (;;) {
+    DEB_BAR_SYNC(BAR_REQ);
+    if (box.cmd == 1) break;
+    if (box.seq != seq) { seq = box.seq; hint2.th = -1; hint2.nu = -1; }
+    helper_compute(P, C, W, box, hint2, lane);
+    __syncwarp();
+    DEB_BAR_ARRIVE(BAR_RDY);
+  }
+}
+#endif
+
+template <int NE, bool HELPER>
+DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, HelpBox* box, int mode DEB_LANE_PARAM) {
   const int n = P.n, nh = P.nh, nch = P.nch, nq = P.nq;
   const int nhb = nh - 1;            // head unknowns inside diagonal blocks (the last head row is a h')
   const int cosmo = mode / P.nk, kidx = mode - cosmo * P.nk;
@@ -854,6 +927,14 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
   DEB_LANE0_END
   const Cosmo& c = *W.cosmo();
   const NuBins& nb = C.nu;
+#ifdef DEB_CPU_EMU
+  Hints hint2; hint2.th = -1; hint2.nu = -1;      // the emulation runs the helper inline
+#endif
+  if (HELPER) {
+    DEB_LANE0_BEGIN
+      box->k = k; box->cmd = 0; box->seq = mode;
+    DEB_LANE0_END
+  }
   const double* tout = P.tau_out + (size_t)cosmo * P.nout;
 
   DEB_REGS(int, pcol, );           // head inverse: pivot column of this lane's row
@@ -1140,11 +1221,23 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
         DEB_LANES_END
         // ---- f(ts, u) + dt d_i dT + sum_j C_ij/dt k_j  -> r ----
         Bg<double> b;
-        compute_bg<double>(c, nb, nq, W.u()[0], hint, W.ic(), b);
-        DEB_LANES_BEGIN
-          if (lane < nch) chain_coeffs_lane<double>(c, nb, b, k, lane, W.u(), P.iq0, W.kc(), W.kap(), W.nur(), W.nup(), W.sl());
-          if (lane == 0) fill_slots<double>(c, b, k, W.sl());
-        DEB_LANES_END
+        if (HELPER) {
+          DEB_BAR_SYNC(BAR_RDY);                 // the helper finished the evaluation posted during the last solve
+          b.a = box->a_req;
+          b.H = box->bgs[0]; b.gc = box->bgs[1]; b.gb = box->bgs[2]; b.gg = box->bgs[3]; b.gr = box->bgs[4]; b.gnu = box->bgs[5];
+          b.gq = box->bgs[6]; b.wq1 = box->bgs[7]; b.ca2 = box->bgs[8]; b.wq = box->bgs[9];
+          b.opac = W.sl()[SL_OPAC]; b.pbo = W.sl()[SL_PBO]; b.cs2 = 0.0;
+          DEB_LANES_BEGIN
+            if (lane == 0) W.u()[0] = b.a;         // exactly the value the helper used
+            if (lane >= 3 && lane < nch) nu_moments_lane(nb, box->vv, W.u(), P.iq0, lane - 3, W.nur(), W.nup());
+          DEB_LANES_END
+        } else {
+          compute_bg<double>(c, nb, nq, W.u()[0], hint, W.ic(), b);
+          DEB_LANES_BEGIN
+            if (lane < nch) chain_coeffs_lane<double>(c, nb, b, k, lane, W.u(), P.iq0, W.kc(), W.kap(), W.nur(), W.nup(), W.sl());
+            if (lane == 0) fill_slots<double>(c, b, k, W.sl());
+          DEB_LANES_END
+        }
         Metric<double> mt;
         compute_metric<double>(P, c, nb, b, W.u(), k, W.nur(), W.nup(), mt);
         const double invts = DEB_RCP(ts);
@@ -1182,6 +1275,29 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, int 
       // ---- solve W x = r in place ----
       const double x0 = W.r()[0] / x0piv;
       DEB_SYNC();          // every lane has read r[0] before lane 0 overwrites it with x0
+      if (HELPER && st < 8) {
+        // scale factor of stage st+1: element 0 of y + sum_j a_{st+1,j} k_j with k_st[0] = x0 (lane 0 owns element 0)
+        DEB_LANES_BEGIN
+          DEB_USE(ks);
+          if (lane == 0) {
+            double an;
+            switch (st) {
+              case 1: an = W.y()[0] + RD_A21 * x0; break;
+              case 2: an = W.y()[0] + RD_A31 * ks[0][0] + RD_A32 * x0; break;
+              case 3: an = W.y()[0] + RD_A41 * ks[0][0] + RD_A42 * ks[1][0] + RD_A43 * x0; break;
+              case 4: an = W.y()[0] + RD_A51 * ks[0][0] + RD_A52 * ks[1][0] + RD_A53 * ks[2][0] + RD_A54 * x0; break;
+              case 5: an = W.y()[0] + RD_A61 * ks[0][0] + RD_A62 * ks[1][0] + RD_A63 * ks[2][0] + RD_A64 * ks[3][0] + RD_A65 * x0; break;
+              default: an = W.u()[0] + x0; break;        // stages 7 and 8: u + k
+            }
+            box->a_req = an;
+          }
+        DEB_LANES_END
+#ifdef DEB_CPU_EMU
+        helper_compute(P, C, W, *box, hint2);
+#else
+        DEB_BAR_ARRIVE(BAR_REQ);
+#endif
+      }
       DEB_LANES_BEGIN
         DEB_FOR_OWN(W.r()[e] = (e == 0) ? x0 : W.r()[e] + W.ja()[e] * x0;)
       DEB_LANES_END

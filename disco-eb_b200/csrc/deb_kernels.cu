@@ -65,15 +65,58 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) k_evolve(const __grid_consta
     // largest k first, cosmologies interleaved
     const int kd = tk / P.ncosmo, cs = tk - kd * P.ncosmo;
     const int mode = cs * P.nk + (P.nk - 1 - kd);
-    integrate_mode<NE>(P, *C, W, mode, lane);
+    integrate_mode<NE, false>(P, *C, W, nullptr, mode, lane);
     __syncwarp();
   }
 }
 
+// Two-warp variant for batches that cannot fill the GPU (<= 4 modes per SM): warp 0 integrates the mode,
+// warp 1 evaluates the next stage's background scalars while warp 0 runs the current solve (named barriers
+// 1/2 as request/ready).  Same source, same per-mode results up to the rounding of the posted scale factor.
+template <int NE>
+__global__ void __launch_bounds__(64, 1) k_evolve_h(const __grid_constant__ Problem P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  CtaConst* C = reinterpret_cast<CtaConst*>(smem_raw);
+  size_t off = (sizeof(CtaConst) + 15) & ~(size_t)15;
+  int* tail = reinterpret_cast<int*>(smem_raw + off);
+  off = (off + (size_t)P.np * sizeof(int) + 15) & ~(size_t)15;
+  double* wsb = reinterpret_cast<double*>(smem_raw + off);
+  HelpBox* box = reinterpret_cast<HelpBox*>(smem_raw + off + warp_ws_bytes(P.np));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  init_cta_const(P, *C, tail, threadIdx.x, 64);
+  __syncthreads();
+  WarpWs W;
+  carve(W, wsb, P.np);
+  if (warp == 1) { helper_loop(P, *C, W, *box, lane); return; }
+  const int total = P.ncosmo * P.nk;
+  for (;;) {
+    unsigned int tk = 0;
+    if (lane == 0) tk = atomicAdd(P.ticket, 1u);
+    tk = __shfl_sync(0xffffffffu, tk, 0);
+    if (tk >= (unsigned int)total) break;
+    const int kd = tk / P.ncosmo, cs = tk - kd * P.ncosmo;
+    const int mode = cs * P.nk + (P.nk - 1 - kd);
+    integrate_mode<NE, true>(P, *C, W, box, mode, lane);
+    __syncwarp();
+  }
+  if (lane == 0) box->cmd = 1;
+  __syncwarp();
+  DEB_BAR_ARRIVE(BAR_REQ);
+}
+
 typedef void (*evolve_kernel_t)(const Problem);
-static evolve_kernel_t pick_kernel(int n, bool many_modes, int* warps) {
+static evolve_kernel_t pick_kernel(int n, bool many_modes, bool few_modes, int* warps, size_t* extra_smem) {
   int ne = (n + 31) / 32;
-  *warps = 1;
+  *warps = 1; *extra_smem = 0;
+  if (few_modes && !getenv("DEB_NO_HELPER")) {
+    *warps = 2; *extra_smem = sizeof(HelpBox) + 16;
+    if (ne <= 3) return k_evolve_h<3>;
+    if (ne <= 4) return k_evolve_h<4>;
+    if (ne <= 6) return k_evolve_h<6>;
+    if (ne <= 9) return k_evolve_h<9>;
+    if (ne <= 12) return k_evolve_h<12>;
+    return nullptr;
+  }
   if (ne <= 3) return many_modes ? k_evolve<3, 12, 1> : k_evolve<3, 1, 1>;
   if (ne <= 4) return many_modes ? k_evolve<4, 12, 1> : k_evolve<4, 1, 1>;
   if (ne <= 6) return k_evolve<6, 1, 1>;
@@ -90,15 +133,20 @@ static int launch_evolve(const Problem& P, cudaStream_t st) {
   CUDA_TRY(cudaGetDevice(&dev));
   CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
   int warps = 1;
-  evolve_kernel_t kern = pick_kernel(P.n, (long)P.ncosmo * P.nk > (long)nsm * 8, &warps);
+  size_t extra = 0;
+  const long nmodes = (long)P.ncosmo * P.nk;
+  // replay/debug modes use the plain kernel; the helper variant serves launches of at most 4 modes per SM
+  evolve_kernel_t kern = pick_kernel(P.n, nmodes > (long)nsm * 8, P.mode == 0 && nmodes <= (long)nsm * 4, &warps, &extra);
   if (!kern) return DEB_E_UNSUPPORTED;
-  size_t smem = cta_smem_bytes(P.np, warps);
+  const bool helper = extra > 0;
+  size_t smem = cta_smem_bytes(P.np, helper ? 1 : warps) + extra;
   CUDA_TRY(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)kern, 32 * warps, smem));
   if (occ < 1) return DEB_E_UNSUPPORTED;
   long total = (long)P.ncosmo * P.nk;
   long grid = (long)nsm * occ;
-  if (grid * warps > total) grid = (total + warps - 1) / warps;
+  const int modes_per_cta = helper ? 1 : warps;
+  if (grid * modes_per_cta > total) grid = (total + modes_per_cta - 1) / modes_per_cta;
   CUDA_TRY(cudaMemsetAsync(P.ticket, 0, sizeof(unsigned int), st));
   kern<<<(unsigned)grid, 32 * warps, smem, st>>>(P);
   CUDA_TRY(cudaGetLastError());

@@ -25,7 +25,7 @@ static void tau_out_host(Problem& P, double* tau_out) {
   P.lt_small = g_lt_small.data();
 }
 
-template <int NE>
+template <int NE, bool HELPER>
 static void run_all(const Problem& P) {
   CtaConst C;
   std::vector<int> tail(P.np);
@@ -36,19 +36,26 @@ static void run_all(const Problem& P) {
   for (int m = 0; m < total; ++m) {
     WarpWs W;
     carve(W, ws.data(), P.np);
-    integrate_mode<NE>(P, C, W, total - 1 - m);
+    HelpBox box;
+    integrate_mode<NE, HELPER>(P, C, W, &box, total - 1 - m);
   }
 }
 
-static int dispatch(const Problem& P) {
+// DEB_EMU_HELPER=1 selects the two-warp (main + helper) code path, the helper being run inline
+template <bool HELPER>
+static int dispatch_h(const Problem& P) {
   int ne = (P.n + 31) / 32;
-  if (ne <= 3) run_all<3>(P);
-  else if (ne <= 4) run_all<4>(P);
-  else if (ne <= 6) run_all<6>(P);
-  else if (ne <= 9) run_all<9>(P);
-  else if (ne <= 12) run_all<12>(P);
+  if (ne <= 3) run_all<3, HELPER>(P);
+  else if (ne <= 4) run_all<4, HELPER>(P);
+  else if (ne <= 6) run_all<6, HELPER>(P);
+  else if (ne <= 9) run_all<9, HELPER>(P);
+  else if (ne <= 12) run_all<12, HELPER>(P);
   else return DEB_E_UNSUPPORTED;
   return DEB_OK;
+}
+static int dispatch(const Problem& P) {
+  const char* h = getenv("DEB_EMU_HELPER");
+  return (h && h[0] == '1') ? dispatch_h<true>(P) : dispatch_h<false>(P);
 }
 
 extern "C" int emu_evolve_host_f64(const deb_dims* dims, const deb_ctrl* ctrl, const double* scalars,

@@ -94,3 +94,24 @@ def test_per_cosmology_k_grids(emu_lib, tables):
     both = emu_lib.evolve_host(mk(2, True), ctrl, np.stack([a.scalars, b.scalars]), np.stack([a.tables, b.tables]), k2, np.array([1.0]))
     one_b = emu_lib.evolve_host(mk(1, False), ctrl, b.scalars[None], b.tables[None], k2[1], np.array([1.0]))
     assert np.array_equal(both["y"][1], one_b["y"][0])
+
+
+@pytest.mark.parametrize("name", ["default_n72", "config2_n265", "many_out_n72"])
+def test_two_warp_variant_source(emu_lib, tables, name, monkeypatch):
+    """The main+helper code path (the helper's evaluations run inline in the CPU build): same checks, and the
+    results agree with the one-warp path to round-off on modes whose step sequences coincide."""
+    from discoeb_b200 import _cabi
+    case = helpers.load_case(name)
+    tab = tables[str(case["cosmology"])]
+    ks, aout, rtol = case["kmodes"], case["aexp_out"], float(case["rtol"])
+    dims = pc.dims_for(case, tab, len(ks), len(aout))
+    ctrl = _cabi.make_ctrl(rtol=rtol, atol=rtol)
+    one = emu_lib.evolve_host(dims, ctrl, tab.scalars[None], tab.tables[None], ks, aout)
+    monkeypatch.setenv("DEB_EMU_HELPER", "1")
+    pc.check_adaptive(emu_lib, tables, name)
+    two = emu_lib.evolve_host(dims, ctrl, tab.scalars[None], tab.tables[None], ks, aout)
+    same = (one["nsteps"] == two["nsteps"]) & (one["naccept"] == two["naccept"])
+    assert same.mean() >= 0.5
+    for m in np.nonzero(same[0])[0]:
+        if one["nsteps"][0, m] <= 100:
+            assert helpers.field_scaled_diff(two["y"][0, m], one["y"][0, m]).max() < 1e-6
