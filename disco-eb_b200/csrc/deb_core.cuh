@@ -623,8 +623,10 @@ struct HelpBox {
   double bgs[10];               // H, gc, gb, gg, gr, gnu, gq, wq1, ca2, wq
   double vv[2 * NQMAX];         // v_i, 1/v_i
   double ic2[ICACHE];           // the helper's own spline interval cache
+  double invts, dtt;            // stage scalars for the helper's share of the tail rows
+  int split;
 };
-enum { BAR_REQ = 1, BAR_RDY = 2 };
+enum { BAR_REQ = 1, BAR_RDY = 2, BAR_GO = 3, BAR_DONE = 4 };
 
 // the a-only half of chain_coeffs_lane (helper warp) ...
 DEB_DEV void chain_a_lane(const Cosmo& c, const NuBins& nb, const Bg<double>& b, double k, int ch, double* kcA, double* kapA,
@@ -878,9 +880,27 @@ DEB_DEV void convert_outputs(const Problem& P, const Cosmo& c, const NuBins& nb,
 // ---------------------------------------------------------------------------------------------
 #ifdef DEB_CPU_EMU
 #define DEB_LANE_PARAM
+#define DEB_LANE_ARG
 #else
 #define DEB_LANE_PARAM , const int lane
+#define DEB_LANE_ARG , lane
 #endif
+
+// tail rows tt in [t0, t1) of a stage right-hand side, added onto r (two rows per trip: both evaluated before
+// either store); executed by one warp
+DEB_DEV void stage_tail_rows(const CtaConst& C, WarpWs& W, int t0, int t1, double invts, double dtt DEB_LANE_PARAM) {
+  DEB_LANES_BEGIN
+    for (int tt = t0 + lane; tt < t1; tt += 64) {
+      int e0, e1 = 0; double tr0, tr1 = 0.0, f1 = 0.0, r1 = 0.0, y1 = 0.0;
+      const bool two = tt + 32 < t1;
+      const double f0 = tail_row<double>(C, W.kc(), W.kap(), W.u(), C.tail[tt], invts, &e0, &tr0);
+      const double r0 = W.r()[e0], y0 = W.y()[e0];
+      if (two) { f1 = tail_row<double>(C, W.kc(), W.kap(), W.u(), C.tail[tt + 32], invts, &e1, &tr1); r1 = W.r()[e1]; y1 = W.y()[e1]; }
+      W.r()[e0] = r0 + f0 + dtt * tr0 * y0;
+      if (two) W.r()[e1] = r1 + f1 + dtt * tr1 * y1;
+    }
+  DEB_LANES_END
+}
 
 // One evaluation by the helper warp: background at box.a_req -> chain coefficients, operator slots, and the
 // scalars the main warp's metric sources need.
@@ -911,6 +931,9 @@ DEB_DEV void helper_loop(const Problem& P, const CtaConst& C, WarpWs& W, HelpBox
     helper_compute(P, C, W, box, hint2, lane);
     __syncwarp();
     DEB_BAR_ARRIVE(BAR_RDY);
+    DEB_BAR_SYNC(BAR_GO);                  // the main warp has formed the C-combinations of this stage in r
+    stage_tail_rows(C, W, box.split, C.ntail, box.invts, box.dtt, lane);
+    DEB_BAR_SYNC(BAR_DONE);
   }
 }
 #endif
@@ -1143,7 +1166,7 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, Help
             const double f = fmul;
             double ra[8], pa[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { ra[i] = rb[i]; pa[i] = pb[i]; }     // slots beyond the block hold zeros
+            for (int i = 0; i < 8; ++i) { ra[i] = rb[i]; pa[i] = (i == bt) ? 0.0 : pb[i]; }   // (the pivot lane rewrites slot bt; unused slots hold zeros)
 #pragma unroll
             for (int i = 0; i < 8; ++i) row[lo + i] = (i == bt) ? -f : ra[i] - f * pa[i];
           }
@@ -1253,23 +1276,34 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, Help
             default: DEB_FOR_OWN(W.r()[e] = invdt * (RD_C81 * ks[0][j] + RD_C82 * ks[1][j] + RD_C83 * ks[2][j] + RD_C84 * ks[3][j] + RD_C85 * ks[4][j] + RD_C86 * ks[5][j] + RD_C87 * ks[6][j]);) break;
           }
         DEB_LANES_END
+        const double dtt = dtd * invt0 * invt0;
+#ifndef DEB_CPU_EMU
+        // two-warp variant: the helper takes the upper part of the tail rows (it idles until the next request)
+        const int split = HELPER ? 32 * (((C.ntail + 31) / 32) * 3 / 7) : C.ntail;
+        if (HELPER) {
+          DEB_LANE0_BEGIN
+            box->invts = invts; box->dtt = dtt; box->split = split;
+          DEB_LANE0_END
+          DEB_BAR_ARRIVE(BAR_GO);
+        }
+#else
+        const int split = C.ntail;
+#endif
         DEB_LANES_BEGIN      // rows are distributed differently from the register-resident k's: new phase
           if (lane < nh) {
             const int e = C.hidx[lane];
             W.r()[e] += head_row<double>(C, W.sl(), W.u(), lane, mt);
           }
           if (lane == 0) W.r()[0] += b.H * b.a;
-          const double dtt = dtd * invt0 * invt0;
-          for (int tt = lane; tt < C.ntail; tt += 64) {      // two rows per trip: both evaluated before either store
-            int e0, e1 = 0; double tr0, tr1 = 0.0, f1 = 0.0, r1 = 0.0, y1 = 0.0;
-            const bool two = tt + 32 < C.ntail;
-            const double f0 = tail_row<double>(C, W.kc(), W.kap(), W.u(), C.tail[tt], invts, &e0, &tr0);
-            const double r0 = W.r()[e0], y0 = W.y()[e0];
-            if (two) { f1 = tail_row<double>(C, W.kc(), W.kap(), W.u(), C.tail[tt + 32], invts, &e1, &tr1); r1 = W.r()[e1]; y1 = W.y()[e1]; }
-            W.r()[e0] = r0 + f0 + dtt * tr0 * y0;
-            if (two) W.r()[e1] = r1 + f1 + dtt * tr1 * y1;
-          }
         DEB_LANES_END
+        {
+          stage_tail_rows(C, W, 0, split, invts, dtt DEB_LANE_ARG);
+#ifndef DEB_CPU_EMU
+          if (HELPER) DEB_BAR_SYNC(BAR_DONE);
+          else
+#endif
+          (void)0;
+        }
       }
 
       // ---- solve W x = r in place ----
