@@ -193,57 +193,154 @@ int deb_evolve_f64(const deb_dims* dims, const deb_ctrl* ctrl, const double* sca
   return launch_evolve(P, st);
 }
 
-// ---- host-pointer conveniences -------------------------------------------------------------
+}  // extern "C" (reopened below)
 
-int deb_evolve_host_f64(const deb_dims* dims, const deb_ctrl* ctrl, const double* scalars, const double* tables,
-                        const double* kmodes, const double* aexp_out, double* y_out, double* pk_out, double* tau_out,
-                        int32_t* status, int32_t* nsteps, int32_t* naccept, int32_t device, float* kernel_ms) {
+// ---- host-pointer entry ----------------------------------------------------------------------
+// A deb_ctx owns what a host-buffer call needs on one device: a stream, two events, ONE device arena and
+// ONE pinned host arena (both grow-only).  A call packs its inputs into the pinned arena, issues a single
+// H2D copy, the two kernels, a single D2H copy of every result, and synchronises once; nothing is allocated
+// in steady state.  (The first version of this entry did 11 cudaMalloc/cudaFree + stream/event creation per
+// call: 52 ms of host overhead around a 36 ms kernel.)
+struct deb_ctx {
+  int device = 0;
+  cudaStream_t st = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  char* dbuf = nullptr; size_t dcap = 0;
+  char* hbuf = nullptr; size_t hcap = 0;
+};
+
+static inline size_t al256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+static int ctx_reserve(deb_ctx* c, size_t dbytes, size_t hbytes) {
+  if (dbytes > c->dcap) {
+    if (c->dbuf) cudaFree(c->dbuf);
+    c->dbuf = nullptr; c->dcap = 0;
+    size_t cap = al256(dbytes + dbytes / 4);
+    CUDA_TRY(cudaMalloc((void**)&c->dbuf, cap));
+    c->dcap = cap;
+  }
+  if (hbytes > c->hcap) {
+    if (c->hbuf) cudaFreeHost(c->hbuf);
+    c->hbuf = nullptr; c->hcap = 0;
+    size_t cap = al256(hbytes + hbytes / 4);
+    CUDA_TRY(cudaMallocHost((void**)&c->hbuf, cap));
+    c->hcap = cap;
+  }
+  return DEB_OK;
+}
+
+extern "C" int deb_ctx_create(int32_t device, deb_ctx** out) {
+  if (!out) return DEB_E_ARG;
+  *out = nullptr;
+  if (deb_device_count() < 1) return DEB_E_NODEVICE;
+  if (device < 0 || device >= deb_device_count()) return DEB_E_ARG;
+  CUDA_TRY(cudaSetDevice(device));
+  deb_ctx* c = new deb_ctx();
+  c->device = device;
+  if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&c->e0) != cudaSuccess || cudaEventCreate(&c->e1) != cudaSuccess) { delete c; return DEB_E_CUDA; }
+  *out = c;
+  return DEB_OK;
+}
+
+extern "C" void deb_ctx_destroy(deb_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->st) cudaStreamSynchronize(c->st);
+  if (c->dbuf) cudaFree(c->dbuf);
+  if (c->hbuf) cudaFreeHost(c->hbuf);
+  if (c->e0) cudaEventDestroy(c->e0);
+  if (c->e1) cudaEventDestroy(c->e1);
+  if (c->st) cudaStreamDestroy(c->st);
+  delete c;
+}
+
+extern "C" int deb_ctx_evolve_host_f64(deb_ctx* c, const deb_dims* dims, const deb_ctrl* ctrl, const double* scalars,
+                                       const double* tables, const double* kmodes, const double* aexp_out, double* y_out,
+                                       double* pk_out, double* tau_out, int32_t* status, int32_t* nsteps, int32_t* naccept,
+                                       float* kernel_ms) {
+  if (!c) return DEB_E_ARG;
   Problem P0;
   int rc = fill_problem(dims, ctrl, &P0);
   if (rc) return rc;
-  if (deb_device_count() < 1) return DEB_E_NODEVICE;
-  CUDA_TRY(cudaSetDevice(device));
+  if (!scalars || !tables || !kmodes || !aexp_out || !y_out || !tau_out || !status || !nsteps) return DEB_E_ARG;
+  CUDA_TRY(cudaSetDevice(c->device));
   const size_t nc = dims->ncosmo, nk = dims->nk, nout = dims->nout;
   const size_t nf = dims->return_full ? (size_t)P0.n : 20;
   const size_t tl = deb_table_len(dims);
   const size_t nkm = dims->k_per_cosmo ? nc * nk : nk;
   const bool pk = dims->power_idx >= 0 && pk_out;
-  DevBuf d_sc, d_tb, d_k, d_a, d_y, d_pk, d_tau, d_st, d_ns, d_na, d_ws;
-  if (d_sc.alloc(nc * DEB_NSCAL * 8) || d_tb.alloc(nc * tl * 8) || d_k.alloc(nkm * 8) || d_a.alloc(nout * 8) ||
-      d_y.alloc(nc * nk * nout * nf * 8) || d_pk.alloc(pk ? nc * nk * nout * 8 : 8) || d_tau.alloc(nc * nout * 8) ||
-      d_st.alloc(nc * nk * 4) || d_ns.alloc(nc * nk * 4) || d_na.alloc(nc * nk * 4) || d_ws.alloc(deb_workspace_bytes(dims)))
-    return DEB_E_CUDA;
-  cudaStream_t st;
-  CUDA_TRY(cudaStreamCreate(&st));
-  CUDA_TRY(cudaMemcpyAsync(d_sc.p, scalars, nc * DEB_NSCAL * 8, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(d_tb.p, tables, nc * tl * 8, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(d_k.p, kmodes, nkm * 8, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(d_a.p, aexp_out, nout * 8, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemsetAsync(d_y.p, 0, nc * nk * nout * nf * 8, st));
-  cudaEvent_t e0, e1;
-  CUDA_TRY(cudaEventCreate(&e0));
-  CUDA_TRY(cudaEventCreate(&e1));
-  CUDA_TRY(cudaEventRecord(e0, st));
+  // input block: scalars | tables | kmodes | aexp_out        output block: y | pk | tau | status | nsteps | naccept
+  const size_t i_sc = 0, i_tb = i_sc + al256(nc * DEB_NSCAL * 8), i_k = i_tb + al256(nc * tl * 8), i_a = i_k + al256(nkm * 8),
+               in_bytes = i_a + al256(nout * 8);
+  const size_t o_y = 0, o_pk = o_y + al256(nc * nk * nout * nf * 8), o_tau = o_pk + al256(pk ? nc * nk * nout * 8 : 0),
+               o_st = o_tau + al256(nc * nout * 8), o_ns = o_st + al256(nc * nk * 4), o_na = o_ns + al256(nc * nk * 4),
+               out_bytes = o_na + al256(nc * nk * 4);
+  const size_t ws_bytes = al256(deb_workspace_bytes(dims));
+  rc = ctx_reserve(c, in_bytes + out_bytes + ws_bytes, in_bytes + out_bytes);
+  if (rc) return rc;
+  char* hin = c->hbuf; char* hout = c->hbuf + in_bytes;
+  char* din = c->dbuf; char* dout = c->dbuf + in_bytes; char* dws = dout + out_bytes;
+  memcpy(hin + i_sc, scalars, nc * DEB_NSCAL * 8);
+  memcpy(hin + i_tb, tables, nc * tl * 8);
+  memcpy(hin + i_k, kmodes, nkm * 8);
+  memcpy(hin + i_a, aexp_out, nout * 8);
+  CUDA_TRY(cudaMemcpyAsync(din, hin, in_bytes, cudaMemcpyHostToDevice, c->st));
+  CUDA_TRY(cudaMemsetAsync(dout + o_y, 0, nc * nk * nout * nf * 8, c->st));
+  CUDA_TRY(cudaEventRecord(c->e0, c->st));
   deb_dims d2 = *dims;
   if (!pk) d2.power_idx = -1;
-  rc = deb_evolve_f64(&d2, ctrl, d_sc.as<double>(), d_tb.as<double>(), d_k.as<double>(), d_a.as<double>(),
-                      d_y.as<double>(), d_pk.as<double>(), d_tau.as<double>(), d_st.as<int32_t>(), d_ns.as<int32_t>(),
-                      d_na.as<int32_t>(), d_ws.p, deb_workspace_bytes(dims), (void*)st);
-  if (rc == DEB_OK) {
-    CUDA_TRY(cudaEventRecord(e1, st));
-    CUDA_TRY(cudaMemcpyAsync(y_out, d_y.p, nc * nk * nout * nf * 8, cudaMemcpyDeviceToHost, st));
-    if (pk) CUDA_TRY(cudaMemcpyAsync(pk_out, d_pk.p, nc * nk * nout * 8, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(tau_out, d_tau.p, nc * nout * 8, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(status, d_st.p, nc * nk * 4, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(nsteps, d_ns.p, nc * nk * 4, cudaMemcpyDeviceToHost, st));
-    if (naccept) CUDA_TRY(cudaMemcpyAsync(naccept, d_na.p, nc * nk * 4, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    if (kernel_ms) CUDA_TRY(cudaEventElapsedTime(kernel_ms, e0, e1));
-  }
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
-  cudaStreamDestroy(st);
+  rc = deb_evolve_f64(&d2, ctrl, (double*)(din + i_sc), (double*)(din + i_tb), (double*)(din + i_k), (double*)(din + i_a),
+                      (double*)(dout + o_y), (double*)(dout + o_pk), (double*)(dout + o_tau), (int32_t*)(dout + o_st),
+                      (int32_t*)(dout + o_ns), (int32_t*)(dout + o_na), dws, ws_bytes, (void*)c->st);
+  if (rc != DEB_OK) { cudaStreamSynchronize(c->st); return rc; }
+  CUDA_TRY(cudaEventRecord(c->e1, c->st));
+  CUDA_TRY(cudaMemcpyAsync(hout, dout, out_bytes, cudaMemcpyDeviceToHost, c->st));
+  CUDA_TRY(cudaStreamSynchronize(c->st));
+  memcpy(y_out, hout + o_y, nc * nk * nout * nf * 8);
+  if (pk) memcpy(pk_out, hout + o_pk, nc * nk * nout * 8);
+  memcpy(tau_out, hout + o_tau, nc * nout * 8);
+  memcpy(status, hout + o_st, nc * nk * 4);
+  memcpy(nsteps, hout + o_ns, nc * nk * 4);
+  if (naccept) memcpy(naccept, hout + o_na, nc * nk * 4);
+  if (kernel_ms) CUDA_TRY(cudaEventElapsedTime(kernel_ms, c->e0, c->e1));
+  return DEB_OK;
+}
+
+// One cached context per (host thread, device) backs the context-free entry; deb_host_cache_release() drops the
+// calling thread's contexts (they are also dropped when the thread exits).
+struct CtxCache {
+  std::vector<deb_ctx*> v;
+  ~CtxCache() { for (deb_ctx* c : v) deb_ctx_destroy(c); }
+};
+static thread_local CtxCache t_cache;
+
+extern "C" void deb_host_cache_release(void) {
+  for (deb_ctx* c : t_cache.v) deb_ctx_destroy(c);
+  t_cache.v.clear();
+}
+
+static int cached_ctx(int32_t device, deb_ctx** out) {
+  for (deb_ctx* c : t_cache.v) if (c->device == device) { *out = c; return DEB_OK; }
+  int rc = deb_ctx_create(device, out);
+  if (rc == DEB_OK) t_cache.v.push_back(*out);
   return rc;
 }
+
+extern "C" int deb_evolve_host_f64(const deb_dims* dims, const deb_ctrl* ctrl, const double* scalars, const double* tables,
+                                   const double* kmodes, const double* aexp_out, double* y_out, double* pk_out, double* tau_out,
+                                   int32_t* status, int32_t* nsteps, int32_t* naccept, int32_t device, float* kernel_ms) {
+  Problem P0;
+  int rc = fill_problem(dims, ctrl, &P0);
+  if (rc) return rc;
+  deb_ctx* c = nullptr;
+  rc = cached_ctx(device, &c);
+  if (rc) return rc;
+  return deb_ctx_evolve_host_f64(c, dims, ctrl, scalars, tables, kmodes, aexp_out, y_out, pk_out, tau_out, status, nsteps,
+                                 naccept, kernel_ms);
+}
+
+extern "C" {
 
 static int debug_common(const deb_dims* dims, const deb_ctrl* ctrl, const double* scalars, const double* tables,
                         const double* kmodes, const double* aexp_out, int32_t device, int mode, size_t nper,

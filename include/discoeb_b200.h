@@ -113,6 +113,22 @@ int deb_evolve_host_f64(const deb_dims* dims, const deb_ctrl* ctrl,
                         int32_t* status, int32_t* nsteps, int32_t* naccept,
                         int32_t device, float* kernel_ms);
 
+/* Host-pointer entry with an explicit context.  A deb_ctx owns a stream, two events, one device
+ * arena and one pinned host arena on `device` (grow-only), so that repeated calls allocate
+ * nothing: inputs are packed into the pinned arena and cross PCIe/C2C in ONE copy, all results
+ * come back in ONE copy.  deb_evolve_host_f64 above uses a context cached per (host thread,
+ * device); deb_host_cache_release() frees the calling thread's cached contexts.  A context must
+ * not be used by two threads at once. */
+typedef struct deb_ctx deb_ctx;
+int deb_ctx_create(int32_t device, deb_ctx** out);
+void deb_ctx_destroy(deb_ctx* ctx);
+int deb_ctx_evolve_host_f64(deb_ctx* ctx, const deb_dims* dims, const deb_ctrl* ctrl,
+                            const double* scalars, const double* tables, const double* kmodes,
+                            const double* aexp_out,
+                            double* y_out, double* pk_out, double* tau_out,
+                            int32_t* status, int32_t* nsteps, int32_t* naccept, float* kernel_ms);
+void deb_host_cache_release(void);
+
 /* Debug/validation entry (host pointers): ONE attempted Rodas5 step per mode from a given
  * state.  t0[nmodes], t1[nmodes], y0[nmodes, n] -> y1[nmodes, n], yerr[nmodes, n].
  * Modes index (cosmology, k) like deb_evolve_f64.  Used by the parity tests to compare the

@@ -64,8 +64,8 @@ class Spline:
         """spline_interpolation.py:130-153 (cubic extrapolation outside the knots)."""
         x, y, S = self.x, self.y, self.S
         n = x.shape[0]
-        xr = np.real(xn)
-        idx = np.clip(np.searchsorted(x, xr, side="left") - 1, 0, n - 2)
+        xr = np.real(xn)      # (complex xn / complex tables: the tangent oracle's complex step; index from real parts)
+        idx = np.clip(np.searchsorted(np.real(x), xr, side="left") - 1, 0, n - 2)
         hl = x[idx + 1] - x[idx]
         t = (xn - x[idx]) / hl
         A = 1 - t

@@ -190,6 +190,119 @@ def rhs(tau, y, p, k, d: Dims):
     return f
 
 
+def _spl_d(sp, xn):
+    """d/dxn of Spline.evaluate's own formula (what forward-mode AD of spline_interpolation.py:130-153 yields)."""
+    x, yv, S = sp.x, sp.y, sp.S
+    n = x.shape[0]
+    idx = np.clip(np.searchsorted(np.real(x), np.real(xn), side="left") - 1, 0, n - 2)
+    hl = x[idx + 1] - x[idx]
+    t = (xn - x[idx]) / hl
+    A, B = 1 - t, t
+    return (yv[idx + 1] - yv[idx]) / hl + ((1 - 3 * A ** 2) * S[idx] + (3 * B ** 2 - 1) * S[idx + 1]) * hl / 6.0
+
+
+def rhs_da(tau, y, p, k, d: Dims):
+    """Hand-derived d f / d a at fixed y[1:] (the scale-factor column of the Jacobian).  Holomorphic in
+    every input, so it can sit inside an outer complex step; checked against the complex-step column
+    of ``jacobian`` on real inputs in tests/test_oracle_tangent.py."""
+    nq, iq0 = d.nq, d.iq0
+    ig, igp, ir = d.ig, d.igp, d.ir
+    Lg, Lp, Lr, Ln = d.lmaxg, d.lmaxgp, d.lmaxr, d.lmaxnu
+    Omegac = p["Omegam"] - p["Omegab"]
+    a = y[..., 0]
+    eta = y[..., 2]
+    deltac, thetac, deltab, thetab = y[..., 3], y[..., 4], y[..., 5], y[..., 6]
+    deltag, thetag = y[..., 7], y[..., 8]
+    deltar, thetar = y[..., ir], y[..., ir + 1]
+    deltaq, thetaq = y[..., -2], y[..., -1]
+    b = _bg(p, a)
+    cs2, pb43, w_Q, rho_Q, H, ca2_Q, opac, xe = b["cs2"], b["pb43"], b["w_Q"], b["rho_Q"], b["H"], b["ca2_Q"], b["opac"], b["xe"]
+    cs2_Q, wa = p["cs2_DE"], p["w_DE_a"]
+    G = p["grhom"] * p["OmegaDE"]
+    k2 = k ** 2
+    loga = np.log(a)
+    # coefficient derivatives
+    sc = p["cs2a_of_loga_spline"].evaluate(loga)
+    dcs2 = _spl_d(p["cs2a_of_loga_spline"], loga) / a ** 2 - sc / a ** 2
+    dxe = _spl_d(p["xe_of_loga_spline"], loga) / a
+    dpb43 = -pb43 / a
+    drhoQ = rho_Q * (-3 * (1 + p["w_DE_0"] + wa) / a + 3 * wa)
+    rhonu = np.exp(p["logrhonu_of_loga_spline"].evaluate(loga))
+    drhonu_bg = rhonu * _spl_d(p["logrhonu_of_loga_spline"], loga) / a
+    dgq = G * (drhoQ * a ** 2 + 2 * a * rho_Q)                 # d/da of grhom OmegaDE rho_Q a^2
+    dgrho_bg = (-p["grhom"] * p["Omegam"] / a ** 2 - 2 * (p["grhog"] + p["grhor"] * (p["Neff"] + p["Nmnu"] * rhonu)) / a ** 3
+                + p["grhor"] * p["Nmnu"] * drhonu_bg / a ** 2 + dgq)
+    dH = dgrho_bg / (6 * H)
+    Dq = (1 + w_Q) + 1e-6
+    dca2 = -wa + wa / (3 * Dq) + wa ** 2 * a / (3 * Dq ** 2)
+    akthom = AKTHOM_RHS * (1.0 - p["YHe"]) * p["Omegab"] * p["H0"] ** 2
+    dopac = akthom * (dxe / a ** 2 - 2 * xe / a ** 3)
+    aq = a[..., None] * p["amnu"] / d.q
+    v = 1 / np.sqrt(1 + aq ** 2)
+    dv = -v ** 3 * aq * p["amnu"] / d.q
+    psi0, psi1, psi2 = y[..., iq0:iq0 + nq], y[..., iq0 + nq:iq0 + 2 * nq], y[..., iq0 + 2 * nq:iq0 + 3 * nq]
+    psi3 = y[..., iq0 + 3 * nq:iq0 + 4 * nq]
+    drhonu = np.sum(d.w * psi0 / v, -1)
+    dpnu = np.sum(d.w * psi0 * v, -1) / 3
+    fnu = np.sum(d.w * psi1, -1)
+    ddrhonu = np.sum(d.w * psi0 * (-dv / v ** 2), -1)
+    ddpnu = np.sum(d.w * psi0 * dv, -1) / 3
+    rpt = (1 + w_Q) * rho_Q * G * thetaq * a ** 2
+    drpt = G * thetaq * (-wa * rho_Q * a ** 2 + (1 + w_Q) * (drhoQ * a ** 2 + 2 * a * rho_Q))
+    # metric sources
+    m1 = p["grhom"] * (Omegac * deltac + p["Omegab"] * deltab)
+    m2 = p["grhog"] * deltag + p["grhor"] * (p["Neff"] * deltar + p["Nmnu"] * drhonu)
+    dgrho = m1 / a + m2 / a ** 2 + G * deltaq * rho_Q * a ** 2
+    ddgrho = -m1 / a ** 2 - 2 * m2 / a ** 3 + p["grhor"] * p["Nmnu"] * ddrhonu / a ** 2 + deltaq * dgq
+    p1 = p["grhog"] * deltag + p["grhor"] * p["Neff"] * deltar
+    dgpres = (p1 / a ** 2 / 3.0 + p["grhor"] * p["Nmnu"] * dpnu / a ** 2
+              + (cs2_Q * G * deltaq * rho_Q * a ** 2 + (cs2_Q - ca2_Q) * (3 * H * rpt / k2)))
+    ddgpres = (-2 * p1 / a ** 3 / 3.0 + p["grhor"] * p["Nmnu"] * (ddpnu / a ** 2 - 2 * dpnu / a ** 3)
+               + cs2_Q * deltaq * dgq - dca2 * (3 * H * rpt / k2) + (cs2_Q - ca2_Q) * 3 * (dH * rpt + H * drpt) / k2)
+    t1 = p["grhom"] * (Omegac * thetac + p["Omegab"] * thetab)
+    t2 = 4.0 / 3.0 * (p["grhog"] * thetag + p["Neff"] * p["grhor"] * thetar) + p["Nmnu"] * p["grhor"] * k * fnu
+    ddgtheta = -t1 / a ** 2 - 2 * t2 / a ** 3 + drpt
+    hprime = (2.0 * k2 * eta + dgrho) / H
+    dhp = ddgrho / H - hprime * dH / H
+    dep = 0.5 * ddgtheta / k2
+    dal = (dhp + 6.0 * dep) / 2.0 / k2
+
+    f = np.zeros_like(y)
+    f[..., 0] = dH * a + H
+    f[..., 1] = -(ddgrho + 3.0 * ddgpres) * a - (dgrho + 3.0 * dgpres)
+    f[..., 2] = dep
+    f[..., 3] = -0.5 * dhp
+    f[..., 4] = -dH * thetac
+    f[..., 5] = -0.5 * dhp
+    f[..., 6] = -dH * thetab + k2 * dcs2 * deltab + (dpb43 * opac + pb43 * dopac) * (thetag - thetab)
+    polter = y[..., ig + 2] + y[..., igp] + y[..., igp + 2]
+    dop = dopac[..., None]
+    f[..., ig] = -2.0 / 3.0 * dhp
+    f[..., ig + 1] = -dopac * (thetag - thetab)
+    f[..., ig + 3:ig + Lg + 1] = -dop * y[..., ig + 3:ig + Lg + 1]
+    f[..., ig + 2] = 8.0 / 15.0 * k2 * dal - dopac * (y[..., ig + 2] - 0.1 * polter)
+    f[..., igp:igp + Lp + 1] = -dop * y[..., igp:igp + Lp + 1]
+    f[..., igp] += dopac * polter / 2
+    f[..., igp + 2] += dopac * polter / 10
+    f[..., ir] = -2.0 / 3.0 * dhp
+    f[..., ir + 2] = 8.0 / 15.0 * k2 * dal
+    dl = d.dlfdlq
+    kk = k[..., None]
+    f[..., iq0:iq0 + nq] = -kk * dv * psi1 + dhp[..., None] * dl / 6.0
+    f[..., iq0 + nq:iq0 + 2 * nq] = kk * dv * (psi0 - 2.0 * psi2) / 3.0
+    f[..., iq0 + 2 * nq:iq0 + 3 * nq] = kk * dv * (2 * psi1 - 3 * psi3) / 5.0 - (dhp / 15 + 2 / 5 * dep)[..., None] * dl
+    for l in range(3, Ln):
+        lo = y[..., iq0 + (l - 1) * nq:iq0 + l * nq]
+        hi = y[..., iq0 + (l + 1) * nq:iq0 + (l + 2) * nq]
+        f[..., iq0 + l * nq:iq0 + (l + 1) * nq] = kk * dv / (2 * l + 1) * (l * lo - (l + 1) * hi)
+    f[..., iq0 + Ln * nq:iq0 + (Ln + 1) * nq] = kk * dv * y[..., iq0 + (Ln - 1) * nq:iq0 + Ln * nq]
+    f[..., -2] = (wa * (thetaq + 0.5 * hprime) - (1 + w_Q) * 0.5 * dhp - 3 * (wa * H + (cs2_Q - w_Q) * dH) * deltaq
+                  - 9 * thetaq / k2 * (-wa * (cs2_Q - ca2_Q) * H ** 2 - (1 + w_Q) * dca2 * H ** 2
+                                       + (1 + w_Q) * (cs2_Q - ca2_Q) * 2 * H * dH))
+    f[..., -1] = -(1 - 3 * cs2_Q) * dH * thetaq + cs2_Q * k2 * deltaq * wa / (1 + w_Q) ** 2
+    return f
+
+
 def jacobian_bruteforce(tau, y, p, k, d: Dims):
     """Dense df/dy exactly as forward-mode AD sees it: the RHS is linear in y[1:], so column
     j>=1 is f(a, e_j) - f(a, 0); column 0 (the scale factor) by the complex step."""
@@ -217,7 +330,9 @@ def jacobian(tau, y, p, k, d: Dims):
     ig, igp, ir = d.ig, d.igp, d.ir
     Lg, Lp, Lr, Ln = d.lmaxg, d.lmaxgp, d.lmaxr, d.lmaxnu
     M = y.shape[0]
-    J = np.zeros((M, n, n))
+    cplx = np.iscomplexobj(y)            # only under the tangent oracle's complex step (oracle/discoeb_tangent.py)
+    dtype = np.complex128 if cplx else np.float64
+    J = np.zeros((M, n, n), dtype=dtype)
     a = y[:, 0]
     b = _bg(p, a)
     cs2, pb43, w_Q, rho_Q, H, ca2_Q, opac = b["cs2"], b["pb43"], b["w_Q"], b["rho_Q"], b["H"], b["ca2_Q"], b["opac"]
@@ -229,9 +344,9 @@ def jacobian(tau, y, p, k, d: Dims):
     dl = d.dlfdlq
 
     # gradients of the metric sources (rows of length n)
-    g_rho = np.zeros((M, n))
-    g_pres = np.zeros((M, n))
-    g_th = np.zeros((M, n))
+    g_rho = np.zeros((M, n), dtype=dtype)
+    g_pres = np.zeros((M, n), dtype=dtype)
+    g_th = np.zeros((M, n), dtype=dtype)
     g_rho[:, 3] = p["grhom"] * Omegac / a
     g_rho[:, 5] = p["grhom"] * p["Omegab"] / a
     g_rho[:, 7] = p["grhog"] / a ** 2
@@ -331,7 +446,11 @@ def jacobian(tau, y, p, k, d: Dims):
     J[:, -2, -2] += -3 * (cs2_Q - w_Q) * H
     J[:, -1, -1] += -(1 - 3 * cs2_Q) * H
     J[:, -1, -2] += cs2_Q / (1 + w_Q) * k2
-    # scale-factor column by complex step (every coefficient depends on a)
+    # scale-factor column by complex step (every coefficient depends on a); when the state is already
+    # complex (an outer complex step is in flight) the hand-derived column is used instead
+    if cplx:
+        J[:, :, 0] = rhs_da(tau, y, p, k, d)
+        return J
     h = 1e-30
     yc = y.astype(np.complex128)
     yc[:, 0] += 1j * h * a
@@ -468,7 +587,7 @@ def _bisect(func, xl, xr, numit):
     xr = np.array(xr, dtype=np.float64, copy=True)
     for _ in range(numit):
         xm = 0.5 * (xl + xr)
-        c = func(xm) * func(xl) > 0
+        c = np.real(func(xm)) * np.real(func(xl)) > 0
         xl, xr = np.where(c, xm, xl), np.where(c, xr, xm)
     return 0.5 * (xl + xr)
 
@@ -497,14 +616,14 @@ def determine_starting_time(p, k):
     xr = np.full(k.shape, np.log(tau1))
     lt_large = _bisect(cond_large_k, xl, xr, 7)
     lt_small = _bisect(cond_small_k, xl, xr, 7)
-    return np.exp(np.minimum(lt_small, lt_large))
+    return np.exp(np.where(np.real(lt_small) <= np.real(lt_large), lt_small, lt_large))
 
 
 def adiabatic_ics(tau, p, k, d: Dims):
     """perturbations.py:526-627 for a batch of modes."""
     M = k.shape[0]
-    y = np.zeros((M, d.n))
     a = p["a_of_tau_spline"].evaluate(tau)
+    y = np.zeros((M, d.n), dtype=np.result_type(a, np.float64))     # complex only under the tangent oracle's complex step
     rhonu_s = np.exp(p["logrhonu_of_loga_spline"].evaluate(np.log(a)))
     rhom = p["grhom"] * p["Omegam"] / a ** 3
     rhor = (p["grhog"] + p["grhor"] * (p["Neff"] + p["Nmnu"] * rhonu_s)) / a ** 4
