@@ -259,6 +259,13 @@ struct Problem {
   const double* rp_tnext; const int* rp_keep; const int* rp_n; int rp_stride;
   int mode;                                      // 0 evolve, 1 single step, 2 prologue only, 3 replay
   unsigned int* ticket;                          // work-queue counter
+  // forward tangents (deb_tangent.cuh): ntan directions, seeds laid out like the primal inputs with a leading [ntan]
+  int ntan;
+  const double* d_scalars; const double* d_tables;
+  const double* dtau_out;                        // [ntan, ncosmo, nout] (pre-kernel)
+  double* dy_out; double* dpk_out;               // [ntan, ncosmo, nk, nout, 20|n], [ntan, ncosmo, nk, nout]
+  const double* rp_dtnext;                       // replay: tangent of the prescribed step ends [ntan, ncosmo*nk, rp_stride]
+  const double* dbg_dt0; const double* dbg_dt1; const double* dbg_dy0; double* dbg_dy1;      // single-step mode
 };
 
 // momentum bins (background.py:27-38); weights already divided by 7 pi^4/120
@@ -938,8 +945,15 @@ DEB_DEV void helper_loop(const Problem& P, const CtaConst& C, WarpWs& W, HelpBox
 }
 #endif
 
-template <int NE, bool HELPER>
-DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, HelpBox* box, int mode DEB_LANE_PARAM) {
+}  // namespace deb
+#include "deb_tangent.cuh"
+namespace deb {
+
+// TAN: also carry one forward tangent (direction `tan` of P.ntan) through the same step sequence; the work
+// item is then (direction, cosmology, k).  TW is the tangent workspace (nullptr otherwise).
+template <int NE, bool HELPER, bool TAN = false>
+DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, HelpBox* box, int mode DEB_LANE_PARAM,
+                            const TanWs* TW = nullptr, int tan = 0) {
   const int n = P.n, nh = P.nh, nch = P.nch, nq = P.nq;
   const int nhb = nh - 1;            // head unknowns inside diagonal blocks (the last head row is a h')
   const int cosmo = mode / P.nk, kidx = mode - cosmo * P.nk;
@@ -974,27 +988,59 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, Help
   double tmin_out = t1;
   for (int j = 1; j < P.nout; ++j) { double tj = DEB_LDG(tout + j); t1 = fmax(t1, tj); tmin_out = fmin(tmin_out, tj); }
   double t, tnext;
+  // tangents of t, tnext, t1 and of the output times (TAN only)
+  double td = 0.0, tnextd = 0.0, t1d = 0.0, tmind = 0.0;
+  const size_t item = (size_t)tan * ((size_t)P.ncosmo * P.nk) + mode;
+  const double* toutd = nullptr;
+  if (TAN) {
+    DEB_LANE0_BEGIN
+      *TW->cd = load_cosmo_d(P, cosmo, tan);
+    DEB_LANE0_END
+    toutd = P.dtau_out + ((size_t)tan * P.ncosmo + cosmo) * P.nout;
+    int jmax = 0, jmin = 0;
+    for (int j = 1; j < P.nout; ++j) {
+      if (DEB_LDG(tout + j) > DEB_LDG(tout + jmax)) jmax = j;
+      if (DEB_LDG(tout + j) < DEB_LDG(tout + jmin)) jmin = j;
+    }
+    t1d = DEB_LDG(toutd + jmax); tmind = DEB_LDG(toutd + jmin);
+  }
   if (P.mode == 1) {
     t = DEB_LDG(P.dbg_t0 + mode); tnext = DEB_LDG(P.dbg_t1 + mode); t1 = tnext;
     DEB_LANES_BEGIN
       for (int e = lane; e < n; e += 32) W.y()[e] = DEB_LDG(P.dbg_y0 + (size_t)mode * n + e);
     DEB_LANES_END
+    if (TAN) {
+      td = DEB_LDG(P.dbg_dt0 + item); tnextd = DEB_LDG(P.dbg_dt1 + item); t1d = tnextd;
+      DEB_LANES_BEGIN
+        for (int e = lane; e < n; e += 32) TW->yd[e] = DEB_LDG(P.dbg_dy0 + item * n + e);
+      DEB_LANES_END
+    }
   } else {
-    double tau_start = 0.99 * fmin(tmin_out, start_time(c, k, DEB_LDG(P.lt_small + cosmo)));
+    const double st0 = start_time(c, k, DEB_LDG(P.lt_small + cosmo));
+    double tau_start = 0.99 * fmin(tmin_out, st0);
     IcScalars ics = ic_scalars(c, tau_start, k);
     DEB_LANES_BEGIN
       for (int e = lane; e < n; e += 32) W.y()[e] = ic_value(P, c, nb, ics, elem_desc(P, e), k);
     DEB_LANES_END
+    if (TAN) {
+      const Dual stD = start_time_d(*TW->cd, k);
+      td = 0.99 * (tmin_out <= st0 ? tmind : stD.d);
+      const IcScalarsD icd = ic_scalars_d(*TW->cd, mk(tau_start, td), k);
+      DEB_LANES_BEGIN
+        for (int e = lane; e < n; e += 32) TW->yd[e] = ic_value_d(P, *TW->cd, nb, icd, elem_desc(P, e), k).d;
+      DEB_LANES_END
+    }
     if (P.mode == 2) {
       DEB_LANES_BEGIN
-        if (lane == 0) P.dbg_tau_start[mode] = tau_start;
-        for (int e = lane; e < n; e += 32) P.dbg_ics[(size_t)mode * n + e] = W.y()[e];
+        if (lane == 0) P.dbg_tau_start[item] = TAN ? td : tau_start;
+        for (int e = lane; e < n; e += 32) P.dbg_ics[item * n + e] = TAN ? TW->yd[e] : W.y()[e];
       DEB_LANES_END
       return;
     }
     t = tau_start;
     tnext = t + fmin(t / 4.0, 0.5 * (t1 - t));          // dt0 (perturbations.py:756)
-    if (tnext > t1 - 1e-10) tnext = t1;
+    if (TAN) tnextd = td + ((t / 4.0 <= 0.5 * (t1 - t)) ? td / 4.0 : 0.5 * (t1d - td));
+    if (tnext > t1 - 1e-10) { tnext = t1; tnextd = t1d; }
   }
 
   double inv_prev = 1.0, inv_pprev = 1.0;
@@ -1005,11 +1051,13 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, Help
     if (P.mode == 3) {
       if (nsteps >= DEB_LDG(P.rp_n + mode)) break;
       tnext = DEB_LDG(P.rp_tnext + (size_t)mode * P.rp_stride + nsteps);
+      if (TAN) tnextd = DEB_LDG(P.rp_dtnext + item * P.rp_stride + nsteps);
       // the prescribed end time comes from another evaluation of tau_of_a(aexp_out): snap it onto ours
-      if (fabs(tnext - t1) <= 1e-12 * fabs(t1)) tnext = t1;
+      if (fabs(tnext - t1) <= 1e-12 * fabs(t1)) { tnext = t1; tnextd = t1d; }
     }
     DEB_REGS(double, ks, [7][NE]);    // stage vectors k_1..k_7: registers, scoped to one step (dead while W is factored)
     const double dt = tnext - t;
+    const double ddt = tnextd - td;
     const double invdt = DEB_RCP(dt);
     const double idg = DEB_RCP(dt * RD_GAMMA);      // diagonal of W = I/(gamma dt) - J
     const double invt0 = DEB_RCP(t);
@@ -1219,6 +1267,64 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, Help
     }
     const double gdt = dt * RD_GAMMA;      // 1 / idg
 
+    // W x = v in place for a second vector with the factorisation above (the tangent right-hand sides); the same
+    // sequence as the primal solve inside the stage loop: a column, backward tail sweep, block inverses + Woodbury,
+    // a h' row, forward tail sweep
+    auto solve_second = [&](double* v) {
+      const double x0 = v[0] / x0piv;
+      DEB_SYNC();
+      DEB_LANES_BEGIN
+        for (int e = lane; e < n; e += 32) v[e] = (e == 0) ? x0 : v[e] + W.ja()[e] * x0;
+      DEB_LANES_END
+      DEB_LANES_BEGIN
+        if (lane < nch) {
+          const int s = C.ch_stride[lane], L = C.ch_lmax[lane];
+          double* rp = v + (C.ch_base[lane] + L * s);
+          const double* mp = W.m() + (C.ch_base[lane] + L * s);
+          double bp = *rp;
+          for (int l = L - 1; l >= 2; --l) { rp -= s; mp -= s; bp = *rp - *mp * bp; *rp = bp; }
+        }
+      DEB_LANES_END
+      DEB_LANES_BEGIN
+        W.xb()[lane] = lane < nhb ? v[C.hidx[W.perm()[lane]]] : 0.0;
+        if (lane < 8) W.xb()[NHMAX + lane] = 0.0;
+      DEB_LANES_END
+      DEB_LANES_BEGIN
+        DEB_USE(pcol); DEB_USE(s1); DEB_USE(s2); DEB_USE(s3); DEB_USE(pval);
+        s1 = s2 = s3 = 0.0; pval = 0.0;
+        if (lane < nhb) {
+          const int lo = C.blo[lane];
+          const double* rb = hrow(W, lane, lo) + lo;
+          const double* xb = W.xb() + lo;
+          double acc = 0.0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc += rb[i] * xb[i];
+          pval = acc;
+          s1 = W.gh()[pcol] * acc; s2 = W.ge()[pcol] * acc; s3 = W.j1()[pcol] * acc;
+        }
+      DEB_LANES_END
+      {
+        const double th = DEB_WARP_SUM(s1), te = DEB_WARP_SUM(s2), ta = DEB_WARP_SUM(s3);
+        const double sh = ci_hh * th + ci_he * te, se = ci_eh * th + ci_ee * te;
+        DEB_LANES_BEGIN
+          DEB_USE(pcol); DEB_USE(pval);
+          if (lane < nhb) v[C.hidx[pcol]] = pval + W.qh()[pcol] * sh + W.qe()[pcol] * se;
+          else if (lane == nhb) v[1] = (v[1] + ta + jq_h * sh + jq_e * se) * gdt;
+        DEB_LANES_END
+      }
+      DEB_LANES_BEGIN
+        if (lane < nch) {
+          const int s = C.ch_stride[lane], L = C.ch_lmax[lane];
+          const int i0 = C.ch_base[lane] + 2 * s;
+          double* rp = v + i0;
+          const double* ip = W.ie() + i0;
+          const double* gp = W.g() + i0;
+          double x = *rp;
+          for (int l = 3; l <= L; ++l) { rp += s; ip += s; gp += s; x = *rp * *ip + *gp * x; *rp = x; }
+        }
+      DEB_LANES_END
+    };
+
     // ================= 8 stages =================
     double errnorm2 = 0.0;
 #pragma unroll 1
@@ -1275,6 +1381,7 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, Help
             case 7: DEB_FOR_OWN(W.r()[e] = invdt * (RD_C71 * ks[0][j] + RD_C72 * ks[1][j] + RD_C73 * ks[2][j] + RD_C74 * ks[3][j] + RD_C75 * ks[4][j] + RD_C76 * ks[5][j]);) break;
             default: DEB_FOR_OWN(W.r()[e] = invdt * (RD_C81 * ks[0][j] + RD_C82 * ks[1][j] + RD_C83 * ks[2][j] + RD_C84 * ks[3][j] + RD_C85 * ks[4][j] + RD_C86 * ks[5][j] + RD_C87 * ks[6][j]);) break;
           }
+          if (TAN) { DEB_FOR_OWN(TW->cc[e] = W.r()[e];) }
         DEB_LANES_END
         const double dtt = dtd * invt0 * invt0;
 #ifndef DEB_CPU_EMU
@@ -1420,17 +1527,29 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, Help
           }
         DEB_LANES_END
       }
+      if (TAN) {
+        // ---- tangent stage: rdot_i, solve with the same factorisation, keep kdot_i ----
+        tan_stage_rhs(P, C, W, *TW, st, k, t, td, dt, ddt DEB_LANE_ARG);
+        solve_second(TW->rd);
+        if (st < 8) {
+          DEB_LANES_BEGIN
+            for (int e = lane; e < n; e += 32) TW->kd[(size_t)(st - 1) * P.np + e] = TW->rd[e];
+          DEB_LANES_END
+        }
+      }
     }
     // y1 = u + k8 -> u ; err = k8 = r
     DEB_LANES_BEGIN
       DEB_USE(nanflag);
       nanflag = 0;
       DEB_FOR_OWN(const double y1v = W.u()[e] + W.r()[e]; W.u()[e] = y1v; nanflag |= (y1v != y1v);)
+      if (TAN) { DEB_FOR_OWN(TW->ud[e] = TW->ud[e] + TW->rd[e];) }
     DEB_LANES_END
 
     if (P.mode == 1) {
       DEB_LANES_BEGIN
-        for (int e = lane; e < n; e += 32) { P.dbg_y1[(size_t)mode * n + e] = W.u()[e]; P.dbg_err[(size_t)mode * n + e] = W.r()[e]; }
+        for (int e = lane; e < n; e += 32) { P.dbg_y1[item * n + e] = W.u()[e]; P.dbg_err[item * n + e] = W.r()[e]; }
+        if (TAN) { for (int e = lane; e < n; e += 32) P.dbg_dy1[item * n + e] = TW->ud[e]; }
       DEB_LANES_END
       return;
     }
@@ -1467,21 +1586,41 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, Help
         const double tt = DEB_LDG(tout + save_idx);
         const double coeff = (tnext == t) ? 0.0 : (tt - t) / (tnext - t);
         const size_t obase = ((size_t)mode * P.nout + save_idx);
+        const bool wr = !TAN || tan == 0;          // every direction repeats the primal solve; direction 0 writes it
+        double coeffd = 0.0;
+        if (TAN && tnext != t) coeffd = ((mk(tt, DEB_LDG(toutd + save_idx)) - mk(t, td)) / (mk(tnext, tnextd) - mk(t, td))).d;
+        const size_t dbase = item * P.nout + save_idx;
         if (P.return_full) {
           DEB_LANES_BEGIN
-            for (int e = lane; e < n; e += 32) P.y_out[obase * n + e] = W.y()[e] + coeff * (W.u()[e] - W.y()[e]);
+            if (wr) { for (int e = lane; e < n; e += 32) P.y_out[obase * n + e] = W.y()[e] + coeff * (W.u()[e] - W.y()[e]); }
+            if (TAN) {
+              for (int e = lane; e < n; e += 32)
+                P.dy_out[dbase * n + e] = TW->yd[e] + coeffd * (W.u()[e] - W.y()[e]) + coeff * (TW->ud[e] - TW->yd[e]);
+            }
           DEB_LANES_END
         } else {
           DEB_LANES_BEGIN
             for (int e = lane; e < n; e += 32) W.r()[e] = W.y()[e] + coeff * (W.u()[e] - W.y()[e]);
+            if (TAN) {
+              for (int e = lane; e < n; e += 32) TW->rd[e] = TW->yd[e] + coeffd * (W.u()[e] - W.y()[e]) + coeff * (TW->ud[e] - TW->yd[e]);
+            }
           DEB_LANES_END
           DEB_LANE0_BEGIN
-            double o20[20];
-            convert_outputs(P, c, nb, W.r(), k, o20);
-            for (int q = 0; q < 20; ++q) P.y_out[obase * 20 + q] = o20[q];
-            if (P.pk_out && P.power_idx >= 0) {
-              double yv = o20[P.power_idx];
-              P.pk_out[obase] = 2.0 * 9.869604401089358 * c.As * pow(k / c.kp, c.ns - 1.0) * pow(k, -3.0) * yv * yv;
+            if (wr) {
+              double o20[20];
+              convert_outputs(P, c, nb, W.r(), k, o20);
+              for (int q = 0; q < 20; ++q) P.y_out[obase * 20 + q] = o20[q];
+              if (P.pk_out && P.power_idx >= 0) {
+                double yv = o20[P.power_idx];
+                P.pk_out[obase] = 2.0 * 9.869604401089358 * c.As * pow(k / c.kp, c.ns - 1.0) * pow(k, -3.0) * yv * yv;
+              }
+            }
+            if (TAN) {
+              Dual od[20];
+              const StateVD sy = {W.r(), TW->rd};
+              convert_outputs_d(P, *TW->cd, nb, sy, k, od);
+              for (int q = 0; q < 20; ++q) P.dy_out[dbase * 20 + q] = od[q].d;
+              if (P.dpk_out && P.power_idx >= 0) P.dpk_out[dbase] = power_d(*TW->cd, k, od[P.power_idx]).d;
             }
           DEB_LANE0_END
         }
@@ -1489,19 +1628,26 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, Help
       }
       DEB_LANES_BEGIN
         DEB_FOR_OWN(W.y()[e] = W.u()[e];)
+        if (TAN) { DEB_FOR_OWN(TW->yd[e] = TW->ud[e];) }
       DEB_LANES_END
       inv_pprev = inv_prev; inv_prev = inv;
+      td = (tnext <= t1) ? tnextd : t1d;
       t = fmin(tnext, t1);
     }
-    double tn = t + dtn;
-    if (tn > t1 - 1e-10) tn = keep ? t1 : t + 0.5 * (t1 - t);
-    tnext = tn;
+    // dt_next = dt * factor: the factor is non-differentiable (diffrax), the step length carries its tangent
+    double tn = t + dtn, tnd = td + ddt * fac;
+    if (tn > t1 - 1e-10) {
+      if (keep) { tn = t1; tnd = t1d; } else { tn = t + 0.5 * (t1 - t); tnd = td + 0.5 * (t1d - td); }
+    }
+    tnext = tn; tnextd = tnd;
     if (!(tnext == tnext) || isinf(tnext)) status = 2;
   }
   if (status == 0 && t < t1) status = 1;
   DEB_LANE0_BEGIN
-    P.status[mode] = status; P.nsteps[mode] = nsteps;
-    if (P.naccept) P.naccept[mode] = nacc;
+    if (!TAN || tan == 0) {
+      P.status[mode] = status; P.nsteps[mode] = nsteps;
+      if (P.naccept) P.naccept[mode] = nacc;
+    }
   DEB_LANE0_END
 }
 

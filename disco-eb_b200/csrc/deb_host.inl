@@ -12,7 +12,7 @@ static inline int fill_problem(const deb_dims* d, const deb_ctrl* c, deb::Proble
   if (!d || !c || !P) return DEB_E_ARG;
   if (d->ncosmo < 1 || d->nk < 1 || d->nout < 1 || d->max_steps < 1) return DEB_E_ARG;
   if (d->nth < 2 || d->nnu < 2) return DEB_E_ARG;
-  if (d->ntan != 0) return DEB_E_UNSUPPORTED;
+  if (d->ntan < 0) return DEB_E_ARG;
   if (d->lmaxg < 3 || d->lmaxgp < 3 || d->lmaxr < 3 || d->lmaxnu < 3) return DEB_E_UNSUPPORTED;
   if (d->lmaxg >= deb::LMAXCAP || d->lmaxgp >= deb::LMAXCAP || d->lmaxr >= deb::LMAXCAP || d->lmaxnu >= deb::LMAXCAP)
     return DEB_E_UNSUPPORTED;
@@ -25,6 +25,7 @@ static inline int fill_problem(const deb_dims* d, const deb_ctrl* c, deb::Proble
   P->nth = d->nth; P->nnu = d->nnu;
   P->max_steps = d->max_steps; P->return_full = d->return_full; P->k_per_cosmo = d->k_per_cosmo;
   P->power_idx = d->power_idx;
+  P->ntan = d->ntan;
   P->n = deb_nvar_impl(d);
   P->np = (P->n + 1) & ~1;
   P->nh = 17 + 3 * d->nqmax;
@@ -44,7 +45,7 @@ static inline const char* deb_strerror_impl(int code) {
   switch (code) {
     case DEB_OK: return "ok";
     case DEB_E_ARG: return "invalid argument";
-    case DEB_E_UNSUPPORTED: return "unsupported configuration (need lmax* in [3,95], nqmax in [3,5], n <= 384, ntan == 0)";
+    case DEB_E_UNSUPPORTED: return "unsupported configuration (need lmax* in [3,95], nqmax in [3,5], n <= 384)";
     case DEB_E_WORKSPACE: return "workspace too small";
     case DEB_E_CUDA: return "CUDA runtime error";
     case DEB_E_NODEVICE: return "no CUDA device";

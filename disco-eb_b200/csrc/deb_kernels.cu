@@ -28,6 +28,13 @@ __global__ void k_tau_out(Problem P, double* tau_out, double* lt_small) {
   Spl s = get_spline(P, c, T_TAU_OF_A);
   if (P.aexp_out) tau_out[i] = spl_eval(s, P.aexp_out[j]);
   if (j == 0) { Cosmo cs = load_cosmo(P, c); lt_small[c] = start_small_k(cs); }
+  // tangents of the output times: aexp_out is fixed, the tau_of_a table carries the seed
+  if (P.ntan > 0 && P.aexp_out && P.dtau_out) {
+    for (int tn = 0; tn < P.ntan; ++tn) {
+      SplT st; st.p = s; st.t = get_spline_from(P.d_tables, P, tn * P.ncosmo + c, T_TAU_OF_A);
+      const_cast<double*>(P.dtau_out)[((size_t)tn * P.ncosmo + c) * P.nout + j] = spl_eval_g<Dual>(st, mk(P.aexp_out[j], 0.0)).d;
+    }
+  }
 }
 
 static __host__ __device__ size_t warp_ws_bytes(int np) { return ((warp_ws_doubles(np) * sizeof(double)) + 15) & ~(size_t)15; }
@@ -104,7 +111,49 @@ __global__ void __launch_bounds__(64, 1) k_evolve_h(const __grid_constant__ Prob
   DEB_BAR_ARRIVE(BAR_REQ);
 }
 
+// Tangent variant: one warp per (direction, cosmology, k) work item; the primal solve is repeated per direction
+// (identical bits), the tangent rides on its factorisations.  Shared memory per item: primal workspace + 12 n doubles.
+template <int NE>
+__global__ void __launch_bounds__(32, 1) k_evolve_t(const __grid_constant__ Problem P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  CtaConst* C = reinterpret_cast<CtaConst*>(smem_raw);
+  size_t off = (sizeof(CtaConst) + 15) & ~(size_t)15;
+  int* tail = reinterpret_cast<int*>(smem_raw + off);
+  off = (off + (size_t)P.np * sizeof(int) + 15) & ~(size_t)15;
+  const int lane = threadIdx.x & 31;
+  double* wsb = reinterpret_cast<double*>(smem_raw + off);
+  init_cta_const(P, *C, tail, threadIdx.x, 32);
+  __syncwarp();
+  WarpWs W;
+  carve(W, wsb, P.np);
+  TanWs TW;
+  carve_tan(TW, reinterpret_cast<double*>(smem_raw + off + warp_ws_bytes(P.np)), P.np);
+  const int per_k = P.ncosmo * P.ntan;
+  const int total = per_k * P.nk;
+  for (;;) {
+    unsigned int tk = 0;
+    if (lane == 0) tk = atomicAdd(P.ticket, 1u);
+    tk = __shfl_sync(0xffffffffu, tk, 0);
+    if (tk >= (unsigned int)total) break;
+    const int kd = tk / per_k, rest = tk - kd * per_k;
+    const int tan = rest / P.ncosmo, cs = rest - tan * P.ncosmo;
+    const int mode = cs * P.nk + (P.nk - 1 - kd);
+    integrate_mode<NE, false, true>(P, *C, W, nullptr, mode, lane, &TW, tan);
+    __syncwarp();
+  }
+}
+
 typedef void (*evolve_kernel_t)(const Problem);
+static evolve_kernel_t pick_tangent_kernel(int n) {
+  int ne = (n + 31) / 32;
+  if (ne <= 3) return k_evolve_t<3>;
+  if (ne <= 4) return k_evolve_t<4>;
+  if (ne <= 6) return k_evolve_t<6>;
+  if (ne <= 9) return k_evolve_t<9>;
+  if (ne <= 12) return k_evolve_t<12>;
+  return nullptr;
+}
+static size_t tan_smem_bytes(int np) { return cta_smem_bytes(np, 1) + ((tan_ws_doubles(np) * sizeof(double) + 15) & ~(size_t)15); }
 static evolve_kernel_t pick_kernel(int n, bool many_modes, bool few_modes, int* warps, size_t* extra_smem) {
   int ne = (n + 31) / 32;
   *warps = 1; *extra_smem = 0;
@@ -132,6 +181,21 @@ static int launch_evolve(const Problem& P, cudaStream_t st) {
   int dev = 0, nsm = 0, occ = 0;
   CUDA_TRY(cudaGetDevice(&dev));
   CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+  if (P.ntan > 0) {
+    evolve_kernel_t kern = pick_tangent_kernel(P.n);
+    if (!kern) return DEB_E_UNSUPPORTED;
+    const size_t smem = tan_smem_bytes(P.np);
+    CUDA_TRY(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)kern, 32, smem));
+    if (occ < 1) return DEB_E_UNSUPPORTED;
+    long total = (long)P.ncosmo * P.nk * P.ntan;
+    long grid = (long)nsm * occ;
+    if (grid > total) grid = total;
+    CUDA_TRY(cudaMemsetAsync(P.ticket, 0, sizeof(unsigned int), st));
+    kern<<<(unsigned)grid, 32, smem, st>>>(P);
+    CUDA_TRY(cudaGetLastError());
+    return DEB_OK;
+  }
   int warps = 1;
   size_t extra = 0;
   const long nmodes = (long)P.ncosmo * P.nk;
@@ -173,12 +237,26 @@ int deb_evolve_f64(const deb_dims* dims, const deb_ctrl* ctrl, const double* sca
                    const double* kmodes, const double* aexp_out, double* y_out, double* pk_out, double* tau_out,
                    int32_t* status, int32_t* nsteps, int32_t* naccept, void* workspace, size_t workspace_bytes,
                    void* stream) {
+  if (dims && dims->ntan != 0) return DEB_E_ARG;       // tangents go through deb_evolve_tangent_f64
+  return deb_evolve_tangent_f64(dims, ctrl, scalars, tables, kmodes, aexp_out, nullptr, nullptr, y_out, nullptr, pk_out, nullptr,
+                                tau_out, nullptr, status, nsteps, naccept, workspace, workspace_bytes, stream);
+}
+
+int deb_evolve_tangent_f64(const deb_dims* dims, const deb_ctrl* ctrl, const double* scalars, const double* tables,
+                           const double* kmodes, const double* aexp_out, const double* d_scalars, const double* d_tables,
+                           double* y_out, double* dy_out, double* pk_out, double* dpk_out, double* tau_out, double* dtau_out,
+                           int32_t* status, int32_t* nsteps, int32_t* naccept, void* workspace, size_t workspace_bytes,
+                           void* stream) {
   Problem P;
   int rc = fill_problem(dims, ctrl, &P);
   if (rc) return rc;
   if (!scalars || !tables || !kmodes || !aexp_out || !y_out || !tau_out || !status || !nsteps || !workspace) return DEB_E_ARG;
   if (workspace_bytes < deb_workspace_bytes(dims)) return DEB_E_WORKSPACE;
   if (dims->power_idx >= 0 && !pk_out) return DEB_E_ARG;
+  if (dims->ntan > 0 && (!d_scalars || !d_tables || !dy_out || !dtau_out)) return DEB_E_ARG;
+  if (dims->ntan > 0 && dims->power_idx >= 0 && !dpk_out) return DEB_E_ARG;
+  P.d_scalars = d_scalars; P.d_tables = d_tables; P.dy_out = dy_out; P.dpk_out = dims->power_idx >= 0 ? dpk_out : nullptr;
+  P.dtau_out = dtau_out;
   cudaStream_t st = (cudaStream_t)stream;
   P.scalars = scalars; P.tables = tables; P.kmodes = kmodes; P.aexp_out = aexp_out;
   P.y_out = y_out; P.pk_out = dims->power_idx >= 0 ? pk_out : nullptr; P.tau_out = tau_out;
@@ -255,27 +333,32 @@ extern "C" void deb_ctx_destroy(deb_ctx* c) {
   delete c;
 }
 
-extern "C" int deb_ctx_evolve_host_f64(deb_ctx* c, const deb_dims* dims, const deb_ctrl* ctrl, const double* scalars,
-                                       const double* tables, const double* kmodes, const double* aexp_out, double* y_out,
-                                       double* pk_out, double* tau_out, int32_t* status, int32_t* nsteps, int32_t* naccept,
-                                       float* kernel_ms) {
+static int ctx_evolve(deb_ctx* c, const deb_dims* dims, const deb_ctrl* ctrl, const double* scalars, const double* tables,
+                      const double* kmodes, const double* aexp_out, const double* d_scalars, const double* d_tables,
+                      double* y_out, double* dy_out, double* pk_out, double* dpk_out, double* tau_out, double* dtau_out,
+                      int32_t* status, int32_t* nsteps, int32_t* naccept, float* kernel_ms) {
   if (!c) return DEB_E_ARG;
   Problem P0;
   int rc = fill_problem(dims, ctrl, &P0);
   if (rc) return rc;
   if (!scalars || !tables || !kmodes || !aexp_out || !y_out || !tau_out || !status || !nsteps) return DEB_E_ARG;
+  const size_t nt = dims->ntan;
+  if (nt > 0 && (!d_scalars || !d_tables || !dy_out || !dtau_out)) return DEB_E_ARG;
   CUDA_TRY(cudaSetDevice(c->device));
   const size_t nc = dims->ncosmo, nk = dims->nk, nout = dims->nout;
   const size_t nf = dims->return_full ? (size_t)P0.n : 20;
   const size_t tl = deb_table_len(dims);
   const size_t nkm = dims->k_per_cosmo ? nc * nk : nk;
-  const bool pk = dims->power_idx >= 0 && pk_out;
-  // input block: scalars | tables | kmodes | aexp_out        output block: y | pk | tau | status | nsteps | naccept
+  const bool pk = dims->power_idx >= 0 && pk_out && (nt == 0 || dpk_out);
+  // input block : scalars | tables | kmodes | aexp_out | d_scalars | d_tables
+  // output block: y | pk | tau | status | nsteps | naccept | dy | dpk | dtau
   const size_t i_sc = 0, i_tb = i_sc + al256(nc * DEB_NSCAL * 8), i_k = i_tb + al256(nc * tl * 8), i_a = i_k + al256(nkm * 8),
-               in_bytes = i_a + al256(nout * 8);
+               i_dsc = i_a + al256(nout * 8), i_dtb = i_dsc + al256(nt * nc * DEB_NSCAL * 8),
+               in_bytes = i_dtb + al256(nt * nc * tl * 8);
   const size_t o_y = 0, o_pk = o_y + al256(nc * nk * nout * nf * 8), o_tau = o_pk + al256(pk ? nc * nk * nout * 8 : 0),
                o_st = o_tau + al256(nc * nout * 8), o_ns = o_st + al256(nc * nk * 4), o_na = o_ns + al256(nc * nk * 4),
-               out_bytes = o_na + al256(nc * nk * 4);
+               o_dy = o_na + al256(nc * nk * 4), o_dpk = o_dy + al256(nt * nc * nk * nout * nf * 8),
+               o_dtau = o_dpk + al256(pk ? nt * nc * nk * nout * 8 : 0), out_bytes = o_dtau + al256(nt * nc * nout * 8);
   const size_t ws_bytes = al256(deb_workspace_bytes(dims));
   rc = ctx_reserve(c, in_bytes + out_bytes + ws_bytes, in_bytes + out_bytes);
   if (rc) return rc;
@@ -285,14 +368,17 @@ extern "C" int deb_ctx_evolve_host_f64(deb_ctx* c, const deb_dims* dims, const d
   memcpy(hin + i_tb, tables, nc * tl * 8);
   memcpy(hin + i_k, kmodes, nkm * 8);
   memcpy(hin + i_a, aexp_out, nout * 8);
+  if (nt) { memcpy(hin + i_dsc, d_scalars, nt * nc * DEB_NSCAL * 8); memcpy(hin + i_dtb, d_tables, nt * nc * tl * 8); }
   CUDA_TRY(cudaMemcpyAsync(din, hin, in_bytes, cudaMemcpyHostToDevice, c->st));
-  CUDA_TRY(cudaMemsetAsync(dout + o_y, 0, nc * nk * nout * nf * 8, c->st));
+  CUDA_TRY(cudaMemsetAsync(dout, 0, out_bytes, c->st));
   CUDA_TRY(cudaEventRecord(c->e0, c->st));
   deb_dims d2 = *dims;
   if (!pk) d2.power_idx = -1;
-  rc = deb_evolve_f64(&d2, ctrl, (double*)(din + i_sc), (double*)(din + i_tb), (double*)(din + i_k), (double*)(din + i_a),
-                      (double*)(dout + o_y), (double*)(dout + o_pk), (double*)(dout + o_tau), (int32_t*)(dout + o_st),
-                      (int32_t*)(dout + o_ns), (int32_t*)(dout + o_na), dws, ws_bytes, (void*)c->st);
+  rc = deb_evolve_tangent_f64(&d2, ctrl, (double*)(din + i_sc), (double*)(din + i_tb), (double*)(din + i_k), (double*)(din + i_a),
+                              nt ? (double*)(din + i_dsc) : nullptr, nt ? (double*)(din + i_dtb) : nullptr,
+                              (double*)(dout + o_y), nt ? (double*)(dout + o_dy) : nullptr, (double*)(dout + o_pk),
+                              nt ? (double*)(dout + o_dpk) : nullptr, (double*)(dout + o_tau), nt ? (double*)(dout + o_dtau) : nullptr,
+                              (int32_t*)(dout + o_st), (int32_t*)(dout + o_ns), (int32_t*)(dout + o_na), dws, ws_bytes, (void*)c->st);
   if (rc != DEB_OK) { cudaStreamSynchronize(c->st); return rc; }
   CUDA_TRY(cudaEventRecord(c->e1, c->st));
   CUDA_TRY(cudaMemcpyAsync(hout, dout, out_bytes, cudaMemcpyDeviceToHost, c->st));
@@ -303,8 +389,32 @@ extern "C" int deb_ctx_evolve_host_f64(deb_ctx* c, const deb_dims* dims, const d
   memcpy(status, hout + o_st, nc * nk * 4);
   memcpy(nsteps, hout + o_ns, nc * nk * 4);
   if (naccept) memcpy(naccept, hout + o_na, nc * nk * 4);
+  if (nt) {
+    memcpy(dy_out, hout + o_dy, nt * nc * nk * nout * nf * 8);
+    if (pk) memcpy(dpk_out, hout + o_dpk, nt * nc * nk * nout * 8);
+    memcpy(dtau_out, hout + o_dtau, nt * nc * nout * 8);
+  }
   if (kernel_ms) CUDA_TRY(cudaEventElapsedTime(kernel_ms, c->e0, c->e1));
   return DEB_OK;
+}
+
+extern "C" int deb_ctx_evolve_host_f64(deb_ctx* c, const deb_dims* dims, const deb_ctrl* ctrl, const double* scalars,
+                                       const double* tables, const double* kmodes, const double* aexp_out, double* y_out,
+                                       double* pk_out, double* tau_out, int32_t* status, int32_t* nsteps, int32_t* naccept,
+                                       float* kernel_ms) {
+  if (dims && dims->ntan != 0) return DEB_E_ARG;
+  return ctx_evolve(c, dims, ctrl, scalars, tables, kmodes, aexp_out, nullptr, nullptr, y_out, nullptr, pk_out, nullptr, tau_out,
+                    nullptr, status, nsteps, naccept, kernel_ms);
+}
+
+extern "C" int deb_ctx_evolve_tangent_host_f64(deb_ctx* c, const deb_dims* dims, const deb_ctrl* ctrl, const double* scalars,
+                                               const double* tables, const double* kmodes, const double* aexp_out,
+                                               const double* d_scalars, const double* d_tables, double* y_out, double* dy_out,
+                                               double* pk_out, double* dpk_out, double* tau_out, double* dtau_out,
+                                               int32_t* status, int32_t* nsteps, int32_t* naccept, float* kernel_ms) {
+  if (!dims || dims->ntan < 1) return DEB_E_ARG;
+  return ctx_evolve(c, dims, ctrl, scalars, tables, kmodes, aexp_out, d_scalars, d_tables, y_out, dy_out, pk_out, dpk_out, tau_out,
+                    dtau_out, status, nsteps, naccept, kernel_ms);
 }
 
 // One cached context per (host thread, device) backs the context-free entry; deb_host_cache_release() drops the
@@ -338,6 +448,21 @@ extern "C" int deb_evolve_host_f64(const deb_dims* dims, const deb_ctrl* ctrl, c
   if (rc) return rc;
   return deb_ctx_evolve_host_f64(c, dims, ctrl, scalars, tables, kmodes, aexp_out, y_out, pk_out, tau_out, status, nsteps,
                                  naccept, kernel_ms);
+}
+
+extern "C" int deb_evolve_tangent_host_f64(const deb_dims* dims, const deb_ctrl* ctrl, const double* scalars, const double* tables,
+                                          const double* kmodes, const double* aexp_out, const double* d_scalars,
+                                          const double* d_tables, double* y_out, double* dy_out, double* pk_out, double* dpk_out,
+                                          double* tau_out, double* dtau_out, int32_t* status, int32_t* nsteps, int32_t* naccept,
+                                          int32_t device, float* kernel_ms) {
+  Problem P0;
+  int rc = fill_problem(dims, ctrl, &P0);
+  if (rc) return rc;
+  deb_ctx* c = nullptr;
+  rc = cached_ctx(device, &c);
+  if (rc) return rc;
+  return deb_ctx_evolve_tangent_host_f64(c, dims, ctrl, scalars, tables, kmodes, aexp_out, d_scalars, d_tables, y_out, dy_out,
+                                         pk_out, dpk_out, tau_out, dtau_out, status, nsteps, naccept, kernel_ms);
 }
 
 extern "C" {
@@ -433,6 +558,65 @@ int deb_debug_replay_host_f64(const deb_dims* dims, const deb_ctrl* ctrl, const 
                               int32_t* nsteps, int32_t device) {
   return debug_common(dims, ctrl, scalars, tables, kmodes, aexp_out, device, 3, 1, nullptr, nullptr, nullptr, nullptr, nullptr,
                       rp_tnext, rp_keep, rp_n, rp_stride, y_out, nsteps);
+}
+
+// replay with one or more tangent directions (host pointers): the parity test of the tangent path
+int deb_debug_replay_tangent_host_f64(const deb_dims* dims, const deb_ctrl* ctrl, const double* scalars, const double* tables,
+                                      const double* kmodes, const double* aexp_out, const double* d_scalars,
+                                      const double* d_tables, const double* rp_tnext, const double* rp_dtnext,
+                                      const int32_t* rp_keep, const int32_t* rp_n, int32_t rp_stride, double* y_out,
+                                      double* dy_out, double* dtau_out, int32_t* nsteps, int32_t device) {
+  Problem P;
+  int rc = fill_problem(dims, ctrl, &P);
+  if (rc) return rc;
+  if (dims->ntan < 1 || !d_scalars || !d_tables || !rp_tnext || !rp_dtnext || !rp_keep || !rp_n || !y_out || !dy_out) return DEB_E_ARG;
+  if (deb_device_count() < 1) return DEB_E_NODEVICE;
+  CUDA_TRY(cudaSetDevice(device));
+  const size_t nc = dims->ncosmo, nk = dims->nk, nout = dims->nout, total = nc * nk, n = P.n, nt = dims->ntan;
+  const size_t tl = deb_table_len(dims);
+  const size_t nkm = dims->k_per_cosmo ? nc * nk : nk;
+  const size_t nf = dims->return_full ? n : 20;
+  DevBuf d_sc, d_tb, d_dsc, d_dtb, d_k, d_a, d_tau, d_dtau, d_st, d_ns, d_ws, d_rt, d_rdt, d_rk, d_rn, d_y, d_dy;
+  if (d_sc.alloc(nc * DEB_NSCAL * 8) || d_tb.alloc(nc * tl * 8) || d_dsc.alloc(nt * nc * DEB_NSCAL * 8) || d_dtb.alloc(nt * nc * tl * 8) ||
+      d_k.alloc(nkm * 8) || d_a.alloc(nout * 8) || d_tau.alloc(nc * nout * 8) || d_dtau.alloc(nt * nc * nout * 8) ||
+      d_st.alloc(total * 4) || d_ns.alloc(total * 4) || d_ws.alloc(deb_workspace_bytes(dims)) ||
+      d_rt.alloc(total * (size_t)rp_stride * 8 + 8) || d_rdt.alloc(nt * total * (size_t)rp_stride * 8 + 8) ||
+      d_rk.alloc(total * (size_t)rp_stride * 4 + 8) || d_rn.alloc(total * 4) || d_y.alloc(total * nout * nf * 8) ||
+      d_dy.alloc(nt * total * nout * nf * 8))
+    return DEB_E_CUDA;
+  CUDA_TRY(cudaMemcpy(d_sc.p, scalars, nc * DEB_NSCAL * 8, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(d_tb.p, tables, nc * tl * 8, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(d_dsc.p, d_scalars, nt * nc * DEB_NSCAL * 8, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(d_dtb.p, d_tables, nt * nc * tl * 8, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(d_k.p, kmodes, nkm * 8, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(d_a.p, aexp_out, nout * 8, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(d_rt.p, rp_tnext, total * (size_t)rp_stride * 8, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(d_rdt.p, rp_dtnext, nt * total * (size_t)rp_stride * 8, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(d_rk.p, rp_keep, total * (size_t)rp_stride * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(d_rn.p, rp_n, total * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemset(d_y.p, 0, total * nout * nf * 8));
+  CUDA_TRY(cudaMemset(d_dy.p, 0, nt * total * nout * nf * 8));
+  P.scalars = d_sc.as<double>(); P.tables = d_tb.as<double>(); P.d_scalars = d_dsc.as<double>(); P.d_tables = d_dtb.as<double>();
+  P.kmodes = d_k.as<double>(); P.aexp_out = d_a.as<double>(); P.tau_out = d_tau.as<double>(); P.dtau_out = d_dtau.as<double>();
+  P.status = d_st.as<int>(); P.nsteps = d_ns.as<int>(); P.naccept = nullptr; P.ticket = (unsigned int*)d_ws.p; P.mode = 3;
+  P.y_out = d_y.as<double>(); P.dy_out = d_dy.as<double>(); P.power_idx = -1;
+  double* lt_small = (double*)((char*)d_ws.p + 256);
+  P.lt_small = lt_small;
+  P.rp_tnext = d_rt.as<double>(); P.rp_dtnext = d_rdt.as<double>(); P.rp_keep = d_rk.as<int>(); P.rp_n = d_rn.as<int>();
+  P.rp_stride = rp_stride;
+  {
+    int ntq = P.ncosmo * P.nout;
+    k_tau_out<<<(ntq + 127) / 128, 128>>>(P, d_tau.as<double>(), lt_small);
+    CUDA_TRY(cudaGetLastError());
+  }
+  rc = launch_evolve(P, 0);
+  if (rc) return rc;
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy(y_out, d_y.p, total * nout * nf * 8, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(dy_out, d_dy.p, nt * total * nout * nf * 8, cudaMemcpyDeviceToHost));
+  if (dtau_out) CUDA_TRY(cudaMemcpy(dtau_out, d_dtau.p, nt * nc * nout * 8, cudaMemcpyDeviceToHost));
+  if (nsteps) CUDA_TRY(cudaMemcpy(nsteps, d_ns.p, total * 4, cudaMemcpyDeviceToHost));
+  return DEB_OK;
 }
 
 // ---- FP64 FMA peak probe (roofline denominator) ---------------------------------------------

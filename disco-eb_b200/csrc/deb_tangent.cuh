@@ -1,0 +1,487 @@
+// deb_tangent.cuh -- forward-mode tangents of the per-mode integrator.
+//
+// What jax.jvp / jax.jacfwd of the reference's evolve_perturbations computes is the exact derivative of the
+// DISCRETE solve: tangents flow through the start time, the initial conditions, every Rosenbrock stage
+// including W = I/(gamma dt) - J (ode_integrators_stiff.py:772-779 carry no stop_gradient), the step end
+// points, the SaveAt interpolation weights and the output conversion, while accept/reject, the PID factor,
+// spline intervals and bisection branches are decided on primal values.  Differentiating stage i,
+//     W k_i = r_i ,   r_i = f(t_i, u_i) + dt d_i dT + sum_j C_ij/dt k_j ,
+// along one direction (dot = d/d eps) gives a linear system with the SAME matrix:
+//     W kdot_i = rdot_i + ddt/(gamma dt^2) k_i + Jdot k_i .
+// The right-hand side f is linear in every state variable except the scale factor a = y[0],
+//     f = A(a, t; theta) y~ + b(a; theta) e_0 ,          J k = A k~ + (df/da) k_0 ,
+// so   Jdot k_i = Adot_0 k~_i + (d/d eps df/da) k_{i,0}   needs
+//   * Adot_0 k~_i : the same row code evaluated on first-order duals with the state held constant (per stage);
+//   * d/d eps df/da : the row code evaluated once per step on second-order duals (eps x delta_a).
+// Hence a tangent costs 8 extra structured solves with the primal factorisation + 17 dual row evaluations per
+// step, and nothing is ever refactored.  The row code below is a plain, generic (templated on the scalar type)
+// statement of perturbations.py:84-371; the primal path keeps its own tuned table-driven version.
+#pragma once
+
+namespace deb {
+
+// ---- nested forward duals -------------------------------------------------------------------------
+template <class S> struct DualOf { S v, d; };
+typedef DualOf<Dual> HD;              // v = (value, d/d eps), d = (d/da, d2/(da d eps))
+
+template <class S> DEB_DEV DualOf<S> mkd(S v, S d) { DualOf<S> r; r.v = v; r.d = d; return r; }
+template <class S> DEB_DEV DualOf<S> operator+(DualOf<S> a, DualOf<S> b) { return mkd<S>(a.v + b.v, a.d + b.d); }
+template <class S> DEB_DEV DualOf<S> operator-(DualOf<S> a, DualOf<S> b) { return mkd<S>(a.v - b.v, a.d - b.d); }
+template <class S> DEB_DEV DualOf<S> operator*(DualOf<S> a, DualOf<S> b) { return mkd<S>(a.v * b.v, a.d * b.v + a.v * b.d); }
+template <class S> DEB_DEV DualOf<S> operator/(DualOf<S> a, DualOf<S> b) { S q = a.v / b.v; return mkd<S>(q, (a.d - q * b.d) / b.v); }
+template <class S> DEB_DEV DualOf<S> operator+(DualOf<S> a, double b) { return mkd<S>(a.v + b, a.d); }
+template <class S> DEB_DEV DualOf<S> operator+(double b, DualOf<S> a) { return mkd<S>(a.v + b, a.d); }
+template <class S> DEB_DEV DualOf<S> operator-(DualOf<S> a, double b) { return mkd<S>(a.v - b, a.d); }
+template <class S> DEB_DEV DualOf<S> operator-(double b, DualOf<S> a) { return mkd<S>(b - a.v, -a.d); }
+template <class S> DEB_DEV DualOf<S> operator-(DualOf<S> a) { return mkd<S>(-a.v, -a.d); }
+template <class S> DEB_DEV DualOf<S> operator*(DualOf<S> a, double b) { return mkd<S>(a.v * b, a.d * b); }
+template <class S> DEB_DEV DualOf<S> operator*(double b, DualOf<S> a) { return mkd<S>(a.v * b, a.d * b); }
+template <class S> DEB_DEV DualOf<S> operator/(DualOf<S> a, double b) { return mkd<S>(a.v / b, a.d / b); }
+template <class S> DEB_DEV DualOf<S> operator/(double b, DualOf<S> a) { S q = b / a.v; return mkd<S>(q, -(q * a.d) / a.v); }
+template <class S> DEB_DEV DualOf<S> dsqrt(DualOf<S> a) { S s = dsqrt(a.v); return mkd<S>(s, (0.5 * a.d) / s); }
+template <class S> DEB_DEV DualOf<S> dexp(DualOf<S> a) { S e = dexp(a.v); return mkd<S>(e, e * a.d); }
+template <class S> DEB_DEV DualOf<S> dlog(DualOf<S> a) { return mkd<S>(dlog(a.v), a.d / a.v); }
+template <class S> DEB_DEV DualOf<S> drsqrt(DualOf<S> a) { S r = drsqrt(a.v); return mkd<S>(r, (-0.5 * r) * a.d / a.v); }
+template <class S> DEB_DEV double val(DualOf<S> a) { return val(a.v); }
+
+// (value, eps-part) -> T
+template <class T> DEB_DEV T lift2(double v, double d);
+template <> DEB_DEV Dual lift2<Dual>(double v, double d) { return mk(v, d); }
+template <> DEB_DEV HD lift2<HD>(double v, double d) { return mkd<Dual>(mk(v, d), mk(0.0, 0.0)); }
+template <class T> DEB_DEV T liftD(Dual x) { return lift2<T>(x.v, x.d); }
+DEB_DEV double eps_part(Dual x) { return x.d; }
+DEB_DEV double eps_part(HD x) { return x.v.d; }
+
+// ---- cosmology scalars and tables with their tangents ------------------------------------------------
+struct SplT { Spl p, t; };            // primal arrays and tangent arrays (same layout)
+struct CosmoD {                       // one direction: every scalar as (value, d/d eps)
+  Dual Omegam, Omegab, OmegaDE, Omegak, grhom, grhog, grhor, Neff, Nmnu, amnu, w0, wa, cs2de, YHe, H0, taumin, As, ns, kp;
+  SplT cs2a, xe, lrn, lpn, a_of_tau, xe_of_tau, tau_of_a;
+};
+DEB_DEV Spl get_spline_from(const double* tables, const Problem& P, int slot, int which) {
+  size_t tl = 3 * (size_t)(5 * P.nth + 2 * P.nnu);
+  const double* base = tables + (size_t)slot * tl;
+  size_t off = 0;
+  for (int s = 0; s < which; ++s) off += 3 * (size_t)((s == T_LRHONU || s == T_LPNU) ? P.nnu : P.nth);
+  int n = (which == T_LRHONU || which == T_LPNU) ? P.nnu : P.nth;
+  Spl r; r.x = base + off; r.y = r.x + n; r.S = r.y + n; r.n = n;
+  return r;
+}
+DEB_DEV CosmoD load_cosmo_d(const Problem& P, int c, int tan) {
+  const double* s = P.scalars + (size_t)c * NSCAL;
+  const size_t slot = (size_t)tan * P.ncosmo + c;
+  const double* d = P.d_scalars + slot * NSCAL;
+  CosmoD o;
+#define DEB_LD(field, idx) o.field = mk(DEB_LDG(s + idx), DEB_LDG(d + idx))
+  DEB_LD(Omegam, S_OMEGAM); DEB_LD(Omegab, S_OMEGAB); DEB_LD(OmegaDE, S_OMEGADE); DEB_LD(Omegak, S_OMEGAK);
+  DEB_LD(grhom, S_GRHOM); DEB_LD(grhog, S_GRHOG); DEB_LD(grhor, S_GRHOR); DEB_LD(Neff, S_NEFF); DEB_LD(Nmnu, S_NMNU);
+  DEB_LD(amnu, S_AMNU); DEB_LD(w0, S_W0); DEB_LD(wa, S_WA); DEB_LD(cs2de, S_CS2DE); DEB_LD(YHe, S_YHE); DEB_LD(H0, S_H0);
+  DEB_LD(taumin, S_TAUMIN); DEB_LD(As, S_AS); DEB_LD(ns, S_NS); DEB_LD(kp, S_KP);
+#undef DEB_LD
+  SplT* sp[NSPLINE] = {&o.cs2a, &o.xe, &o.lrn, &o.lpn, &o.a_of_tau, &o.xe_of_tau, &o.tau_of_a};
+  for (int w = 0; w < NSPLINE; ++w) { sp[w]->p = get_spline(P, c, w); sp[w]->t = get_spline_from(P.d_tables, P, (int)slot, w); }
+  return o;
+}
+
+// spline value with tangents in the knots, the values, the second derivatives and the abscissa
+// (spline_interpolation.py:130-153; the interval comes from primal values)
+template <class T>
+DEB_DEV T spl_eval_g(const SplT& s, T xn) {
+  const int i = spl_locate(s.p.x, s.p.n, val(xn), -1);
+  const T x0 = lift2<T>(DEB_LDG(s.p.x + i), DEB_LDG(s.t.x + i)), x1 = lift2<T>(DEB_LDG(s.p.x + i + 1), DEB_LDG(s.t.x + i + 1));
+  const T y0 = lift2<T>(DEB_LDG(s.p.y + i), DEB_LDG(s.t.y + i)), y1 = lift2<T>(DEB_LDG(s.p.y + i + 1), DEB_LDG(s.t.y + i + 1));
+  const T S0 = lift2<T>(DEB_LDG(s.p.S + i), DEB_LDG(s.t.S + i)), S1 = lift2<T>(DEB_LDG(s.p.S + i + 1), DEB_LDG(s.t.S + i + 1));
+  const T h = x1 - x0;
+  const T t = (xn - x0) / h;
+  const T A = 1.0 - t, B = t;
+  return A * y0 + B * y1 + ((A * A * A - A) * S0 + (B * B * B - B) * S1) * (h * h) / 6.0;
+}
+
+// ---- background coefficients (perturbations.py:176-218, background.py:110-121), generic --------------
+template <class T> struct BgG {
+  T a, H, opac, k2cs2, pbo, wq1, wq, ca2, gc, gb, gg, gr, gnu, gq;
+  T kv[NQMAX], vv[NQMAX];            // k v_i and v_i
+};
+template <class T>
+DEB_DEV void compute_bg_g(const CosmoD& c, const NuBins& nb, int nq, T a, double k, BgG<T>& b) {
+  const T loga = dlog(a);
+  const T inva = 1.0 / a, inva2 = inva * inva;
+  const T grhom = liftD<T>(c.grhom), grhog = liftD<T>(c.grhog), grhor = liftD<T>(c.grhor);
+  const T Omegab = liftD<T>(c.Omegab), Omegam = liftD<T>(c.Omegam), wa = liftD<T>(c.wa), w0 = liftD<T>(c.w0);
+  const T Neff = liftD<T>(c.Neff), Nmnu = liftD<T>(c.Nmnu);
+  b.a = a;
+  const T cs2 = spl_eval_g<T>(c.cs2a, loga) * inva;
+  b.k2cs2 = (k * k) * cs2;
+  const T xe = spl_eval_g<T>(c.xe, loga);
+  const T rhonu = dexp(spl_eval_g<T>(c.lrn, loga));
+  const T rhoq = dexp((-3.0 * (1.0 + w0 + wa)) * loga + 3.0 * wa * (a - 1.0));
+  b.wq = w0 + wa * (1.0 - a);
+  b.wq1 = 1.0 + b.wq;
+  b.gc = (grhom * (Omegam - Omegab)) * inva;
+  b.gb = (grhom * Omegab) * inva;
+  b.gg = grhog * inva2;
+  b.gr = (grhor * Neff) * inva2;
+  b.gnu = (grhor * Nmnu) * inva2;
+  b.gq = (grhom * liftD<T>(c.OmegaDE)) * rhoq * (a * a);
+  const T grho = (grhom * Omegam) * inva + (grhog + grhor * (Neff + Nmnu * rhonu)) * inva2 + b.gq + grhom * liftD<T>(c.Omegak);
+  b.H = dsqrt(grho * (1.0 / 3.0));
+  b.ca2 = b.wq + (wa * a) / (3.0 * (b.wq1 + 1e-6));
+  const T H0 = liftD<T>(c.H0);
+  const T akthom = (AKTHOM_RHS * (1.0 - liftD<T>(c.YHe))) * Omegab * H0 * H0;
+  b.opac = xe * akthom * inva2;
+  b.pbo = ((4.0 / 3.0) * grhog / (grhom * Omegab)) * inva * b.opac;
+  const T amnu = liftD<T>(c.amnu);
+  for (int i = 0; i < nq; ++i) {
+    const T aq = a * (amnu / nb.q[i]);
+    b.vv[i] = drsqrt(1.0 + aq * aq);
+    b.kv[i] = b.vv[i] * k;
+  }
+}
+
+// state accessors: u[e] as T
+struct StateVD { const double* v; const double* d; };        // (value, eps-part) from two vectors
+struct StateV0 { const double* v; };                          // constant state (eps-part zero)
+template <class T> DEB_DEV T sget(const StateVD& s, int e) { return lift2<T>(s.v[e], s.d[e]); }
+template <class T> DEB_DEV T sget(const StateV0& s, int e) { return lift2<T>(s.v[e], 0.0); }
+
+// metric sources (perturbations.py:229-261), generic
+template <class T> struct MetricG { T hp, ep, al, f1; };
+template <class T, class St>
+DEB_DEV void compute_metric_g(const Problem& P, const CosmoD& c, const NuBins& nb, const BgG<T>& b, const St& u, double k, MetricG<T>& mt) {
+  const int nq = P.nq, iq0 = P.iq0, n = P.n;
+  const T eta = sget<T>(u, 2), dc = sget<T>(u, 3), tc = sget<T>(u, 4), db = sget<T>(u, 5), tb = sget<T>(u, 6);
+  const T dg = sget<T>(u, 7), tg = sget<T>(u, 8), dr = sget<T>(u, P.ir), tr = sget<T>(u, P.ir + 1);
+  const T dq = sget<T>(u, n - 2), tq = sget<T>(u, n - 1);
+  T drhonu = 0.0 * b.a, dpnu3 = 0.0 * b.a, fnu = 0.0 * b.a;
+  for (int i = 0; i < nq; ++i) {
+    const T p0 = nb.w[i] * sget<T>(u, iq0 + i);
+    drhonu = drhonu + p0 / b.vv[i];
+    dpnu3 = dpnu3 + p0 * b.vv[i];
+    fnu = fnu + nb.w[i] * sget<T>(u, iq0 + nq + i);
+  }
+  const double k2 = k * k, ik2 = 1.0 / k2;
+  const T cs2de = liftD<T>(c.cs2de);
+  const T rpt = b.wq1 * b.gq * tq;
+  const T dgrho = b.gc * dc + b.gb * db + b.gg * dg + b.gr * dr + b.gnu * drhonu + b.gq * dq;
+  const T dgpres3 = (b.gg * dg + b.gr * dr) + b.gnu * dpnu3 + 3.0 * (cs2de * (b.gq * dq)) + (cs2de - b.ca2) * ((9.0 * ik2) * (b.H * rpt));
+  const T dgtheta = b.gc * tc + b.gb * tb + (4.0 / 3.0) * (b.gg * tg + b.gr * tr) + b.gnu * (k * fnu) + rpt;
+  mt.f1 = -(dgrho + dgpres3) * b.a;
+  mt.hp = ((2.0 * k2) * eta + dgrho) / b.H;
+  mt.ep = (0.5 * ik2) * dgtheta;
+  mt.al = (mt.hp + 6.0 * mt.ep) * (0.5 * ik2);
+}
+
+// row e of f (perturbations.py:226-369).  `lin`: drop the one term that does not multiply a state variable
+// (row 0 = H a), which turns the routine into the linear operator A(a, t; theta) applied to the state.
+template <class T, class St>
+DEB_DEV T row_g(const Problem& P, const CtaConst& C, const CosmoD& c, const BgG<T>& b, const MetricG<T>& mt, const St& u,
+                int e, int desc, T invtau, double k, bool lin) {
+  const int type = desc & 0xff, l = (desc >> 8) & 0xff, chain = desc >> 16;
+  const int ig = P.ig, igp = P.igp, ir = P.ir, n = P.n, nq = P.nq;
+  const double k2 = k * k;
+  switch (type) {
+    case R_A: return lin ? 0.0 * b.a : b.H * b.a;
+    case R_AHP: return mt.f1;
+    case R_ETA: return mt.ep;
+    case R_DC: return -sget<T>(u, 4) - 0.5 * mt.hp;
+    case R_TC: return -(b.H * sget<T>(u, 4));
+    case R_DB: return -sget<T>(u, 6) - 0.5 * mt.hp;
+    case R_TB: return -(b.H * sget<T>(u, 6)) + b.k2cs2 * sget<T>(u, 5) + b.pbo * (sget<T>(u, 8) - sget<T>(u, 6));
+    case R_F0: return (4.0 / 3.0) * (-sget<T>(u, ig + 1) - 0.5 * mt.hp);
+    case R_F1: return k2 * (0.25 * sget<T>(u, ig) - 0.5 * sget<T>(u, ig + 2)) - b.opac * (sget<T>(u, ig + 1) - sget<T>(u, 6));
+    case R_F2: {
+      const T polter = sget<T>(u, ig + 2) + sget<T>(u, igp) + sget<T>(u, igp + 2);
+      return (8.0 / 15.0) * (sget<T>(u, ig + 1) + k2 * mt.al) - (0.6 * k) * sget<T>(u, ig + 3) - b.opac * (sget<T>(u, ig + 2) - 0.1 * polter);
+    }
+    case R_G0: {
+      const T polter = sget<T>(u, ig + 2) + sget<T>(u, igp) + sget<T>(u, igp + 2);
+      return -(k * sget<T>(u, igp + 1)) - b.opac * sget<T>(u, igp) + b.opac * (0.5 * polter);
+    }
+    case R_G1: return (k / 3.0) * (sget<T>(u, igp) - 2.0 * sget<T>(u, igp + 2)) - b.opac * sget<T>(u, igp + 1);
+    case R_G2: {
+      const T polter = sget<T>(u, ig + 2) + sget<T>(u, igp) + sget<T>(u, igp + 2);
+      return (k / 5.0) * (2.0 * sget<T>(u, igp + 1) - 3.0 * sget<T>(u, igp + 3)) - b.opac * sget<T>(u, igp + 2) + b.opac * (0.1 * polter);
+    }
+    case R_N0: return (4.0 / 3.0) * (-sget<T>(u, ir + 1) - 0.5 * mt.hp);
+    case R_N1: return k2 * (0.25 * sget<T>(u, ir) - 0.5 * sget<T>(u, ir + 2));
+    case R_N2: return (8.0 / 15.0) * (sget<T>(u, ir + 1) + k2 * mt.al) - (0.6 * k) * sget<T>(u, ir + 3);
+    case R_P0: { const int i = chain - 3; return -(b.kv[i] * sget<T>(u, e + nq)) + mt.hp * (C.nu.dl[i] / 6.0); }
+    case R_P1: { const int i = chain - 3; return b.kv[i] * ((sget<T>(u, e - nq) - 2.0 * sget<T>(u, e + nq)) / 3.0); }
+    case R_P2: {
+      const int i = chain - 3;
+      return b.kv[i] * ((2.0 * sget<T>(u, e - nq) - 3.0 * sget<T>(u, e + nq)) / 5.0) - (mt.hp / 15.0 + 0.4 * mt.ep) * C.nu.dl[i];
+    }
+    case R_GEN: case R_TRUNC: {
+      const int s = C.ch_stride[chain], L = C.ch_lmax[chain];
+      const T kc = chain >= 3 ? b.kv[chain - 3] : 0.0 * b.a + k;
+      const T kap = chain < 2 ? b.opac : 0.0 * b.a;
+      if (type == R_GEN) return kc * ((C.cl[l] * sget<T>(u, e - s)) - C.ch[l] * sget<T>(u, e + s)) - kap * sget<T>(u, e);
+      return kc * sget<T>(u, e - s) - ((double)(L + 1) * invtau + kap) * sget<T>(u, e);
+    }
+    case R_DQ: {
+      const T cs2de = liftD<T>(c.cs2de);
+      return -(b.wq1 * (sget<T>(u, n - 1) + 0.5 * mt.hp)) - 3.0 * ((cs2de - b.wq) * b.H) * sget<T>(u, n - 2)
+             - (9.0 / k2) * (b.wq1 * (cs2de - b.ca2) * (b.H * b.H)) * sget<T>(u, n - 1);
+    }
+    case R_TQ: {
+      const T cs2de = liftD<T>(c.cs2de);
+      return -((1.0 - 3.0 * cs2de) * b.H) * sget<T>(u, n - 1) + ((cs2de * k2) / b.wq1) * sget<T>(u, n - 2);
+    }
+    default: return 0.0 * b.a;
+  }
+}
+
+// ---- prologue with tangents: start time (perturbations.py:630-681) and adiabatic ICs (:526-627) ------------
+DEB_DEV Dual aprimeoa_d(const CosmoD& c, Dual a) {
+  const Dual loga = dlog(a);
+  const Dual rhonu = dexp(spl_eval_g<Dual>(c.lrn, loga));
+  const Dual rhoq = dexp((-3.0 * (1.0 + c.w0 + c.wa)) * loga + 3.0 * c.wa * (a - 1.0));
+  const Dual grho = c.grhom * c.Omegam / a + (c.grhog + c.grhor * (c.Neff + c.Nmnu * rhonu)) / (a * a)
+                  + c.grhom * c.OmegaDE * rhoq * (a * a) + c.grhom * c.Omegak;
+  return dsqrt(grho / 3.0);
+}
+DEB_DEV Dual cond_small_k_d(const CosmoD& c, Dual lt) {
+  const Dual tau = dexp(lt);
+  const Dual akthom = (AKTHOM_START * (1.0 - c.YHe)) * c.Omegab * c.H0 * c.H0;
+  const Dual xe = spl_eval_g<Dual>(c.xe_of_tau, tau);
+  const Dual a = spl_eval_g<Dual>(c.a_of_tau, tau);
+  const Dual opac = xe * akthom / (a * a);
+  const Dual H = aprimeoa_d(c, a);
+  return (1.0 / opac) / (1.0 / H) / 0.0004 - 1.0;
+}
+DEB_DEV Dual cond_large_k_d(const CosmoD& c, Dual lt, double k) {
+  const Dual a = spl_eval_g<Dual>(c.a_of_tau, dexp(lt));
+  return (1.0 / aprimeoa_d(c, a)) / (1.0 / k) / 0.07 - 1.0;
+}
+// bisection of util.py:365-396: the branches are decided on primal values, the end points carry tangents
+DEB_DEV Dual start_time_d(const CosmoD& c, double k) {
+  Dual res[2];
+  for (int which = 0; which < 2; ++which) {
+    Dual xl = dlog(c.taumin), xr = dlog(spl_eval_g<Dual>(c.tau_of_a, mk(0.1, 0.0)));
+    double fl = which == 0 ? cond_small_k_d(c, xl).v : cond_large_k_d(c, xl, k).v;
+    for (int it = 0; it < 7; ++it) {
+      const Dual xm = 0.5 * (xl + xr);
+      const double fm = which == 0 ? cond_small_k_d(c, xm).v : cond_large_k_d(c, xm, k).v;
+      if (fm * fl > 0) { xl = xm; fl = fm; } else xr = xm;
+    }
+    res[which] = 0.5 * (xl + xr);
+  }
+  return dexp(res[0].v <= res[1].v ? res[0] : res[1]);
+}
+
+struct IcScalarsD { Dual a, deltag, thetag, deltar, thetar, shearr, deltaq, thetaq, eta; };
+DEB_DEV IcScalarsD ic_scalars_d(const CosmoD& c, Dual tau, double k) {
+  IcScalarsD s;
+  const Dual a = spl_eval_g<Dual>(c.a_of_tau, tau);
+  const Dual rn = dexp(spl_eval_g<Dual>(c.lrn, dlog(a)));
+  const Dual a2 = a * a, a4 = a2 * a2;
+  const Dual rhom = c.grhom * c.Omegam / (a2 * a);
+  const Dual rhor = (c.grhog + c.grhor * (c.Neff + c.Nmnu * rn)) / a4;
+  const Dual rhonu = c.grhor * (c.Neff + c.Nmnu * rn) / a4;
+  const Dual fracb = c.Omegab / c.Omegam, fracnu = rhonu / rhor;
+  const Dual om = a * rhom / dsqrt(rhor);
+  const double ci = -1.0;
+  const Dual kt = k * tau, kt2 = kt * kt;
+  s.a = a;
+  s.deltag = -kt2 / 3.0 * (1.0 - om * tau / 5.0) * ci;
+  s.thetag = -(kt2 * kt) / tau / 36.0 * (1.0 - 3.0 * (1.0 + 5.0 * fracb - fracnu) / 20.0 / (1.0 - fracnu) * om * tau) * ci;
+  s.deltar = s.deltag;
+  s.thetar = -(kt2 * kt2) / tau / 36.0 / (4.0 * fracnu + 15.0)
+           * (4.0 * fracnu + 11.0 + 12.0 - 3.0 * (8.0 * fracnu * fracnu + 50.0 * fracnu + 275.0) / 20.0 / (2.0 * fracnu + 15.0) * tau * om) * ci;
+  s.shearr = kt2 / (45.0 + 12.0 * fracnu) * 2.0 * (1.0 + (4.0 * fracnu - 5.0) / 4.0 / (2.0 * fracnu + 15.0) * tau * om) * ci;
+  const Dual wq = c.w0 + c.wa * (1.0 - a);
+  s.deltaq = kt2 / 4.0 * (1.0 + wq) * (4.0 - 3.0 * c.cs2de) / (4.0 - 6.0 * wq + 3.0 * c.cs2de) * ci;
+  s.thetaq = (kt2 * kt2) / tau / 4.0 * c.cs2de / (4.0 - 6.0 * wq + 3.0 * c.cs2de) * ci;
+  s.eta = ci * (1.0 - kt2 / 12.0 / (15.0 + 4.0 * fracnu)
+                * (5.0 + 4.0 * fracnu - (16.0 * fracnu * fracnu + 280.0 * fracnu + 325.0) / 10.0 / (2.0 * fracnu + 15.0) * tau * om));
+  return s;
+}
+DEB_DEV Dual ic_value_d(const Problem& P, const CosmoD& c, const NuBins& nb, const IcScalarsD& s, int desc, double k) {
+  const int type = desc & 0xff, chain = desc >> 16;
+  switch (type) {
+    case R_A: return s.a;
+    case R_ETA: return s.eta;
+    case R_DC: case R_DB: return 0.75 * s.deltag;
+    case R_TB: case R_F1: return s.thetag;
+    case R_F0: return s.deltag;
+    case R_N0: return s.deltar;
+    case R_N1: return s.thetar;
+    case R_N2: return s.shearr * 2.0;
+    case R_DQ: return s.deltaq;
+    case R_TQ: return s.thetaq;
+    case R_P0: case R_P1: case R_P2: {
+      const int i = chain - 3;
+      const Dual aq = s.a * c.amnu / nb.q[i];
+      const Dual v = 1.0 / dsqrt(1.0 + aq * aq);
+      const double dl = nb.dl[i];
+      if (type == R_P0) return (-0.25 * dl) * s.deltar;
+      if (type == R_P1) return (-dl) * s.thetar / v / k / 3.0;
+      return (-0.5 * dl) * s.shearr;
+    }
+    default: return mk(0.0, 0.0);
+  }
+}
+
+// ---- epilogue with tangents: 20 output fields (perturbations.py:374-523) and get_power (:1101-1123) ------
+DEB_DEV void convert_outputs_d(const Problem& P, const CosmoD& c, const NuBins& nb, const StateVD& y, double k, Dual* out) {
+  const int nq = P.nq, iq0 = P.iq0, n = P.n;
+  const Dual a = sget<Dual>(y, 0), eta = sget<Dual>(y, 2), dc = sget<Dual>(y, 3), tc = sget<Dual>(y, 4), db = sget<Dual>(y, 5);
+  const Dual tb = sget<Dual>(y, 6), dg = sget<Dual>(y, 7), tg = sget<Dual>(y, 8);
+  const Dual dr = sget<Dual>(y, P.ir), tr = sget<Dual>(y, P.ir + 1), dq = sget<Dual>(y, n - 2), tq = sget<Dual>(y, n - 1);
+  const Dual la = dlog(a);
+  const Dual rhonu = dexp(spl_eval_g<Dual>(c.lrn, la)), pnu = dexp(spl_eval_g<Dual>(c.lpn, la));
+  Dual drhonu = mk(0.0, 0.0), fnu = mk(0.0, 0.0);
+  for (int i = 0; i < nq; ++i) {
+    const Dual aq = a * c.amnu / nb.q[i];
+    const Dual v = 1.0 / dsqrt(1.0 + aq * aq);
+    drhonu = drhonu + nb.w[i] * sget<Dual>(y, iq0 + i) / v;
+    fnu = fnu + nb.w[i] * sget<Dual>(y, iq0 + nq + i);
+  }
+  const Dual deltanu = drhonu / rhonu, thetanu = k * fnu / (rhonu + pnu);
+  const Dual wq = c.w0 + c.wa * (1.0 - a);
+  const Dual rhoq = dexp((-3.0 * (1.0 + c.w0 + c.wa)) * la + 3.0 * (a - 1.0) * c.wa);
+  const Dual a2 = a * a;
+  const Dual Omegac = c.Omegam - c.Omegab;
+  const Dual rpt = (1.0 + wq) * rhoq * c.grhom * c.OmegaDE * tq * a2;
+  const Dual grho = c.grhom * c.Omegam / a + (c.grhog + c.grhor * (c.Neff + c.Nmnu * rhonu)) / a2
+                  + c.grhom * c.OmegaDE * rhoq * a2 + c.grhom * c.Omegak;
+  const Dual H = dsqrt(grho / 3.0);
+  const Dual mat = c.grhom * (Omegac * dc + c.Omegab * db) / a;
+  const Dual matth = c.grhom * (Omegac * tc + c.Omegab * tb) / a;
+  const Dual dgrho = mat + (c.grhog * dg + c.grhor * (c.Neff * dr + c.Nmnu * drhonu)) / a2 + c.grhom * c.OmegaDE * dq * rhoq * a2;
+  const Dual dgtheta = matth + 4.0 / 3.0 * (c.grhog * tg + c.Neff * c.grhor * tr) / a2 + c.Nmnu * c.grhor * k * fnu / a2 + rpt;
+  const double k2 = k * k;
+  const Dual hp = (2.0 * k2 * eta + dgrho) / H, ep = 0.5 * dgtheta / k2, al = (hp + 6.0 * ep) / 2.0 / k2;
+  const Dual deltam = (mat + (c.grhor * c.Nmnu * drhonu) / a2) / (c.grhom * c.Omegam / a + (c.grhor * c.Nmnu * rhonu) / a2);
+  Dual thetam = (matth + c.Nmnu * c.grhor * k * fnu / a2) / (3.0 * (c.grhom * c.Omegam / a + c.grhor * c.Nmnu * rhonu / a2));
+  const Dual deltabc = mat / (c.grhom * c.Omegam / a);
+  Dual thetabc = matth / (3.0 * (c.grhom * c.Omegam / a) / a2);
+  thetam = thetam + al * k2; thetabc = thetabc + al * k2;
+  out[0] = eta; out[1] = ep; out[2] = hp; out[3] = al;
+  out[4] = deltam; out[5] = thetam / H; out[6] = deltabc; out[7] = thetabc / H;
+  out[8] = dc; out[9] = tc / H; out[10] = db; out[11] = tb / H; out[12] = dg; out[13] = tg / H;
+  out[14] = dr; out[15] = tr / H; out[16] = deltanu; out[17] = thetanu / H; out[18] = dq; out[19] = tq / H;
+}
+DEB_DEV Dual power_d(const CosmoD& c, double k, Dual yv) {
+  const Dual tilt = dexp((c.ns - 1.0) * dlog(k / c.kp));
+  return (2.0 * 9.869604401089358) * c.As * tilt * pow(k, -3.0) * yv * yv;
+}
+
+// ---- per-mode tangent workspace (shared memory, carved after the primal workspace) ---------------------
+struct TanWs {
+  double* yd;     // tangent of the accepted state [np]
+  double* ud;     // tangent of the stage state [np]
+  double* rd;     // tangent right-hand side, solved in place -> kdot_i [np]
+  double* jad;    // d/d eps of d f/d a at (t0, y0) [np]
+  double* cc;     // primal sum_j C_ij/dt k_j of the current stage [np]
+  double* kd;     // kdot_1 .. kdot_7 [7 np]
+  CosmoD* cd;     // scalars and tables of this (cosmology, direction)
+};
+DEB_HD size_t tan_ws_doubles(int np) { return (size_t)12 * np + (sizeof(CosmoD) + 7) / 8; }
+DEB_DEV void carve_tan(TanWs& T, double* base, int np) {
+  T.yd = base; T.ud = T.yd + np; T.rd = T.ud + np; T.jad = T.rd + np; T.cc = T.jad + np; T.kd = T.cc + np;
+  T.cd = (CosmoD*)(T.kd + (size_t)7 * np);
+}
+
+// Everything of tangent stage `st` up to (not including) the linear solve: forms rdot_i in TW.rd.
+//   ys/yd  : accepted state and its tangent at (t, td)         us/ud : stage state u_i and its tangent
+//   ki     : k_i of the primal stage (W.r after the primal solve)
+template <class Dummy = void>
+DEB_DEV void tan_stage_rhs(const Problem& P, const CtaConst& C, const WarpWs& W, const TanWs& TW, int st, double k,
+                           double t, double td, double dt, double ddt DEB_LANE_PARAM) {
+  const int n = P.n, np = P.np;
+  const CosmoD& cd = *TW.cd;
+  const NuBins& nb = C.nu;
+  // ---- u_dot ----
+  DEB_LANES_BEGIN
+    for (int e = lane; e < n; e += 32) {
+      const double* k1 = TW.kd + e;
+      double v;
+      switch (st) {
+        case 1: v = TW.yd[e]; break;
+        case 2: v = TW.yd[e] + RD_A21 * k1[0]; break;
+        case 3: v = TW.yd[e] + RD_A31 * k1[0] + RD_A32 * k1[np]; break;
+        case 4: v = TW.yd[e] + RD_A41 * k1[0] + RD_A42 * k1[np] + RD_A43 * k1[2 * np]; break;
+        case 5: v = TW.yd[e] + RD_A51 * k1[0] + RD_A52 * k1[np] + RD_A53 * k1[2 * np] + RD_A54 * k1[3 * np]; break;
+        case 6: v = TW.yd[e] + RD_A61 * k1[0] + RD_A62 * k1[np] + RD_A63 * k1[2 * np] + RD_A64 * k1[3 * np] + RD_A65 * k1[4 * np]; break;
+        case 7: v = TW.ud[e] + k1[5 * np]; break;
+        default: v = TW.ud[e] + k1[6 * np]; break;
+      }
+      TW.ud[e] = v;
+    }
+  DEB_LANES_END
+  const double* us = st == 1 ? W.y() : W.u();
+  const double ci = st == 2 ? RD_CT2 : st == 3 ? RD_CT3 : st == 4 ? RD_CT4 : st == 5 ? RD_CT5 : (st == 1 ? 0.0 : 1.0);
+  const double di = st == 1 ? RD_D1 : st == 2 ? RD_D2 : st == 3 ? RD_D3 : st == 4 ? RD_D4 : st == 5 ? RD_D5 : 0.0;
+  const Dual tsD = mk(t + ci * dt, td + ci * ddt);
+  const Dual t0D = mk(t, td);
+  const Dual invts = 1.0 / tsD, invt0 = 1.0 / t0D;
+  const double invdt = 1.0 / dt;
+  const double wdiag = ddt / (RD_GAMMA * dt * dt);
+  const double* ki = W.r();
+  const double ki0 = ki[0];
+  // base-point coefficients with the state held constant: Adot_0 k~_i
+  BgG<Dual> b0;
+  compute_bg_g<Dual>(cd, nb, P.nq, mk(W.y()[0], TW.yd[0]), k, b0);
+  const StateV0 sk = {ki};
+  MetricG<Dual> m0;
+  compute_metric_g<Dual>(P, cd, nb, b0, sk, k, m0);
+  const StateVD su = {us, TW.ud};
+  if (st == 1) {
+    // second-order duals at (t0, y0): eps-part = fdot, (a x eps)-part = d/d eps of df/da
+    BgG<HD> bh;
+    compute_bg_g<HD>(cd, nb, P.nq, mkd<Dual>(mk(W.y()[0], TW.yd[0]), mk(1.0, 0.0)), k, bh);
+    MetricG<HD> mh;
+    compute_metric_g<HD>(P, cd, nb, bh, su, k, mh);
+    const HD invtH = liftD<HD>(invt0);
+    DEB_LANES_BEGIN
+      for (int e = lane; e < n; e += 32) {
+        const int desc = elem_desc(P, e);
+        const HD f = row_g<HD>(P, C, cd, bh, mh, su, e, desc, invtH, k, false);
+        const Dual g = row_g<Dual>(P, C, cd, b0, m0, sk, e, desc, invt0, k, true);
+        const double jd = f.d.d;
+        TW.jad[e] = jd;
+        double r = f.v.d + g.d + jd * ki0 + wdiag * ki[e];
+        if ((desc & 0xff) == R_TRUNC) {
+          const double tr = (double)(C.ch_lmax[desc >> 16] + 1);
+          const double it2 = 1.0 / (t * t);
+          r += di * (ddt * (tr * it2 * W.y()[e]) + dt * tr * (TW.yd[e] * it2 - 2.0 * W.y()[e] * td * it2 / t));
+        }
+        TW.rd[e] = r;
+      }
+    DEB_LANES_END
+    return;
+  }
+  BgG<Dual> bi;
+  compute_bg_g<Dual>(cd, nb, P.nq, mk(us[0], TW.ud[0]), k, bi);
+  MetricG<Dual> mi;
+  compute_metric_g<Dual>(P, cd, nb, bi, su, k, mi);
+  DEB_LANES_BEGIN
+    for (int e = lane; e < n; e += 32) {
+      const int desc = elem_desc(P, e);
+      const Dual f = row_g<Dual>(P, C, cd, bi, mi, su, e, desc, invts, k, false);
+      const Dual g = row_g<Dual>(P, C, cd, b0, m0, sk, e, desc, invt0, k, true);
+      double r = f.d + g.d + TW.jad[e] * ki0 + wdiag * ki[e];
+      if (st <= 5 && (desc & 0xff) == R_TRUNC) {
+        const double tr = (double)(C.ch_lmax[desc >> 16] + 1);
+        const double it2 = 1.0 / (t * t);
+        r += di * (ddt * (tr * it2 * W.y()[e]) + dt * tr * (TW.yd[e] * it2 - 2.0 * W.y()[e] * td * it2 / t));
+      }
+      const double* k1 = TW.kd + e;
+      double cs;
+      switch (st) {
+        case 2: cs = RD_C21 * k1[0]; break;
+        case 3: cs = RD_C31 * k1[0] + RD_C32 * k1[np]; break;
+        case 4: cs = RD_C41 * k1[0] + RD_C42 * k1[np] + RD_C43 * k1[2 * np]; break;
+        case 5: cs = RD_C51 * k1[0] + RD_C52 * k1[np] + RD_C53 * k1[2 * np] + RD_C54 * k1[3 * np]; break;
+        case 6: cs = RD_C61 * k1[0] + RD_C62 * k1[np] + RD_C63 * k1[2 * np] + RD_C64 * k1[3 * np] + RD_C65 * k1[4 * np]; break;
+        case 7: cs = RD_C71 * k1[0] + RD_C72 * k1[np] + RD_C73 * k1[2 * np] + RD_C74 * k1[3 * np] + RD_C75 * k1[4 * np] + RD_C76 * k1[5 * np]; break;
+        default: cs = RD_C81 * k1[0] + RD_C82 * k1[np] + RD_C83 * k1[2 * np] + RD_C84 * k1[3 * np] + RD_C85 * k1[4 * np] + RD_C86 * k1[5 * np] + RD_C87 * k1[6 * np]; break;
+      }
+      r += invdt * cs - (ddt * invdt) * TW.cc[e];
+      TW.rd[e] = r;
+    }
+  DEB_LANES_END
+}
+
+}  // namespace deb

@@ -68,3 +68,25 @@ def pack_params(params):
             raise ValueError("all cosmologies of a batch must use the same table sizes")
     return (np.ascontiguousarray(np.stack([p[0] for p in packed])),
             np.ascontiguousarray(np.stack([p[1] for p in packed])), nth, nnu)
+
+
+def pack_tangent(param, dparam):
+    """Tangent seed of one cosmology along one direction -> (d_scalars[NSCAL], d_tables[tl]) in the layout of
+    ``pack_param``.  ``dparam`` maps any subset of the scalar keys to floats and of the spline keys to objects
+    carrying the tangents of ``x, y, S`` (what ``jax.jvp`` holds for the ``param`` pytree); missing keys have
+    zero tangent."""
+    dscal = np.zeros(NSCAL, dtype=np.float64)
+    for i, key in enumerate(SCALAR_KEYS):
+        if key in dparam:
+            dscal[i] = float(dparam[key])
+    parts = []
+    for key in SPLINE_KEYS:
+        x, y, S = _spline_arrays(param[key])
+        if key in dparam:
+            dx, dy, dS = _spline_arrays(dparam[key])
+            if not (dx.shape == x.shape and dy.shape == y.shape and dS.shape == S.shape):
+                raise ValueError(f"dparam['{key}']: tangent arrays must have the shapes of the primal spline")
+            parts += [dx, dy, dS]
+        else:
+            parts += [np.zeros_like(x), np.zeros_like(y), np.zeros_like(S)]
+    return dscal, np.concatenate(parts)

@@ -21,9 +21,10 @@ from __future__ import annotations
 import numpy as np
 
 from . import _cabi
-from ._pack import pack_param, pack_params
+from ._pack import pack_param, pack_params, pack_tangent
 
-__all__ = ["evolve_perturbations", "evolve_perturbations_batched", "evolve_perturbations_multi", "get_power"]
+__all__ = ["evolve_perturbations", "evolve_perturbations_batched", "evolve_perturbations_multi", "evolve_perturbations_jvp",
+           "get_power"]
 
 
 class MaxStepsReached(RuntimeError):
@@ -136,6 +137,56 @@ def evolve_perturbations_multi(*, params, aexp_out, kmin: float, kmax: float, nu
                  power_idx=power_idx)
     _check_status(out["status"], out["nsteps"], max_steps, throw)
     return out["y"], kmodes, out
+
+
+def evolve_perturbations_jvp(*, param, dparam, aexp_out, kmin: float, kmax: float, num_k: int,
+                             lmaxg: int = 11, lmaxgp: int = 11, lmaxr: int = 11, lmaxnu: int = 8,
+                             nqmax: int = 3, rtol: float = 1e-4, atol: float = 1e-4,
+                             pcoeff: float = 0.25, icoeff: float = 0.80, dcoeff: float = 0.0,
+                             factormax: float = 20.0, factormin: float = 0.3, max_steps: int = 2048,
+                             return_full: bool = False, dologk: bool = True, device: int = 0, throw: bool = True,
+                             power_idx: int = -1):
+    """Forward-mode derivative of ``evolve_perturbations`` -- what ``jax.jvp(evolve_perturbations, (param,),
+    (dparam,))`` / ``jax.jacfwd`` returns in the reference (minimal notebook cell 14, Fisher notebook cell 7):
+    the exact tangent of the discrete solve, computed by the tangent kernel in the same launch.
+
+    ``dparam`` is one tangent of the ``param`` pytree (a dict with any subset of the scalar keys and of the spline
+    keys, each spline carrying the tangents of ``x, y, S``), or a sequence of such dicts (the columns of a
+    Jacobian).  Returns ``(y, dy, kmodes, info)``: ``dy`` has the shape of ``y`` (one dict) or a leading axis
+    over directions; ``info`` holds ``tau_out, dtau_out, status, nsteps, naccept, kernel_ms`` and, with
+    ``power_idx >= 0``, ``pk`` / ``dpk`` (``get_power`` and its tangent, A_s / n_s / k_p seeds included).
+    ``param`` receives the same side effects as in ``evolve_perturbations``."""
+    single = isinstance(dparam, dict)
+    dlist = [dparam] if single else list(dparam)
+    if not dlist:
+        raise ValueError("dparam must hold at least one direction")
+    lib = _cabi.default_library()
+    kmodes = _kgrid(kmin, kmax, num_k, dologk)
+    scalars, tables, nth, nnu = pack_params([param])
+    seeds = [pack_tangent(param, d) for d in dlist]
+    d_scalars = np.stack([s[0] for s in seeds])[:, None]
+    d_tables = np.stack([s[1] for s in seeds])[:, None]
+    aexp_out = np.atleast_1d(np.asarray(aexp_out, dtype=np.float64))
+    if aexp_out.ndim != 1 or aexp_out.size < 1 or np.any(np.diff(aexp_out) < 0):
+        raise ValueError("aexp_out must be a scalar or an ascending 1-d array")
+    dims = _cabi.make_dims(ncosmo=1, nk=num_k, nout=aexp_out.size, lmaxg=lmaxg, lmaxgp=lmaxgp, lmaxr=lmaxr, lmaxnu=lmaxnu,
+                           nqmax=nqmax, nth=nth, nnu=nnu, max_steps=max_steps, return_full=return_full, power_idx=power_idx,
+                           ntan=len(dlist))
+    ctrl = _cabi.make_ctrl(rtol=rtol, atol=atol, pcoeff=pcoeff, icoeff=icoeff, dcoeff=dcoeff, factormax=factormax,
+                           factormin=factormin)
+    out = lib.evolve_tangent_host(dims, ctrl, scalars, tables, kmodes, aexp_out, d_scalars, d_tables, device=device,
+                                  want_pk=power_idx >= 0)
+    _check_status(out["status"], out["nsteps"], max_steps, throw)
+    param["lmaxg"], param["lmaxgp"], param["lmaxr"], param["lmaxnu"], param["nqmax"] = lmaxg, lmaxgp, lmaxr, lmaxnu, nqmax
+    param["nout"] = out["tau_out"].shape[1]
+    param["tau_out"] = out["tau_out"][0]
+    dy = out["dy"][:, 0]
+    info = dict(tau_out=out["tau_out"][0], dtau_out=out["dtau_out"][:, 0], status=out["status"][0], nsteps=out["nsteps"][0],
+                naccept=out["naccept"][0], kernel_ms=out["kernel_ms"])
+    if power_idx >= 0:
+        info["pk"] = out["pk"][0]
+        info["dpk"] = out["dpk"][0, 0] if single else out["dpk"][:, 0]
+    return out["y"][0], (dy[0] if single else dy), kmodes, info
 
 
 def get_power(*, k, y, idx: int, param):

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DEB_ABI_VERSION 1
+#define DEB_ABI_VERSION 2
 #define DEB_NSCAL 24        /* doubles per cosmology in `scalars` */
 #define DEB_NSPLINE 7       /* splines per cosmology in `tables`  */
 #define DEB_NFIELD 20       /* output fields (perturbations.py:511-521) */
@@ -52,7 +52,7 @@ typedef struct deb_dims {
   int32_t ncosmo;        /* cosmologies in the batch                                  */
   int32_t nk;            /* k-modes per cosmology                                     */
   int32_t nout;          /* output times (ascending aexp_out)                         */
-  int32_t ntan;          /* forward tangents (0 in this ABI version)                  */
+  int32_t ntan;          /* forward-tangent directions (0 for the primal entries)     */
   int32_t lmaxg, lmaxgp, lmaxr, lmaxnu;   /* hierarchy cut-offs, each >= 3            */
   int32_t nqmax;         /* massive-neutrino momentum bins (3,4,5)                    */
   int32_t nth, nnu;      /* knots of the thermo / neutrino splines                    */
@@ -103,6 +103,28 @@ int deb_evolve_f64(const deb_dims* dims, const deb_ctrl* ctrl,
                    int32_t* status, int32_t* nsteps, int32_t* naccept,
                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* Forward tangents (jax.jvp / jax.jacfwd of evolve_perturbations in the reference: the minimal
+ * notebook cell 14, the Fisher notebook cell 7).  For each of dims->ntan
+ * directions the caller supplies the tangent of every input, laid out like the primal input
+ * with a leading [ntan] axis:
+ *   d_scalars [ntan, ncosmo, DEB_NSCAL]      d_tables [ntan, ncosmo, deb_table_len]
+ * (x, y and S tangents of every spline; zero where an array does not depend on the parameter),
+ * and receives the exact derivative of the discrete solve -- tangents flow through the start
+ * time, the initial conditions, every Rosenbrock stage including W = I/(gamma dt) - J, the step
+ * end points, the output interpolation and conversion, while accept/reject, the PID factor,
+ * spline intervals and bisection branches follow the primal run (diffrax semantics):
+ *   dy_out   [ntan, ncosmo, nk, nout, 20|n]   dpk_out [ntan, ncosmo, nk, nout] or NULL
+ *   dtau_out [ntan, ncosmo, nout]             tangent of tau_of_a(aexp_out)
+ * The primal outputs are those of deb_evolve_f64 for the same step sequence.  kmodes and
+ * aexp_out carry no tangent.  With ntan == 0 this is deb_evolve_f64. */
+int deb_evolve_tangent_f64(const deb_dims* dims, const deb_ctrl* ctrl,
+                           const double* scalars, const double* tables, const double* kmodes,
+                           const double* aexp_out, const double* d_scalars, const double* d_tables,
+                           double* y_out, double* dy_out, double* pk_out, double* dpk_out,
+                           double* tau_out, double* dtau_out,
+                           int32_t* status, int32_t* nsteps, int32_t* naccept,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
 /* Host-pointer entry: same arguments with HOST buffers; copies inputs to device `device`,
  * runs deb_evolve_f64, copies results back and synchronises.  If kernel_ms is non-NULL it
  * receives the device time of the solve kernel alone (CUDA events). */
@@ -128,6 +150,20 @@ int deb_ctx_evolve_host_f64(deb_ctx* ctx, const deb_dims* dims, const deb_ctrl* 
                             double* y_out, double* pk_out, double* tau_out,
                             int32_t* status, int32_t* nsteps, int32_t* naccept, float* kernel_ms);
 void deb_host_cache_release(void);
+/* host-buffer forms of deb_evolve_tangent_f64 (explicit context / per-thread cached context) */
+int deb_ctx_evolve_tangent_host_f64(deb_ctx* ctx, const deb_dims* dims, const deb_ctrl* ctrl,
+                                    const double* scalars, const double* tables, const double* kmodes,
+                                    const double* aexp_out, const double* d_scalars, const double* d_tables,
+                                    double* y_out, double* dy_out, double* pk_out, double* dpk_out,
+                                    double* tau_out, double* dtau_out,
+                                    int32_t* status, int32_t* nsteps, int32_t* naccept, float* kernel_ms);
+int deb_evolve_tangent_host_f64(const deb_dims* dims, const deb_ctrl* ctrl,
+                                const double* scalars, const double* tables, const double* kmodes,
+                                const double* aexp_out, const double* d_scalars, const double* d_tables,
+                                double* y_out, double* dy_out, double* pk_out, double* dpk_out,
+                                double* tau_out, double* dtau_out,
+                                int32_t* status, int32_t* nsteps, int32_t* naccept,
+                                int32_t device, float* kernel_ms);
 
 /* Debug/validation entry (host pointers): ONE attempted Rodas5 step per mode from a given
  * state.  t0[nmodes], t1[nmodes], y0[nmodes, n] -> y1[nmodes, n], yerr[nmodes, n].
@@ -152,6 +188,16 @@ int deb_debug_replay_host_f64(const deb_dims* dims, const deb_ctrl* ctrl, const 
                               const double* tables, const double* kmodes, const double* aexp_out,
                               const double* rp_tnext, const int32_t* rp_keep, const int32_t* rp_n,
                               int32_t rp_stride, double* y_out, int32_t* nsteps, int32_t device);
+
+/* Debug/validation entry (host pointers): deb_debug_replay_host_f64 with tangents.  rp_dtnext
+ * [ntan, ncosmo*nk, rp_stride] holds the tangent of every prescribed step end. */
+int deb_debug_replay_tangent_host_f64(const deb_dims* dims, const deb_ctrl* ctrl, const double* scalars,
+                                      const double* tables, const double* kmodes, const double* aexp_out,
+                                      const double* d_scalars, const double* d_tables,
+                                      const double* rp_tnext, const double* rp_dtnext,
+                                      const int32_t* rp_keep, const int32_t* rp_n, int32_t rp_stride,
+                                      double* y_out, double* dy_out, double* dtau_out, int32_t* nsteps,
+                                      int32_t device);
 
 /* Measures the FP64 FMA peak of `device` (dependent-free DFMA streams on every SM) and
  * returns it in TFLOP/s; the roofline denominator bench.py reports against. */

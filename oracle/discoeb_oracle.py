@@ -583,8 +583,8 @@ def integrate_modes(t0, t1, y0, ts, p, k, d: Dims, rtol, atol, pcoeff=0.25, icoe
 
 def _bisect(func, xl, xr, numit):
     """util.py:365-396 (keeps [mid, right] when f(mid) f(left) > 0)."""
-    xl = np.array(xl, dtype=np.float64, copy=True)
-    xr = np.array(xr, dtype=np.float64, copy=True)
+    xl = np.array(xl, dtype=np.result_type(xl, np.float64), copy=True)      # (complex under the tangent oracle)
+    xr = np.array(xr, dtype=np.result_type(xr, np.float64), copy=True)
     for _ in range(numit):
         xm = 0.5 * (xl + xr)
         c = np.real(func(xm)) * np.real(func(xl)) > 0

@@ -14,15 +14,50 @@
 using namespace deb;
 
 static std::vector<double> g_lt_small;       // per call; the harness is single-caller
-static void tau_out_host(Problem& P, double* tau_out) {
+static void tau_out_host(Problem& P, double* tau_out, double* dtau_out = nullptr) {
   g_lt_small.assign(P.ncosmo, 0.0);
   for (int c = 0; c < P.ncosmo; ++c) {
     Spl s = get_spline(P, c, T_TAU_OF_A);
     if (P.aexp_out) for (int j = 0; j < P.nout; ++j) tau_out[(size_t)c * P.nout + j] = spl_eval(s, P.aexp_out[j]);
     Cosmo cs = load_cosmo(P, c);
     g_lt_small[c] = start_small_k(cs);
+    if (dtau_out && P.aexp_out)
+      for (int tn = 0; tn < P.ntan; ++tn) {
+        SplT st; st.p = s; st.t = get_spline_from(P.d_tables, P, tn * P.ncosmo + c, T_TAU_OF_A);
+        for (int j = 0; j < P.nout; ++j)
+          dtau_out[((size_t)tn * P.ncosmo + c) * P.nout + j] = spl_eval_g<Dual>(st, mk(P.aexp_out[j], 0.0)).d;
+      }
   }
   P.lt_small = g_lt_small.data();
+}
+
+// tangent path: one work item per (direction, cosmology, k)
+template <int NE>
+static void run_all_tan(const Problem& P) {
+  CtaConst C;
+  std::vector<int> tail(P.np);
+  for (int t = 0; t < 32; ++t) init_cta_const(P, C, tail.data(), t, 32);
+  std::vector<double> ws(warp_ws_doubles(P.np) + tan_ws_doubles(P.np));
+  const int modes = P.ncosmo * P.nk, total = modes * P.ntan;
+#pragma omp parallel for schedule(dynamic, 1) firstprivate(ws)
+  for (int it = 0; it < total; ++it) {
+    WarpWs W;
+    carve(W, ws.data(), P.np);
+    TanWs TW;
+    carve_tan(TW, ws.data() + warp_ws_doubles(P.np), P.np);
+    HelpBox box;
+    integrate_mode<NE, false, true>(P, C, W, &box, modes - 1 - it % modes, &TW, it / modes);
+  }
+}
+static int dispatch_tan(const Problem& P) {
+  int ne = (P.n + 31) / 32;
+  if (ne <= 3) run_all_tan<3>(P);
+  else if (ne <= 4) run_all_tan<4>(P);
+  else if (ne <= 6) run_all_tan<6>(P);
+  else if (ne <= 9) run_all_tan<9>(P);
+  else if (ne <= 12) run_all_tan<12>(P);
+  else return DEB_E_UNSUPPORTED;
+  return DEB_OK;
 }
 
 template <int NE, bool HELPER>
@@ -126,4 +161,45 @@ extern "C" int emu_debug_replay_host_f64(const deb_dims* dims, const deb_ctrl* c
   P.rp_tnext = rp_tnext; P.rp_keep = rp_keep; P.rp_n = rp_n; P.rp_stride = rp_stride;
   P.mode = 3;
   return dispatch(P);
+}
+
+extern "C" int emu_evolve_tangent_host_f64(const deb_dims* dims, const deb_ctrl* ctrl, const double* scalars,
+                                           const double* tables, const double* kmodes, const double* aexp_out,
+                                           const double* d_scalars, const double* d_tables, double* y_out, double* dy_out,
+                                           double* pk_out, double* dpk_out, double* tau_out, double* dtau_out,
+                                           int32_t* status, int32_t* nsteps, int32_t* naccept) {
+  Problem P;
+  int rc = fill_problem(dims, ctrl, &P);
+  if (rc) return rc;
+  if (P.ntan < 1) return DEB_E_ARG;
+  P.scalars = scalars; P.tables = tables; P.kmodes = kmodes; P.aexp_out = aexp_out; P.d_scalars = d_scalars; P.d_tables = d_tables;
+  P.y_out = y_out; P.dy_out = dy_out; P.pk_out = pk_out; P.dpk_out = dpk_out; P.status = status; P.nsteps = nsteps; P.naccept = naccept;
+  tau_out_host(P, tau_out, dtau_out);
+  P.tau_out = tau_out; P.dtau_out = dtau_out;
+  P.mode = 0;
+  return dispatch_tan(P);
+}
+
+extern "C" int emu_debug_replay_tangent_host_f64(const deb_dims* dims, const deb_ctrl* ctrl, const double* scalars,
+                                                 const double* tables, const double* kmodes, const double* aexp_out,
+                                                 const double* d_scalars, const double* d_tables, const double* rp_tnext,
+                                                 const double* rp_dtnext, const int32_t* rp_keep, const int32_t* rp_n,
+                                                 int32_t rp_stride, double* y_out, double* dy_out, double* dtau_out,
+                                                 int32_t* nsteps) {
+  Problem P;
+  int rc = fill_problem(dims, ctrl, &P);
+  if (rc) return rc;
+  if (P.ntan < 1) return DEB_E_ARG;
+  const int total = P.ncosmo * P.nk;
+  std::vector<double> tau_out((size_t)P.ncosmo * P.nout), dtau((size_t)P.ntan * P.ncosmo * P.nout);
+  std::vector<int32_t> st(total);
+  P.scalars = scalars; P.tables = tables; P.kmodes = kmodes; P.aexp_out = aexp_out; P.d_scalars = d_scalars; P.d_tables = d_tables;
+  tau_out_host(P, tau_out.data(), dtau.data());
+  P.tau_out = tau_out.data(); P.dtau_out = dtau.data();
+  P.status = st.data(); P.nsteps = nsteps; P.naccept = nullptr; P.y_out = y_out; P.dy_out = dy_out; P.power_idx = -1;
+  P.rp_tnext = rp_tnext; P.rp_dtnext = rp_dtnext; P.rp_keep = rp_keep; P.rp_n = rp_n; P.rp_stride = rp_stride;
+  P.mode = 3;
+  rc = dispatch_tan(P);
+  if (dtau_out) memcpy(dtau_out, dtau.data(), dtau.size() * sizeof(double));
+  return rc;
 }

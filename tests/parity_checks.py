@@ -96,3 +96,119 @@ def check_adaptive(lib, tables, name):
             assert helpers.field_scaled_diff(y[m], ref[m]).max() < 1e-5, (name, m)
         assert rel < 50 * rtol, (name, m, rel)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# forward tangents: kernel vs the complex-step oracle (tests/golden/tangent_*.npz,
+# tools/make_golden_tangent.py).  Bars: replay of the oracle's step sequence 1e-6 (north_star: 1e-5) of each
+# field's tangent scale; free-running, modes whose step counts equal the oracle's: 1e-5 for <= 100 steps.
+# ---------------------------------------------------------------------------------------------------
+TANGENT_CASES = ("default_n72", "w0wa_n43", "fisher_n265")
+
+
+def load_tangent_case(name):
+    import os
+    z = np.load(os.path.join(helpers.GOLD, f"tangent_{name}.npz"), allow_pickle=False)
+    return {k: z[k] for k in z.files}
+
+
+def tangent_dims(case, nk=None, **kw):
+    lg, lp, lr, ln, nq = (int(v) for v in case["dims"])
+    return _cabi.make_dims(ncosmo=1, nk=nk or len(case["kmodes"]), nout=len(case["aexp_out"]), lmaxg=lg, lmaxgp=lp, lmaxr=lr,
+                           lmaxnu=ln, nqmax=nq, nth=int(case["nth"]), nnu=int(case["nnu"]), max_steps=kw.pop("max_steps", 4096),
+                           ntan=kw.pop("ntan", case["d_scalars"].shape[0]), **kw)
+
+
+def tangent_scaled_diff(dy, dref, ref):
+    """max |dy - dref| per field relative to that field's tangent scale.  A field whose tangent is anomalously small
+    (theta_c = 0, the scale factor under a post-processing parameter) is measured against |field| x the typical
+    logarithmic derivative of the other fields instead."""
+    ax = tuple(range(ref.ndim - 1))
+    fmax = np.maximum(np.abs(ref).max(axis=ax), 1e-300)
+    dmax = np.abs(dref).max(axis=ax)
+    typical = np.median(dmax / fmax)
+    sc = np.maximum(dmax, fmax * typical)
+    nine = 9 if ref.shape[-1] == 20 else 4          # theta_c: round-off only (helpers.field_scaled_diff)
+    sc[nine] = max(sc[nine], sc[nine + 2], sc[nine + 4])      # ... measured against the baryon / photon velocities
+    return np.abs(dy - dref).max(axis=ax) / np.maximum(sc, 1e-300)
+
+
+def check_tangent_replay(lib, name, tol=1e-6):
+    case = load_tangent_case(name)
+    ks, aout = case["kmodes"], case["aexp_out"]
+    ctrl = _cabi.make_ctrl(rtol=float(case["rtol"]), atol=float(case["rtol"]))
+    nt = case["d_scalars"].shape[0]
+    worst = 0.0
+    for full in (False, True):
+        dims = tangent_dims(case, return_full=full)
+        y, dy, dtau, ns = lib.debug_replay_tangent(dims, ctrl, case["scalars"][None], case["tables"][None], ks, aout,
+                                                   case["d_scalars"][:, None], case["d_tables"][:, None], case["rp_tnext"],
+                                                   case["rp_dtnext"], case["rp_keep"], case["nsteps"])
+        assert np.array_equal(ns[0], case["nsteps"])
+        np.testing.assert_allclose(dtau[:, 0], case["dtau_out"], rtol=1e-9, atol=1e-9 * np.abs(case["dtau_out"]).max() + 1e-300)
+        ref, dref = (case["yfull"], case["dyfull"]) if full else (case["y"], case["dy"])
+        for m in range(len(ks)):
+            assert helpers.field_scaled_diff(y[0, m], ref[m]).max() < tol, (name, full, m)
+            for d in range(nt):
+                if not np.any(dref[d, m]):
+                    assert not np.any(dy[d, 0, m]), (name, full, m, d)      # post-processing-only direction: exactly zero
+                    continue
+                e = tangent_scaled_diff(dy[d, 0, m], dref[d, m], ref[m]).max()
+                worst = max(worst, e)
+                assert e < tol, (name, full, m, d, e)
+    return worst
+
+
+def check_tangent_adaptive(lib, name):
+    """Free-running: the public tangent entry (controller on) against the oracle, incl. P(k) and its tangent."""
+    case = load_tangent_case(name)
+    ks, aout, rtol = case["kmodes"], case["aexp_out"], float(case["rtol"])
+    nt = case["d_scalars"].shape[0]
+    dims = tangent_dims(case, power_idx=4)
+    ctrl = _cabi.make_ctrl(rtol=rtol, atol=rtol)
+    out = lib.evolve_tangent_host(dims, ctrl, case["scalars"][None], case["tables"][None], ks, aout, case["d_scalars"][:, None],
+                                  case["d_tables"][:, None], want_pk=True)
+    assert np.all(out["status"] == 0)
+    np.testing.assert_allclose(out["tau_out"][0], case["tau_out"], rtol=1e-13)
+    # the primal half must be what the primal entry returns for the same inputs (same kernel code path modulo the
+    # helper-warp variant: 50 rtol; bitwise when that variant is not selected is checked on the GPU suite)
+    same = (out["nsteps"][0] == case["nsteps"]) & (out["naccept"][0] == case["naccept"])
+    assert same[case["nsteps"] <= 100].all(), (out["nsteps"][0], case["nsteps"])      # short modes: identical step counts
+    for m in range(len(ks)):
+        relp = np.abs(out["pk"][0, m] / case["pk4"][m] - 1).max()
+        assert relp < 400 * rtol, (name, m, relp)      # P ~ delta^2: twice the 50..200 rtol global error of a free-running solve
+        for d in range(nt):
+            dref = case["dpk4"][d, m]
+            rel = np.abs(out["dpk"][d, 0, m] - dref).max() / (np.abs(dref).max() + 1e-9 * np.abs(case["pk4"][m]).max())
+            tight = same[m] and case["nsteps"][m] <= 100
+            assert rel < (1e-5 if tight else 2000 * rtol), (name, m, d, rel)
+            if tight and np.any(case["dy"][d, m]):
+                assert tangent_scaled_diff(out["dy"][d, 0, m], case["dy"][d, m], case["y"][m]).max() < 1e-5, (name, m, d)
+    return out
+
+
+def check_tangent_properties(lib, name="default_n72", nk=16):
+    """Size-independent properties of the tangent map: linearity in the seed, d P/d A_s = P/A_s,
+    d P/d n_s = P log(k/k_p), zero seed -> zero tangent, and the primal half equals the plain solve."""
+    case = load_tangent_case(name)
+    aout, rtol = case["aexp_out"], float(case["rtol"])
+    ks = np.geomspace(1e-3, 1.0, nk)
+    ctrl = _cabi.make_ctrl(rtol=rtol, atol=rtol)
+    sc, tb = case["scalars"], case["tables"]
+    d1s, d1t, d2s, d2t = case["d_scalars"][0], case["d_tables"][0], case["d_scalars"][1], case["d_tables"][1]
+    dAs = np.zeros_like(sc); dAs[16] = 1.0
+    dns = np.zeros_like(sc); dns[17] = 1.0
+    zt = np.zeros_like(tb)
+    seeds_s = np.stack([d1s, d2s, 0.3 * d1s - 1.7 * d2s, dAs, dns, np.zeros_like(sc)])
+    seeds_t = np.stack([d1t, d2t, 0.3 * d1t - 1.7 * d2t, zt, zt, zt])
+    dims = tangent_dims(case, nk=nk, ntan=len(seeds_s), power_idx=4)
+    out = lib.evolve_tangent_host(dims, ctrl, sc[None], tb[None], ks, aout, seeds_s[:, None], seeds_t[:, None], want_pk=True)
+    assert np.all(out["status"] == 0)
+    dy, dpk, pk = out["dy"][:, 0], out["dpk"][:, 0], out["pk"][0]
+    lin = 0.3 * dy[0] - 1.7 * dy[1]
+    scale = np.abs(dy[0]).max(axis=(0, 1)) + np.abs(dy[1]).max(axis=(0, 1)) + 1e-300
+    assert (np.abs(dy[2] - lin).max(axis=(0, 1)) / scale).max() < 1e-9
+    np.testing.assert_allclose(dpk[3], pk / sc[16], rtol=1e-12)
+    np.testing.assert_allclose(dpk[4], pk * np.log(ks / sc[18])[:, None], rtol=1e-10, atol=1e-12 * np.abs(pk).max())
+    assert not np.any(dy[3]) and not np.any(dy[4]) and not np.any(dy[5]) and not np.any(dpk[5])
+    return out

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_library_metadata_calls_without_gpu():
     lib = _cabi.Library()
-    assert lib.lib.deb_abi_version() == 1
+    assert lib.lib.deb_abi_version() == 2
     d = _cabi.make_dims(ncosmo=1, nk=4, nout=1, lmaxg=31, lmaxgp=31, lmaxr=31, lmaxnu=31, nqmax=5, nth=256, nnu=512, max_steps=10)
     assert lib.lib.deb_nvar(ctypes.byref(d)) == 265
     assert lib.lib.deb_table_len(ctypes.byref(d)) == 3 * (5 * 256 + 2 * 512)
