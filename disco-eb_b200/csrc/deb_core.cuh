@@ -994,7 +994,7 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, Help
   const double* toutd = nullptr;
   if (TAN) {
     DEB_LANE0_BEGIN
-      *TW->cd = load_cosmo_d(P, cosmo, tan);
+      load_cosmo_d(P, cosmo, tan, TW->cd);
     DEB_LANE0_END
     toutd = P.dtau_out + ((size_t)tan * P.ncosmo + cosmo) * P.nout;
     int jmax = 0, jmin = 0;
@@ -1529,7 +1529,7 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, Help
       }
       if (TAN) {
         // ---- tangent stage: rdot_i, solve with the same factorisation, keep kdot_i ----
-        tan_stage_rhs(P, C, W, *TW, st, k, t, td, dt, ddt DEB_LANE_ARG);
+        tan_stage_rhs(P, C, W, *TW, st, k, t, td, dt, ddt, hint DEB_LANE_ARG);
         solve_second(TW->rd);
         if (st < 8) {
           DEB_LANES_BEGIN

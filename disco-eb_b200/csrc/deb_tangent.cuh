@@ -67,27 +67,27 @@ DEB_DEV Spl get_spline_from(const double* tables, const Problem& P, int slot, in
   Spl r; r.x = base + off; r.y = r.x + n; r.S = r.y + n; r.n = n;
   return r;
 }
-DEB_DEV CosmoD load_cosmo_d(const Problem& P, int c, int tan) {
+DEB_DEV void load_cosmo_d(const Problem& P, int c, int tan, CosmoD* dst) {      // dst: shared memory
   const double* s = P.scalars + (size_t)c * NSCAL;
   const size_t slot = (size_t)tan * P.ncosmo + c;
   const double* d = P.d_scalars + slot * NSCAL;
-  CosmoD o;
-#define DEB_LD(field, idx) o.field = mk(DEB_LDG(s + idx), DEB_LDG(d + idx))
+#define DEB_LD(field, idx) dst->field = mk(DEB_LDG(s + idx), DEB_LDG(d + idx))
   DEB_LD(Omegam, S_OMEGAM); DEB_LD(Omegab, S_OMEGAB); DEB_LD(OmegaDE, S_OMEGADE); DEB_LD(Omegak, S_OMEGAK);
   DEB_LD(grhom, S_GRHOM); DEB_LD(grhog, S_GRHOG); DEB_LD(grhor, S_GRHOR); DEB_LD(Neff, S_NEFF); DEB_LD(Nmnu, S_NMNU);
   DEB_LD(amnu, S_AMNU); DEB_LD(w0, S_W0); DEB_LD(wa, S_WA); DEB_LD(cs2de, S_CS2DE); DEB_LD(YHe, S_YHE); DEB_LD(H0, S_H0);
   DEB_LD(taumin, S_TAUMIN); DEB_LD(As, S_AS); DEB_LD(ns, S_NS); DEB_LD(kp, S_KP);
 #undef DEB_LD
-  SplT* sp[NSPLINE] = {&o.cs2a, &o.xe, &o.lrn, &o.lpn, &o.a_of_tau, &o.xe_of_tau, &o.tau_of_a};
-  for (int w = 0; w < NSPLINE; ++w) { sp[w]->p = get_spline(P, c, w); sp[w]->t = get_spline_from(P.d_tables, P, (int)slot, w); }
-  return o;
+#define DEB_LS(field, w) dst->field.p = get_spline(P, c, w); dst->field.t = get_spline_from(P.d_tables, P, (int)slot, w)
+  DEB_LS(cs2a, T_CS2A); DEB_LS(xe, T_XE); DEB_LS(lrn, T_LRHONU); DEB_LS(lpn, T_LPNU); DEB_LS(a_of_tau, T_A_OF_TAU);
+  DEB_LS(xe_of_tau, T_XE_OF_TAU); DEB_LS(tau_of_a, T_TAU_OF_A);
+#undef DEB_LS
 }
 
 // spline value with tangents in the knots, the values, the second derivatives and the abscissa
 // (spline_interpolation.py:130-153; the interval comes from primal values)
 template <class T>
-DEB_DEV T spl_eval_g(const SplT& s, T xn) {
-  const int i = spl_locate(s.p.x, s.p.n, val(xn), -1);
+DEB_DEV T spl_eval_g(const SplT& s, T xn, int hint = -1) {
+  const int i = spl_locate(s.p.x, s.p.n, val(xn), hint);
   const T x0 = lift2<T>(DEB_LDG(s.p.x + i), DEB_LDG(s.t.x + i)), x1 = lift2<T>(DEB_LDG(s.p.x + i + 1), DEB_LDG(s.t.x + i + 1));
   const T y0 = lift2<T>(DEB_LDG(s.p.y + i), DEB_LDG(s.t.y + i)), y1 = lift2<T>(DEB_LDG(s.p.y + i + 1), DEB_LDG(s.t.y + i + 1));
   const T S0 = lift2<T>(DEB_LDG(s.p.S + i), DEB_LDG(s.t.S + i)), S1 = lift2<T>(DEB_LDG(s.p.S + i + 1), DEB_LDG(s.t.S + i + 1));
@@ -98,22 +98,35 @@ DEB_DEV T spl_eval_g(const SplT& s, T xn) {
 }
 
 // ---- background coefficients (perturbations.py:176-218, background.py:110-121), generic --------------
+// (scalars only, so that the struct lives in registers; the per-bin velocities v_i go through shared memory)
 template <class T> struct BgG {
   T a, H, opac, k2cs2, pbo, wq1, wq, ca2, gc, gb, gg, gr, gnu, gq;
-  T kv[NQMAX], vv[NQMAX];            // k v_i and v_i
 };
+constexpr int BG_NS = 14;             // scalars in BgG
+// v_i = 1/sqrt(1 + (a amnu/q_i)^2) as T -> 4 doubles per bin (value, eps, d/da, d2); Dual uses the first two
+template <class T> DEB_DEV void vv_store(double* dst, T v);
+template <> DEB_DEV void vv_store<Dual>(double* dst, Dual v) { dst[0] = v.v; dst[1] = v.d; }
+template <> DEB_DEV void vv_store<HD>(double* dst, HD v) { dst[0] = v.v.v; dst[1] = v.v.d; dst[2] = v.d.v; dst[3] = v.d.d; }
+template <class T> DEB_DEV T vv_load(const double* src);
+template <> DEB_DEV Dual vv_load<Dual>(const double* src) { return mk(src[0], src[1]); }
+template <> DEB_DEV HD vv_load<HD>(const double* src) { return mkd<Dual>(mk(src[0], src[1]), mk(src[2], src[3])); }
 template <class T>
-DEB_DEV void compute_bg_g(const CosmoD& c, const NuBins& nb, int nq, T a, double k, BgG<T>& b) {
+DEB_DEV void nu_velocity_g(const CosmoD& c, const NuBins& nb, T a, int i, double* dst) {
+  const T aq = a * (liftD<T>(c.amnu) / nb.q[i]);
+  vv_store<T>(dst, drsqrt(1.0 + aq * aq));
+}
+template <class T>
+DEB_DEV void compute_bg_g(const CosmoD& c, T a, double k, int hint_th, int hint_nu, BgG<T>& b) {
   const T loga = dlog(a);
   const T inva = 1.0 / a, inva2 = inva * inva;
   const T grhom = liftD<T>(c.grhom), grhog = liftD<T>(c.grhog), grhor = liftD<T>(c.grhor);
   const T Omegab = liftD<T>(c.Omegab), Omegam = liftD<T>(c.Omegam), wa = liftD<T>(c.wa), w0 = liftD<T>(c.w0);
   const T Neff = liftD<T>(c.Neff), Nmnu = liftD<T>(c.Nmnu);
   b.a = a;
-  const T cs2 = spl_eval_g<T>(c.cs2a, loga) * inva;
+  const T cs2 = spl_eval_g<T>(c.cs2a, loga, hint_th) * inva;
   b.k2cs2 = (k * k) * cs2;
-  const T xe = spl_eval_g<T>(c.xe, loga);
-  const T rhonu = dexp(spl_eval_g<T>(c.lrn, loga));
+  const T xe = spl_eval_g<T>(c.xe, loga, hint_th);
+  const T rhonu = dexp(spl_eval_g<T>(c.lrn, loga, hint_nu));
   const T rhoq = dexp((-3.0 * (1.0 + w0 + wa)) * loga + 3.0 * wa * (a - 1.0));
   b.wq = w0 + wa * (1.0 - a);
   b.wq1 = 1.0 + b.wq;
@@ -130,12 +143,19 @@ DEB_DEV void compute_bg_g(const CosmoD& c, const NuBins& nb, int nq, T a, double
   const T akthom = (AKTHOM_RHS * (1.0 - liftD<T>(c.YHe))) * Omegab * H0 * H0;
   b.opac = xe * akthom * inva2;
   b.pbo = ((4.0 / 3.0) * grhog / (grhom * Omegab)) * inva * b.opac;
-  const T amnu = liftD<T>(c.amnu);
-  for (int i = 0; i < nq; ++i) {
-    const T aq = a * (amnu / nb.q[i]);
-    b.vv[i] = drsqrt(1.0 + aq * aq);
-    b.kv[i] = b.vv[i] * k;
-  }
+}
+// a BgG<Dual> to / from 2 BG_NS doubles of shared memory (the base-point coefficients are per step, not per stage)
+#define DEB_BG_FIELDS(X) X(a, 0) X(H, 1) X(opac, 2) X(k2cs2, 3) X(pbo, 4) X(wq1, 5) X(wq, 6) X(ca2, 7) X(gc, 8) X(gb, 9) X(gg, 10) \
+  X(gr, 11) X(gnu, 12) X(gq, 13)
+DEB_DEV void bg_store(double* dst, const BgG<Dual>& b) {
+#define DEB_X(f, i) dst[2 * i] = b.f.v; dst[2 * i + 1] = b.f.d;
+  DEB_BG_FIELDS(DEB_X)
+#undef DEB_X
+}
+DEB_DEV void bg_load(const double* src, BgG<Dual>& b) {
+#define DEB_X(f, i) b.f = mk(src[2 * i], src[2 * i + 1]);
+  DEB_BG_FIELDS(DEB_X)
+#undef DEB_X
 }
 
 // state accessors: u[e] as T
@@ -147,7 +167,8 @@ template <class T> DEB_DEV T sget(const StateV0& s, int e) { return lift2<T>(s.v
 // metric sources (perturbations.py:229-261), generic
 template <class T> struct MetricG { T hp, ep, al, f1; };
 template <class T, class St>
-DEB_DEV void compute_metric_g(const Problem& P, const CosmoD& c, const NuBins& nb, const BgG<T>& b, const St& u, double k, MetricG<T>& mt) {
+DEB_DEV void compute_metric_g(const Problem& P, const CosmoD& c, const NuBins& nb, const BgG<T>& b, const double* vvs, const St& u,
+                              double k, MetricG<T>& mt) {
   const int nq = P.nq, iq0 = P.iq0, n = P.n;
   const T eta = sget<T>(u, 2), dc = sget<T>(u, 3), tc = sget<T>(u, 4), db = sget<T>(u, 5), tb = sget<T>(u, 6);
   const T dg = sget<T>(u, 7), tg = sget<T>(u, 8), dr = sget<T>(u, P.ir), tr = sget<T>(u, P.ir + 1);
@@ -155,8 +176,9 @@ DEB_DEV void compute_metric_g(const Problem& P, const CosmoD& c, const NuBins& n
   T drhonu = 0.0 * b.a, dpnu3 = 0.0 * b.a, fnu = 0.0 * b.a;
   for (int i = 0; i < nq; ++i) {
     const T p0 = nb.w[i] * sget<T>(u, iq0 + i);
-    drhonu = drhonu + p0 / b.vv[i];
-    dpnu3 = dpnu3 + p0 * b.vv[i];
+    const T v = vv_load<T>(vvs + 4 * i);
+    drhonu = drhonu + p0 / v;
+    dpnu3 = dpnu3 + p0 * v;
     fnu = fnu + nb.w[i] * sget<T>(u, iq0 + nq + i);
   }
   const double k2 = k * k, ik2 = 1.0 / k2;
@@ -174,8 +196,8 @@ DEB_DEV void compute_metric_g(const Problem& P, const CosmoD& c, const NuBins& n
 // row e of f (perturbations.py:226-369).  `lin`: drop the one term that does not multiply a state variable
 // (row 0 = H a), which turns the routine into the linear operator A(a, t; theta) applied to the state.
 template <class T, class St>
-DEB_DEV T row_g(const Problem& P, const CtaConst& C, const CosmoD& c, const BgG<T>& b, const MetricG<T>& mt, const St& u,
-                int e, int desc, T invtau, double k, bool lin) {
+DEB_DEV T row_g(const Problem& P, const CtaConst& C, const CosmoD& c, const BgG<T>& b, const double* vvs, const MetricG<T>& mt,
+                const St& u, int e, int desc, T invtau, double k, bool lin) {
   const int type = desc & 0xff, l = (desc >> 8) & 0xff, chain = desc >> 16;
   const int ig = P.ig, igp = P.igp, ir = P.ir, n = P.n, nq = P.nq;
   const double k2 = k * k;
@@ -205,15 +227,16 @@ DEB_DEV T row_g(const Problem& P, const CtaConst& C, const CosmoD& c, const BgG<
     case R_N0: return (4.0 / 3.0) * (-sget<T>(u, ir + 1) - 0.5 * mt.hp);
     case R_N1: return k2 * (0.25 * sget<T>(u, ir) - 0.5 * sget<T>(u, ir + 2));
     case R_N2: return (8.0 / 15.0) * (sget<T>(u, ir + 1) + k2 * mt.al) - (0.6 * k) * sget<T>(u, ir + 3);
-    case R_P0: { const int i = chain - 3; return -(b.kv[i] * sget<T>(u, e + nq)) + mt.hp * (C.nu.dl[i] / 6.0); }
-    case R_P1: { const int i = chain - 3; return b.kv[i] * ((sget<T>(u, e - nq) - 2.0 * sget<T>(u, e + nq)) / 3.0); }
+    case R_P0: { const int i = chain - 3; return -((k * vv_load<T>(vvs + 4 * i)) * sget<T>(u, e + nq)) + mt.hp * (C.nu.dl[i] / 6.0); }
+    case R_P1: { const int i = chain - 3; return (k * vv_load<T>(vvs + 4 * i)) * ((sget<T>(u, e - nq) - 2.0 * sget<T>(u, e + nq)) / 3.0); }
     case R_P2: {
       const int i = chain - 3;
-      return b.kv[i] * ((2.0 * sget<T>(u, e - nq) - 3.0 * sget<T>(u, e + nq)) / 5.0) - (mt.hp / 15.0 + 0.4 * mt.ep) * C.nu.dl[i];
+      return (k * vv_load<T>(vvs + 4 * i)) * ((2.0 * sget<T>(u, e - nq) - 3.0 * sget<T>(u, e + nq)) / 5.0)
+             - (mt.hp / 15.0 + 0.4 * mt.ep) * C.nu.dl[i];
     }
     case R_GEN: case R_TRUNC: {
       const int s = C.ch_stride[chain], L = C.ch_lmax[chain];
-      const T kc = chain >= 3 ? b.kv[chain - 3] : 0.0 * b.a + k;
+      const T kc = chain >= 3 ? k * vv_load<T>(vvs + 4 * (chain - 3)) : 0.0 * b.a + k;
       const T kap = chain < 2 ? b.opac : 0.0 * b.a;
       if (type == R_GEN) return kc * ((C.cl[l] * sget<T>(u, e - s)) - C.ch[l] * sget<T>(u, e + s)) - kap * sget<T>(u, e);
       return kc * sget<T>(u, e - s) - ((double)(L + 1) * invtau + kap) * sget<T>(u, e);
@@ -255,7 +278,7 @@ DEB_DEV Dual cond_large_k_d(const CosmoD& c, Dual lt, double k) {
 }
 // bisection of util.py:365-396: the branches are decided on primal values, the end points carry tangents
 DEB_DEV Dual start_time_d(const CosmoD& c, double k) {
-  Dual res[2];
+  Dual res0 = mk(0.0, 0.0), res1 = mk(0.0, 0.0);
   for (int which = 0; which < 2; ++which) {
     Dual xl = dlog(c.taumin), xr = dlog(spl_eval_g<Dual>(c.tau_of_a, mk(0.1, 0.0)));
     double fl = which == 0 ? cond_small_k_d(c, xl).v : cond_large_k_d(c, xl, k).v;
@@ -264,9 +287,9 @@ DEB_DEV Dual start_time_d(const CosmoD& c, double k) {
       const double fm = which == 0 ? cond_small_k_d(c, xm).v : cond_large_k_d(c, xm, k).v;
       if (fm * fl > 0) { xl = xm; fl = fm; } else xr = xm;
     }
-    res[which] = 0.5 * (xl + xr);
+    if (which == 0) res0 = 0.5 * (xl + xr); else res1 = 0.5 * (xl + xr);
   }
-  return dexp(res[0].v <= res[1].v ? res[0] : res[1]);
+  return dexp(res0.v <= res1.v ? res0 : res1);
 }
 
 struct IcScalarsD { Dual a, deltag, thetag, deltar, thetar, shearr, deltaq, thetaq, eta; };
@@ -375,12 +398,16 @@ struct TanWs {
   double* jad;    // d/d eps of d f/d a at (t0, y0) [np]
   double* cc;     // primal sum_j C_ij/dt k_j of the current stage [np]
   double* kd;     // kdot_1 .. kdot_7 [7 np]
+  double* b0;     // base-point coefficients BgG<Dual> at (a0, a0dot) [2 BG_NS]
+  double* vv0;    // base-point v_i [4 NQMAX]
+  double* vvi;    // stage v_i [4 NQMAX]
   CosmoD* cd;     // scalars and tables of this (cosmology, direction)
 };
-DEB_HD size_t tan_ws_doubles(int np) { return (size_t)12 * np + (sizeof(CosmoD) + 7) / 8; }
+DEB_HD size_t tan_ws_doubles(int np) { return (size_t)12 * np + 2 * BG_NS + 8 * NQMAX + (sizeof(CosmoD) + 7) / 8; }
 DEB_DEV void carve_tan(TanWs& T, double* base, int np) {
   T.yd = base; T.ud = T.yd + np; T.rd = T.ud + np; T.jad = T.rd + np; T.cc = T.jad + np; T.kd = T.cc + np;
-  T.cd = (CosmoD*)(T.kd + (size_t)7 * np);
+  T.b0 = T.kd + (size_t)7 * np; T.vv0 = T.b0 + 2 * BG_NS; T.vvi = T.vv0 + 4 * NQMAX;
+  T.cd = (CosmoD*)(T.vvi + 4 * NQMAX);
 }
 
 // Everything of tangent stage `st` up to (not including) the linear solve: forms rdot_i in TW.rd.
@@ -388,8 +415,8 @@ DEB_DEV void carve_tan(TanWs& T, double* base, int np) {
 //   ki     : k_i of the primal stage (W.r after the primal solve)
 template <class Dummy = void>
 DEB_DEV void tan_stage_rhs(const Problem& P, const CtaConst& C, const WarpWs& W, const TanWs& TW, int st, double k,
-                           double t, double td, double dt, double ddt DEB_LANE_PARAM) {
-  const int n = P.n, np = P.np;
+                           double t, double td, double dt, double ddt, const Hints& hint DEB_LANE_PARAM) {
+  const int n = P.n, np = P.np, nq = P.nq;
   const CosmoD& cd = *TW.cd;
   const NuBins& nb = C.nu;
   // ---- u_dot ----
@@ -420,25 +447,30 @@ DEB_DEV void tan_stage_rhs(const Problem& P, const CtaConst& C, const WarpWs& W,
   const double wdiag = ddt / (RD_GAMMA * dt * dt);
   const double* ki = W.r();
   const double ki0 = ki[0];
-  // base-point coefficients with the state held constant: Adot_0 k~_i
-  BgG<Dual> b0;
-  compute_bg_g<Dual>(cd, nb, P.nq, mk(W.y()[0], TW.yd[0]), k, b0);
   const StateV0 sk = {ki};
-  MetricG<Dual> m0;
-  compute_metric_g<Dual>(P, cd, nb, b0, sk, k, m0);
   const StateVD su = {us, TW.ud};
+  BgG<Dual> b0;
+  MetricG<Dual> m0;
   if (st == 1) {
+    // base-point coefficients (a0, a0dot), once per step: kept in shared memory for the other seven stages
+    compute_bg_g<Dual>(cd, mk(W.y()[0], TW.yd[0]), k, hint.th, hint.nu, b0);
     // second-order duals at (t0, y0): eps-part = fdot, (a x eps)-part = d/d eps of df/da
     BgG<HD> bh;
-    compute_bg_g<HD>(cd, nb, P.nq, mkd<Dual>(mk(W.y()[0], TW.yd[0]), mk(1.0, 0.0)), k, bh);
+    const HD aH = mkd<Dual>(mk(W.y()[0], TW.yd[0]), mk(1.0, 0.0));
+    compute_bg_g<HD>(cd, aH, k, hint.th, hint.nu, bh);
+    DEB_LANES_BEGIN
+      if (lane == 0) bg_store(TW.b0, b0);
+      if (lane < nq) { nu_velocity_g<Dual>(cd, nb, b0.a, lane, TW.vv0 + 4 * lane); nu_velocity_g<HD>(cd, nb, aH, lane, TW.vvi + 4 * lane); }
+    DEB_LANES_END
+    compute_metric_g<Dual>(P, cd, nb, b0, TW.vv0, sk, k, m0);
     MetricG<HD> mh;
-    compute_metric_g<HD>(P, cd, nb, bh, su, k, mh);
+    compute_metric_g<HD>(P, cd, nb, bh, TW.vvi, su, k, mh);
     const HD invtH = liftD<HD>(invt0);
     DEB_LANES_BEGIN
       for (int e = lane; e < n; e += 32) {
         const int desc = elem_desc(P, e);
-        const HD f = row_g<HD>(P, C, cd, bh, mh, su, e, desc, invtH, k, false);
-        const Dual g = row_g<Dual>(P, C, cd, b0, m0, sk, e, desc, invt0, k, true);
+        const HD f = row_g<HD>(P, C, cd, bh, TW.vvi, mh, su, e, desc, invtH, k, false);
+        const Dual g = row_g<Dual>(P, C, cd, b0, TW.vv0, m0, sk, e, desc, invt0, k, true);
         const double jd = f.d.d;
         TW.jad[e] = jd;
         double r = f.v.d + g.d + jd * ki0 + wdiag * ki[e];
@@ -452,15 +484,20 @@ DEB_DEV void tan_stage_rhs(const Problem& P, const CtaConst& C, const WarpWs& W,
     DEB_LANES_END
     return;
   }
+  bg_load(TW.b0, b0);
   BgG<Dual> bi;
-  compute_bg_g<Dual>(cd, nb, P.nq, mk(us[0], TW.ud[0]), k, bi);
+  compute_bg_g<Dual>(cd, mk(us[0], TW.ud[0]), k, hint.th, hint.nu, bi);
+  DEB_LANES_BEGIN
+    if (lane < nq) nu_velocity_g<Dual>(cd, nb, bi.a, lane, TW.vvi + 4 * lane);
+  DEB_LANES_END
+  compute_metric_g<Dual>(P, cd, nb, b0, TW.vv0, sk, k, m0);
   MetricG<Dual> mi;
-  compute_metric_g<Dual>(P, cd, nb, bi, su, k, mi);
+  compute_metric_g<Dual>(P, cd, nb, bi, TW.vvi, su, k, mi);
   DEB_LANES_BEGIN
     for (int e = lane; e < n; e += 32) {
       const int desc = elem_desc(P, e);
-      const Dual f = row_g<Dual>(P, C, cd, bi, mi, su, e, desc, invts, k, false);
-      const Dual g = row_g<Dual>(P, C, cd, b0, m0, sk, e, desc, invt0, k, true);
+      const Dual f = row_g<Dual>(P, C, cd, bi, TW.vvi, mi, su, e, desc, invts, k, false);
+      const Dual g = row_g<Dual>(P, C, cd, b0, TW.vv0, m0, sk, e, desc, invt0, k, true);
       double r = f.d + g.d + TW.jad[e] * ki0 + wdiag * ki[e];
       if (st <= 5 && (desc & 0xff) == R_TRUNC) {
         const double tr = (double)(C.ch_lmax[desc >> 16] + 1);
