@@ -45,7 +45,7 @@ WORKLOAD = dict(name="config2: LCDM + 1 massive nu, lmax=31 (32 multipoles), nq=
 METRIC = "k-modes/sec (ms per P(k), N_k=512, in ms_per_step)"
 
 
-NCU_DRAM_BYTES_PER_LAUNCH = 935680 + 29184     # ncu --set full, k_evolve<9>, 512 modes (profiles/r1_v6_k_evolve9_ncu_summary.txt)
+NCU_DRAM_BYTES_PER_LAUNCH = 344320 + 22528     # ncu --set full, k_evolve_h<9>, 512 modes (profiles/r1_v10_k_evolve_h9_ncu_summary.txt)
 
 
 def f_step(n):
@@ -253,7 +253,7 @@ def run_ours(args, rank, world):
                                   note="FP64 FMA pipe (the path is neither HBM- nor tensor-bound); peak measured on this GPU by "
                                        "deb_fp64_peak_tflops (dependent-free DFMA streams) x n_gpus; algorithmic flops = "
                                        "(370 n + 3000) x attempted steps, n=265; traffic = dram bytes read+written per k_evolve "
-                                       "launch from profiles/r1_v6_k_evolve9_ncu_summary.txt (0.96 MB: HBM is idle)"),
+                                       "launch from profiles/r1_v10_k_evolve_h9_ncu_summary.txt (0.37 MB: HBM is idle)"),
                     e2e=dict(value=world * nk / (e2e * 1e-3), unit="k-modes/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
                              ms_per_step=e2e),
                     gpu_launches=2 * args.steps, clocks=clocks)
