@@ -5,7 +5,7 @@ Mirrors the reference's keyword API on the ``param`` dict
 
 * ``evolve_perturbations``          -> :926-997   returns ``(y, kmodes, param)``
 * ``evolve_perturbations_batched``  -> :1000-1061 returns ``(y, kmodes)``
-* ``get_power``                     -> :1101-1123
+* ``get_power``                     -> :1101-1123   (and the other spectra entry points :1063-1224, see spectra.py)
 
 Same argument names, defaults, return shapes, ``param`` side effects (:989-995) and failure
 behaviour (diffrax raises when ``max_steps`` is exhausted; so does this).  The arithmetic runs in
@@ -24,7 +24,7 @@ from . import _cabi
 from ._pack import pack_param, pack_params, pack_tangent
 
 __all__ = ["evolve_perturbations", "evolve_perturbations_batched", "evolve_perturbations_multi", "evolve_perturbations_jvp",
-           "get_power"]
+           "get_power", "get_power_smoothed", "power_Kaiser", "power_multipoles", "get_xi_from_P"]
 
 
 class MaxStepsReached(RuntimeError):
@@ -189,9 +189,4 @@ def evolve_perturbations_jvp(*, param, dparam, aexp_out, kmin: float, kmax: floa
     return out["y"][0], (dy[0] if single else dy), kmodes, info
 
 
-def get_power(*, k, y, idx: int, param):
-    """``2 pi^2 A_s (k/k_p)^(n_s-1) k^-3 y[..., idx]^2`` (perturbations.py:1101-1123); pure array
-    math on the solver output, kept on the host like in the reference."""
-    k = np.asarray(k)
-    y = np.asarray(y)
-    return 2 * np.pi ** 2 * param["A_s"] * (k / param["k_p"]) ** (param["n_s"] - 1) * k ** (-3) * y[..., idx] ** 2
+from .spectra import get_power, get_power_smoothed, power_Kaiser, power_multipoles, get_xi_from_P  # noqa: E402,F401
