@@ -212,3 +212,32 @@ def check_tangent_properties(lib, name="default_n72", nk=16):
     np.testing.assert_allclose(dpk[4], pk * np.log(ks / sc[18])[:, None], rtol=1e-10, atol=1e-12 * np.abs(pk).max())
     assert not np.any(dy[3]) and not np.any(dy[4]) and not np.any(dy[5]) and not np.any(dpk[5])
     return out
+
+
+def check_tangent_batch_of_cosmologies(lib, nk=6):
+    """[ntan, ncosmo, ...] indexing: two cosmologies x two directions in one launch equal the four single launches;
+    per-cosmology k grids and the raw-state output included."""
+    a, b = load_tangent_case("default_n72"), load_tangent_case("w0wa_n43")
+    # same table sizes, different cosmologies (fiducial / w0wa); use the n=72 layout for both
+    sc = np.stack([a["scalars"], b["scalars"]]); tb = np.stack([a["tables"], b["tables"]])
+    ds = np.stack([np.stack([a["d_scalars"][0], b["d_scalars"][0]]), np.stack([a["d_scalars"][1], b["d_scalars"][1]])])
+    dt = np.stack([np.stack([a["d_tables"][0], b["d_tables"][0]]), np.stack([a["d_tables"][1], b["d_tables"][1]])])
+    ks = np.stack([np.geomspace(1e-3, 0.3, nk), np.geomspace(2e-3, 0.5, nk)])
+    aout = np.array([0.2, 1.0])
+    ctrl = _cabi.make_ctrl(rtol=1e-4, atol=1e-4)
+    for full in (False, True):
+        dims = tangent_dims(a, nk=nk, ntan=2, power_idx=-1 if full else 6, k_per_cosmo=True, return_full=full)
+        dims.ncosmo = 2
+        out = lib.evolve_tangent_host(dims, ctrl, sc, tb, ks, aout, ds, dt, want_pk=not full)
+        assert np.all(out["status"] == 0)
+        for c in range(2):
+            for d in range(2):
+                d1 = tangent_dims(a, nk=nk, ntan=1, power_idx=-1 if full else 6, return_full=full)
+                one = lib.evolve_tangent_host(d1, ctrl, sc[c:c + 1], tb[c:c + 1], ks[c], aout, ds[d:d + 1, c:c + 1], dt[d:d + 1, c:c + 1],
+                                              want_pk=not full)
+                assert np.array_equal(one["nsteps"][0], out["nsteps"][c])
+                np.testing.assert_array_equal(one["y"][0], out["y"][c])
+                np.testing.assert_array_equal(one["dy"][0, 0], out["dy"][d, c])
+                np.testing.assert_array_equal(one["dtau_out"][0, 0], out["dtau_out"][d, c])
+                if not full:
+                    np.testing.assert_array_equal(one["dpk"][0, 0], out["dpk"][d, c])

@@ -72,3 +72,53 @@ def test_world_size_2_gloo_matches_single_process(emu_lib):
         assert nout == 2
         np.testing.assert_allclose(k, ks, rtol=1e-15)
         assert np.array_equal(y, ref["y"][0])        # per-mode results do not depend on the sharding
+
+
+def _worker_jvp(rank, world, port, emu_path, q):
+    import sys
+    sys.path.insert(0, helpers.ROOT)
+    sys.path.insert(0, os.path.join(helpers.ROOT, "disco-eb_b200"))
+    sys.path.insert(0, os.path.join(helpers.ROOT, "tests"))
+    import torch.distributed as dist
+    import parity_checks as pc
+    from discoeb_b200 import _cabi
+    from discoeb_b200.distributed import evolve_perturbations_jvp_sharded
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lib = _cabi.Library(emu_path, prefix="emu_")
+    case = pc.load_tangent_case("default_n72")
+    p = helpers.Tables(case["scalars"], case["tables"], case["nth"], case["nnu"]).param()
+    dps = [helpers.Tables(case["d_scalars"][d], case["d_tables"][d], case["nth"], case["nnu"]).param() for d in range(2)]
+    y, dy, pk, dpk, k = evolve_perturbations_jvp_sharded(param=p, dparam=dps, aexp_out=[0.5, 1.0], kmin=1e-3, kmax=0.3, num_k=7, lib=lib)
+    q.put((rank, y, dy, pk, dpk, k))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_sharded_jvp_matches_single_process(emu_lib):
+    """Config-5 path at N>1: (direction, k) items dealt over two ranks == one process."""
+    import torch.multiprocessing as mp
+    import parity_checks as pc
+    from discoeb_b200 import _cabi
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_jvp, args=(r, 2, port, emu_lib.path, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    results = [q.get(timeout=300) for _ in procs]
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    case = pc.load_tangent_case("default_n72")
+    ks = np.geomspace(1e-3, 0.3, 7)
+    dims = pc.tangent_dims(case, nk=7, ntan=2, power_idx=4)
+    dims.nout = 2
+    ctrl = _cabi.make_ctrl(rtol=1e-4, atol=1e-4)
+    ref = emu_lib.evolve_tangent_host(dims, ctrl, case["scalars"][None], case["tables"][None], ks, np.array([0.5, 1.0]),
+                                      case["d_scalars"][:2, None], case["d_tables"][:2, None], want_pk=True)
+    for rank, y, dy, pk, dpk, k in results:
+        np.testing.assert_allclose(k, ks, rtol=1e-15)
+        assert np.array_equal(y, ref["y"][0]) and np.array_equal(dy, ref["dy"][:, 0])
+        assert np.array_equal(pk, ref["pk"][0]) and np.array_equal(dpk, ref["dpk"][:, 0])

@@ -30,6 +30,10 @@ def test_tangent_properties_full_size_n265(gpu_lib):
     pc.check_tangent_properties(gpu_lib, name="fisher_n265x2", nk=64)
 
 
+def test_tangent_batch_of_cosmologies(gpu_lib):
+    pc.check_tangent_batch_of_cosmologies(gpu_lib)
+
+
 def test_tangent_primal_half_equals_plain_solve(gpu_lib):
     """The primal outputs of the tangent launch are those of the primal kernel (same source, same step sequence)."""
     case = pc.load_tangent_case("default_n72")

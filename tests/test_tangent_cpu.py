@@ -83,3 +83,7 @@ def test_kernel_source_tangent_adaptive(emu_lib, name):
 
 def test_kernel_source_tangent_properties(emu_lib):
     pc.check_tangent_properties(emu_lib)
+
+
+def test_kernel_source_tangent_batch_of_cosmologies(emu_lib):
+    pc.check_tangent_batch_of_cosmologies(emu_lib)
