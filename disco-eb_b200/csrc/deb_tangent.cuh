@@ -193,65 +193,55 @@ DEB_DEV void compute_metric_g(const Problem& P, const CosmoD& c, const NuBins& n
   mt.al = (mt.hp + 6.0 * mt.ep) * (0.5 * ik2);
 }
 
-// row e of f (perturbations.py:226-369).  `lin`: drop the one term that does not multiply a state variable
-// (row 0 = H a), which turns the routine into the linear operator A(a, t; theta) applied to the state.
-template <class T, class St>
-DEB_DEV T row_g(const Problem& P, const CtaConst& C, const CosmoD& c, const BgG<T>& b, const double* vvs, const MetricG<T>& mt,
-                const St& u, int e, int desc, T invtau, double k, bool lin) {
-  const int type = desc & 0xff, l = (desc >> 8) & 0xff, chain = desc >> 16;
-  const int ig = P.ig, igp = P.igp, ir = P.ir, n = P.n, nq = P.nq;
+// ---- rows, branch-free -------------------------------------------------------------------------------
+// The 17+3nq head rows (eta, fluids, l <= 2 of every hierarchy, dark energy) are evaluated one lane per row from the
+// primal path's operator table (CtaConst::hop_*: constant x background slot x state index), with the slots as T;
+// the l >= 3 rows of the hierarchies by the generic three-term recurrence over the tail list.  (A first version
+// evaluated every element through one switch over the row type: with 32 lanes on ~12 different row types per trip
+// the warp executed each case in turn -- 112 k warp-instructions per step.)
+// A T lives in shared memory as 4 doubles (value, eps, d/da, d2); Dual uses the first two.
+template <class T>
+DEB_DEV void fill_slots_g(const CosmoD& c, const BgG<T>& b, double k, double* sl) {      // slots 0 .. SL_KV0-1 (one lane)
   const double k2 = k * k;
-  switch (type) {
-    case R_A: return lin ? 0.0 * b.a : b.H * b.a;
-    case R_AHP: return mt.f1;
-    case R_ETA: return mt.ep;
-    case R_DC: return -sget<T>(u, 4) - 0.5 * mt.hp;
-    case R_TC: return -(b.H * sget<T>(u, 4));
-    case R_DB: return -sget<T>(u, 6) - 0.5 * mt.hp;
-    case R_TB: return -(b.H * sget<T>(u, 6)) + b.k2cs2 * sget<T>(u, 5) + b.pbo * (sget<T>(u, 8) - sget<T>(u, 6));
-    case R_F0: return (4.0 / 3.0) * (-sget<T>(u, ig + 1) - 0.5 * mt.hp);
-    case R_F1: return k2 * (0.25 * sget<T>(u, ig) - 0.5 * sget<T>(u, ig + 2)) - b.opac * (sget<T>(u, ig + 1) - sget<T>(u, 6));
-    case R_F2: {
-      const T polter = sget<T>(u, ig + 2) + sget<T>(u, igp) + sget<T>(u, igp + 2);
-      return (8.0 / 15.0) * (sget<T>(u, ig + 1) + k2 * mt.al) - (0.6 * k) * sget<T>(u, ig + 3) - b.opac * (sget<T>(u, ig + 2) - 0.1 * polter);
-    }
-    case R_G0: {
-      const T polter = sget<T>(u, ig + 2) + sget<T>(u, igp) + sget<T>(u, igp + 2);
-      return -(k * sget<T>(u, igp + 1)) - b.opac * sget<T>(u, igp) + b.opac * (0.5 * polter);
-    }
-    case R_G1: return (k / 3.0) * (sget<T>(u, igp) - 2.0 * sget<T>(u, igp + 2)) - b.opac * sget<T>(u, igp + 1);
-    case R_G2: {
-      const T polter = sget<T>(u, ig + 2) + sget<T>(u, igp) + sget<T>(u, igp + 2);
-      return (k / 5.0) * (2.0 * sget<T>(u, igp + 1) - 3.0 * sget<T>(u, igp + 3)) - b.opac * sget<T>(u, igp + 2) + b.opac * (0.1 * polter);
-    }
-    case R_N0: return (4.0 / 3.0) * (-sget<T>(u, ir + 1) - 0.5 * mt.hp);
-    case R_N1: return k2 * (0.25 * sget<T>(u, ir) - 0.5 * sget<T>(u, ir + 2));
-    case R_N2: return (8.0 / 15.0) * (sget<T>(u, ir + 1) + k2 * mt.al) - (0.6 * k) * sget<T>(u, ir + 3);
-    case R_P0: { const int i = chain - 3; return -((k * vv_load<T>(vvs + 4 * i)) * sget<T>(u, e + nq)) + mt.hp * (C.nu.dl[i] / 6.0); }
-    case R_P1: { const int i = chain - 3; return (k * vv_load<T>(vvs + 4 * i)) * ((sget<T>(u, e - nq) - 2.0 * sget<T>(u, e + nq)) / 3.0); }
-    case R_P2: {
-      const int i = chain - 3;
-      return (k * vv_load<T>(vvs + 4 * i)) * ((2.0 * sget<T>(u, e - nq) - 3.0 * sget<T>(u, e + nq)) / 5.0)
-             - (mt.hp / 15.0 + 0.4 * mt.ep) * C.nu.dl[i];
-    }
-    case R_GEN: case R_TRUNC: {
-      const int s = C.ch_stride[chain], L = C.ch_lmax[chain];
-      const T kc = chain >= 3 ? k * vv_load<T>(vvs + 4 * (chain - 3)) : 0.0 * b.a + k;
-      const T kap = chain < 2 ? b.opac : 0.0 * b.a;
-      if (type == R_GEN) return kc * ((C.cl[l] * sget<T>(u, e - s)) - C.ch[l] * sget<T>(u, e + s)) - kap * sget<T>(u, e);
-      return kc * sget<T>(u, e - s) - ((double)(L + 1) * invtau + kap) * sget<T>(u, e);
-    }
-    case R_DQ: {
-      const T cs2de = liftD<T>(c.cs2de);
-      return -(b.wq1 * (sget<T>(u, n - 1) + 0.5 * mt.hp)) - 3.0 * ((cs2de - b.wq) * b.H) * sget<T>(u, n - 2)
-             - (9.0 / k2) * (b.wq1 * (cs2de - b.ca2) * (b.H * b.H)) * sget<T>(u, n - 1);
-    }
-    case R_TQ: {
-      const T cs2de = liftD<T>(c.cs2de);
-      return -((1.0 - 3.0 * cs2de) * b.H) * sget<T>(u, n - 1) + ((cs2de * k2) / b.wq1) * sget<T>(u, n - 2);
-    }
-    default: return 0.0 * b.a;
+  const T cs2de = liftD<T>(c.cs2de);
+  const T one = 0.0 * b.a + 1.0;
+  vv_store<T>(sl + 4 * SL_ONE, one); vv_store<T>(sl + 4 * SL_H, b.H); vv_store<T>(sl + 4 * SL_OPAC, b.opac);
+  vv_store<T>(sl + 4 * SL_PBO, b.pbo); vv_store<T>(sl + 4 * SL_K2CS2, b.k2cs2); vv_store<T>(sl + 4 * SL_WQ1, b.wq1);
+  vv_store<T>(sl + 4 * SL_DQD, (cs2de - b.wq) * b.H);
+  vv_store<T>(sl + 4 * SL_DQT, b.wq1 * (cs2de - b.ca2) * (b.H * b.H) * (1.0 / k2));
+  vv_store<T>(sl + 4 * SL_TQD, (cs2de * k2) / b.wq1);
+  vv_store<T>(sl + 4 * SL_TQT, (1.0 - 3.0 * cs2de) * b.H);
+  vv_store<T>(sl + 4 * SL_K, one * k); vv_store<T>(sl + 4 * SL_K2, one * k2);
+}
+// per chain: wavenumber k or k v_i, damping opac or 0; lane `ch` < nch.  Also the k v_i slots of the head operator.
+template <class T>
+DEB_DEV void chain_coeffs_g(const BgG<T>& b, const double* vvs, double k, int ch, double* kcs, double* kaps, double* sl) {
+  T kc = 0.0 * b.a + k;
+  if (ch >= 3) { kc = k * vv_load<T>(vvs + 4 * (ch - 3)); vv_store<T>(sl + 4 * (SL_KV0 + ch - 3), kc); }
+  vv_store<T>(kcs + 4 * ch, kc);
+  vv_store<T>(kaps + 4 * ch, ch < 2 ? b.opac : 0.0 * b.a);
+}
+template <class T, class St>
+DEB_DEV T head_row_g(const CtaConst& C, const double* sl, const St& u, int r, const MetricG<T>& mt) {
+  T f = (C.hop_chc[r] * vv_load<T>(sl + 4 * C.hop_chs[r])) * mt.hp + C.hop_cec[r] * mt.ep;
+#pragma unroll
+  for (int t = 0; t < HOP_NT; ++t) {
+    const int m = C.hop_meta[t][r];
+    f = f + (C.hop_c[t][r] * sget<T>(u, (m >> 8) & 0xfff)) * vv_load<T>(sl + 4 * (m & 0xff));
   }
+  return C.htype[r] == R_AHP ? mt.f1 : f;
+}
+template <class T, class St>
+DEB_DEV T tail_row_g(const CtaConst& C, const double* kcs, const double* kaps, const St& u, int info, T invtau, int* e_out,
+                     double* trunc_out) {
+  const int e = info & 0xfff, chain = (info >> 12) & 0xf, l = info >> 16;
+  const int s = C.ch_stride[chain], L = C.ch_lmax[chain];
+  const bool isT = (l == L);
+  const double clv = isT ? 1.0 : C.cl[l], chv = isT ? 0.0 : C.ch[l];
+  const double tr = isT ? (double)(L + 1) : 0.0;
+  const T lin = clv * sget<T>(u, e - s) - chv * sget<T>(u, isT ? e : e + s);
+  *e_out = e; *trunc_out = tr;
+  return vv_load<T>(kcs + 4 * chain) * lin - (vv_load<T>(kaps + 4 * chain) + tr * invtau) * sget<T>(u, e);
 }
 
 // ---- prologue with tangents: start time (perturbations.py:630-681) and adiabatic ICs (:526-627) ------------
@@ -401,40 +391,65 @@ struct TanWs {
   double* b0;     // base-point coefficients BgG<Dual> at (a0, a0dot) [2 BG_NS]
   double* vv0;    // base-point v_i [4 NQMAX]
   double* vvi;    // stage v_i [4 NQMAX]
+  double* sl0;    // base-point operator slots [4 NSLOT]
+  double* sli;    // stage operator slots [4 NSLOT]
+  double* kc0;    // base-point chain wavenumbers / dampings [4 NCHMAX] each
+  double* kap0;
+  double* kci;    // stage chain wavenumbers / dampings
+  double* kapi;
   CosmoD* cd;     // scalars and tables of this (cosmology, direction)
 };
-DEB_HD size_t tan_ws_doubles(int np) { return (size_t)12 * np + 2 * BG_NS + 8 * NQMAX + (sizeof(CosmoD) + 7) / 8; }
+DEB_HD size_t tan_ws_doubles(int np) {
+  return (size_t)12 * np + 2 * BG_NS + 8 * NQMAX + 8 * NSLOT + 16 * NCHMAX + (sizeof(CosmoD) + 7) / 8;
+}
 DEB_DEV void carve_tan(TanWs& T, double* base, int np) {
   T.yd = base; T.ud = T.yd + np; T.rd = T.ud + np; T.jad = T.rd + np; T.cc = T.jad + np; T.kd = T.cc + np;
   T.b0 = T.kd + (size_t)7 * np; T.vv0 = T.b0 + 2 * BG_NS; T.vvi = T.vv0 + 4 * NQMAX;
-  T.cd = (CosmoD*)(T.vvi + 4 * NQMAX);
+  T.sl0 = T.vvi + 4 * NQMAX; T.sli = T.sl0 + 4 * NSLOT;
+  T.kc0 = T.sli + 4 * NSLOT; T.kap0 = T.kc0 + 4 * NCHMAX; T.kci = T.kap0 + 4 * NCHMAX; T.kapi = T.kci + 4 * NCHMAX;
+  T.cd = (CosmoD*)(T.kapi + 4 * NCHMAX);
 }
 
 // Everything of tangent stage `st` up to (not including) the linear solve: forms rdot_i in TW.rd.
-//   ys/yd  : accepted state and its tangent at (t, td)         us/ud : stage state u_i and its tangent
-//   ki     : k_i of the primal stage (W.r after the primal solve)
+//   y/yd  : accepted state and its tangent at (t, td)         u/ud : stage state u_i and its tangent
+//   ki    : k_i of the primal stage (W.r after the primal solve)
 template <class Dummy = void>
 DEB_DEV void tan_stage_rhs(const Problem& P, const CtaConst& C, const WarpWs& W, const TanWs& TW, int st, double k,
                            double t, double td, double dt, double ddt, const Hints& hint DEB_LANE_PARAM) {
-  const int n = P.n, np = P.np, nq = P.nq;
+  const int n = P.n, np = P.np, nq = P.nq, nh = P.nh, nch = P.nch;
   const CosmoD& cd = *TW.cd;
   const NuBins& nb = C.nu;
-  // ---- u_dot ----
+  const double invdt = 1.0 / dt;
+  const double wdiag = ddt / (RD_GAMMA * dt * dt);
+  const double* ki = W.r();
+  const double ki0 = ki[0];
+  // ---- u_dot, and the part of rdot that needs no row evaluation:
+  //      ddt/(gamma dt^2) k_i + (d/d eps df/da) k_i0 + sum_j C_ij (kdot_j/dt - k_j ddt/dt^2)
   DEB_LANES_BEGIN
     for (int e = lane; e < n; e += 32) {
       const double* k1 = TW.kd + e;
-      double v;
+      double v, cs = 0.0;
       switch (st) {
         case 1: v = TW.yd[e]; break;
-        case 2: v = TW.yd[e] + RD_A21 * k1[0]; break;
-        case 3: v = TW.yd[e] + RD_A31 * k1[0] + RD_A32 * k1[np]; break;
-        case 4: v = TW.yd[e] + RD_A41 * k1[0] + RD_A42 * k1[np] + RD_A43 * k1[2 * np]; break;
-        case 5: v = TW.yd[e] + RD_A51 * k1[0] + RD_A52 * k1[np] + RD_A53 * k1[2 * np] + RD_A54 * k1[3 * np]; break;
-        case 6: v = TW.yd[e] + RD_A61 * k1[0] + RD_A62 * k1[np] + RD_A63 * k1[2 * np] + RD_A64 * k1[3 * np] + RD_A65 * k1[4 * np]; break;
-        case 7: v = TW.ud[e] + k1[5 * np]; break;
-        default: v = TW.ud[e] + k1[6 * np]; break;
+        case 2: v = TW.yd[e] + RD_A21 * k1[0];
+                cs = RD_C21 * k1[0]; break;
+        case 3: v = TW.yd[e] + RD_A31 * k1[0] + RD_A32 * k1[np];
+                cs = RD_C31 * k1[0] + RD_C32 * k1[np]; break;
+        case 4: v = TW.yd[e] + RD_A41 * k1[0] + RD_A42 * k1[np] + RD_A43 * k1[2 * np];
+                cs = RD_C41 * k1[0] + RD_C42 * k1[np] + RD_C43 * k1[2 * np]; break;
+        case 5: v = TW.yd[e] + RD_A51 * k1[0] + RD_A52 * k1[np] + RD_A53 * k1[2 * np] + RD_A54 * k1[3 * np];
+                cs = RD_C51 * k1[0] + RD_C52 * k1[np] + RD_C53 * k1[2 * np] + RD_C54 * k1[3 * np]; break;
+        case 6: v = TW.yd[e] + RD_A61 * k1[0] + RD_A62 * k1[np] + RD_A63 * k1[2 * np] + RD_A64 * k1[3 * np] + RD_A65 * k1[4 * np];
+                cs = RD_C61 * k1[0] + RD_C62 * k1[np] + RD_C63 * k1[2 * np] + RD_C64 * k1[3 * np] + RD_C65 * k1[4 * np]; break;
+        case 7: v = TW.ud[e] + k1[5 * np];
+                cs = RD_C71 * k1[0] + RD_C72 * k1[np] + RD_C73 * k1[2 * np] + RD_C74 * k1[3 * np] + RD_C75 * k1[4 * np] + RD_C76 * k1[5 * np]; break;
+        default: v = TW.ud[e] + k1[6 * np];
+                cs = RD_C81 * k1[0] + RD_C82 * k1[np] + RD_C83 * k1[2 * np] + RD_C84 * k1[3 * np] + RD_C85 * k1[4 * np] + RD_C86 * k1[5 * np] + RD_C87 * k1[6 * np]; break;
       }
       TW.ud[e] = v;
+      double r = wdiag * ki[e];
+      if (st > 1) r += TW.jad[e] * ki0 + invdt * cs - (ddt * invdt) * TW.cc[e];
+      TW.rd[e] = r;
     }
   DEB_LANES_END
   const double* us = st == 1 ? W.y() : W.u();
@@ -443,10 +458,7 @@ DEB_DEV void tan_stage_rhs(const Problem& P, const CtaConst& C, const WarpWs& W,
   const Dual tsD = mk(t + ci * dt, td + ci * ddt);
   const Dual t0D = mk(t, td);
   const Dual invts = 1.0 / tsD, invt0 = 1.0 / t0D;
-  const double invdt = 1.0 / dt;
-  const double wdiag = ddt / (RD_GAMMA * dt * dt);
-  const double* ki = W.r();
-  const double ki0 = ki[0];
+  const double it2 = 1.0 / (t * t);
   const StateV0 sk = {ki};
   const StateVD su = {us, TW.ud};
   BgG<Dual> b0;
@@ -459,27 +471,35 @@ DEB_DEV void tan_stage_rhs(const Problem& P, const CtaConst& C, const WarpWs& W,
     const HD aH = mkd<Dual>(mk(W.y()[0], TW.yd[0]), mk(1.0, 0.0));
     compute_bg_g<HD>(cd, aH, k, hint.th, hint.nu, bh);
     DEB_LANES_BEGIN
-      if (lane == 0) bg_store(TW.b0, b0);
+      if (lane == 0) { bg_store(TW.b0, b0); fill_slots_g<Dual>(cd, b0, k, TW.sl0); fill_slots_g<HD>(cd, bh, k, TW.sli); }
       if (lane < nq) { nu_velocity_g<Dual>(cd, nb, b0.a, lane, TW.vv0 + 4 * lane); nu_velocity_g<HD>(cd, nb, aH, lane, TW.vvi + 4 * lane); }
+    DEB_LANES_END
+    DEB_LANES_BEGIN
+      if (lane < nch) {
+        chain_coeffs_g<Dual>(b0, TW.vv0, k, lane, TW.kc0, TW.kap0, TW.sl0);
+        chain_coeffs_g<HD>(bh, TW.vvi, k, lane, TW.kci, TW.kapi, TW.sli);
+      }
     DEB_LANES_END
     compute_metric_g<Dual>(P, cd, nb, b0, TW.vv0, sk, k, m0);
     MetricG<HD> mh;
     compute_metric_g<HD>(P, cd, nb, bh, TW.vvi, su, k, mh);
     const HD invtH = liftD<HD>(invt0);
     DEB_LANES_BEGIN
-      for (int e = lane; e < n; e += 32) {
-        const int desc = elem_desc(P, e);
-        const HD f = row_g<HD>(P, C, cd, bh, TW.vvi, mh, su, e, desc, invtH, k, false);
-        const Dual g = row_g<Dual>(P, C, cd, b0, TW.vv0, m0, sk, e, desc, invt0, k, true);
-        const double jd = f.d.d;
-        TW.jad[e] = jd;
-        double r = f.v.d + g.d + jd * ki0 + wdiag * ki[e];
-        if ((desc & 0xff) == R_TRUNC) {
-          const double tr = (double)(C.ch_lmax[desc >> 16] + 1);
-          const double it2 = 1.0 / (t * t);
-          r += di * (ddt * (tr * it2 * W.y()[e]) + dt * tr * (TW.yd[e] * it2 - 2.0 * W.y()[e] * td * it2 / t));
-        }
-        TW.rd[e] = r;
+      if (lane < nh) {
+        const int e = C.hidx[lane];
+        const HD f = head_row_g<HD>(C, TW.sli, su, lane, mh);
+        const Dual g = head_row_g<Dual>(C, TW.sl0, sk, lane, m0);
+        TW.jad[e] = f.d.d;
+        TW.rd[e] += f.v.d + g.d + f.d.d * ki0;
+      }
+      if (lane == 0) { const HD f = bh.H * bh.a; TW.jad[0] = f.d.d; TW.rd[0] += f.v.d + f.d.d * ki0; }
+      for (int tt = lane; tt < C.ntail; tt += 32) {
+        int e; double tr;
+        const HD f = tail_row_g<HD>(C, TW.kci, TW.kapi, su, C.tail[tt], invtH, &e, &tr);
+        const Dual g = tail_row_g<Dual>(C, TW.kc0, TW.kap0, sk, C.tail[tt], invt0, &e, &tr);
+        TW.jad[e] = f.d.d;
+        TW.rd[e] += f.v.d + g.d + f.d.d * ki0
+                  + di * (ddt * (tr * it2 * W.y()[e]) + dt * tr * (TW.yd[e] * it2 - 2.0 * W.y()[e] * td * it2 / t));
       }
     DEB_LANES_END
     return;
@@ -488,35 +508,27 @@ DEB_DEV void tan_stage_rhs(const Problem& P, const CtaConst& C, const WarpWs& W,
   BgG<Dual> bi;
   compute_bg_g<Dual>(cd, mk(us[0], TW.ud[0]), k, hint.th, hint.nu, bi);
   DEB_LANES_BEGIN
+    if (lane == 0) fill_slots_g<Dual>(cd, bi, k, TW.sli);
     if (lane < nq) nu_velocity_g<Dual>(cd, nb, bi.a, lane, TW.vvi + 4 * lane);
+  DEB_LANES_END
+  DEB_LANES_BEGIN
+    if (lane < nch) chain_coeffs_g<Dual>(bi, TW.vvi, k, lane, TW.kci, TW.kapi, TW.sli);
   DEB_LANES_END
   compute_metric_g<Dual>(P, cd, nb, b0, TW.vv0, sk, k, m0);
   MetricG<Dual> mi;
   compute_metric_g<Dual>(P, cd, nb, bi, TW.vvi, su, k, mi);
+  const double dtrunc = st <= 5 ? di : 0.0;
   DEB_LANES_BEGIN
-    for (int e = lane; e < n; e += 32) {
-      const int desc = elem_desc(P, e);
-      const Dual f = row_g<Dual>(P, C, cd, bi, TW.vvi, mi, su, e, desc, invts, k, false);
-      const Dual g = row_g<Dual>(P, C, cd, b0, TW.vv0, m0, sk, e, desc, invt0, k, true);
-      double r = f.d + g.d + TW.jad[e] * ki0 + wdiag * ki[e];
-      if (st <= 5 && (desc & 0xff) == R_TRUNC) {
-        const double tr = (double)(C.ch_lmax[desc >> 16] + 1);
-        const double it2 = 1.0 / (t * t);
-        r += di * (ddt * (tr * it2 * W.y()[e]) + dt * tr * (TW.yd[e] * it2 - 2.0 * W.y()[e] * td * it2 / t));
-      }
-      const double* k1 = TW.kd + e;
-      double cs;
-      switch (st) {
-        case 2: cs = RD_C21 * k1[0]; break;
-        case 3: cs = RD_C31 * k1[0] + RD_C32 * k1[np]; break;
-        case 4: cs = RD_C41 * k1[0] + RD_C42 * k1[np] + RD_C43 * k1[2 * np]; break;
-        case 5: cs = RD_C51 * k1[0] + RD_C52 * k1[np] + RD_C53 * k1[2 * np] + RD_C54 * k1[3 * np]; break;
-        case 6: cs = RD_C61 * k1[0] + RD_C62 * k1[np] + RD_C63 * k1[2 * np] + RD_C64 * k1[3 * np] + RD_C65 * k1[4 * np]; break;
-        case 7: cs = RD_C71 * k1[0] + RD_C72 * k1[np] + RD_C73 * k1[2 * np] + RD_C74 * k1[3 * np] + RD_C75 * k1[4 * np] + RD_C76 * k1[5 * np]; break;
-        default: cs = RD_C81 * k1[0] + RD_C82 * k1[np] + RD_C83 * k1[2 * np] + RD_C84 * k1[3 * np] + RD_C85 * k1[4 * np] + RD_C86 * k1[5 * np] + RD_C87 * k1[6 * np]; break;
-      }
-      r += invdt * cs - (ddt * invdt) * TW.cc[e];
-      TW.rd[e] = r;
+    if (lane < nh) {
+      const int e = C.hidx[lane];
+      TW.rd[e] += head_row_g<Dual>(C, TW.sli, su, lane, mi).d + head_row_g<Dual>(C, TW.sl0, sk, lane, m0).d;
+    }
+    if (lane == 0) TW.rd[0] += (bi.H * bi.a).d;
+    for (int tt = lane; tt < C.ntail; tt += 32) {
+      int e; double tr;
+      const Dual f = tail_row_g<Dual>(C, TW.kci, TW.kapi, su, C.tail[tt], invts, &e, &tr);
+      const Dual g = tail_row_g<Dual>(C, TW.kc0, TW.kap0, sk, C.tail[tt], invt0, &e, &tr);
+      TW.rd[e] += f.d + g.d + dtrunc * (ddt * (tr * it2 * W.y()[e]) + dt * tr * (TW.yd[e] * it2 - 2.0 * W.y()[e] * td * it2 / t));
     }
   DEB_LANES_END
 }
