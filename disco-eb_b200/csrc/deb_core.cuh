@@ -264,6 +264,7 @@ struct Problem {
   const double* d_scalars; const double* d_tables;
   const double* dtau_out;                        // [ntan, ncosmo, nout] (pre-kernel)
   double* dy_out; double* dpk_out;               // [ntan, ncosmo, nk, nout, 20|n], [ntan, ncosmo, nk, nout]
+  const double* d_kmodes;                        // tangent of the wavenumbers [ntan, nk] / [ntan, ncosmo, nk], or NULL (zero)
   const double* rp_dtnext;                       // replay: tangent of the prescribed step ends [ntan, ncosmo*nk, rp_stride]
   const double* dbg_dt0; const double* dbg_dt1; const double* dbg_dy0; double* dbg_dy1;      // single-step mode
 };
@@ -992,7 +993,12 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, Help
   double td = 0.0, tnextd = 0.0, t1d = 0.0, tmind = 0.0;
   const size_t item = (size_t)tan * ((size_t)P.ncosmo * P.nk) + mode;
   const double* toutd = nullptr;
+  Dual kD = mk(k, 0.0);
   if (TAN) {
+    if (P.d_kmodes) {
+      const size_t nkm = P.k_per_cosmo ? (size_t)P.ncosmo * P.nk : (size_t)P.nk;
+      kD.d = DEB_LDG(P.d_kmodes + (size_t)tan * nkm + (P.k_per_cosmo ? (size_t)cosmo * P.nk + kidx : (size_t)kidx));
+    }
     DEB_LANE0_BEGIN
       load_cosmo_d(P, cosmo, tan, TW->cd);
     DEB_LANE0_END
@@ -1023,11 +1029,11 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, Help
       for (int e = lane; e < n; e += 32) W.y()[e] = ic_value(P, c, nb, ics, elem_desc(P, e), k);
     DEB_LANES_END
     if (TAN) {
-      const Dual stD = start_time_d(*TW->cd, k);
+      const Dual stD = start_time_d(*TW->cd, kD);
       td = 0.99 * (tmin_out <= st0 ? tmind : stD.d);
-      const IcScalarsD icd = ic_scalars_d(*TW->cd, mk(tau_start, td), k);
+      const IcScalarsD icd = ic_scalars_d(*TW->cd, mk(tau_start, td), kD);
       DEB_LANES_BEGIN
-        for (int e = lane; e < n; e += 32) TW->yd[e] = ic_value_d(P, *TW->cd, nb, icd, elem_desc(P, e), k).d;
+        for (int e = lane; e < n; e += 32) TW->yd[e] = ic_value_d(P, *TW->cd, nb, icd, elem_desc(P, e), kD).d;
       DEB_LANES_END
     }
     if (P.mode == 2) {
@@ -1529,7 +1535,7 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, Help
       }
       if (TAN) {
         // ---- tangent stage: rdot_i, solve with the same factorisation, keep kdot_i ----
-        tan_stage_rhs(P, C, W, *TW, st, k, t, td, dt, ddt, hint DEB_LANE_ARG);
+        tan_stage_rhs(P, C, W, *TW, st, kD, t, td, dt, ddt, hint DEB_LANE_ARG);
         solve_second(TW->rd);
         if (st < 8) {
           DEB_LANES_BEGIN
@@ -1618,9 +1624,9 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, Help
             if (TAN) {
               Dual od[20];
               const StateVD sy = {W.r(), TW->rd};
-              convert_outputs_d(P, *TW->cd, nb, sy, k, od);
+              convert_outputs_d(P, *TW->cd, nb, sy, kD, od);
               for (int q = 0; q < 20; ++q) P.dy_out[dbase * 20 + q] = od[q].d;
-              if (P.dpk_out && P.power_idx >= 0) P.dpk_out[dbase] = power_d(*TW->cd, k, od[P.power_idx]).d;
+              if (P.dpk_out && P.power_idx >= 0) P.dpk_out[dbase] = power_d(*TW->cd, kD, od[P.power_idx]).d;
             }
           DEB_LANE0_END
         }

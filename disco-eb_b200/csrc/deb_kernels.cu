@@ -238,15 +238,15 @@ int deb_evolve_f64(const deb_dims* dims, const deb_ctrl* ctrl, const double* sca
                    int32_t* status, int32_t* nsteps, int32_t* naccept, void* workspace, size_t workspace_bytes,
                    void* stream) {
   if (dims && dims->ntan != 0) return DEB_E_ARG;       // tangents go through deb_evolve_tangent_f64
-  return deb_evolve_tangent_f64(dims, ctrl, scalars, tables, kmodes, aexp_out, nullptr, nullptr, y_out, nullptr, pk_out, nullptr,
+  return deb_evolve_tangent_f64(dims, ctrl, scalars, tables, kmodes, aexp_out, nullptr, nullptr, nullptr, y_out, nullptr, pk_out, nullptr,
                                 tau_out, nullptr, status, nsteps, naccept, workspace, workspace_bytes, stream);
 }
 
 int deb_evolve_tangent_f64(const deb_dims* dims, const deb_ctrl* ctrl, const double* scalars, const double* tables,
                            const double* kmodes, const double* aexp_out, const double* d_scalars, const double* d_tables,
-                           double* y_out, double* dy_out, double* pk_out, double* dpk_out, double* tau_out, double* dtau_out,
-                           int32_t* status, int32_t* nsteps, int32_t* naccept, void* workspace, size_t workspace_bytes,
-                           void* stream) {
+                           const double* d_kmodes, double* y_out, double* dy_out, double* pk_out, double* dpk_out, double* tau_out,
+                           double* dtau_out, int32_t* status, int32_t* nsteps, int32_t* naccept, void* workspace,
+                           size_t workspace_bytes, void* stream) {
   Problem P;
   int rc = fill_problem(dims, ctrl, &P);
   if (rc) return rc;
@@ -255,7 +255,7 @@ int deb_evolve_tangent_f64(const deb_dims* dims, const deb_ctrl* ctrl, const dou
   if (dims->power_idx >= 0 && !pk_out) return DEB_E_ARG;
   if (dims->ntan > 0 && (!d_scalars || !d_tables || !dy_out || !dtau_out)) return DEB_E_ARG;
   if (dims->ntan > 0 && dims->power_idx >= 0 && !dpk_out) return DEB_E_ARG;
-  P.d_scalars = d_scalars; P.d_tables = d_tables; P.dy_out = dy_out; P.dpk_out = dims->power_idx >= 0 ? dpk_out : nullptr;
+  P.d_scalars = d_scalars; P.d_tables = d_tables; P.d_kmodes = dims->ntan > 0 ? d_kmodes : nullptr; P.dy_out = dy_out; P.dpk_out = dims->power_idx >= 0 ? dpk_out : nullptr;
   P.dtau_out = dtau_out;
   cudaStream_t st = (cudaStream_t)stream;
   P.scalars = scalars; P.tables = tables; P.kmodes = kmodes; P.aexp_out = aexp_out;
@@ -335,8 +335,8 @@ extern "C" void deb_ctx_destroy(deb_ctx* c) {
 
 static int ctx_evolve(deb_ctx* c, const deb_dims* dims, const deb_ctrl* ctrl, const double* scalars, const double* tables,
                       const double* kmodes, const double* aexp_out, const double* d_scalars, const double* d_tables,
-                      double* y_out, double* dy_out, double* pk_out, double* dpk_out, double* tau_out, double* dtau_out,
-                      int32_t* status, int32_t* nsteps, int32_t* naccept, float* kernel_ms) {
+                      const double* d_kmodes, double* y_out, double* dy_out, double* pk_out, double* dpk_out, double* tau_out,
+                      double* dtau_out, int32_t* status, int32_t* nsteps, int32_t* naccept, float* kernel_ms) {
   if (!c) return DEB_E_ARG;
   Problem P0;
   int rc = fill_problem(dims, ctrl, &P0);
@@ -350,11 +350,11 @@ static int ctx_evolve(deb_ctx* c, const deb_dims* dims, const deb_ctrl* ctrl, co
   const size_t tl = deb_table_len(dims);
   const size_t nkm = dims->k_per_cosmo ? nc * nk : nk;
   const bool pk = dims->power_idx >= 0 && pk_out && (nt == 0 || dpk_out);
-  // input block : scalars | tables | kmodes | aexp_out | d_scalars | d_tables
+  // input block : scalars | tables | kmodes | aexp_out | d_scalars | d_tables | d_kmodes
   // output block: y | pk | tau | status | nsteps | naccept | dy | dpk | dtau
   const size_t i_sc = 0, i_tb = i_sc + al256(nc * DEB_NSCAL * 8), i_k = i_tb + al256(nc * tl * 8), i_a = i_k + al256(nkm * 8),
                i_dsc = i_a + al256(nout * 8), i_dtb = i_dsc + al256(nt * nc * DEB_NSCAL * 8),
-               in_bytes = i_dtb + al256(nt * nc * tl * 8);
+               i_dk = i_dtb + al256(nt * nc * tl * 8), in_bytes = i_dk + al256(d_kmodes ? nt * nkm * 8 : 0);
   const size_t o_y = 0, o_pk = o_y + al256(nc * nk * nout * nf * 8), o_tau = o_pk + al256(pk ? nc * nk * nout * 8 : 0),
                o_st = o_tau + al256(nc * nout * 8), o_ns = o_st + al256(nc * nk * 4), o_na = o_ns + al256(nc * nk * 4),
                o_dy = o_na + al256(nc * nk * 4), o_dpk = o_dy + al256(nt * nc * nk * nout * nf * 8),
@@ -369,6 +369,7 @@ static int ctx_evolve(deb_ctx* c, const deb_dims* dims, const deb_ctrl* ctrl, co
   memcpy(hin + i_k, kmodes, nkm * 8);
   memcpy(hin + i_a, aexp_out, nout * 8);
   if (nt) { memcpy(hin + i_dsc, d_scalars, nt * nc * DEB_NSCAL * 8); memcpy(hin + i_dtb, d_tables, nt * nc * tl * 8); }
+  if (nt && d_kmodes) memcpy(hin + i_dk, d_kmodes, nt * nkm * 8);
   CUDA_TRY(cudaMemcpyAsync(din, hin, in_bytes, cudaMemcpyHostToDevice, c->st));
   CUDA_TRY(cudaMemsetAsync(dout, 0, out_bytes, c->st));
   CUDA_TRY(cudaEventRecord(c->e0, c->st));
@@ -376,7 +377,7 @@ static int ctx_evolve(deb_ctx* c, const deb_dims* dims, const deb_ctrl* ctrl, co
   if (!pk) d2.power_idx = -1;
   rc = deb_evolve_tangent_f64(&d2, ctrl, (double*)(din + i_sc), (double*)(din + i_tb), (double*)(din + i_k), (double*)(din + i_a),
                               nt ? (double*)(din + i_dsc) : nullptr, nt ? (double*)(din + i_dtb) : nullptr,
-                              (double*)(dout + o_y), nt ? (double*)(dout + o_dy) : nullptr, (double*)(dout + o_pk),
+                              (nt && d_kmodes) ? (double*)(din + i_dk) : nullptr, (double*)(dout + o_y), nt ? (double*)(dout + o_dy) : nullptr, (double*)(dout + o_pk),
                               nt ? (double*)(dout + o_dpk) : nullptr, (double*)(dout + o_tau), nt ? (double*)(dout + o_dtau) : nullptr,
                               (int32_t*)(dout + o_st), (int32_t*)(dout + o_ns), (int32_t*)(dout + o_na), dws, ws_bytes, (void*)c->st);
   if (rc != DEB_OK) { cudaStreamSynchronize(c->st); return rc; }
@@ -403,18 +404,19 @@ extern "C" int deb_ctx_evolve_host_f64(deb_ctx* c, const deb_dims* dims, const d
                                        double* pk_out, double* tau_out, int32_t* status, int32_t* nsteps, int32_t* naccept,
                                        float* kernel_ms) {
   if (dims && dims->ntan != 0) return DEB_E_ARG;
-  return ctx_evolve(c, dims, ctrl, scalars, tables, kmodes, aexp_out, nullptr, nullptr, y_out, nullptr, pk_out, nullptr, tau_out,
-                    nullptr, status, nsteps, naccept, kernel_ms);
+  return ctx_evolve(c, dims, ctrl, scalars, tables, kmodes, aexp_out, nullptr, nullptr, nullptr, y_out, nullptr, pk_out, nullptr,
+                    tau_out, nullptr, status, nsteps, naccept, kernel_ms);
 }
 
 extern "C" int deb_ctx_evolve_tangent_host_f64(deb_ctx* c, const deb_dims* dims, const deb_ctrl* ctrl, const double* scalars,
                                                const double* tables, const double* kmodes, const double* aexp_out,
-                                               const double* d_scalars, const double* d_tables, double* y_out, double* dy_out,
-                                               double* pk_out, double* dpk_out, double* tau_out, double* dtau_out,
-                                               int32_t* status, int32_t* nsteps, int32_t* naccept, float* kernel_ms) {
+                                               const double* d_scalars, const double* d_tables, const double* d_kmodes,
+                                               double* y_out, double* dy_out, double* pk_out, double* dpk_out, double* tau_out,
+                                               double* dtau_out, int32_t* status, int32_t* nsteps, int32_t* naccept,
+                                               float* kernel_ms) {
   if (!dims || dims->ntan < 1) return DEB_E_ARG;
-  return ctx_evolve(c, dims, ctrl, scalars, tables, kmodes, aexp_out, d_scalars, d_tables, y_out, dy_out, pk_out, dpk_out, tau_out,
-                    dtau_out, status, nsteps, naccept, kernel_ms);
+  return ctx_evolve(c, dims, ctrl, scalars, tables, kmodes, aexp_out, d_scalars, d_tables, d_kmodes, y_out, dy_out, pk_out, dpk_out,
+                    tau_out, dtau_out, status, nsteps, naccept, kernel_ms);
 }
 
 // One cached context per (host thread, device) backs the context-free entry; deb_host_cache_release() drops the
@@ -452,17 +454,17 @@ extern "C" int deb_evolve_host_f64(const deb_dims* dims, const deb_ctrl* ctrl, c
 
 extern "C" int deb_evolve_tangent_host_f64(const deb_dims* dims, const deb_ctrl* ctrl, const double* scalars, const double* tables,
                                           const double* kmodes, const double* aexp_out, const double* d_scalars,
-                                          const double* d_tables, double* y_out, double* dy_out, double* pk_out, double* dpk_out,
-                                          double* tau_out, double* dtau_out, int32_t* status, int32_t* nsteps, int32_t* naccept,
-                                          int32_t device, float* kernel_ms) {
+                                          const double* d_tables, const double* d_kmodes, double* y_out, double* dy_out,
+                                          double* pk_out, double* dpk_out, double* tau_out, double* dtau_out, int32_t* status,
+                                          int32_t* nsteps, int32_t* naccept, int32_t device, float* kernel_ms) {
   Problem P0;
   int rc = fill_problem(dims, ctrl, &P0);
   if (rc) return rc;
   deb_ctx* c = nullptr;
   rc = cached_ctx(device, &c);
   if (rc) return rc;
-  return deb_ctx_evolve_tangent_host_f64(c, dims, ctrl, scalars, tables, kmodes, aexp_out, d_scalars, d_tables, y_out, dy_out,
-                                         pk_out, dpk_out, tau_out, dtau_out, status, nsteps, naccept, kernel_ms);
+  return deb_ctx_evolve_tangent_host_f64(c, dims, ctrl, scalars, tables, kmodes, aexp_out, d_scalars, d_tables, d_kmodes, y_out,
+                                         dy_out, pk_out, dpk_out, tau_out, dtau_out, status, nsteps, naccept, kernel_ms);
 }
 
 extern "C" {
@@ -563,7 +565,7 @@ int deb_debug_replay_host_f64(const deb_dims* dims, const deb_ctrl* ctrl, const 
 // replay with one or more tangent directions (host pointers): the parity test of the tangent path
 int deb_debug_replay_tangent_host_f64(const deb_dims* dims, const deb_ctrl* ctrl, const double* scalars, const double* tables,
                                       const double* kmodes, const double* aexp_out, const double* d_scalars,
-                                      const double* d_tables, const double* rp_tnext, const double* rp_dtnext,
+                                      const double* d_tables, const double* d_kmodes, const double* rp_tnext, const double* rp_dtnext,
                                       const int32_t* rp_keep, const int32_t* rp_n, int32_t rp_stride, double* y_out,
                                       double* dy_out, double* dtau_out, int32_t* nsteps, int32_t device) {
   Problem P;
@@ -576,6 +578,8 @@ int deb_debug_replay_tangent_host_f64(const deb_dims* dims, const deb_ctrl* ctrl
   const size_t tl = deb_table_len(dims);
   const size_t nkm = dims->k_per_cosmo ? nc * nk : nk;
   const size_t nf = dims->return_full ? n : 20;
+  DevBuf d_dk;
+  if (d_kmodes) { if (d_dk.alloc(nt * nkm * 8)) return DEB_E_CUDA; CUDA_TRY(cudaMemcpy(d_dk.p, d_kmodes, nt * nkm * 8, cudaMemcpyHostToDevice)); }
   DevBuf d_sc, d_tb, d_dsc, d_dtb, d_k, d_a, d_tau, d_dtau, d_st, d_ns, d_ws, d_rt, d_rdt, d_rk, d_rn, d_y, d_dy;
   if (d_sc.alloc(nc * DEB_NSCAL * 8) || d_tb.alloc(nc * tl * 8) || d_dsc.alloc(nt * nc * DEB_NSCAL * 8) || d_dtb.alloc(nt * nc * tl * 8) ||
       d_k.alloc(nkm * 8) || d_a.alloc(nout * 8) || d_tau.alloc(nc * nout * 8) || d_dtau.alloc(nt * nc * nout * 8) ||
@@ -600,6 +604,7 @@ int deb_debug_replay_tangent_host_f64(const deb_dims* dims, const deb_ctrl* ctrl
   P.kmodes = d_k.as<double>(); P.aexp_out = d_a.as<double>(); P.tau_out = d_tau.as<double>(); P.dtau_out = d_dtau.as<double>();
   P.status = d_st.as<int>(); P.nsteps = d_ns.as<int>(); P.naccept = nullptr; P.ticket = (unsigned int*)d_ws.p; P.mode = 3;
   P.y_out = d_y.as<double>(); P.dy_out = d_dy.as<double>(); P.power_idx = -1;
+  P.d_kmodes = d_kmodes ? d_dk.as<double>() : nullptr;
   double* lt_small = (double*)((char*)d_ws.p + 256);
   P.lt_small = lt_small;
   P.rp_tnext = d_rt.as<double>(); P.rp_dtnext = d_rdt.as<double>(); P.rp_keep = d_rk.as<int>(); P.rp_n = d_rn.as<int>();

@@ -116,7 +116,7 @@ DEB_DEV void nu_velocity_g(const CosmoD& c, const NuBins& nb, T a, int i, double
   vv_store<T>(dst, drsqrt(1.0 + aq * aq));
 }
 template <class T>
-DEB_DEV void compute_bg_g(const CosmoD& c, T a, double k, int hint_th, int hint_nu, BgG<T>& b) {
+DEB_DEV void compute_bg_g(const CosmoD& c, T a, Dual kD, int hint_th, int hint_nu, BgG<T>& b) {
   const T loga = dlog(a);
   const T inva = 1.0 / a, inva2 = inva * inva;
   const T grhom = liftD<T>(c.grhom), grhog = liftD<T>(c.grhog), grhor = liftD<T>(c.grhor);
@@ -124,7 +124,8 @@ DEB_DEV void compute_bg_g(const CosmoD& c, T a, double k, int hint_th, int hint_
   const T Neff = liftD<T>(c.Neff), Nmnu = liftD<T>(c.Nmnu);
   b.a = a;
   const T cs2 = spl_eval_g<T>(c.cs2a, loga, hint_th) * inva;
-  b.k2cs2 = (k * k) * cs2;
+  const T kT = liftD<T>(kD);
+  b.k2cs2 = (kT * kT) * cs2;
   const T xe = spl_eval_g<T>(c.xe, loga, hint_th);
   const T rhonu = dexp(spl_eval_g<T>(c.lrn, loga, hint_nu));
   const T rhoq = dexp((-3.0 * (1.0 + w0 + wa)) * loga + 3.0 * wa * (a - 1.0));
@@ -168,7 +169,7 @@ template <class T> DEB_DEV T sget(const StateV0& s, int e) { return lift2<T>(s.v
 template <class T> struct MetricG { T hp, ep, al, f1; };
 template <class T, class St>
 DEB_DEV void compute_metric_g(const Problem& P, const CosmoD& c, const NuBins& nb, const BgG<T>& b, const double* vvs, const St& u,
-                              double k, MetricG<T>& mt) {
+                              Dual kD, MetricG<T>& mt) {
   const int nq = P.nq, iq0 = P.iq0, n = P.n;
   const T eta = sget<T>(u, 2), dc = sget<T>(u, 3), tc = sget<T>(u, 4), db = sget<T>(u, 5), tb = sget<T>(u, 6);
   const T dg = sget<T>(u, 7), tg = sget<T>(u, 8), dr = sget<T>(u, P.ir), tr = sget<T>(u, P.ir + 1);
@@ -181,7 +182,7 @@ DEB_DEV void compute_metric_g(const Problem& P, const CosmoD& c, const NuBins& n
     dpnu3 = dpnu3 + p0 * v;
     fnu = fnu + nb.w[i] * sget<T>(u, iq0 + nq + i);
   }
-  const double k2 = k * k, ik2 = 1.0 / k2;
+  const T k = liftD<T>(kD), k2 = k * k, ik2 = 1.0 / k2;
   const T cs2de = liftD<T>(c.cs2de);
   const T rpt = b.wq1 * b.gq * tq;
   const T dgrho = b.gc * dc + b.gb * db + b.gg * dg + b.gr * dr + b.gnu * drhonu + b.gq * dq;
@@ -201,8 +202,8 @@ DEB_DEV void compute_metric_g(const Problem& P, const CosmoD& c, const NuBins& n
 // the warp executed each case in turn -- 112 k warp-instructions per step.)
 // A T lives in shared memory as 4 doubles (value, eps, d/da, d2); Dual uses the first two.
 template <class T>
-DEB_DEV void fill_slots_g(const CosmoD& c, const BgG<T>& b, double k, double* sl) {      // slots 0 .. SL_KV0-1 (one lane)
-  const double k2 = k * k;
+DEB_DEV void fill_slots_g(const CosmoD& c, const BgG<T>& b, Dual kD, double* sl) {      // slots 0 .. SL_KV0-1 (one lane)
+  const T k = liftD<T>(kD), k2 = k * k;
   const T cs2de = liftD<T>(c.cs2de);
   const T one = 0.0 * b.a + 1.0;
   vv_store<T>(sl + 4 * SL_ONE, one); vv_store<T>(sl + 4 * SL_H, b.H); vv_store<T>(sl + 4 * SL_OPAC, b.opac);
@@ -211,12 +212,13 @@ DEB_DEV void fill_slots_g(const CosmoD& c, const BgG<T>& b, double k, double* sl
   vv_store<T>(sl + 4 * SL_DQT, b.wq1 * (cs2de - b.ca2) * (b.H * b.H) * (1.0 / k2));
   vv_store<T>(sl + 4 * SL_TQD, (cs2de * k2) / b.wq1);
   vv_store<T>(sl + 4 * SL_TQT, (1.0 - 3.0 * cs2de) * b.H);
-  vv_store<T>(sl + 4 * SL_K, one * k); vv_store<T>(sl + 4 * SL_K2, one * k2);
+  vv_store<T>(sl + 4 * SL_K, k); vv_store<T>(sl + 4 * SL_K2, k2);
 }
 // per chain: wavenumber k or k v_i, damping opac or 0; lane `ch` < nch.  Also the k v_i slots of the head operator.
 template <class T>
-DEB_DEV void chain_coeffs_g(const BgG<T>& b, const double* vvs, double k, int ch, double* kcs, double* kaps, double* sl) {
-  T kc = 0.0 * b.a + k;
+DEB_DEV void chain_coeffs_g(const BgG<T>& b, const double* vvs, Dual kD, int ch, double* kcs, double* kaps, double* sl) {
+  const T k = liftD<T>(kD);
+  T kc = k;
   if (ch >= 3) { kc = k * vv_load<T>(vvs + 4 * (ch - 3)); vv_store<T>(sl + 4 * (SL_KV0 + ch - 3), kc); }
   vv_store<T>(kcs + 4 * ch, kc);
   vv_store<T>(kaps + 4 * ch, ch < 2 ? b.opac : 0.0 * b.a);
@@ -262,12 +264,12 @@ DEB_DEV Dual cond_small_k_d(const CosmoD& c, Dual lt) {
   const Dual H = aprimeoa_d(c, a);
   return (1.0 / opac) / (1.0 / H) / 0.0004 - 1.0;
 }
-DEB_DEV Dual cond_large_k_d(const CosmoD& c, Dual lt, double k) {
+DEB_DEV Dual cond_large_k_d(const CosmoD& c, Dual lt, Dual k) {
   const Dual a = spl_eval_g<Dual>(c.a_of_tau, dexp(lt));
   return (1.0 / aprimeoa_d(c, a)) / (1.0 / k) / 0.07 - 1.0;
 }
 // bisection of util.py:365-396: the branches are decided on primal values, the end points carry tangents
-DEB_DEV Dual start_time_d(const CosmoD& c, double k) {
+DEB_DEV Dual start_time_d(const CosmoD& c, Dual k) {
   Dual res0 = mk(0.0, 0.0), res1 = mk(0.0, 0.0);
   for (int which = 0; which < 2; ++which) {
     Dual xl = dlog(c.taumin), xr = dlog(spl_eval_g<Dual>(c.tau_of_a, mk(0.1, 0.0)));
@@ -283,7 +285,7 @@ DEB_DEV Dual start_time_d(const CosmoD& c, double k) {
 }
 
 struct IcScalarsD { Dual a, deltag, thetag, deltar, thetar, shearr, deltaq, thetaq, eta; };
-DEB_DEV IcScalarsD ic_scalars_d(const CosmoD& c, Dual tau, double k) {
+DEB_DEV IcScalarsD ic_scalars_d(const CosmoD& c, Dual tau, Dual k) {
   IcScalarsD s;
   const Dual a = spl_eval_g<Dual>(c.a_of_tau, tau);
   const Dual rn = dexp(spl_eval_g<Dual>(c.lrn, dlog(a)));
@@ -309,7 +311,7 @@ DEB_DEV IcScalarsD ic_scalars_d(const CosmoD& c, Dual tau, double k) {
                 * (5.0 + 4.0 * fracnu - (16.0 * fracnu * fracnu + 280.0 * fracnu + 325.0) / 10.0 / (2.0 * fracnu + 15.0) * tau * om));
   return s;
 }
-DEB_DEV Dual ic_value_d(const Problem& P, const CosmoD& c, const NuBins& nb, const IcScalarsD& s, int desc, double k) {
+DEB_DEV Dual ic_value_d(const Problem& P, const CosmoD& c, const NuBins& nb, const IcScalarsD& s, int desc, Dual k) {
   const int type = desc & 0xff, chain = desc >> 16;
   switch (type) {
     case R_A: return s.a;
@@ -336,7 +338,7 @@ DEB_DEV Dual ic_value_d(const Problem& P, const CosmoD& c, const NuBins& nb, con
 }
 
 // ---- epilogue with tangents: 20 output fields (perturbations.py:374-523) and get_power (:1101-1123) ------
-DEB_DEV void convert_outputs_d(const Problem& P, const CosmoD& c, const NuBins& nb, const StateVD& y, double k, Dual* out) {
+DEB_DEV void convert_outputs_d(const Problem& P, const CosmoD& c, const NuBins& nb, const StateVD& y, Dual k, Dual* out) {
   const int nq = P.nq, iq0 = P.iq0, n = P.n;
   const Dual a = sget<Dual>(y, 0), eta = sget<Dual>(y, 2), dc = sget<Dual>(y, 3), tc = sget<Dual>(y, 4), db = sget<Dual>(y, 5);
   const Dual tb = sget<Dual>(y, 6), dg = sget<Dual>(y, 7), tg = sget<Dual>(y, 8);
@@ -363,7 +365,7 @@ DEB_DEV void convert_outputs_d(const Problem& P, const CosmoD& c, const NuBins& 
   const Dual matth = c.grhom * (Omegac * tc + c.Omegab * tb) / a;
   const Dual dgrho = mat + (c.grhog * dg + c.grhor * (c.Neff * dr + c.Nmnu * drhonu)) / a2 + c.grhom * c.OmegaDE * dq * rhoq * a2;
   const Dual dgtheta = matth + 4.0 / 3.0 * (c.grhog * tg + c.Neff * c.grhor * tr) / a2 + c.Nmnu * c.grhor * k * fnu / a2 + rpt;
-  const double k2 = k * k;
+  const Dual k2 = k * k;
   const Dual hp = (2.0 * k2 * eta + dgrho) / H, ep = 0.5 * dgtheta / k2, al = (hp + 6.0 * ep) / 2.0 / k2;
   const Dual deltam = (mat + (c.grhor * c.Nmnu * drhonu) / a2) / (c.grhom * c.Omegam / a + (c.grhor * c.Nmnu * rhonu) / a2);
   Dual thetam = (matth + c.Nmnu * c.grhor * k * fnu / a2) / (3.0 * (c.grhom * c.Omegam / a + c.grhor * c.Nmnu * rhonu / a2));
@@ -375,9 +377,9 @@ DEB_DEV void convert_outputs_d(const Problem& P, const CosmoD& c, const NuBins& 
   out[8] = dc; out[9] = tc / H; out[10] = db; out[11] = tb / H; out[12] = dg; out[13] = tg / H;
   out[14] = dr; out[15] = tr / H; out[16] = deltanu; out[17] = thetanu / H; out[18] = dq; out[19] = tq / H;
 }
-DEB_DEV Dual power_d(const CosmoD& c, double k, Dual yv) {
+DEB_DEV Dual power_d(const CosmoD& c, Dual k, Dual yv) {
   const Dual tilt = dexp((c.ns - 1.0) * dlog(k / c.kp));
-  return (2.0 * 9.869604401089358) * c.As * tilt * pow(k, -3.0) * yv * yv;
+  return (2.0 * 9.869604401089358) * c.As * tilt * (1.0 / (k * k * k)) * yv * yv;
 }
 
 // ---- per-mode tangent workspace (shared memory, carved after the primal workspace) ---------------------
@@ -414,7 +416,7 @@ DEB_DEV void carve_tan(TanWs& T, double* base, int np) {
 //   y/yd  : accepted state and its tangent at (t, td)         u/ud : stage state u_i and its tangent
 //   ki    : k_i of the primal stage (W.r after the primal solve)
 template <class Dummy = void>
-DEB_DEV void tan_stage_rhs(const Problem& P, const CtaConst& C, const WarpWs& W, const TanWs& TW, int st, double k,
+DEB_DEV void tan_stage_rhs(const Problem& P, const CtaConst& C, const WarpWs& W, const TanWs& TW, int st, Dual k,
                            double t, double td, double dt, double ddt, const Hints& hint DEB_LANE_PARAM) {
   const int n = P.n, np = P.np, nq = P.nq, nh = P.nh, nch = P.nch;
   const CosmoD& cd = *TW.cd;

@@ -71,12 +71,12 @@ class Library:
         r.restype = C.c_int
         self._debug_replay = r
         tg = getattr(self.lib, prefix + "evolve_tangent_host_f64")
-        tg.argtypes = [C.POINTER(DebDims), C.POINTER(DebCtrl)] + [_dp] * 12 + [_ip, _ip, _ip] + \
+        tg.argtypes = [C.POINTER(DebDims), C.POINTER(DebCtrl)] + [_dp] * 13 + [_ip, _ip, _ip] + \
             ([C.c_int32, C.POINTER(C.c_float)] if prefix == "deb_" else [])
         tg.restype = C.c_int
         self._evolve_tangent_host = tg
         rt = getattr(self.lib, prefix + "debug_replay_tangent_host_f64")
-        rt.argtypes = [C.POINTER(DebDims), C.POINTER(DebCtrl)] + [_dp] * 8 + [_ip, _ip, C.c_int32, _dp, _dp, _dp, _ip] + \
+        rt.argtypes = [C.POINTER(DebDims), C.POINTER(DebCtrl)] + [_dp] * 9 + [_ip, _ip, C.c_int32, _dp, _dp, _dp, _ip] + \
             ([C.c_int32] if prefix == "deb_" else [])
         rt.restype = C.c_int
         self._debug_replay_tangent = rt
@@ -135,21 +135,26 @@ class Library:
         return dict(y=y, pk=pk, tau_out=tau_out, status=status, nsteps=nsteps, naccept=nacc, kernel_ms=kms.value)
 
     def evolve_tangent_host(self, dims: DebDims, ctrl: DebCtrl, scalars, tables, kmodes, aexp_out, d_scalars, d_tables,
-                            device: int = 0, want_pk: bool = False):
-        """Primal + ``dims.ntan`` forward tangents; d_scalars [ntan, nc, NSCAL], d_tables [ntan, nc, tl]."""
+                            device: int = 0, want_pk: bool = False, d_kmodes=None):
+        """Primal + ``dims.ntan`` forward tangents; d_scalars [ntan, nc, NSCAL], d_tables [ntan, nc, tl],
+        optional d_kmodes [ntan] + kmodes.shape."""
         nc, nk, nout, nt = dims.ncosmo, dims.nk, dims.nout, dims.ntan
         nf = self.nvar(dims.lmaxg, dims.lmaxgp, dims.lmaxr, dims.lmaxnu, dims.nqmax) if dims.return_full else 20
         f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
         scalars, tables, kmodes, aexp_out, d_scalars, d_tables = map(f64, (scalars, tables, kmodes, aexp_out, d_scalars, d_tables))
         if d_scalars.shape != (nt,) + scalars.shape or d_tables.shape != (nt,) + tables.shape:
             raise ValueError("tangent seeds must have the primal shapes with a leading [ntan] axis")
+        if d_kmodes is not None:
+            d_kmodes = f64(d_kmodes)
+            if d_kmodes.shape != (nt,) + kmodes.shape:
+                raise ValueError("d_kmodes must have the shape of kmodes with a leading [ntan] axis")
         y = np.zeros((nc, nk, nout, nf)); dy = np.zeros((nt, nc, nk, nout, nf))
         pk = np.zeros((nc, nk, nout)) if want_pk else None
         dpk = np.zeros((nt, nc, nk, nout)) if want_pk else None
         tau_out = np.zeros((nc, nout)); dtau_out = np.zeros((nt, nc, nout))
         status = np.zeros((nc, nk), dtype=np.int32); nsteps = np.zeros((nc, nk), dtype=np.int32); nacc = np.zeros((nc, nk), dtype=np.int32)
         args = [C.byref(dims), C.byref(ctrl), _d(scalars), _d(tables), _d(kmodes), _d(aexp_out), _d(d_scalars), _d(d_tables),
-                _d(y), _d(dy), _d(pk), _d(dpk), _d(tau_out), _d(dtau_out), _i(status), _i(nsteps), _i(nacc)]
+                _d(d_kmodes), _d(y), _d(dy), _d(pk), _d(dpk), _d(tau_out), _d(dtau_out), _i(status), _i(nsteps), _i(nacc)]
         kms = C.c_float(0.0)
         if self.prefix == "deb_":
             args += [C.c_int32(device), C.byref(kms)]
@@ -158,7 +163,7 @@ class Library:
                     kernel_ms=kms.value)
 
     def debug_replay_tangent(self, dims: DebDims, ctrl: DebCtrl, scalars, tables, kmodes, aexp_out, d_scalars, d_tables,
-                             rp_tnext, rp_dtnext, rp_keep, rp_n, device: int = 0):
+                             rp_tnext, rp_dtnext, rp_keep, rp_n, device: int = 0, d_kmodes=None):
         nt = dims.ntan
         nf = self.nvar(dims.lmaxg, dims.lmaxgp, dims.lmaxr, dims.lmaxnu, dims.nqmax) if dims.return_full else 20
         f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
@@ -169,7 +174,8 @@ class Library:
         dtau = np.zeros((nt, dims.ncosmo, dims.nout))
         ns = np.zeros((dims.ncosmo, dims.nk), dtype=np.int32)
         args = [C.byref(dims), C.byref(ctrl), _d(f64(scalars)), _d(f64(tables)), _d(f64(kmodes)), _d(f64(aexp_out)),
-                _d(f64(d_scalars)), _d(f64(d_tables)), _d(rp_tnext), _d(rp_dtnext), _i(rp_keep), _i(rp_n),
+                _d(f64(d_scalars)), _d(f64(d_tables)), _d(None if d_kmodes is None else f64(d_kmodes)), _d(rp_tnext), _d(rp_dtnext),
+                _i(rp_keep), _i(rp_n),
                 C.c_int32(rp_tnext.shape[-1]), _d(y), _d(dy), _d(dtau), _i(ns)]
         if self.prefix == "deb_":
             args.append(C.c_int32(device))

@@ -145,7 +145,7 @@ def evolve_perturbations_jvp(*, param, dparam, aexp_out, kmin: float, kmax: floa
                              pcoeff: float = 0.25, icoeff: float = 0.80, dcoeff: float = 0.0,
                              factormax: float = 20.0, factormin: float = 0.3, max_steps: int = 2048,
                              return_full: bool = False, dologk: bool = True, device: int = 0, throw: bool = True,
-                             power_idx: int = -1):
+                             power_idx: int = -1, dkmin=0.0, dkmax=0.0):
     """Forward-mode derivative of ``evolve_perturbations`` -- what ``jax.jvp(evolve_perturbations, (param,),
     (dparam,))`` / ``jax.jacfwd`` returns in the reference (minimal notebook cell 14, Fisher notebook cell 7):
     the exact tangent of the discrete solve, computed by the tangent kernel in the same launch.
@@ -155,7 +155,9 @@ def evolve_perturbations_jvp(*, param, dparam, aexp_out, kmin: float, kmax: floa
     Jacobian).  Returns ``(y, dy, kmodes, info)``: ``dy`` has the shape of ``y`` (one dict) or a leading axis
     over directions; ``info`` holds ``tau_out, dtau_out, status, nsteps, naccept, kernel_ms`` and, with
     ``power_idx >= 0``, ``pk`` / ``dpk`` (``get_power`` and its tangent, A_s / n_s / k_p seeds included).
-    ``param`` receives the same side effects as in ``evolve_perturbations``."""
+    ``dkmin`` / ``dkmax`` (a float, or one per direction) are the tangents of ``kmin`` / ``kmax`` for callers whose
+    k grid moves with a parameter (k in units of h: ``nb_discoeb_rsd_eyes_plot.ipynb`` cell 5); the tangent of the
+    ``geomspace`` / ``linspace`` grid follows.  ``param`` receives the same side effects as in ``evolve_perturbations``."""
     single = isinstance(dparam, dict)
     dlist = [dparam] if single else list(dparam)
     if not dlist:
@@ -174,8 +176,17 @@ def evolve_perturbations_jvp(*, param, dparam, aexp_out, kmin: float, kmax: floa
                            ntan=len(dlist))
     ctrl = _cabi.make_ctrl(rtol=rtol, atol=atol, pcoeff=pcoeff, icoeff=icoeff, dcoeff=dcoeff, factormax=factormax,
                            factormin=factormin)
+    d_kmodes = None
+    dkmin = np.broadcast_to(np.asarray(dkmin, dtype=np.float64), (len(dlist),))
+    dkmax = np.broadcast_to(np.asarray(dkmax, dtype=np.float64), (len(dlist),))
+    if np.any(dkmin != 0.0) or np.any(dkmax != 0.0):
+        f = np.linspace(0.0, 1.0, num_k)
+        if dologk:      # log k_i = (1 - f_i) log kmin + f_i log kmax
+            d_kmodes = kmodes[None, :] * ((1.0 - f)[None, :] * (dkmin / kmin)[:, None] + f[None, :] * (dkmax / kmax)[:, None])
+        else:
+            d_kmodes = (1.0 - f)[None, :] * dkmin[:, None] + f[None, :] * dkmax[:, None]
     out = lib.evolve_tangent_host(dims, ctrl, scalars, tables, kmodes, aexp_out, d_scalars, d_tables, device=device,
-                                  want_pk=power_idx >= 0)
+                                  want_pk=power_idx >= 0, d_kmodes=d_kmodes)
     _check_status(out["status"], out["nsteps"], max_steps, throw)
     param["lmaxg"], param["lmaxgp"], param["lmaxr"], param["lmaxnu"], param["nqmax"] = lmaxg, lmaxgp, lmaxr, lmaxnu, nqmax
     param["nout"] = out["tau_out"].shape[1]

@@ -115,11 +115,14 @@ int deb_evolve_f64(const deb_dims* dims, const deb_ctrl* ctrl,
  * spline intervals and bisection branches follow the primal run (diffrax semantics):
  *   dy_out   [ntan, ncosmo, nk, nout, 20|n]   dpk_out [ntan, ncosmo, nk, nout] or NULL
  *   dtau_out [ntan, ncosmo, nout]             tangent of tau_of_a(aexp_out)
- * The primal outputs are those of deb_evolve_f64 for the same step sequence.  kmodes and
- * aexp_out carry no tangent.  With ntan == 0 this is deb_evolve_f64. */
+ * d_kmodes [ntan, nk] (or [ntan, ncosmo, nk] with k_per_cosmo) is the tangent of the wavenumbers
+ * themselves, for callers whose k grid depends on a parameter (kmin, kmax scaled by h); NULL = 0.
+ * The primal outputs are those of deb_evolve_f64 for the same step sequence.  aexp_out carries
+ * no tangent.  With ntan == 0 this is deb_evolve_f64. */
 int deb_evolve_tangent_f64(const deb_dims* dims, const deb_ctrl* ctrl,
                            const double* scalars, const double* tables, const double* kmodes,
                            const double* aexp_out, const double* d_scalars, const double* d_tables,
+                           const double* d_kmodes,
                            double* y_out, double* dy_out, double* pk_out, double* dpk_out,
                            double* tau_out, double* dtau_out,
                            int32_t* status, int32_t* nsteps, int32_t* naccept,
@@ -154,12 +157,14 @@ void deb_host_cache_release(void);
 int deb_ctx_evolve_tangent_host_f64(deb_ctx* ctx, const deb_dims* dims, const deb_ctrl* ctrl,
                                     const double* scalars, const double* tables, const double* kmodes,
                                     const double* aexp_out, const double* d_scalars, const double* d_tables,
+                                    const double* d_kmodes,
                                     double* y_out, double* dy_out, double* pk_out, double* dpk_out,
                                     double* tau_out, double* dtau_out,
                                     int32_t* status, int32_t* nsteps, int32_t* naccept, float* kernel_ms);
 int deb_evolve_tangent_host_f64(const deb_dims* dims, const deb_ctrl* ctrl,
                                 const double* scalars, const double* tables, const double* kmodes,
                                 const double* aexp_out, const double* d_scalars, const double* d_tables,
+                                const double* d_kmodes,
                                 double* y_out, double* dy_out, double* pk_out, double* dpk_out,
                                 double* tau_out, double* dtau_out,
                                 int32_t* status, int32_t* nsteps, int32_t* naccept,
@@ -193,7 +198,7 @@ int deb_debug_replay_host_f64(const deb_dims* dims, const deb_ctrl* ctrl, const 
  * [ntan, ncosmo*nk, rp_stride] holds the tangent of every prescribed step end. */
 int deb_debug_replay_tangent_host_f64(const deb_dims* dims, const deb_ctrl* ctrl, const double* scalars,
                                       const double* tables, const double* kmodes, const double* aexp_out,
-                                      const double* d_scalars, const double* d_tables,
+                                      const double* d_scalars, const double* d_tables, const double* d_kmodes,
                                       const double* rp_tnext, const double* rp_dtnext,
                                       const int32_t* rp_keep, const int32_t* rp_n, int32_t rp_stride,
                                       double* y_out, double* dy_out, double* dtau_out, int32_t* nsteps,

@@ -594,7 +594,7 @@ def _bisect(func, xl, xr, numit):
 
 def determine_starting_time(p, k):
     """perturbations.py:630-681."""
-    k = np.asarray(k, dtype=np.float64)
+    k = np.asarray(k, dtype=np.result_type(np.asarray(k).dtype, np.float64))      # (complex under the tangent oracle)
     tau0 = p["taumin"]
     tau1 = p["tau_of_a_spline"].evaluate(0.1)
     tau_k = 1.0 / k

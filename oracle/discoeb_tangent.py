@@ -99,7 +99,7 @@ def integrate_modes_cs(t0, t1, y0, ts, p, k, d, rtol, atol, pcoeff=0.25, icoeff=
         with np.errstate(all="ignore"):
             y1, err = O.rodas5_step(tp, tn, ya, p, ka, d)
             errr = np.where(np.isnan(np.real(err)), np.inf, np.real(err))
-            E = O.scaled_error_norm(np.real(ya), np.real(y1), errr, ka, rtol, atol)
+            E = O.scaled_error_norm(np.real(ya), np.real(y1), errr, np.real(ka), rtol, atol)
             if replay is None:
                 keep = E < 1
                 inv = 1.0 / E
@@ -139,7 +139,7 @@ def integrate_modes_cs(t0, t1, y0, ts, p, k, d, rtol, atol, pcoeff=0.25, icoeff=
     return ys, status, nsteps, nacc
 
 
-def evolve_perturbations_jvp(*, param, dparam, aexp_out, kmodes, lmaxg=11, lmaxgp=11, lmaxr=11, lmaxnu=8, nqmax=3,
+def evolve_perturbations_jvp(*, param, dparam, aexp_out, kmodes, dkmodes=None, lmaxg=11, lmaxgp=11, lmaxr=11, lmaxnu=8, nqmax=3,
                              rtol=1e-4, atol=1e-4, pcoeff=0.25, icoeff=0.80, dcoeff=0.0, factormax=20.0, factormin=0.3,
                              max_steps=2048, h=H_CS, replay=None):
     """Primal and tangent of ``evolve_perturbations`` (perturbations.py:926-997) along ``dparam``.
@@ -149,7 +149,9 @@ def evolve_perturbations_jvp(*, param, dparam, aexp_out, kmodes, lmaxg=11, lmaxg
     dtau_start``; ``y0, dy0``; the step trace ``rp_tnext, rp_dtnext, rp_keep, rp_fac`` [M, S]; ``nsteps``,
     ``naccept``."""
     pc = complexify(param, dparam, h)
-    kmodes = np.asarray(kmodes, dtype=np.float64)
+    kreal = np.asarray(kmodes, dtype=np.float64)
+    # tangent of the wavenumbers themselves (callers that scale kmin/kmax by h: nb_discoeb_rsd_eyes_plot.ipynb cell 5)
+    kmodes = kreal if dkmodes is None else kreal + 1j * h * np.asarray(dkmodes, dtype=np.float64)
     aexp_out = np.atleast_1d(np.asarray(aexp_out, dtype=np.float64))
     d = O.Dims(lmaxg, lmaxgp, lmaxr, lmaxnu, nqmax)
     tau_out = pc["tau_of_a_spline"].evaluate(aexp_out)
@@ -175,7 +177,7 @@ def evolve_perturbations_jvp(*, param, dparam, aexp_out, kmodes, lmaxg=11, lmaxg
         rp_f[act, cnt[act]] = fac
         cnt[act] += 1
     y20 = O.convert_to_output(ys, pc, kmodes[:, None], d)
-    out = dict(kmodes=kmodes, aexp_out=aexp_out, nsteps=ns.astype(np.int32), naccept=na.astype(np.int32),
+    out = dict(kmodes=kreal, aexp_out=aexp_out, nsteps=ns.astype(np.int32), naccept=na.astype(np.int32),
                rp_tnext=rp_t.real.copy(), rp_dtnext=rp_t.imag / h, rp_keep=rp_k, rp_fac=rp_f)
     for name, z in (("y", y20), ("yfull", ys), ("tau_out", tau_out), ("tau_start", tau_start), ("y0", y0)):
         out[name] = np.real(z).copy()

@@ -165,7 +165,8 @@ extern "C" int emu_debug_replay_host_f64(const deb_dims* dims, const deb_ctrl* c
 
 extern "C" int emu_evolve_tangent_host_f64(const deb_dims* dims, const deb_ctrl* ctrl, const double* scalars,
                                            const double* tables, const double* kmodes, const double* aexp_out,
-                                           const double* d_scalars, const double* d_tables, double* y_out, double* dy_out,
+                                           const double* d_scalars, const double* d_tables, const double* d_kmodes,
+                                           double* y_out, double* dy_out,
                                            double* pk_out, double* dpk_out, double* tau_out, double* dtau_out,
                                            int32_t* status, int32_t* nsteps, int32_t* naccept) {
   Problem P;
@@ -174,6 +175,7 @@ extern "C" int emu_evolve_tangent_host_f64(const deb_dims* dims, const deb_ctrl*
   if (P.ntan < 1) return DEB_E_ARG;
   P.scalars = scalars; P.tables = tables; P.kmodes = kmodes; P.aexp_out = aexp_out; P.d_scalars = d_scalars; P.d_tables = d_tables;
   P.y_out = y_out; P.dy_out = dy_out; P.pk_out = pk_out; P.dpk_out = dpk_out; P.status = status; P.nsteps = nsteps; P.naccept = naccept;
+  P.d_kmodes = d_kmodes;
   tau_out_host(P, tau_out, dtau_out);
   P.tau_out = tau_out; P.dtau_out = dtau_out;
   P.mode = 0;
@@ -182,7 +184,8 @@ extern "C" int emu_evolve_tangent_host_f64(const deb_dims* dims, const deb_ctrl*
 
 extern "C" int emu_debug_replay_tangent_host_f64(const deb_dims* dims, const deb_ctrl* ctrl, const double* scalars,
                                                  const double* tables, const double* kmodes, const double* aexp_out,
-                                                 const double* d_scalars, const double* d_tables, const double* rp_tnext,
+                                                 const double* d_scalars, const double* d_tables, const double* d_kmodes,
+                                                 const double* rp_tnext,
                                                  const double* rp_dtnext, const int32_t* rp_keep, const int32_t* rp_n,
                                                  int32_t rp_stride, double* y_out, double* dy_out, double* dtau_out,
                                                  int32_t* nsteps) {
@@ -197,6 +200,7 @@ extern "C" int emu_debug_replay_tangent_host_f64(const deb_dims* dims, const deb
   tau_out_host(P, tau_out.data(), dtau.data());
   P.tau_out = tau_out.data(); P.dtau_out = dtau.data();
   P.status = st.data(); P.nsteps = nsteps; P.naccept = nullptr; P.y_out = y_out; P.dy_out = dy_out; P.power_idx = -1;
+  P.d_kmodes = d_kmodes;
   P.rp_tnext = rp_tnext; P.rp_dtnext = rp_dtnext; P.rp_keep = rp_keep; P.rp_n = rp_n; P.rp_stride = rp_stride;
   P.mode = 3;
   rc = dispatch_tan(P);

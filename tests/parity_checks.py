@@ -103,7 +103,7 @@ def check_adaptive(lib, tables, name):
 # tools/make_golden_tangent.py).  Bars: replay of the oracle's step sequence 1e-6 (north_star: 1e-5) of each
 # field's tangent scale; free-running, modes whose step counts equal the oracle's: 1e-5 for <= 100 steps.
 # ---------------------------------------------------------------------------------------------------
-TANGENT_CASES = ("default_n72", "w0wa_n43", "fisher_n265")
+TANGENT_CASES = ("default_n72", "w0wa_n43", "fisher_n265", "kscaled_n72")
 
 
 def load_tangent_case(name):
@@ -143,7 +143,7 @@ def check_tangent_replay(lib, name, tol=1e-6):
         dims = tangent_dims(case, return_full=full)
         y, dy, dtau, ns = lib.debug_replay_tangent(dims, ctrl, case["scalars"][None], case["tables"][None], ks, aout,
                                                    case["d_scalars"][:, None], case["d_tables"][:, None], case["rp_tnext"],
-                                                   case["rp_dtnext"], case["rp_keep"], case["nsteps"])
+                                                   case["rp_dtnext"], case["rp_keep"], case["nsteps"], d_kmodes=case.get("d_kmodes"))
         assert np.array_equal(ns[0], case["nsteps"])
         np.testing.assert_allclose(dtau[:, 0], case["dtau_out"], rtol=1e-9, atol=1e-9 * np.abs(case["dtau_out"]).max() + 1e-300)
         ref, dref = (case["yfull"], case["dyfull"]) if full else (case["y"], case["dy"])
@@ -167,7 +167,7 @@ def check_tangent_adaptive(lib, name):
     dims = tangent_dims(case, power_idx=4)
     ctrl = _cabi.make_ctrl(rtol=rtol, atol=rtol)
     out = lib.evolve_tangent_host(dims, ctrl, case["scalars"][None], case["tables"][None], ks, aout, case["d_scalars"][:, None],
-                                  case["d_tables"][:, None], want_pk=True)
+                                  case["d_tables"][:, None], want_pk=True, d_kmodes=case.get("d_kmodes"))
     assert np.all(out["status"] == 0)
     np.testing.assert_allclose(out["tau_out"][0], case["tau_out"], rtol=1e-13)
     # the primal half must be what the primal entry returns for the same inputs (same kernel code path modulo the

@@ -16,7 +16,7 @@ def test_tangent_replay_of_oracle_step_sequence(gpu_lib, name):
     print(name, "worst scaled tangent deviation", worst)
 
 
-@pytest.mark.parametrize("name", ("default_n72", "w0wa_n43"))
+@pytest.mark.parametrize("name", ("default_n72", "w0wa_n43", "kscaled_n72"))
 def test_tangent_adaptive_against_oracle(gpu_lib, name):
     pc.check_tangent_adaptive(gpu_lib, name)
 

@@ -76,7 +76,7 @@ def test_kernel_source_tangent_replay(emu_lib, name):
     print(name, "worst scaled tangent deviation", worst)
 
 
-@pytest.mark.parametrize("name", ("default_n72", "w0wa_n43"))
+@pytest.mark.parametrize("name", ("default_n72", "w0wa_n43", "kscaled_n72"))
 def test_kernel_source_tangent_adaptive(emu_lib, name):
     pc.check_tangent_adaptive(emu_lib, name)
 

@@ -64,7 +64,11 @@ CASES = {
     "w0wa_n43": (dict(w_DE_0=-0.9, w_DE_a=0.1), (5, 4, 6, 3, 4), [2e-3, 0.2], [0.5], 1e-3, ("w_DE_a", "Omegab")),
     "fisher_n265": ({}, (31, 31, 31, 31, 5), [0.01, 0.3], [0.5, 1.0], 1e-4, ("Omegam",)),
     "fisher_n265x2": ({}, (31, 31, 31, 31, 5), [0.02], [0.5, 1.0], 1e-4, ("Omegab", "H0")),      # seeds for the full-size property test
+    # wavenumbers that move with the parameter (k = const x h, nb_discoeb_rsd_eyes_plot.ipynb cell 5): d k / d H0 = k / H0;
+    # the second direction moves k alone (all other seeds zero)
+    "kscaled_n72": ({}, (11, 11, 11, 8, 3), [2e-3, 0.1], [0.3, 1.0], 1e-4, ("H0", "n_s")),
 }
+DKMODES = {"kscaled_n72": lambda ks, p: np.stack([ks / p["H0"], ks])}
 KEEP = ("y", "dy", "yfull", "dyfull", "pk4", "dpk4", "tau_out", "dtau_out", "tau_start", "dtau_start", "y0", "dy0",
         "rp_tnext", "rp_dtnext", "rp_keep", "nsteps", "naccept")
 
@@ -78,13 +82,18 @@ def main():
         ks = np.asarray(ks, dtype=np.float64)
         outs, dscal, dtab = [], [], []
         replay = None
-        for key in dirs:
+        dks = None
+        for idir, key in enumerate(dirs):
             p, dp = param_tangent(key, **over)
+            if name in DKMODES:
+                dks = DKMODES[name](ks, p)
+                if key == "n_s":
+                    dp["n_s"] = 0.0            # a pure wavenumber direction
             # direction 0 runs the controller; the others follow its decisions (the real part of a complex run carries
             # direction-dependent round-off, and the controller is chaotic under round-off -- DESIGN.md "Parity")
             out = T.evolve_perturbations_jvp(param=p, dparam=dp, aexp_out=aout, kmodes=ks, rtol=rtol, atol=rtol,
                                              lmaxg=dims[0], lmaxgp=dims[1], lmaxr=dims[2], lmaxnu=dims[3], nqmax=dims[4],
-                                             max_steps=4096, replay=replay)
+                                             max_steps=4096, replay=replay, dkmodes=None if dks is None else dks[idir])
             if replay is None:
                 replay = (out["rp_keep"], out["rp_fac"], out["nsteps"])
             outs.append(out)
@@ -97,6 +106,8 @@ def main():
         save = dict(scalars=scal, tables=tab, nth=nth, nnu=nnu, d_scalars=np.stack(dscal), d_tables=np.stack(dtab),
                     kmodes=ks, aexp_out=np.asarray(aout, dtype=np.float64), dims=np.array(dims), rtol=rtol,
                     directions=np.array(dirs))
+        if dks is not None:
+            save["d_kmodes"] = dks
         for f in KEEP:
             if f.startswith("d") or f == "rp_dtnext":
                 save[f] = np.stack([o[f] for o in outs])
