@@ -785,6 +785,7 @@ DEB_DEV double start_time(const Cosmo& c, double k, double lt_small) {
     if (fm * fl > 0) { xl = xm; fl = fm; } else xr = xm;
   }
   const double lt_large = 0.5 * (xl + xr);
+  if (!(lt_small == lt_small) || !(lt_large == lt_large)) return NAN;
   return exp(fmin(lt_small, lt_large));
 }
 
@@ -1024,6 +1025,7 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, Help
   } else {
     const double st0 = start_time(c, k, DEB_LDG(P.lt_small + cosmo));
     double tau_start = 0.99 * fmin(tmin_out, st0);
+    if (!(st0 == st0)) tau_start = st0;
     IcScalars ics = ic_scalars(c, tau_start, k);
     DEB_LANES_BEGIN
       for (int e = lane; e < n; e += 32) W.y()[e] = ic_value(P, c, nb, ics, elem_desc(P, e), k);
@@ -1051,6 +1053,9 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, Help
 
   double inv_prev = 1.0, inv_pprev = 1.0;
   int nsteps = 0, nacc = 0, save_idx = 0, status = 0;
+  // a non-finite start (NaN in taumin or in the tables) must fail like the reference's NaN-propagating jnp.minimum,
+  // not be swallowed by fmin
+  if (!(t == t) || !(tnext == tnext) || !(t1 == t1)) status = 2;
   Hints hint; hint.th = -1; hint.nu = -1;
 
   while (t < t1 && nsteps < P.max_steps && status == 0) {

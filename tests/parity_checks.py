@@ -241,3 +241,42 @@ def check_tangent_batch_of_cosmologies(lib, nk=6):
                 np.testing.assert_array_equal(one["dtau_out"][0, 0], out["dtau_out"][d, c])
                 if not full:
                     np.testing.assert_array_equal(one["dpk"][0, 0], out["dpk"][d, c])
+
+
+def check_edge_shapes(lib, tables):
+    """Shapes the golden cases do not cover: the largest supported hierarchy (n = 337, 11 elements per lane), four
+    momentum bins, a single mode with a single output, and a non-finite input (status 2, as diffrax's non-finite result)."""
+    tab = tables["fiducial"]
+    p = tab.param()
+    for dims5 in ((40, 40, 40, 40, 5), (12, 9, 10, 7, 4)):
+        d = O.Dims(*dims5)
+        M = 4
+        ks = np.geomspace(2e-3, 2.0, M)
+        rng = np.random.default_rng(3)
+        t0 = np.array([3.0, 40.0, 300.0, 5000.0])
+        t1 = t0 * 1.03
+        y = rng.normal(size=(M, d.n))
+        y[:, 0] = p["a_of_tau_spline"].evaluate(t0)
+        dims = _cabi.make_dims(ncosmo=1, nk=M, nout=1, lmaxg=dims5[0], lmaxgp=dims5[1], lmaxr=dims5[2], lmaxnu=dims5[3],
+                               nqmax=dims5[4], nth=tab.nth, nnu=tab.nnu, max_steps=4096)
+        y1, err = lib.debug_step(dims, tab.scalars, tab.tables, ks, t0, t1, y)
+        y1o, erro = O.rodas5_step(t0, t1, y, p, ks, d)
+        assert (np.abs(y1 - y1o) / np.abs(y1o).max(axis=1, keepdims=True)).max() < 1e-7, dims5
+    # one mode, one output, largest hierarchy, free-running
+    dims = _cabi.make_dims(ncosmo=1, nk=1, nout=1, lmaxg=40, lmaxgp=40, lmaxr=40, lmaxnu=40, nqmax=5, nth=tab.nth, nnu=tab.nnu,
+                           max_steps=4096, power_idx=4)
+    ctrl = _cabi.make_ctrl(rtol=1e-4, atol=1e-4)
+    out = lib.evolve_host(dims, ctrl, tab.scalars[None], tab.tables[None], np.array([0.02]), np.array([1.0]), want_pk=True)
+    assert out["status"][0, 0] == 0 and out["y"].shape == (1, 1, 1, 20) and out["pk"][0, 0, 0] > 0
+    dims31 = _cabi.make_dims(ncosmo=1, nk=1, nout=1, lmaxg=31, lmaxgp=31, lmaxr=31, lmaxnu=31, nqmax=5, nth=tab.nth, nnu=tab.nnu,
+                             max_steps=4096, power_idx=4)
+    out31 = lib.evolve_host(dims31, ctrl, tab.scalars[None], tab.tables[None], np.array([0.02]), np.array([1.0]), want_pk=True)
+    assert abs(out["pk"][0, 0, 0] / out31["pk"][0, 0, 0] - 1) < 1e-3          # the cut-off does not matter at k = 0.02
+    # non-finite input
+    dims = _cabi.make_dims(ncosmo=1, nk=2, nout=1, lmaxg=11, lmaxgp=11, lmaxr=11, lmaxnu=8, nqmax=3, nth=tab.nth, nnu=tab.nnu,
+                           max_steps=256)
+    for idx in (4, 15):                                                      # grhom (every coefficient), taumin (the start time)
+        bad = tab.scalars.copy()
+        bad[idx] = np.nan
+        outb = lib.evolve_host(dims, ctrl, bad[None], tab.tables[None], np.array([0.01, 0.1]), np.array([1.0]))
+        assert np.all(outb["status"] != 0), idx

@@ -144,3 +144,7 @@ def test_batch_of_cosmologies(gpu_lib, tables):
     for i, p in enumerate(ps):
         yi, _, _ = evolve_perturbations(param=p, aexp_out=[0.5, 1.0], kmin=1e-3, kmax=1.0, num_k=16)
         assert np.array_equal(yi, y[i])
+
+
+def test_edge_shapes(gpu_lib, tables):
+    pc.check_edge_shapes(gpu_lib, tables)

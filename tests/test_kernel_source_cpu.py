@@ -115,3 +115,7 @@ def test_two_warp_variant_source(emu_lib, tables, name, monkeypatch):
     for m in np.nonzero(same[0])[0]:
         if one["nsteps"][0, m] <= 100:
             assert helpers.field_scaled_diff(two["y"][0, m], one["y"][0, m]).max() < 1e-6
+
+
+def test_edge_shapes(emu_lib, tables):
+    pc.check_edge_shapes(emu_lib, tables)
