@@ -259,6 +259,7 @@ struct Problem {
   const double* rp_tnext; const int* rp_keep; const int* rp_n; int rp_stride;
   int mode;                                      // 0 evolve, 1 single step, 2 prologue only, 3 replay
   unsigned int* ticket;                          // work-queue counter
+  int batch_size;                                // > 0: shared-step batches of this many consecutive modes (Rodas5Batched)
   // forward tangents (deb_tangent.cuh): ntan directions, seeds laid out like the primal inputs with a leading [ntan]
   int ntan;
   const double* d_scalars; const double* d_tables;
@@ -947,15 +948,81 @@ DEB_DEV void helper_loop(const Problem& P, const CtaConst& C, WarpWs& W, HelpBox
 }
 #endif
 
+// ---------------------------------------------------------------------------------------------
+// Batched variant (ode_integrators_stiff.py:846-1010 Rodas5Batched, perturbations.py:786-922): the modes of a batch
+// advance with ONE adaptive step size.  Every mode still runs on its own warp; what the batch shares is (i) the start
+// time (the smallest of its modes') and (ii) per attempted step the error norm, an RMS over all B x 6 filtered
+// components.  Both are all-to-all exchanges of one double per mode: lane 0 of every warp writes its slot, a barrier,
+// every warp reads all B slots (lane i <- slot i) and reduces them with the same butterfly, so that all warps of
+// the batch hold bit-identical values and take identical accept/reject decisions.  A batch is bw warps per CTA
+// x ncta CTAs of one thread-block cluster (8 warps per CTA is what the register file allows); remote slots are read
+// through distributed shared memory, the barrier is the cluster's.
+// ---------------------------------------------------------------------------------------------
+struct BatchCtx {
+  double* slots;        // this CTA's [2][bw][2] doubles (double-buffered by `parity`): value, flag
+  int bw, ncta, B;      // warps per CTA, CTAs per batch, modes per batch
+  int idx;              // this warp's position in the batch
+  int parity;
+#ifdef DEB_CPU_EMU
+  double* all;          // emulation: one array [2][B][2] shared by the B threads that play the warps
+#endif
+};
+enum { BATCH_SUM = 0, BATCH_MIN = 1 };
+#ifdef DEB_CPU_EMU
+inline void batch_exchange(BatchCtx& bc, double v, double f, int op, double* out_v, double* out_f) {
+  double* buf = bc.all + (size_t)bc.parity * bc.B * 2;
+  buf[2 * bc.idx] = v; buf[2 * bc.idx + 1] = f;
+#pragma omp barrier
+  // the butterfly of the device code: pairwise tree over 32 lanes (missing lanes hold the neutral element)
+  double x[32], g[32];
+  for (int i = 0; i < 32; ++i) { x[i] = i < bc.B ? buf[2 * i] : (op == BATCH_MIN ? INFINITY : 0.0); g[i] = i < bc.B ? buf[2 * i + 1] : 0.0; }
+  for (int o = 16; o > 0; o >>= 1)
+    for (int i = 0; i < 32; ++i) if ((i & o) == 0) {
+      const double a = x[i], b = x[i ^ o];
+      const double r = op == BATCH_MIN ? ((a != a || b != b) ? NAN : fmin(a, b)) : a + b;
+      x[i] = x[i ^ o] = r;
+      const double h = g[i] + g[i ^ o]; g[i] = g[i ^ o] = h;
+    }
+  *out_v = x[0]; *out_f = g[0];
+  bc.parity ^= 1;
+}
+#else
+}  // namespace deb
+#include <cooperative_groups.h>
+namespace deb {
+__device__ __forceinline__ void batch_exchange(BatchCtx& bc, double v, double f, int op, double* out_v, double* out_f) {
+  namespace cg = cooperative_groups;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* mine = bc.slots + ((size_t)bc.parity * bc.bw + warp) * 2;
+  if (lane == 0) { mine[0] = v; mine[1] = f; }
+  if (bc.ncta > 1) cg::this_cluster().sync(); else __syncthreads();
+  double x = op == BATCH_MIN ? INFINITY : 0.0, g = 0.0;
+  if (lane < bc.B) {
+    const int cta = lane / bc.bw, w = lane - cta * bc.bw;
+    const double* src = bc.slots + ((size_t)bc.parity * bc.bw + w) * 2;
+    if (bc.ncta > 1) src = cg::this_cluster().map_shared_rank(const_cast<double*>(src), cta);
+    x = src[0]; g = src[1];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double b = __shfl_xor_sync(0xffffffffu, x, o), h = __shfl_xor_sync(0xffffffffu, g, o);
+    x = op == BATCH_MIN ? ((x != x || b != b) ? NAN : fmin(x, b)) : x + b;
+    g += h;
+  }
+  *out_v = x; *out_f = g;
+  bc.parity ^= 1;       // the other buffer next time: nobody can still be reading it (every warp passed this barrier since)
+}
+#endif
+
 }  // namespace deb
 #include "deb_tangent.cuh"
 namespace deb {
 
 // TAN: also carry one forward tangent (direction `tan` of P.ntan) through the same step sequence; the work
 // item is then (direction, cosmology, k).  TW is the tangent workspace (nullptr otherwise).
-template <int NE, bool HELPER, bool TAN = false>
+template <int NE, bool HELPER, bool TAN = false, bool BATCH = false>
 DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, HelpBox* box, int mode DEB_LANE_PARAM,
-                            const TanWs* TW = nullptr, int tan = 0) {
+                            const TanWs* TW = nullptr, int tan = 0, BatchCtx* BC = nullptr) {
   const int n = P.n, nh = P.nh, nch = P.nch, nq = P.nq;
   const int nhb = nh - 1;            // head unknowns inside diagonal blocks (the last head row is a h')
   const int cosmo = mode / P.nk, kidx = mode - cosmo * P.nk;
@@ -1026,6 +1093,10 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, Help
     const double st0 = start_time(c, k, DEB_LDG(P.lt_small + cosmo));
     double tau_start = 0.99 * fmin(tmin_out, st0);
     if (!(st0 == st0)) tau_start = st0;
+    if (BATCH) {         // the batch starts at the earliest of its modes' start times (perturbations.py:786-805)
+      double fdummy;
+      batch_exchange(*BC, tau_start, 0.0, BATCH_MIN, &tau_start, &fdummy);
+    }
     IcScalars ics = ic_scalars(c, tau_start, k);
     DEB_LANES_BEGIN
       for (int e = lane; e < n; e += 32) W.y()[e] = ic_value(P, c, nb, ics, elem_desc(P, e), k);
@@ -1567,11 +1638,25 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, Help
 
     // ================= error norm, PID controller (diffrax semantics) =================
     {
-      const bool anynan = DEB_ANY(nanflag) != 0;
+      bool anynan = DEB_ANY(nanflag) != 0;
       const double ik2 = DEB_RCP(k2);
 #define DEB_ERRC(e, w) { double y0v = W.y()[e], y1v = anynan ? y0v : W.u()[e], ev = W.r()[e]; if (ev != ev) ev = INFINITY; \
         double sc = ev / (P.atol + fmax(fabs(y0v), fabs(y1v)) * P.rtol) * (w); errnorm2 += sc * sc; }
       DEB_ERRC(0, 1.0) DEB_ERRC(2, k2) DEB_ERRC(3, 1.0) DEB_ERRC(5, 1.0) DEB_ERRC(6, ik2) DEB_ERRC(7, 1.0)
+      if (BATCH && P.mode != 3) {
+        // one norm for the batch: sum the 6 B squared components; a NaN candidate anywhere in the batch switches
+        // EVERY mode's error scale to y0 (diffrax tests the whole (B, n) array), which needs a second round
+        double tot, nanc;
+        batch_exchange(*BC, errnorm2, anynan ? 1.0 : 0.0, BATCH_SUM, &tot, &nanc);
+        if (nanc > 0.0) {
+          if (!anynan) {
+            anynan = true; errnorm2 = 0.0;
+            DEB_ERRC(0, 1.0) DEB_ERRC(2, k2) DEB_ERRC(3, 1.0) DEB_ERRC(5, 1.0) DEB_ERRC(6, ik2) DEB_ERRC(7, 1.0)
+          }
+          batch_exchange(*BC, errnorm2, 0.0, BATCH_SUM, &tot, &nanc);
+        }
+        errnorm2 = tot / (double)BC->B;
+      }
 #undef DEB_ERRC
       DEB_SYNC();          // y, u, r are rewritten below (output sampling, accepted state)
     }

@@ -12,7 +12,8 @@ static inline int fill_problem(const deb_dims* d, const deb_ctrl* c, deb::Proble
   if (!d || !c || !P) return DEB_E_ARG;
   if (d->ncosmo < 1 || d->nk < 1 || d->nout < 1 || d->max_steps < 1) return DEB_E_ARG;
   if (d->nth < 2 || d->nnu < 2) return DEB_E_ARG;
-  if (d->ntan < 0) return DEB_E_ARG;
+  if (d->ntan < 0 || d->batch_size < 0) return DEB_E_ARG;
+  if (d->batch_size > 0 && (d->nk % d->batch_size != 0 || d->batch_size > 32 || d->ntan != 0)) return DEB_E_ARG;
   if (d->lmaxg < 3 || d->lmaxgp < 3 || d->lmaxr < 3 || d->lmaxnu < 3) return DEB_E_UNSUPPORTED;
   if (d->lmaxg >= deb::LMAXCAP || d->lmaxgp >= deb::LMAXCAP || d->lmaxr >= deb::LMAXCAP || d->lmaxnu >= deb::LMAXCAP)
     return DEB_E_UNSUPPORTED;
@@ -26,6 +27,7 @@ static inline int fill_problem(const deb_dims* d, const deb_ctrl* c, deb::Proble
   P->max_steps = d->max_steps; P->return_full = d->return_full; P->k_per_cosmo = d->k_per_cosmo;
   P->power_idx = d->power_idx;
   P->ntan = d->ntan;
+  P->batch_size = d->batch_size;
   P->n = deb_nvar_impl(d);
   P->np = (P->n + 1) & ~1;
   P->nh = 17 + 3 * d->nqmax;

@@ -143,6 +143,43 @@ __global__ void __launch_bounds__(32, 1) k_evolve_t(const __grid_constant__ Prob
   }
 }
 
+// Batched variant (shared step size per batch, Rodas5Batched): a batch = BW warps per CTA x NCTA CTAs of one cluster;
+// cluster c of the grid integrates batch c (no work queue: the warps of a batch must stay in lock-step).
+template <int NE>
+__global__ void __launch_bounds__(256, 1) k_evolve_b(const __grid_constant__ Problem P, int bw, int ncta) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  CtaConst* C = reinterpret_cast<CtaConst*>(smem_raw);
+  size_t off = (sizeof(CtaConst) + 15) & ~(size_t)15;
+  int* tail = reinterpret_cast<int*>(smem_raw + off);
+  off = (off + (size_t)P.np * sizeof(int) + 15) & ~(size_t)15;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* slots = reinterpret_cast<double*>(smem_raw + off);
+  off += (size_t)4 * bw * sizeof(double);
+  double* wsb = reinterpret_cast<double*>(smem_raw + off + warp * warp_ws_bytes(P.np));
+  init_cta_const(P, *C, tail, threadIdx.x, blockDim.x);
+  __syncthreads();
+  WarpWs W;
+  carve(W, wsb, P.np);
+  const int batch = blockIdx.x / ncta, cta = blockIdx.x - batch * ncta;
+  BatchCtx bc;
+  bc.slots = slots; bc.bw = bw; bc.ncta = ncta; bc.B = P.batch_size; bc.idx = cta * bw + warp; bc.parity = 0;
+  // batches tile every cosmology's k list in order (perturbations.py:830: jnp.split(kmodes, n_batches))
+  const int mode = batch * P.batch_size + bc.idx;
+  integrate_mode<NE, false, false, true>(P, *C, W, nullptr, mode, lane, nullptr, 0, &bc);
+  // nobody may leave while a peer can still read its slots
+  if (ncta > 1) cooperative_groups::this_cluster().sync(); else __syncthreads();
+}
+typedef void (*batched_kernel_t)(const Problem, int, int);
+static batched_kernel_t pick_batched_kernel(int n) {
+  int ne = (n + 31) / 32;
+  if (ne <= 3) return k_evolve_b<3>;
+  if (ne <= 4) return k_evolve_b<4>;
+  if (ne <= 6) return k_evolve_b<6>;
+  if (ne <= 9) return k_evolve_b<9>;
+  if (ne <= 12) return k_evolve_b<12>;
+  return nullptr;
+}
+
 typedef void (*evolve_kernel_t)(const Problem);
 static evolve_kernel_t pick_tangent_kernel(int n) {
   int ne = (n + 31) / 32;
@@ -181,6 +218,31 @@ static int launch_evolve(const Problem& P, cudaStream_t st) {
   int dev = 0, nsm = 0, occ = 0;
   CUDA_TRY(cudaGetDevice(&dev));
   CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+  if (P.batch_size > 0) {
+    batched_kernel_t kern = pick_batched_kernel(P.n);
+    if (!kern) return DEB_E_UNSUPPORTED;
+    // warps per CTA: the largest divisor of the batch size that fits 8 warps (255 registers each) and the shared memory
+    int bw = 0;
+    for (int w = 8; w >= 1; --w) {
+      if (P.batch_size % w) continue;
+      if (cta_smem_bytes(P.np, w) + 4 * w * sizeof(double) + 16 <= 227 * 1024) { bw = w; break; }
+    }
+    if (!bw) return DEB_E_UNSUPPORTED;
+    const int ncta = P.batch_size / bw;
+    if (ncta > 8) return DEB_E_UNSUPPORTED;          // portable cluster size
+    const size_t smem = cta_smem_bytes(P.np, bw) + 4 * bw * sizeof(double) + 16;
+    CUDA_TRY(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long nbatch = (long)P.ncosmo * P.nk / P.batch_size;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(nbatch * ncta)); cfg.blockDim = dim3(32 * bw); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = ncta; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, P, bw, ncta));
+    CUDA_TRY(cudaGetLastError());
+    return DEB_OK;
+  }
   if (P.ntan > 0) {
     evolve_kernel_t kern = pick_tangent_kernel(P.n);
     if (!kern) return DEB_E_UNSUPPORTED;

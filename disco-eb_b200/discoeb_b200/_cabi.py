@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libdiscoeb_b200.so")
 class DebDims(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "ncosmo", "nk", "nout", "ntan", "lmaxg", "lmaxgp", "lmaxr", "lmaxnu", "nqmax", "nth", "nnu",
-        "max_steps", "return_full", "k_per_cosmo", "power_idx", "reserved")]
+        "max_steps", "return_full", "k_per_cosmo", "power_idx", "batch_size")]
 
 
 class DebCtrl(C.Structure):
@@ -242,10 +242,10 @@ def default_library() -> Library:
 
 
 def make_dims(*, ncosmo, nk, nout, lmaxg, lmaxgp, lmaxr, lmaxnu, nqmax, nth, nnu, max_steps, return_full=False,
-              k_per_cosmo=False, power_idx=-1, ntan=0) -> DebDims:
+              k_per_cosmo=False, power_idx=-1, ntan=0, batch_size=0) -> DebDims:
     return DebDims(ncosmo=ncosmo, nk=nk, nout=nout, ntan=ntan, lmaxg=lmaxg, lmaxgp=lmaxgp, lmaxr=lmaxr, lmaxnu=lmaxnu,
                    nqmax=nqmax, nth=nth, nnu=nnu, max_steps=max_steps, return_full=int(bool(return_full)),
-                   k_per_cosmo=int(bool(k_per_cosmo)), power_idx=power_idx, reserved=0)
+                   k_per_cosmo=int(bool(k_per_cosmo)), power_idx=power_idx, batch_size=batch_size)
 
 
 def make_ctrl(*, rtol, atol, pcoeff=0.25, icoeff=0.8, dcoeff=0.0, factormax=20.0, factormin=0.3, safety=0.9) -> DebCtrl:

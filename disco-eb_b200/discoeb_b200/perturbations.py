@@ -11,10 +11,14 @@ Same argument names, defaults, return shapes, ``param`` side effects (:989-995) 
 behaviour (diffrax raises when ``max_steps`` is exhausted; so does this).  The arithmetic runs in
 ``libdiscoeb_b200.so`` through the C-ABI of ``include/discoeb_b200.h``; there is no CPU path.
 
-Documented deviation: ``evolve_perturbations_batched`` integrates every mode with its own step
-sequence (the reference's batched solver shares one step size per batch, which changes results
-at O(rtol)).  ``batch_size`` only has to divide ``num_k`` as in the
-reference (:830).
+``evolve_perturbations_batched`` reproduces the reference's batched numerics: consecutive groups of
+``batch_size`` modes start at the earliest of their start times and share ONE adaptive step size, controlled
+by the RMS error over the whole batch (``Rodas5Batched``, ``ode_integrators_stiff.py:846-1010``;
+``evolve_modes_batched``, ``perturbations.py:786-922``) -- the batched CUDA kernel keeps the warps of a batch in
+lock-step through a thread-block cluster.  ``shared_step=False`` selects per-mode stepping instead (the
+numerics of ``evolve_perturbations``, faster).  One reference quirk is consciously not reproduced: for more
+than one output time the reference reshapes ``(n_batches, nout, batch, n)`` to ``(num_k, nout, n)`` without
+transposing (:907-909), which scrambles modes and output times; the modes come back in order here.
 """
 from __future__ import annotations
 
@@ -48,7 +52,7 @@ def _check_status(status, nsteps, max_steps, throw):
 
 
 def _solve(params, kmodes, aexp_out, *, lmaxg, lmaxgp, lmaxr, lmaxnu, nqmax, rtol, atol, pcoeff, icoeff, dcoeff,
-           factormax, factormin, max_steps, return_full, device, power_idx=-1, lib=None, k_per_cosmo=False):
+           factormax, factormin, max_steps, return_full, device, power_idx=-1, lib=None, k_per_cosmo=False, batch_size=0):
     lib = lib or _cabi.default_library()
     scalars, tables, nth, nnu = pack_params(params)
     aexp_out = np.atleast_1d(np.asarray(aexp_out, dtype=np.float64))
@@ -59,7 +63,7 @@ def _solve(params, kmodes, aexp_out, *, lmaxg, lmaxgp, lmaxr, lmaxnu, nqmax, rto
     nk = kmodes.shape[-1]
     dims = _cabi.make_dims(ncosmo=len(params), nk=nk, nout=aexp_out.size, lmaxg=lmaxg, lmaxgp=lmaxgp, lmaxr=lmaxr,
                            lmaxnu=lmaxnu, nqmax=nqmax, nth=nth, nnu=nnu, max_steps=max_steps,
-                           return_full=return_full, k_per_cosmo=k_per_cosmo, power_idx=power_idx)
+                           return_full=return_full, k_per_cosmo=k_per_cosmo, power_idx=power_idx, batch_size=batch_size)
     ctrl = _cabi.make_ctrl(rtol=rtol, atol=atol, pcoeff=pcoeff, icoeff=icoeff, dcoeff=dcoeff, factormax=factormax,
                            factormin=factormin)
     return lib.evolve_host(dims, ctrl, scalars, tables, kmodes, aexp_out, device=device, want_pk=power_idx >= 0)
@@ -105,15 +109,19 @@ def evolve_perturbations_batched(*, param, aexp_out, kmin: float, kmax: float, n
                                  nqmax: int = 3, rtol: float = 1e-4, atol: float = 1e-4,
                                  pcoeff: float = 0.25, icoeff: float = 0.80, dcoeff: float = 0.0,
                                  factormax: float = 20.0, factormin: float = 0.3, max_steps: int = 2048,
-                                 batch_size: int = 16, device: int = 0, throw: bool = True):
-    """API-compatible with ``perturbations.py:1000-1061``: returns ``(y, kmodes)``.  Per-mode
-    stepping (see module docstring)."""
+                                 batch_size: int = 16, device: int = 0, throw: bool = True, shared_step: bool = True):
+    """``perturbations.py:1000-1061``: returns ``(y, kmodes)``; every batch of ``batch_size`` consecutive modes
+    advances with one shared step size (see module docstring).  ``batch_size`` must divide ``num_k`` (:830) and be
+    at most 32."""
     if num_k % batch_size != 0:
         raise ValueError("num_k must be divisible by batch_size (jnp.split at perturbations.py:830)")
+    if shared_step and batch_size > 32:
+        raise ValueError("batch_size > 32 is not supported by the shared-step kernel (use shared_step=False)")
     kmodes = np.geomspace(kmin, kmax, num_k)
     out = _solve([param], kmodes, aexp_out, lmaxg=lmaxg, lmaxgp=lmaxgp, lmaxr=lmaxr, lmaxnu=lmaxnu, nqmax=nqmax,
                  rtol=rtol, atol=atol, pcoeff=pcoeff, icoeff=icoeff, dcoeff=dcoeff, factormax=factormax,
-                 factormin=factormin, max_steps=max_steps, return_full=False, device=device)
+                 factormin=factormin, max_steps=max_steps, return_full=False, device=device,
+                 batch_size=batch_size if shared_step else 0)
     _check_status(out["status"], out["nsteps"], max_steps, throw)
     param["nout"] = out["tau_out"].shape[1]
     return out["y"][0], kmodes

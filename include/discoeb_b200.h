@@ -60,7 +60,10 @@ typedef struct deb_dims {
   int32_t return_full;   /* 0: 20 output fields, 1: raw state vector (return_full)    */
   int32_t k_per_cosmo;   /* 0: kmodes[nk] shared, 1: kmodes[ncosmo*nk]                */
   int32_t power_idx;     /* >=0: also write P(k) of this field to pk_out (get_power)  */
-  int32_t reserved;
+  int32_t batch_size;    /* 0: every mode has its own adaptive step sequence (evolve_perturbations);
+                            B > 0: consecutive groups of B k-modes share ONE step size and start time, the
+                            numerics of evolve_perturbations_batched / Rodas5Batched (perturbations.py:786-922,
+                            ode_integrators_stiff.py:846-1010); needs nk % B == 0, B <= 32, ntan == 0 */
 } deb_dims;
 
 typedef struct deb_ctrl {

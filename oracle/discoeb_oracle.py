@@ -749,3 +749,114 @@ def evolve_perturbations(*, param, aexp_out, kmin, kmax, num_k, lmaxg=11, lmaxgp
 def get_power(*, k, y, idx, param):
     """perturbations.py:1101-1123."""
     return 2 * np.pi ** 2 * param["A_s"] * (k / param["k_p"]) ** (param["n_s"] - 1) * k ** (-3) * y[..., idx] ** 2
+
+
+# --------------------------------------------------------------------------------------------------
+# batched variant: one shared step size per batch of modes
+# (perturbations.py:786-922 evolve_modes_batched, ode_integrators_stiff.py:846-1010 Rodas5Batched)
+# --------------------------------------------------------------------------------------------------
+def integrate_batch(t0, t1, y0, ts, p, k, d: Dims, rtol, atol, pcoeff=0.25, icoeff=0.8, dcoeff=0.0, factormax=20.0,
+                    factormin=0.3, max_steps=2048, safety=0.9, order=5.0, trace=None):
+    """diffrax.diffeqsolve of ONE batch: state y[B, n] is a single pytree, so there is one t, one dt, one
+    accept/reject decision and one error norm -- the RMS over all B x 6 filtered, weighted components
+    (rms_norm_filtered_batched, perturbations.py:689-693); a NaN anywhere in the batch's candidate replaces the whole
+    candidate by y0 in the error scale (diffrax's ``jnp.isnan(y1).any()`` acts on the whole array).
+    Returns (ys[B, nout, n], status, nsteps, naccept) -- scalars shared by the batch."""
+    B, n = y0.shape
+    nout = len(ts)
+    ys = np.full((B, nout, n), np.nan)
+    tprev = float(t0)
+    tnext = tprev + min(tprev / 4, 0.5 * (t1 - tprev))
+    if tnext > t1 - 1e-10:
+        tnext = t1
+    y = y0.copy()
+    inv_prev = inv_pprev = 1.0
+    save_idx = nsteps = nacc = status = 0
+    c1 = (icoeff + pcoeff + dcoeff) / order
+    c2 = -(pcoeff + 2 * dcoeff) / order
+    c3 = dcoeff / order
+    idx = np.array([0, 2, 3, 5, 6, 7])
+    wts = np.stack([np.ones_like(k), k ** 2, np.ones_like(k), np.ones_like(k), 1 / k ** 2, np.ones_like(k)], -1)
+    while tprev < t1 and status == 0 and nsteps < max_steps:
+        tp = np.full(B, tprev)
+        tn = np.full(B, tnext)
+        with np.errstate(all="ignore"):
+            y1, err = rodas5_step(tp, tn, y, p, k, d)
+            err = np.where(np.isnan(err), np.inf, err)
+            y1c = y if np.isnan(y1).any() else y1
+            sc = err / (atol + np.maximum(np.abs(y), np.abs(y1c)) * rtol)
+            x = sc[:, idx] * wts
+            E = float(np.sqrt(np.mean(x * x)))
+            keep = E < 1
+            inv = 1.0 / E if E != 0 else np.inf
+            f1 = inv ** c1 if c1 != 0 else 1.0
+            f2 = inv_prev ** c2 if c2 != 0 else 1.0
+            f3 = inv_pprev ** c3 if c3 != 0 else 1.0
+            fac = float(np.clip(safety * f1 * f2 * f3, 1.0 if keep else factormin, factormax))
+            dtn = (tnext - tprev) * fac
+            if inv == 0 or np.isinf(inv):
+                inv = 1.0
+        nsteps += 1
+        nacc += int(keep)
+        if trace is not None:
+            trace.append((tprev, tnext, E, keep))
+        if keep:
+            while save_idx < nout and ts[save_idx] <= tnext:
+                tt = ts[save_idx]
+                coeff = 0.0 if tnext == tprev else (tt - tprev) / (tnext - tprev)
+                ys[:, save_idx] = y + coeff * (y1 - y)
+                save_idx += 1
+            y = y1
+            inv_pprev, inv_prev = inv_prev, inv
+            tprev = min(tnext, t1)
+        tn_ = tprev + dtn
+        if tn_ > t1 - 1e-10:
+            tn_ = t1 if keep else tprev + 0.5 * (t1 - tprev)
+        tnext = tn_
+        if not np.isfinite(tnext) or not np.all(np.isfinite(y)):
+            status = 2
+    if status == 0 and tprev < t1:
+        status = 1
+    return ys, status, nsteps, nacc
+
+
+def evolve_perturbations_batched(*, param, aexp_out, kmin, kmax, num_k, lmaxg=11, lmaxgp=11, lmaxr=11, lmaxnu=8, nqmax=3,
+                                 rtol=1e-4, atol=1e-4, pcoeff=0.25, icoeff=0.80, dcoeff=0.0, factormax=20.0, factormin=0.3,
+                                 max_steps=2048, batch_size=16, kmodes=None, return_info=False):
+    """perturbations.py:1000-1061 (+ evolve_modes_batched :820-922): consecutive k-modes are grouped into batches of
+    ``batch_size``; a batch starts at the smallest of its modes' start times (:786-805) and advances with one shared
+    adaptive step.  Returns ``(y[num_k, nout, 20], kmodes)``.  (The reference reshapes ``ys[n_batches, nout, batch, n]``
+    to ``(num_k, nout, n)`` without transposing, :907-909, which scrambles modes and output times whenever nout > 1;
+    the modes are returned in order here.)"""
+    if kmodes is None:
+        kmodes = np.geomspace(kmin, kmax, num_k)
+    kmodes = np.asarray(kmodes, dtype=np.float64)
+    M = kmodes.shape[0]
+    if M % batch_size != 0:
+        raise ValueError("num_k must be divisible by batch_size")
+    aexp_out = np.atleast_1d(np.asarray(aexp_out, dtype=np.float64))
+    tau_out = param["tau_of_a_spline"].evaluate(aexp_out)
+    tau_max = np.max(tau_out)
+    d = Dims(lmaxg, lmaxgp, lmaxr, lmaxnu, nqmax)
+    nout = tau_out.shape[0]
+    tau_start_modes = 0.99 * np.minimum(np.min(tau_out), determine_starting_time(param, kmodes))
+    nb = M // batch_size
+    yfull = np.zeros((M, nout, d.n))
+    info = dict(nsteps=np.zeros(nb, dtype=np.int64), naccept=np.zeros(nb, dtype=np.int64), tau_start=np.zeros(nb), traces=[])
+    for b in range(nb):
+        sl = slice(b * batch_size, (b + 1) * batch_size)
+        ts_b = float(np.min(tau_start_modes[sl]))
+        y0 = adiabatic_ics(np.full(batch_size, ts_b), param, kmodes[sl], d)
+        tr = []
+        ys, st, ns, na = integrate_batch(ts_b, tau_max, y0, tau_out, param, kmodes[sl], d, rtol, atol, pcoeff, icoeff, dcoeff,
+                                         factormax, factormin, max_steps, trace=tr)
+        if st != 0:
+            raise RuntimeError(f"oracle (batched): batch {b} failed with status {st}")
+        yfull[sl] = ys
+        info["nsteps"][b], info["naccept"][b], info["tau_start"][b] = ns, na, ts_b
+        info["traces"].append(tr)
+    y = convert_to_output(yfull, param, kmodes[:, None], d)
+    if return_info:
+        info["yfull"] = yfull
+        return y, kmodes, info
+    return y, kmodes

@@ -6,6 +6,7 @@
 #define DEB_CPU_EMU 1
 #include <cstdlib>
 #include <cstring>
+#include <omp.h>
 #include <vector>
 #include "../../include/discoeb_b200.h"
 #include "../../disco-eb_b200/csrc/deb_core.cuh"
@@ -88,7 +89,46 @@ static int dispatch_h(const Problem& P) {
   else return DEB_E_UNSUPPORTED;
   return DEB_OK;
 }
+// batched variant: the B warps of a batch are played by B OpenMP threads, the cluster barrier by `omp barrier`
+template <int NE>
+static int run_batched(const Problem& P) {
+  CtaConst C;
+  std::vector<int> tail(P.np);
+  for (int t = 0; t < 32; ++t) init_cta_const(P, C, tail.data(), t, 32);
+  const int B = P.batch_size, nb = P.ncosmo * P.nk / B;
+  int bad = 0;
+  omp_set_dynamic(0);
+  for (int b = 0; b < nb; ++b) {
+    std::vector<double> shared((size_t)2 * B * 2, 0.0);
+#pragma omp parallel num_threads(B)
+    {
+      if (omp_get_num_threads() != B) {
+#pragma omp atomic
+        bad += 1;
+      } else {
+        std::vector<double> ws(warp_ws_doubles(P.np));
+        WarpWs W;
+        carve(W, ws.data(), P.np);
+        BatchCtx bc;
+        bc.slots = nullptr; bc.all = shared.data(); bc.B = B; bc.bw = B; bc.ncta = 1; bc.idx = omp_get_thread_num(); bc.parity = 0;
+        HelpBox box;
+        integrate_mode<NE, false, false, true>(P, C, W, &box, b * B + bc.idx, nullptr, 0, &bc);
+      }
+    }
+  }
+  return bad ? DEB_E_UNSUPPORTED : DEB_OK;
+}
+static int dispatch_batched(const Problem& P) {
+  int ne = (P.n + 31) / 32;
+  if (ne <= 3) return run_batched<3>(P);
+  if (ne <= 4) return run_batched<4>(P);
+  if (ne <= 6) return run_batched<6>(P);
+  if (ne <= 9) return run_batched<9>(P);
+  if (ne <= 12) return run_batched<12>(P);
+  return DEB_E_UNSUPPORTED;
+}
 static int dispatch(const Problem& P) {
+  if (P.batch_size > 0) return dispatch_batched(P);
   const char* h = getenv("DEB_EMU_HELPER");
   return (h && h[0] == '1') ? dispatch_h<true>(P) : dispatch_h<false>(P);
 }

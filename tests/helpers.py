@@ -49,8 +49,9 @@ def field_scaled_diff(a, b):
     sc = np.maximum(np.abs(b).max(axis=tuple(range(b.ndim - 1))), 1e-300)
     # theta_c is identically zero in synchronous gauge (perturbations.py:269): it only carries
     # round-off, so it is measured against the baryon velocity that sits next to it
+    # ... or the photon velocity (the baryon velocity itself is tiny for super-horizon modes)
     if b.shape[-1] == 20:
-        sc[9] = max(sc[9], sc[11])
+        sc[9] = max(sc[9], sc[11], sc[13])
     else:
-        sc[4] = max(sc[4], sc[6])
+        sc[4] = max(sc[4], sc[6], sc[8])
     return np.abs(a - b).max(axis=tuple(range(b.ndim - 1))) / sc

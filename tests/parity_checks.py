@@ -280,3 +280,49 @@ def check_edge_shapes(lib, tables):
         bad[idx] = np.nan
         outb = lib.evolve_host(dims, ctrl, bad[None], tab.tables[None], np.array([0.01, 0.1]), np.array([1.0]))
         assert np.all(outb["status"] != 0), idx
+
+
+# ---------------------------------------------------------------------------------------------------
+# batched variant: one shared adaptive step per batch of modes
+# (Rodas5Batched, evolve_modes_batched).  Oracle: oracle.evolve_perturbations_batched -> tests/golden/oracle_batched_*.npz
+# ---------------------------------------------------------------------------------------------------
+BATCHED_CASES = ("batched_n72", "batched_lowk_n72", "batched_n265")
+
+
+def check_batched_replay(lib, tables, name, tol=1e-6):
+    """Shared start time + the oracle's shared step sequence: whole trajectories at round-off level."""
+    case = helpers.load_case(name)
+    tab = tables[str(case["cosmology"])]
+    ks, aout, B = case["kmodes"], case["aexp_out"], int(case["batch_size"])
+    ctrl = _cabi.make_ctrl(rtol=float(case["rtol"]), atol=float(case["rtol"]))
+    for full in (False, True):
+        dims = dims_for(case, tab, len(ks), len(aout), return_full=full, batch_size=B)
+        y, ns = lib.debug_replay(dims, ctrl, tab.scalars, tab.tables, ks, aout, case["rp_tnext"], case["rp_keep"], case["nsteps"])
+        assert np.array_equal(ns[0], case["nsteps"])
+        ref = case["yfull"] if full else case["y"]
+        for m in range(len(ks)):
+            assert helpers.field_scaled_diff(y[0, m], ref[m]).max() < tol, (name, full, m)
+
+
+def check_batched_adaptive(lib, tables, name):
+    """Free-running: every mode of a batch reports the same step counts; batches of at most 100 steps must reproduce
+    the oracle's counts and agree to 1e-5, longer ones to 50 rtol on the matter fields (DESIGN.md "Parity")."""
+    case = helpers.load_case(name)
+    tab = tables[str(case["cosmology"])]
+    ks, aout, B, rtol = case["kmodes"], case["aexp_out"], int(case["batch_size"]), float(case["rtol"])
+    dims = dims_for(case, tab, len(ks), len(aout), batch_size=B)
+    out = lib.evolve_host(dims, _cabi.make_ctrl(rtol=rtol, atol=rtol), tab.scalars[None], tab.tables[None], ks, aout)
+    assert np.all(out["status"] == 0)
+    ns, na = out["nsteps"][0].reshape(-1, B), out["naccept"][0].reshape(-1, B)
+    assert np.all(ns == ns[:, :1]) and np.all(na == na[:, :1])                 # lock-step inside a batch
+    for b in range(ns.shape[0]):
+        sl = slice(b * B, (b + 1) * B)
+        short = case["nsteps"][b * B] <= 100
+        if short:
+            assert ns[b, 0] == case["nsteps"][b * B] and na[b, 0] == case["naccept"][b * B], (name, b, ns[b, 0], case["nsteps"][b * B])
+        for m in range(sl.start, sl.stop):
+            if short:
+                assert helpers.field_scaled_diff(out["y"][0, m], case["y"][m]).max() < 1e-5, (name, m)
+            rel = np.abs(out["y"][0, m][:, MATTER_FIELDS] / case["y"][m][:, MATTER_FIELDS] - 1).max()
+            assert rel < 50 * rtol, (name, m, rel)
+    return out

@@ -148,3 +148,31 @@ def test_batch_of_cosmologies(gpu_lib, tables):
 
 def test_edge_shapes(gpu_lib, tables):
     pc.check_edge_shapes(gpu_lib, tables)
+
+
+@pytest.mark.parametrize("name", pc.BATCHED_CASES)
+def test_batched_shared_step_replay(gpu_lib, tables, name):
+    pc.check_batched_replay(gpu_lib, tables, name)
+
+
+@pytest.mark.parametrize("name", pc.BATCHED_CASES)
+def test_batched_shared_step_adaptive(gpu_lib, tables, name):
+    pc.check_batched_adaptive(gpu_lib, tables, name)
+
+
+def test_python_batched_api_matches_batched_oracle(gpu_lib, tables):
+    """evolve_perturbations_batched = the reference's shared-step numerics (row B): the low-k batch reproduces the
+    batched oracle to 1e-5 and differs from the per-mode solve at O(rtol), as the reference's two entry points do."""
+    from discoeb_b200.perturbations import evolve_perturbations_batched, evolve_perturbations
+    case = helpers.load_case("batched_lowk_n72")
+    p = tables[str(case["cosmology"])].param()
+    kw = dict(aexp_out=case["aexp_out"], kmin=1e-4, kmax=3e-3, num_k=8)
+    yb, kb = evolve_perturbations_batched(param=p, batch_size=8, **kw)
+    np.testing.assert_allclose(kb, case["kmodes"], rtol=1e-14)
+    for m in range(8):
+        assert helpers.field_scaled_diff(yb[m], case["y"][m]).max() < 1e-5
+    yu, _, _ = evolve_perturbations(param=p, **kw)
+    yn, _ = evolve_perturbations_batched(param=p, batch_size=8, shared_step=False, **kw)
+    assert np.array_equal(yn, yu)
+    d = np.abs(yb[..., 4] / yu[..., 4] - 1).max()
+    assert 1e-9 < d < 50e-4

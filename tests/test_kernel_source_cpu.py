@@ -119,3 +119,13 @@ def test_two_warp_variant_source(emu_lib, tables, name, monkeypatch):
 
 def test_edge_shapes(emu_lib, tables):
     pc.check_edge_shapes(emu_lib, tables)
+
+
+@pytest.mark.parametrize("name", pc.BATCHED_CASES)
+def test_batched_shared_step_replay(emu_lib, tables, name):
+    pc.check_batched_replay(emu_lib, tables, name)
+
+
+@pytest.mark.parametrize("name", pc.BATCHED_CASES)
+def test_batched_shared_step_adaptive(emu_lib, tables, name):
+    pc.check_batched_adaptive(emu_lib, tables, name)

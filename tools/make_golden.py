@@ -87,6 +87,34 @@ def run_case(p, dims, ks, aout, rtol, max_steps=4096):
                 naccept=na.astype(np.int32), rp_tnext=rp_t, rp_keep=rp_k, rp_E=rp_E, dims=np.array(dims), rtol=rtol)
 
 
+BATCHED = {
+    # name: (cosmology, dims, (kmin, kmax, num_k), batch_size, aexp_out, rtol)
+    "batched_n72": ("fiducial", (11, 11, 11, 8, 3), (1e-3, 0.3, 8), 4, [0.1, 1.0], 1e-4),
+    "batched_lowk_n72": ("w0wa", (11, 11, 11, 8, 3), (1e-4, 3e-3, 8), 8, [0.5, 1.0], 1e-4),       # few steps: counts must match
+    "batched_n265": ("fiducial", (31, 31, 31, 31, 5), (1e-3, 0.03, 16), 16, [1.0], 1e-4),          # 2 CTAs x 8 warps on the GPU
+}
+
+
+def run_batched_case(p, dims, kgrid, batch, aout, rtol):
+    """Shared-step batches (oracle.evolve_perturbations_batched); the per-batch trace is replicated per mode so that
+    the kernel's replay entry can follow it."""
+    y, ks, info = O.evolve_perturbations_batched(param=p, aexp_out=aout, kmin=kgrid[0], kmax=kgrid[1], num_k=kgrid[2],
+                                                 lmaxg=dims[0], lmaxgp=dims[1], lmaxr=dims[2], lmaxnu=dims[3], nqmax=dims[4],
+                                                 rtol=rtol, atol=rtol, max_steps=4096, batch_size=batch, return_info=True)
+    M = len(ks)
+    stride = int(info["nsteps"].max())
+    rp_t = np.zeros((M, stride)); rp_k = np.zeros((M, stride), dtype=np.int32)
+    for b, tr in enumerate(info["traces"]):
+        for s_, (tp, tn, E, keep) in enumerate(tr):
+            rp_t[b * batch:(b + 1) * batch, s_] = tn
+            rp_k[b * batch:(b + 1) * batch, s_] = keep
+    aout = np.asarray(aout, dtype=np.float64)
+    return dict(kmodes=ks, aexp_out=aout, tau_out=p["tau_of_a_spline"].evaluate(aout), y=y, yfull=info["yfull"],
+                nsteps=np.repeat(info["nsteps"], batch).astype(np.int32), naccept=np.repeat(info["naccept"], batch).astype(np.int32),
+                tau_start=np.repeat(info["tau_start"], batch), rp_tnext=rp_t, rp_keep=rp_k, dims=np.array(dims), rtol=rtol,
+                batch_size=batch)
+
+
 def main():
     only = sys.argv[1:]
     params = make_tables() if not only else {c: helpers_param(c) for c in COSMOLOGIES}
@@ -97,6 +125,13 @@ def main():
         out = run_case(params[cos], dims, np.asarray(ks, dtype=np.float64), aout, rtol)
         np.savez_compressed(os.path.join(GOLD, f"oracle_{name}.npz"), cosmology=cos, **out)
         print(name, "steps", out["nsteps"], "%.1fs" % (time.time() - t), flush=True)
+    for name, (cos, dims, kgrid, batch, aout, rtol) in BATCHED.items():
+        if only and name not in only:
+            continue
+        t = time.time()
+        out = run_batched_case(params[cos], dims, kgrid, batch, aout, rtol)
+        np.savez_compressed(os.path.join(GOLD, f"oracle_{name}.npz"), cosmology=cos, **out)
+        print(name, "steps", out["nsteps"][::batch], "%.1fs" % (time.time() - t), flush=True)
 
 
 if __name__ == "__main__":
