@@ -953,7 +953,7 @@ DEB_DEV void helper_loop(const Problem& P, const CtaConst& C, WarpWs& W, HelpBox
 // advance with ONE adaptive step size.  Every mode still runs on its own warp; what the batch shares is (i) the start
 // time (the smallest of its modes') and (ii) per attempted step the error norm, an RMS over all B x 6 filtered
 // components.  Both are all-to-all exchanges of one double per mode: lane 0 of every warp writes its slot, a barrier,
-// every warp reads all B slots (lane i <- slot i) and reduces them with the same butterfly, so that all warps of
+// every warp reads all B slots (lane i <- slots i and i + 32) and reduces them with the same butterfly, so that all warps of
 // the batch hold bit-identical values and take identical accept/reject decisions.  A batch is bw warps per CTA
 // x ncta CTAs of one thread-block cluster (8 warps per CTA is what the register file allows); remote slots are read
 // through distributed shared memory, the barrier is the cluster's.
@@ -975,7 +975,12 @@ inline void batch_exchange(BatchCtx& bc, double v, double f, int op, double* out
 #pragma omp barrier
   // the butterfly of the device code: pairwise tree over 32 lanes (missing lanes hold the neutral element)
   double x[32], g[32];
-  for (int i = 0; i < 32; ++i) { x[i] = i < bc.B ? buf[2 * i] : (op == BATCH_MIN ? INFINITY : 0.0); g[i] = i < bc.B ? buf[2 * i + 1] : 0.0; }
+  const double neutral = op == BATCH_MIN ? INFINITY : 0.0;
+  for (int i = 0; i < 32; ++i) {          // lane i holds slots i and i + 32 (B <= 64)
+    const double a = i < bc.B ? buf[2 * i] : neutral, b = i + 32 < bc.B ? buf[2 * (i + 32)] : neutral;
+    x[i] = op == BATCH_MIN ? ((a != a || b != b) ? NAN : fmin(a, b)) : a + b;
+    g[i] = (i < bc.B ? buf[2 * i + 1] : 0.0) + (i + 32 < bc.B ? buf[2 * (i + 32) + 1] : 0.0);
+  }
   for (int o = 16; o > 0; o >>= 1)
     for (int i = 0; i < 32; ++i) if ((i & o) == 0) {
       const double a = x[i], b = x[i ^ o];
@@ -996,12 +1001,20 @@ __device__ __forceinline__ void batch_exchange(BatchCtx& bc, double v, double f,
   double* mine = bc.slots + ((size_t)bc.parity * bc.bw + warp) * 2;
   if (lane == 0) { mine[0] = v; mine[1] = f; }
   if (bc.ncta > 1) cg::this_cluster().sync(); else __syncthreads();
-  double x = op == BATCH_MIN ? INFINITY : 0.0, g = 0.0;
-  if (lane < bc.B) {
-    const int cta = lane / bc.bw, w = lane - cta * bc.bw;
-    const double* src = bc.slots + ((size_t)bc.parity * bc.bw + w) * 2;
-    if (bc.ncta > 1) src = cg::this_cluster().map_shared_rank(const_cast<double*>(src), cta);
-    x = src[0]; g = src[1];
+  const double neutral = op == BATCH_MIN ? INFINITY : 0.0;
+  double x = neutral, g = 0.0;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {             // lane i holds slots i and i + 32 (B <= 64)
+    const int slot = lane + 32 * h;
+    double a = neutral, fa = 0.0;
+    if (slot < bc.B) {
+      const int cta = slot / bc.bw, w = slot - cta * bc.bw;
+      const double* src = bc.slots + ((size_t)bc.parity * bc.bw + w) * 2;
+      if (bc.ncta > 1) src = cg::this_cluster().map_shared_rank(const_cast<double*>(src), cta);
+      a = src[0]; fa = src[1];
+    }
+    if (h == 0) { x = a; g = fa; }
+    else { x = op == BATCH_MIN ? ((x != x || a != a) ? NAN : fmin(x, a)) : x + a; g += fa; }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {

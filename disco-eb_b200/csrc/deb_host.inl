@@ -13,7 +13,7 @@ static inline int fill_problem(const deb_dims* d, const deb_ctrl* c, deb::Proble
   if (d->ncosmo < 1 || d->nk < 1 || d->nout < 1 || d->max_steps < 1) return DEB_E_ARG;
   if (d->nth < 2 || d->nnu < 2) return DEB_E_ARG;
   if (d->ntan < 0 || d->batch_size < 0) return DEB_E_ARG;
-  if (d->batch_size > 0 && (d->nk % d->batch_size != 0 || d->batch_size > 32 || d->ntan != 0)) return DEB_E_ARG;
+  if (d->batch_size > 0 && (d->nk % d->batch_size != 0 || d->batch_size > 64 || d->ntan != 0)) return DEB_E_ARG;
   if (d->lmaxg < 3 || d->lmaxgp < 3 || d->lmaxr < 3 || d->lmaxnu < 3) return DEB_E_UNSUPPORTED;
   if (d->lmaxg >= deb::LMAXCAP || d->lmaxgp >= deb::LMAXCAP || d->lmaxr >= deb::LMAXCAP || d->lmaxnu >= deb::LMAXCAP)
     return DEB_E_UNSUPPORTED;

@@ -112,11 +112,11 @@ def evolve_perturbations_batched(*, param, aexp_out, kmin: float, kmax: float, n
                                  batch_size: int = 16, device: int = 0, throw: bool = True, shared_step: bool = True):
     """``perturbations.py:1000-1061``: returns ``(y, kmodes)``; every batch of ``batch_size`` consecutive modes
     advances with one shared step size (see module docstring).  ``batch_size`` must divide ``num_k`` (:830) and be
-    at most 32."""
+    at most 64."""
     if num_k % batch_size != 0:
         raise ValueError("num_k must be divisible by batch_size (jnp.split at perturbations.py:830)")
-    if shared_step and batch_size > 32:
-        raise ValueError("batch_size > 32 is not supported by the shared-step kernel (use shared_step=False)")
+    if shared_step and batch_size > 64:
+        raise ValueError("batch_size > 64 is not supported by the shared-step kernel (use shared_step=False)")
     kmodes = np.geomspace(kmin, kmax, num_k)
     out = _solve([param], kmodes, aexp_out, lmaxg=lmaxg, lmaxgp=lmaxgp, lmaxr=lmaxr, lmaxnu=lmaxnu, nqmax=nqmax,
                  rtol=rtol, atol=atol, pcoeff=pcoeff, icoeff=icoeff, dcoeff=dcoeff, factormax=factormax,

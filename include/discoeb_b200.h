@@ -63,7 +63,7 @@ typedef struct deb_dims {
   int32_t batch_size;    /* 0: every mode has its own adaptive step sequence (evolve_perturbations);
                             B > 0: consecutive groups of B k-modes share ONE step size and start time, the
                             numerics of evolve_perturbations_batched / Rodas5Batched (perturbations.py:786-922,
-                            ode_integrators_stiff.py:846-1010); needs nk % B == 0, B <= 32, ntan == 0 */
+                            ode_integrators_stiff.py:846-1010); needs nk % B == 0, B <= 64, ntan == 0 */
 } deb_dims;
 
 typedef struct deb_ctrl {

@@ -176,3 +176,25 @@ def test_python_batched_api_matches_batched_oracle(gpu_lib, tables):
     assert np.array_equal(yn, yu)
     d = np.abs(yb[..., 4] / yu[..., 4] - 1).max()
     assert 1e-9 < d < 50e-4
+
+
+@pytest.mark.parametrize("batch_size", [4, 8, 16, 32, 64])
+def test_class_golden_curve_batched(gpu_lib, tables, batch_size):
+    """The reference's acceptance tests of the batched variant at full size (tests/test_perturbations.py:95-125:
+    512 modes, lmax=31, nq=5, z=99, rtol=atol=1e-4, batch sizes 4...64): P_bc within 0.5 % of CLASS for k <= 10/Mpc."""
+    from discoeb_b200 import _cabi
+    tab = tables["fiducial"]
+    g = json.load(open(os.path.join(helpers.GOLD, "CLASS_data.json")))
+    kc, Pc = np.array(g["k"]), np.array(g["Pkbc"])
+    nk = 512
+    ks = np.geomspace(1e-5, 10.0, nk)
+    dims = _cabi.make_dims(ncosmo=1, nk=nk, nout=1, lmaxg=31, lmaxgp=31, lmaxr=31, lmaxnu=31, nqmax=5, nth=tab.nth,
+                           nnu=tab.nnu, max_steps=2048, power_idx=6, batch_size=batch_size)
+    out = gpu_lib.evolve_host(dims, _cabi.make_ctrl(rtol=1e-4, atol=1e-4), tab.scalars[None], tab.tables[None], ks,
+                              np.array([0.01]), want_pk=True)
+    assert np.all(out["status"] == 0)
+    ns = out["nsteps"][0].reshape(-1, batch_size)
+    assert np.all(ns == ns[:, :1])
+    m = (kc >= 1e-5) & (kc <= 10.0)
+    np.testing.assert_allclose(np.interp(kc[m], ks, out["pk"][0, :, 0]), Pc[m], rtol=0.005)
+    print("batch", batch_size, "kernel_ms", out["kernel_ms"], "steps per batch", ns[:, 0].min(), "...", ns[:, 0].max())
