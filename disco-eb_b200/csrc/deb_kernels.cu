@@ -214,10 +214,24 @@ static evolve_kernel_t pick_kernel(int n, bool many_modes, bool few_modes, int* 
   return nullptr;
 }
 
+int deb_launch_team(const Problem& P, cudaStream_t st, int nsm);      // deb_team.cu
+
+// Kernel choice can be forced for tests and measurements: DEB_VARIANT = warp | helper | team
+static int variant_forced(const char* name) { const char* v = getenv("DEB_VARIANT"); return v && !strcmp(v, name); }
+
 static int launch_evolve(const Problem& P, cudaStream_t st) {
   int dev = 0, nsm = 0, occ = 0;
   CUDA_TRY(cudaGetDevice(&dev));
   CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+  if (P.batch_size == 0 && P.ntan == 0) {
+    // launches that cannot fill the GPU: one CTA (4 warps) per mode, deb_team.cuh
+    const long nm = (long)P.ncosmo * P.nk;
+    const bool want = getenv("DEB_VARIANT") ? variant_forced("team") : nm <= (long)nsm * 4;
+    if (want) {
+      const int rc = deb_launch_team(P, st, nsm);
+      if (rc != DEB_E_UNSUPPORTED) return rc;
+    }
+  }
   if (P.batch_size > 0) {
     batched_kernel_t kern = pick_batched_kernel(P.n);
     if (!kern) return DEB_E_UNSUPPORTED;
@@ -262,7 +276,8 @@ static int launch_evolve(const Problem& P, cudaStream_t st) {
   size_t extra = 0;
   const long nmodes = (long)P.ncosmo * P.nk;
   // replay/debug modes use the plain kernel; the helper variant serves launches of at most 4 modes per SM
-  evolve_kernel_t kern = pick_kernel(P.n, nmodes > (long)nsm * 8, P.mode == 0 && nmodes <= (long)nsm * 4, &warps, &extra);
+  const bool few = (variant_forced("helper") && P.mode == 0) || (!getenv("DEB_VARIANT") && P.mode == 0 && nmodes <= (long)nsm * 4);
+  evolve_kernel_t kern = pick_kernel(P.n, nmodes > (long)nsm * 8, few, &warps, &extra);
   if (!kern) return DEB_E_UNSUPPORTED;
   const bool helper = extra > 0;
   size_t smem = cta_smem_bytes(P.np, helper ? 1 : warps) + extra;

@@ -1,0 +1,87 @@
+// deb_team.cu -- sm_100a kernel of the CTA-per-mode ("team") variant (deb_team.cuh) and its launcher.
+//
+// Launch geometry: one CTA of TEAM warps integrates one (cosmology, k) mode; CTAs pull modes from the global
+// ticket counter, largest k first.  Chosen by launch_evolve (deb_kernels.cu) for launches of at most
+// DEB_TEAM_MAX_PER_SM modes per SM, where the time of the launch is the latency of its slowest mode.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include "../../include/discoeb_b200.h"
+#include "deb_core.cuh"
+#include "deb_team.cuh"
+
+using namespace deb;
+
+#define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
+  fprintf(stderr, "[discoeb_b200] CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return DEB_E_CUDA; } } while (0)
+
+static __host__ __device__ size_t al16(size_t b) { return (b + 15) & ~(size_t)15; }
+static __host__ __device__ size_t team_smem_bytes(int np) {
+  return al16(sizeof(CtaConst)) + al16((size_t)np * sizeof(int)) + al16(warp_ws_doubles(np) * sizeof(double)) + al16(sizeof(TeamBox)) + 16;
+}
+
+template <int NE, int TEAM, int MINB>
+__global__ void __launch_bounds__(32 * TEAM, MINB) k_evolve_team(const __grid_constant__ Problem P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  CtaConst* C = reinterpret_cast<CtaConst*>(smem_raw);
+  size_t off = al16(sizeof(CtaConst));
+  int* tail = reinterpret_cast<int*>(smem_raw + off);
+  off += al16((size_t)P.np * sizeof(int));
+  double* wsb = reinterpret_cast<double*>(smem_raw + off);
+  off += al16(warp_ws_doubles(P.np) * sizeof(double));
+  TeamBox* box = reinterpret_cast<TeamBox*>(smem_raw + off);
+  off += al16(sizeof(TeamBox));
+  unsigned int* s_tk = reinterpret_cast<unsigned int*>(smem_raw + off);
+  const int tid = threadIdx.x;
+  init_cta_const(P, *C, tail, tid, 32 * TEAM);
+  __syncthreads();
+  WarpWs W;
+  carve(W, wsb, P.np);
+  const int total = P.ncosmo * P.nk;
+  for (;;) {
+    if (tid == 0) *s_tk = atomicAdd(P.ticket, 1u);
+    __syncthreads();
+    const unsigned int tk = *s_tk;
+    if (tk >= (unsigned int)total) break;
+    // largest k first, cosmologies interleaved
+    const int kd = tk / P.ncosmo, cs = tk - kd * P.ncosmo;
+    const int mode = cs * P.nk + (P.nk - 1 - kd);
+    integrate_mode_team<NE, TEAM>(P, *C, W, *box, mode, tid);
+    __syncthreads();
+  }
+}
+
+typedef void (*evolve_kernel_t)(const Problem);
+
+template <int TEAM, int MINB>
+static evolve_kernel_t pick_team(int n) {
+  const int ne = (n + 32 * TEAM - 1) / (32 * TEAM);
+  if (ne <= 1) return k_evolve_team<1, TEAM, MINB>;
+  if (ne <= 2) return k_evolve_team<2, TEAM, MINB>;
+  if (ne <= 3) return k_evolve_team<3, TEAM, MINB>;
+  return nullptr;
+}
+
+// returns DEB_OK after launching, DEB_E_UNSUPPORTED when no team kernel serves this shape (the caller falls back to
+// the one-warp kernels, which are CUDA kernels too)
+int deb_launch_team(const Problem& P, cudaStream_t st, int nsm) {
+  int team = 4, minb = 2;
+  if (const char* e = getenv("DEB_TEAM")) team = atoi(e);
+  if (const char* e = getenv("DEB_TEAM_MINB")) minb = atoi(e);
+  evolve_kernel_t kern = nullptr;
+  if (team == 4) kern = minb >= 4 ? pick_team<4, 4>(P.n) : (minb == 3 ? pick_team<4, 3>(P.n) : pick_team<4, 2>(P.n));
+  else if (team == 8) kern = pick_team<8, 2>(P.n);
+  if (!kern) return DEB_E_UNSUPPORTED;
+  const size_t smem = team_smem_bytes(P.np);
+  int occ = 0;
+  CUDA_TRY(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)kern, 32 * team, smem));
+  if (occ < 1) return DEB_E_UNSUPPORTED;
+  const long total = (long)P.ncosmo * P.nk;
+  long grid = (long)nsm * occ;
+  if (grid > total) grid = total;
+  CUDA_TRY(cudaMemsetAsync(P.ticket, 0, sizeof(unsigned int), st));
+  kern<<<(unsigned)grid, 32 * team, smem, st>>>(P);
+  CUDA_TRY(cudaGetLastError());
+  return DEB_OK;
+}

@@ -1,0 +1,632 @@
+// deb_team.cuh -- CTA-per-mode ("team") variant of the per-mode integrator for launches that cannot fill the GPU.
+//
+// integrate_mode (deb_core.cuh) runs one mode on ONE warp: with 512 modes on 148 SMs every warp has a scheduler to
+// itself and the time of the launch is the latency of its slowest mode, 8 stages x (serial solve + element-wise
+// work) per step.  62 % of a step's instructions are element-parallel (stage combinations, hierarchy rows l >= 3,
+// the d f/d a column, k_i stores).  Here a mode gets a team of TEAM warps (one CTA):
+//   * every thread owns the elements e = tid + 32 TEAM j of the stage vectors k_1..k_7 (registers) and evaluates
+//     the tail rows tt = tid + 32 TEAM j;
+//   * warp 0 runs what is serial: metric sources, the head rows, the bordered solve (tail sweeps, block inverses,
+//     Woodbury correction); the d f/d a column is folded into the sweeps and the head gather;
+//   * warp 1 is also the "helper": the scale factor of the NEXT stage is known as soon as x_0 = r_0 / W_00 is, so
+//     it evaluates the background scalars of stage i+1 while warp 0 solves stage i; at the start of a step it
+//     factors the hierarchy tails while warp 0 builds the head;
+//   * three CTA barriers per stage separate the phases.
+// Same arithmetic, expression by expression, as the two-warp variant of integrate_mode (reference map: see
+// include/discoeb_b200.h and the comments in deb_core.cuh).  Debug modes 1-3 are supported, tangents and shared-step
+// batches are not (they keep the one-warp kernels).
+#pragma once
+
+namespace deb {
+
+struct TeamBox {
+  double a_req, k;
+  double bgs[10];               // H, gc, gb, gg, gr, gnu, gq, wq1, ca2, wq at a_req
+  double vv[2 * NQMAX];         // v_i, 1/v_i
+  double kc[NCHMAX], kap[NCHMAX];
+  double sl[2 * NSLOT];         // operator slots at a_req (value part used)
+  double ic2[ICACHE];           // the helper's own spline interval cache
+  double ka0[8];                // element 0 of k_1..k_7
+};
+
+#ifdef DEB_CPU_EMU
+#define DEB_TID_PARAM
+#define DEB_T_BEGIN for (int tid = 0; tid < NT; ++tid) {
+#define DEB_T_END }
+#define DEB_T_BAR()
+#define DEB_TREGS(type, name, dims) type name##_all[NT] dims
+#define DEB_TUSE(name) auto& name = name##_all[tid]
+#define DEB_IF_WARP(w)
+#define DEB_T_OR(name) ([&]() { int a_ = 0; for (int l_ = 0; l_ < NT; ++l_) a_ |= (name##_all[l_] != 0); return a_; }())
+#else
+#define DEB_TID_PARAM , const int tid
+#define DEB_T_BEGIN {
+#define DEB_T_END }
+#define DEB_T_BAR() __syncthreads()
+#define DEB_TREGS(type, name, dims) type name dims
+#define DEB_TUSE(name)
+#define DEB_IF_WARP(w) if (wid == (w))
+#define DEB_T_OR(name) __syncthreads_or(name)
+#endif
+
+#define DEB_FOR_TEAM(body) _Pragma("unroll") for (int j = 0; j < NE; ++j) { const int e = tid + NT * j; if (e < n) { body } }
+
+// background at box.a_req -> chain coefficients, operator slots and the scalars of the metric sources (warp 1)
+DEB_DEV void team_helper_compute(const Problem& P, const CtaConst& C, const Cosmo& c, TeamBox& box, Hints& hint2 DEB_LANE_PARAM) {
+  const double k = box.k;
+  Bg<double> b;
+  compute_bg<double>(c, C.nu, P.nq, box.a_req, hint2, box.ic2, b);
+  DEB_LANES_BEGIN
+    if (lane < P.nch) chain_a_lane(c, C.nu, b, k, lane, box.kc, box.kap, box.vv, box.sl);
+    if (lane == 0) {
+      fill_slots<double>(c, b, k, box.sl);
+      box.bgs[0] = b.H; box.bgs[1] = b.gc; box.bgs[2] = b.gb; box.bgs[3] = b.gg; box.bgs[4] = b.gr; box.bgs[5] = b.gnu;
+      box.bgs[6] = b.gq; box.bgs[7] = b.wq1; box.bgs[8] = b.ca2; box.bgs[9] = b.wq;
+    }
+  DEB_LANES_END
+}
+
+template <int NE, int TEAM>
+DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W, TeamBox& box, int mode DEB_TID_PARAM) {
+  constexpr int NT = 32 * TEAM;
+#ifndef DEB_CPU_EMU
+  const int lane = tid & 31, wid = tid >> 5;
+#endif
+  const int n = P.n, nh = P.nh, nch = P.nch, nq = P.nq;
+  const int nhb = nh - 1;
+  const int cosmo = mode / P.nk, kidx = mode - cosmo * P.nk;
+  const double k = DEB_LDG(P.kmodes + (P.k_per_cosmo ? (size_t)cosmo * P.nk + kidx : (size_t)kidx));
+  const double k2 = k * k;
+  DEB_T_BEGIN
+    if (tid == 0) { *W.cosmo() = load_cosmo(P, cosmo); box.k = k; }
+  DEB_T_END
+  DEB_T_BAR();
+  const Cosmo& c = *W.cosmo();
+  const NuBins& nb = C.nu;
+  const double* tout = P.tau_out + (size_t)cosmo * P.nout;
+
+  DEB_REGS(int, pcol, );
+  DEB_REGS(double, rscale, );
+  DEB_REGS(unsigned, pkey, );
+  DEB_REGS(int, pivl, );
+  DEB_REGS(double, fmul, );
+  DEB_REGS(double, pval, );
+  DEB_REGS(double, s1, ); DEB_REGS(double, s2, ); DEB_REGS(double, s3, ); DEB_REGS(double, s4, );
+  DEB_TREGS(int, nanflag, );
+
+  // ---- prologue (every thread evaluates the scalars; the state is filled element-wise) ----
+  double t1 = DEB_LDG(tout);
+  double tmin_out = t1;
+  for (int j = 1; j < P.nout; ++j) { double tj = DEB_LDG(tout + j); t1 = fmax(t1, tj); tmin_out = fmin(tmin_out, tj); }
+  double t, tnext;
+  const size_t item = (size_t)mode;
+  if (P.mode == 1) {
+    t = DEB_LDG(P.dbg_t0 + mode); tnext = DEB_LDG(P.dbg_t1 + mode); t1 = tnext;
+    DEB_T_BEGIN
+      for (int e = tid; e < n; e += NT) W.y()[e] = DEB_LDG(P.dbg_y0 + (size_t)mode * n + e);
+    DEB_T_END
+  } else {
+    const double st0 = start_time(c, k, DEB_LDG(P.lt_small + cosmo));
+    double tau_start = 0.99 * fmin(tmin_out, st0);
+    if (!(st0 == st0)) tau_start = st0;
+    IcScalars ics = ic_scalars(c, tau_start, k);
+    DEB_T_BEGIN
+      for (int e = tid; e < n; e += NT) W.y()[e] = ic_value(P, c, nb, ics, elem_desc(P, e), k);
+    DEB_T_END
+    if (P.mode == 2) {
+      DEB_T_BEGIN
+        if (tid == 0) P.dbg_tau_start[item] = tau_start;
+        for (int e = tid; e < n; e += NT) P.dbg_ics[item * n + e] = W.y()[e];
+      DEB_T_END
+      DEB_T_BAR();
+      return;
+    }
+    t = tau_start;
+    tnext = t + fmin(t / 4.0, 0.5 * (t1 - t));          // dt0 (perturbations.py:756)
+    if (tnext > t1 - 1e-10) tnext = t1;
+  }
+  DEB_T_BAR();
+
+  double inv_prev = 1.0, inv_pprev = 1.0;
+  int nsteps = 0, nacc = 0, save_idx = 0, status = 0;
+  if (!(t == t) || !(tnext == tnext) || !(t1 == t1)) status = 2;
+  Hints hint; hint.th = -1; hint.nu = -1;          // warp 0 (Jacobian evaluation)
+  Hints hint2; hint2.th = -1; hint2.nu = -1;       // warp 1 (stage evaluations)
+
+  while (t < t1 && nsteps < P.max_steps && status == 0) {
+    if (P.mode == 3) {
+      if (nsteps >= DEB_LDG(P.rp_n + mode)) break;
+      tnext = DEB_LDG(P.rp_tnext + (size_t)mode * P.rp_stride + nsteps);
+      if (fabs(tnext - t1) <= 1e-12 * fabs(t1)) tnext = t1;
+    }
+    DEB_TREGS(double, ks, [7][NE]);    // stage vectors k_1..k_7 of the thread's own elements
+    const double dt = tnext - t;
+    const double invdt = DEB_RCP(dt);
+    const double idg = DEB_RCP(dt * RD_GAMMA);      // diagonal of W = I/(gamma dt) - J
+    const double invt0 = DEB_RCP(t);
+    const double gdt = dt * RD_GAMMA;
+
+    // ================= Jacobian pieces at (t, y) =================
+    Bg<Dual> bd;
+    DEB_IF_WARP(0) {
+      compute_bg<Dual>(c, nb, nq, mk(W.y()[0], 1.0), hint, W.ic(), bd);
+      DEB_LANES_BEGIN
+        if (lane < nch) chain_coeffs_lane<Dual>(c, nb, bd, k, lane, W.y(), P.iq0, W.kc(), W.kap(), W.nur(), W.nup(), W.sl());
+        if (lane == 0) fill_slots<Dual>(c, bd, k, W.sl());
+      DEB_LANES_END
+    }
+    DEB_T_BAR();                                      // kc, kap (value, d/da) visible to the team
+    DEB_IF_WARP(0) {
+      Metric<Dual> md;
+      compute_metric<Dual>(P, c, nb, bd, W.y(), k, W.nur(), W.nup(), md);
+      const double H = bd.H.v, a = bd.a.v;
+      DEB_LANES_BEGIN
+        if (lane < nh) {                      // head rows: f -> r (stage-1 right-hand side), d f/d a -> ja
+          const int e = C.hidx[lane];
+          Dual f = head_row<Dual>(C, W.sl(), W.y(), lane, md);
+          W.r()[e] = f.v; W.ja()[e] = f.d;
+        }
+        if (lane == 0) { Dual f = bd.H * bd.a; W.r()[0] = f.v; W.ja()[0] = f.d; }
+        if (lane < nh) {                      // head-column gradients of h', eta' and of row 1 (value parts only)
+          int ty = C.htype[lane], bin = C.hbin[lane];
+          double wr = 0.0, wp = 0.0, wt = 0.0, extra = 0.0;
+          switch (ty) {
+            case R_ETA: extra = 2.0 * k2 / H; break;
+            case R_DC: wr = bd.gc.v; break;
+            case R_TC: wt = bd.gc.v; break;
+            case R_DB: wr = bd.gb.v; break;
+            case R_TB: wt = bd.gb.v; break;
+            case R_F0: wr = bd.gg.v; wp = bd.gg.v / 3.0; break;
+            case R_F1: wt = 4.0 / 3.0 * bd.gg.v; break;
+            case R_N0: wr = bd.gr.v; wp = bd.gr.v / 3.0; break;
+            case R_N1: wt = 4.0 / 3.0 * bd.gr.v; break;
+            case R_P0: { const double vb = W.kc()[3 + bin] / k; wr = bd.gnu.v * nb.w[bin] / vb; wp = bd.gnu.v * nb.w[bin] * vb / 3.0; } break;
+            case R_P1: wt = bd.gnu.v * k * nb.w[bin]; break;
+            case R_DQ: wr = bd.gq.v; wp = c.cs2de * bd.gq.v; break;
+            case R_TQ: wt = bd.wq1.v * bd.gq.v; wp = (c.cs2de - bd.ca2.v) * 3.0 * H * wt / k2; break;
+            default: break;
+          }
+          W.gh()[lane] = wr / H + extra;
+          W.ge()[lane] = 0.5 * wt / k2;
+          W.j1()[lane] = -(wr + 3.0 * wp) * a;
+        }
+      DEB_LANES_END
+    }
+    DEB_IF_WARP(TEAM > 1 ? 1 : 0) {
+      // ---- tails: pivot-free backward elimination l = L .. 3 (one lane per chain) ----
+      DEB_LANES_BEGIN
+        if (lane < nch) {
+          const int base = C.ch_base[lane], s = C.ch_stride[lane], L = C.ch_lmax[lane];
+          const double kc = W.kc()[lane], kp = W.kap()[lane];
+          double e = idg + kp + (double)(L + 1) * invt0;
+          double ie = DEB_RCP(e);
+          int idx = base + L * s;
+          W.ie()[idx] = ie;
+          W.g()[idx] = kc * ie;
+          double lower_next = -kc;
+          for (int l = L - 1; l >= 2; --l) {
+            idx -= s;
+            double up = kc * C.ch[l];
+            double mm = up * ie;
+            W.m()[idx] = mm;
+            if (l >= 3) {
+              e = idg + kp - mm * lower_next;
+              ie = DEB_RCP(e);
+              W.ie()[idx] = ie;
+              lower_next = -kc * C.cl[l];
+              W.g()[idx] = -lower_next * ie;
+            } else {
+              W.ie()[idx] = -mm * lower_next;        // Schur increment for the head diagonal (l = 2 row)
+            }
+          }
+        }
+      DEB_LANES_END
+    }
+    {
+      // tail rows of f and d f/d a, two rows per trip
+      const double d1t = (dt * RD_D1) * invt0 * invt0;
+      // (warp 0 is busy with the head and warp 1 with the tail factors: the rows go to the other warps)
+      constexpr int TJ0 = TEAM >= 3 ? 64 : 0, NTJ = NT - TJ0;
+      DEB_T_BEGIN
+        if (tid >= TJ0)
+        for (int tt = tid - TJ0; tt < C.ntail; tt += 2 * NTJ) {
+          int e0, e1 = 0; double tr0, tr1 = 0.0;
+          const bool two = tt + NTJ < C.ntail;
+          Dual f0 = tail_row<Dual>(C, W.kc(), W.kap(), W.y(), C.tail[tt], invt0, &e0, &tr0);
+          Dual f1 = mk(0.0, 0.0);
+          if (two) f1 = tail_row<Dual>(C, W.kc(), W.kap(), W.y(), C.tail[tt + NTJ], invt0, &e1, &tr1);
+          W.r()[e0] = f0.v + d1t * tr0 * W.y()[e0]; W.ja()[e0] = f0.d;
+          if (two) { W.r()[e1] = f1.v + d1t * tr1 * W.y()[e1]; W.ja()[e1] = f1.d; }
+        }
+      DEB_T_END
+    }
+    DEB_T_BAR();                                      // r, ja, tail factors complete
+    const double x0piv = idg - W.ja()[0];            // W_00 = 1/(gamma dt) - d(H a)/da
+    double x0 = W.r()[0] / x0piv;                    // stage 1 (every thread: the same bits)
+
+    double ci_hh = 0.0, ci_he = 0.0, ci_eh = 0.0, ci_ee = 0.0, jq_h = 0.0, jq_e = 0.0;
+    DEB_IF_WARP(0) {
+      // ---- head:  W_h = D - chv gh^T - cev ge^T  (+ the a h' row); D block diagonal -> block inverses + Woodbury
+      DEB_LANES_BEGIN
+        DEB_USE(pcol); DEB_USE(rscale);
+        pcol = -1; rscale = 1.0;
+        if (lane < nhb) {
+          const int ty = C.htype[lane], lo = C.blo[lane];
+          double* row = hrow(W, lane, lo);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) row[lo + i] = 0.0;
+          double diag = idg;
+          if (ty == R_F2 || ty == R_G2 || ty == R_N2 || ty == R_P2) {      // Schur complement of the chain tail
+            const int chain = ty == R_F2 ? 0 : (ty == R_G2 ? 1 : (ty == R_N2 ? 2 : 3 + C.hbin[lane]));
+            diag += W.ie()[C.ch_base[chain] + 2 * C.ch_stride[chain]];
+          }
+          row[lane] = diag;
+#pragma unroll
+          for (int q = 0; q < HOP_NT; ++q) {
+            const int m = C.hop_meta[q][lane], hc = (m >> 20) - 1;
+            if (hc >= 0) row[hc] -= C.hop_c[q][lane] * W.sl()[m & 0xff];
+          }
+        }
+      DEB_LANES_END
+      for (int bt = 0; bt < 8; ++bt) {
+        DEB_LANES_BEGIN
+          DEB_USE(pcol); DEB_USE(pkey);
+          const int lo = C.blo[lane], hi = C.bhi[lane];
+          pkey = (lane < nhb && lo + bt < hi && pcol < 0) ? hi32abs(hrow(W, lane, lo)[lo + bt]) + 1u : 0u;
+        DEB_LANES_END
+        DEB_LANES_BEGIN
+          DEB_USE(pcol); DEB_USE(rscale); DEB_USE(pkey); DEB_USE(pivl); DEB_USE(fmul);
+          const int lo = C.blo[lane], hi = C.bhi[lane], j = lo + bt;
+          int piv = lane; unsigned best = 0u;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int src = (lo + i < hi) ? lo + i : lane;
+            const unsigned kk = DEB_SHFL(pkey, src);
+            if (lo + i < hi && kk > best) { best = kk; piv = lo + i; }
+          }
+          pivl = piv; fmul = 0.0;
+          if (lane < nhb && j < hi) {
+            const double ipv = DEB_RCP(hrow(W, piv, lo)[j]);
+            if (lane == piv) { pcol = j; rscale = ipv; W.perm()[j] = piv; }
+            else fmul = hrow(W, lane, lo)[j] * ipv;
+          }
+        DEB_LANES_END
+        DEB_LANES_BEGIN
+          DEB_USE(pivl); DEB_USE(fmul);
+          const int lo = C.blo[lane], hi = C.bhi[lane], j = lo + bt;
+          if (lane < nhb && j < hi) {
+            double* row = hrow(W, lane, lo);
+            if (lane == pivl) row[j] = 1.0;
+            else {
+              const double* rb = row + lo;
+              const double* pb = hrow(W, pivl, lo) + lo;
+              const double f = fmul;
+              double ra[8], pa[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) { ra[i] = rb[i]; pa[i] = (i == bt) ? 0.0 : pb[i]; }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) row[lo + i] = (i == bt) ? -f : ra[i] - f * pa[i];
+            }
+          }
+        DEB_LANES_END
+      }
+      DEB_LANES_BEGIN
+        DEB_USE(rscale);
+        if (lane < nhb) {
+          double* rb = hrow(W, lane, C.blo[lane]) + C.blo[lane];
+          double ra[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) ra[i] = rb[i];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) rb[i] = ra[i] * rscale;
+        }
+        W.xb()[lane] = 0.0;
+      DEB_LANES_END
+      DEB_LANES_BEGIN
+        DEB_USE(pcol); DEB_USE(s1); DEB_USE(s2); DEB_USE(s3); DEB_USE(s4);
+        s1 = s2 = s3 = s4 = 0.0;
+        if (lane < nhb) {
+          const int lo = C.blo[lane], hi = C.bhi[lane];
+          const double* row = hrow(W, lane, lo);
+          double ah = 0.0, ae = 0.0;
+          for (int cc = lo; cc < hi; ++cc) {
+            const int pr = W.perm()[cc];
+            ah += row[cc] * (C.hop_chc[pr] * W.sl()[C.hop_chs[pr]]);
+            ae += row[cc] * C.hop_cec[pr];
+          }
+          W.qh()[pcol] = ah; W.qe()[pcol] = ae;
+          const double ghc = W.gh()[pcol], gec = W.ge()[pcol], j1c = W.j1()[pcol];
+          s1 = ghc * ah; s2 = ghc * ae; s3 = gec * ah; s4 = gec * ae;
+          W.xb()[lane] = j1c;
+        }
+      DEB_LANES_END
+      {
+        const double c_hh = 1.0 - DEB_WARP_SUM(s1), c_he = -DEB_WARP_SUM(s2), c_eh = -DEB_WARP_SUM(s3), c_ee = 1.0 - DEB_WARP_SUM(s4);
+        const double idet = DEB_RCP(c_hh * c_ee - c_he * c_eh);
+        ci_hh = c_ee * idet; ci_he = -c_he * idet; ci_eh = -c_eh * idet; ci_ee = c_hh * idet;
+        DEB_LANES_BEGIN
+          DEB_USE(pcol); DEB_USE(s1); DEB_USE(s2);
+          s1 = s2 = 0.0;
+          if (lane < nhb) { const double j1c = W.xb()[lane]; s1 = j1c * W.qh()[pcol]; s2 = j1c * W.qe()[pcol]; }
+        DEB_LANES_END
+        jq_h = DEB_WARP_SUM(s1); jq_e = DEB_WARP_SUM(s2);
+      }
+    }
+
+    // ================= 8 stages =================
+    double errnorm2 = 0.0;
+#pragma unroll 1
+    for (int st = 1; st <= 8; ++st) {
+      if (st > 1) {
+        const double ts = st == 2 ? t + RD_CT2 * dt : st == 3 ? t + RD_CT3 * dt : st == 4 ? t + RD_CT4 * dt
+                        : st == 5 ? t + RD_CT5 * dt : t + dt;
+        const double dtd = st == 2 ? dt * RD_D2 : st == 3 ? dt * RD_D3 : st == 4 ? dt * RD_D4 : st == 5 ? dt * RD_D5 : 0.0;
+        // ---- own elements: keep k_{st-1}, stage state u, C-combinations -> r ----
+        DEB_T_BEGIN
+          DEB_TUSE(ks);
+          switch (st) {
+            case 2: DEB_FOR_TEAM(const double kv = e == 0 ? x0 : W.r()[e]; ks[0][j] = kv;
+                                 W.u()[e] = W.y()[e] + RD_A21 * ks[0][j];
+                                 W.r()[e] = invdt * (RD_C21 * ks[0][j]);) break;
+            case 3: DEB_FOR_TEAM(const double kv = e == 0 ? x0 : W.r()[e]; ks[1][j] = kv;
+                                 W.u()[e] = W.y()[e] + RD_A31 * ks[0][j] + RD_A32 * ks[1][j];
+                                 W.r()[e] = invdt * (RD_C31 * ks[0][j] + RD_C32 * ks[1][j]);) break;
+            case 4: DEB_FOR_TEAM(const double kv = e == 0 ? x0 : W.r()[e]; ks[2][j] = kv;
+                                 W.u()[e] = W.y()[e] + RD_A41 * ks[0][j] + RD_A42 * ks[1][j] + RD_A43 * ks[2][j];
+                                 W.r()[e] = invdt * (RD_C41 * ks[0][j] + RD_C42 * ks[1][j] + RD_C43 * ks[2][j]);) break;
+            case 5: DEB_FOR_TEAM(const double kv = e == 0 ? x0 : W.r()[e]; ks[3][j] = kv;
+                                 W.u()[e] = W.y()[e] + RD_A51 * ks[0][j] + RD_A52 * ks[1][j] + RD_A53 * ks[2][j] + RD_A54 * ks[3][j];
+                                 W.r()[e] = invdt * (RD_C51 * ks[0][j] + RD_C52 * ks[1][j] + RD_C53 * ks[2][j] + RD_C54 * ks[3][j]);) break;
+            case 6: DEB_FOR_TEAM(const double kv = e == 0 ? x0 : W.r()[e]; ks[4][j] = kv;
+                                 W.u()[e] = W.y()[e] + RD_A61 * ks[0][j] + RD_A62 * ks[1][j] + RD_A63 * ks[2][j] + RD_A64 * ks[3][j] + RD_A65 * ks[4][j];
+                                 W.r()[e] = invdt * (RD_C61 * ks[0][j] + RD_C62 * ks[1][j] + RD_C63 * ks[2][j] + RD_C64 * ks[3][j] + RD_C65 * ks[4][j]);) break;
+            case 7: DEB_FOR_TEAM(const double kv = e == 0 ? x0 : W.r()[e]; ks[5][j] = kv;
+                                 W.u()[e] = W.u()[e] + ks[5][j];
+                                 W.r()[e] = invdt * (RD_C71 * ks[0][j] + RD_C72 * ks[1][j] + RD_C73 * ks[2][j] + RD_C74 * ks[3][j] + RD_C75 * ks[4][j] + RD_C76 * ks[5][j]);) break;
+            default: DEB_FOR_TEAM(const double kv = e == 0 ? x0 : W.r()[e]; ks[6][j] = kv;
+                                 W.u()[e] = W.u()[e] + ks[6][j];
+                                 W.r()[e] = invdt * (RD_C81 * ks[0][j] + RD_C82 * ks[1][j] + RD_C83 * ks[2][j] + RD_C84 * ks[3][j] + RD_C85 * ks[4][j] + RD_C86 * ks[5][j] + RD_C87 * ks[6][j]);) break;
+          }
+          if (tid == 0) W.u()[0] = box.a_req;         // exactly the value the helper evaluated the background at
+        DEB_T_END
+        DEB_T_BAR();                                   // u, r (C-combinations) and the helper's scalars visible
+        // ---- f(ts, u) + dt d_i dT added onto r ----
+        const double invts = DEB_RCP(ts);
+        const double dtt = dtd * invt0 * invt0;
+        DEB_IF_WARP(0) {
+          Bg<double> b;
+          b.a = box.a_req;
+          b.H = box.bgs[0]; b.gc = box.bgs[1]; b.gb = box.bgs[2]; b.gg = box.bgs[3]; b.gr = box.bgs[4]; b.gnu = box.bgs[5];
+          b.gq = box.bgs[6]; b.wq1 = box.bgs[7]; b.ca2 = box.bgs[8]; b.wq = box.bgs[9];
+          b.opac = box.sl[SL_OPAC]; b.pbo = box.sl[SL_PBO]; b.cs2 = 0.0;
+          DEB_LANES_BEGIN
+            if (lane >= 3 && lane < nch) nu_moments_lane(nb, box.vv, W.u(), P.iq0, lane - 3, W.nur(), W.nup());
+          DEB_LANES_END
+          Metric<double> mt;
+          compute_metric<double>(P, c, nb, b, W.u(), k, W.nur(), W.nup(), mt);
+          DEB_LANES_BEGIN
+            if (lane < nh) {
+              const int e = C.hidx[lane];
+              W.r()[e] += head_row<double>(C, box.sl, W.u(), lane, mt);
+            }
+            if (lane == 0) W.r()[0] += b.H * b.a;
+          DEB_LANES_END
+        }
+        // (warp 0 evaluates the metric sources and the head rows meanwhile: the tail rows go to the other warps)
+        constexpr int TS0 = TEAM >= 2 ? 32 : 0, NTS = NT - TS0;
+        DEB_T_BEGIN
+          if (tid >= TS0)
+          for (int tt = tid - TS0; tt < C.ntail; tt += 2 * NTS) {
+            int e0, e1 = 0; double tr0, tr1 = 0.0, f1 = 0.0, r1 = 0.0, y1 = 0.0;
+            const bool two = tt + NTS < C.ntail;
+            const double f0 = tail_row<double>(C, box.kc, box.kap, W.u(), C.tail[tt], invts, &e0, &tr0);
+            const double r0 = W.r()[e0], y0 = W.y()[e0];
+            if (two) { f1 = tail_row<double>(C, box.kc, box.kap, W.u(), C.tail[tt + NTS], invts, &e1, &tr1); r1 = W.r()[e1]; y1 = W.y()[e1]; }
+            W.r()[e0] = r0 + f0 + dtt * tr0 * y0;
+            if (two) W.r()[e1] = r1 + f1 + dtt * tr1 * y1;
+          }
+        DEB_T_END
+        DEB_T_BAR();                                   // r complete
+        x0 = W.r()[0] / x0piv;
+      }
+
+      // ---- warp 1: background scalars of stage st+1 at a = y_0 + sum_j a_{st+1,j} k_{j,0}  (k_{st,0} = x0) ----
+      if (st < 8) {
+        DEB_IF_WARP(TEAM > 1 ? 1 : 0) {
+          DEB_LANES_BEGIN
+            if (lane == 0) {
+              box.ka0[st - 1] = x0;
+              const double* ka = box.ka0;
+              double an;
+              switch (st) {
+                case 1: an = W.y()[0] + RD_A21 * x0; break;
+                case 2: an = W.y()[0] + RD_A31 * ka[0] + RD_A32 * x0; break;
+                case 3: an = W.y()[0] + RD_A41 * ka[0] + RD_A42 * ka[1] + RD_A43 * x0; break;
+                case 4: an = W.y()[0] + RD_A51 * ka[0] + RD_A52 * ka[1] + RD_A53 * ka[2] + RD_A54 * x0; break;
+                case 5: an = W.y()[0] + RD_A61 * ka[0] + RD_A62 * ka[1] + RD_A63 * ka[2] + RD_A64 * ka[3] + RD_A65 * x0; break;
+                default: an = W.u()[0] + x0; break;        // stages 7 and 8: u + k
+              }
+              box.a_req = an;
+            }
+          DEB_LANES_END
+          team_helper_compute(P, C, c, box, hint2 DEB_LANE_ARG);
+        }
+      }
+
+      // ---- warp 0: solve W x = r in place (x_0 = x0 is already known; its column is folded in on the fly) ----
+      DEB_IF_WARP(0) {
+        DEB_LANES_BEGIN
+          if (lane < nch) {          // backward sweep: b'_l = b_l - m_l b'_{l+1}, l = L-1 .. 2, with b_l = r_l + ja_l x0
+            const int s = C.ch_stride[lane], L = C.ch_lmax[lane];
+            const int iL = C.ch_base[lane] + L * s;
+            double* rp = W.r() + iL;
+            const double* jp = W.ja() + iL;
+            const double* mp = W.m() + iL;
+            double bp = *rp + *jp * x0;
+            *rp = bp;
+            rp -= s; jp -= s; mp -= s;
+            double rn = *rp + *jp * x0, mn = *mp;
+#pragma unroll 4
+            for (int l = L - 1; l > 2; --l) {
+              const double rc = rn, mc = mn;
+              rn = *(rp - s) + *(jp - s) * x0; mn = *(mp - s);
+              bp = rc - mc * bp;
+              *rp = bp;
+              rp -= s; jp -= s; mp -= s;
+            }
+            *rp = rn - mn * bp;
+          }
+        DEB_LANES_END
+        // head: p = D^-1 b (block inverses), then the rank-2 Woodbury correction and the a h' row
+        DEB_LANES_BEGIN
+          double xv = 0.0;
+          if (lane < nhb) {
+            const int pr = W.perm()[lane], e = C.hidx[pr], ty = C.htype[pr];
+            const bool swept = (ty == R_F2 || ty == R_G2 || ty == R_N2 || ty == R_P2);     // the sweep already added the column
+            xv = swept ? W.r()[e] : W.r()[e] + W.ja()[e] * x0;
+          }
+          W.xb()[lane] = xv;
+          if (lane < 8) W.xb()[NHMAX + lane] = 0.0;
+        DEB_LANES_END
+        DEB_LANES_BEGIN
+          DEB_USE(pcol); DEB_USE(s1); DEB_USE(s2); DEB_USE(s3); DEB_USE(pval);
+          s1 = s2 = s3 = 0.0; pval = 0.0;
+          if (lane < nhb) {
+            const int lo = C.blo[lane];
+            const double* rb = hrow(W, lane, lo) + lo;
+            const double* xb = W.xb() + lo;
+            double ra[8], xa[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { ra[i] = rb[i]; xa[i] = xb[i]; }
+            const double acc = ((ra[0] * xa[0] + ra[1] * xa[1]) + (ra[2] * xa[2] + ra[3] * xa[3]))
+                             + ((ra[4] * xa[4] + ra[5] * xa[5]) + (ra[6] * xa[6] + ra[7] * xa[7]));
+            pval = acc;
+            s1 = W.gh()[pcol] * acc; s2 = W.ge()[pcol] * acc; s3 = W.j1()[pcol] * acc;
+          }
+        DEB_LANES_END
+        {
+          const double th = DEB_WARP_SUM(s1), te = DEB_WARP_SUM(s2), ta = DEB_WARP_SUM(s3);
+          const double sh = ci_hh * th + ci_he * te, se = ci_eh * th + ci_ee * te;
+          DEB_LANES_BEGIN
+            DEB_USE(pcol); DEB_USE(pval);
+            if (lane < nhb) W.r()[C.hidx[pcol]] = pval + W.qh()[pcol] * sh + W.qe()[pcol] * se;
+            else if (lane == nhb) W.r()[1] = ((W.r()[1] + W.ja()[1] * x0) + ta + jq_h * sh + jq_e * se) * gdt;
+          DEB_LANES_END
+        }
+        DEB_LANES_BEGIN
+          if (lane < nch) {          // forward sweep: x_l = b'_l/e_l + g_l x_{l-1}, l = 3 .. L
+            const int s = C.ch_stride[lane], L = C.ch_lmax[lane];
+            const int i0 = C.ch_base[lane] + 2 * s;
+            double* rp = W.r() + i0;
+            const double* ip = W.ie() + i0;
+            const double* gp = W.g() + i0;
+            double x = *rp;
+            rp += s; ip += s; gp += s;
+            double cn = *rp * *ip, gn = *gp;
+#pragma unroll 4
+            for (int l = 3; l < L; ++l) {
+              const double cc = cn, gc = gn;
+              cn = *(rp + s) * *(ip + s); gn = *(gp + s);
+              x = cc + gc * x;
+              *rp = x;
+              rp += s; ip += s; gp += s;
+            }
+            *rp = cn + gn * x;
+          }
+        DEB_LANES_END
+      }
+      DEB_T_BAR();                                     // r = k_st (element 0: x0), the helper's results posted
+    }
+
+    // y1 = u + k8 -> u ; err = k8 = r
+    DEB_T_BEGIN
+      DEB_TUSE(nanflag);
+      nanflag = 0;
+      DEB_FOR_TEAM(const double kv = e == 0 ? x0 : W.r()[e]; if (e == 0) W.r()[0] = x0;
+                   const double y1v = W.u()[e] + kv; W.u()[e] = y1v; nanflag |= (y1v != y1v);)
+    DEB_T_END
+    bool anynan = DEB_T_OR(nanflag) != 0;              // (a barrier)
+
+    if (P.mode == 1) {
+      DEB_T_BEGIN
+        for (int e = tid; e < n; e += NT) { P.dbg_y1[item * n + e] = W.u()[e]; P.dbg_err[item * n + e] = W.r()[e]; }
+      DEB_T_END
+      DEB_T_BAR();
+      return;
+    }
+
+    // ================= error norm, PID controller (diffrax semantics) =================
+    {
+      const double ik2 = DEB_RCP(k2);
+#define DEB_ERRC(e, w) { double y0v = W.y()[e], y1v = anynan ? y0v : W.u()[e], ev = W.r()[e]; if (ev != ev) ev = INFINITY; \
+        double sc = ev / (P.atol + fmax(fabs(y0v), fabs(y1v)) * P.rtol) * (w); errnorm2 += sc * sc; }
+      DEB_ERRC(0, 1.0) DEB_ERRC(2, k2) DEB_ERRC(3, 1.0) DEB_ERRC(5, 1.0) DEB_ERRC(6, ik2) DEB_ERRC(7, 1.0)
+#undef DEB_ERRC
+    }
+    DEB_T_BAR();          // y, u, r are rewritten below (output sampling, accepted state)
+    const double E = sqrt(errnorm2 / 6.0);
+    const bool keep = (P.mode == 3) ? (DEB_LDG(P.rp_keep + (size_t)mode * P.rp_stride + nsteps) != 0) : (E < 1.0);
+    double inv = 1.0 / E;
+    double f1 = P.c1 != 0.0 ? ((inv > 0.0 && !isinf(inv)) ? exp(P.c1 * log(inv)) : pow(inv, P.c1)) : 1.0;
+    double f2 = P.c2 != 0.0 ? exp(P.c2 * log(inv_prev)) : 1.0;
+    double f3 = P.c3 != 0.0 ? exp(P.c3 * log(inv_pprev)) : 1.0;
+    double fac = fmin(fmax(P.safety * f1 * f2 * f3, keep ? 1.0 : P.factormin), P.factormax);
+    if (!(fac == fac)) fac = NAN;
+    const double dtn = dt * fac;
+    if (inv == 0.0 || isinf(inv)) inv = 1.0;
+    ++nsteps;
+    if (keep) {
+      ++nacc;
+      // SaveAt(ts): linear interpolation inside the accepted step
+      while (save_idx < P.nout && DEB_LDG(tout + save_idx) <= tnext) {
+        const double tt = DEB_LDG(tout + save_idx);
+        const double coeff = (tnext == t) ? 0.0 : (tt - t) / (tnext - t);
+        const size_t obase = ((size_t)mode * P.nout + save_idx);
+        if (P.return_full) {
+          DEB_T_BEGIN
+            for (int e = tid; e < n; e += NT) P.y_out[obase * n + e] = W.y()[e] + coeff * (W.u()[e] - W.y()[e]);
+          DEB_T_END
+        } else {
+          DEB_T_BEGIN
+            for (int e = tid; e < n; e += NT) W.r()[e] = W.y()[e] + coeff * (W.u()[e] - W.y()[e]);
+          DEB_T_END
+          DEB_T_BAR();
+          DEB_T_BEGIN
+            if (tid == 0) {
+              double o20[20];
+              convert_outputs(P, c, nb, W.r(), k, o20);
+              for (int q = 0; q < 20; ++q) P.y_out[obase * 20 + q] = o20[q];
+              if (P.pk_out && P.power_idx >= 0) {
+                double yv = o20[P.power_idx];
+                P.pk_out[obase] = 2.0 * 9.869604401089358 * c.As * pow(k / c.kp, c.ns - 1.0) * pow(k, -3.0) * yv * yv;
+              }
+            }
+          DEB_T_END
+          DEB_T_BAR();
+        }
+        ++save_idx;
+      }
+      DEB_T_BEGIN
+        DEB_FOR_TEAM(W.y()[e] = W.u()[e];)
+      DEB_T_END
+      inv_pprev = inv_prev; inv_prev = inv;
+      t = fmin(tnext, t1);
+    }
+    DEB_T_BAR();          // the accepted state is visible before the next Jacobian evaluation
+    double tn = t + dtn;
+    if (tn > t1 - 1e-10) {
+      if (keep) tn = t1; else tn = t + 0.5 * (t1 - t);
+    }
+    tnext = tn;
+    if (!(tnext == tnext) || isinf(tnext)) status = 2;
+  }
+  if (status == 0 && t < t1) status = 1;
+  DEB_T_BEGIN
+    if (tid == 0) {
+      P.status[mode] = status; P.nsteps[mode] = nsteps;
+      if (P.naccept) P.naccept[mode] = nacc;
+    }
+  DEB_T_END
+}
+
+}  // namespace deb

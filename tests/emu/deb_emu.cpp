@@ -10,6 +10,7 @@
 #include <vector>
 #include "../../include/discoeb_b200.h"
 #include "../../disco-eb_b200/csrc/deb_core.cuh"
+#include "../../disco-eb_b200/csrc/deb_team.cuh"
 #include "../../disco-eb_b200/csrc/deb_host.inl"
 
 using namespace deb;
@@ -127,8 +128,41 @@ static int dispatch_batched(const Problem& P) {
   if (ne <= 12) return run_batched<12>(P);
   return DEB_E_UNSUPPORTED;
 }
+// DEB_EMU_TEAM=T selects the CTA-per-mode variant (deb_team.cuh) with T warps per mode, the threads run by loops
+template <int NE, int TEAM>
+static void run_all_team(const Problem& P) {
+  CtaConst C;
+  std::vector<int> tail(P.np);
+  for (int t = 0; t < 32; ++t) init_cta_const(P, C, tail.data(), t, 32);
+  std::vector<double> ws(warp_ws_doubles(P.np));
+  const int total = P.ncosmo * P.nk;
+#pragma omp parallel for schedule(dynamic, 1) firstprivate(ws)
+  for (int m = 0; m < total; ++m) {
+    WarpWs W;
+    carve(W, ws.data(), P.np);
+    TeamBox box;
+    integrate_mode_team<NE, TEAM>(P, C, W, box, total - 1 - m);
+  }
+}
+template <int TEAM>
+static int dispatch_team(const Problem& P) {
+  const int ne = (P.n + 32 * TEAM - 1) / (32 * TEAM);
+  if (ne <= 1) run_all_team<1, TEAM>(P);
+  else if (ne <= 2) run_all_team<2, TEAM>(P);
+  else if (ne <= 3) run_all_team<3, TEAM>(P);
+  else if (ne <= 4) run_all_team<4, TEAM>(P);
+  else if (ne <= 6) run_all_team<6, TEAM>(P);
+  else return DEB_E_UNSUPPORTED;
+  return DEB_OK;
+}
 static int dispatch(const Problem& P) {
   if (P.batch_size > 0) return dispatch_batched(P);
+  if (const char* tm = getenv("DEB_EMU_TEAM")) {
+    const int T = atoi(tm);
+    if (T == 2) return dispatch_team<2>(P);
+    if (T == 4) return dispatch_team<4>(P);
+    if (T == 8) return dispatch_team<8>(P);
+  }
   const char* h = getenv("DEB_EMU_HELPER");
   return (h && h[0] == '1') ? dispatch_h<true>(P) : dispatch_h<false>(P);
 }

@@ -33,6 +33,39 @@ def test_adaptive_solve_against_oracle(gpu_lib, tables, name):
     pc.check_adaptive(gpu_lib, tables, name)
 
 
+@pytest.mark.parametrize("variant", ["warp", "team"])
+@pytest.mark.parametrize("name", helpers.CASES)
+def test_forced_kernel_variants(gpu_lib, tables, name, variant, monkeypatch):
+    """Small launches pick the CTA-per-mode kernel (deb_team.cu) on their own; DEB_VARIANT pins the choice so that the
+    one-warp kernel (what large launches run) and the team kernel both face the oracle in every debug mode."""
+    monkeypatch.setenv("DEB_VARIANT", variant)
+    pc.check_prologue(gpu_lib, tables, name)
+    pc.check_single_step(gpu_lib, tables, name)
+    pc.check_replay(gpu_lib, tables, name)
+    pc.check_adaptive(gpu_lib, tables, name)
+
+
+def test_team_kernel_is_bit_identical_to_two_warp_kernel(gpu_lib, tables, monkeypatch):
+    """BASELINE config 2 at full size: the team kernel distributes the same arithmetic over 4 warps, so every mode's
+    step counts and outputs equal the main+helper kernel's bit for bit (a race or a missing barrier would show here)."""
+    from discoeb_b200 import _cabi
+    tab = tables["fiducial"]
+    nk = 512
+    ks = np.geomspace(1e-4, 10.0, nk)
+    dims = _cabi.make_dims(ncosmo=1, nk=nk, nout=1, lmaxg=31, lmaxgp=31, lmaxr=31, lmaxnu=31, nqmax=5, nth=tab.nth,
+                           nnu=tab.nnu, max_steps=2048, power_idx=4)
+    ctrl = _cabi.make_ctrl(rtol=1e-4, atol=1e-4)
+    res = {}
+    for v in ("helper", "team"):
+        monkeypatch.setenv("DEB_VARIANT", v)
+        res[v] = gpu_lib.evolve_host(dims, ctrl, tab.scalars[None], tab.tables[None], ks, np.array([1.0]), want_pk=True)
+        assert np.all(res[v]["status"] == 0)
+    assert np.array_equal(res["team"]["nsteps"], res["helper"]["nsteps"])
+    assert np.array_equal(res["team"]["y"], res["helper"]["y"])
+    assert np.array_equal(res["team"]["pk"], res["helper"]["pk"])
+    print("kernel_ms helper", res["helper"]["kernel_ms"], "team", res["team"]["kernel_ms"])
+
+
 def test_gpu_matches_cpu_build_of_same_source(gpu_lib, emu_lib, tables):
     """Same source, two compilers: any difference beyond round-off is a GPU-only defect
     (missing __syncwarp, shuffle misuse, shared-memory race)."""

@@ -117,6 +117,34 @@ def test_two_warp_variant_source(emu_lib, tables, name, monkeypatch):
             assert helpers.field_scaled_diff(two["y"][0, m], one["y"][0, m]).max() < 1e-6
 
 
+@pytest.mark.parametrize("team", ["2", "4", "8"])
+@pytest.mark.parametrize("name", ["default_n72", "config2_n265", "odd_dims_n43", "min_dims_n33", "many_out_n72"])
+def test_team_variant_source(emu_lib, tables, name, team, monkeypatch):
+    """The CTA-per-mode code path (deb_team.cuh; the team's threads run by loops in the CPU build): prologue,
+    single step and replay against the oracle, and the free-running solve BIT-identical to the main+helper
+    path (same arithmetic, expression by expression; only the distribution over threads differs)."""
+    from discoeb_b200 import _cabi
+    case = helpers.load_case(name)
+    tab = tables[str(case["cosmology"])]
+    ks, aout, rtol = case["kmodes"], case["aexp_out"], float(case["rtol"])
+    dims = pc.dims_for(case, tab, len(ks), len(aout))
+    ctrl = _cabi.make_ctrl(rtol=rtol, atol=rtol)
+    monkeypatch.setenv("DEB_EMU_HELPER", "1")
+    two = emu_lib.evolve_host(dims, ctrl, tab.scalars[None], tab.tables[None], ks, aout, want_pk=False)
+    monkeypatch.setenv("DEB_EMU_TEAM", team)
+    pc.check_prologue(emu_lib, tables, name)
+    pc.check_single_step(emu_lib, tables, name)
+    pc.check_replay(emu_lib, tables, name)
+    tm = emu_lib.evolve_host(dims, ctrl, tab.scalars[None], tab.tables[None], ks, aout, want_pk=False)
+    assert np.array_equal(tm["nsteps"], two["nsteps"]) and np.array_equal(tm["naccept"], two["naccept"])
+    assert np.array_equal(tm["y"], two["y"])
+
+
+def test_team_variant_edge_shapes(emu_lib, tables, monkeypatch):
+    monkeypatch.setenv("DEB_EMU_TEAM", "4")
+    pc.check_edge_shapes(emu_lib, tables)
+
+
 def test_edge_shapes(emu_lib, tables):
     pc.check_edge_shapes(emu_lib, tables)
 
