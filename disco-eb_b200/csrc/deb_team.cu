@@ -8,6 +8,9 @@
 #include <stdlib.h>
 #include "../../include/discoeb_b200.h"
 #include "deb_core.cuh"
+#ifdef DEB_TEAM_TIMING
+__device__ long long g_team_timing[16];
+#endif
 #include "deb_team.cuh"
 
 using namespace deb;
@@ -17,7 +20,8 @@ using namespace deb;
 
 static __host__ __device__ size_t al16(size_t b) { return (b + 15) & ~(size_t)15; }
 static __host__ __device__ size_t team_smem_bytes(int np) {
-  return al16(sizeof(CtaConst)) + al16((size_t)np * sizeof(int)) + al16(warp_ws_doubles(np) * sizeof(double)) + al16(sizeof(TeamBox)) + 16;
+  return al16(sizeof(CtaConst)) + 2 * al16((size_t)np * sizeof(int)) + al16((warp_ws_doubles(np) + team_ws_doubles(np)) * sizeof(double))
+       + al16(sizeof(TeamBox)) + 16;
 }
 
 template <int NE, int TEAM, int MINB>
@@ -27,16 +31,22 @@ __global__ void __launch_bounds__(32 * TEAM, MINB) k_evolve_team(const __grid_co
   size_t off = al16(sizeof(CtaConst));
   int* tail = reinterpret_cast<int*>(smem_raw + off);
   off += al16((size_t)P.np * sizeof(int));
+  int* eslot = reinterpret_cast<int*>(smem_raw + off);
+  off += al16((size_t)P.np * sizeof(int));
   double* wsb = reinterpret_cast<double*>(smem_raw + off);
-  off += al16(warp_ws_doubles(P.np) * sizeof(double));
+  off += al16((warp_ws_doubles(P.np) + team_ws_doubles(P.np)) * sizeof(double));
   TeamBox* box = reinterpret_cast<TeamBox*>(smem_raw + off);
   off += al16(sizeof(TeamBox));
   unsigned int* s_tk = reinterpret_cast<unsigned int*>(smem_raw + off);
   const int tid = threadIdx.x;
   init_cta_const(P, *C, tail, tid, 32 * TEAM);
   __syncthreads();
+  init_team_const(P, *C, eslot, tid, 32 * TEAM);
+  __syncthreads();
   WarpWs W;
   carve(W, wsb, P.np);
+  TeamWs X;
+  X.mc = wsb + warp_ws_doubles(P.np); X.gc = X.mc + P.np; X.eslot = eslot;
   const int total = P.ncosmo * P.nk;
   for (;;) {
     if (tid == 0) *s_tk = atomicAdd(P.ticket, 1u);
@@ -46,7 +56,7 @@ __global__ void __launch_bounds__(32 * TEAM, MINB) k_evolve_team(const __grid_co
     // largest k first, cosmologies interleaved
     const int kd = tk / P.ncosmo, cs = tk - kd * P.ncosmo;
     const int mode = cs * P.nk + (P.nk - 1 - kd);
-    integrate_mode_team<NE, TEAM>(P, *C, W, *box, mode, tid);
+    integrate_mode_team<NE, TEAM>(P, *C, W, X, *box, mode, tid);
     __syncthreads();
   }
 }
@@ -85,3 +95,12 @@ int deb_launch_team(const Problem& P, cudaStream_t st, int nsm) {
   CUDA_TRY(cudaGetLastError());
   return DEB_OK;
 }
+
+#ifdef DEB_TEAM_TIMING
+// measurement build only: cycles warp 0 of the largest-k mode spent per phase (see DEB_TICK), slot 15 = steps
+extern "C" int deb_debug_team_timing(long long* out16, int reset) {
+  if (out16) CUDA_TRY(cudaMemcpyFromSymbol(out16, g_team_timing, sizeof(long long) * 16));
+  if (reset) { long long z[16] = {0}; CUDA_TRY(cudaMemcpyToSymbol(g_team_timing, z, sizeof(z))); }
+  return DEB_OK;
+}
+#endif

@@ -19,21 +19,67 @@
 
 namespace deb {
 
-struct TeamBox {
-  double a_req, k;
+struct TeamBg {                 // what warp 1 posts for one stage (double-buffered by stage parity)
+  double a_req;
   double bgs[10];               // H, gc, gb, gg, gr, gnu, gq, wq1, ca2, wq at a_req
   double vv[2 * NQMAX];         // v_i, 1/v_i
   double kc[NCHMAX], kap[NCHMAX];
   double sl[2 * NSLOT];         // operator slots at a_req (value part used)
-  double ic2[ICACHE];           // the helper's own spline interval cache
-  double ka0[8];                // element 0 of k_1..k_7
 };
+constexpr int TEAM_NSEG = 4;    // segments per hierarchy tail in the sweeps (TEAM_NSEG * NCHMAX = 32 lanes)
+constexpr int TEAM_KF = TEAM_NSEG * NCHMAX + 8;
+// what the Jacobian evaluation needs of the background at a = y_0, as (value, d/da): posted by warp 1 one step ahead
+// (the scale factor of the accepted state, u_0 + x_0 of stage 8, is known before stage 8 is solved)
+struct TeamJac {
+  Bg<Dual> bd;
+  double kc[2 * NCHMAX], kap[2 * NCHMAX];
+  double sl[2 * NSLOT];
+  double vvd[4 * NQMAX];        // v_i (value, d/da), 1/v_i (value, d/da)
+};
+struct TeamBox {
+  TeamBg bg[2];
+  TeamJac jac[2];               // [jcur]: at the state of the current step; [jcur ^ 1]: at the candidate of this step
+  double k, x0, x0piv;          // x0 = r_0 / W_00 of the current stage (element 0 of k_i), W_00
+  double ic2[ICACHE];           // warp 1's own spline interval cache
+  double ka0[8];                // element 0 of k_1..k_7
+  double kf[TEAM_KF];           // forward-sweep carry of (segment, chain) = slot; slot 32 stays 0 (head elements)
+};
+// per-mode arrays of the segmented sweeps and the launch-constant element -> carry slot table
+struct TeamWs {
+  double* mc;                   // [np] backward: prod of -m over the rows of the segment above and including l
+  double* gc;                   // [np] forward:  prod of  g over the rows of the segment up to and including l (0: head)
+  const int* eslot;             // [np] element -> slot of kf
+};
+DEB_HD size_t team_ws_doubles(int np) { return (size_t)2 * np; }
+// rows [lo, hi) of chain c's tail (l = 3 .. L) that segment s sweeps
+DEB_DEV void team_segment(const CtaConst& C, int c, int s, int* lo, int* hi) {
+  const int L = C.ch_lmax[c], len = (L - 2 + TEAM_NSEG - 1) / TEAM_NSEG;
+  int a = 3 + s * len, b = a + len;
+  if (b > L + 1) b = L + 1;
+  if (a > b) a = b;
+  *lo = a; *hi = b;
+}
+DEB_DEV void init_team_const(const Problem& P, const CtaConst& C, int* eslot, int tid, int nthreads) {
+  for (int e = tid; e < P.np; e += nthreads) {
+    int slot = TEAM_NSEG * NCHMAX;
+    const int d = elem_desc(P, e);
+    if (d >= 0) {
+      const int ty = d & 0xff, l = (d >> 8) & 0xff, c = d >> 16;
+      if (ty == R_GEN || ty == R_TRUNC) {
+        const int L = C.ch_lmax[c], len = (L - 2 + TEAM_NSEG - 1) / TEAM_NSEG;
+        slot = ((l - 3) / len) * P.nch + c;
+      }
+    }
+    eslot[e] = slot;
+  }
+}
 
 #ifdef DEB_CPU_EMU
 #define DEB_TID_PARAM
 #define DEB_T_BEGIN for (int tid = 0; tid < NT; ++tid) {
 #define DEB_T_END }
 #define DEB_T_BAR()
+#define DEB_T_BAR_BUT1()
 #define DEB_TREGS(type, name, dims) type name##_all[NT] dims
 #define DEB_TUSE(name) auto& name = name##_all[tid]
 #define DEB_IF_WARP(w)
@@ -43,31 +89,84 @@ struct TeamBox {
 #define DEB_T_BEGIN {
 #define DEB_T_END }
 #define DEB_T_BAR() __syncthreads()
+// barrier of the team without warp 1 (named barrier 1): warp 1 evaluates the next stage's background from the first
+// barrier of a stage to the last and must not hold up the solve
+#define DEB_T_BAR_BUT1() do { if (TEAM >= 3) { if (wid != 1) asm volatile("bar.sync 1, %0;" ::"n"(32 * TEAM - 32) : "memory"); } else __syncthreads(); } while (0)
 #define DEB_TREGS(type, name, dims) type name dims
 #define DEB_TUSE(name)
 #define DEB_IF_WARP(w) if (wid == (w))
 #define DEB_T_OR(name) __syncthreads_or(name)
 #endif
 
+// element e of the stage vector just solved: x0 for e = 0, otherwise r plus the deferred forward-sweep carry
+#define DEB_KV(e) ((e) == 0 ? x0 : W.r()[e] + X.gc[e] * box.kf[X.eslot[e]])
+// optional phase timing of warp 0 (build with -DDEB_TEAM_TIMING; tools/team_timing.py reads the counters)
+#if defined(DEB_TEAM_TIMING) && !defined(DEB_CPU_EMU)
+#define DEB_TICK(slot) do { const long long now_ = clock64(); if (tid == 0 && kidx == P.nk - 1) atomicAdd((unsigned long long*)&g_team_timing[slot], (unsigned long long)(now_ - tick_)); tick_ = now_; } while (0)
+#define DEB_TICK_INIT long long tick_ = clock64(); long long tick2_ = tick_;
+#define DEB_TICK2(slot) do { const long long now_ = clock64(); if (tid == 0 && kidx == P.nk - 1) atomicAdd((unsigned long long*)&g_team_timing[slot], (unsigned long long)(now_ - tick2_)); tick2_ = now_; } while (0)
+#define DEB_TICK2_START tick2_ = clock64();
+#else
+#define DEB_TICK(slot)
+#define DEB_TICK2(slot)
+#define DEB_TICK2_START
+#define DEB_TICK_INIT
+#endif
 #define DEB_FOR_TEAM(body) _Pragma("unroll") for (int j = 0; j < NE; ++j) { const int e = tid + NT * j; if (e < n) { body } }
 
 // background at box.a_req -> chain coefficients, operator slots and the scalars of the metric sources (warp 1)
-DEB_DEV void team_helper_compute(const Problem& P, const CtaConst& C, const Cosmo& c, TeamBox& box, Hints& hint2 DEB_LANE_PARAM) {
+DEB_DEV void team_helper_compute(const Problem& P, const CtaConst& C, const Cosmo& c, TeamBox& box, TeamBg& o, Hints& hint2 DEB_LANE_PARAM) {
   const double k = box.k;
   Bg<double> b;
-  compute_bg<double>(c, C.nu, P.nq, box.a_req, hint2, box.ic2, b);
+  compute_bg<double>(c, C.nu, P.nq, o.a_req, hint2, box.ic2, b);
   DEB_LANES_BEGIN
-    if (lane < P.nch) chain_a_lane(c, C.nu, b, k, lane, box.kc, box.kap, box.vv, box.sl);
+    if (lane < P.nch) chain_a_lane(c, C.nu, b, k, lane, o.kc, o.kap, o.vv, o.sl);
     if (lane == 0) {
-      fill_slots<double>(c, b, k, box.sl);
-      box.bgs[0] = b.H; box.bgs[1] = b.gc; box.bgs[2] = b.gb; box.bgs[3] = b.gg; box.bgs[4] = b.gr; box.bgs[5] = b.gnu;
-      box.bgs[6] = b.gq; box.bgs[7] = b.wq1; box.bgs[8] = b.ca2; box.bgs[9] = b.wq;
+      fill_slots<double>(c, b, k, o.sl);
+      o.bgs[0] = b.H; o.bgs[1] = b.gc; o.bgs[2] = b.gb; o.bgs[3] = b.gg; o.bgs[4] = b.gr; o.bgs[5] = b.gnu;
+      o.bgs[6] = b.gq; o.bgs[7] = b.wq1; o.bgs[8] = b.ca2; o.bgs[9] = b.wq;
     }
   DEB_LANES_END
 }
 
+// the a-only half of chain_coeffs_lane<Dual> (warp 1) ...
+DEB_DEV void chain_a_lane_dual(const Cosmo& c, const NuBins& nb, const Bg<Dual>& b, double k, int ch, double* kcA, double* kapA,
+                               double* vvd, double* sl) {
+  Dual kc = 0.0 * b.a + k;
+  if (ch >= 3) {
+    const int i = ch - 3;
+    Dual aq = b.a * (c.amnu / nb.q[i]);
+    Dual s2 = 1.0 + aq * aq;
+    Dual v = drsqrt(s2);
+    Dual iv = s2 * v;
+    kc = v * k;
+    vvd[i] = v.v; vvd[NQMAX + i] = v.d; vvd[2 * NQMAX + i] = iv.v; vvd[3 * NQMAX + i] = iv.d;
+    sl[SL_KV0 + i] = kc.v; sl[NSLOT + SL_KV0 + i] = kc.d;
+  }
+  Dual kp = ch < 2 ? b.opac : 0.0 * b.a;
+  kcA[ch] = kc.v; kcA[NCHMAX + ch] = kc.d;
+  kapA[ch] = kp.v; kapA[NCHMAX + ch] = kp.d;
+}
+// ... and the half that needs the state (warp 0)
+DEB_DEV void nu_moments_lane_dual(const NuBins& nb, const double* vvd, const double* u, int iq0, int i, double* nurA, double* nupA) {
+  const double wp0 = nb.w[i] * u[iq0 + i];
+  const Dual v = mk(vvd[i], vvd[NQMAX + i]), iv = mk(vvd[2 * NQMAX + i], vvd[3 * NQMAX + i]);
+  const Dual tr = iv * wp0, tp = v * wp0;
+  nurA[i] = tr.v; nurA[NQMAX + i] = tr.d;
+  nupA[i] = tp.v; nupA[NQMAX + i] = tp.d;
+}
+DEB_DEV void team_jac_compute(const Problem& P, const CtaConst& C, const Cosmo& c, TeamBox& box, TeamJac& o, double a, Hints& hint2 DEB_LANE_PARAM) {
+  const double k = box.k;
+  Bg<Dual> bd;
+  compute_bg<Dual>(c, C.nu, P.nq, mk(a, 1.0), hint2, box.ic2, bd);
+  DEB_LANES_BEGIN
+    if (lane < P.nch) chain_a_lane_dual(c, C.nu, bd, k, lane, o.kc, o.kap, o.vvd, o.sl);
+    if (lane == 0) { fill_slots<Dual>(c, bd, k, o.sl); o.bd = bd; }
+  DEB_LANES_END
+}
+
 template <int NE, int TEAM>
-DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W, TeamBox& box, int mode DEB_TID_PARAM) {
+DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W, const TeamWs& X, TeamBox& box, int mode DEB_TID_PARAM) {
   constexpr int NT = 32 * TEAM;
 #ifndef DEB_CPU_EMU
   const int lane = tid & 31, wid = tid >> 5;
@@ -79,6 +178,8 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
   const double k2 = k * k;
   DEB_T_BEGIN
     if (tid == 0) { *W.cosmo() = load_cosmo(P, cosmo); box.k = k; }
+    for (int e = tid; e < P.np; e += NT) { X.mc[e] = 0.0; X.gc[e] = 0.0; }
+    if (tid < TEAM_KF) box.kf[tid] = 0.0;
   DEB_T_END
   DEB_T_BAR();
   const Cosmo& c = *W.cosmo();
@@ -93,6 +194,18 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
   DEB_REGS(double, pval, );
   DEB_REGS(double, s1, ); DEB_REGS(double, s2, ); DEB_REGS(double, s3, ); DEB_REGS(double, s4, );
   DEB_TREGS(int, nanflag, );
+  // lane constants of the segmented sweeps: lane = segment * nch + chain sweeps rows [sLo, sHi) of its chain
+  DEB_REGS(int, sSeg, ); DEB_REGS(int, sLo, ); DEB_REGS(int, sHi, ); DEB_REGS(int, sBase, ); DEB_REGS(int, sStr, );
+  DEB_LANES_BEGIN
+    DEB_USE(sSeg); DEB_USE(sLo); DEB_USE(sHi); DEB_USE(sBase); DEB_USE(sStr);
+    sSeg = -1; sLo = sHi = 3; sBase = 0; sStr = 1;
+    if (lane < TEAM_NSEG * nch) {
+      sSeg = lane / nch;
+      const int ch = lane - sSeg * nch;
+      sBase = C.ch_base[ch]; sStr = C.ch_stride[ch];
+      team_segment(C, ch, sSeg, &sLo, &sHi);
+    }
+  DEB_LANES_END
 
   // ---- prologue (every thread evaluates the scalars; the state is filled element-wise) ----
   double t1 = DEB_LDG(tout);
@@ -130,8 +243,12 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
   double inv_prev = 1.0, inv_pprev = 1.0;
   int nsteps = 0, nacc = 0, save_idx = 0, status = 0;
   if (!(t == t) || !(tnext == tnext) || !(t1 == t1)) status = 2;
-  Hints hint; hint.th = -1; hint.nu = -1;          // warp 0 (Jacobian evaluation)
-  Hints hint2; hint2.th = -1; hint2.nu = -1;       // warp 1 (stage evaluations)
+  Hints hint2; hint2.th = -1; hint2.nu = -1;       // warp 1 (all background evaluations)
+  int jcur = 0;
+  DEB_IF_WARP(TEAM > 1 ? 1 : 0) {
+    team_jac_compute(P, C, c, box, box.jac[0], W.y()[0], hint2 DEB_LANE_ARG);
+  }
+  DEB_T_BAR();
 
   while (t < t1 && nsteps < P.max_steps && status == 0) {
     if (P.mode == 3) {
@@ -147,26 +264,30 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
     const double gdt = dt * RD_GAMMA;
 
     // ================= Jacobian pieces at (t, y) =================
-    Bg<Dual> bd;
+    // (the background at a = y_0, the chain coefficients and the operator slots were posted by warp 1 already)
+    DEB_TICK_INIT
+    const TeamJac& J = box.jac[jcur];
+    // row 0 is closed (a' = H a): x_0 of stage 1 is known at once, and with it the d f/d a column of every row
+    const Dual f00 = J.bd.H * J.bd.a;
+    const double x0piv = idg - f00.d;                // W_00 = 1/(gamma dt) - d(H a)/da
+    double x0 = f00.v / x0piv;
+    DEB_T_BEGIN
+      if (tid == 0) { W.r()[0] = f00.v; W.ja()[0] = f00.d; }
+    DEB_T_END
     DEB_IF_WARP(0) {
-      compute_bg<Dual>(c, nb, nq, mk(W.y()[0], 1.0), hint, W.ic(), bd);
+      const Bg<Dual> bd = J.bd;
       DEB_LANES_BEGIN
-        if (lane < nch) chain_coeffs_lane<Dual>(c, nb, bd, k, lane, W.y(), P.iq0, W.kc(), W.kap(), W.nur(), W.nup(), W.sl());
-        if (lane == 0) fill_slots<Dual>(c, bd, k, W.sl());
+        if (lane >= 3 && lane < nch) nu_moments_lane_dual(nb, J.vvd, W.y(), P.iq0, lane - 3, W.nur(), W.nup());
       DEB_LANES_END
-    }
-    DEB_T_BAR();                                      // kc, kap (value, d/da) visible to the team
-    DEB_IF_WARP(0) {
       Metric<Dual> md;
       compute_metric<Dual>(P, c, nb, bd, W.y(), k, W.nur(), W.nup(), md);
       const double H = bd.H.v, a = bd.a.v;
       DEB_LANES_BEGIN
         if (lane < nh) {                      // head rows: f -> r (stage-1 right-hand side), d f/d a -> ja
           const int e = C.hidx[lane];
-          Dual f = head_row<Dual>(C, W.sl(), W.y(), lane, md);
-          W.r()[e] = f.v; W.ja()[e] = f.d;
+          Dual f = head_row<Dual>(C, J.sl, W.y(), lane, md);
+          W.r()[e] = f.v + f.d * x0; W.ja()[e] = f.d;
         }
-        if (lane == 0) { Dual f = bd.H * bd.a; W.r()[0] = f.v; W.ja()[0] = f.d; }
         if (lane < nh) {                      // head-column gradients of h', eta' and of row 1 (value parts only)
           int ty = C.htype[lane], bin = C.hbin[lane];
           double wr = 0.0, wp = 0.0, wt = 0.0, extra = 0.0;
@@ -180,7 +301,7 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
             case R_F1: wt = 4.0 / 3.0 * bd.gg.v; break;
             case R_N0: wr = bd.gr.v; wp = bd.gr.v / 3.0; break;
             case R_N1: wt = 4.0 / 3.0 * bd.gr.v; break;
-            case R_P0: { const double vb = W.kc()[3 + bin] / k; wr = bd.gnu.v * nb.w[bin] / vb; wp = bd.gnu.v * nb.w[bin] * vb / 3.0; } break;
+            case R_P0: { const double vb = J.kc[3 + bin] / k; wr = bd.gnu.v * nb.w[bin] / vb; wp = bd.gnu.v * nb.w[bin] * vb / 3.0; } break;
             case R_P1: wt = bd.gnu.v * k * nb.w[bin]; break;
             case R_DQ: wr = bd.gq.v; wp = c.cs2de * bd.gq.v; break;
             case R_TQ: wt = bd.wq1.v * bd.gq.v; wp = (c.cs2de - bd.ca2.v) * 3.0 * H * wt / k2; break;
@@ -197,12 +318,13 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
       DEB_LANES_BEGIN
         if (lane < nch) {
           const int base = C.ch_base[lane], s = C.ch_stride[lane], L = C.ch_lmax[lane];
-          const double kc = W.kc()[lane], kp = W.kap()[lane];
+          const double kc = J.kc[lane], kp = J.kap[lane];
           double e = idg + kp + (double)(L + 1) * invt0;
           double ie = DEB_RCP(e);
           int idx = base + L * s;
           W.ie()[idx] = ie;
           W.g()[idx] = kc * ie;
+          W.m()[idx] = 0.0;                            // nothing above the truncation row
           double lower_next = -kc;
           for (int l = L - 1; l >= 2; --l) {
             idx -= s;
@@ -221,6 +343,17 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
           }
         }
       DEB_LANES_END
+      // cumulative multipliers inside every segment of the sweeps (one lane per (segment, chain))
+      DEB_LANES_BEGIN
+        DEB_USE(sSeg); DEB_USE(sLo); DEB_USE(sHi); DEB_USE(sBase); DEB_USE(sStr);
+        if (sSeg >= 0) {
+          const int base = sBase, s = sStr, lo = sLo, hi = sHi;
+          double acc = 1.0;
+          for (int l = hi - 1; l >= lo; --l) { const int idx = base + l * s; acc = -W.m()[idx] * acc; X.mc[idx] = acc; }
+          acc = 1.0;
+          for (int l = lo; l < hi; ++l) { const int idx = base + l * s; acc = W.g()[idx] * acc; X.gc[idx] = acc; }
+        }
+      DEB_LANES_END
     }
     {
       // tail rows of f and d f/d a, two rows per trip
@@ -232,17 +365,17 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
         for (int tt = tid - TJ0; tt < C.ntail; tt += 2 * NTJ) {
           int e0, e1 = 0; double tr0, tr1 = 0.0;
           const bool two = tt + NTJ < C.ntail;
-          Dual f0 = tail_row<Dual>(C, W.kc(), W.kap(), W.y(), C.tail[tt], invt0, &e0, &tr0);
+          Dual f0 = tail_row<Dual>(C, J.kc, J.kap, W.y(), C.tail[tt], invt0, &e0, &tr0);
           Dual f1 = mk(0.0, 0.0);
-          if (two) f1 = tail_row<Dual>(C, W.kc(), W.kap(), W.y(), C.tail[tt + NTJ], invt0, &e1, &tr1);
-          W.r()[e0] = f0.v + d1t * tr0 * W.y()[e0]; W.ja()[e0] = f0.d;
-          if (two) { W.r()[e1] = f1.v + d1t * tr1 * W.y()[e1]; W.ja()[e1] = f1.d; }
+          if (two) f1 = tail_row<Dual>(C, J.kc, J.kap, W.y(), C.tail[tt + NTJ], invt0, &e1, &tr1);
+          W.r()[e0] = f0.v + d1t * tr0 * W.y()[e0] + f0.d * x0; W.ja()[e0] = f0.d;
+          if (two) { W.r()[e1] = f1.v + d1t * tr1 * W.y()[e1] + f1.d * x0; W.ja()[e1] = f1.d; }
         }
       DEB_T_END
     }
-    DEB_T_BAR();                                      // r, ja, tail factors complete
-    const double x0piv = idg - W.ja()[0];            // W_00 = 1/(gamma dt) - d(H a)/da
-    double x0 = W.r()[0] / x0piv;                    // stage 1 (every thread: the same bits)
+    DEB_TICK(0);
+    DEB_T_BAR();                                      // r (incl. the d f/d a column), ja, tail factors complete
+    DEB_TICK(1);
 
     double ci_hh = 0.0, ci_he = 0.0, ci_eh = 0.0, ci_ee = 0.0, jq_h = 0.0, jq_e = 0.0;
     DEB_IF_WARP(0) {
@@ -264,7 +397,7 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
 #pragma unroll
           for (int q = 0; q < HOP_NT; ++q) {
             const int m = C.hop_meta[q][lane], hc = (m >> 20) - 1;
-            if (hc >= 0) row[hc] -= C.hop_c[q][lane] * W.sl()[m & 0xff];
+            if (hc >= 0) row[hc] -= C.hop_c[q][lane] * J.sl[m & 0xff];
           }
         }
       DEB_LANES_END
@@ -331,7 +464,7 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
           double ah = 0.0, ae = 0.0;
           for (int cc = lo; cc < hi; ++cc) {
             const int pr = W.perm()[cc];
-            ah += row[cc] * (C.hop_chc[pr] * W.sl()[C.hop_chs[pr]]);
+            ah += row[cc] * (C.hop_chc[pr] * J.sl[C.hop_chs[pr]]);
             ae += row[cc] * C.hop_cec[pr];
           }
           W.qh()[pcol] = ah; W.qe()[pcol] = ae;
@@ -353,86 +486,90 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
       }
     }
 
+    DEB_TICK(2);
     // ================= 8 stages =================
     double errnorm2 = 0.0;
 #pragma unroll 1
     for (int st = 1; st <= 8; ++st) {
       if (st > 1) {
+        TeamBg& cur = box.bg[st & 1];                  // posted by warp 1 during stage st-1
         const double ts = st == 2 ? t + RD_CT2 * dt : st == 3 ? t + RD_CT3 * dt : st == 4 ? t + RD_CT4 * dt
                         : st == 5 ? t + RD_CT5 * dt : t + dt;
         const double dtd = st == 2 ? dt * RD_D2 : st == 3 ? dt * RD_D3 : st == 4 ? dt * RD_D4 : st == 5 ? dt * RD_D5 : 0.0;
-        // ---- own elements: keep k_{st-1}, stage state u, C-combinations -> r ----
+        // ---- own elements: keep k_{st-1}, stage state u, C-combinations -> r; thread 0 closes row 0: x_0 of this stage ----
+#define DEB_ROW0 if (e == 0) { W.r()[0] += cur.bgs[0] * cur.a_req; W.u()[0] = cur.a_req; }
         DEB_T_BEGIN
           DEB_TUSE(ks);
           switch (st) {
-            case 2: DEB_FOR_TEAM(const double kv = e == 0 ? x0 : W.r()[e]; ks[0][j] = kv;
+            case 2: DEB_FOR_TEAM(ks[0][j] = DEB_KV(e);
                                  W.u()[e] = W.y()[e] + RD_A21 * ks[0][j];
-                                 W.r()[e] = invdt * (RD_C21 * ks[0][j]);) break;
-            case 3: DEB_FOR_TEAM(const double kv = e == 0 ? x0 : W.r()[e]; ks[1][j] = kv;
+                                 W.r()[e] = invdt * (RD_C21 * ks[0][j]); DEB_ROW0) break;
+            case 3: DEB_FOR_TEAM(ks[1][j] = DEB_KV(e);
                                  W.u()[e] = W.y()[e] + RD_A31 * ks[0][j] + RD_A32 * ks[1][j];
-                                 W.r()[e] = invdt * (RD_C31 * ks[0][j] + RD_C32 * ks[1][j]);) break;
-            case 4: DEB_FOR_TEAM(const double kv = e == 0 ? x0 : W.r()[e]; ks[2][j] = kv;
+                                 W.r()[e] = invdt * (RD_C31 * ks[0][j] + RD_C32 * ks[1][j]); DEB_ROW0) break;
+            case 4: DEB_FOR_TEAM(ks[2][j] = DEB_KV(e);
                                  W.u()[e] = W.y()[e] + RD_A41 * ks[0][j] + RD_A42 * ks[1][j] + RD_A43 * ks[2][j];
-                                 W.r()[e] = invdt * (RD_C41 * ks[0][j] + RD_C42 * ks[1][j] + RD_C43 * ks[2][j]);) break;
-            case 5: DEB_FOR_TEAM(const double kv = e == 0 ? x0 : W.r()[e]; ks[3][j] = kv;
+                                 W.r()[e] = invdt * (RD_C41 * ks[0][j] + RD_C42 * ks[1][j] + RD_C43 * ks[2][j]); DEB_ROW0) break;
+            case 5: DEB_FOR_TEAM(ks[3][j] = DEB_KV(e);
                                  W.u()[e] = W.y()[e] + RD_A51 * ks[0][j] + RD_A52 * ks[1][j] + RD_A53 * ks[2][j] + RD_A54 * ks[3][j];
-                                 W.r()[e] = invdt * (RD_C51 * ks[0][j] + RD_C52 * ks[1][j] + RD_C53 * ks[2][j] + RD_C54 * ks[3][j]);) break;
-            case 6: DEB_FOR_TEAM(const double kv = e == 0 ? x0 : W.r()[e]; ks[4][j] = kv;
+                                 W.r()[e] = invdt * (RD_C51 * ks[0][j] + RD_C52 * ks[1][j] + RD_C53 * ks[2][j] + RD_C54 * ks[3][j]); DEB_ROW0) break;
+            case 6: DEB_FOR_TEAM(ks[4][j] = DEB_KV(e);
                                  W.u()[e] = W.y()[e] + RD_A61 * ks[0][j] + RD_A62 * ks[1][j] + RD_A63 * ks[2][j] + RD_A64 * ks[3][j] + RD_A65 * ks[4][j];
-                                 W.r()[e] = invdt * (RD_C61 * ks[0][j] + RD_C62 * ks[1][j] + RD_C63 * ks[2][j] + RD_C64 * ks[3][j] + RD_C65 * ks[4][j]);) break;
-            case 7: DEB_FOR_TEAM(const double kv = e == 0 ? x0 : W.r()[e]; ks[5][j] = kv;
+                                 W.r()[e] = invdt * (RD_C61 * ks[0][j] + RD_C62 * ks[1][j] + RD_C63 * ks[2][j] + RD_C64 * ks[3][j] + RD_C65 * ks[4][j]); DEB_ROW0) break;
+            case 7: DEB_FOR_TEAM(ks[5][j] = DEB_KV(e);
                                  W.u()[e] = W.u()[e] + ks[5][j];
-                                 W.r()[e] = invdt * (RD_C71 * ks[0][j] + RD_C72 * ks[1][j] + RD_C73 * ks[2][j] + RD_C74 * ks[3][j] + RD_C75 * ks[4][j] + RD_C76 * ks[5][j]);) break;
-            default: DEB_FOR_TEAM(const double kv = e == 0 ? x0 : W.r()[e]; ks[6][j] = kv;
+                                 W.r()[e] = invdt * (RD_C71 * ks[0][j] + RD_C72 * ks[1][j] + RD_C73 * ks[2][j] + RD_C74 * ks[3][j] + RD_C75 * ks[4][j] + RD_C76 * ks[5][j]); DEB_ROW0) break;
+            default: DEB_FOR_TEAM(ks[6][j] = DEB_KV(e);
                                  W.u()[e] = W.u()[e] + ks[6][j];
-                                 W.r()[e] = invdt * (RD_C81 * ks[0][j] + RD_C82 * ks[1][j] + RD_C83 * ks[2][j] + RD_C84 * ks[3][j] + RD_C85 * ks[4][j] + RD_C86 * ks[5][j] + RD_C87 * ks[6][j]);) break;
+                                 W.r()[e] = invdt * (RD_C81 * ks[0][j] + RD_C82 * ks[1][j] + RD_C83 * ks[2][j] + RD_C84 * ks[3][j] + RD_C85 * ks[4][j] + RD_C86 * ks[5][j] + RD_C87 * ks[6][j]); DEB_ROW0) break;
           }
-          if (tid == 0) W.u()[0] = box.a_req;         // exactly the value the helper evaluated the background at
         DEB_T_END
-        DEB_T_BAR();                                   // u, r (C-combinations) and the helper's scalars visible
-        // ---- f(ts, u) + dt d_i dT added onto r ----
+#undef DEB_ROW0
+        DEB_TICK(3);
+        DEB_T_BAR();
+        DEB_TICK(4);                                   // u, r (C-combinations; row 0 complete) visible
+        x0 = W.r()[0] / x0piv;                         // every thread: the same bits
+        // ---- f(ts, u) + dt d_i dT + (d f/d a) x0 added onto r:  warp 0 the head rows, warps >= 2 the tail rows ----
         const double invts = DEB_RCP(ts);
         const double dtt = dtd * invt0 * invt0;
         DEB_IF_WARP(0) {
           Bg<double> b;
-          b.a = box.a_req;
-          b.H = box.bgs[0]; b.gc = box.bgs[1]; b.gb = box.bgs[2]; b.gg = box.bgs[3]; b.gr = box.bgs[4]; b.gnu = box.bgs[5];
-          b.gq = box.bgs[6]; b.wq1 = box.bgs[7]; b.ca2 = box.bgs[8]; b.wq = box.bgs[9];
-          b.opac = box.sl[SL_OPAC]; b.pbo = box.sl[SL_PBO]; b.cs2 = 0.0;
+          b.a = cur.a_req;
+          b.H = cur.bgs[0]; b.gc = cur.bgs[1]; b.gb = cur.bgs[2]; b.gg = cur.bgs[3]; b.gr = cur.bgs[4]; b.gnu = cur.bgs[5];
+          b.gq = cur.bgs[6]; b.wq1 = cur.bgs[7]; b.ca2 = cur.bgs[8]; b.wq = cur.bgs[9];
+          b.opac = cur.sl[SL_OPAC]; b.pbo = cur.sl[SL_PBO]; b.cs2 = 0.0;
           DEB_LANES_BEGIN
-            if (lane >= 3 && lane < nch) nu_moments_lane(nb, box.vv, W.u(), P.iq0, lane - 3, W.nur(), W.nup());
+            if (lane >= 3 && lane < nch) nu_moments_lane(nb, cur.vv, W.u(), P.iq0, lane - 3, W.nur(), W.nup());
           DEB_LANES_END
           Metric<double> mt;
           compute_metric<double>(P, c, nb, b, W.u(), k, W.nur(), W.nup(), mt);
           DEB_LANES_BEGIN
             if (lane < nh) {
               const int e = C.hidx[lane];
-              W.r()[e] += head_row<double>(C, box.sl, W.u(), lane, mt);
+              const double rv = W.r()[e] + head_row<double>(C, cur.sl, W.u(), lane, mt);
+              W.r()[e] = rv + W.ja()[e] * x0;
             }
-            if (lane == 0) W.r()[0] += b.H * b.a;
           DEB_LANES_END
         }
-        // (warp 0 evaluates the metric sources and the head rows meanwhile: the tail rows go to the other warps)
-        constexpr int TS0 = TEAM >= 2 ? 32 : 0, NTS = NT - TS0;
+        constexpr int TS0 = TEAM >= 3 ? 64 : (TEAM == 2 ? 32 : 0), NTS = NT - TS0;
         DEB_T_BEGIN
           if (tid >= TS0)
           for (int tt = tid - TS0; tt < C.ntail; tt += 2 * NTS) {
             int e0, e1 = 0; double tr0, tr1 = 0.0, f1 = 0.0, r1 = 0.0, y1 = 0.0;
             const bool two = tt + NTS < C.ntail;
-            const double f0 = tail_row<double>(C, box.kc, box.kap, W.u(), C.tail[tt], invts, &e0, &tr0);
+            const double f0 = tail_row<double>(C, cur.kc, cur.kap, W.u(), C.tail[tt], invts, &e0, &tr0);
             const double r0 = W.r()[e0], y0 = W.y()[e0];
-            if (two) { f1 = tail_row<double>(C, box.kc, box.kap, W.u(), C.tail[tt + NTS], invts, &e1, &tr1); r1 = W.r()[e1]; y1 = W.y()[e1]; }
-            W.r()[e0] = r0 + f0 + dtt * tr0 * y0;
-            if (two) W.r()[e1] = r1 + f1 + dtt * tr1 * y1;
+            if (two) { f1 = tail_row<double>(C, cur.kc, cur.kap, W.u(), C.tail[tt + NTS], invts, &e1, &tr1); r1 = W.r()[e1]; y1 = W.y()[e1]; }
+            W.r()[e0] = r0 + f0 + dtt * tr0 * y0 + W.ja()[e0] * x0;
+            if (two) W.r()[e1] = r1 + f1 + dtt * tr1 * y1 + W.ja()[e1] * x0;
           }
         DEB_T_END
-        DEB_T_BAR();                                   // r complete
-        x0 = W.r()[0] / x0piv;
       }
 
       // ---- warp 1: background scalars of stage st+1 at a = y_0 + sum_j a_{st+1,j} k_{j,0}  (k_{st,0} = x0) ----
       if (st < 8) {
         DEB_IF_WARP(TEAM > 1 ? 1 : 0) {
+          TeamBg& nxt = box.bg[(st + 1) & 1];
           DEB_LANES_BEGIN
             if (lane == 0) {
               box.ka0[st - 1] = x0;
@@ -446,46 +583,72 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
                 case 5: an = W.y()[0] + RD_A61 * ka[0] + RD_A62 * ka[1] + RD_A63 * ka[2] + RD_A64 * ka[3] + RD_A65 * x0; break;
                 default: an = W.u()[0] + x0; break;        // stages 7 and 8: u + k
               }
-              box.a_req = an;
+              nxt.a_req = an;
             }
           DEB_LANES_END
-          team_helper_compute(P, C, c, box, hint2 DEB_LANE_ARG);
+          team_helper_compute(P, C, c, box, nxt, hint2 DEB_LANE_ARG);
+        }
+      } else {
+        // stage 8: the candidate's scale factor y1_0 = u_0 + x0 is known -> background of the next step's Jacobian
+        DEB_IF_WARP(TEAM > 1 ? 1 : 0) {
+          team_jac_compute(P, C, c, box, box.jac[jcur ^ 1], W.u()[0] + x0, hint2 DEB_LANE_ARG);
         }
       }
+      DEB_TICK(5);
+      if (st > 1) DEB_T_BAR_BUT1();
+      DEB_TICK(6);                    // r complete (stage 1: the barrier after the Jacobian pieces)
 
-      // ---- warp 0: solve W x = r in place (x_0 = x0 is already known; its column is folded in on the fly) ----
+      // ---- warp 0: solve W x = r in place.  x_0 and its column are already in; every hierarchy tail is swept in
+      //      TEAM_NSEG segments at once (lane = segment * nch + chain): local recurrences from zero, a carry chain
+      //      over the segments, then x_l = local_l + (product of multipliers) * carry.  The forward carries are applied
+      //      by whoever reads the result (DEB_KV).
       DEB_IF_WARP(0) {
-        DEB_LANES_BEGIN
-          if (lane < nch) {          // backward sweep: b'_l = b_l - m_l b'_{l+1}, l = L-1 .. 2, with b_l = r_l + ja_l x0
-            const int s = C.ch_stride[lane], L = C.ch_lmax[lane];
-            const int iL = C.ch_base[lane] + L * s;
-            double* rp = W.r() + iL;
-            const double* jp = W.ja() + iL;
-            const double* mp = W.m() + iL;
-            double bp = *rp + *jp * x0;
-            *rp = bp;
-            rp -= s; jp -= s; mp -= s;
-            double rn = *rp + *jp * x0, mn = *mp;
-#pragma unroll 4
-            for (int l = L - 1; l > 2; --l) {
-              const double rc = rn, mc = mn;
-              rn = *(rp - s) + *(jp - s) * x0; mn = *(mp - s);
-              bp = rc - mc * bp;
-              *rp = bp;
-              rp -= s; jp -= s; mp -= s;
+        DEB_REGS(double, sT, ); DEB_REGS(double, sE, ); DEB_REGS(double, sA, ); DEB_REGS(double, sK, );
+        DEB_TICK2_START
+        DEB_LANES_BEGIN          // backward sweep: b'_l = b_l - m_l b'_{l+1}
+          DEB_USE(sT); DEB_USE(sE); DEB_USE(sA); DEB_USE(sK);
+          DEB_USE(sSeg); DEB_USE(sLo); DEB_USE(sHi); DEB_USE(sBase); DEB_USE(sStr);
+          sE = 0.0; sA = 1.0; sK = 0.0;
+          if (sSeg >= 0) {
+            const int base = sBase, s = sStr, lo = sLo, hi = sHi;
+            if (hi > lo) {
+              double* rp = W.r() + (base + (hi - 1) * s);
+              const double* mp = W.m() + (base + (hi - 1) * s);
+              double p = 0.0;
+              double rn = *rp, mn = *mp;
+              for (int l = hi - 1; l > lo; --l) {
+                const double rc = rn, mc = mn;
+                rn = *(rp - s); mn = *(mp - s);
+                p = rc - mc * p;
+                *rp = p;
+                rp -= s; mp -= s;
+              }
+              p = rn - mn * p;
+              *rp = p;
+              sE = p; sA = X.mc[base + lo * s];
             }
-            *rp = rn - mn * bp;
+          }
+          sT = sE;
+        DEB_LANES_END
+        DEB_TICK2(10);
+        for (int sg = TEAM_NSEG - 2; sg >= 0; --sg) {        // carry chain: the true b' just above segment sg
+          DEB_LANES_BEGIN
+            DEB_USE(sT); DEB_USE(sE); DEB_USE(sA); DEB_USE(sK); DEB_USE(sSeg);
+            const double kin = DEB_SHFL(sT, (lane + nch) & 31);
+            if (sSeg == sg) { sK = kin; sT = sE + sA * kin; }
+          DEB_LANES_END
+        }
+        DEB_LANES_BEGIN
+          DEB_USE(sT);
+          if (lane < nch) {        // l = 2 (a head row): b'_2 = b_2 - m_2 b'_3
+            const int i2 = C.ch_base[lane] + 2 * C.ch_stride[lane];
+            W.r()[i2] = W.r()[i2] - W.m()[i2] * sT;
           }
         DEB_LANES_END
+        DEB_TICK2(11);
         // head: p = D^-1 b (block inverses), then the rank-2 Woodbury correction and the a h' row
         DEB_LANES_BEGIN
-          double xv = 0.0;
-          if (lane < nhb) {
-            const int pr = W.perm()[lane], e = C.hidx[pr], ty = C.htype[pr];
-            const bool swept = (ty == R_F2 || ty == R_G2 || ty == R_N2 || ty == R_P2);     // the sweep already added the column
-            xv = swept ? W.r()[e] : W.r()[e] + W.ja()[e] * x0;
-          }
-          W.xb()[lane] = xv;
+          W.xb()[lane] = lane < nhb ? W.r()[C.hidx[W.perm()[lane]]] : 0.0;
           if (lane < 8) W.xb()[NHMAX + lane] = 0.0;
         DEB_LANES_END
         DEB_LANES_BEGIN
@@ -504,45 +667,71 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
             s1 = W.gh()[pcol] * acc; s2 = W.ge()[pcol] * acc; s3 = W.j1()[pcol] * acc;
           }
         DEB_LANES_END
+        DEB_TICK2(12);
         {
           const double th = DEB_WARP_SUM(s1), te = DEB_WARP_SUM(s2), ta = DEB_WARP_SUM(s3);
           const double sh = ci_hh * th + ci_he * te, se = ci_eh * th + ci_ee * te;
           DEB_LANES_BEGIN
             DEB_USE(pcol); DEB_USE(pval);
             if (lane < nhb) W.r()[C.hidx[pcol]] = pval + W.qh()[pcol] * sh + W.qe()[pcol] * se;
-            else if (lane == nhb) W.r()[1] = ((W.r()[1] + W.ja()[1] * x0) + ta + jq_h * sh + jq_e * se) * gdt;
+            else if (lane == nhb) W.r()[1] = (W.r()[1] + ta + jq_h * sh + jq_e * se) * gdt;     // a h' (state 1): closed row
+          DEB_LANES_END
+        }
+        DEB_TICK2(13);
+        DEB_LANES_BEGIN          // forward sweep: x_l = b'_l/e_l + g_l x_{l-1}
+          DEB_USE(sT); DEB_USE(sE); DEB_USE(sA); DEB_USE(sK);
+          DEB_USE(sSeg); DEB_USE(sLo); DEB_USE(sHi); DEB_USE(sBase); DEB_USE(sStr);
+          const double kb = sK;          // backward carry of this lane's segment
+          sE = 0.0; sA = 1.0; sK = 0.0;
+          if (sSeg >= 0) {
+            const int sg = sSeg, base = sBase, s = sStr, lo = sLo, hi = sHi;
+            double x = sg == 0 ? W.r()[base + 2 * s] : 0.0;        // segment 0 starts from x_2, the others from zero
+            if (hi > lo) {
+              const int i0 = base + lo * s;
+              double* rp = W.r() + i0;
+              const double* ip = W.ie() + i0;
+              const double* gp = W.g() + i0;
+              const double* cp = X.mc + i0;
+              double cn = (*rp + *cp * kb) * *ip, gn = *gp;
+              for (int l = lo; l < hi - 1; ++l) {
+                const double cc = cn, gc = gn;
+                cn = (*(rp + s) + *(cp + s) * kb) * *(ip + s); gn = *(gp + s);
+                x = cc + gc * x;
+                *rp = x;
+                rp += s; ip += s; gp += s; cp += s;
+              }
+              x = cn + gn * x;
+              *rp = x;
+              sA = X.gc[base + (hi - 1) * s];
+            }
+            sE = x;
+            if (sg == 0) sA = 0.0;                                  // x_2 is already inside segment 0
+          }
+          sT = sE;
+        DEB_LANES_END
+        DEB_TICK2(14);
+        for (int sg = 1; sg < TEAM_NSEG; ++sg) {              // carry chain: the true x just below segment sg
+          DEB_LANES_BEGIN
+            DEB_USE(sT); DEB_USE(sE); DEB_USE(sA); DEB_USE(sK); DEB_USE(sSeg);
+            const double kin = DEB_SHFL(sT, (lane - nch) & 31);
+            if (sSeg == sg) { sK = kin; sT = sE + sA * kin; }
           DEB_LANES_END
         }
         DEB_LANES_BEGIN
-          if (lane < nch) {          // forward sweep: x_l = b'_l/e_l + g_l x_{l-1}, l = 3 .. L
-            const int s = C.ch_stride[lane], L = C.ch_lmax[lane];
-            const int i0 = C.ch_base[lane] + 2 * s;
-            double* rp = W.r() + i0;
-            const double* ip = W.ie() + i0;
-            const double* gp = W.g() + i0;
-            double x = *rp;
-            rp += s; ip += s; gp += s;
-            double cn = *rp * *ip, gn = *gp;
-#pragma unroll 4
-            for (int l = 3; l < L; ++l) {
-              const double cc = cn, gc = gn;
-              cn = *(rp + s) * *(ip + s); gn = *(gp + s);
-              x = cc + gc * x;
-              *rp = x;
-              rp += s; ip += s; gp += s;
-            }
-            *rp = cn + gn * x;
-          }
+          DEB_USE(sK); DEB_USE(sSeg);
+          if (sSeg >= 0) box.kf[lane] = sK;
         DEB_LANES_END
       }
-      DEB_T_BAR();                                     // r = k_st (element 0: x0), the helper's results posted
+      DEB_TICK(7);
+      DEB_T_BAR();                                     // r, kf = k_st (element 0: x0), warp 1's results posted
+      DEB_TICK(8);
     }
 
-    // y1 = u + k8 -> u ; err = k8 = r
+    // y1 = u + k8 -> u ; err = k8 -> r
     DEB_T_BEGIN
       DEB_TUSE(nanflag);
       nanflag = 0;
-      DEB_FOR_TEAM(const double kv = e == 0 ? x0 : W.r()[e]; if (e == 0) W.r()[0] = x0;
+      DEB_FOR_TEAM(const double kv = DEB_KV(e); W.r()[e] = kv;
                    const double y1v = W.u()[e] + kv; W.u()[e] = y1v; nanflag |= (y1v != y1v);)
     DEB_T_END
     bool anynan = DEB_T_OR(nanflag) != 0;              // (a barrier)
@@ -611,6 +800,7 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
       DEB_T_END
       inv_pprev = inv_prev; inv_prev = inv;
       t = fmin(tnext, t1);
+      jcur ^= 1;                 // the background posted during stage 8 is the accepted state's
     }
     DEB_T_BAR();          // the accepted state is visible before the next Jacobian evaluation
     double tn = t + dtn;
@@ -619,6 +809,10 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
     }
     tnext = tn;
     if (!(tnext == tnext) || isinf(tnext)) status = 2;
+    DEB_TICK(9);
+#if defined(DEB_TEAM_TIMING) && !defined(DEB_CPU_EMU)
+    if (tid == 0 && kidx == P.nk - 1) atomicAdd((unsigned long long*)&g_team_timing[15], 1ull);
+#endif
   }
   if (status == 0 && t < t1) status = 1;
   DEB_T_BEGIN
