@@ -66,6 +66,14 @@
 #define DEB_WARP_SUM(name) deb::warp_sum(name)
 #endif
 
+// exp/log/pow go through these names so that a translation unit can route them to out-of-line copies
+// (deb_team.cu: the step loop must fit the instruction cache; each inlined exp/log is 1-2 KB, pow 5 KB)
+#ifndef DEB_EXP
+#define DEB_EXP(x) exp(x)
+#define DEB_LOG(x) log(x)
+#define DEB_POW(x, y) pow(x, y)
+#endif
+
 namespace deb {
 
 constexpr int NSCAL = 24;
@@ -168,11 +176,11 @@ DEB_DEV Dual operator*(double b, Dual a) { return mk(a.v * b, a.d * b); }
 DEB_DEV Dual operator/(Dual a, double b) { return mk(a.v / b, a.d / b); }
 DEB_DEV Dual operator/(double b, Dual a) { double ia = DEB_RCP(a.v), q = b * ia; return mk(q, -q * a.d * ia); }
 DEB_DEV Dual dsqrt(Dual a) { double s = sqrt(a.v); return mk(s, 0.5 * a.d / s); }
-DEB_DEV Dual dexp(Dual a) { double e = exp(a.v); return mk(e, e * a.d); }
-DEB_DEV Dual dlog(Dual a) { return mk(log(a.v), a.d / a.v); }
+DEB_DEV Dual dexp(Dual a) { double e = DEB_EXP(a.v); return mk(e, e * a.d); }
+DEB_DEV Dual dlog(Dual a) { return mk(DEB_LOG(a.v), a.d / a.v); }
 DEB_DEV double dsqrt(double a) { return sqrt(a); }
-DEB_DEV double dexp(double a) { return exp(a); }
-DEB_DEV double dlog(double a) { return log(a); }
+DEB_DEV double dexp(double a) { return DEB_EXP(a); }
+DEB_DEV double dlog(double a) { return DEB_LOG(a); }
 DEB_DEV double val(double a) { return a; }
 DEB_DEV double val(Dual a) { return a.v; }
 DEB_DEV double der(double) { return 0.0; }
@@ -356,7 +364,7 @@ DEB_DEV void init_cta_const(const Problem& P, CtaConst& C, int* tail, int tid, i
     for (int i = 0; i < nq; ++i) {
       double q = nq == 3 ? q3[i] : (nq == 4 ? q4[i] : q5[i]);
       double kw = nq == 3 ? k3[i] : (nq == 4 ? k4[i] : k5[i]);
-      double dl = -q / (1.0 + exp(-q));
+      double dl = -q / (1.0 + DEB_EXP(-q));
       C.nu.q[i] = q; C.nu.dl[i] = dl;
       C.nu.w[i] = kw / (-0.25 * dl) / 5.682196976983475;
     }
@@ -747,15 +755,15 @@ DEB_DEV T tail_row(const CtaConst& C, const double* kcA, const double* kapA, con
 // prologue: start time (perturbations.py:630-681, util.py:365-396)
 // ---------------------------------------------------------------------------------------------
 DEB_DEV double aprimeoa_plain(const Cosmo& c, double a) {
-  double loga = log(a);
-  double rhonu = exp(spl_eval(c.lrn, loga));
-  double rhoq = exp(c.rq_exp * loga + 3.0 * c.wa * (a - 1.0));
+  double loga = DEB_LOG(a);
+  double rhonu = DEB_EXP(spl_eval(c.lrn, loga));
+  double rhoq = DEB_EXP(c.rq_exp * loga + 3.0 * c.wa * (a - 1.0));
   double grho = c.grhom * c.Omegam / a + (c.grhog + c.grhor * (c.Neff + c.Nmnu * rhonu)) / (a * a)
               + c.grhom * c.OmegaDE * rhoq * (a * a) + c.grhom * c.Omegak;
   return sqrt(grho / 3.0);
 }
 DEB_DEV double cond_small_k(const Cosmo& c, double lt) {
-  double tau = exp(lt);
+  double tau = DEB_EXP(lt);
   double akthom = AKTHOM_START * (1.0 - c.YHe) * c.Omegab * c.H0 * c.H0;
   double xe = spl_eval(c.xe_of_tau, tau);
   double a = spl_eval(c.a_of_tau, tau);
@@ -764,13 +772,13 @@ DEB_DEV double cond_small_k(const Cosmo& c, double lt) {
   return (1.0 / opac) / (1.0 / H) / 0.0004 - 1.0;
 }
 DEB_DEV double cond_large_k(const Cosmo& c, double lt, double k) {
-  double a = spl_eval(c.a_of_tau, exp(lt));
+  double a = spl_eval(c.a_of_tau, DEB_EXP(lt));
   return (1.0 / aprimeoa_plain(c, a)) / (1.0 / k) / 0.07 - 1.0;
 }
 // util.py:365-396 keeps [mid, right] when f(mid) f(left) > 0.  f(left) is carried along instead of being
 // re-evaluated (same function at the same point: identical value), which halves the spline lookups.
 DEB_DEV double start_small_k(const Cosmo& c) {          // k-independent root: once per cosmology
-  double xl = log(c.taumin), xr = log(spl_eval(c.tau_of_a, 0.1));
+  double xl = DEB_LOG(c.taumin), xr = DEB_LOG(spl_eval(c.tau_of_a, 0.1));
   double fl = cond_small_k(c, xl);
   for (int it = 0; it < 7; ++it) {
     const double xm = 0.5 * (xl + xr), fm = cond_small_k(c, xm);
@@ -779,7 +787,7 @@ DEB_DEV double start_small_k(const Cosmo& c) {          // k-independent root: o
   return 0.5 * (xl + xr);
 }
 DEB_DEV double start_time(const Cosmo& c, double k, double lt_small) {
-  double xl = log(c.taumin), xr = log(spl_eval(c.tau_of_a, 0.1));
+  double xl = DEB_LOG(c.taumin), xr = DEB_LOG(spl_eval(c.tau_of_a, 0.1));
   double fl = cond_large_k(c, xl, k);
   for (int it = 0; it < 7; ++it) {
     const double xm = 0.5 * (xl + xr), fm = cond_large_k(c, xm, k);
@@ -787,7 +795,7 @@ DEB_DEV double start_time(const Cosmo& c, double k, double lt_small) {
   }
   const double lt_large = 0.5 * (xl + xr);
   if (!(lt_small == lt_small) || !(lt_large == lt_large)) return NAN;
-  return exp(fmin(lt_small, lt_large));
+  return DEB_EXP(fmin(lt_small, lt_large));
 }
 
 // adiabatic initial conditions (perturbations.py:526-627): value of element e
@@ -795,7 +803,7 @@ struct IcScalars { double a, deltag, thetag, deltar, thetar, shearr, deltaq, the
 DEB_DEV IcScalars ic_scalars(const Cosmo& c, double tau, double k) {
   IcScalars s;
   double a = spl_eval(c.a_of_tau, tau);
-  double rn = exp(spl_eval(c.lrn, log(a)));
+  double rn = DEB_EXP(spl_eval(c.lrn, DEB_LOG(a)));
   double a2 = a * a, a4 = a2 * a2;
   double rhom = c.grhom * c.Omegam / (a2 * a);
   double rhor = (c.grhog + c.grhor * (c.Neff + c.Nmnu * rn)) / a4;
@@ -851,8 +859,8 @@ DEB_DEV void convert_outputs(const Problem& P, const Cosmo& c, const NuBins& nb,
   const int nq = P.nq, iq0 = P.iq0, n = P.n;
   double a = y[0], eta = y[2], dc = y[3], tc = y[4], db = y[5], tb = y[6], dg = y[7], tg = y[8];
   double dr = y[P.ir], tr = y[P.ir + 1], dq = y[n - 2], tq = y[n - 1];
-  double la = log(a);
-  double rhonu = exp(spl_eval(c.lrn, la)), pnu = exp(spl_eval(c.lpn, la));
+  double la = DEB_LOG(a);
+  double rhonu = DEB_EXP(spl_eval(c.lrn, la)), pnu = DEB_EXP(spl_eval(c.lpn, la));
   double drhonu = 0.0, fnu = 0.0;
   for (int i = 0; i < nq; ++i) {
     double aq = a * c.amnu / nb.q[i];
@@ -862,7 +870,7 @@ DEB_DEV void convert_outputs(const Problem& P, const Cosmo& c, const NuBins& nb,
   }
   double deltanu = drhonu / rhonu, thetanu = k * fnu / (rhonu + pnu);
   double wq = c.w0 + c.wa * (1.0 - a);
-  double rhoq = pow(a, c.rq_exp) * exp(3.0 * (a - 1.0) * c.wa);
+  double rhoq = DEB_POW(a, c.rq_exp) * DEB_EXP(3.0 * (a - 1.0) * c.wa);
   double a2 = a * a;
   double rpt = (1.0 + wq) * rhoq * c.grhom * c.OmegaDE * tq * a2;
   double grho = c.grhom * c.Omegam / a + (c.grhog + c.grhor * (c.Neff + c.Nmnu * rhonu)) / a2
@@ -1677,9 +1685,9 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, Help
     const bool keep = (P.mode == 3) ? (DEB_LDG(P.rp_keep + (size_t)mode * P.rp_stride + nsteps) != 0) : (E < 1.0);
     double inv = 1.0 / E;
     // inv^c1 * inv_prev^c2 * inv_pprev^c3 (PID law) through one exp; E = 0 or inf keep their limits
-    double f1 = P.c1 != 0.0 ? ((inv > 0.0 && !isinf(inv)) ? exp(P.c1 * log(inv)) : pow(inv, P.c1)) : 1.0;
-    double f2 = P.c2 != 0.0 ? exp(P.c2 * log(inv_prev)) : 1.0;
-    double f3 = P.c3 != 0.0 ? exp(P.c3 * log(inv_pprev)) : 1.0;
+    double f1 = P.c1 != 0.0 ? ((inv > 0.0 && !isinf(inv)) ? DEB_EXP(P.c1 * DEB_LOG(inv)) : DEB_POW(inv, P.c1)) : 1.0;
+    double f2 = P.c2 != 0.0 ? DEB_EXP(P.c2 * DEB_LOG(inv_prev)) : 1.0;
+    double f3 = P.c3 != 0.0 ? DEB_EXP(P.c3 * DEB_LOG(inv_pprev)) : 1.0;
     double fac = fmin(fmax(P.safety * f1 * f2 * f3, keep ? 1.0 : P.factormin), P.factormax);
     if (!(fac == fac)) fac = NAN;
     const double dtn = dt * fac;
@@ -1721,7 +1729,7 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, Help
               for (int q = 0; q < 20; ++q) P.y_out[obase * 20 + q] = o20[q];
               if (P.pk_out && P.power_idx >= 0) {
                 double yv = o20[P.power_idx];
-                P.pk_out[obase] = 2.0 * 9.869604401089358 * c.As * pow(k / c.kp, c.ns - 1.0) * pow(k, -3.0) * yv * yv;
+                P.pk_out[obase] = 2.0 * 9.869604401089358 * c.As * DEB_POW(k / c.kp, c.ns - 1.0) * DEB_POW(k, -3.0) * yv * yv;
               }
             }
             if (TAN) {

@@ -7,6 +7,13 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include "../../include/discoeb_b200.h"
+// one out-of-line copy of each transcendental for this translation unit (see DEB_EXP in deb_core.cuh)
+static __device__ __noinline__ double deb_ni_exp(double x) { return exp(x); }
+static __device__ __noinline__ double deb_ni_log(double x) { return log(x); }
+static __device__ __noinline__ double deb_ni_pow(double x, double y) { return pow(x, y); }
+#define DEB_EXP(x) deb_ni_exp(x)
+#define DEB_LOG(x) deb_ni_log(x)
+#define DEB_POW(x, y) deb_ni_pow(x, y)
 #include "deb_core.cuh"
 #ifdef DEB_TEAM_TIMING
 __device__ long long g_team_timing[16];
@@ -19,8 +26,8 @@ using namespace deb;
   fprintf(stderr, "[discoeb_b200] CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return DEB_E_CUDA; } } while (0)
 
 static __host__ __device__ size_t al16(size_t b) { return (b + 15) & ~(size_t)15; }
-static __host__ __device__ size_t team_smem_bytes(int np) {
-  return al16(sizeof(CtaConst)) + 2 * al16((size_t)np * sizeof(int)) + al16((warp_ws_doubles(np) + team_ws_doubles(np)) * sizeof(double))
+static __host__ __device__ size_t team_smem_bytes(int np, int segrows) {
+  return al16(sizeof(CtaConst)) + 4 * al16((size_t)np * sizeof(int)) + al16((warp_ws_doubles(np) + team_ws_doubles(segrows)) * sizeof(double))
        + al16(sizeof(TeamBox)) + 16;
 }
 
@@ -33,20 +40,35 @@ __global__ void __launch_bounds__(32 * TEAM, MINB) k_evolve_team(const __grid_co
   off += al16((size_t)P.np * sizeof(int));
   int* eslot = reinterpret_cast<int*>(smem_raw + off);
   off += al16((size_t)P.np * sizeof(int));
+  int* epos = reinterpret_cast<int*>(smem_raw + off);
+  off += al16((size_t)P.np * sizeof(int));
+  int* tailpos = reinterpret_cast<int*>(smem_raw + off);
+  off += al16((size_t)P.np * sizeof(int));
+  const int segrows = team_segrows(P.lmaxg, P.lmaxgp, P.lmaxr, P.lmaxnu);
   double* wsb = reinterpret_cast<double*>(smem_raw + off);
-  off += al16((warp_ws_doubles(P.np) + team_ws_doubles(P.np)) * sizeof(double));
+  off += al16((warp_ws_doubles(P.np) + team_ws_doubles(segrows)) * sizeof(double));
   TeamBox* box = reinterpret_cast<TeamBox*>(smem_raw + off);
   off += al16(sizeof(TeamBox));
   unsigned int* s_tk = reinterpret_cast<unsigned int*>(smem_raw + off);
   const int tid = threadIdx.x;
   init_cta_const(P, *C, tail, tid, 32 * TEAM);
   __syncthreads();
-  init_team_const(P, *C, eslot, tid, 32 * TEAM);
+  init_team_const(P, *C, eslot, epos, tailpos, tid, 32 * TEAM);
   __syncthreads();
   WarpWs W;
   carve(W, wsb, P.np);
   TeamWs X;
-  X.mc = wsb + warp_ws_doubles(P.np); X.gc = X.mc + P.np; X.eslot = eslot;
+  carve_team(X, wsb + warp_ws_doubles(P.np), segrows, eslot, epos, tailpos);
+  // Two CTAs share an SM and warp slot w issues from scheduler w % 4: with the same role order in both, the two
+  // serial warps (and the two helpers) would compete for one scheduler while two others idle (+15 % per step,
+  // measured).  The CTA on the odd group of warp slots rotates its roles by two warps.
+  if (tid == 0) {
+    unsigned int wslot;
+    asm volatile("mov.u32 %0, %%warpid;" : "=r"(wslot));
+    s_tk[1] = ((wslot / TEAM) & 1u) * (TEAM / 2);
+  }
+  __syncthreads();
+  const int ltid = ((((tid >> 5) + TEAM - (int)s_tk[1]) % TEAM) << 5) | (tid & 31);
   const int total = P.ncosmo * P.nk;
   for (;;) {
     if (tid == 0) *s_tk = atomicAdd(P.ticket, 1u);
@@ -56,7 +78,7 @@ __global__ void __launch_bounds__(32 * TEAM, MINB) k_evolve_team(const __grid_co
     // largest k first, cosmologies interleaved
     const int kd = tk / P.ncosmo, cs = tk - kd * P.ncosmo;
     const int mode = cs * P.nk + (P.nk - 1 - kd);
-    integrate_mode_team<NE, TEAM>(P, *C, W, X, *box, mode, tid);
+    integrate_mode_team<NE, TEAM>(P, *C, W, X, *box, mode, ltid);
     __syncthreads();
   }
 }
@@ -82,7 +104,7 @@ int deb_launch_team(const Problem& P, cudaStream_t st, int nsm) {
   if (team == 4) kern = minb >= 4 ? pick_team<4, 4>(P.n) : (minb == 3 ? pick_team<4, 3>(P.n) : pick_team<4, 2>(P.n));
   else if (team == 8) kern = pick_team<8, 2>(P.n);
   if (!kern) return DEB_E_UNSUPPORTED;
-  const size_t smem = team_smem_bytes(P.np);
+  const size_t smem = team_smem_bytes(P.np, team_segrows(P.lmaxg, P.lmaxgp, P.lmaxr, P.lmaxnu));
   int occ = 0;
   CUDA_TRY(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)kern, 32 * team, smem));

@@ -44,13 +44,36 @@ struct TeamBox {
   double ka0[8];                // element 0 of k_1..k_7
   double kf[TEAM_KF];           // forward-sweep carry of (segment, chain) = slot; slot 32 stays 0 (head elements)
 };
-// per-mode arrays of the segmented sweeps and the launch-constant element -> carry slot table
+// Segmented sweeps work on a TRANSPOSED copy of every tail (l >= 3) quantity: row i of segment lane `ln` lives at
+// i * TEAM_ROW + ln, so that the 32 lanes of a sweep step touch 32 consecutive doubles (the natural layout puts the three
+// stride-1 hierarchies 32 doubles apart: every sweep access was an 8-way bank conflict and the sweeps were half of the
+// solve).  The odd row pitch keeps the element-wise phases (consecutive l of one chain) conflict-free too.  The right-hand
+// side / solution of tail elements exists ONLY there (rt); head elements stay in W.r().
+constexpr int TEAM_ROW = 33;
 struct TeamWs {
-  double* mc;                   // [np] backward: prod of -m over the rows of the segment above and including l
-  double* gc;                   // [np] forward:  prod of  g over the rows of the segment up to and including l (0: head)
-  const int* eslot;             // [np] element -> slot of kf
+  double* rt;                   // [segrows * TEAM_ROW] right-hand side -> solution, tail elements
+  double* mt;                   // backward multipliers m_l (0 on the truncation row)
+  double* iet;                  // inverse pivots 1/e_l
+  double* gt;                   // forward multipliers g_l
+  double* mct;                  // backward: prod of -m over the rows of the segment above and including l
+  double* gct;                  // forward:  prod of  g over the rows of the segment up to and including l
+  const int* eslot;             // [np] element -> slot of kf (32: not a tail element)
+  const int* epos;              // [np] element -> position in the transposed arrays (-1: not a tail element)
+  const int* tailpos;           // [ntail] tail row tt -> position of its element
+  int segrows;                  // rows of the transposed arrays = longest segment
 };
-DEB_HD size_t team_ws_doubles(int np) { return (size_t)2 * np; }
+DEB_HD int team_segrows(int lmaxg, int lmaxgp, int lmaxr, int lmaxnu) {
+  int L = lmaxg > lmaxgp ? lmaxg : lmaxgp;
+  if (lmaxr > L) L = lmaxr;
+  if (lmaxnu > L) L = lmaxnu;
+  return (L - 2 + TEAM_NSEG - 1) / TEAM_NSEG;
+}
+DEB_HD size_t team_ws_doubles(int segrows) { return (size_t)6 * segrows * TEAM_ROW; }
+DEB_DEV void carve_team(TeamWs& X, double* base, int segrows, const int* eslot, const int* epos, const int* tailpos) {
+  const size_t a = (size_t)segrows * TEAM_ROW;
+  X.rt = base; X.mt = X.rt + a; X.iet = X.mt + a; X.gt = X.iet + a; X.mct = X.gt + a; X.gct = X.mct + a;
+  X.eslot = eslot; X.epos = epos; X.tailpos = tailpos; X.segrows = segrows;
+}
 // rows [lo, hi) of chain c's tail (l = 3 .. L) that segment s sweeps
 DEB_DEV void team_segment(const CtaConst& C, int c, int s, int* lo, int* hi) {
   const int L = C.ch_lmax[c], len = (L - 2 + TEAM_NSEG - 1) / TEAM_NSEG;
@@ -59,18 +82,29 @@ DEB_DEV void team_segment(const CtaConst& C, int c, int s, int* lo, int* hi) {
   if (a > b) a = b;
   *lo = a; *hi = b;
 }
-DEB_DEV void init_team_const(const Problem& P, const CtaConst& C, int* eslot, int tid, int nthreads) {
+// position of row l of chain c in the transposed arrays
+DEB_DEV int team_pos(const CtaConst& C, int nch, int c, int l) {
+  const int L = C.ch_lmax[c], len = (L - 2 + TEAM_NSEG - 1) / TEAM_NSEG;
+  const int sg = (l - 3) / len;
+  return (l - 3 - sg * len) * TEAM_ROW + sg * nch + c;
+}
+DEB_DEV void init_team_const(const Problem& P, const CtaConst& C, int* eslot, int* epos, int* tailpos, int tid, int nthreads) {
   for (int e = tid; e < P.np; e += nthreads) {
-    int slot = TEAM_NSEG * NCHMAX;
+    int slot = TEAM_NSEG * NCHMAX, pos = -1;
     const int d = elem_desc(P, e);
     if (d >= 0) {
       const int ty = d & 0xff, l = (d >> 8) & 0xff, c = d >> 16;
       if (ty == R_GEN || ty == R_TRUNC) {
         const int L = C.ch_lmax[c], len = (L - 2 + TEAM_NSEG - 1) / TEAM_NSEG;
         slot = ((l - 3) / len) * P.nch + c;
+        pos = team_pos(C, P.nch, c, l);
       }
     }
-    eslot[e] = slot;
+    eslot[e] = slot; epos[e] = pos;
+  }
+  for (int tt = tid; tt < C.ntail; tt += nthreads) {
+    const int info = C.tail[tt];
+    tailpos[tt] = team_pos(C, P.nch, (info >> 12) & 0xf, info >> 16);
   }
 }
 
@@ -99,7 +133,9 @@ DEB_DEV void init_team_const(const Problem& P, const CtaConst& C, int* eslot, in
 #endif
 
 // element e of the stage vector just solved: x0 for e = 0, otherwise r plus the deferred forward-sweep carry
-#define DEB_KV(e) ((e) == 0 ? x0 : W.r()[e] + X.gc[e] * box.kf[X.eslot[e]])
+// (own element j of the thread: orp[j] points at its right-hand side / solution slot, ogp[j] at its cumulative forward
+//  multiplier -- a zero for head elements --, osl[j] is its carry slot)
+#define DEB_KV(e) ((e) == 0 ? x0 : *orp[j] + *ogp[j] * box.kf[osl[j]])
 // optional phase timing of warp 0 (build with -DDEB_TEAM_TIMING; tools/team_timing.py reads the counters)
 #if defined(DEB_TEAM_TIMING) && !defined(DEB_CPU_EMU)
 #define DEB_TICK(slot) do { const long long now_ = clock64(); if (tid == 0 && kidx == P.nk - 1) atomicAdd((unsigned long long*)&g_team_timing[slot], (unsigned long long)(now_ - tick_)); tick_ = now_; } while (0)
@@ -113,6 +149,17 @@ DEB_DEV void init_team_const(const Problem& P, const CtaConst& C, int* eslot, in
 #define DEB_TICK_INIT
 #endif
 #define DEB_FOR_TEAM(body) _Pragma("unroll") for (int j = 0; j < NE; ++j) { const int e = tid + NT * j; if (e < n) { body } }
+
+// the output conversion runs once per mode and output time: kept out of line, away from the step loop
+#ifdef DEB_CPU_EMU
+inline void team_convert_outputs(const Problem& P, const Cosmo& c, const NuBins& nb, const double* y, double k, double* out) {
+  convert_outputs(P, c, nb, y, k, out);
+}
+#else
+static __device__ __noinline__ void team_convert_outputs(const Problem& P, const Cosmo& c, const NuBins& nb, const double* y, double k, double* out) {
+  convert_outputs(P, c, nb, y, k, out);
+}
+#endif
 
 // background at box.a_req -> chain coefficients, operator slots and the scalars of the metric sources (warp 1)
 DEB_DEV void team_helper_compute(const Problem& P, const CtaConst& C, const Cosmo& c, TeamBox& box, TeamBg& o, Hints& hint2 DEB_LANE_PARAM) {
@@ -178,7 +225,7 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
   const double k2 = k * k;
   DEB_T_BEGIN
     if (tid == 0) { *W.cosmo() = load_cosmo(P, cosmo); box.k = k; }
-    for (int e = tid; e < P.np; e += NT) { X.mc[e] = 0.0; X.gc[e] = 0.0; }
+    for (int e = tid; e < 6 * X.segrows * TEAM_ROW; e += NT) X.rt[e] = 0.0;        // all six transposed arrays
     if (tid < TEAM_KF) box.kf[tid] = 0.0;
   DEB_T_END
   DEB_T_BAR();
@@ -195,17 +242,34 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
   DEB_REGS(double, s1, ); DEB_REGS(double, s2, ); DEB_REGS(double, s3, ); DEB_REGS(double, s4, );
   DEB_TREGS(int, nanflag, );
   // lane constants of the segmented sweeps: lane = segment * nch + chain sweeps rows [sLo, sHi) of its chain
-  DEB_REGS(int, sSeg, ); DEB_REGS(int, sLo, ); DEB_REGS(int, sHi, ); DEB_REGS(int, sBase, ); DEB_REGS(int, sStr, );
+  DEB_REGS(int, sSeg, ); DEB_REGS(int, sLen, ); DEB_REGS(int, sI2, );
   DEB_LANES_BEGIN
-    DEB_USE(sSeg); DEB_USE(sLo); DEB_USE(sHi); DEB_USE(sBase); DEB_USE(sStr);
-    sSeg = -1; sLo = sHi = 3; sBase = 0; sStr = 1;
+    DEB_USE(sSeg); DEB_USE(sLen); DEB_USE(sI2);
+    sSeg = -1; sLen = 0; sI2 = 0;
     if (lane < TEAM_NSEG * nch) {
       sSeg = lane / nch;
       const int ch = lane - sSeg * nch;
-      sBase = C.ch_base[ch]; sStr = C.ch_stride[ch];
-      team_segment(C, ch, sSeg, &sLo, &sHi);
+      int lo, hi;
+      team_segment(C, ch, sSeg, &lo, &hi);
+      sLen = hi - lo;
+      sI2 = C.ch_base[ch] + 2 * C.ch_stride[ch];      // the chain's l = 2 element (a head row)
     }
   DEB_LANES_END
+  // where the thread's own elements keep their right-hand side / solution
+  DEB_TREGS(double*, orp, [NE]); DEB_TREGS(const double*, ogp, [NE]); DEB_TREGS(int, osl, [NE]);
+  DEB_T_BEGIN
+    DEB_TUSE(orp); DEB_TUSE(ogp); DEB_TUSE(osl);
+#pragma unroll
+    for (int j = 0; j < NE; ++j) {
+      const int e = tid + NT * j;
+      orp[j] = W.r(); ogp[j] = &box.kf[TEAM_NSEG * NCHMAX]; osl[j] = TEAM_NSEG * NCHMAX;
+      if (e < n) {
+        const int ep = X.epos[e];
+        osl[j] = X.eslot[e];
+        if (ep >= 0) { orp[j] = X.rt + ep; ogp[j] = X.gct + ep; } else { orp[j] = W.r() + e; }
+      }
+    }
+  DEB_T_END
 
   // ---- prologue (every thread evaluates the scalars; the state is filled element-wise) ----
   double t1 = DEB_LDG(tout);
@@ -314,44 +378,44 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
       DEB_LANES_END
     }
     DEB_IF_WARP(TEAM > 1 ? 1 : 0) {
-      // ---- tails: pivot-free backward elimination l = L .. 3 (one lane per chain) ----
+      // ---- tails: pivot-free backward elimination l = L .. 3 (one lane per chain), factors into the transposed arrays ----
       DEB_LANES_BEGIN
         if (lane < nch) {
-          const int base = C.ch_base[lane], s = C.ch_stride[lane], L = C.ch_lmax[lane];
+          const int L = C.ch_lmax[lane], len = (L - 2 + TEAM_NSEG - 1) / TEAM_NSEG;
           const double kc = J.kc[lane], kp = J.kap[lane];
           double e = idg + kp + (double)(L + 1) * invt0;
           double ie = DEB_RCP(e);
-          int idx = base + L * s;
-          W.ie()[idx] = ie;
-          W.g()[idx] = kc * ie;
-          W.m()[idx] = 0.0;                            // nothing above the truncation row
+          int sg = (L - 3) / len, i = L - 3 - sg * len;            // position of row L
+          int pos = i * TEAM_ROW + sg * nch + lane;
+          X.iet[pos] = ie;
+          X.gt[pos] = kc * ie;
+          X.mt[pos] = 0.0;                             // nothing above the truncation row
           double lower_next = -kc;
-          for (int l = L - 1; l >= 2; --l) {
-            idx -= s;
-            double up = kc * C.ch[l];
-            double mm = up * ie;
-            W.m()[idx] = mm;
-            if (l >= 3) {
-              e = idg + kp - mm * lower_next;
-              ie = DEB_RCP(e);
-              W.ie()[idx] = ie;
-              lower_next = -kc * C.cl[l];
-              W.g()[idx] = -lower_next * ie;
-            } else {
-              W.ie()[idx] = -mm * lower_next;        // Schur increment for the head diagonal (l = 2 row)
-            }
+          for (int l = L - 1; l >= 3; --l) {
+            if (--i < 0) { i = len - 1; --sg; }
+            pos = i * TEAM_ROW + sg * nch + lane;
+            const double mm = (kc * C.ch[l]) * ie;     // W_{l,l+1} / e_{l+1}
+            X.mt[pos] = mm;
+            e = idg + kp - mm * lower_next;
+            ie = DEB_RCP(e);
+            X.iet[pos] = ie;
+            lower_next = -kc * C.cl[l];
+            X.gt[pos] = -lower_next * ie;
           }
+          const int i2 = C.ch_base[lane] + 2 * C.ch_stride[lane];
+          const double mm = (kc * C.ch[2]) * ie;
+          W.m()[i2] = mm;
+          W.ie()[i2] = -mm * lower_next;               // Schur increment for the head diagonal (l = 2 row)
         }
       DEB_LANES_END
       // cumulative multipliers inside every segment of the sweeps (one lane per (segment, chain))
       DEB_LANES_BEGIN
-        DEB_USE(sSeg); DEB_USE(sLo); DEB_USE(sHi); DEB_USE(sBase); DEB_USE(sStr);
+        DEB_USE(sSeg); DEB_USE(sLen);
         if (sSeg >= 0) {
-          const int base = sBase, s = sStr, lo = sLo, hi = sHi;
           double acc = 1.0;
-          for (int l = hi - 1; l >= lo; --l) { const int idx = base + l * s; acc = -W.m()[idx] * acc; X.mc[idx] = acc; }
+          for (int i = sLen - 1; i >= 0; --i) { acc = -X.mt[i * TEAM_ROW + lane] * acc; X.mct[i * TEAM_ROW + lane] = acc; }
           acc = 1.0;
-          for (int l = lo; l < hi; ++l) { const int idx = base + l * s; acc = W.g()[idx] * acc; X.gc[idx] = acc; }
+          for (int i = 0; i < sLen; ++i) { acc = X.gt[i * TEAM_ROW + lane] * acc; X.gct[i * TEAM_ROW + lane] = acc; }
         }
       DEB_LANES_END
     }
@@ -368,8 +432,8 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
           Dual f0 = tail_row<Dual>(C, J.kc, J.kap, W.y(), C.tail[tt], invt0, &e0, &tr0);
           Dual f1 = mk(0.0, 0.0);
           if (two) f1 = tail_row<Dual>(C, J.kc, J.kap, W.y(), C.tail[tt + NTJ], invt0, &e1, &tr1);
-          W.r()[e0] = f0.v + d1t * tr0 * W.y()[e0] + f0.d * x0; W.ja()[e0] = f0.d;
-          if (two) { W.r()[e1] = f1.v + d1t * tr1 * W.y()[e1] + f1.d * x0; W.ja()[e1] = f1.d; }
+          X.rt[X.tailpos[tt]] = f0.v + d1t * tr0 * W.y()[e0] + f0.d * x0; W.ja()[e0] = f0.d;
+          if (two) { X.rt[X.tailpos[tt + NTJ]] = f1.v + d1t * tr1 * W.y()[e1] + f1.d * x0; W.ja()[e1] = f1.d; }
         }
       DEB_T_END
     }
@@ -401,6 +465,7 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
           }
         }
       DEB_LANES_END
+#pragma unroll 1
       for (int bt = 0; bt < 8; ++bt) {
         DEB_LANES_BEGIN
           DEB_USE(pcol); DEB_USE(pkey);
@@ -499,29 +564,29 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
         // ---- own elements: keep k_{st-1}, stage state u, C-combinations -> r; thread 0 closes row 0: x_0 of this stage ----
 #define DEB_ROW0 if (e == 0) { W.r()[0] += cur.bgs[0] * cur.a_req; W.u()[0] = cur.a_req; }
         DEB_T_BEGIN
-          DEB_TUSE(ks);
+          DEB_TUSE(ks); DEB_TUSE(orp); DEB_TUSE(ogp); DEB_TUSE(osl);
           switch (st) {
             case 2: DEB_FOR_TEAM(ks[0][j] = DEB_KV(e);
                                  W.u()[e] = W.y()[e] + RD_A21 * ks[0][j];
-                                 W.r()[e] = invdt * (RD_C21 * ks[0][j]); DEB_ROW0) break;
+                                 *orp[j] = invdt * (RD_C21 * ks[0][j]); DEB_ROW0) break;
             case 3: DEB_FOR_TEAM(ks[1][j] = DEB_KV(e);
                                  W.u()[e] = W.y()[e] + RD_A31 * ks[0][j] + RD_A32 * ks[1][j];
-                                 W.r()[e] = invdt * (RD_C31 * ks[0][j] + RD_C32 * ks[1][j]); DEB_ROW0) break;
+                                 *orp[j] = invdt * (RD_C31 * ks[0][j] + RD_C32 * ks[1][j]); DEB_ROW0) break;
             case 4: DEB_FOR_TEAM(ks[2][j] = DEB_KV(e);
                                  W.u()[e] = W.y()[e] + RD_A41 * ks[0][j] + RD_A42 * ks[1][j] + RD_A43 * ks[2][j];
-                                 W.r()[e] = invdt * (RD_C41 * ks[0][j] + RD_C42 * ks[1][j] + RD_C43 * ks[2][j]); DEB_ROW0) break;
+                                 *orp[j] = invdt * (RD_C41 * ks[0][j] + RD_C42 * ks[1][j] + RD_C43 * ks[2][j]); DEB_ROW0) break;
             case 5: DEB_FOR_TEAM(ks[3][j] = DEB_KV(e);
                                  W.u()[e] = W.y()[e] + RD_A51 * ks[0][j] + RD_A52 * ks[1][j] + RD_A53 * ks[2][j] + RD_A54 * ks[3][j];
-                                 W.r()[e] = invdt * (RD_C51 * ks[0][j] + RD_C52 * ks[1][j] + RD_C53 * ks[2][j] + RD_C54 * ks[3][j]); DEB_ROW0) break;
+                                 *orp[j] = invdt * (RD_C51 * ks[0][j] + RD_C52 * ks[1][j] + RD_C53 * ks[2][j] + RD_C54 * ks[3][j]); DEB_ROW0) break;
             case 6: DEB_FOR_TEAM(ks[4][j] = DEB_KV(e);
                                  W.u()[e] = W.y()[e] + RD_A61 * ks[0][j] + RD_A62 * ks[1][j] + RD_A63 * ks[2][j] + RD_A64 * ks[3][j] + RD_A65 * ks[4][j];
-                                 W.r()[e] = invdt * (RD_C61 * ks[0][j] + RD_C62 * ks[1][j] + RD_C63 * ks[2][j] + RD_C64 * ks[3][j] + RD_C65 * ks[4][j]); DEB_ROW0) break;
+                                 *orp[j] = invdt * (RD_C61 * ks[0][j] + RD_C62 * ks[1][j] + RD_C63 * ks[2][j] + RD_C64 * ks[3][j] + RD_C65 * ks[4][j]); DEB_ROW0) break;
             case 7: DEB_FOR_TEAM(ks[5][j] = DEB_KV(e);
                                  W.u()[e] = W.u()[e] + ks[5][j];
-                                 W.r()[e] = invdt * (RD_C71 * ks[0][j] + RD_C72 * ks[1][j] + RD_C73 * ks[2][j] + RD_C74 * ks[3][j] + RD_C75 * ks[4][j] + RD_C76 * ks[5][j]); DEB_ROW0) break;
+                                 *orp[j] = invdt * (RD_C71 * ks[0][j] + RD_C72 * ks[1][j] + RD_C73 * ks[2][j] + RD_C74 * ks[3][j] + RD_C75 * ks[4][j] + RD_C76 * ks[5][j]); DEB_ROW0) break;
             default: DEB_FOR_TEAM(ks[6][j] = DEB_KV(e);
                                  W.u()[e] = W.u()[e] + ks[6][j];
-                                 W.r()[e] = invdt * (RD_C81 * ks[0][j] + RD_C82 * ks[1][j] + RD_C83 * ks[2][j] + RD_C84 * ks[3][j] + RD_C85 * ks[4][j] + RD_C86 * ks[5][j] + RD_C87 * ks[6][j]); DEB_ROW0) break;
+                                 *orp[j] = invdt * (RD_C81 * ks[0][j] + RD_C82 * ks[1][j] + RD_C83 * ks[2][j] + RD_C84 * ks[3][j] + RD_C85 * ks[4][j] + RD_C86 * ks[5][j] + RD_C87 * ks[6][j]); DEB_ROW0) break;
           }
         DEB_T_END
 #undef DEB_ROW0
@@ -558,10 +623,12 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
             int e0, e1 = 0; double tr0, tr1 = 0.0, f1 = 0.0, r1 = 0.0, y1 = 0.0;
             const bool two = tt + NTS < C.ntail;
             const double f0 = tail_row<double>(C, cur.kc, cur.kap, W.u(), C.tail[tt], invts, &e0, &tr0);
-            const double r0 = W.r()[e0], y0 = W.y()[e0];
-            if (two) { f1 = tail_row<double>(C, cur.kc, cur.kap, W.u(), C.tail[tt + NTS], invts, &e1, &tr1); r1 = W.r()[e1]; y1 = W.y()[e1]; }
-            W.r()[e0] = r0 + f0 + dtt * tr0 * y0 + W.ja()[e0] * x0;
-            if (two) W.r()[e1] = r1 + f1 + dtt * tr1 * y1 + W.ja()[e1] * x0;
+            const int p0 = X.tailpos[tt];
+            int p1 = 0;
+            const double r0 = X.rt[p0], y0 = W.y()[e0];
+            if (two) { f1 = tail_row<double>(C, cur.kc, cur.kap, W.u(), C.tail[tt + NTS], invts, &e1, &tr1); p1 = X.tailpos[tt + NTS]; r1 = X.rt[p1]; y1 = W.y()[e1]; }
+            X.rt[p0] = r0 + f0 + dtt * tr0 * y0 + W.ja()[e0] * x0;
+            if (two) X.rt[p1] = r1 + f1 + dtt * tr1 * y1 + W.ja()[e1] * x0;
           }
         DEB_T_END
       }
@@ -606,27 +673,23 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
         DEB_REGS(double, sT, ); DEB_REGS(double, sE, ); DEB_REGS(double, sA, ); DEB_REGS(double, sK, );
         DEB_TICK2_START
         DEB_LANES_BEGIN          // backward sweep: b'_l = b_l - m_l b'_{l+1}
-          DEB_USE(sT); DEB_USE(sE); DEB_USE(sA); DEB_USE(sK);
-          DEB_USE(sSeg); DEB_USE(sLo); DEB_USE(sHi); DEB_USE(sBase); DEB_USE(sStr);
+          DEB_USE(sT); DEB_USE(sE); DEB_USE(sA); DEB_USE(sK); DEB_USE(sSeg); DEB_USE(sLen);
           sE = 0.0; sA = 1.0; sK = 0.0;
-          if (sSeg >= 0) {
-            const int base = sBase, s = sStr, lo = sLo, hi = sHi;
-            if (hi > lo) {
-              double* rp = W.r() + (base + (hi - 1) * s);
-              const double* mp = W.m() + (base + (hi - 1) * s);
-              double p = 0.0;
-              double rn = *rp, mn = *mp;
-              for (int l = hi - 1; l > lo; --l) {
-                const double rc = rn, mc = mn;
-                rn = *(rp - s); mn = *(mp - s);
-                p = rc - mc * p;
-                *rp = p;
-                rp -= s; mp -= s;
-              }
-              p = rn - mn * p;
+          if (sLen > 0) {
+            double* rp = X.rt + ((sLen - 1) * TEAM_ROW + lane);
+            const double* mp = X.mt + ((sLen - 1) * TEAM_ROW + lane);
+            double p = 0.0;
+            double rn = *rp, mn = *mp;
+            for (int i = sLen - 1; i > 0; --i) {
+              const double rc = rn, mc = mn;
+              rn = *(rp - TEAM_ROW); mn = *(mp - TEAM_ROW);
+              p = rc - mc * p;
               *rp = p;
-              sE = p; sA = X.mc[base + lo * s];
+              rp -= TEAM_ROW; mp -= TEAM_ROW;
             }
+            p = rn - mn * p;
+            *rp = p;
+            sE = p; sA = X.mct[lane];
           }
           sT = sE;
         DEB_LANES_END
@@ -640,10 +703,8 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
         }
         DEB_LANES_BEGIN
           DEB_USE(sT);
-          if (lane < nch) {        // l = 2 (a head row): b'_2 = b_2 - m_2 b'_3
-            const int i2 = C.ch_base[lane] + 2 * C.ch_stride[lane];
-            W.r()[i2] = W.r()[i2] - W.m()[i2] * sT;
-          }
+          DEB_USE(sI2);
+          if (lane < nch) W.r()[sI2] = W.r()[sI2] - W.m()[sI2] * sT;        // l = 2 (a head row): b'_2 = b_2 - m_2 b'_3
         DEB_LANES_END
         DEB_TICK2(11);
         // head: p = D^-1 b (block inverses), then the rank-2 Woodbury correction and the a h' row
@@ -679,33 +740,30 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
         }
         DEB_TICK2(13);
         DEB_LANES_BEGIN          // forward sweep: x_l = b'_l/e_l + g_l x_{l-1}
-          DEB_USE(sT); DEB_USE(sE); DEB_USE(sA); DEB_USE(sK);
-          DEB_USE(sSeg); DEB_USE(sLo); DEB_USE(sHi); DEB_USE(sBase); DEB_USE(sStr);
+          DEB_USE(sT); DEB_USE(sE); DEB_USE(sA); DEB_USE(sK); DEB_USE(sSeg); DEB_USE(sLen); DEB_USE(sI2);
           const double kb = sK;          // backward carry of this lane's segment
           sE = 0.0; sA = 1.0; sK = 0.0;
           if (sSeg >= 0) {
-            const int sg = sSeg, base = sBase, s = sStr, lo = sLo, hi = sHi;
-            double x = sg == 0 ? W.r()[base + 2 * s] : 0.0;        // segment 0 starts from x_2, the others from zero
-            if (hi > lo) {
-              const int i0 = base + lo * s;
-              double* rp = W.r() + i0;
-              const double* ip = W.ie() + i0;
-              const double* gp = W.g() + i0;
-              const double* cp = X.mc + i0;
+            double x = sSeg == 0 ? W.r()[sI2] : 0.0;        // segment 0 starts from x_2, the others from zero
+            if (sLen > 0) {
+              double* rp = X.rt + lane;
+              const double* ip = X.iet + lane;
+              const double* gp = X.gt + lane;
+              const double* cp = X.mct + lane;
               double cn = (*rp + *cp * kb) * *ip, gn = *gp;
-              for (int l = lo; l < hi - 1; ++l) {
+              for (int i = 0; i < sLen - 1; ++i) {
                 const double cc = cn, gc = gn;
-                cn = (*(rp + s) + *(cp + s) * kb) * *(ip + s); gn = *(gp + s);
+                cn = (*(rp + TEAM_ROW) + *(cp + TEAM_ROW) * kb) * *(ip + TEAM_ROW); gn = *(gp + TEAM_ROW);
                 x = cc + gc * x;
                 *rp = x;
-                rp += s; ip += s; gp += s; cp += s;
+                rp += TEAM_ROW; ip += TEAM_ROW; gp += TEAM_ROW; cp += TEAM_ROW;
               }
               x = cn + gn * x;
               *rp = x;
-              sA = X.gc[base + (hi - 1) * s];
+              sA = X.gct[(sLen - 1) * TEAM_ROW + lane];
             }
             sE = x;
-            if (sg == 0) sA = 0.0;                                  // x_2 is already inside segment 0
+            if (sSeg == 0) sA = 0.0;                                // x_2 is already inside segment 0
           }
           sT = sE;
         DEB_LANES_END
@@ -729,7 +787,7 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
 
     // y1 = u + k8 -> u ; err = k8 -> r
     DEB_T_BEGIN
-      DEB_TUSE(nanflag);
+      DEB_TUSE(nanflag); DEB_TUSE(orp); DEB_TUSE(ogp); DEB_TUSE(osl);
       nanflag = 0;
       DEB_FOR_TEAM(const double kv = DEB_KV(e); W.r()[e] = kv;
                    const double y1v = W.u()[e] + kv; W.u()[e] = y1v; nanflag |= (y1v != y1v);)
@@ -756,9 +814,9 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
     const double E = sqrt(errnorm2 / 6.0);
     const bool keep = (P.mode == 3) ? (DEB_LDG(P.rp_keep + (size_t)mode * P.rp_stride + nsteps) != 0) : (E < 1.0);
     double inv = 1.0 / E;
-    double f1 = P.c1 != 0.0 ? ((inv > 0.0 && !isinf(inv)) ? exp(P.c1 * log(inv)) : pow(inv, P.c1)) : 1.0;
-    double f2 = P.c2 != 0.0 ? exp(P.c2 * log(inv_prev)) : 1.0;
-    double f3 = P.c3 != 0.0 ? exp(P.c3 * log(inv_pprev)) : 1.0;
+    double f1 = P.c1 != 0.0 ? ((inv > 0.0 && !isinf(inv)) ? DEB_EXP(P.c1 * DEB_LOG(inv)) : DEB_POW(inv, P.c1)) : 1.0;
+    double f2 = P.c2 != 0.0 ? DEB_EXP(P.c2 * DEB_LOG(inv_prev)) : 1.0;
+    double f3 = P.c3 != 0.0 ? DEB_EXP(P.c3 * DEB_LOG(inv_pprev)) : 1.0;
     double fac = fmin(fmax(P.safety * f1 * f2 * f3, keep ? 1.0 : P.factormin), P.factormax);
     if (!(fac == fac)) fac = NAN;
     const double dtn = dt * fac;
@@ -783,11 +841,11 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
           DEB_T_BEGIN
             if (tid == 0) {
               double o20[20];
-              convert_outputs(P, c, nb, W.r(), k, o20);
+              team_convert_outputs(P, c, nb, W.r(), k, o20);
               for (int q = 0; q < 20; ++q) P.y_out[obase * 20 + q] = o20[q];
               if (P.pk_out && P.power_idx >= 0) {
                 double yv = o20[P.power_idx];
-                P.pk_out[obase] = 2.0 * 9.869604401089358 * c.As * pow(k / c.kp, c.ns - 1.0) * pow(k, -3.0) * yv * yv;
+                P.pk_out[obase] = 2.0 * 9.869604401089358 * c.As * DEB_POW(k / c.kp, c.ns - 1.0) * DEB_POW(k, -3.0) * yv * yv;
               }
             }
           DEB_T_END

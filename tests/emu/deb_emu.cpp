@@ -134,16 +134,17 @@ static void run_all_team(const Problem& P) {
   CtaConst C;
   std::vector<int> tail(P.np);
   for (int t = 0; t < 32; ++t) init_cta_const(P, C, tail.data(), t, 32);
-  std::vector<int> eslot(P.np);
-  for (int t = 0; t < 32; ++t) init_team_const(P, C, eslot.data(), t, 32);
-  std::vector<double> ws(warp_ws_doubles(P.np) + team_ws_doubles(P.np));
+  std::vector<int> eslot(P.np), epos(P.np), tailpos(P.np);
+  for (int t = 0; t < 32; ++t) init_team_const(P, C, eslot.data(), epos.data(), tailpos.data(), t, 32);
+  const int segrows = team_segrows(P.lmaxg, P.lmaxgp, P.lmaxr, P.lmaxnu);
+  std::vector<double> ws(warp_ws_doubles(P.np) + team_ws_doubles(segrows));
   const int total = P.ncosmo * P.nk;
 #pragma omp parallel for schedule(dynamic, 1) firstprivate(ws)
   for (int m = 0; m < total; ++m) {
     WarpWs W;
     carve(W, ws.data(), P.np);
     TeamWs X;
-    X.mc = ws.data() + warp_ws_doubles(P.np); X.gc = X.mc + P.np; X.eslot = eslot.data();
+    carve_team(X, ws.data() + warp_ws_doubles(P.np), segrows, eslot.data(), epos.data(), tailpos.data());
     TeamBox box;
     integrate_mode_team<NE, TEAM>(P, C, W, X, box, total - 1 - m);
   }

@@ -34,8 +34,10 @@ def test_tangent_batch_of_cosmologies(gpu_lib):
     pc.check_tangent_batch_of_cosmologies(gpu_lib)
 
 
-def test_tangent_primal_half_equals_plain_solve(gpu_lib):
-    """The primal outputs of the tangent launch are those of the primal kernel (same source, same step sequence)."""
+def test_tangent_primal_half_equals_plain_solve(gpu_lib, monkeypatch):
+    """The primal outputs of the tangent launch are those of the one-warp primal kernel (same source, same step
+    sequence; a small primal launch would otherwise pick the CTA-per-mode kernel, whose sweeps round differently)."""
+    monkeypatch.setenv("DEB_VARIANT", "warp")
     case = pc.load_tangent_case("default_n72")
     ks = np.geomspace(1e-3, 1.0, 24)
     ctrl = _cabi.make_ctrl(rtol=1e-4, atol=1e-4)

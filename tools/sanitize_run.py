@@ -13,6 +13,8 @@ for dm, nk in (((11, 11, 11, 8, 3), 6), ((31, 31, 31, 31, 5), 4)):
     dims = _cabi.make_dims(ncosmo=1, nk=nk, nout=2, lmaxg=lg, lmaxgp=lp, lmaxr=lr, lmaxnu=ln, nqmax=nq, nth=tab.nth, nnu=tab.nnu, max_steps=60, power_idx=4)
     out = lib.evolve_host(dims, _cabi.make_ctrl(rtol=1e-3, atol=1e-3), tab.scalars[None], tab.tables[None], ks, np.array([0.001, 0.002]), want_pk=True)
     print("n", lib.nvar(*dm), "status", out["status"][0], "steps", out["nsteps"][0])
+if os.environ.get("DEB_SANITIZE_PRIMAL_ONLY"):
+    sys.exit(0)
 # tangent kernel (one direction) and batched shared-step kernel (one CTA; a 2-CTA cluster)
 z = np.load(os.path.join(ROOT, "tests", "golden", "fisher_seeds.npz"))
 ks = np.geomspace(1e-3, 0.05, 3)

@@ -9,19 +9,21 @@ from discoeb_b200 import _cabi
 lib = _cabi.default_library()
 tab = helpers.load_tables("fiducial")
 nk = int(sys.argv[1]) if len(sys.argv) > 1 else 512
-ks = np.geomspace(1e-4, 10.0, nk)
+kmax = float(sys.argv[2]) if len(sys.argv) > 2 else 10.0
+aout = float(sys.argv[3]) if len(sys.argv) > 3 else 1.0
+ks = np.geomspace(1e-4, kmax, nk)
 dims = _cabi.make_dims(ncosmo=1, nk=nk, nout=1, lmaxg=31, lmaxgp=31, lmaxr=31, lmaxnu=31, nqmax=5, nth=tab.nth, nnu=tab.nnu, max_steps=2048, power_idx=4)
 ctrl = _cabi.make_ctrl(rtol=1e-4, atol=1e-4)
 os.environ["DEB_VARIANT"] = "team"
 buf = (ctypes.c_longlong * 16)()
 lib.lib.deb_debug_team_timing(buf, 1)
-out = lib.evolve_host(dims, ctrl, tab.scalars[None], tab.tables[None], ks, np.array([1.0]), want_pk=True)
+out = lib.evolve_host(dims, ctrl, tab.scalars[None], tab.tables[None], ks, np.array([aout]), want_pk=True)
 lib.lib.deb_debug_team_timing(buf, 0)
 t = np.array(list(buf), dtype=float)
 steps = t[15]
 names = ["J: rows/factors (own work)", "J: wait barrier", "J: block inverses + Woodbury", "stage: own elements", "stage: wait B1", "stage: metric+head rows (+x0)",
          "stage: wait B2", "stage: solve", "stage: wait B4", "step end: norm, controller, copy"]
-print(f"kernel_ms {out['kernel_ms']:.2f} steps of the largest-k mode {int(steps)} cycles/step {t[:10].sum()/steps:.0f}")
+print(f"kmax {kmax} a_out {aout} kernel_ms {out['kernel_ms']:.2f} steps of the largest-k mode {int(steps)} cycles/step {t[:10].sum()/steps:.0f}")
 for i, nm in enumerate(names):
     print(f"  {nm:42s} {t[i]/steps:9.0f} cycles/step  {100*t[i]/t[:10].sum():5.1f} %")
 for i, nm in zip(range(10, 15), ["solve: backward local sweep", "solve: backward carry + l=2 rows", "solve: gather + block multiply", "solve: Woodbury sums + write-back", "solve: forward local sweep"]):
