@@ -45,7 +45,23 @@ WORKLOAD = dict(name="config2: LCDM + 1 massive nu, lmax=31 (32 multipoles), nq=
 METRIC = "k-modes/sec (ms per P(k), N_k=512, in ms_per_step)"
 
 
-NCU_DRAM_BYTES_PER_LAUNCH = 344320 + 22528     # ncu --set full, k_evolve_h<9>, 512 modes (profiles/r1_v10_k_evolve_h9_ncu_summary.txt)
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_evolve_team<3,4,2> launch on this workload (ncu --set full),
+# read from the committed summary so that the number and its evidence cannot drift apart
+NCU_SUMMARY = os.path.join(ROOT, "profiles", "r1_v18_k_evolve_team_ncu_summary.txt")
+
+
+def ncu_dram_bytes_per_launch():
+    try:
+        tot = 0.0
+        for ln in open(NCU_SUMMARY):
+            for key in ("dram__bytes_read.sum [", "dram__bytes_write.sum ["):
+                if ln.startswith(key):
+                    unit = ln[len(key):ln.index("]")]
+                    val = float(ln.split("=")[1])
+                    tot += val * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+        return int(tot) if tot > 0 else None
+    except Exception:
+        return None
 
 
 def f_step(n):
@@ -249,11 +265,11 @@ def run_ours(args, rank, world):
                     config=dict(workload=WORKLOAD["name"], modes_per_gpu=nk, attempted_steps_per_pass=total_steps,
                                 l2="flushed between timed iterations (256 MB write)", parallelism=f"k-modes x{world} (independent batches, all-gather of y)"),
                     roofline=dict(bound="fp64", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak,
-                                  traffic=NCU_DRAM_BYTES_PER_LAUNCH,
+                                  traffic=ncu_dram_bytes_per_launch(), kernel="k_evolve_team<3,4,2> (one CTA of 4 warps per mode)",
                                   note="FP64 FMA pipe (the path is neither HBM- nor tensor-bound); peak measured on this GPU by "
                                        "deb_fp64_peak_tflops (dependent-free DFMA streams) x n_gpus; algorithmic flops = "
-                                       "(370 n + 3000) x attempted steps, n=265; traffic = dram bytes read+written per k_evolve "
-                                       "launch from profiles/r1_v10_k_evolve_h9_ncu_summary.txt (0.37 MB: HBM is idle)"),
+                                       "(370 n + 3000) x attempted steps, n=265; traffic = dram bytes read+written per k_evolve_team "
+                                       "launch from profiles/r1_v18_k_evolve_team_ncu_summary.txt (HBM is idle)"),
                     e2e=dict(value=world * nk / (e2e * 1e-3), unit="k-modes/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
                              ms_per_step=e2e),
                     gpu_launches=2 * args.steps, clocks=clocks)

@@ -568,6 +568,17 @@ DEB_DEV Dual spl_at(const double* v, const SplPos& p, Dual xn) {
   return mk(p.A * v[0] + p.B * v[1] + (p.cA * v[2] + p.cB * v[3]), ((v[1] - v[0]) + (p.dA * v[2] + p.dB * v[3])) * p.invh * xn.d);
 }
 
+// the refill runs once per few dozen evaluations: a translation unit may keep it out of line (DEB_COLD), away from
+// the step loop's instruction footprint
+#ifndef DEB_COLD
+#define DEB_COLD DEB_DEV
+#endif
+DEB_COLD void icache_refill(const Cosmo& c, double lg, Hints& hint, double* ic, bool miss_th, bool miss_nu) {
+  DEB_SYNC();
+  if (miss_th) { hint.th = spl_locate(c.cs2a.x, c.cs2a.n, lg, hint.th); icache_fill(ic, c.cs2a, &c.xe, hint.th); }   // cs2a, xe share knots
+  if (miss_nu) { hint.nu = spl_locate(c.lrn.x, c.lrn.n, lg, hint.nu); icache_fill(ic + 12, c.lrn, nullptr, hint.nu); }
+  DEB_SYNC();
+}
 template <class T>
 DEB_DEV void compute_bg(const Cosmo& c, const NuBins& nb, int nq, T a, Hints& hint, double* ic, Bg<T>& b) {
   T loga = dlog(a);
@@ -575,12 +586,7 @@ DEB_DEV void compute_bg(const Cosmo& c, const NuBins& nb, int nq, T a, Hints& hi
   // (all lanes take the same branch: the test reads the cache before anyone refills it; the refill writes the
   //  same values from every lane, fenced on both sides)
   const bool miss_th = !icache_hit(ic, hint.th, c.cs2a.n, lg), miss_nu = !icache_hit(ic + 12, hint.nu, c.lrn.n, lg);
-  if (miss_th || miss_nu) {
-    DEB_SYNC();
-    if (miss_th) { hint.th = spl_locate(c.cs2a.x, c.cs2a.n, lg, hint.th); icache_fill(ic, c.cs2a, &c.xe, hint.th); }   // cs2a, xe share knots
-    if (miss_nu) { hint.nu = spl_locate(c.lrn.x, c.lrn.n, lg, hint.nu); icache_fill(ic + 12, c.lrn, nullptr, hint.nu); }
-    DEB_SYNC();
-  }
+  if (miss_th || miss_nu) icache_refill(c, lg, hint, ic, miss_th, miss_nu);
   const SplPos pth = spl_pos(ic, lg);
   const SplPos pnu = spl_pos(ic + 12, lg);
   T inva = 1.0 / a;

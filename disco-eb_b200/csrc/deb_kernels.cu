@@ -224,9 +224,11 @@ static int launch_evolve(const Problem& P, cudaStream_t st) {
   CUDA_TRY(cudaGetDevice(&dev));
   CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
   if (P.batch_size == 0 && P.ntan == 0) {
-    // launches that cannot fill the GPU: one CTA (4 warps) per mode, deb_team.cuh
+    // launches that cannot fill the GPU: one CTA (4 warps) per mode, deb_team.cuh.  Measured crossover against the
+    // one-warp kernels (tools/time_crossover.py, profiles/r1_v19_crossover.txt): ~10 modes per SM at n = 265
+    // (1536 modes: 45.0 vs 44.4 ms), ~7 per SM at n = 72 (1024 modes: 32.4 vs 33.0 ms)
     const long nm = (long)P.ncosmo * P.nk;
-    const bool want = getenv("DEB_VARIANT") ? variant_forced("team") : nm <= (long)nsm * 4;
+    const bool want = getenv("DEB_VARIANT") ? variant_forced("team") : nm <= (long)nsm * (P.n > 128 ? 8 : 6);
     if (want) {
       const int rc = deb_launch_team(P, st, nsm);
       if (rc != DEB_E_UNSUPPORTED) return rc;

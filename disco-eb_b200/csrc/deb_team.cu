@@ -14,6 +14,7 @@ static __device__ __noinline__ double deb_ni_pow(double x, double y) { return po
 #define DEB_EXP(x) deb_ni_exp(x)
 #define DEB_LOG(x) deb_ni_log(x)
 #define DEB_POW(x, y) deb_ni_pow(x, y)
+#define DEB_COLD static __device__ __noinline__
 #include "deb_core.cuh"
 #ifdef DEB_TEAM_TIMING
 __device__ long long g_team_timing[16];

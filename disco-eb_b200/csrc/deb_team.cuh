@@ -391,6 +391,7 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
           X.gt[pos] = kc * ie;
           X.mt[pos] = 0.0;                             // nothing above the truncation row
           double lower_next = -kc;
+#pragma unroll 1
           for (int l = L - 1; l >= 3; --l) {
             if (--i < 0) { i = len - 1; --sg; }
             pos = i * TEAM_ROW + sg * nch + lane;
@@ -413,8 +414,10 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
         DEB_USE(sSeg); DEB_USE(sLen);
         if (sSeg >= 0) {
           double acc = 1.0;
+#pragma unroll 1
           for (int i = sLen - 1; i >= 0; --i) { acc = -X.mt[i * TEAM_ROW + lane] * acc; X.mct[i * TEAM_ROW + lane] = acc; }
           acc = 1.0;
+#pragma unroll 1
           for (int i = 0; i < sLen; ++i) { acc = X.gt[i * TEAM_ROW + lane] * acc; X.gct[i * TEAM_ROW + lane] = acc; }
         }
       DEB_LANES_END
@@ -805,10 +808,16 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
     // ================= error norm, PID controller (diffrax semantics) =================
     {
       const double ik2 = DEB_RCP(k2);
-#define DEB_ERRC(e, w) { double y0v = W.y()[e], y1v = anynan ? y0v : W.u()[e], ev = W.r()[e]; if (ev != ev) ev = INFINITY; \
-        double sc = ev / (P.atol + fmax(fabs(y0v), fabs(y1v)) * P.rtol) * (w); errnorm2 += sc * sc; }
-      DEB_ERRC(0, 1.0) DEB_ERRC(2, k2) DEB_ERRC(3, 1.0) DEB_ERRC(5, 1.0) DEB_ERRC(6, ik2) DEB_ERRC(7, 1.0)
-#undef DEB_ERRC
+      // components 0, 2, 3, 5, 6, 7 with weights 1, k^2, 1, 1, 1/k^2, 1 (perturbations.py:701-724), one copy of the code
+#pragma unroll 1
+      for (int q = 0; q < 6; ++q) {
+        const int e = q == 0 ? 0 : (q < 3 ? q + 1 : q + 2);
+        const double w = q == 1 ? k2 : (q == 4 ? ik2 : 1.0);
+        double y0v = W.y()[e], y1v = anynan ? y0v : W.u()[e], ev = W.r()[e];
+        if (ev != ev) ev = INFINITY;
+        const double sc = ev / (P.atol + fmax(fabs(y0v), fabs(y1v)) * P.rtol) * w;
+        errnorm2 += sc * sc;
+      }
     }
     DEB_T_BAR();          // y, u, r are rewritten below (output sampling, accepted state)
     const double E = sqrt(errnorm2 / 6.0);
