@@ -43,6 +43,8 @@ struct TeamBox {
   double ic2[ICACHE];           // warp 1's own spline interval cache
   double ka0[8];                // element 0 of k_1..k_7
   double kf[TEAM_KF];           // forward-sweep carry of (segment, chain) = slot; slot 32 stays 0 (head elements)
+  double t3[NCHMAX];            // sweep warp -> warp 0: the swept b'_3 of every chain
+  double fe[32], fa[32];        // sweep warp -> warp 0: end value and multiplier product of every forward segment
 };
 // Segmented sweeps work on a TRANSPOSED copy of every tail (l >= 3) quantity: row i of segment lane `ln` lives at
 // i * TEAM_ROW + ln, so that the 32 lanes of a sweep step touch 32 consecutive doubles (the natural layout puts the three
@@ -114,6 +116,8 @@ DEB_DEV void init_team_const(const Problem& P, const CtaConst& C, int* eslot, in
 #define DEB_T_END }
 #define DEB_T_BAR()
 #define DEB_T_BAR_BUT1()
+#define DEB_NB_ARRIVE(id, nthr)
+#define DEB_NB_SYNC(id, nthr)
 #define DEB_TREGS(type, name, dims) type name##_all[NT] dims
 #define DEB_TUSE(name) auto& name = name##_all[tid]
 #define DEB_IF_WARP(w)
@@ -126,6 +130,9 @@ DEB_DEV void init_team_const(const Problem& P, const CtaConst& C, int* eslot, in
 // barrier of the team without warp 1 (named barrier 1): warp 1 evaluates the next stage's background from the first
 // barrier of a stage to the last and must not hold up the solve
 #define DEB_T_BAR_BUT1() do { if (TEAM >= 3) { if (wid != 1) asm volatile("bar.sync 1, %0;" ::"n"(32 * TEAM - 32) : "memory"); } else __syncthreads(); } while (0)
+// producer/consumer hand-off between two warps (PTX named barriers): the producer arrives and goes on, the consumer waits
+#define DEB_NB_ARRIVE(id, nthr) asm volatile("bar.arrive %0, %1;" ::"n"(id), "n"(nthr) : "memory")
+#define DEB_NB_SYNC(id, nthr) asm volatile("bar.sync %0, %1;" ::"n"(id), "n"(nthr) : "memory")
 #define DEB_TREGS(type, name, dims) type name dims
 #define DEB_TUSE(name)
 #define DEB_IF_WARP(w) if (wid == (w))
@@ -665,16 +672,24 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
         }
       }
       DEB_TICK(5);
-      if (st > 1) DEB_T_BAR_BUT1();
-      DEB_TICK(6);                    // r complete (stage 1: the barrier after the Jacobian pieces)
-
-      // ---- warp 0: solve W x = r in place.  x_0 and its column are already in; every hierarchy tail is swept in
-      //      TEAM_NSEG segments at once (lane = segment * nch + chain): local recurrences from zero, a carry chain
-      //      over the segments, then x_l = local_l + (product of multipliers) * carry.  The forward carries are applied
-      //      by whoever reads the result (DEB_KV).
-      DEB_IF_WARP(0) {
+      // ---- solve W x = r in place.  x_0 and its column are already in.  Every hierarchy tail is swept in TEAM_NSEG
+      //      segments at once (lane = segment * nch + chain): local recurrences from zero, a carry chain over the
+      //      segments, then x_l = local_l + (product of multipliers) * carry.  The sweeps need the tail rows only, so
+      //      the LAST warp runs them while warp 0 is still busy with the metric sources and the head rows (stage 1: the
+      //      block inverses): backward sweep + carries, then the forward recurrences from zero, which do not depend on
+      //      the head either.  Warp 0 takes the swept l = 3 values into the head solve and finishes with the forward
+      //      carry chain; the forward carries are applied by whoever reads the result (DEB_KV).
+      constexpr int WS = TEAM - 1;                     // the sweep warp
+      if (st > 1 && TEAM >= 4) {                       // tail rows (warps 2 .. TEAM-1) complete before the sweeps start
+        DEB_IF_WARP(WS) { DEB_NB_SYNC(2, 32 * (TEAM - 2)); }
+#ifndef DEB_CPU_EMU
+        else if (wid >= 2) DEB_NB_ARRIVE(2, 32 * (TEAM - 2));
+#endif
+      } else if (st > 1) {
+        DEB_T_BAR_BUT1();
+      }
+      DEB_IF_WARP(WS) {
         DEB_REGS(double, sT, ); DEB_REGS(double, sE, ); DEB_REGS(double, sA, ); DEB_REGS(double, sK, );
-        DEB_TICK2_START
         DEB_LANES_BEGIN          // backward sweep: b'_l = b_l - m_l b'_{l+1}
           DEB_USE(sT); DEB_USE(sE); DEB_USE(sA); DEB_USE(sK); DEB_USE(sSeg); DEB_USE(sLen);
           sE = 0.0; sA = 1.0; sK = 0.0;
@@ -696,7 +711,6 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
           }
           sT = sE;
         DEB_LANES_END
-        DEB_TICK2(10);
         for (int sg = TEAM_NSEG - 2; sg >= 0; --sg) {        // carry chain: the true b' just above segment sg
           DEB_LANES_BEGIN
             DEB_USE(sT); DEB_USE(sE); DEB_USE(sA); DEB_USE(sK); DEB_USE(sSeg);
@@ -706,8 +720,41 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
         }
         DEB_LANES_BEGIN
           DEB_USE(sT);
+          if (lane < nch) box.t3[lane] = sT;           // b'_3 of the chain, for its l = 2 row in the head
+        DEB_LANES_END
+        if (TEAM >= 4) DEB_NB_ARRIVE(3, 64);
+        DEB_LANES_BEGIN          // forward recurrences from zero: x_l = b'_l/e_l + g_l x_{l-1}
+          DEB_USE(sK); DEB_USE(sSeg); DEB_USE(sLen);
+          const double kb = sK;          // backward carry of this lane's segment
+          double x = 0.0, a = 1.0;
+          if (sLen > 0) {
+            double* rp = X.rt + lane;
+            const double* ip = X.iet + lane;
+            const double* gp = X.gt + lane;
+            const double* cp = X.mct + lane;
+            double cn = (*rp + *cp * kb) * *ip, gn = *gp;
+            for (int i = 0; i < sLen - 1; ++i) {
+              const double cc = cn, gc = gn;
+              cn = (*(rp + TEAM_ROW) + *(cp + TEAM_ROW) * kb) * *(ip + TEAM_ROW); gn = *(gp + TEAM_ROW);
+              x = cc + gc * x;
+              *rp = x;
+              rp += TEAM_ROW; ip += TEAM_ROW; gp += TEAM_ROW; cp += TEAM_ROW;
+            }
+            x = cn + gn * x;
+            *rp = x;
+            a = X.gct[(sLen - 1) * TEAM_ROW + lane];
+          }
+          box.fe[lane] = x; box.fa[lane] = a;
+        DEB_LANES_END
+        if (TEAM >= 4) DEB_NB_ARRIVE(4, 64);
+      }
+      DEB_TICK(6);
+      DEB_IF_WARP(0) {
+        if (TEAM >= 4) DEB_NB_SYNC(3, 64);             // the swept tails are in
+        DEB_TICK2_START
+        DEB_LANES_BEGIN
           DEB_USE(sI2);
-          if (lane < nch) W.r()[sI2] = W.r()[sI2] - W.m()[sI2] * sT;        // l = 2 (a head row): b'_2 = b_2 - m_2 b'_3
+          if (lane < nch) W.r()[sI2] = W.r()[sI2] - W.m()[sI2] * box.t3[lane];        // l = 2 (a head row): b'_2 = b_2 - m_2 b'_3
         DEB_LANES_END
         DEB_TICK2(11);
         // head: p = D^-1 b (block inverses), then the rank-2 Woodbury correction and the a h' row
@@ -742,46 +789,26 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
           DEB_LANES_END
         }
         DEB_TICK2(13);
-        DEB_LANES_BEGIN          // forward sweep: x_l = b'_l/e_l + g_l x_{l-1}
-          DEB_USE(sT); DEB_USE(sE); DEB_USE(sA); DEB_USE(sK); DEB_USE(sSeg); DEB_USE(sLen); DEB_USE(sI2);
-          const double kb = sK;          // backward carry of this lane's segment
-          sE = 0.0; sA = 1.0; sK = 0.0;
-          if (sSeg >= 0) {
-            double x = sSeg == 0 ? W.r()[sI2] : 0.0;        // segment 0 starts from x_2, the others from zero
-            if (sLen > 0) {
-              double* rp = X.rt + lane;
-              const double* ip = X.iet + lane;
-              const double* gp = X.gt + lane;
-              const double* cp = X.mct + lane;
-              double cn = (*rp + *cp * kb) * *ip, gn = *gp;
-              for (int i = 0; i < sLen - 1; ++i) {
-                const double cc = cn, gc = gn;
-                cn = (*(rp + TEAM_ROW) + *(cp + TEAM_ROW) * kb) * *(ip + TEAM_ROW); gn = *(gp + TEAM_ROW);
-                x = cc + gc * x;
-                *rp = x;
-                rp += TEAM_ROW; ip += TEAM_ROW; gp += TEAM_ROW; cp += TEAM_ROW;
-              }
-              x = cn + gn * x;
-              *rp = x;
-              sA = X.gct[(sLen - 1) * TEAM_ROW + lane];
-            }
-            sE = x;
-            if (sSeg == 0) sA = 0.0;                                // x_2 is already inside segment 0
-          }
-          sT = sE;
+        if (TEAM >= 4) DEB_NB_SYNC(4, 64);             // the forward recurrences are in
+        // forward carry chain: the true x just below every segment (x_2 of the head for segment 0)
+        DEB_REGS(double, fT, ); DEB_REGS(double, fK, );
+        DEB_LANES_BEGIN
+          DEB_USE(fT); DEB_USE(fK); DEB_USE(sSeg); DEB_USE(sI2);
+          fK = 0.0; fT = 0.0;
+          if (sSeg == 0) { fK = W.r()[sI2]; fT = box.fe[lane] + box.fa[lane] * fK; }
         DEB_LANES_END
-        DEB_TICK2(14);
-        for (int sg = 1; sg < TEAM_NSEG; ++sg) {              // carry chain: the true x just below segment sg
+        for (int sg = 1; sg < TEAM_NSEG; ++sg) {
           DEB_LANES_BEGIN
-            DEB_USE(sT); DEB_USE(sE); DEB_USE(sA); DEB_USE(sK); DEB_USE(sSeg);
-            const double kin = DEB_SHFL(sT, (lane - nch) & 31);
-            if (sSeg == sg) { sK = kin; sT = sE + sA * kin; }
+            DEB_USE(fT); DEB_USE(fK); DEB_USE(sSeg);
+            const double kin = DEB_SHFL(fT, (lane - nch) & 31);
+            if (sSeg == sg) { fK = kin; fT = box.fe[lane] + box.fa[lane] * kin; }
           DEB_LANES_END
         }
         DEB_LANES_BEGIN
-          DEB_USE(sK); DEB_USE(sSeg);
-          if (sSeg >= 0) box.kf[lane] = sK;
+          DEB_USE(fK); DEB_USE(sSeg);
+          if (sSeg >= 0) box.kf[lane] = fK;
         DEB_LANES_END
+        DEB_TICK2(14);
       }
       DEB_TICK(7);
       DEB_T_BAR();                                     // r, kf = k_st (element 0: x0), warp 1's results posted

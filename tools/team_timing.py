@@ -22,9 +22,9 @@ lib.lib.deb_debug_team_timing(buf, 0)
 t = np.array(list(buf), dtype=float)
 steps = t[15]
 names = ["J: rows/factors (own work)", "J: wait barrier", "J: block inverses + Woodbury", "stage: own elements", "stage: wait B1", "stage: metric+head rows (+x0)",
-         "stage: wait B2", "stage: solve", "stage: wait B4", "step end: norm, controller, copy"]
+         "stage: sweeps by the last warp (as seen by warp 0)", "stage: head solve + carries (warp 0)", "stage: wait B4", "step end: norm, controller, copy"]
 print(f"kmax {kmax} a_out {aout} kernel_ms {out['kernel_ms']:.2f} steps of the largest-k mode {int(steps)} cycles/step {t[:10].sum()/steps:.0f}")
 for i, nm in enumerate(names):
     print(f"  {nm:42s} {t[i]/steps:9.0f} cycles/step  {100*t[i]/t[:10].sum():5.1f} %")
-for i, nm in zip(range(10, 15), ["solve: backward local sweep", "solve: backward carry + l=2 rows", "solve: gather + block multiply", "solve: Woodbury sums + write-back", "solve: forward local sweep"]):
+for i, nm in zip(range(11, 15), ["solve: wait for the swept tails + l=2 rows", "solve: gather + block multiply", "solve: Woodbury sums + write-back", "solve: wait for forward recurrences + carry chain"]):
     print(f"    {nm:40s} {t[i]/steps/8:9.0f} cycles/stage")
