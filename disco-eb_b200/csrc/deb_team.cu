@@ -17,7 +17,8 @@ static __device__ __noinline__ double deb_ni_pow(double x, double y) { return po
 #define DEB_COLD static __device__ __noinline__
 #include "deb_core.cuh"
 #ifdef DEB_TEAM_TIMING
-__device__ long long g_team_timing[16];
+__device__ long long g_team_timing[32];
+__device__ int g_team_skip;
 #endif
 #include "deb_team.cuh"
 
@@ -121,9 +122,10 @@ int deb_launch_team(const Problem& P, cudaStream_t st, int nsm) {
 
 #ifdef DEB_TEAM_TIMING
 // measurement build only: cycles warp 0 of the largest-k mode spent per phase (see DEB_TICK), slot 15 = steps
+extern "C" int deb_debug_team_skip(int mask) { CUDA_TRY(cudaMemcpyToSymbol(g_team_skip, &mask, sizeof(int))); return DEB_OK; }
 extern "C" int deb_debug_team_timing(long long* out16, int reset) {
-  if (out16) CUDA_TRY(cudaMemcpyFromSymbol(out16, g_team_timing, sizeof(long long) * 16));
-  if (reset) { long long z[16] = {0}; CUDA_TRY(cudaMemcpyToSymbol(g_team_timing, z, sizeof(z))); }
+  if (out16) CUDA_TRY(cudaMemcpyFromSymbol(out16, g_team_timing, sizeof(long long) * 32));
+  if (reset) { long long z[32] = {0}; CUDA_TRY(cudaMemcpyToSymbol(g_team_timing, z, sizeof(z))); }
   return DEB_OK;
 }
 #endif

@@ -143,19 +143,41 @@ DEB_DEV void init_team_const(const Problem& P, const CtaConst& C, int* eslot, in
 // (own element j of the thread: orp[j] points at its right-hand side / solution slot, ogp[j] at its cumulative forward
 //  multiplier -- a zero for head elements --, osl[j] is its carry slot)
 #define DEB_KV(e) ((e) == 0 ? x0 : *orp[j] + *ogp[j] * box.kf[osl[j]])
+// measurement builds only (-DDEB_TEAM_TIMING): g_team_skip knocks phases out (results are then wrong on purpose) so
+// that the drop in cycles per step says what a phase contributes to the critical path (tools/team_timing.py)
+#if defined(DEB_TEAM_TIMING) && !defined(DEB_CPU_EMU)
+#define DEB_KEEP(bit) (!(g_team_skip & (bit)))
+#else
+#define DEB_KEEP(bit) true
+#endif
 // optional phase timing of warp 0 (build with -DDEB_TEAM_TIMING; tools/team_timing.py reads the counters)
 #if defined(DEB_TEAM_TIMING) && !defined(DEB_CPU_EMU)
 #define DEB_TICK(slot) do { const long long now_ = clock64(); if (tid == 0 && kidx == P.nk - 1) atomicAdd((unsigned long long*)&g_team_timing[slot], (unsigned long long)(now_ - tick_)); tick_ = now_; } while (0)
-#define DEB_TICK_INIT long long tick_ = clock64(); long long tick2_ = tick_;
+#define DEB_TICK_INIT long long tick_ = clock64(); long long tick2_ = tick_; long long tick3_ = tick_;
+#define DEB_TICK3(slot) do { const long long now_ = clock64(); if (tid == 0 && kidx == P.nk - 1) atomicAdd((unsigned long long*)&g_team_timing[slot], (unsigned long long)(now_ - tick3_)); tick3_ = now_; } while (0)
+#define DEB_TICK3_START tick3_ = clock64();
 #define DEB_TICK2(slot) do { const long long now_ = clock64(); if (tid == 0 && kidx == P.nk - 1) atomicAdd((unsigned long long*)&g_team_timing[slot], (unsigned long long)(now_ - tick2_)); tick2_ = now_; } while (0)
 #define DEB_TICK2_START tick2_ = clock64();
 #else
 #define DEB_TICK(slot)
 #define DEB_TICK2(slot)
 #define DEB_TICK2_START
+#define DEB_TICK3(slot)
+#define DEB_TICK3_START
 #define DEB_TICK_INIT
 #endif
 #define DEB_FOR_TEAM(body) _Pragma("unroll") for (int j = 0; j < NE; ++j) { const int e = tid + NT * j; if (e < n) { body } }
+
+// Rodas5 coefficients of the stage combinations in constant memory: a 64-bit immediate costs two UMOVs in front of
+// every DFMA (60 of the 131 instructions of one stage's combination code, each a dependency stall); operands from
+// the constant bank cost nothing
+enum { TRD_A21, TRD_A31, TRD_A32, TRD_A41, TRD_A42, TRD_A43, TRD_A51, TRD_A52, TRD_A53, TRD_A54, TRD_A61, TRD_A62, TRD_A63, TRD_A64, TRD_A65, TRD_C21, TRD_C31, TRD_C32, TRD_C41, TRD_C42, TRD_C43, TRD_C51, TRD_C52, TRD_C53, TRD_C54, TRD_C61, TRD_C62, TRD_C63, TRD_C64, TRD_C65, TRD_C71, TRD_C72, TRD_C73, TRD_C74, TRD_C75, TRD_C76, TRD_C81, TRD_C82, TRD_C83, TRD_C84, TRD_C85, TRD_C86, TRD_C87, TRD_N };
+#ifdef DEB_CPU_EMU
+static const double g_trd[TRD_N] = { RD_A21, RD_A31, RD_A32, RD_A41, RD_A42, RD_A43, RD_A51, RD_A52, RD_A53, RD_A54, RD_A61, RD_A62, RD_A63, RD_A64, RD_A65, RD_C21, RD_C31, RD_C32, RD_C41, RD_C42, RD_C43, RD_C51, RD_C52, RD_C53, RD_C54, RD_C61, RD_C62, RD_C63, RD_C64, RD_C65, RD_C71, RD_C72, RD_C73, RD_C74, RD_C75, RD_C76, RD_C81, RD_C82, RD_C83, RD_C84, RD_C85, RD_C86, RD_C87 };
+#else
+__constant__ double g_trd[TRD_N] = { RD_A21, RD_A31, RD_A32, RD_A41, RD_A42, RD_A43, RD_A51, RD_A52, RD_A53, RD_A54, RD_A61, RD_A62, RD_A63, RD_A64, RD_A65, RD_C21, RD_C31, RD_C32, RD_C41, RD_C42, RD_C43, RD_C51, RD_C52, RD_C53, RD_C54, RD_C61, RD_C62, RD_C63, RD_C64, RD_C65, RD_C71, RD_C72, RD_C73, RD_C74, RD_C75, RD_C76, RD_C81, RD_C82, RD_C83, RD_C84, RD_C85, RD_C86, RD_C87 };
+#endif
+#define TRD(name) g_trd[TRD_##name]
 
 // the output conversion runs once per mode and output time: kept out of line, away from the step loop
 #ifdef DEB_CPU_EMU
@@ -387,7 +409,7 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
     DEB_IF_WARP(TEAM > 1 ? 1 : 0) {
       // ---- tails: pivot-free backward elimination l = L .. 3 (one lane per chain), factors into the transposed arrays ----
       DEB_LANES_BEGIN
-        if (lane < nch) {
+        if (lane < nch && DEB_KEEP(128)) {
           const int L = C.ch_lmax[lane], len = (L - 2 + TEAM_NSEG - 1) / TEAM_NSEG;
           const double kc = J.kc[lane], kp = J.kap[lane];
           double e = idg + kp + (double)(L + 1) * invt0;
@@ -476,7 +498,7 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
         }
       DEB_LANES_END
 #pragma unroll 1
-      for (int bt = 0; bt < 8; ++bt) {
+      for (int bt = 0; bt < (DEB_KEEP(64) ? 8 : 0); ++bt) {
         DEB_LANES_BEGIN
           DEB_USE(pcol); DEB_USE(pkey);
           const int lo = C.blo[lane], hi = C.bhi[lane];
@@ -566,6 +588,7 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
     double errnorm2 = 0.0;
 #pragma unroll 1
     for (int st = 1; st <= 8; ++st) {
+      DEB_TICK3_START
       if (st > 1) {
         TeamBg& cur = box.bg[st & 1];                  // posted by warp 1 during stage st-1
         const double ts = st == 2 ? t + RD_CT2 * dt : st == 3 ? t + RD_CT3 * dt : st == 4 ? t + RD_CT4 * dt
@@ -575,28 +598,29 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
 #define DEB_ROW0 if (e == 0) { W.r()[0] += cur.bgs[0] * cur.a_req; W.u()[0] = cur.a_req; }
         DEB_T_BEGIN
           DEB_TUSE(ks); DEB_TUSE(orp); DEB_TUSE(ogp); DEB_TUSE(osl);
+          if (DEB_KEEP(1))
           switch (st) {
             case 2: DEB_FOR_TEAM(ks[0][j] = DEB_KV(e);
-                                 W.u()[e] = W.y()[e] + RD_A21 * ks[0][j];
-                                 *orp[j] = invdt * (RD_C21 * ks[0][j]); DEB_ROW0) break;
+                                 W.u()[e] = W.y()[e] + TRD(A21) * ks[0][j];
+                                 *orp[j] = invdt * (TRD(C21) * ks[0][j]); DEB_ROW0) break;
             case 3: DEB_FOR_TEAM(ks[1][j] = DEB_KV(e);
-                                 W.u()[e] = W.y()[e] + RD_A31 * ks[0][j] + RD_A32 * ks[1][j];
-                                 *orp[j] = invdt * (RD_C31 * ks[0][j] + RD_C32 * ks[1][j]); DEB_ROW0) break;
+                                 W.u()[e] = W.y()[e] + TRD(A31) * ks[0][j] + TRD(A32) * ks[1][j];
+                                 *orp[j] = invdt * (TRD(C31) * ks[0][j] + TRD(C32) * ks[1][j]); DEB_ROW0) break;
             case 4: DEB_FOR_TEAM(ks[2][j] = DEB_KV(e);
-                                 W.u()[e] = W.y()[e] + RD_A41 * ks[0][j] + RD_A42 * ks[1][j] + RD_A43 * ks[2][j];
-                                 *orp[j] = invdt * (RD_C41 * ks[0][j] + RD_C42 * ks[1][j] + RD_C43 * ks[2][j]); DEB_ROW0) break;
+                                 W.u()[e] = W.y()[e] + TRD(A41) * ks[0][j] + TRD(A42) * ks[1][j] + TRD(A43) * ks[2][j];
+                                 *orp[j] = invdt * (TRD(C41) * ks[0][j] + TRD(C42) * ks[1][j] + TRD(C43) * ks[2][j]); DEB_ROW0) break;
             case 5: DEB_FOR_TEAM(ks[3][j] = DEB_KV(e);
-                                 W.u()[e] = W.y()[e] + RD_A51 * ks[0][j] + RD_A52 * ks[1][j] + RD_A53 * ks[2][j] + RD_A54 * ks[3][j];
-                                 *orp[j] = invdt * (RD_C51 * ks[0][j] + RD_C52 * ks[1][j] + RD_C53 * ks[2][j] + RD_C54 * ks[3][j]); DEB_ROW0) break;
+                                 W.u()[e] = W.y()[e] + TRD(A51) * ks[0][j] + TRD(A52) * ks[1][j] + TRD(A53) * ks[2][j] + TRD(A54) * ks[3][j];
+                                 *orp[j] = invdt * (TRD(C51) * ks[0][j] + TRD(C52) * ks[1][j] + TRD(C53) * ks[2][j] + TRD(C54) * ks[3][j]); DEB_ROW0) break;
             case 6: DEB_FOR_TEAM(ks[4][j] = DEB_KV(e);
-                                 W.u()[e] = W.y()[e] + RD_A61 * ks[0][j] + RD_A62 * ks[1][j] + RD_A63 * ks[2][j] + RD_A64 * ks[3][j] + RD_A65 * ks[4][j];
-                                 *orp[j] = invdt * (RD_C61 * ks[0][j] + RD_C62 * ks[1][j] + RD_C63 * ks[2][j] + RD_C64 * ks[3][j] + RD_C65 * ks[4][j]); DEB_ROW0) break;
+                                 W.u()[e] = W.y()[e] + TRD(A61) * ks[0][j] + TRD(A62) * ks[1][j] + TRD(A63) * ks[2][j] + TRD(A64) * ks[3][j] + TRD(A65) * ks[4][j];
+                                 *orp[j] = invdt * (TRD(C61) * ks[0][j] + TRD(C62) * ks[1][j] + TRD(C63) * ks[2][j] + TRD(C64) * ks[3][j] + TRD(C65) * ks[4][j]); DEB_ROW0) break;
             case 7: DEB_FOR_TEAM(ks[5][j] = DEB_KV(e);
                                  W.u()[e] = W.u()[e] + ks[5][j];
-                                 *orp[j] = invdt * (RD_C71 * ks[0][j] + RD_C72 * ks[1][j] + RD_C73 * ks[2][j] + RD_C74 * ks[3][j] + RD_C75 * ks[4][j] + RD_C76 * ks[5][j]); DEB_ROW0) break;
+                                 *orp[j] = invdt * (TRD(C71) * ks[0][j] + TRD(C72) * ks[1][j] + TRD(C73) * ks[2][j] + TRD(C74) * ks[3][j] + TRD(C75) * ks[4][j] + TRD(C76) * ks[5][j]); DEB_ROW0) break;
             default: DEB_FOR_TEAM(ks[6][j] = DEB_KV(e);
                                  W.u()[e] = W.u()[e] + ks[6][j];
-                                 *orp[j] = invdt * (RD_C81 * ks[0][j] + RD_C82 * ks[1][j] + RD_C83 * ks[2][j] + RD_C84 * ks[3][j] + RD_C85 * ks[4][j] + RD_C86 * ks[5][j] + RD_C87 * ks[6][j]); DEB_ROW0) break;
+                                 *orp[j] = invdt * (TRD(C81) * ks[0][j] + TRD(C82) * ks[1][j] + TRD(C83) * ks[2][j] + TRD(C84) * ks[3][j] + TRD(C85) * ks[4][j] + TRD(C86) * ks[5][j] + TRD(C87) * ks[6][j]); DEB_ROW0) break;
           }
         DEB_T_END
 #undef DEB_ROW0
@@ -617,9 +641,10 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
             if (lane >= 3 && lane < nch) nu_moments_lane(nb, cur.vv, W.u(), P.iq0, lane - 3, W.nur(), W.nup());
           DEB_LANES_END
           Metric<double> mt;
-          compute_metric<double>(P, c, nb, b, W.u(), k, W.nur(), W.nup(), mt);
+          mt.hp = mt.ep = mt.al = mt.f1 = 0.0;
+          if (DEB_KEEP(8)) compute_metric<double>(P, c, nb, b, W.u(), k, W.nur(), W.nup(), mt);
           DEB_LANES_BEGIN
-            if (lane < nh) {
+            if (lane < nh && DEB_KEEP(8)) {
               const int e = C.hidx[lane];
               const double rv = W.r()[e] + head_row<double>(C, cur.sl, W.u(), lane, mt);
               W.r()[e] = rv + W.ja()[e] * x0;
@@ -628,7 +653,7 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
         }
         constexpr int TS0 = TEAM >= 3 ? 64 : (TEAM == 2 ? 32 : 0), NTS = NT - TS0;
         DEB_T_BEGIN
-          if (tid >= TS0)
+          if (tid >= TS0 && DEB_KEEP(2))
           for (int tt = tid - TS0; tt < C.ntail; tt += 2 * NTS) {
             int e0, e1 = 0; double tr0, tr1 = 0.0, f1 = 0.0, r1 = 0.0, y1 = 0.0;
             const bool two = tt + NTS < C.ntail;
@@ -663,12 +688,12 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
               nxt.a_req = an;
             }
           DEB_LANES_END
-          team_helper_compute(P, C, c, box, nxt, hint2 DEB_LANE_ARG);
+          if (DEB_KEEP(4)) team_helper_compute(P, C, c, box, nxt, hint2 DEB_LANE_ARG);
         }
       } else {
         // stage 8: the candidate's scale factor y1_0 = u_0 + x0 is known -> background of the next step's Jacobian
         DEB_IF_WARP(TEAM > 1 ? 1 : 0) {
-          team_jac_compute(P, C, c, box, box.jac[jcur ^ 1], W.u()[0] + x0, hint2 DEB_LANE_ARG);
+          if (DEB_KEEP(4)) team_jac_compute(P, C, c, box, box.jac[jcur ^ 1], W.u()[0] + x0, hint2 DEB_LANE_ARG);
         }
       }
       DEB_TICK(5);
@@ -693,7 +718,7 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
         DEB_LANES_BEGIN          // backward sweep: b'_l = b_l - m_l b'_{l+1}
           DEB_USE(sT); DEB_USE(sE); DEB_USE(sA); DEB_USE(sK); DEB_USE(sSeg); DEB_USE(sLen);
           sE = 0.0; sA = 1.0; sK = 0.0;
-          if (sLen > 0) {
+          if (sLen > 0 && DEB_KEEP(16)) {
             double* rp = X.rt + ((sLen - 1) * TEAM_ROW + lane);
             const double* mp = X.mt + ((sLen - 1) * TEAM_ROW + lane);
             double p = 0.0;
@@ -727,7 +752,7 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
           DEB_USE(sK); DEB_USE(sSeg); DEB_USE(sLen);
           const double kb = sK;          // backward carry of this lane's segment
           double x = 0.0, a = 1.0;
-          if (sLen > 0) {
+          if (sLen > 0 && DEB_KEEP(16)) {
             double* rp = X.rt + lane;
             const double* ip = X.iet + lane;
             const double* gp = X.gt + lane;
@@ -758,6 +783,7 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
         DEB_LANES_END
         DEB_TICK2(11);
         // head: p = D^-1 b (block inverses), then the rank-2 Woodbury correction and the a h' row
+        if (DEB_KEEP(32)) {
         DEB_LANES_BEGIN
           W.xb()[lane] = lane < nhb ? W.r()[C.hidx[W.perm()[lane]]] : 0.0;
           if (lane < 8) W.xb()[NHMAX + lane] = 0.0;
@@ -788,6 +814,7 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
             else if (lane == nhb) W.r()[1] = (W.r()[1] + ta + jq_h * sh + jq_e * se) * gdt;     // a h' (state 1): closed row
           DEB_LANES_END
         }
+        }
         DEB_TICK2(13);
         if (TEAM >= 4) DEB_NB_SYNC(4, 64);             // the forward recurrences are in
         // forward carry chain: the true x just below every segment (x_2 of the head for segment 0)
@@ -813,6 +840,7 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
       DEB_TICK(7);
       DEB_T_BAR();                                     // r, kf = k_st (element 0: x0), warp 1's results posted
       DEB_TICK(8);
+      DEB_TICK3(16 + st);
     }
 
     // y1 = u + k8 -> u ; err = k8 -> r

@@ -15,7 +15,11 @@ ks = np.geomspace(1e-4, kmax, nk)
 dims = _cabi.make_dims(ncosmo=1, nk=nk, nout=1, lmaxg=31, lmaxgp=31, lmaxr=31, lmaxnu=31, nqmax=5, nth=tab.nth, nnu=tab.nnu, max_steps=2048, power_idx=4)
 ctrl = _cabi.make_ctrl(rtol=1e-4, atol=1e-4)
 os.environ["DEB_VARIANT"] = "team"
-buf = (ctypes.c_longlong * 16)()
+buf = (ctypes.c_longlong * 32)()
+skip = int(os.environ.get("DEB_TEAM_SKIP", "0"))
+lib.lib.deb_debug_team_skip(skip)       # knock phases out (wrong results on purpose): what does a phase cost the step?
+if skip:
+    dims.max_steps = 300
 lib.lib.deb_debug_team_timing(buf, 1)
 out = lib.evolve_host(dims, ctrl, tab.scalars[None], tab.tables[None], ks, np.array([aout]), want_pk=True)
 lib.lib.deb_debug_team_timing(buf, 0)
@@ -23,8 +27,9 @@ t = np.array(list(buf), dtype=float)
 steps = t[15]
 names = ["J: rows/factors (own work)", "J: wait barrier", "J: block inverses + Woodbury", "stage: own elements", "stage: wait B1", "stage: metric+head rows (+x0)",
          "stage: sweeps by the last warp (as seen by warp 0)", "stage: head solve + carries (warp 0)", "stage: wait B4", "step end: norm, controller, copy"]
-print(f"kmax {kmax} a_out {aout} kernel_ms {out['kernel_ms']:.2f} steps of the largest-k mode {int(steps)} cycles/step {t[:10].sum()/steps:.0f}")
+print(f"skip mask {skip} kmax {kmax} a_out {aout} kernel_ms {out['kernel_ms']:.2f} steps of the largest-k mode {int(steps)} cycles/step {t[:10].sum()/steps:.0f}")
 for i, nm in enumerate(names):
     print(f"  {nm:42s} {t[i]/steps:9.0f} cycles/step  {100*t[i]/t[:10].sum():5.1f} %")
 for i, nm in zip(range(11, 15), ["solve: wait for the swept tails + l=2 rows", "solve: gather + block multiply", "solve: Woodbury sums + write-back", "solve: wait for forward recurrences + carry chain"]):
     print(f"    {nm:40s} {t[i]/steps/8:9.0f} cycles/stage")
+print("  whole stage by stage number (cycles per step): " + "  ".join(f"st{st}: {t[16 + st] / steps:.0f}" for st in range(1, 9)))
