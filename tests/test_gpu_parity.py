@@ -137,6 +137,31 @@ def test_full_size_properties_config2(gpu_lib, emu_lib, tables):
     assert rel.max() < 50 * 1e-4
 
 
+def test_full_size_properties_config3(gpu_lib, tables, monkeypatch):
+    """BASELINE config 3 at full size (w0wa + massive nu, n=265, 4096 modes): every mode completes, and a mode's result
+    does not depend on what else is in the launch -- every 8th mode re-run as a 512-mode launch of the same (pinned)
+    kernel gives the same bits, step counts included; the automatic choice (team kernel for the small launch) agrees to
+    the free-running tolerance."""
+    from discoeb_b200 import _cabi
+    tab = tables["w0wa"]
+    nk = 4096
+    ks = np.geomspace(1e-4, 10.0, nk)
+    mk = lambda n_: _cabi.make_dims(ncosmo=1, nk=n_, nout=1, lmaxg=31, lmaxgp=31, lmaxr=31, lmaxnu=31, nqmax=5, nth=tab.nth,
+                                    nnu=tab.nnu, max_steps=2048, power_idx=4)
+    ctrl = _cabi.make_ctrl(rtol=1e-4, atol=1e-4)
+    run = lambda k: gpu_lib.evolve_host(mk(len(k)), ctrl, tab.scalars[None], tab.tables[None], k, np.array([1.0]), want_pk=True)
+    monkeypatch.setenv("DEB_VARIANT", "warp")
+    big = run(ks)
+    assert np.all(big["status"] == 0) and np.all(np.isfinite(big["pk"])) and np.all(big["pk"] > 0)
+    sub = run(ks[::8])
+    assert np.array_equal(sub["nsteps"][0], big["nsteps"][0][::8])
+    assert np.array_equal(sub["y"][0], big["y"][0][::8]) and np.array_equal(sub["pk"][0], big["pk"][0][::8])
+    monkeypatch.delenv("DEB_VARIANT")
+    auto = run(ks[::8])
+    assert np.all(auto["status"] == 0)
+    assert np.abs(auto["y"][0, :, 0, 4] / big["y"][0, ::8, 0, 4] - 1).max() < 50 * 1e-4
+
+
 def test_tight_tolerance_meets_1e5(gpu_lib, tables):
     """At rtol=atol=1e-7 the free-running solve agrees with the oracle within the 1e-5 of
     north_star on the matter transfer functions, whatever the step sequences do."""
