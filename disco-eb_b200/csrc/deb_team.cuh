@@ -271,16 +271,16 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
   DEB_REGS(double, s1, ); DEB_REGS(double, s2, ); DEB_REGS(double, s3, ); DEB_REGS(double, s4, );
   DEB_TREGS(int, nanflag, );
   // lane constants of the segmented sweeps: lane = segment * nch + chain sweeps rows [sLo, sHi) of its chain
-  DEB_REGS(int, sSeg, ); DEB_REGS(int, sLen, ); DEB_REGS(int, sI2, );
+  DEB_REGS(int, sSeg, ); DEB_REGS(int, sLen, ); DEB_REGS(int, sI2, ); DEB_REGS(int, sCh, ); DEB_REGS(int, sLo, );
   DEB_LANES_BEGIN
-    DEB_USE(sSeg); DEB_USE(sLen); DEB_USE(sI2);
-    sSeg = -1; sLen = 0; sI2 = 0;
+    DEB_USE(sSeg); DEB_USE(sLen); DEB_USE(sI2); DEB_USE(sCh); DEB_USE(sLo);
+    sSeg = -1; sLen = 0; sI2 = 0; sCh = 0; sLo = 3;
     if (lane < TEAM_NSEG * nch) {
       sSeg = lane / nch;
       const int ch = lane - sSeg * nch;
       int lo, hi;
       team_segment(C, ch, sSeg, &lo, &hi);
-      sLen = hi - lo;
+      sLen = hi - lo; sCh = ch; sLo = lo;
       sI2 = C.ch_base[ch] + 2 * C.ch_stride[ch];      // the chain's l = 2 element (a head row)
     }
   DEB_LANES_END
@@ -333,7 +333,7 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
   }
   DEB_T_BAR();
 
-  double inv_prev = 1.0, inv_pprev = 1.0;
+  double inv_prev = 1.0, inv_pprev = 1.0, linv_prev = 0.0;
   int nsteps = 0, nacc = 0, save_idx = 0, status = 0;
   if (!(t == t) || !(tnext == tnext) || !(t1 == t1)) status = 2;
   Hints hint2; hint2.th = -1; hint2.nu = -1;       // warp 1 (all background evaluations)
@@ -407,47 +407,68 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
       DEB_LANES_END
     }
     DEB_IF_WARP(TEAM > 1 ? 1 : 0) {
-      // ---- tails: pivot-free backward elimination l = L .. 3 (one lane per chain), factors into the transposed arrays ----
+      // ---- tails: pivot-free backward elimination l = L .. 3, factors into the transposed arrays.  Only the pivot
+      //      recurrence e_l = d_l + w_l / e_{l+1}, w_l = W_{l,l+1} W_{l+1,l}, is sequential (one lane per chain: a DFMA and
+      //      a reciprocal per row); the products w_l before it and the multipliers m_l, g_l with their cumulative
+      //      products after it are made by one lane per (segment, chain).
+      DEB_LANES_BEGIN
+        DEB_USE(sSeg); DEB_USE(sLen); DEB_USE(sCh); DEB_USE(sLo);
+        if (sSeg >= 0 && DEB_KEEP(128)) {
+          const int L = C.ch_lmax[sCh];
+          const double kc = J.kc[sCh];
+#pragma unroll 1
+          for (int i = 0; i < sLen; ++i) {
+            const int l = sLo + i;
+            const double clx = (l + 1 >= L) ? 1.0 : C.cl[l + 1];          // W_{l+1,l} = -kc cl_{l+1} (truncation row: -kc)
+            X.mct[i * TEAM_ROW + lane] = l < L ? (kc * C.ch[l]) * (kc * clx) : 0.0;      // (scratch: overwritten below)
+          }
+        }
+      DEB_LANES_END
       DEB_LANES_BEGIN
         if (lane < nch && DEB_KEEP(128)) {
           const int L = C.ch_lmax[lane], len = (L - 2 + TEAM_NSEG - 1) / TEAM_NSEG;
-          const double kc = J.kc[lane], kp = J.kap[lane];
-          double e = idg + kp + (double)(L + 1) * invt0;
-          double ie = DEB_RCP(e);
+          const double kc = J.kc[lane], base = idg + J.kap[lane];
+          double ie = DEB_RCP(base + (double)(L + 1) * invt0);
           int sg = (L - 3) / len, i = L - 3 - sg * len;            // position of row L
           int pos = i * TEAM_ROW + sg * nch + lane;
           X.iet[pos] = ie;
-          X.gt[pos] = kc * ie;
-          X.mt[pos] = 0.0;                             // nothing above the truncation row
-          double lower_next = -kc;
 #pragma unroll 1
           for (int l = L - 1; l >= 3; --l) {
             if (--i < 0) { i = len - 1; --sg; }
             pos = i * TEAM_ROW + sg * nch + lane;
-            const double mm = (kc * C.ch[l]) * ie;     // W_{l,l+1} / e_{l+1}
-            X.mt[pos] = mm;
-            e = idg + kp - mm * lower_next;
-            ie = DEB_RCP(e);
+            ie = DEB_RCP(base + X.mct[pos] * ie);
             X.iet[pos] = ie;
-            lower_next = -kc * C.cl[l];
-            X.gt[pos] = -lower_next * ie;
           }
           const int i2 = C.ch_base[lane] + 2 * C.ch_stride[lane];
           const double mm = (kc * C.ch[2]) * ie;
           W.m()[i2] = mm;
-          W.ie()[i2] = -mm * lower_next;               // Schur increment for the head diagonal (l = 2 row)
+          W.ie()[i2] = mm * (kc * (3 >= L ? 1.0 : C.cl[3]));     // Schur increment for the head diagonal (l = 2 row)
         }
       DEB_LANES_END
-      // cumulative multipliers inside every segment of the sweeps (one lane per (segment, chain))
       DEB_LANES_BEGIN
-        DEB_USE(sSeg); DEB_USE(sLen);
-        if (sSeg >= 0) {
+        DEB_USE(sSeg); DEB_USE(sLen); DEB_USE(sCh); DEB_USE(sLo);
+        if (sSeg >= 0 && DEB_KEEP(128)) {
+          const int L = C.ch_lmax[sCh];
+          const double kc = J.kc[sCh];
           double acc = 1.0;
 #pragma unroll 1
-          for (int i = sLen - 1; i >= 0; --i) { acc = -X.mt[i * TEAM_ROW + lane] * acc; X.mct[i * TEAM_ROW + lane] = acc; }
+          for (int i = sLen - 1; i >= 0; --i) {          // m_l = W_{l,l+1} / e_{l+1} and its products from the top of the segment
+            const int l = sLo + i;
+            const double ie_up = l >= L ? 0.0 : (i + 1 < sLen ? X.iet[(i + 1) * TEAM_ROW + lane] : X.iet[lane + nch]);
+            const double mm = l >= L ? 0.0 : (kc * C.ch[l]) * ie_up;
+            X.mt[i * TEAM_ROW + lane] = mm;
+            acc = -mm * acc;
+            X.mct[i * TEAM_ROW + lane] = acc;
+          }
           acc = 1.0;
 #pragma unroll 1
-          for (int i = 0; i < sLen; ++i) { acc = X.gt[i * TEAM_ROW + lane] * acc; X.gct[i * TEAM_ROW + lane] = acc; }
+          for (int i = 0; i < sLen; ++i) {               // g_l = -W_{l,l-1} / e_l and its products from the bottom
+            const int l = sLo + i;
+            const double gg = (kc * (l >= L ? 1.0 : C.cl[l])) * X.iet[i * TEAM_ROW + lane];
+            X.gt[i * TEAM_ROW + lane] = gg;
+            acc = gg * acc;
+            X.gct[i * TEAM_ROW + lane] = acc;
+          }
         }
       DEB_LANES_END
     }
@@ -863,23 +884,32 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
     // ================= error norm, PID controller (diffrax semantics) =================
     {
       const double ik2 = DEB_RCP(k2);
-      // components 0, 2, 3, 5, 6, 7 with weights 1, k^2, 1, 1, 1/k^2, 1 (perturbations.py:701-724), one copy of the code
-#pragma unroll 1
-      for (int q = 0; q < 6; ++q) {
-        const int e = q == 0 ? 0 : (q < 3 ? q + 1 : q + 2);
-        const double w = q == 1 ? k2 : (q == 4 ? ik2 : 1.0);
-        double y0v = W.y()[e], y1v = anynan ? y0v : W.u()[e], ev = W.r()[e];
-        if (ev != ev) ev = INFINITY;
-        const double sc = ev / (P.atol + fmax(fabs(y0v), fabs(y1v)) * P.rtol) * w;
-        errnorm2 += sc * sc;
-      }
+      // components 0, 2, 3, 5, 6, 7 with weights 1, k^2, 1, 1, 1/k^2, 1 (perturbations.py:701-724): one lane each (every
+      // warp of the team does the same), summed in the reference's order so that all threads hold the same bits
+      DEB_REGS(double, esq, );
+      DEB_LANES_BEGIN
+        DEB_USE(esq);
+        esq = 0.0;
+        if (lane < 6) {
+          const int q = lane, e = q == 0 ? 0 : (q < 3 ? q + 1 : q + 2);
+          const double w = q == 1 ? k2 : (q == 4 ? ik2 : 1.0);
+          double y0v = W.y()[e], y1v = anynan ? y0v : W.u()[e], ev = W.r()[e];
+          if (ev != ev) ev = INFINITY;
+          const double sc = ev / (P.atol + fmax(fabs(y0v), fabs(y1v)) * P.rtol) * w;
+          esq = sc * sc;
+        }
+      DEB_LANES_END
+#pragma unroll
+      for (int q = 0; q < 6; ++q) errnorm2 += DEB_SHFL(esq, q);
     }
     DEB_T_BAR();          // y, u, r are rewritten below (output sampling, accepted state)
     const double E = sqrt(errnorm2 / 6.0);
     const bool keep = (P.mode == 3) ? (DEB_LDG(P.rp_keep + (size_t)mode * P.rp_stride + nsteps) != 0) : (E < 1.0);
     double inv = 1.0 / E;
-    double f1 = P.c1 != 0.0 ? ((inv > 0.0 && !isinf(inv)) ? DEB_EXP(P.c1 * DEB_LOG(inv)) : DEB_POW(inv, P.c1)) : 1.0;
-    double f2 = P.c2 != 0.0 ? DEB_EXP(P.c2 * DEB_LOG(inv_prev)) : 1.0;
+    const bool inv_regular = inv > 0.0 && !isinf(inv);
+    const double linv = inv_regular ? DEB_LOG(inv) : 0.0;        // (inv = 0 or inf is reset to 1 below: log = 0)
+    double f1 = P.c1 != 0.0 ? (inv_regular ? DEB_EXP(P.c1 * linv) : DEB_POW(inv, P.c1)) : 1.0;
+    double f2 = P.c2 != 0.0 ? DEB_EXP(P.c2 * linv_prev) : 1.0;        // linv_prev = log(inv_prev), kept from the step that set it
     double f3 = P.c3 != 0.0 ? DEB_EXP(P.c3 * DEB_LOG(inv_pprev)) : 1.0;
     double fac = fmin(fmax(P.safety * f1 * f2 * f3, keep ? 1.0 : P.factormin), P.factormax);
     if (!(fac == fac)) fac = NAN;
@@ -921,6 +951,7 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
         DEB_FOR_TEAM(W.y()[e] = W.u()[e];)
       DEB_T_END
       inv_pprev = inv_prev; inv_prev = inv;
+      linv_prev = linv;
       t = fmin(tnext, t1);
       jcur ^= 1;                 // the background posted during stage 8 is the accepted state's
     }
