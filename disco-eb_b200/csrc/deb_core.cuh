@@ -276,6 +276,9 @@ struct Problem {
   const double* d_kmodes;                        // tangent of the wavenumbers [ntan, nk] / [ntan, ncosmo, nk], or NULL (zero)
   const double* rp_dtnext;                       // replay: tangent of the prescribed step ends [ntan, ncosmo*nk, rp_stride]
   const double* dbg_dt0; const double* dbg_dt1; const double* dbg_dy0; double* dbg_dy1;      // single-step mode
+  // cost-ordered work list left in the caller's workspace by the previous launch of the same shape (team kernel):
+  // header {magic, nmodes, shape hash, ...} + mode ids by descending step count; NULL when the workspace is too small
+  int* order_hdr; int shape_hash;
 };
 
 // momentum bins (background.py:27-38); weights already divided by 7 pi^4/120

@@ -307,7 +307,14 @@ extern "C" {
 
 int32_t deb_nvar(const deb_dims* d) { return d ? deb_nvar_impl(d) : 0; }
 size_t deb_table_len(const deb_dims* d) { return d ? 3 * (size_t)(5 * d->nth + 2 * d->nnu) : 0; }
-size_t deb_workspace_bytes(const deb_dims* d) { return 256 + 8 * (size_t)(d ? d->ncosmo : 0); }
+// [0,256) work-queue counter | [256, 256 + 8 ncosmo) start-time roots | 16-aligned: order header (8 ints) + mode ids.
+// The first two parts are required; the order list is used when the buffer is large enough for it (what this returns).
+static size_t ws_min_bytes(const deb_dims* d) { return 256 + 8 * (size_t)d->ncosmo; }
+static size_t ws_order_offset(const deb_dims* d) { return (ws_min_bytes(d) + 15) & ~(size_t)15; }
+size_t deb_workspace_bytes(const deb_dims* d) {
+  if (!d) return 0;
+  return ws_order_offset(d) + 32 + 4 * (size_t)d->ncosmo * (size_t)d->nk;
+}
 const char* deb_strerror(int code) { return deb_strerror_impl(code); }
 int32_t deb_abi_version(void) { return DEB_ABI_VERSION; }
 int32_t deb_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
@@ -330,7 +337,9 @@ int deb_evolve_tangent_f64(const deb_dims* dims, const deb_ctrl* ctrl, const dou
   int rc = fill_problem(dims, ctrl, &P);
   if (rc) return rc;
   if (!scalars || !tables || !kmodes || !aexp_out || !y_out || !tau_out || !status || !nsteps || !workspace) return DEB_E_ARG;
-  if (workspace_bytes < deb_workspace_bytes(dims)) return DEB_E_WORKSPACE;
+  if (workspace_bytes < ws_min_bytes(dims)) return DEB_E_WORKSPACE;
+  P.order_hdr = workspace_bytes >= deb_workspace_bytes(dims) ? (int*)((char*)workspace + ws_order_offset(dims)) : nullptr;
+  P.shape_hash = (int)(((unsigned)P.n * 2654435761u) ^ ((unsigned)dims->nk * 40503u) ^ ((unsigned)dims->ncosmo * 69069u) ^ (unsigned)dims->nout);
   if (dims->power_idx >= 0 && !pk_out) return DEB_E_ARG;
   if (dims->ntan > 0 && (!d_scalars || !d_tables || !dy_out || !dtau_out)) return DEB_E_ARG;
   if (dims->ntan > 0 && dims->power_idx >= 0 && !dpk_out) return DEB_E_ARG;

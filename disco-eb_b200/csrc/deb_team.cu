@@ -19,10 +19,13 @@ static __device__ __noinline__ double deb_ni_pow(double x, double y) { return po
 #ifdef DEB_TEAM_TIMING
 __device__ long long g_team_timing[32];
 __device__ int g_team_skip;
+__device__ long long g_mode_log[4096][4];      // per mode: start ns, end ns, SM id, CTA slot on the SM (measurement builds)
 #endif
 #include "deb_team.cuh"
 
 using namespace deb;
+
+#define DEB_ORDER_MAGIC 0x0EB0DE55
 
 #define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
   fprintf(stderr, "[discoeb_b200] CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return DEB_E_CUDA; } } while (0)
@@ -72,17 +75,70 @@ __global__ void __launch_bounds__(32 * TEAM, MINB) k_evolve_team(const __grid_co
   __syncthreads();
   const int ltid = ((((tid >> 5) + TEAM - (int)s_tk[1]) % TEAM) << 5) | (tid & 31);
   const int total = P.ncosmo * P.nk;
+  // Work list.  Default: largest k first, cosmologies interleaved.  When the previous launch of this shape left a
+  // cost-ordered list in the workspace (k_learn_order below), positions follow descending step count, and the FIRST
+  // position of a CTA is static: the hardware places CTAs 2i and 2i+1 on one SM, so even CTAs take the G/2 longest
+  // modes and odd CTAs the next G/2 -- every SM starts with one long mode instead of two neighbours in k that stay
+  // paired (and out of step) for the whole launch.
+  const int G = gridDim.x;
+  const bool ordered = P.order_hdr && P.order_hdr[0] == DEB_ORDER_MAGIC && P.order_hdr[1] == total && P.order_hdr[2] == P.shape_hash;
+  const int* order = P.order_hdr + 8;
+  bool first = true;
   for (;;) {
-    if (tid == 0) *s_tk = atomicAdd(P.ticket, 1u);
+    if (tid == 0) {
+      unsigned int t;
+      if (ordered && first) t = (G & 1) ? (unsigned int)blockIdx.x : (unsigned int)((blockIdx.x & 1) * (G / 2) + (blockIdx.x >> 1));
+      else t = (ordered ? (unsigned int)G : 0u) + atomicAdd(P.ticket, 1u);
+      *s_tk = t;
+    }
+    first = false;
     __syncthreads();
     const unsigned int tk = *s_tk;
     if (tk >= (unsigned int)total) break;
-    // largest k first, cosmologies interleaved
     const int kd = tk / P.ncosmo, cs = tk - kd * P.ncosmo;
-    const int mode = cs * P.nk + (P.nk - 1 - kd);
+    const int mode = ordered ? order[tk] : cs * P.nk + (P.nk - 1 - kd);
+#ifdef DEB_TEAM_TIMING
+    long long t_start_ = 0;
+    if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start_));
+#endif
     integrate_mode_team<NE, TEAM>(P, *C, W, X, *box, mode, ltid);
     __syncthreads();
+#ifdef DEB_TEAM_TIMING
+    if (tid == 0 && mode < 4096) {
+      long long t_end_; unsigned int smid_;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end_));
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid_));
+      g_mode_log[mode][0] = t_start_; g_mode_log[mode][1] = t_end_; g_mode_log[mode][2] = smid_; g_mode_log[mode][3] = s_tk[1];
+    }
+#endif
   }
+}
+
+// After a team launch: mode ids by descending attempted-step count -> workspace, for the next launch of the same shape
+// (MCMC / emulator loops call with near-identical inputs).  One block, bitonic sort of <= 2048 keys in shared memory.
+__global__ void __launch_bounds__(1024) k_learn_order(const int* __restrict__ nsteps, int total, int* hdr, int shape_hash) {
+  __shared__ unsigned int key[2048];
+  for (int i = threadIdx.x; i < 2048; i += 1024) {
+    unsigned int v = 0u;
+    if (i < total) { const int ns = nsteps[i]; v = ((unsigned int)(ns < 0 ? 0 : (ns > 0xfffff ? 0xfffff : ns)) << 11) | (unsigned int)(2047 - i); v += 1u << 31; }
+    key[i] = v;                                  // real entries carry the top bit: padding sorts last
+  }
+  __syncthreads();
+  for (int k2 = 2; k2 <= 2048; k2 <<= 1)
+    for (int j = k2 >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < 2048; i += 1024) {
+        const int l = i ^ j;
+        if (l > i) {
+          const unsigned int a = key[i], b = key[l];
+          const bool desc = (i & k2) == 0;       // descending overall
+          if (desc ? a < b : a > b) { key[i] = b; key[l] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  for (int i = threadIdx.x; i < total; i += 1024) hdr[8 + i] = 2047 - (int)(key[i] & 2047u);
+  __syncthreads();
+  if (threadIdx.x == 0) { hdr[1] = total; hdr[2] = shape_hash; __threadfence(); hdr[0] = DEB_ORDER_MAGIC; }
 }
 
 typedef void (*evolve_kernel_t)(const Problem);
@@ -117,11 +173,19 @@ int deb_launch_team(const Problem& P, cudaStream_t st, int nsm) {
   CUDA_TRY(cudaMemsetAsync(P.ticket, 0, sizeof(unsigned int), st));
   kern<<<(unsigned)grid, 32 * team, smem, st>>>(P);
   CUDA_TRY(cudaGetLastError());
+  if (P.order_hdr && P.mode == 0 && total <= 2048 && !getenv("DEB_NO_ORDER")) {
+    k_learn_order<<<1, 1024, 0, st>>>(P.nsteps, (int)total, P.order_hdr, P.shape_hash);
+    CUDA_TRY(cudaGetLastError());
+  }
   return DEB_OK;
 }
 
 #ifdef DEB_TEAM_TIMING
 // measurement build only: cycles warp 0 of the largest-k mode spent per phase (see DEB_TICK), slot 15 = steps
+extern "C" int deb_debug_team_mode_log(long long* out, int nmodes) {
+  CUDA_TRY(cudaMemcpyFromSymbol(out, g_mode_log, sizeof(long long) * 4 * nmodes));
+  return DEB_OK;
+}
 extern "C" int deb_debug_team_skip(int mask) { CUDA_TRY(cudaMemcpyToSymbol(g_team_skip, &mask, sizeof(int))); return DEB_OK; }
 extern "C" int deb_debug_team_timing(long long* out16, int reset) {
   if (out16) CUDA_TRY(cudaMemcpyFromSymbol(out16, g_team_timing, sizeof(long long) * 32));

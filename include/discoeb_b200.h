@@ -82,7 +82,11 @@ enum deb_status {
 int32_t deb_nvar(const deb_dims* dims);
 /* doubles per cosmology in `tables` */
 size_t deb_table_len(const deb_dims* dims);
-/* bytes of device scratch deb_evolve_f64 needs */
+/* bytes of device scratch deb_evolve_f64 wants: a work-queue counter, one start-time root per cosmology and -- optional,
+ * used when the buffer is at least this large -- a list of the modes ordered by the step counts of the PREVIOUS call
+ * with the same buffer and shape.  Callers that keep the buffer between calls (an MCMC or emulator loop evaluating
+ * near-identical cosmologies) get longest-first scheduling from the second call on; results do not depend on it.
+ * The contents need no initialisation; 256 + 8 ncosmo bytes are the hard minimum. */
 size_t deb_workspace_bytes(const deb_dims* dims);
 const char* deb_strerror(int code);
 int32_t deb_abi_version(void);
