@@ -90,3 +90,30 @@ def test_unsorted_outputs_rejected(tables):
     from discoeb_b200.perturbations import evolve_perturbations
     with pytest.raises(ValueError, match="ascending"):
         evolve_perturbations(param=tables["fiducial"].param(), aexp_out=[1.0, 0.5], kmin=1e-3, kmax=1.0, num_k=4)
+
+
+def test_host_api_signatures_match_reference():
+    """Drop-in check: every keyword of the reference's entry points (perturbations.py:926-1224, recorded by
+    tools/make_reference_signatures.py) exists here in the same order with the same default; the mirror may
+    only append keywords of its own (device, throw, ...)."""
+    import inspect
+    import json
+    from discoeb_b200 import perturbations
+
+    ref = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_signatures.json")))
+    assert len(ref) == 7
+    for name, sig in ref.items():
+        fn = getattr(perturbations, name)  # as in the reference: all seven live in `perturbations`
+        p = inspect.signature(fn).parameters
+        assert [q.name for q in p.values() if q.kind is q.POSITIONAL_OR_KEYWORD] == sig["positional"], name
+        mine = [(q.name, q.default) for q in p.values() if q.kind is q.KEYWORD_ONLY]
+        want = sig["keyword_only"]
+        assert [m[0] for m in mine[:len(want)]] == [w[0] for w in want], name
+        for (kw, default), (_, have) in zip(want, mine):
+            if default is None:
+                # required in the reference; get_xi_from_P's N may default to None here
+                assert have is inspect.Parameter.empty or have is None, (name, kw)
+            else:
+                assert have == eval(default), (name, kw, have, default)
+        # additions must be optional
+        assert all(d is not inspect.Parameter.empty for _, d in mine[len(want):]), name
