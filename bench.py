@@ -47,7 +47,7 @@ METRIC = "k-modes/sec (ms per P(k), N_k=512, in ms_per_step)"
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_evolve_team<3,4,2> launch on this workload (ncu --set full),
 # read from the committed summary so that the number and its evidence cannot drift apart
-NCU_SUMMARY = os.path.join(ROOT, "profiles", "r1_v23_k_evolve_team_ncu_summary.txt")
+NCU_SUMMARY = os.path.join(ROOT, "profiles", "r1_v24_k_evolve_team_ncu_summary.txt")
 
 
 def ncu_dram_bytes_per_launch():
@@ -269,7 +269,7 @@ def run_ours(args, rank, world):
                                   note="FP64 FMA pipe (the path is neither HBM- nor tensor-bound); peak measured on this GPU by "
                                        "deb_fp64_peak_tflops (dependent-free DFMA streams) x n_gpus; algorithmic flops = "
                                        "(370 n + 3000) x attempted steps, n=265; traffic = dram bytes read+written per k_evolve_team "
-                                       "launch from profiles/r1_v23_k_evolve_team_ncu_summary.txt (HBM is idle)"),
+                                       "launch from profiles/r1_v24_k_evolve_team_ncu_summary.txt (HBM is idle)"),
                     e2e=dict(value=world * nk / (e2e * 1e-3), unit="k-modes/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
                              ms_per_step=e2e),
                     gpu_launches=2 * args.steps, clocks=clocks)
