@@ -272,7 +272,8 @@ def run_ours(args, rank, world):
                                        "launch from profiles/r1_v24_k_evolve_team_ncu_summary.txt (HBM is idle)"),
                     e2e=dict(value=world * nk / (e2e * 1e-3), unit="k-modes/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
                              ms_per_step=e2e),
-                    gpu_launches=2 * args.steps, clocks=clocks)
+                    gpu_launches=3 * args.steps,  # k_tau_out, k_evolve_team, k_learn_order per pass (profiles/r1_v24_launch_list_bench.txt)
+                    clocks=clocks)
         if world == 1 and not args.no_cpu_baseline:
             m, dt, st = cpu_reference_pass(tab, 64)
             line["cpu_baseline"] = dict(value=m / dt, unit="k-modes/s", cores=os.cpu_count(), kind="port",
