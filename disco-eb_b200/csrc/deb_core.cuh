@@ -77,6 +77,11 @@
 namespace deb {
 
 constexpr int NSCAL = 24;
+// learned work list (team kernel): header magic and the largest launch it is kept for
+#define DEB_ORDER_MAGIC 0x0EB0DE55
+#define DEB_ORDER_MAX 2048
+// status[] before a mode has been integrated (include/discoeb_b200.h: 0 ok, 1 max_steps, 2 non-finite, 3 not processed)
+#define DEB_STATUS_UNPROCESSED 3
 enum { S_OMEGAM = 0, S_OMEGAB, S_OMEGADE, S_OMEGAK, S_GRHOM, S_GRHOG, S_GRHOR, S_NEFF, S_NMNU, S_AMNU,
        S_W0, S_WA, S_CS2DE, S_YHE, S_H0, S_TAUMIN, S_AS, S_NS, S_KP };
 enum { T_CS2A = 0, T_XE, T_LRHONU, T_LPNU, T_A_OF_TAU, T_XE_OF_TAU, T_TAU_OF_A, NSPLINE };

@@ -20,8 +20,38 @@ using namespace deb;
   fprintf(stderr, "[discoeb_b200] CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return DEB_E_CUDA; } } while (0)
 
 // tau_out[c, j] = tau_of_a_spline(aexp_out[j])   (perturbations.py:975)
-// ... and, once per cosmology, the k-independent root of the start-time search (perturbations.py:679)
-__global__ void k_tau_out(Problem P, double* tau_out, double* lt_small) {
+// ... and, once per cosmology, the k-independent root of the start-time search (perturbations.py:679).
+// The blocks past `tau_blocks` prepare the launch: every status word gets the sentinel DEB_STATUS_UNPROCESSED
+// (a mode that no warp integrates can never read as "ok"), and the first of them decides whether the cost-ordered
+// work list a previous launch left in the workspace may be used: header (magic, size, shape hash) AND an exact
+// permutation test of all entries (shared-memory bitmap) -- a list that was partly overwritten, or that belongs to
+// another layout of a reused arena, is rejected here and never dereferenced.  Verdict -> ticket[2].
+__global__ void __launch_bounds__(128) k_tau_out(Problem P, double* tau_out, double* lt_small, int tau_blocks) {
+  if ((int)blockIdx.x >= tau_blocks) {
+    const int pb = blockIdx.x - tau_blocks, npb = gridDim.x - tau_blocks;
+    const int total = P.ncosmo * P.nk;
+    if (P.mode == 0)
+      for (int i = pb * 128 + threadIdx.x; i < total; i += npb * 128) P.status[i] = DEB_STATUS_UNPROCESSED;
+    if (pb == 0) {
+      __shared__ unsigned int bm[DEB_ORDER_MAX / 32];
+      __shared__ int bad;
+      if (threadIdx.x == 0) bad = 0;
+      for (int i = threadIdx.x; i < DEB_ORDER_MAX / 32; i += 128) bm[i] = 0u;
+      __syncthreads();
+      const int* h = P.order_hdr;
+      const bool hdr_ok = h && total <= DEB_ORDER_MAX && h[0] == DEB_ORDER_MAGIC && h[1] == total && h[2] == P.shape_hash;
+      if (hdr_ok) {
+        for (int i = threadIdx.x; i < total; i += 128) {
+          const unsigned int m = (unsigned int)h[8 + i];
+          if (m >= (unsigned int)total) bad = 1;
+          else if (atomicOr(&bm[m >> 5], 1u << (m & 31)) & (1u << (m & 31))) bad = 1;
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) P.ticket[2] = (hdr_ok && !bad) ? 1u : 0u;
+    }
+    return;
+  }
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P.ncosmo * P.nout) return;
   int c = i / P.nout, j = i - c * P.nout;
@@ -353,8 +383,11 @@ int deb_evolve_tangent_f64(const deb_dims* dims, const deb_ctrl* ctrl, const dou
   double* lt_small = (double*)((char*)workspace + 256);
   P.lt_small = lt_small;
   P.mode = 0;
-  int nt = P.ncosmo * P.nout;
-  k_tau_out<<<(nt + 127) / 128, 128, 0, st>>>(P, tau_out, lt_small);
+  const int nt = P.ncosmo * P.nout, tau_blocks = (nt + 127) / 128;
+  long prep_blocks = ((long)P.ncosmo * P.nk + 4095) / 4096;
+  if (prep_blocks < 1) prep_blocks = 1;
+  if (prep_blocks > 256) prep_blocks = 256;
+  k_tau_out<<<tau_blocks + (int)prep_blocks, 128, 0, st>>>(P, tau_out, lt_small, tau_blocks);
   CUDA_TRY(cudaGetLastError());
   return launch_evolve(P, st);
 }
@@ -383,6 +416,7 @@ static int ctx_reserve(deb_ctx* c, size_t dbytes, size_t hbytes) {
     c->dbuf = nullptr; c->dcap = 0;
     size_t cap = al256(dbytes + dbytes / 4);
     CUDA_TRY(cudaMalloc((void**)&c->dbuf, cap));
+    CUDA_TRY(cudaMemset(c->dbuf, 0, cap));
     c->dcap = cap;
   }
   if (hbytes > c->hcap) {
@@ -451,7 +485,10 @@ static int ctx_evolve(deb_ctx* c, const deb_dims* dims, const deb_ctrl* ctrl, co
   rc = ctx_reserve(c, in_bytes + out_bytes + ws_bytes, in_bytes + out_bytes);
   if (rc) return rc;
   char* hin = c->hbuf; char* hout = c->hbuf + in_bytes;
-  char* din = c->dbuf; char* dout = c->dbuf + in_bytes; char* dws = dout + out_bytes;
+  // device arena: workspace | inputs | outputs.  The workspace sits at offset 0 so that what a launch leaves there for
+  // the next one (the learned work list) is never overlaid by another call shape's inputs or outputs; a regrown
+  // arena starts zeroed (ctx_reserve), and k_tau_out re-validates the list in full before every use.
+  char* dws = c->dbuf; char* din = dws + ws_bytes; char* dout = din + in_bytes;
   memcpy(hin + i_sc, scalars, nc * DEB_NSCAL * 8);
   memcpy(hin + i_tb, tables, nc * tl * 8);
   memcpy(hin + i_k, kmodes, nkm * 8);
@@ -595,7 +632,7 @@ static int debug_common(const deb_dims* dims, const deb_ctrl* ctrl, const double
   }
   {
     int nt = P.ncosmo * P.nout;
-    k_tau_out<<<(nt + 127) / 128, 128>>>(P, d_tau.as<double>(), lt_small);
+    k_tau_out<<<(nt + 127) / 128, 128>>>(P, d_tau.as<double>(), lt_small, (nt + 127) / 128);
     CUDA_TRY(cudaGetLastError());
   }
   if (mode == 1) {
@@ -699,7 +736,7 @@ int deb_debug_replay_tangent_host_f64(const deb_dims* dims, const deb_ctrl* ctrl
   P.rp_stride = rp_stride;
   {
     int ntq = P.ncosmo * P.nout;
-    k_tau_out<<<(ntq + 127) / 128, 128>>>(P, d_tau.as<double>(), lt_small);
+    k_tau_out<<<(ntq + 127) / 128, 128>>>(P, d_tau.as<double>(), lt_small, (ntq + 127) / 128);
     CUDA_TRY(cudaGetLastError());
   }
   rc = launch_evolve(P, 0);

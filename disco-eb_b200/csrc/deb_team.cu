@@ -25,8 +25,6 @@ __device__ long long g_mode_log[4096][4];      // per mode: start ns, end ns, SM
 
 using namespace deb;
 
-#define DEB_ORDER_MAGIC 0x0EB0DE55
-
 #define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
   fprintf(stderr, "[discoeb_b200] CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return DEB_E_CUDA; } } while (0)
 
@@ -81,7 +79,8 @@ __global__ void __launch_bounds__(32 * TEAM, MINB) k_evolve_team(const __grid_co
   // modes and odd CTAs the next G/2 -- every SM starts with one long mode instead of two neighbours in k that stay
   // paired (and out of step) for the whole launch.
   const int G = gridDim.x;
-  const bool ordered = P.order_hdr && P.order_hdr[0] == DEB_ORDER_MAGIC && P.order_hdr[1] == total && P.order_hdr[2] == P.shape_hash;
+  // (the list is used only when this launch's pre-kernel verified it entry by entry: k_tau_out -> ticket[2])
+  const bool ordered = P.order_hdr && P.ticket[2] == 1u;
   const int* order = P.order_hdr + 8;
   bool first = true;
   for (;;) {
@@ -173,7 +172,7 @@ int deb_launch_team(const Problem& P, cudaStream_t st, int nsm) {
   CUDA_TRY(cudaMemsetAsync(P.ticket, 0, sizeof(unsigned int), st));
   kern<<<(unsigned)grid, 32 * team, smem, st>>>(P);
   CUDA_TRY(cudaGetLastError());
-  if (P.order_hdr && P.mode == 0 && total <= 2048 && !getenv("DEB_NO_ORDER")) {
+  if (P.order_hdr && P.mode == 0 && total <= DEB_ORDER_MAX && !getenv("DEB_NO_ORDER")) {
     k_learn_order<<<1, 1024, 0, st>>>(P.nsteps, (int)total, P.order_hdr, P.shape_hash);
     CUDA_TRY(cudaGetLastError());
   }

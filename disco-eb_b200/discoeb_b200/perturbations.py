@@ -47,7 +47,8 @@ def _check_status(status, nsteps, max_steps, throw):
     if bad.size:
         kinds = sorted(set(int(s) for s in status[status != 0]))
         msg = (f"{bad.shape[0]} of {status.size} modes did not complete (status codes {kinds}; 1 = the maximum "
-               f"number of solver steps ({max_steps}) was reached, 2 = non-finite step). Try increasing max_steps.")
+               f"number of solver steps ({max_steps}) was reached, 2 = non-finite step, 3 = the mode was never integrated "
+               f"(library fault)). Try increasing max_steps.")
         raise MaxStepsReached(msg)
 
 

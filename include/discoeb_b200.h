@@ -13,7 +13,8 @@
  * Conventions: plain pointers and sizes, float64 everywhere, row-major, no allocation and no
  * synchronisation inside the *_f64 device entry (asynchronous on `stream`), re-entrant, no
  * global state.  Return value 0 or a negative deb_status code; per-mode solver outcomes go to
- * status[] (0 ok, 1 max_steps exhausted, 2 non-finite), mirroring diffrax's RESULTS.
+ * status[] (0 ok, 1 max_steps exhausted, 2 non-finite, 3 not processed: the value every entry holds until
+ * a warp has integrated the mode), mirroring diffrax's RESULTS.
  */
 #ifndef DISCOEB_B200_H
 #define DISCOEB_B200_H

@@ -76,6 +76,30 @@ def test_team_kernel_full_size(gpu_lib, emu_lib, tables, monkeypatch):
     print("kernel_ms helper", two["kernel_ms"], "team", a["kernel_ms"])
 
 
+def test_context_reuse_across_shapes(gpu_lib, tables, monkeypatch):
+    """One cached context, alternating call shapes: the learned work list of one shape must never be
+    used -- or mis-read -- by another.  num_k 100 / 101 / 100 moved the workspace inside the old arena layout by
+    exactly the size of a list entry block; every call is compared with a fresh-process-equivalent run (DEB_NO_ORDER)
+    and must be bit-identical, with every mode processed (status 0, never the sentinel 3)."""
+    from discoeb_b200 import _cabi
+    tab = tables["fiducial"]
+    monkeypatch.setenv("DEB_VARIANT", "team")
+    ctrl = _cabi.make_ctrl(rtol=1e-3, atol=1e-3)
+    def run(nk, ncosmo=1):
+        dims = _cabi.make_dims(ncosmo=ncosmo, nk=nk, nout=1, lmaxg=11, lmaxgp=11, lmaxr=11, lmaxnu=8, nqmax=3, nth=tab.nth,
+                               nnu=tab.nnu, max_steps=2048, power_idx=4)
+        ks = np.geomspace(1e-3, 0.3, nk)
+        sc = np.repeat(tab.scalars[None], ncosmo, 0); tb = np.repeat(tab.tables[None], ncosmo, 0)
+        return gpu_lib.evolve_host(dims, ctrl, sc, tb, ks, np.array([1.0]), want_pk=True)
+    monkeypatch.setenv("DEB_NO_ORDER", "1")
+    ref = {key: run(*key) for key in ((100, 1), (101, 1), (50, 2), (37, 3))}
+    monkeypatch.delenv("DEB_NO_ORDER")
+    for key in ((100, 1), (101, 1), (100, 1), (50, 2), (100, 1), (37, 3), (101, 1), (100, 1), (100, 1)):
+        out = run(*key)
+        assert np.all(out["status"] == 0), (key, np.unique(out["status"]))
+        assert np.array_equal(out["y"], ref[key]["y"]) and np.array_equal(out["nsteps"], ref[key]["nsteps"]), key
+
+
 def test_gpu_matches_cpu_build_of_same_source(gpu_lib, emu_lib, tables):
     """Same source, two compilers: any difference beyond round-off is a GPU-only defect
     (missing __syncwarp, shuffle misuse, shared-memory race)."""
