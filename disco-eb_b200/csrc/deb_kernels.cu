@@ -245,6 +245,7 @@ static evolve_kernel_t pick_kernel(int n, bool many_modes, bool few_modes, int* 
 }
 
 int deb_launch_team(const Problem& P, cudaStream_t st, int nsm);      // deb_team.cu
+int deb_launch_lane(const Problem& P, cudaStream_t st, int nsm);      // deb_lane.cu
 
 // Kernel choice can be forced for tests and measurements: DEB_VARIANT = warp | helper | team
 static int variant_forced(const char* name) { const char* v = getenv("DEB_VARIANT"); return v && !strcmp(v, name); }
@@ -263,6 +264,10 @@ static int launch_evolve(const Problem& P, cudaStream_t st) {
       const int rc = deb_launch_team(P, st, nsm);
       if (rc != DEB_E_UNSUPPORTED) return rc;
     }
+  }
+  if (P.batch_size == 0 && P.ntan == 0 && variant_forced("lane")) {
+    const int rc = deb_launch_lane(P, st, nsm);
+    if (rc != DEB_E_UNSUPPORTED) return rc;
   }
   if (P.batch_size > 0) {
     batched_kernel_t kern = pick_batched_kernel(P.n);

@@ -11,6 +11,7 @@
 #include "../../include/discoeb_b200.h"
 #include "../../disco-eb_b200/csrc/deb_core.cuh"
 #include "../../disco-eb_b200/csrc/deb_team.cuh"
+#include "../../disco-eb_b200/csrc/deb_lane.cuh"
 #include "../../disco-eb_b200/csrc/deb_host.inl"
 
 using namespace deb;
@@ -160,8 +161,38 @@ static int dispatch_team(const Problem& P) {
   else return DEB_E_UNSUPPORTED;
   return DEB_OK;
 }
+// DEB_EMU_LANE=1 selects the register-resident chain-lane variant (deb_lane.cuh)
+template <int NT>
+static void run_all_lane(const Problem& P) {
+  CtaConst C;
+  std::vector<int> tail(P.np);
+  for (int t = 0; t < 32; ++t) init_cta_const(P, C, tail.data(), t, 32);
+  std::vector<LaneTab<NT>> tab(1);
+  for (int t = 0; t < 32; ++t) init_lane_tab<NT>(P, C, tab[0], t, 32);
+  const int total = P.ncosmo * P.nk;
+#pragma omp parallel
+  {
+    std::vector<LaneWs<NT>> ws(1);
+#pragma omp for schedule(dynamic, 1)
+    for (int m = 0; m < total; ++m) integrate_mode_lane<NT>(P, C, tab[0], ws[0], total - 1 - m);
+  }
+}
+static int dispatch_lane(const Problem& P) {
+  if (LN_NSEG * P.nch > 32 || P.nh > 32) return DEB_E_UNSUPPORTED;
+  switch (lane_nt(P.lmaxg, P.lmaxgp, P.lmaxr, P.lmaxnu)) {
+    case 1: run_all_lane<1>(P); break;
+    case 2: run_all_lane<2>(P); break;
+    case 3: run_all_lane<3>(P); break;
+    case 4: run_all_lane<4>(P); break;
+    case 6: run_all_lane<6>(P); break;
+    case 8: run_all_lane<8>(P); break;
+    default: return DEB_E_UNSUPPORTED;
+  }
+  return DEB_OK;
+}
 static int dispatch(const Problem& P) {
   if (P.batch_size > 0) return dispatch_batched(P);
+  if (const char* ln = getenv("DEB_EMU_LANE")) { if (ln[0] == '1') return dispatch_lane(P); }
   if (const char* tm = getenv("DEB_EMU_TEAM")) {
     const int T = atoi(tm);
     if (T == 2) return dispatch_team<2>(P);

@@ -35,8 +35,17 @@ def load_tables(name):
 
 
 def load_case(name):
-    z = np.load(os.path.join(GOLD, f"oracle_{name}.npz"), allow_pickle=False)
+    """``name`` -> tests/golden/oracle_<name>.npz (NumPy oracle); ``ref:<name>`` -> tests/golden/ref_<name>.npz, the same
+    layout produced by the REFERENCE's own sources (tools/make_reference_fixtures.py)."""
+    fn = f"ref_{name[4:]}.npz" if name.startswith("ref:") else f"oracle_{name}.npz"
+    z = np.load(os.path.join(GOLD, fn), allow_pickle=False)
     return {k: z[k] for k in z.files}
+
+
+def ref_cases():
+    """Reference-produced fixtures present in tests/golden (``ref:<name>`` ids)."""
+    import glob
+    return tuple(sorted("ref:" + os.path.basename(f)[4:-4] for f in glob.glob(os.path.join(GOLD, "ref_*.npz"))))
 
 
 CASES = ("default_n72", "config1_n111", "config2_n265", "w0wa_n72", "odd_dims_n43", "min_dims_n33", "many_out_n72")

@@ -78,6 +78,20 @@ def check_replay(lib, tables, name, tol=1e-6):
             assert helpers.field_scaled_diff(y[0, m], ref[m]).max() < tol, (name, full, m)
 
 
+def check_reference_step(lib, tables, name):
+    """One Rodas5 step of the kernel against what the REFERENCE's own ``Rodas5Transformed.step`` returned for the same
+    (t0, t1, y0) -- ref_<case>.npz: step_* (jacfwd Jacobian + LAPACK LU under tools/refshim).  Bars as check_single_step."""
+    case = helpers.load_case(name)
+    tab = tables[str(case["cosmology"])]
+    ks = case["kmodes"]
+    dims = dims_for(case, tab, len(ks), 1)
+    y1, err = lib.debug_step(dims, tab.scalars, tab.tables, ks, case["step_t0"], case["step_t1"], case["rhs_state"])
+    sc = np.abs(case["step_y1"]).max(axis=1, keepdims=True)
+    assert (np.abs(y1 - case["step_y1"]) / sc).max() < 1e-7
+    sce = np.abs(case["step_err"]).max(axis=1, keepdims=True)
+    assert (np.abs(err - case["step_err"]) / sce).max() < 1e-5
+
+
 def check_adaptive(lib, tables, name):
     case = helpers.load_case(name)
     tab = tables[str(case["cosmology"])]

@@ -33,7 +33,21 @@ def test_adaptive_solve_against_oracle(gpu_lib, tables, name):
     pc.check_adaptive(gpu_lib, tables, name)
 
 
-@pytest.mark.parametrize("variant", ["warp", "team"])
+@pytest.mark.parametrize("variant", ["default", "warp", "team", "lane"])
+@pytest.mark.parametrize("name", helpers.ref_cases())
+def test_against_the_reference_itself(gpu_lib, tables, name, variant, monkeypatch):
+    """tests/golden/ref_*.npz were produced by the REFERENCE's own sources (tools/make_reference_fixtures.py).  Every
+    kernel variant takes one Rodas5 step from the reference's inputs (1e-7 of the state norm), replays the
+    reference's accepted/rejected step sequence onto the reference's outputs (1e-6 of each field, raw state and 20
+    fields) and solves free-running (equal step counts and 1e-5 on short modes, 50 rtol on the matter fields)."""
+    if variant != "default":
+        monkeypatch.setenv("DEB_VARIANT", variant)
+    pc.check_reference_step(gpu_lib, tables, name)
+    pc.check_replay(gpu_lib, tables, name)
+    pc.check_adaptive(gpu_lib, tables, name)
+
+
+@pytest.mark.parametrize("variant", ["warp", "team", "lane"])
 @pytest.mark.parametrize("name", helpers.CASES)
 def test_forced_kernel_variants(gpu_lib, tables, name, variant, monkeypatch):
     """Small launches pick the CTA-per-mode kernel (deb_team.cu) on their own; DEB_VARIANT pins the choice so that the
