@@ -265,7 +265,15 @@ static int launch_evolve(const Problem& P, cudaStream_t st) {
       if (rc != DEB_E_UNSUPPORTED) return rc;
     }
   }
-  if (P.batch_size == 0 && P.ntan == 0 && variant_forced("lane")) {
+  // throughput launches (more modes than the 8 per SM the register file holds) of the large hierarchies: the
+  // register-resident chain-lane kernel (deb_lane.cuh), +11 % over the cyclic one-warp kernel at n = 265
+  // (profiles/r2_lane_*); at n = 72 the cyclic layout with 12 modes per SM stays ahead
+  if (P.batch_size == 0 && P.ntan == 0 && P.mode == 0 &&
+      (variant_forced("lane") || (!getenv("DEB_VARIANT") && P.n > 128 && (long)P.ncosmo * P.nk > (long)nsm * 8))) {
+    const int rc = deb_launch_lane(P, st, nsm);
+    if (rc != DEB_E_UNSUPPORTED) return rc;
+  }
+  if (P.batch_size == 0 && P.ntan == 0 && variant_forced("lane")) {      // debug modes on request
     const int rc = deb_launch_lane(P, st, nsm);
     if (rc != DEB_E_UNSUPPORTED) return rc;
   }

@@ -80,6 +80,10 @@ class Library:
             ([C.c_int32] if prefix == "deb_" else [])
         rt.restype = C.c_int
         self._debug_replay_tangent = rt
+        bgf = getattr(self.lib, prefix + "background_host_f64")
+        bgf.argtypes = [C.c_int32, C.c_int32, C.c_int32, _dp, _dp, _dp, C.POINTER(C.c_float)]
+        bgf.restype = C.c_int
+        self._background_host = bgf
         if prefix == "deb_":
             self.lib.deb_strerror.restype = C.c_char_p
             self.lib.deb_strerror.argtypes = [C.c_int]
@@ -110,6 +114,17 @@ class Library:
     @staticmethod
     def nvar(lmaxg, lmaxgp, lmaxr, lmaxnu, nqmax):
         return 7 + (lmaxg + 1) + (lmaxgp + 1) + (lmaxr + 1) + nqmax * (lmaxnu + 1) + 2
+
+    def background_host(self, bg_in, nth: int, device: int = 0, nnu: int = 512):
+        """Table producer (deb_background_host_f64): bg_in[nc, 16] -> (scalars[nc, 24], tables[nc, 3 (5 nth + 2 nnu)], kernel ms)."""
+        bg_in = np.ascontiguousarray(bg_in, dtype=np.float64)
+        nc = bg_in.shape[0]
+        scal = np.zeros((nc, 24), dtype=np.float64)
+        tab = np.zeros((nc, 3 * (5 * nth + 2 * nnu)), dtype=np.float64)
+        kms = C.c_float(0.0)
+        self._check(self._background_host(C.c_int32(device), C.c_int32(nc), C.c_int32(nth), _d(bg_in), _d(scal), _d(tab), C.byref(kms)),
+                    "background_host_f64")
+        return scal, tab, kms.value
 
     def evolve_host(self, dims: DebDims, ctrl: DebCtrl, scalars, tables, kmodes, aexp_out, device: int = 0,
                     want_pk: bool = False):

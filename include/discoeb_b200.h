@@ -212,6 +212,27 @@ int deb_debug_replay_tangent_host_f64(const deb_dims* dims, const deb_ctrl* ctrl
                                       double* y_out, double* dy_out, double* dtau_out, int32_t* nsteps,
                                       int32_t device);
 
+/* ---- table production --------------------------------------------------------------------
+ * Replaces, for a batch of cosmologies, what the reference's
+ *   evolve_background(param, thermo_module='RECFAST', num_thermo)      /root/reference/src/discoeb/background.py:191-255
+ *     -> setup_background_evolution                                     background.py:140-188
+ *     -> evaluate_thermo / compute_thermal_history / solve_ionization   thermodynamics_recfast.py:124-500
+ *        (GRKT4.step ode_integrators_stiff.py:77-215 under diffrax's PID loop)
+ *     -> spline_interpolation(...) constructors                         spline_interpolation.py:8-113
+ * leaves in `param` for evolve_perturbations: one CTA per cosmology writes scalars[DEB_NSCAL] (deb_scalar order; slots
+ * 19..22 = taumax, Omegamnu, Tcmb, mnu) and tables[deb_table_len] (deb_spline order, nnu = 512) in exactly the layout
+ * deb_evolve_f64 consumes, so a cosmology batch goes from parameters to P(k) without leaving the device.
+ *   bg_in [ncosmo, 16]: Omegam, Omegab, Omegak, w_DE_0, w_DE_a, cs2_DE, H0, Tcmb, YHe, Neff, Nmnu, mnu, A_s, n_s, k_p, (pad)
+ * All pointers of deb_background_f64 are DEVICE pointers; no allocation, no synchronisation, asynchronous on `stream`.
+ * nth = num_thermo (16..1024).  workspace: deb_background_workspace_bytes(ncosmo, nth) bytes, contents undefined. */
+size_t deb_background_workspace_bytes(int32_t ncosmo, int32_t nth);
+size_t deb_background_nin(void);
+int deb_background_f64(int32_t ncosmo, int32_t nth, const double* bg_in, double* scalars, double* tables,
+                       void* workspace, size_t workspace_bytes, void* stream);
+/* host-buffer form: H2D of bg_in, the kernel, D2H of scalars and tables; kernel_ms (optional) = device time */
+int deb_background_host_f64(int32_t device, int32_t ncosmo, int32_t nth, const double* bg_in, double* scalars,
+                            double* tables, float* kernel_ms);
+
 /* Measures the FP64 FMA peak of `device` (dependent-free DFMA streams on every SM) and
  * returns it in TFLOP/s; the roofline denominator bench.py reports against. */
 int deb_fp64_peak_tflops(int32_t device, double* tflops, float* sm_clock_mhz);

@@ -50,6 +50,7 @@ def emu_lib():
     out = os.path.join(ROOT, "tests", "emu", "_build", "libdeb_emu.so")
     deps = [src, os.path.join(ROOT, "disco-eb_b200", "csrc", "deb_core.cuh"),
             os.path.join(ROOT, "disco-eb_b200", "csrc", "deb_team.cuh"), os.path.join(ROOT, "disco-eb_b200", "csrc", "deb_tangent.cuh"),
+            os.path.join(ROOT, "disco-eb_b200", "csrc", "deb_lane.cuh"), os.path.join(ROOT, "disco-eb_b200", "csrc", "deb_background.cuh"),
             os.path.join(ROOT, "disco-eb_b200", "csrc", "deb_host.inl"), os.path.join(ROOT, "include", "discoeb_b200.h")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         os.makedirs(os.path.dirname(out), exist_ok=True)

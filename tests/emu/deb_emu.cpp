@@ -12,6 +12,7 @@
 #include "../../disco-eb_b200/csrc/deb_core.cuh"
 #include "../../disco-eb_b200/csrc/deb_team.cuh"
 #include "../../disco-eb_b200/csrc/deb_lane.cuh"
+#include "../../disco-eb_b200/csrc/deb_background.cuh"
 #include "../../disco-eb_b200/csrc/deb_host.inl"
 
 using namespace deb;
@@ -316,4 +317,23 @@ extern "C" int emu_debug_replay_tangent_host_f64(const deb_dims* dims, const deb
   rc = dispatch_tan(P);
   if (dtau_out) memcpy(dtau_out, dtau.data(), dtau.size() * sizeof(double));
   return rc;
+}
+
+// table producer (deb_background.cuh) on the CPU: one cosmology per OpenMP thread
+extern "C" int emu_background_host_f64(int32_t device, int32_t ncosmo, int32_t nth, const double* bg_in, double* scalars, double* tables,
+                                       float* kernel_ms) {
+  (void)device;
+  using namespace deb::bg;
+  if (ncosmo < 1 || nth < 16 || nth > NTH_MAX) return DEB_E_ARG;
+  double q[NNUQ], w[NNUQ];
+  nu_quadrature(q, w);
+  const size_t tl = 3 * (size_t)(5 * nth + 2 * NNU);
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int c = 0; c < ncosmo; ++c) {
+    std::vector<BgWork> W(1);
+    for (int i = 0; i < DEB_NSCAL; ++i) scalars[(size_t)c * DEB_NSCAL + i] = 0.0;
+    background_one(bg_in + (size_t)c * NBGIN, q, w, nth, scalars + (size_t)c * DEB_NSCAL, tables + (size_t)c * tl, W[0], 0, 1);
+  }
+  if (kernel_ms) *kernel_ms = 0.0f;
+  return DEB_OK;
 }

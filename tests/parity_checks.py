@@ -75,7 +75,7 @@ def check_replay(lib, tables, name, tol=1e-6):
         assert np.array_equal(ns[0], case["nsteps"])
         ref = case["yfull"] if full else case["y"]
         for m in range(len(ks)):          # per mode: the fields of different k differ by orders of magnitude
-            assert helpers.field_scaled_diff(y[0, m], ref[m]).max() < tol, (name, full, m)
+            assert helpers.field_scaled_diff(y[0, m], ref[m], dims=case["dims"]).max() < tol, (name, full, m)
 
 
 def check_reference_step(lib, tables, name):
@@ -162,7 +162,7 @@ def check_tangent_replay(lib, name, tol=1e-6):
         np.testing.assert_allclose(dtau[:, 0], case["dtau_out"], rtol=1e-9, atol=1e-9 * np.abs(case["dtau_out"]).max() + 1e-300)
         ref, dref = (case["yfull"], case["dyfull"]) if full else (case["y"], case["dy"])
         for m in range(len(ks)):
-            assert helpers.field_scaled_diff(y[0, m], ref[m]).max() < tol, (name, full, m)
+            assert helpers.field_scaled_diff(y[0, m], ref[m], dims=case["dims"]).max() < tol, (name, full, m)
             for d in range(nt):
                 if not np.any(dref[d, m]):
                     assert not np.any(dy[d, 0, m]), (name, full, m, d)      # post-processing-only direction: exactly zero
@@ -315,7 +315,7 @@ def check_batched_replay(lib, tables, name, tol=1e-6):
         assert np.array_equal(ns[0], case["nsteps"])
         ref = case["yfull"] if full else case["y"]
         for m in range(len(ks)):
-            assert helpers.field_scaled_diff(y[0, m], ref[m]).max() < tol, (name, full, m)
+            assert helpers.field_scaled_diff(y[0, m], ref[m], dims=case["dims"]).max() < tol, (name, full, m)
 
 
 def check_batched_adaptive(lib, tables, name):

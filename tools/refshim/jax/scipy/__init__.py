@@ -7,12 +7,12 @@ from ..numpy import _wrap
 
 class _Linalg:
     @staticmethod
-    def lu_factor(a):
-        lu, piv = _sl.lu_factor(_np.asarray(a), check_finite=False)
+    def lu_factor(a, overwrite_a=False, check_finite=True):
+        lu, piv = _sl.lu_factor(_np.array(a), check_finite=False)
         return _wrap(lu), piv
 
     @staticmethod
-    def lu_solve(lu_and_piv, b, trans=0):
+    def lu_solve(lu_and_piv, b, trans=0, overwrite_b=False, check_finite=True):
         lu, piv = lu_and_piv
         return _wrap(_sl.lu_solve((_np.asarray(lu), piv), _np.asarray(b), trans=trans, check_finite=False))
 
