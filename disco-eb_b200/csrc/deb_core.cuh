@@ -284,7 +284,38 @@ struct Problem {
   // cost-ordered work list left in the caller's workspace by the previous launch of the same shape (team kernel):
   // header {magic, nmodes, shape hash, ...} + mode ids by descending step count; NULL when the workspace is too small
   int* order_hdr; int shape_hash;
+  // sharded launch with peer stores (deb_evolve_sharded_peer_f64): a rank integrates every `out_mul`-th k-mode and writes
+  // the 20 fields, P(k) and the status words of local mode kidx to row kidx*out_mul + out_add (of out_nk) of the FULL-SIZE
+  // buffers of all npeer ranks -- its own and, through NVLink peer mappings, everybody else's: the epilogue is the gather
+  int npeer, out_mul, out_add, out_nk;
+  double* y_peer[8]; double* pk_peer[8]; int* st_peer[8]; int* ns_peer[8];
 };
+
+// epilogue stores: 20 output fields (+ P(k)) of (mode, save_idx), and the per-mode status words
+DEB_DEV void store_fields(const Problem& P, int mode, int save_idx, const double* o20, bool has_pk, double pk) {
+  if (P.npeer == 0) {
+    const size_t obase = (size_t)mode * P.nout + save_idx;
+    for (int q = 0; q < 20; ++q) P.y_out[obase * 20 + q] = o20[q];
+    if (has_pk) P.pk_out[obase] = pk;
+    return;
+  }
+  const int cosmo = mode / P.nk, kidx = mode - cosmo * P.nk;
+  const size_t obase = ((size_t)cosmo * P.out_nk + (size_t)kidx * P.out_mul + P.out_add) * P.nout + save_idx;
+  for (int r = 0; r < P.npeer; ++r) {
+    double* y = P.y_peer[r];
+    for (int q = 0; q < 20; ++q) y[obase * 20 + q] = o20[q];
+    if (has_pk) P.pk_peer[r][obase] = pk;
+  }
+}
+DEB_DEV void store_status(const Problem& P, int mode, int status, int nsteps, int nacc) {
+  P.status[mode] = status; P.nsteps[mode] = nsteps;
+  if (P.naccept) P.naccept[mode] = nacc;
+  if (P.npeer > 0) {
+    const int cosmo = mode / P.nk, kidx = mode - cosmo * P.nk;
+    const size_t g = (size_t)cosmo * P.out_nk + (size_t)kidx * P.out_mul + P.out_add;
+    for (int r = 0; r < P.npeer; ++r) { P.st_peer[r][g] = status; P.ns_peer[r][g] = nsteps; }
+  }
+}
 
 // momentum bins (background.py:27-38); weights already divided by 7 pi^4/120
 struct NuBins { double q[NQMAX], w[NQMAX], dl[NQMAX]; };
@@ -1740,11 +1771,10 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, Help
             if (wr) {
               double o20[20];
               convert_outputs(P, c, nb, W.r(), k, o20);
-              for (int q = 0; q < 20; ++q) P.y_out[obase * 20 + q] = o20[q];
-              if (P.pk_out && P.power_idx >= 0) {
-                double yv = o20[P.power_idx];
-                P.pk_out[obase] = 2.0 * 9.869604401089358 * c.As * DEB_POW(k / c.kp, c.ns - 1.0) * DEB_POW(k, -3.0) * yv * yv;
-              }
+              const bool has_pk = P.pk_out && P.power_idx >= 0;
+              double pkv = 0.0;
+              if (has_pk) { const double yv = o20[P.power_idx]; pkv = 2.0 * 9.869604401089358 * c.As * DEB_POW(k / c.kp, c.ns - 1.0) * DEB_POW(k, -3.0) * yv * yv; }
+              store_fields(P, mode, save_idx, o20, has_pk, pkv);
             }
             if (TAN) {
               Dual od[20];
@@ -1776,8 +1806,7 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, Help
   if (status == 0 && t < t1) status = 1;
   DEB_LANE0_BEGIN
     if (!TAN || tan == 0) {
-      P.status[mode] = status; P.nsteps[mode] = nsteps;
-      if (P.naccept) P.naccept[mode] = nacc;
+      store_status(P, mode, status, nsteps, nacc);
     }
   DEB_LANE0_END
 }

@@ -362,23 +362,24 @@ const char* deb_strerror(int code) { return deb_strerror_impl(code); }
 int32_t deb_abi_version(void) { return DEB_ABI_VERSION; }
 int32_t deb_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
 
-int deb_evolve_f64(const deb_dims* dims, const deb_ctrl* ctrl, const double* scalars, const double* tables,
-                   const double* kmodes, const double* aexp_out, double* y_out, double* pk_out, double* tau_out,
-                   int32_t* status, int32_t* nsteps, int32_t* naccept, void* workspace, size_t workspace_bytes,
-                   void* stream) {
-  if (dims && dims->ntan != 0) return DEB_E_ARG;       // tangents go through deb_evolve_tangent_f64
-  return deb_evolve_tangent_f64(dims, ctrl, scalars, tables, kmodes, aexp_out, nullptr, nullptr, nullptr, y_out, nullptr, pk_out, nullptr,
-                                tau_out, nullptr, status, nsteps, naccept, workspace, workspace_bytes, stream);
-}
 
-int deb_evolve_tangent_f64(const deb_dims* dims, const deb_ctrl* ctrl, const double* scalars, const double* tables,
-                           const double* kmodes, const double* aexp_out, const double* d_scalars, const double* d_tables,
-                           const double* d_kmodes, double* y_out, double* dy_out, double* pk_out, double* dpk_out, double* tau_out,
-                           double* dtau_out, int32_t* status, int32_t* nsteps, int32_t* naccept, void* workspace,
-                           size_t workspace_bytes, void* stream) {
+struct PeerSpec { int npeer, mul, add, out_nk; double* const* y; double* const* pk; int32_t* const* st; int32_t* const* ns; };
+
+static int evolve_common(const deb_dims* dims, const deb_ctrl* ctrl, const double* scalars, const double* tables,
+                         const double* kmodes, const double* aexp_out, const double* d_scalars, const double* d_tables,
+                         const double* d_kmodes, double* y_out, double* dy_out, double* pk_out, double* dpk_out, double* tau_out,
+                         double* dtau_out, int32_t* status, int32_t* nsteps, int32_t* naccept, void* workspace,
+                         size_t workspace_bytes, void* stream, const PeerSpec* peers) {
   Problem P;
   int rc = fill_problem(dims, ctrl, &P);
   if (rc) return rc;
+  if (peers) {
+    if (peers->npeer < 1 || peers->npeer > 8 || dims->return_full || dims->ntan || dims->batch_size) return DEB_E_UNSUPPORTED;
+    P.npeer = peers->npeer; P.out_mul = peers->mul; P.out_add = peers->add; P.out_nk = peers->out_nk;
+    for (int r = 0; r < peers->npeer; ++r) {
+      P.y_peer[r] = peers->y[r]; P.pk_peer[r] = peers->pk ? peers->pk[r] : nullptr; P.st_peer[r] = peers->st[r]; P.ns_peer[r] = peers->ns[r];
+    }
+  }
   if (!scalars || !tables || !kmodes || !aexp_out || !y_out || !tau_out || !status || !nsteps || !workspace) return DEB_E_ARG;
   if (workspace_bytes < ws_min_bytes(dims)) return DEB_E_WORKSPACE;
   P.order_hdr = workspace_bytes >= deb_workspace_bytes(dims) ? (int*)((char*)workspace + ws_order_offset(dims)) : nullptr;
@@ -403,6 +404,37 @@ int deb_evolve_tangent_f64(const deb_dims* dims, const deb_ctrl* ctrl, const dou
   k_tau_out<<<tau_blocks + (int)prep_blocks, 128, 0, st>>>(P, tau_out, lt_small, tau_blocks);
   CUDA_TRY(cudaGetLastError());
   return launch_evolve(P, st);
+}
+
+int deb_evolve_tangent_f64(const deb_dims* dims, const deb_ctrl* ctrl, const double* scalars, const double* tables,
+                           const double* kmodes, const double* aexp_out, const double* d_scalars, const double* d_tables,
+                           const double* d_kmodes, double* y_out, double* dy_out, double* pk_out, double* dpk_out, double* tau_out,
+                           double* dtau_out, int32_t* status, int32_t* nsteps, int32_t* naccept, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  return evolve_common(dims, ctrl, scalars, tables, kmodes, aexp_out, d_scalars, d_tables, d_kmodes, y_out, dy_out, pk_out, dpk_out, tau_out,
+                       dtau_out, status, nsteps, naccept, workspace, workspace_bytes, stream, nullptr);
+}
+
+int deb_evolve_f64(const deb_dims* dims, const deb_ctrl* ctrl, const double* scalars, const double* tables,
+                   const double* kmodes, const double* aexp_out, double* y_out, double* pk_out, double* tau_out,
+                   int32_t* status, int32_t* nsteps, int32_t* naccept, void* workspace, size_t workspace_bytes,
+                   void* stream) {
+  if (dims && dims->ntan != 0) return DEB_E_ARG;       // tangents go through deb_evolve_tangent_f64
+  return deb_evolve_tangent_f64(dims, ctrl, scalars, tables, kmodes, aexp_out, nullptr, nullptr, nullptr, y_out, nullptr, pk_out, nullptr,
+                                tau_out, nullptr, status, nsteps, naccept, workspace, workspace_bytes, stream);
+}
+
+// deb_evolve_f64 whose epilogue ALSO stores every mode's row into the full-size buffers of `npeer` ranks (peer-mapped
+// device pointers): local mode kidx is row kidx*out_mul + out_add of out_nk.  See deb_dist.cu.
+int deb_evolve_peer_f64(const deb_dims* dims, const deb_ctrl* ctrl, const double* scalars, const double* tables,
+                        const double* kmodes, const double* aexp_out, double* y_out, double* pk_out, double* tau_out,
+                        int32_t* status, int32_t* nsteps, int32_t* naccept, void* workspace, size_t workspace_bytes, void* stream,
+                        int32_t npeer, int32_t out_mul, int32_t out_add, int32_t out_nk,
+                        double* const* y_peer, double* const* pk_peer, int32_t* const* st_peer, int32_t* const* ns_peer) {
+  if (!y_peer || !st_peer || !ns_peer) return DEB_E_ARG;
+  PeerSpec ps = {npeer, out_mul, out_add, out_nk, y_peer, pk_peer, st_peer, ns_peer};
+  return evolve_common(dims, ctrl, scalars, tables, kmodes, aexp_out, nullptr, nullptr, nullptr, y_out, nullptr, pk_out, nullptr, tau_out,
+                       nullptr, status, nsteps, naccept, workspace, workspace_bytes, stream, &ps);
 }
 
 }  // extern "C" (reopened below)

@@ -695,11 +695,10 @@ DEB_DEV void integrate_mode_lane(const Problem& P, const CtaConst& C, const Lane
           DEB_LANE0_BEGIN
             double o20[20];
             convert_outputs(P, c, nb, W.o_(), k, o20);
-            for (int q = 0; q < 20; ++q) P.y_out[obase * 20 + q] = o20[q];
-            if (P.pk_out && P.power_idx >= 0) {
-              double yv = o20[P.power_idx];
-              P.pk_out[obase] = 2.0 * 9.869604401089358 * c.As * DEB_POW(k / c.kp, c.ns - 1.0) * DEB_POW(k, -3.0) * yv * yv;
-            }
+            const bool has_pk = P.pk_out && P.power_idx >= 0;
+            double pkv = 0.0;
+            if (has_pk) { const double yv = o20[P.power_idx]; pkv = 2.0 * 9.869604401089358 * c.As * DEB_POW(k / c.kp, c.ns - 1.0) * DEB_POW(k, -3.0) * yv * yv; }
+            store_fields(P, mode, save_idx, o20, has_pk, pkv);
           DEB_LANE0_END
         }
         ++save_idx;
@@ -722,8 +721,7 @@ DEB_DEV void integrate_mode_lane(const Problem& P, const CtaConst& C, const Lane
   }
   if (status == 0 && t < t1) status = 1;
   DEB_LANE0_BEGIN
-    P.status[mode] = status; P.nsteps[mode] = nsteps;
-    if (P.naccept) P.naccept[mode] = nacc;
+    store_status(P, mode, status, nsteps, nacc);
   DEB_LANE0_END
 }
 

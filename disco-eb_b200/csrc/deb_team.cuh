@@ -936,11 +936,10 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
             if (tid == 0) {
               double o20[20];
               team_convert_outputs(P, c, nb, W.r(), k, o20);
-              for (int q = 0; q < 20; ++q) P.y_out[obase * 20 + q] = o20[q];
-              if (P.pk_out && P.power_idx >= 0) {
-                double yv = o20[P.power_idx];
-                P.pk_out[obase] = 2.0 * 9.869604401089358 * c.As * DEB_POW(k / c.kp, c.ns - 1.0) * DEB_POW(k, -3.0) * yv * yv;
-              }
+              const bool has_pk = P.pk_out && P.power_idx >= 0;
+              double pkv = 0.0;
+              if (has_pk) { const double yv = o20[P.power_idx]; pkv = 2.0 * 9.869604401089358 * c.As * DEB_POW(k / c.kp, c.ns - 1.0) * DEB_POW(k, -3.0) * yv * yv; }
+              store_fields(P, mode, save_idx, o20, has_pk, pkv);
             }
           DEB_T_END
           DEB_T_BAR();
@@ -970,8 +969,7 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
   if (status == 0 && t < t1) status = 1;
   DEB_T_BEGIN
     if (tid == 0) {
-      P.status[mode] = status; P.nsteps[mode] = nsteps;
-      if (P.naccept) P.naccept[mode] = nacc;
+      store_status(P, mode, status, nsteps, nacc);
     }
   DEB_T_END
 }

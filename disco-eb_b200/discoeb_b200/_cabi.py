@@ -126,6 +126,21 @@ class Library:
                     "background_host_f64")
         return scal, tab, kms.value
 
+    def evolve_sharded_host(self, comm, dims: DebDims, ctrl: DebCtrl, scalars, tables, kmodes, aexp_out, want_pk: bool = False):
+        """deb_evolve_sharded_host_f64: the k grid of `dims` dealt over comm.world ranks, NCCL all-gather, full-size results."""
+        nc, nk, nout = dims.ncosmo, dims.nk, dims.nout
+        scalars = np.ascontiguousarray(scalars, dtype=np.float64); tables = np.ascontiguousarray(tables, dtype=np.float64)
+        kmodes = np.ascontiguousarray(kmodes, dtype=np.float64); aexp_out = np.ascontiguousarray(aexp_out, dtype=np.float64)
+        y = np.zeros((nc, nk, nout, 20)); pk = np.zeros((nc, nk, nout)) if want_pk else None
+        tau_out = np.zeros((nc, nout)); status = np.zeros((nc, nk), dtype=np.int32); nsteps = np.zeros((nc, nk), dtype=np.int32)
+        ms = C.c_float(0.0)
+        f = self.lib.deb_evolve_sharded_host_f64
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_int32, C.POINTER(DebDims), C.POINTER(DebCtrl), _dp, _dp, _dp, _dp, _dp, _dp, _dp, _ip, _ip, C.POINTER(C.c_float)]
+        self._check(f(comm.handle, C.c_int32(comm.device), C.byref(dims), C.byref(ctrl), _d(scalars), _d(tables), _d(kmodes), _d(aexp_out),
+                      _d(y), _d(pk), _d(tau_out), _i(status), _i(nsteps), C.byref(ms)), "evolve_sharded_host_f64")
+        return dict(y=y, pk=pk, tau_out=tau_out, status=status, nsteps=nsteps, elapsed_ms=ms.value)
+
     def evolve_host(self, dims: DebDims, ctrl: DebCtrl, scalars, tables, kmodes, aexp_out, device: int = 0,
                     want_pk: bool = False):
         """numpy in -> dict of numpy out (y, pk, tau_out, status, nsteps, naccept, kernel_ms)."""

@@ -233,6 +233,42 @@ int deb_background_f64(int32_t ncosmo, int32_t nth, const double* bg_in, double*
 int deb_background_host_f64(int32_t device, int32_t ncosmo, int32_t nth, const double* bg_in, double* scalars,
                             double* tables, float* kernel_ms);
 
+/* ---- multi-GPU: one k grid dealt round-robin over the ranks of one box ---------------------------
+ * The reference has no multi-device code; its vmap over k (perturbations.py:980-987) is what gets sharded: rank r integrates
+ * modes r, r + W, ... (cost rises steeply with k) and EVERY rank ends with the full-size y_all[ncosmo, nk, nout, 20],
+ * pk_all[ncosmo, nk, nout], status_all / nsteps_all[ncosmo, nk].  dims describes the WHOLE problem (nk = all modes;
+ * return_full = 0, k_per_cosmo = 0, ntan = 0, batch_size = 0).  All array arguments are device pointers, the call is
+ * asynchronous on `stream`, nothing is allocated.
+ *   gather = 0: one ncclAllGather (communicator of deb_comm_create) + a kernel that undoes the deal;
+ *   gather = 1: no collective -- the kernels' epilogue stores each mode's row into the full-size buffers of ALL ranks:
+ *               y_peer[r] / pk_peer[r] / st_peer[r] / ns_peer[r] (host arrays of W device pointers, r = rank) must be
+ *               addresses valid on THIS device for rank r's y_all / pk_all / status_all / nsteps_all (CUDA IPC or
+ *               symmetric-memory mappings over NVLink; entry `rank` is the local buffer).  The caller runs a cross-rank
+ *               barrier after the stream work before anybody reads. */
+typedef struct deb_comm deb_comm;
+int deb_nccl_unique_id(void* id128);                       /* rank 0: 128 bytes to hand to every rank */
+int deb_comm_create(int32_t world, int32_t rank, const void* id128, deb_comm** out);   /* on the current device; collective */
+int deb_comm_create_on(int32_t device, int32_t world, int32_t rank, const void* id128, deb_comm** out);
+void deb_comm_destroy(deb_comm* comm);
+size_t deb_sharded_workspace_bytes(const deb_dims* dims, int32_t world);
+int deb_evolve_sharded_f64(deb_comm* comm, int32_t world, int32_t rank, const deb_dims* dims, const deb_ctrl* ctrl,
+                           const double* scalars, const double* tables, const double* kmodes, const double* aexp_out,
+                           double* y_all, double* pk_all, double* tau_out, int32_t* status_all, int32_t* nsteps_all,
+                           void* workspace, size_t workspace_bytes, int32_t gather,
+                           double* const* y_peer, double* const* pk_peer, int32_t* const* st_peer, int32_t* const* ns_peer,
+                           void* stream);
+/* host-buffer form of deb_evolve_sharded_f64 with gather = 0 (every rank passes the same host inputs) */
+int deb_evolve_sharded_host_f64(deb_comm* comm, int32_t device, const deb_dims* dims, const deb_ctrl* ctrl, const double* scalars,
+                                const double* tables, const double* kmodes, const double* aexp_out, double* y_all, double* pk_all,
+                                double* tau_out, int32_t* status_all, int32_t* nsteps_all, float* elapsed_ms);
+/* deb_evolve_f64 whose epilogue also stores every mode's row (20 nout fields, P(k), status, step count) into `npeer`
+ * full-size peer buffers: local mode kidx is row kidx * out_mul + out_add of out_nk. */
+int deb_evolve_peer_f64(const deb_dims* dims, const deb_ctrl* ctrl, const double* scalars, const double* tables,
+                        const double* kmodes, const double* aexp_out, double* y_out, double* pk_out, double* tau_out,
+                        int32_t* status, int32_t* nsteps, int32_t* naccept, void* workspace, size_t workspace_bytes, void* stream,
+                        int32_t npeer, int32_t out_mul, int32_t out_add, int32_t out_nk,
+                        double* const* y_peer, double* const* pk_peer, int32_t* const* st_peer, int32_t* const* ns_peer);
+
 /* Measures the FP64 FMA peak of `device` (dependent-free DFMA streams on every SM) and
  * returns it in TFLOP/s; the roofline denominator bench.py reports against. */
 int deb_fp64_peak_tflops(int32_t device, double* tflops, float* sm_clock_mhz);

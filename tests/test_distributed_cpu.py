@@ -18,6 +18,16 @@ def _free_port():
     return p
 
 
+def _gloo_allgather(buf):
+    """The host-side gather the package asks its caller for: here torch.distributed on gloo (test plumbing)."""
+    import torch
+    import torch.distributed as dist
+    t = torch.from_numpy(np.ascontiguousarray(buf))
+    out = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return [o.numpy() for o in out]
+
+
 def _worker(rank, world, port, emu_path, q):
     import sys
     sys.path.insert(0, helpers.ROOT)
@@ -30,10 +40,49 @@ def _worker(rank, world, port, emu_path, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     lib = _cabi.Library(emu_path, prefix="emu_")
     p = helpers.load_tables("fiducial").param()
-    y, k, p = evolve_perturbations_sharded(param=p, aexp_out=[0.5, 1.0], kmin=1e-3, kmax=1.0, num_k=11, lib=lib)
+    y, k, p = evolve_perturbations_sharded(param=p, aexp_out=[0.5, 1.0], kmin=1e-3, kmax=1.0, num_k=11, lib=lib, rank=rank, world=world,
+                                           allgather=_gloo_allgather)
     q.put((rank, y, k, p["nout"]))
     dist.barrier()
     dist.destroy_process_group()
+
+
+def test_package_does_not_import_torch():
+    """north_star excludes PyTorch from the product: the package must import and shard without it."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); import discoeb_b200.distributed, discoeb_b200.perturbations, discoeb_b200.background; "
+            "assert 'torch' not in sys.modules, 'torch imported by the package'" % os.path.join(helpers.ROOT, "disco-eb_b200"))
+    subprocess.check_call([sys.executable, "-c", code])
+
+
+def test_empty_share_and_more_ranks_than_modes(emu_lib):
+    """world > num_k leaves ranks without modes: they contribute padding and nobody hangs or fails."""
+    from discoeb_b200.distributed import evolve_perturbations_sharded
+    p = helpers.load_tables("fiducial").param()
+    world = 4
+    bufs = {}
+
+    def fake_gather_factory(rank):
+        def g(buf):
+            return [bufs[r] for r in range(world)]
+        return g
+    # first pass: collect every rank's buffer by running the local part with a recording gather
+    from discoeb_b200 import distributed as D
+    for r in range(world):
+        rec = {}
+        def rec_gather(buf, r=r, rec=rec):
+            rec["buf"] = buf.copy()
+            raise KeyboardInterrupt          # stop after the local part
+        try:
+            evolve_perturbations_sharded(param=dict(p), aexp_out=[1.0], kmin=1e-3, kmax=1e-2, num_k=3, lib=emu_lib, rank=r, world=world, allgather=rec_gather)
+        except KeyboardInterrupt:
+            pass
+        bufs[r] = rec["buf"]
+    y, k, _ = evolve_perturbations_sharded(param=dict(p), aexp_out=[1.0], kmin=1e-3, kmax=1e-2, num_k=3, lib=emu_lib, rank=3, world=world,
+                                           allgather=fake_gather_factory(3))
+    ref, _, _ = evolve_perturbations_sharded(param=dict(p), aexp_out=[1.0], kmin=1e-3, kmax=1e-2, num_k=3, lib=emu_lib)
+    assert np.array_equal(y, ref)
 
 
 def test_partition_and_merge_roundtrip():
@@ -90,7 +139,8 @@ def _worker_jvp(rank, world, port, emu_path, q):
     case = pc.load_tangent_case("default_n72")
     p = helpers.Tables(case["scalars"], case["tables"], case["nth"], case["nnu"]).param()
     dps = [helpers.Tables(case["d_scalars"][d], case["d_tables"][d], case["nth"], case["nnu"]).param() for d in range(2)]
-    y, dy, pk, dpk, k = evolve_perturbations_jvp_sharded(param=p, dparam=dps, aexp_out=[0.5, 1.0], kmin=1e-3, kmax=0.3, num_k=7, lib=lib)
+    y, dy, pk, dpk, k = evolve_perturbations_jvp_sharded(param=p, dparam=dps, aexp_out=[0.5, 1.0], kmin=1e-3, kmax=0.3, num_k=7, lib=lib,
+                                                         rank=rank, world=world, allgather=_gloo_allgather)
     q.put((rank, y, dy, pk, dpk, k))
     dist.barrier()
     dist.destroy_process_group()
