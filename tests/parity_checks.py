@@ -33,9 +33,16 @@ def dims_for(case, tab, nk, nout, **kw):
                            nth=tab.nth, nnu=tab.nnu, max_steps=kw.pop("max_steps", 4096), **kw)
 
 
+def case_tables(case, tables):
+    """Packed tables of a case: the named committed set, or the set stored in the fixture itself (config-4 draws)."""
+    if "scalars" in case and "tables" in case:
+        return helpers.Tables(case["scalars"], case["tables"], int(case["nth"]), int(case["nnu"]))
+    return tables[str(case["cosmology"])]
+
+
 def check_prologue(lib, tables, name):
     case = helpers.load_case(name)
-    tab = tables[str(case["cosmology"])]
+    tab = case_tables(case, tables)
     ks, aout = case["kmodes"], case["aexp_out"]
     dims = dims_for(case, tab, len(ks), len(aout))
     ts, y0 = lib.debug_ics(dims, tab.scalars, tab.tables, ks, aout)
@@ -45,7 +52,7 @@ def check_prologue(lib, tables, name):
 
 def check_single_step(lib, tables, name, seed=0):
     case = helpers.load_case(name)
-    tab = tables[str(case["cosmology"])]
+    tab = case_tables(case, tables)
     p = tab.param()
     d = O.Dims(*(int(v) for v in case["dims"]))
     M = 6
@@ -66,7 +73,7 @@ def check_single_step(lib, tables, name, seed=0):
 
 def check_replay(lib, tables, name, tol=1e-6):
     case = helpers.load_case(name)
-    tab = tables[str(case["cosmology"])]
+    tab = case_tables(case, tables)
     ks, aout = case["kmodes"], case["aexp_out"]
     ctrl = _cabi.make_ctrl(rtol=float(case["rtol"]), atol=float(case["rtol"]))
     for full in (False, True):
@@ -82,7 +89,7 @@ def check_reference_step(lib, tables, name):
     """One Rodas5 step of the kernel against what the REFERENCE's own ``Rodas5Transformed.step`` returned for the same
     (t0, t1, y0) -- ref_<case>.npz: step_* (jacfwd Jacobian + LAPACK LU under tools/refshim).  Bars as check_single_step."""
     case = helpers.load_case(name)
-    tab = tables[str(case["cosmology"])]
+    tab = case_tables(case, tables)
     ks = case["kmodes"]
     dims = dims_for(case, tab, len(ks), 1)
     y1, err = lib.debug_step(dims, tab.scalars, tab.tables, ks, case["step_t0"], case["step_t1"], case["rhs_state"])
@@ -92,9 +99,64 @@ def check_reference_step(lib, tables, name):
     assert (np.abs(err - case["step_err"]) / sce).max() < 1e-5
 
 
+def check_convergence(lib, tables, rtols=(1e-4, 1e-5), tight=1e-7):
+    """VERDICT r1 item 1(b).  Truth = the oracle at rtol = atol = 1e-8 on 32 modes of BASELINE config 2 (n = 265, k up to
+    10/Mpc; tests/golden/oracle_converge_n265.npz).  At every working tolerance the kernel's free-running error against
+    the truth must not exceed 1.5 x the oracle's own (per field, worst mode; + 1e-7 floor) on the metric and matter
+    fields 0-11 -- what the error norm controls (a, eta, delta_c, delta_b, theta_b, delta_gamma: perturbations.py:759)
+    and what get_power reads -- and 3 x on the radiation / neutrino / dark-energy fields 12-19, which the norm does not
+    see and whose z = 0 values at large k are tolerance-level noise in BOTH solvers (measured at rtol 1e-4: delta_m
+    1.07e-4 kernel vs 1.08e-4 oracle; theta_gamma 3.8e-4 vs 2.2e-4; delta_gamma 0.49 vs 0.49 of its scale).  So the
+    differences between kernel and oracle at rtol = 1e-4 are the SOLVER's tolerance-level error, present in the
+    reference algorithm itself, not a defect of the structured solve.  At rtol = 1e-7 kernel and oracle agree to 1e-5 on
+    the controlled fields (measured 7e-7 vs truth)."""
+    import os
+    z = np.load(os.path.join(helpers.GOLD, "oracle_converge_n265.npz"))
+    case = {k: z[k] for k in z.files}
+    tab = tables[str(case["cosmology"])]
+    ks, aout = case["kmodes"], case["aexp_out"]
+    truth = case["y_1e-08"]
+    dims = dims_for(case, tab, len(ks), len(aout), max_steps=32768)
+    report = {}
+    for rt in tuple(rtols) + (tight,):
+        ctrl = _cabi.make_ctrl(rtol=rt, atol=rt)
+        out = lib.evolve_host(dims, ctrl, tab.scalars[None], tab.tables[None], ks, aout)
+        assert np.all(out["status"] == 0)
+        y, yo = out["y"][0], case[f"y_{rt:g}"]
+        ek = np.array([helpers.field_scaled_diff(y[m], truth[m]) for m in range(len(ks))]).max(axis=0)
+        eo = np.array([helpers.field_scaled_diff(yo[m], truth[m]) for m in range(len(ks))]).max(axis=0)
+        eko = np.array([helpers.field_scaled_diff(y[m], yo[m]) for m in range(len(ks))]).max(axis=0)
+        report[rt] = dict(delta_m_kernel_vs_truth=float(ek[4]), delta_m_oracle_vs_truth=float(eo[4]), kernel_vs_oracle_controlled=float(eko[:12].max()))
+        if rt == tight:
+            assert eko[:12].max() < 1e-5, (rt, eko)
+        else:
+            assert np.all(ek[:12] <= 1.5 * eo[:12] + 1e-7), (rt, ek, eo)
+            assert np.all(ek[12:] <= 3.0 * eo[12:] + 1e-7), (rt, ek, eo)
+    return report
+
+
+def check_full_grid_parity(lib, tables, bar=1e-5):
+    """All 512 modes of the bench workload (BASELINE config 2) against the oracle's committed P(k) and fields
+    (tests/golden/oracle_config2_full512.npz): fraction of modes within `bar`, worst deviation, and the 50 rtol
+    envelope every mode must satisfy (free-running solves: see check_adaptive)."""
+    case = helpers.load_case("config2_full512")
+    tab = tables["fiducial"]
+    ks, aout, rtol = case["kmodes"], case["aexp_out"], float(case["rtol"])
+    dims = dims_for(case, tab, len(ks), len(aout), max_steps=2048, power_idx=4)
+    ctrl = _cabi.make_ctrl(rtol=rtol, atol=rtol)
+    out = lib.evolve_host(dims, ctrl, tab.scalars[None], tab.tables[None], ks, aout, want_pk=True)
+    assert np.all(out["status"] == 0)
+    rel = np.abs(out["pk"][0, :, 0] / case["pk4"][:, 0] - 1)
+    same = out["nsteps"][0] == case["nsteps"]
+    assert rel.max() < 2 * 50 * rtol                     # P ~ delta^2
+    assert rel[same & (case["nsteps"] <= 100)].max() < 2e-5
+    return dict(frac_within_bar=float((rel < bar).mean()), max_rel=float(rel.max()), median_rel=float(np.median(rel)),
+                same_step_counts=float(same.mean()))
+
+
 def check_adaptive(lib, tables, name):
     case = helpers.load_case(name)
-    tab = tables[str(case["cosmology"])]
+    tab = case_tables(case, tables)
     ks, aout, rtol = case["kmodes"], case["aexp_out"], float(case["rtol"])
     dims = dims_for(case, tab, len(ks), len(aout))
     ctrl = _cabi.make_ctrl(rtol=rtol, atol=rtol)
@@ -306,7 +368,7 @@ BATCHED_CASES = ("batched_n72", "batched_lowk_n72", "batched_n265")
 def check_batched_replay(lib, tables, name, tol=1e-6):
     """Shared start time + the oracle's shared step sequence: whole trajectories at round-off level."""
     case = helpers.load_case(name)
-    tab = tables[str(case["cosmology"])]
+    tab = case_tables(case, tables)
     ks, aout, B = case["kmodes"], case["aexp_out"], int(case["batch_size"])
     ctrl = _cabi.make_ctrl(rtol=float(case["rtol"]), atol=float(case["rtol"]))
     for full in (False, True):
@@ -322,7 +384,7 @@ def check_batched_adaptive(lib, tables, name):
     """Free-running: every mode of a batch reports the same step counts; batches of at most 100 steps must reproduce
     the oracle's counts and agree to 1e-5, longer ones to 50 rtol on the matter fields (DESIGN.md "Parity")."""
     case = helpers.load_case(name)
-    tab = tables[str(case["cosmology"])]
+    tab = case_tables(case, tables)
     ks, aout, B, rtol = case["kmodes"], case["aexp_out"], int(case["batch_size"]), float(case["rtol"])
     dims = dims_for(case, tab, len(ks), len(aout), batch_size=B)
     out = lib.evolve_host(dims, _cabi.make_ctrl(rtol=rtol, atol=rtol), tab.scalars[None], tab.tables[None], ks, aout)

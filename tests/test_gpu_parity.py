@@ -47,6 +47,31 @@ def test_against_the_reference_itself(gpu_lib, tables, name, variant, monkeypatc
     pc.check_adaptive(gpu_lib, tables, name)
 
 
+@pytest.mark.parametrize("variant", ["default", "warp", "team", "lane"])
+@pytest.mark.parametrize("name", helpers.BASELINE_CASES)
+def test_baseline_configs_at_their_own_size(gpu_lib, tables, name, variant, monkeypatch):
+    """BASELINE config 2 (every 8th of the 512 modes: 64 modes, k up to 10/Mpc, the ~600-step modes
+    included), config 3 (w0wa, 32 modes of the 4096-mode grid), config 4 (three default_rng(0) cosmologies x 16 k on the
+    REFERENCE's own evolve_background tables), all at n = 265: replay of the oracle's step sequence at 1e-6 on the 20
+    fields and the raw state, then the free-running solve, for every kernel variant."""
+    if variant != "default":
+        monkeypatch.setenv("DEB_VARIANT", variant)
+    pc.check_replay(gpu_lib, tables, name)
+    pc.check_adaptive(gpu_lib, tables, name)
+
+
+@pytest.mark.parametrize("variant", ["default", "lane"])
+def test_full_grid_parity_and_convergence(gpu_lib, tables, variant, monkeypatch):
+    """All 512 modes of the bench workload against the oracle's committed P(k) (what the bench line's `parity` block
+    reports), and the rtol ladder against the oracle's rtol = 1e-8 truth."""
+    if variant != "default":
+        monkeypatch.setenv("DEB_VARIANT", variant)
+    rep = pc.check_full_grid_parity(gpu_lib, tables)
+    assert rep["frac_within_bar"] > 0.9, rep
+    conv = pc.check_convergence(gpu_lib, tables)
+    print(variant, "full grid:", rep, "convergence:", conv)
+
+
 @pytest.mark.parametrize("variant", ["warp", "team", "lane"])
 @pytest.mark.parametrize("name", helpers.CASES)
 def test_forced_kernel_variants(gpu_lib, tables, name, variant, monkeypatch):

@@ -30,6 +30,25 @@ def test_adaptive_solve_against_oracle(emu_lib, tables, name):
     pc.check_adaptive(emu_lib, tables, name)
 
 
+@pytest.mark.parametrize("variant", ["cyclic", "lane"])
+@pytest.mark.parametrize("name", helpers.BASELINE_CASES)
+def test_baseline_configs_replay_and_adaptive(emu_lib, tables, name, variant, monkeypatch):
+    """BASELINE configs 2 (64 modes, k up to 10/Mpc, the ~600-step modes included), 3 (w0wa, 32 modes) and 4 (three
+    default_rng(0) cosmologies x 16 k on the reference's own evolve_background tables) at n = 265: replay of the
+    oracle's step sequence at 1e-6 on all 20 fields and the raw state, and the free-running solve."""
+    if variant == "lane":
+        monkeypatch.setenv("DEB_EMU_LANE", "1")
+    pc.check_replay(emu_lib, tables, name)
+    pc.check_adaptive(emu_lib, tables, name)
+
+
+def test_full_grid_parity_and_convergence_through_kernel_source(emu_lib, tables):
+    rep = pc.check_full_grid_parity(emu_lib, tables)
+    assert rep["frac_within_bar"] > 0.5
+    conv = pc.check_convergence(emu_lib, tables)
+    print("full grid", rep, "convergence (kernel-truth, oracle-truth, kernel-oracle):", conv)
+
+
 def test_class_golden_curve_through_kernel_source(emu_lib, tables):
     """The reference's own acceptance test (tests/test_perturbations.py:95-109): P_bc(k) at z=99,
     lmax=31, nq=5, 512 modes, rtol=atol=1e-4, linearly interpolated onto the CLASS k grid, within

@@ -101,3 +101,18 @@ def test_oracle_against_class_golden_curve(tables):
     bao = (kc[m] > 0.03) & (kc[m] < 0.6)
     assert rel[~bao].max() < 0.005
     assert rel[bao].max() < 0.025
+
+
+def test_oracle_full_class_grid_linear_interpolation():
+    """the oracle on the reference's full 512-mode acceptance grid (z = 99, k in [1e-5, 10]/Mpc,
+    lmax = 31, nq = 5, rtol = atol = 1e-4; committed by tools/make_golden_baseline.py), interpolated LINEARLY onto the
+    CLASS k grid as the reference's test does (tests/test_perturbations.py:107-109), within 0.5 % over the whole range."""
+    import json
+    import os
+    import helpers
+    z = np.load(os.path.join(helpers.GOLD, "oracle_class_grid512.npz"))
+    g = json.load(open(os.path.join(helpers.GOLD, "CLASS_data.json")))
+    kc, Pc = np.array(g["k"]), np.array(g["Pkbc"])
+    m = (kc >= 1e-5) & (kc <= 10.0)
+    rel = np.abs(np.interp(kc[m], z["kmodes"], z["pk6"][:, 0]) / Pc[m] - 1)
+    assert rel.max() < 0.005, rel.max()
