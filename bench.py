@@ -9,9 +9,11 @@ to the 20 output fields + P(k).  Inputs are the committed fiducial tables (tests
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-N>1 is launched by torchrun (one rank per GPU): every rank integrates its own 512-mode batch
-(weak scaling: independent cosmologies, no data-path collective) and the transfer functions are
-all-gathered over NCCL at the end of each step, inside the timed region.
+N>1 is launched by torchrun (one rank per GPU): the step integrates ONE k grid of 512 x N modes over the same k range,
+dealt round-robin over the ranks (512 modes per GPU: weak scaling, no data-path collective during the solve), and the
+library's own multi-GPU entry (deb_evolve_sharded_f64: ncclAllGather on the device) leaves the full result on every
+rank inside the timed region.  Sub-records (key `sub`) time BASELINE config 3 (4096 modes dealt over the N ranks: strong
+scaling) and config 4 (128 default_rng(0) cosmologies x 256 k per GPU, tables produced on the GPU first).
 
 `value`   : k-modes/s, whole job, inputs resident in HBM, CUDA-event time of the step (max over ranks).
 `e2e`     : same metric through the host C-ABI entry (deb_evolve_host_f64) with HOST buffers:
@@ -21,7 +23,11 @@ all-gathered over NCCL at the end of each step, inside the timed region.
             over the kernel's CUDA-event time, against the DFMA peak measured on this GPU by
             deb_fp64_peak_tflops (MEASURED_PEAKS.json holds no FP64 figure).
 `cpu_baseline`: the restated reference (NumPy/LAPACK oracle, dense Jacobian + dense LU, lock-step
-            over modes like the reference's vmap) on the host cores, on a bounded sub-sample.
+            over modes like the reference's vmap) on the host cores, on a bounded sub-sample; `cpu_structured` next to
+            it = the kernel SOURCE compiled for the host (tests/emu, OpenMP, all cores) on all 512 modes: what the same
+            structured algorithm does on the CPU, i.e. what the B200 buys.
+`parity`  : the timed step's own P(k) against the oracle's committed vector for all 512 modes
+            (tests/golden/oracle_config2_full512.npz): fraction within 1e-5 and the worst deviation.
 """
 import argparse
 import json
@@ -77,10 +83,11 @@ def load_tables():
 # CPU arm: the restated reference on the host cores
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_pass(tab, stride):
-    """One bounded pass: every `stride`-th mode of the workload through the NumPy oracle."""
+    """One bounded pass: every `stride`-th mode of the workload through the NumPy oracle, ALL of them in one
+    lock-step chunk (the way jax.vmap advances the reference's modes, perturbations.py:980-987)."""
     import oracle.discoeb_oracle as O
     p = tab.param()
-    ks = np.geomspace(WORKLOAD["kmin"], WORKLOAD["kmax"], WORKLOAD["nk"])[stride // 2::stride]
+    ks = np.geomspace(WORKLOAD["kmin"], WORKLOAD["kmax"], WORKLOAD["nk"])[stride - 1::stride]
     lg, lp, lr, ln, nq = WORKLOAD["dims"]
     t = time.perf_counter()
     y, k, _, info = O.evolve_perturbations(param=p, aexp_out=WORKLOAD["aexp_out"], kmin=0, kmax=0, num_k=len(ks), kmodes=ks,
@@ -91,11 +98,37 @@ def cpu_reference_pass(tab, stride):
     return len(ks), dt, int(info["nsteps"].sum())
 
 
+def cpu_structured_pass(tab):
+    """The kernel source compiled for the host (tests/emu/_build/libdeb_emu.so, OpenMP over modes) on the whole workload."""
+    from discoeb_b200 import _cabi
+    path = os.path.join(ROOT, "tests", "emu", "_build", "libdeb_emu.so")
+    if not os.path.exists(path):
+        return None
+    lib = _cabi.Library(path, prefix="emu_")
+    lg, lp, lr, ln, nq = WORKLOAD["dims"]
+    ks = np.geomspace(WORKLOAD["kmin"], WORKLOAD["kmax"], WORKLOAD["nk"])
+    dims = _cabi.make_dims(ncosmo=1, nk=len(ks), nout=1, lmaxg=lg, lmaxgp=lp, lmaxr=lr, lmaxnu=ln, nqmax=nq, nth=tab.nth, nnu=tab.nnu,
+                           max_steps=WORKLOAD["max_steps"], power_idx=4)
+    ctrl = _cabi.make_ctrl(rtol=WORKLOAD["rtol"], atol=WORKLOAD["rtol"])
+    best = 1e9
+    for _ in range(3):
+        t = time.perf_counter()
+        lib.evolve_host(dims, ctrl, tab.scalars[None], tab.tables[None], ks, np.asarray(WORKLOAD["aexp_out"]), want_pk=True)
+        best = min(best, time.perf_counter() - t)
+    return dict(value=len(ks) / best, unit="k-modes/s", cores=os.cpu_count(), kind="kernel source compiled for the host (tests/emu), OpenMP over modes",
+                sample=f"all {len(ks)} modes of the workload, best of 3 ({best * 1e3:.0f} ms per pass)")
+
+
 def run_reference(args, rank):
+    """Reference arm: the restated reference on the host cores.  A step = one lock-step pass over a bounded sample of
+    the workload; the sample is the largest of 64 / 32 / 16 modes that keeps warm-up + K steps within ~5 minutes
+    (calibrated on a first 16-mode pass; the oracle is LAPACK-bound, so modes/s barely moves with the sample)."""
     if rank != 0:
         return
     tab = load_tables()
-    stride = 128
+    m, dt, _ = cpu_reference_pass(tab, 32)
+    budget = 300.0 / max(1, args.warmup + args.steps)
+    stride = 8 if 4.5 * dt < budget else (16 if 2.2 * dt < budget else 32)
     times, modes = [], 0
     for i in range(args.warmup + args.steps):
         m, dt, st = cpu_reference_pass(tab, stride)
@@ -104,7 +137,7 @@ def run_reference(args, rank):
             modes = m
     ms = 1e3 * float(np.mean(times))
     value = modes / (ms * 1e-3)
-    sample = (f"every {stride}th mode of the 512-mode workload ({modes} modes, log-spaced over the full k range) per step; "
+    sample = (f"every {stride}th mode of the 512-mode workload ({modes} modes, log-spaced over the full k range, ONE lock-step chunk) per step; "
               "restated-reference CPU (NumPy oracle: dense Jacobian + LAPACK getrf/getrs, lock-step over modes), not JAX: "
               "jax/diffrax are not installable here")
     line = dict(impl="reference", metric=METRIC, value=value, unit="k-modes/s", n_gpus=args.gpus, steps=args.steps,
@@ -112,6 +145,9 @@ def run_reference(args, rank):
                 data="synthetic", config=dict(workload=WORKLOAD["name"], sample=sample),
                 cpu_baseline=dict(value=value, unit="k-modes/s", cores=os.cpu_count(), kind="port", sample=sample),
                 e2e=dict(value=value, unit="k-modes/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    cs = cpu_structured_pass(tab)
+    if cs:
+        line["cpu_structured"] = cs
     print(json.dumps(line))
 
 
@@ -170,116 +206,242 @@ def run_ours(args, rank, world):
     import torch
     import torch.distributed as dist
     from discoeb_b200 import _cabi
+    from discoeb_b200.background import config4_draws, pack_background_input
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    lib = _cabi.default_library()
+    L = lib.lib
+    comm = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    lib = _cabi.default_library()
+        from discoeb_b200.distributed import NativeComm
+
+        def bcast(payload):
+            box = [payload]
+            dist.broadcast_object_list(box, src=0)
+            return box[0]
+        comm = NativeComm(world, rank, bcast, device=local, lib=lib)      # the library's own NCCL communicator
+    L.deb_sharded_workspace_bytes.restype = C.c_size_t
+    L.deb_sharded_workspace_bytes.argtypes = [C.POINTER(_cabi.DebDims), C.c_int32]
+    L.deb_evolve_sharded_f64.restype = C.c_int
+    L.deb_evolve_sharded_f64.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(_cabi.DebDims), C.POINTER(_cabi.DebCtrl)] + [C.c_void_p] * 9 + \
+        [C.c_void_p, C.c_size_t, C.c_int32] + [C.c_void_p] * 4 + [C.c_void_p]
+    L.deb_background_f64.restype = C.c_int
+    L.deb_background_f64.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.deb_background_workspace_bytes.restype = C.c_size_t
+    L.deb_background_workspace_bytes.argtypes = [C.c_int32, C.c_int32]
     tab = load_tables()
     lg, lp, lr, ln, nq = WORKLOAD["dims"]
-    nk, nout = WORKLOAD["nk"], len(WORKLOAD["aexp_out"])
+    nk1, nout = WORKLOAD["nk"], len(WORKLOAD["aexp_out"])
     n = lib.nvar(lg, lp, lr, ln, nq)
-    ks = np.geomspace(WORKLOAD["kmin"], WORKLOAD["kmax"], nk)
-    # weak scaling: every rank owns one cosmology's 512 modes.  Ranks > 0 perturb n_s/A_s only
-    # (post-processing scalars), so all ranks do the same amount of work on distinct inputs.
-    scal = tab.scalars.copy()
-    scal[16] *= 1.0 + 0.01 * rank
-    dims = _cabi.make_dims(ncosmo=1, nk=nk, nout=nout, lmaxg=lg, lmaxgp=lp, lmaxr=lr, lmaxnu=ln, nqmax=nq, nth=tab.nth,
-                           nnu=tab.nnu, max_steps=WORKLOAD["max_steps"], power_idx=4)
-    ctrl = _cabi.make_ctrl(rtol=WORKLOAD["rtol"], atol=WORKLOAD["rtol"])
     f64 = dict(dtype=torch.float64, device=dev)
-    d_sc = torch.from_numpy(scal[None]).to(dev)
-    d_tb = torch.from_numpy(tab.tables[None].copy()).to(dev)
-    d_k = torch.from_numpy(ks).to(dev)
-    d_a = torch.tensor(WORKLOAD["aexp_out"], **f64)
-    d_y = torch.zeros((1, nk, nout, 20), **f64)
-    d_pk = torch.zeros((1, nk, nout), **f64)
-    d_tau = torch.zeros((1, nout), **f64)
-    d_st = torch.zeros((1, nk), dtype=torch.int32, device=dev)
-    d_ns = torch.zeros((1, nk), dtype=torch.int32, device=dev)
-    d_na = torch.zeros((1, nk), dtype=torch.int32, device=dev)
-    d_ws = torch.zeros(1024, dtype=torch.int32, device=dev)       # >= deb_workspace_bytes(dims) = 256 + 8 ncosmo
-    gathered = torch.zeros((world, nk, nout, 20), **f64) if world > 1 else None
+    i32 = dict(dtype=torch.int32, device=dev)
+    ctrl = _cabi.make_ctrl(rtol=WORKLOAD["rtol"], atol=WORKLOAD["rtol"])
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)      # > 126 MB L2
-
-    def device_step():
-        st = torch.cuda.current_stream().cuda_stream
-        rc = lib.lib.deb_evolve_f64(C.byref(dims), C.byref(ctrl), d_sc.data_ptr(), d_tb.data_ptr(), d_k.data_ptr(), d_a.data_ptr(),
-                                    d_y.data_ptr(), d_pk.data_ptr(), d_tau.data_ptr(), d_st.data_ptr(), d_ns.data_ptr(),
-                                    d_na.data_ptr(), d_ws.data_ptr(), C.c_size_t(4096), C.c_void_p(st))
-        if rc != 0:
-            raise RuntimeError(lib.strerror(rc))
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, d_y[0])
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        device_step()
-    barrier()
-    assert int(d_st.abs().max().item()) == 0, "some modes did not complete"
-    total_steps = int(d_ns.sum().item())
+    class Sharded:
+        """One k grid of nk modes (ncosmo cosmologies) dealt over the ranks through deb_evolve_sharded_f64 (gather = 0)."""
+
+        def __init__(self, scal, tabs, nk, max_steps):
+            self.nc, self.nk = scal.shape[0], nk
+            self.ks = np.geomspace(WORKLOAD["kmin"], WORKLOAD["kmax"], nk)
+            self.dims = _cabi.make_dims(ncosmo=self.nc, nk=nk, nout=nout, lmaxg=lg, lmaxgp=lp, lmaxr=lr, lmaxnu=ln, nqmax=nq, nth=tab.nth,
+                                        nnu=tab.nnu, max_steps=max_steps, power_idx=4)
+            self.d_sc = scal if torch.is_tensor(scal) else torch.from_numpy(np.ascontiguousarray(scal)).to(dev)
+            self.d_tb = tabs if torch.is_tensor(tabs) else torch.from_numpy(np.ascontiguousarray(tabs)).to(dev)
+            self.d_k = torch.from_numpy(self.ks).to(dev)
+            self.d_a = torch.tensor(WORKLOAD["aexp_out"], **f64)
+            self.d_y = torch.zeros((self.nc, nk, nout, 20), **f64); self.d_pk = torch.zeros((self.nc, nk, nout), **f64)
+            self.d_tau = torch.zeros((self.nc, nout), **f64)
+            self.d_st = torch.zeros((self.nc, nk), **i32); self.d_ns = torch.zeros((self.nc, nk), **i32)
+            self.wsb = L.deb_sharded_workspace_bytes(C.byref(self.dims), world)
+            self.d_ws = torch.zeros(self.wsb // 8 + 8, **f64)
+
+        def step(self):
+            rc = L.deb_evolve_sharded_f64(comm.handle if comm else None, world, rank, C.byref(self.dims), C.byref(ctrl), self.d_sc.data_ptr(),
+                                          self.d_tb.data_ptr(), self.d_k.data_ptr(), self.d_a.data_ptr(), self.d_y.data_ptr(), self.d_pk.data_ptr(),
+                                          self.d_tau.data_ptr(), self.d_st.data_ptr(), self.d_ns.data_ptr(), self.d_ws.data_ptr(), C.c_size_t(self.wsb),
+                                          0, None, None, None, None, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+            if rc != 0:
+                raise RuntimeError(lib.strerror(rc))
+
+        def timed(self, steps, warmup):
+            for _ in range(warmup):
+                self.step()
+            barrier()
+            assert int(self.d_st.abs().max().item()) == 0, "some modes did not complete"
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+            barrier()
+            for e0, e1 in ev:
+                flush.fill_(1.0)                   # L2 flush between timed iterations (outside the event pair)
+                e0.record(); self.step(); e1.record()
+            barrier()
+            ms = sum(e0.elapsed_time(e1) for e0, e1 in ev) / steps
+            if world > 1:
+                t = torch.tensor([ms], **f64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t[0])
+            return ms
+
+    # ---------------- headline: 512 modes per GPU (one k grid of 512 x N modes dealt over the ranks) ----------------
+    head = Sharded(tab.scalars[None], tab.tables[None], nk1 * world, WORKLOAD["max_steps"])
     sampler = ClockSampler(local)
+    for _ in range(max(args.warmup, 3)):
+        head.step()
+    barrier()
     if rank == 0:
         sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    t_wall = time.perf_counter()
-    for e0, e1 in ev:
-        flush.fill_(1.0)                       # L2 flush between timed iterations (outside the event pair)
-        e0.record()
-        device_step()
-        e1.record()
-    barrier()
-    t_wall = time.perf_counter() - t_wall
-    ms_dev = sum(e0.elapsed_time(e1) for e0, e1 in ev) / args.steps
-    # e2e through the host C-ABI entry (host buffers, copies inside the timed region)
-    h_y = np.zeros((1, nk, nout, 20))
+    ms_dev = head.timed(args.steps, 0)
+    total_steps = int(head.d_ns.sum().item())
+    # parity of the timed step's own output (N = 1: the 512-mode grid the committed oracle vector is on)
+    parity = None
+    if world == 1:
+        try:
+            import helpers
+            ora = helpers.load_case("config2_full512")
+            rel = np.abs(head.d_pk[0, :, 0].cpu().numpy() / ora["pk4"][:, 0] - 1)
+            parity = dict(against="NumPy oracle, all 512 modes, tests/golden/oracle_config2_full512.npz (P(k) of delta_m at z=0)",
+                          frac_within_1e5=float((rel < 1e-5).mean()), max_rel=float(rel.max()), median_rel=float(np.median(rel)),
+                          same_step_counts=float((head.d_ns[0].cpu().numpy() == ora["nsteps"]).mean()),
+                          note="free-running adaptive solves at rtol=1e-4: modes whose accept/reject sequence differs from the oracle's "
+                               "differ by the solver's own tolerance-level error (tests/parity_checks.py: check_convergence); replay "
+                               "along the reference's step sequence agrees to <= 2e-8 (tests/test_gpu_parity.py)")
+        except Exception as e:      # noqa: BLE001
+            parity = dict(error=repr(e)[:200])
+    # e2e through the host C-ABI entry (host buffers, copies -- and at N > 1 the NCCL gather -- inside the timed region)
+    ks_all = head.ks
     e2e_ms = []
     for i in range(2 + args.steps):
+        barrier()
         t = time.perf_counter()
-        out = lib.evolve_host(dims, ctrl, scal[None], tab.tables[None], ks, np.asarray(WORKLOAD["aexp_out"]), device=local, want_pk=True)
+        if world == 1:
+            out = lib.evolve_host(head.dims, ctrl, tab.scalars[None], tab.tables[None], ks_all, np.asarray(WORKLOAD["aexp_out"]), device=local, want_pk=True)
+        else:
+            out = lib.evolve_sharded_host(comm, head.dims, ctrl, tab.scalars[None], tab.tables[None], ks_all, np.asarray(WORKLOAD["aexp_out"]), want_pk=True)
         if i >= 2:
             e2e_ms.append(1e3 * (time.perf_counter() - t))
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     e2e = float(np.mean(e2e_ms))
-    h2d = scal.nbytes + tab.tables.nbytes + ks.nbytes + 8 * nout
-    d2h = h_y.nbytes + 8 * nk * nout + 8 * nout + 3 * 4 * nk
     if world > 1:
-        t = torch.tensor([ms_dev, e2e], **f64)
+        t = torch.tensor([e2e], **f64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_dev, e2e = float(t[0]), float(t[1])
+        e2e = float(t[0])
+    nk_tot = nk1 * world
+    h2d = tab.scalars.nbytes + tab.tables.nbytes + ks_all.nbytes + 8 * nout
+    d2h = nk_tot * nout * 20 * 8 + 8 * nk_tot * nout + 8 * nout + 2 * 4 * nk_tot
+
+    # ---------------- sub-records: BASELINE config 3 (strong scaling) and config 4 (cosmology batch) ----------------
+    sub = {}
+    if not args.no_sub:
+        import helpers
+        w0 = helpers.load_tables("w0wa")
+        c3 = Sharded(w0.scalars[None], w0.tables[None], 4096, 4096)
+        ms3 = c3.timed(3, 2)
+        sub["config3_strong"] = dict(workload="w0wa + massive nu, n=265, 4096 k dealt round-robin over the ranks, all-gather by the library",
+                                     modes=4096, ms_per_step=ms3, value=4096 / (ms3 * 1e-3), unit="k-modes/s", scaling="strong",
+                                     attempted_steps=int(c3.d_ns.sum().item()))
+        del c3
+        # config 4: every rank owns 128 of the 1024 default_rng(0) cosmologies x 256 k; tables produced on the GPU first
+        ncs = 128
+        base = dict(Omegam=0.3099, Omegab=0.0488911, w_DE_0=-0.99, w_DE_a=0.0, cs2_DE=1.0, Omegak=0.0, A_s=2.1064e-09, n_s=0.96822,
+                    H0=67.742, Tcmb=2.7255, YHe=0.248, Neff=2.046, Nmnu=1, mnu=0.06, k_p=0.05)
+        draws = config4_draws(1024)[rank * ncs:(rank + 1) * ncs]
+        d_in = torch.from_numpy(np.stack([pack_background_input({**base, **d}) for d in draws])).to(dev)
+        tl = 3 * (5 * 256 + 2 * 512)
+        d_sc4 = torch.zeros((ncs, 24), **f64); d_tb4 = torch.zeros((ncs, tl), **f64)
+        bws = L.deb_background_workspace_bytes(ncs, 256)
+        d_bws = torch.zeros(bws // 8 + 8, **f64)
+        tb_ms = []
+        for i in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = L.deb_background_f64(ncs, 256, d_in.data_ptr(), d_sc4.data_ptr(), d_tb4.data_ptr(), d_bws.data_ptr(), C.c_size_t(bws),
+                                      C.c_void_p(torch.cuda.current_stream().cuda_stream))
+            e1.record(); torch.cuda.synchronize()
+            assert rc == 0, lib.strerror(rc)
+            tb_ms.append(e0.elapsed_time(e1))
+        # solve: local cosmologies only (cosmology batches shard contiguously, no gather needed beyond concatenation)
+        ks4 = np.geomspace(WORKLOAD["kmin"], WORKLOAD["kmax"], 256)
+        dims4 = _cabi.make_dims(ncosmo=ncs, nk=256, nout=nout, lmaxg=lg, lmaxgp=lp, lmaxr=lr, lmaxnu=ln, nqmax=nq, nth=256, nnu=512, max_steps=4096, power_idx=4)
+        d_k4 = torch.from_numpy(ks4).to(dev); d_a4 = torch.tensor(WORKLOAD["aexp_out"], **f64)
+        d_y4 = torch.zeros((ncs, 256, nout, 20), **f64); d_pk4 = torch.zeros((ncs, 256, nout), **f64); d_tau4 = torch.zeros((ncs, nout), **f64)
+        d_st4 = torch.zeros((ncs, 256), **i32); d_ns4 = torch.zeros((ncs, 256), **i32); d_na4 = torch.zeros((ncs, 256), **i32)
+        L.deb_workspace_bytes.restype = C.c_size_t
+        wsb4 = L.deb_workspace_bytes(C.byref(dims4))
+        d_ws4 = torch.zeros(wsb4 // 8 + 8, **f64)
+        sv_ms = []
+        for i in range(3):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = L.deb_evolve_f64(C.byref(dims4), C.byref(ctrl), d_sc4.data_ptr(), d_tb4.data_ptr(), d_k4.data_ptr(), d_a4.data_ptr(), d_y4.data_ptr(),
+                                  d_pk4.data_ptr(), d_tau4.data_ptr(), d_st4.data_ptr(), d_ns4.data_ptr(), d_na4.data_ptr(), d_ws4.data_ptr(),
+                                  C.c_size_t(wsb4), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+            e1.record(); torch.cuda.synchronize()
+            assert rc == 0, lib.strerror(rc)
+            if i > 0:
+                sv_ms.append(e0.elapsed_time(e1))
+        ok4 = int(d_st4.abs().max().item()) == 0
+        t4 = torch.tensor([min(sv_ms), min(tb_ms[1:]), float(d_ns4.sum().item()), 0.0 if ok4 else 1.0], **f64)
+        if world > 1:
+            tm = t4.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            ts = t4.clone(); dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+            t4 = torch.stack([tm[0], tm[1], ts[2], tm[3]])
+        modes4 = ncs * 256 * world
+        sub["config4"] = dict(workload=f"{ncs * world} numpy.random.default_rng(0) cosmologies x 256 k, n=265 ({ncs} distinct table sets per GPU, produced "
+                                       "on the GPU by deb_background_f64); cosmologies sharded contiguously",
+                              modes=modes4, solve_ms=float(t4[0]), tables_ms=float(t4[1]), value=modes4 / (float(t4[0]) * 1e-3),
+                              value_with_tables=modes4 / ((float(t4[0]) + float(t4[1])) * 1e-3), unit="k-modes/s", scaling="weak",
+                              attempted_steps=int(t4[2]), all_modes_ok=bool(float(t4[3]) == 0.0))
+
     if rank == 0:
         peak1, _ = lib.fp64_peak_tflops(local)
         peak = peak1 * world
-        flops = world * total_steps * f_step(n)          # every rank integrates the same number of steps
+        flops = total_steps * f_step(n)
         achieved = flops / (ms_dev * 1e-3) / 1e12
-        line = dict(metric=METRIC, value=world * nk / (ms_dev * 1e-3), unit="k-modes/s", n_gpus=world, steps=args.steps,
+        launches = 3 if world == 1 else 6
+        line = dict(metric=METRIC, value=nk_tot / (ms_dev * 1e-3), unit="k-modes/s", n_gpus=world, steps=args.steps,
                     warmup=max(args.warmup, 3), ms_per_step=ms_dev, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype="f64", data="synthetic",
-                    config=dict(workload=WORKLOAD["name"], modes_per_gpu=nk, attempted_steps_per_pass=total_steps,
-                                l2="flushed between timed iterations (256 MB write)", parallelism=f"k-modes x{world} (independent batches, all-gather of y)"),
+                    config=dict(workload=WORKLOAD["name"], modes_per_gpu=nk1, attempted_steps_per_pass=total_steps,
+                                l2="flushed between timed iterations (256 MB write)",
+                                parallelism=(f"one k grid of {nk_tot} modes dealt round-robin over {world} GPUs (512 per GPU), ncclAllGather by the library "
+                                             "(deb_evolve_sharded_f64)" if world > 1 else "1 GPU"),
+                                state="steady state: the caller's workspace holds the work list learned from the previous call (DESIGN.md section 3)"),
                     roofline=dict(bound="fp64", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak,
                                   traffic=ncu_dram_bytes_per_launch(), kernel="k_evolve_team<3,4,2> (one CTA of 4 warps per mode)",
                                   note="FP64 FMA pipe (the path is neither HBM- nor tensor-bound); peak measured on this GPU by "
                                        "deb_fp64_peak_tflops (dependent-free DFMA streams) x n_gpus; algorithmic flops = "
                                        "(370 n + 3000) x attempted steps, n=265; traffic = dram bytes read+written per k_evolve_team "
-                                       "launch from profiles/r1_v24_k_evolve_team_ncu_summary.txt (HBM is idle)"),
-                    e2e=dict(value=world * nk / (e2e * 1e-3), unit="k-modes/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
+                                       f"launch from {os.path.relpath(NCU_SUMMARY, ROOT)} (HBM is idle)"),
+                    e2e=dict(value=nk_tot / (e2e * 1e-3), unit="k-modes/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
                              ms_per_step=e2e),
-                    gpu_launches=3 * args.steps,  # k_tau_out, k_evolve_team, k_learn_order per pass (profiles/r1_v24_launch_list_bench.txt)
+                    gpu_launches=launches * args.steps,
+                    gpu_launches_note=("k_tau_out, k_evolve_team, k_learn_order per pass" if world == 1 else
+                                       "k_take_modes, k_tau_out, k_evolve_team, k_learn_order, k_pack_rows, k_unpack_rows per pass per rank (+ NCCL's all-gather kernel)"),
                     clocks=clocks)
+        if parity is not None:
+            line["parity"] = parity
+        if sub:
+            line["sub"] = sub
         if world == 1 and not args.no_cpu_baseline:
-            m, dt, st = cpu_reference_pass(tab, 64)
+            m, dt, st = cpu_reference_pass(tab, 32)
             line["cpu_baseline"] = dict(value=m / dt, unit="k-modes/s", cores=os.cpu_count(), kind="port",
-                                        sample=f"every 64th mode of the workload ({m} modes, {st} attempted steps) in {dt:.1f} s; NumPy oracle "
+                                        sample=f"every 32nd mode of the workload ({m} modes in one lock-step chunk, {st} attempted steps) in {dt:.1f} s; NumPy oracle "
                                                "(dense Jacobian + LAPACK LU), restated reference, not JAX")
+            cs = cpu_structured_pass(tab)
+            if cs:
+                line["cpu_structured"] = cs
         print(json.dumps(line))
+    if comm is not None:
+        comm.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -291,6 +453,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sub", action="store_true", help="skip the config-3 / config-4 sub-records")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
