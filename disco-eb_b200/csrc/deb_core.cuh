@@ -287,6 +287,7 @@ struct Problem {
   // sharded launch with peer stores (deb_evolve_sharded_peer_f64): a rank integrates every `out_mul`-th k-mode and writes
   // the 20 fields, P(k) and the status words of local mode kidx to row kidx*out_mul + out_add (of out_nk) of the FULL-SIZE
   // buffers of all npeer ranks -- its own and, through NVLink peer mappings, everybody else's: the epilogue is the gather
+  int lockstep;              // chain-lane kernel: warps of a CTA advance stage by stage together (deb_lane.cuh)
   int npeer, out_mul, out_add, out_nk;
   double* y_peer[8]; double* pk_peer[8]; int* st_peer[8]; int* ns_peer[8];
 };

@@ -33,28 +33,38 @@ template <int NT> static __host__ __device__ size_t lane_smem_bytes(int np, int 
 template <int NT, int WARPS, int MINB>
 __global__ void __launch_bounds__(32 * WARPS, MINB) k_evolve_lane(const __grid_constant__ Problem P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  // layout: CtaConst | LaneTab | WARPS x LaneWs | tail table (the only run-time-sized part, last).  The per-warp block
+  // offset is made opaque to the compiler: otherwise it re-derives (threadIdx.x >> 5) * sizeof(LaneWs) in front of shared
+  // accesses all over the step loop (2.3 k instructions per step, profiles/r2_lane_v3_*) instead of keeping one register.
   CtaConst* C = reinterpret_cast<CtaConst*>(smem_raw);
-  size_t off = al16(sizeof(CtaConst));
-  int* tail = reinterpret_cast<int*>(smem_raw + off);
-  off += al16((size_t)P.np * sizeof(int));
-  LaneTab<NT>* T = reinterpret_cast<LaneTab<NT>*>(smem_raw + off);
-  off += al16(sizeof(LaneTab<NT>));
+  constexpr unsigned OFF_T = (unsigned)((sizeof(CtaConst) + 15) & ~(size_t)15);
+  constexpr unsigned OFF_W = OFF_T + (unsigned)((sizeof(LaneTab<NT>) + 15) & ~(size_t)15);
+  constexpr unsigned SZ_W = (unsigned)((sizeof(LaneWs<NT>) + 15) & ~(size_t)15);
+  LaneTab<NT>* T = reinterpret_cast<LaneTab<NT>*>(smem_raw + OFF_T);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  LaneWs<NT>& W = *reinterpret_cast<LaneWs<NT>*>(smem_raw + off + warp * al16(sizeof(LaneWs<NT>)));
+  unsigned woff = OFF_W + (unsigned)warp * SZ_W;
+  asm volatile("" : "+r"(woff));
+  LaneWs<NT>& W = *reinterpret_cast<LaneWs<NT>*>(smem_raw + woff);
+  int* tail = reinterpret_cast<int*>(smem_raw + OFF_W + WARPS * SZ_W);
   init_cta_const(P, *C, tail, threadIdx.x, 32 * WARPS);
   __syncthreads();
   init_lane_tab<NT>(P, *C, *T, threadIdx.x, 32 * WARPS);
   __syncthreads();
   const int total = P.ncosmo * P.nk;
+  LaneSync SY;
+  SY.cnt = 32 * WARPS; SY.on = (P.mode == 0 && P.lockstep) ? 1 : 0;
   for (;;) {
     unsigned int tk = 0;
     if (lane == 0) tk = atomicAdd(P.ticket, 1u);
     tk = __shfl_sync(0xffffffffu, tk, 0);
-    if (tk >= (unsigned int)total) break;
-    const int kd = tk / P.ncosmo, cs = tk - kd * P.ncosmo;
-    const int mode = cs * P.nk + (P.nk - 1 - kd);
-    integrate_mode_lane<NT>(P, *C, *T, W, mode, lane);
+    // largest k first, cosmologies interleaved; mode -1 = out of work: with lock-step on, the warp goes through the SAME
+    // call (one copy of the code, the same barrier instructions) to attend the barriers until every warp is done
+    int mode = -1;
+    if (tk < (unsigned int)total) { const int kd = tk / P.ncosmo, cs = tk - kd * P.ncosmo; mode = cs * P.nk + (P.nk - 1 - kd); }
+    if (mode < 0 && !SY.on) break;
+    integrate_mode_lane<NT>(P, *C, *T, W, SY, mode, lane);
     __syncwarp();
+    if (mode < 0) break;
   }
 }
 
@@ -78,8 +88,9 @@ static LaneKernel pick_lane(int nt, int np) {
 int deb_launch_lane(const Problem& P, cudaStream_t st, int nsm) {
   const int nt = lane_nt(P.lmaxg, P.lmaxgp, P.lmaxr, P.lmaxnu);
   if (nt == 0 || LN_NSEG * P.nch > 32 || P.nh > 32 || P.n > 34 + 32 * nt) return DEB_E_UNSUPPORTED;
-  // 8 modes in flight per SM (255 registers each) as two CTAs of 4 warps (one CTA of 8 warps measured 2 % slower)
-  int warps = 4;
+  // 8 modes in flight per SM (255 registers each) as ONE CTA of 8 warps advancing in lock-step (LN_BAR): 225.7 -> 199.0 ms
+  // on 16384 modes against free-running warps; two CTAs of 4 warps in lock-step: 206.2 ms (profiles/r2_lane_lockstep.txt)
+  int warps = 8;
   if (const char* e = getenv("DEB_LANE_WARPS")) warps = atoi(e);
   const LaneKernel lk = warps == 4 ? pick_lane<4, 2>(nt, P.np) : pick_lane<8, 1>(nt, P.np);
   if (warps != 4) warps = 8;
@@ -92,7 +103,9 @@ int deb_launch_lane(const Problem& P, cudaStream_t st, int nsm) {
   long grid = (long)nsm * occ;
   if (grid * warps > total) grid = (total + warps - 1) / warps;
   CUDA_TRY(cudaMemsetAsync(P.ticket, 0, sizeof(unsigned int), st));
-  lk.fn<<<(unsigned)grid, 32 * warps, lk.smem, st>>>(P);
+  Problem Q = P;
+  Q.lockstep = getenv("DEB_LANE_LOCKSTEP") ? atoi(getenv("DEB_LANE_LOCKSTEP")) : 1;
+  lk.fn<<<(unsigned)grid, 32 * warps, lk.smem, st>>>(Q);
   CUDA_TRY(cudaGetLastError());
   return DEB_OK;
 }

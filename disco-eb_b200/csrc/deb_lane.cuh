@@ -30,6 +30,20 @@ namespace deb {
 
 constexpr int LN_NSEG = 4;
 
+// Lock-step of the warps of a CTA (each on its own mode).  The step loop is ~170 KB of straight-line code executed
+// once per attempted step: 8 warps in 8 different places stream it from L2 eight times (instruction-fetch stalls were
+// 22-45 % of the issue cycles, profiles/r2_lane_v1/v2_*); warps that pass the same point together share every fetched
+// line in the SM's instruction cache.  LN_BAR is a counted CTA barrier at the top of the Jacobian phase and of every
+// stage, executed by ALL threads of the CTA every time; `barrier.red.popc` returns how many threads still have work.  A
+// warp whose work queue ran dry keeps attending (it arrives at once and sleeps in the barrier) until that count is zero.
+struct LaneSync { unsigned cnt; int on; };
+#ifdef DEB_CPU_EMU
+#define LN_BAR(SY, stay)
+#else
+#define LN_BAR(SY, stay) do { if ((SY).on) { unsigned nc_; asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\tbarrier.red.popc.u32 %0, 1, p;\n\t}" \
+  : "=r"(nc_) : "r"((unsigned)(stay)) : "memory"); (SY).cnt = nc_; } } while (0)
+#endif
+
 #ifdef DEB_CPU_EMU
 #define LN_BEGIN for (int lane = 0; lane < 32; ++lane) {
 #define LN_END }
@@ -53,6 +67,7 @@ template <int NT> struct alignas(16) LaneWs {
   double kc_[2 * NCHMAX], kap_[2 * NCHMAX], nur_[2 * NQMAX], nup_[2 * NQMAX], sl_[2 * NSLOT], ic_[ICACHE];
   double m2[NCHMAX], sch[NCHMAX];                   // per chain: backward multiplier of its l = 2 (head) row, Schur increment of that row
   double ka0[8];                                    // element 0 (scale factor) of k_1..k_7
+  double khs[7 * 32];                               // k_1..k_7 of the head rows: column `lane` is private to the lane that owns the row
   int perm_[NHMAX];
   Cosmo cosmo_;
   // interpolated output state (reference layout): pct/qct/jat are dead at the end of a step, 3 TA >= NPCAP doubles
@@ -93,9 +108,13 @@ DEB_HD int lane_nt(int lmaxg, int lmaxgp, int lmaxr, int lmaxnu) {
    : RD_A61 * (K0) + RD_A62 * (K1) + RD_A63 * (K2) + RD_A64 * (K3) + RD_A65 * (K4))
 
 template <int NT>
-DEB_DEV void integrate_mode_lane(const Problem& P, const CtaConst& C, const LaneTab<NT>& T, LaneWs<NT>& W, int mode DEB_LANE_PARAM) {
+DEB_DEV void integrate_mode_lane(const Problem& P, const CtaConst& C, const LaneTab<NT>& T, LaneWs<NT>& W, LaneSync& SY, int mode_in DEB_LANE_PARAM) {
   const int n = P.n, nh = P.nh, nch = P.nch, nq = P.nq;
   const int nhb = nh - 1;
+  // mode_in < 0: the warp is out of work and only attends the CTA's lock-step barriers (same barrier instructions as the
+  // working warps) until nobody has work left; it runs the prologue of mode 0 into its own workspace and writes nothing
+  const bool idle = mode_in < 0;
+  const int mode = idle ? 0 : mode_in;
   const int cosmo = mode / P.nk, kidx = mode - cosmo * P.nk;
   const double k = DEB_LDG(P.kmodes + (P.k_per_cosmo ? (size_t)cosmo * P.nk + kidx : (size_t)kidx));
   const double k2 = k * k;
@@ -175,18 +194,17 @@ DEB_DEV void integrate_mode_lane(const Problem& P, const CtaConst& C, const Lane
   if (!(t == t) || !(tnext == tnext) || !(t1 == t1)) status = 2;
   Hints hint; hint.th = -1; hint.nu = -1;
 
-  while (t < t1 && nsteps < P.max_steps && status == 0) {
+  while (idle || (t < t1 && nsteps < P.max_steps && status == 0)) {
     if (P.mode == 3) {
       if (nsteps >= DEB_LDG(P.rp_n + mode)) break;
       tnext = DEB_LDG(P.rp_tnext + (size_t)mode * P.rp_stride + nsteps);
       if (fabs(tnext - t1) <= 1e-12 * fabs(t1)) tnext = t1;
     }
     DEB_REGS(double, kt, [7][NT]);      // k_1..k_7 of the lane's tail rows
-    DEB_REGS(double, kh, [7]);          // ... of its head row
     DEB_REGS(double, ut, [NT]);         // stage state of the tail rows
     DEB_REGS(double, bt, [NT]);         // right-hand side -> solution of the tail rows
     DEB_REGS(double, ufirst, ); DEB_REGS(double, ulast, ); DEB_REGS(double, cfirst, ); DEB_REGS(double, clast, );
-    DEB_REGS(double, ptot, ); DEB_REGS(double, qtot, ); DEB_REGS(double, cin, );
+    DEB_REGS(double, cin, );
     DEB_REGS(double, kcl, ); DEB_REGS(double, kpl, );
     const double dt = tnext - t;
     const double invdt = DEB_RCP(dt);
@@ -195,7 +213,11 @@ DEB_DEV void integrate_mode_lane(const Problem& P, const CtaConst& C, const Lane
     const double gdt = dt * RD_GAMMA;
 
     // ================= Jacobian pieces at (t, y): stage-1 right-hand side, d f/d a, factorisation =================
-    double x0piv, r0;
+    LN_BAR(SY, !idle);
+    if (idle && SY.cnt == 0) return;
+    double x0piv = 1.0, r0 = 0.0;
+    double ci_hh = 0.0, ci_he = 0.0, ci_eh = 0.0, ci_ee = 0.0, jq_h = 0.0, jq_e = 0.0;     // inverse capacitance; a h' row applied to qh, qe
+    if (!idle) {
     {
       Bg<Dual> bd;
       compute_bg<Dual>(c, nb, nq, mk(W.y_[0], 1.0), hint, W.ic_, bd);
@@ -305,15 +327,12 @@ DEB_DEV void integrate_mode_lane(const Problem& P, const CtaConst& C, const Lane
       DEB_LANES_END
       // cumulative multiplier products of every segment: backward  P_j = prod_{jj >= j} (-m_jj), forward Q_j = prod_{jj <= j} g_jj
       DEB_LANES_BEGIN
-        DEB_USE(ptot); DEB_USE(qtot);
         double p = 1.0;
 #pragma unroll
         for (int j = NT - 1; j >= 0; --j) { p *= -W.mt[j * 32 + lane]; W.pct[j * 32 + lane] = p; }
-        ptot = p;
         double q = 1.0;
 #pragma unroll
         for (int j = 0; j < NT; ++j) { q *= W.gt[j * 32 + lane]; W.qct[j * 32 + lane] = q; }
-        qtot = q;
       DEB_LANES_END
 
       // ---- head:  W_h = D - chv gh^T - cev ge^T  (+ the a h' row); D block diagonal -> block inverses + Woodbury ----
@@ -412,7 +431,6 @@ DEB_DEV void integrate_mode_lane(const Problem& P, const CtaConst& C, const Lane
         W.xb_[lane] = j1c;
       }
     DEB_LANES_END
-    double ci_hh, ci_he, ci_eh, ci_ee, jq_h, jq_e;
     {
       const double c_hh = 1.0 - DEB_WARP_SUM(s1), c_he = -DEB_WARP_SUM(s2), c_eh = -DEB_WARP_SUM(s3), c_ee = 1.0 - DEB_WARP_SUM(s4);
       const double idet = DEB_RCP(c_hh * c_ee - c_he * c_eh);
@@ -425,6 +443,7 @@ DEB_DEV void integrate_mode_lane(const Problem& P, const CtaConst& C, const Lane
       jq_h = DEB_WARP_SUM(s1); jq_e = DEB_WARP_SUM(s2);
     }
 
+    }     // !idle
     // ================= 8 stages =================
     double errnorm2 = 0.0;
     double ua = W.y_[0];            // scale factor of the stage state (element 0), uniform over the warp
@@ -432,6 +451,8 @@ DEB_DEV void integrate_mode_lane(const Problem& P, const CtaConst& C, const Lane
     double ts = t, invts = invt0;
 #pragma unroll 1
     for (int st = 1; st <= 8; ++st) {
+      LN_BAR(SY, !idle);
+      if (idle) continue;
       if (st > 1) {
         ts = st == 2 ? t + RD_CT2 * dt : st == 3 ? t + RD_CT3 * dt : st == 4 ? t + RD_CT4 * dt : st == 5 ? t + RD_CT5 * dt : t + dt;
         const double dtd = st == 2 ? dt * RD_D2 : st == 3 ? dt * RD_D3 : st == 4 ? dt * RD_D4 : st == 5 ? dt * RD_D5 : 0.0;
@@ -457,7 +478,9 @@ DEB_DEV void integrate_mode_lane(const Problem& P, const CtaConst& C, const Lane
         }
         // own rows: u = y + sum a_ij k_j (stages 7, 8: u + k), c-combination -> bt / rh
         DEB_LANES_BEGIN
-          DEB_USE(kt); DEB_USE(kh); DEB_USE(ut); DEB_USE(bt); DEB_USE(nrow); DEB_USE(he); DEB_USE(tsg); DEB_USE(eb);
+          DEB_USE(kt); DEB_USE(ut); DEB_USE(bt); DEB_USE(nrow); DEB_USE(he); DEB_USE(tsg); DEB_USE(eb);
+          const double* kh_ = W.khs + lane;
+#define kh(i) kh_[(i) * 32]
           DEB_USE(ufirst); DEB_USE(ulast); DEB_USE(cfirst);
           double yv[NT];
 #pragma unroll
@@ -467,27 +490,28 @@ DEB_DEV void integrate_mode_lane(const Problem& P, const CtaConst& C, const Lane
 #define LN_T(expr_u, expr_c) _Pragma("unroll") for (int j = 0; j < NT; ++j) { ut[j] = (expr_u); bt[j] = invdt * (expr_c); }
           switch (st) {
             case 2: LN_T(yv[j] + RD_A21 * kt[0][j], RD_C21 * kt[0][j])
-                    uh = yh + RD_A21 * kh[0]; chh = RD_C21 * kh[0]; break;
+                    uh = yh + RD_A21 * kh(0); chh = RD_C21 * kh(0); break;
             case 3: LN_T(yv[j] + RD_A31 * kt[0][j] + RD_A32 * kt[1][j], RD_C31 * kt[0][j] + RD_C32 * kt[1][j])
-                    uh = yh + RD_A31 * kh[0] + RD_A32 * kh[1]; chh = RD_C31 * kh[0] + RD_C32 * kh[1]; break;
+                    uh = yh + RD_A31 * kh(0) + RD_A32 * kh(1); chh = RD_C31 * kh(0) + RD_C32 * kh(1); break;
             case 4: LN_T(yv[j] + RD_A41 * kt[0][j] + RD_A42 * kt[1][j] + RD_A43 * kt[2][j], RD_C41 * kt[0][j] + RD_C42 * kt[1][j] + RD_C43 * kt[2][j])
-                    uh = yh + RD_A41 * kh[0] + RD_A42 * kh[1] + RD_A43 * kh[2]; chh = RD_C41 * kh[0] + RD_C42 * kh[1] + RD_C43 * kh[2]; break;
+                    uh = yh + RD_A41 * kh(0) + RD_A42 * kh(1) + RD_A43 * kh(2); chh = RD_C41 * kh(0) + RD_C42 * kh(1) + RD_C43 * kh(2); break;
             case 5: LN_T(yv[j] + RD_A51 * kt[0][j] + RD_A52 * kt[1][j] + RD_A53 * kt[2][j] + RD_A54 * kt[3][j],
                          RD_C51 * kt[0][j] + RD_C52 * kt[1][j] + RD_C53 * kt[2][j] + RD_C54 * kt[3][j])
-                    uh = yh + RD_A51 * kh[0] + RD_A52 * kh[1] + RD_A53 * kh[2] + RD_A54 * kh[3];
-                    chh = RD_C51 * kh[0] + RD_C52 * kh[1] + RD_C53 * kh[2] + RD_C54 * kh[3]; break;
+                    uh = yh + RD_A51 * kh(0) + RD_A52 * kh(1) + RD_A53 * kh(2) + RD_A54 * kh(3);
+                    chh = RD_C51 * kh(0) + RD_C52 * kh(1) + RD_C53 * kh(2) + RD_C54 * kh(3); break;
             case 6: LN_T(yv[j] + RD_A61 * kt[0][j] + RD_A62 * kt[1][j] + RD_A63 * kt[2][j] + RD_A64 * kt[3][j] + RD_A65 * kt[4][j],
                          RD_C61 * kt[0][j] + RD_C62 * kt[1][j] + RD_C63 * kt[2][j] + RD_C64 * kt[3][j] + RD_C65 * kt[4][j])
-                    uh = yh + RD_A61 * kh[0] + RD_A62 * kh[1] + RD_A63 * kh[2] + RD_A64 * kh[3] + RD_A65 * kh[4];
-                    chh = RD_C61 * kh[0] + RD_C62 * kh[1] + RD_C63 * kh[2] + RD_C64 * kh[3] + RD_C65 * kh[4]; break;
+                    uh = yh + RD_A61 * kh(0) + RD_A62 * kh(1) + RD_A63 * kh(2) + RD_A64 * kh(3) + RD_A65 * kh(4);
+                    chh = RD_C61 * kh(0) + RD_C62 * kh(1) + RD_C63 * kh(2) + RD_C64 * kh(3) + RD_C65 * kh(4); break;
             case 7: LN_T(ut[j] + kt[5][j], RD_C71 * kt[0][j] + RD_C72 * kt[1][j] + RD_C73 * kt[2][j] + RD_C74 * kt[3][j] + RD_C75 * kt[4][j] + RD_C76 * kt[5][j])
-                    uh = W.u_[he] + kh[5];
-                    chh = RD_C71 * kh[0] + RD_C72 * kh[1] + RD_C73 * kh[2] + RD_C74 * kh[3] + RD_C75 * kh[4] + RD_C76 * kh[5]; break;
+                    uh = (lane < nh ? W.u_[he] : 0.0) + kh(5);
+                    chh = RD_C71 * kh(0) + RD_C72 * kh(1) + RD_C73 * kh(2) + RD_C74 * kh(3) + RD_C75 * kh(4) + RD_C76 * kh(5); break;
             default: LN_T(ut[j] + kt[6][j], RD_C81 * kt[0][j] + RD_C82 * kt[1][j] + RD_C83 * kt[2][j] + RD_C84 * kt[3][j] + RD_C85 * kt[4][j] + RD_C86 * kt[5][j] + RD_C87 * kt[6][j])
-                    uh = W.u_[he] + kh[6];
-                    chh = RD_C81 * kh[0] + RD_C82 * kh[1] + RD_C83 * kh[2] + RD_C84 * kh[3] + RD_C85 * kh[4] + RD_C86 * kh[5] + RD_C87 * kh[6]; break;
+                    uh = (lane < nh ? W.u_[he] : 0.0) + kh(6);
+                    chh = RD_C81 * kh(0) + RD_C82 * kh(1) + RD_C83 * kh(2) + RD_C84 * kh(3) + RD_C85 * kh(4) + RD_C86 * kh(5) + RD_C87 * kh(6); break;
           }
 #undef LN_T
+#undef kh
           cfirst = chh;                                   // parked: the head row is formed after the metric sources
           ufirst = ut[0]; ulast = ut[NT - 1];
           if (lane < nh) W.u_[he] = uh;
@@ -549,7 +573,7 @@ DEB_DEV void integrate_mode_lane(const Problem& P, const CtaConst& C, const Lane
 #pragma unroll
       for (int rd = 1; rd < LN_NSEG; ++rd) {
         LN_BEGIN
-          DEB_USE(bt); DEB_USE(cfirst); DEB_USE(cin); DEB_USE(tsg); DEB_USE(tch); DEB_USE(hasnext); DEB_USE(ptot);
+          DEB_USE(bt); DEB_USE(cfirst); DEB_USE(cin); DEB_USE(tsg); DEB_USE(tch); DEB_USE(hasnext);
           const double v = LN_SHFL(cfirst, lane + nch);
           if (tch >= 0 && tsg == LN_NSEG - 1 - rd && hasnext) { cin = v; cfirst = bt[0] + W.pct[lane] * v; }
         LN_END
@@ -591,29 +615,29 @@ DEB_DEV void integrate_mode_lane(const Problem& P, const CtaConst& C, const Lane
       }
       // forward sweep: x_l = b'_l / e_l + g_l x_{l-1}
       LN_BEGIN
-        DEB_USE(bt); DEB_USE(clast); DEB_USE(cin); DEB_USE(tch); DEB_USE(tsg); DEB_USE(h2); DEB_USE(qtot); DEB_USE(nrow);
+        DEB_USE(bt); DEB_USE(clast); DEB_USE(cin); DEB_USE(tch); DEB_USE(tsg); DEB_USE(h2); DEB_USE(nrow);
         double loc = 0.0;
 #pragma unroll
         for (int j = 0; j < NT; ++j) { loc = bt[j] * W.iet[j * 32 + lane] + W.gt[j * 32 + lane] * loc; bt[j] = loc; }
         cin = (tch >= 0 && tsg == 0 && nrow > 0) ? W.rh[h2] : 0.0;                 // x_2 of the chain (head solution)
-        clast = loc + qtot * cin;
+        clast = loc + W.qct[(NT - 1) * 32 + lane] * cin;
       LN_END
 #pragma unroll
       for (int rd = 1; rd < LN_NSEG; ++rd) {
         LN_BEGIN
-          DEB_USE(bt); DEB_USE(clast); DEB_USE(cin); DEB_USE(tsg); DEB_USE(tch); DEB_USE(qtot); DEB_USE(nrow);
+          DEB_USE(bt); DEB_USE(clast); DEB_USE(cin); DEB_USE(tsg); DEB_USE(tch); DEB_USE(nrow);
           const double v = LN_SHFL(clast, lane - nch);
-          if (tch >= 0 && tsg == rd && nrow > 0) { cin = v; clast = bt[NT - 1] + qtot * v; }
+          if (tch >= 0 && tsg == rd && nrow > 0) { cin = v; clast = bt[NT - 1] + W.qct[(NT - 1) * 32 + lane] * v; }
         LN_END
       }
       DEB_LANES_BEGIN
-        DEB_USE(bt); DEB_USE(cin); DEB_USE(kt); DEB_USE(kh);
+        DEB_USE(bt); DEB_USE(cin); DEB_USE(kt);
 #pragma unroll
         for (int j = 0; j < NT; ++j) bt[j] = bt[j] + W.qct[j * 32 + lane] * cin;
         const double xh = lane < nh ? W.rh[lane] : 0.0;
         // ---- keep k_st ----
         switch (st) {
-#define LN_K(i) _Pragma("unroll") for (int j = 0; j < NT; ++j) kt[i][j] = bt[j]; kh[i] = xh; if (lane == 0) W.ka0[i] = x0;
+#define LN_K(i) _Pragma("unroll") for (int j = 0; j < NT; ++j) kt[i][j] = bt[j]; W.khs[(i) * 32 + lane] = xh; if (lane == 0) W.ka0[i] = x0;
           case 1: LN_K(0) break;
           case 2: LN_K(1) break;
           case 3: LN_K(2) break;
@@ -626,6 +650,7 @@ DEB_DEV void integrate_mode_lane(const Problem& P, const CtaConst& C, const Lane
         }
       DEB_LANES_END
     }
+    if (idle) continue;
     // y1 = u + k8 (candidate; error estimate = k8): tails stay in registers, head and a go to u_
     DEB_LANES_BEGIN
       DEB_USE(nanflag); DEB_USE(ut); DEB_USE(bt); DEB_USE(he);

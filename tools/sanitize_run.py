@@ -7,7 +7,7 @@ import helpers
 from discoeb_b200 import _cabi
 lib = _cabi.default_library()
 tab = helpers.load_tables("fiducial")
-for dm, nk in (((11, 11, 11, 8, 3), 6), ((31, 31, 31, 31, 5), 4)):
+for dm, nk in (((11, 11, 11, 8, 3), 6), ((31, 31, 31, 31, 5), 4), ((31, 31, 31, 31, 5), 21)):
     lg, lp, lr, ln, nq = dm
     ks = np.geomspace(1e-3, 0.05, nk)
     dims = _cabi.make_dims(ncosmo=1, nk=nk, nout=2, lmaxg=lg, lmaxgp=lp, lmaxr=lr, lmaxnu=ln, nqmax=nq, nth=tab.nth, nnu=tab.nnu, max_steps=60, power_idx=4)
