@@ -46,7 +46,9 @@
 #else
 #define DEB_DEV __device__ __forceinline__
 #define DEB_HD __host__ __device__ __forceinline__
+#ifndef DEB_LDG
 #define DEB_LDG(p) __ldg(p)
+#endif
 #define DEB_LANES_BEGIN {
 #define DEB_LANES_END } __syncwarp();
 #define DEB_LANE0_BEGIN if (lane == 0) {
@@ -288,6 +290,7 @@ struct Problem {
   // the 20 fields, P(k) and the status words of local mode kidx to row kidx*out_mul + out_add (of out_nk) of the FULL-SIZE
   // buffers of all npeer ranks -- its own and, through NVLink peer mappings, everybody else's: the epilogue is the gather
   int lockstep;              // chain-lane kernel: warps of a CTA advance stage by stage together (deb_lane.cuh)
+  int stage_tables;          // chain-lane kernel, ncosmo == 1: the three RHS splines staged in shared memory by one bulk async copy
   int npeer, out_mul, out_add, out_nk;
   double* y_peer[8]; double* pk_peer[8]; int* st_peer[8]; int* ns_peer[8];
 };

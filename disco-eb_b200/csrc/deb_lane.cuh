@@ -108,7 +108,7 @@ DEB_HD int lane_nt(int lmaxg, int lmaxgp, int lmaxr, int lmaxnu) {
    : RD_A61 * (K0) + RD_A62 * (K1) + RD_A63 * (K2) + RD_A64 * (K3) + RD_A65 * (K4))
 
 template <int NT>
-DEB_DEV void integrate_mode_lane(const Problem& P, const CtaConst& C, const LaneTab<NT>& T, LaneWs<NT>& W, LaneSync& SY, int mode_in DEB_LANE_PARAM) {
+DEB_DEV void integrate_mode_lane(const Problem& P, const CtaConst& C, const LaneTab<NT>& T, LaneWs<NT>& W, LaneSync& SY, int mode_in DEB_LANE_PARAM, const double* stab = nullptr) {
   const int n = P.n, nh = P.nh, nch = P.nch, nq = P.nq;
   const int nhb = nh - 1;
   // mode_in < 0: the warp is out of work and only attends the CTA's lock-step barriers (same barrier instructions as the
@@ -119,7 +119,15 @@ DEB_DEV void integrate_mode_lane(const Problem& P, const CtaConst& C, const Lane
   const double k = DEB_LDG(P.kmodes + (P.k_per_cosmo ? (size_t)cosmo * P.nk + kidx : (size_t)kidx));
   const double k2 = k * k;
   DEB_LANES_BEGIN
-    if (lane == 0) W.cosmo_ = load_cosmo(P, cosmo);
+    if (lane == 0) {
+      W.cosmo_ = load_cosmo(P, cosmo);
+      if (stab) {       // RHS splines (cs2a, xe, log rho_nu: one contiguous 24 KB block of the table set) staged in shared memory
+        Cosmo& cc = W.cosmo_;
+        cc.cs2a.x = stab; cc.cs2a.y = stab + P.nth; cc.cs2a.S = stab + 2 * P.nth;
+        cc.xe.x = stab + 3 * P.nth; cc.xe.y = stab + 4 * P.nth; cc.xe.S = stab + 5 * P.nth;
+        cc.lrn.x = stab + 6 * P.nth; cc.lrn.y = stab + 6 * P.nth + P.nnu; cc.lrn.S = stab + 6 * P.nth + 2 * P.nnu;
+      }
+    }
     { double* z = W.tails(); for (int i = lane; i < 7 * NT * 32; i += 32) z[i] = 0.0; }
     if (lane < NCHMAX) { W.m2[lane] = 0.0; W.sch[lane] = 0.0; }
     if (lane < 8) W.ka0[lane] = 0.0;
