@@ -84,6 +84,10 @@ class Library:
         bgf.argtypes = [C.c_int32, C.c_int32, C.c_int32, _dp, _dp, _dp, C.POINTER(C.c_float)]
         bgf.restype = C.c_int
         self._background_host = bgf
+        spf = getattr(self.lib, prefix + "spectra_host_f64")
+        spf.argtypes = [C.c_int32, C.c_int32, C.c_int32, _dp, _dp, C.c_double, C.c_double, C.c_double, C.c_double, _dp, C.c_int32, _dp, C.c_int32] + [_dp] * 8
+        spf.restype = C.c_int
+        self._spectra_host = spf
         if prefix == "deb_":
             self.lib.deb_strerror.restype = C.c_char_p
             self.lib.deb_strerror.argtypes = [C.c_int]
@@ -125,6 +129,20 @@ class Library:
         self._check(self._background_host(C.c_int32(device), C.c_int32(nc), C.c_int32(nth), _d(bg_in), _d(scal), _d(tab), C.byref(kms)),
                     "background_host_f64")
         return scal, tab, kms.value
+
+    def spectra_host(self, y, k, As, ns, kp, bias, sg_coef, mu, ell, want_xi, device: int = 0):
+        """deb_spectra_host_f64 -> dict(P0, P2, P4, Pkmu, Ps_delta, Ps_theta, xi, r) (entries None when not requested)."""
+        nk = y.shape[0]
+        nmu = 0 if mu is None else len(mu)
+        w = 0 if sg_coef is None else len(sg_coef)
+        P0, P2, P4 = np.zeros(nk), np.zeros(nk), np.zeros(nk)
+        Pkmu = np.zeros((nk, nmu)) if nmu else None
+        Psd, Pst = (np.zeros(nk), np.zeros(nk)) if w else (None, None)
+        xi, r = (np.zeros(nk), np.zeros(nk)) if want_xi else (None, None)
+        self._check(self._spectra_host(C.c_int32(device), C.c_int32(nk), C.c_int32(nmu), _d(y), _d(k), C.c_double(As), C.c_double(ns), C.c_double(kp),
+                                       C.c_double(bias), _d(sg_coef), C.c_int32(w), _d(mu), C.c_int32(ell), _d(P0), _d(P2), _d(P4), _d(Pkmu), _d(Psd),
+                                       _d(Pst), _d(xi), _d(r)), "spectra_host_f64")
+        return dict(P0=P0, P2=P2, P4=P4, Pkmu=Pkmu, Ps_delta=Psd, Ps_theta=Pst, xi=xi, r=r)
 
     def evolve_sharded_host(self, comm, dims: DebDims, ctrl: DebCtrl, scalars, tables, kmodes, aexp_out, want_pk: bool = False):
         """deb_evolve_sharded_host_f64: the k grid of `dims` dealt over comm.world ranks, NCCL all-gather, full-size results."""

@@ -269,6 +269,23 @@ int deb_evolve_peer_f64(const deb_dims* dims, const deb_ctrl* ctrl, const double
                         int32_t npeer, int32_t out_mul, int32_t out_add, int32_t out_nk,
                         double* const* y_peer, double* const* pk_peer, int32_t* const* st_peer, int32_t* const* ns_peer);
 
+/* ---- spectra epilogues -----------------------------------------------------------------
+ * What the reference's host API derives from y right after the solve (/root/reference/src/discoeb/perturbations.py):
+ * power_multipoles :1202-1224 (P0, P2, P4), power_Kaiser :1162-1199 (Pkmu[nk, nmu] on the given mu grid),
+ * get_power_smoothed :1126-1160 (Ps_delta, Ps_theta: Savitzky-Golay in log-log, sg_coef[sg_window] = the centre weights of
+ * util.savgol_filter :407-444; sg_window = 0: none, Kaiser then uses the raw amplitudes) and get_xi_from_P :1065-1098
+ * (FFTlog of P_delta -- smoothed if sg_window > 0 -- multipole `ell`; xi, r ascending in r; NULL to skip).
+ * y[nk, 20] is the solver output of ONE cosmology and output time; all pointers of deb_spectra_f64 are DEVICE pointers
+ * (asynchronous on `stream`, so the call chains behind deb_evolve_f64 without y leaving the GPU). */
+size_t deb_spectra_workspace_bytes(int32_t nk);
+int deb_spectra_f64(int32_t nk, int32_t nmu, const double* y, const double* kmodes, double As, double ns, double kp, double bias,
+                    const double* sg_coef, int32_t sg_window, const double* mu, int32_t ell,
+                    double* P0, double* P2, double* P4, double* Pkmu, double* Ps_delta, double* Ps_theta, double* xi, double* r,
+                    void* workspace, size_t workspace_bytes, void* stream);
+int deb_spectra_host_f64(int32_t device, int32_t nk, int32_t nmu, const double* y, const double* kmodes, double As, double ns, double kp, double bias,
+                         const double* sg_coef, int32_t sg_window, const double* mu, int32_t ell,
+                         double* P0, double* P2, double* P4, double* Pkmu, double* Ps_delta, double* Ps_theta, double* xi, double* r);
+
 /* Measures the FP64 FMA peak of `device` (dependent-free DFMA streams on every SM) and
  * returns it in TFLOP/s; the roofline denominator bench.py reports against. */
 int deb_fp64_peak_tflops(int32_t device, double* tflops, float* sm_clock_mhz);

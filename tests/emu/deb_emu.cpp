@@ -13,6 +13,7 @@
 #include "../../disco-eb_b200/csrc/deb_team.cuh"
 #include "../../disco-eb_b200/csrc/deb_lane.cuh"
 #include "../../disco-eb_b200/csrc/deb_background.cuh"
+#include "../../disco-eb_b200/csrc/deb_spectra.cuh"
 #include "../../disco-eb_b200/csrc/deb_host.inl"
 
 using namespace deb;
@@ -336,5 +337,29 @@ extern "C" int emu_background_host_f64(int32_t device, int32_t ncosmo, int32_t n
     background_one(bg_in + (size_t)c * NBGIN, q, w, nth, scalars + (size_t)c * DEB_NSCAL, tables + (size_t)c * tl, W[0], 0, 1);
   }
   if (kernel_ms) *kernel_ms = 0.0f;
+  return DEB_OK;
+}
+
+// spectra epilogues (deb_spectra.cuh) on the CPU
+extern "C" int emu_spectra_host_f64(int32_t device, int32_t nk, int32_t nmu, const double* y, const double* kmodes, double As, double ns, double kp,
+                                    double bias, const double* sg_coef, int32_t sg_window, const double* mu, int32_t ell, double* P0, double* P2,
+                                    double* P4, double* Pkmu, double* Ps_delta, double* Ps_theta, double* xi, double* r) {
+  (void)device;
+  using namespace deb::sp;
+  std::vector<double> dm(nk), tm(nk), lPd(nk), lPt(nk), Pd(nk);
+  for (int i = 0; i < nk; ++i) point(i, y, kmodes, As, ns, kp, bias, dm.data(), tm.data(), P0, P2, P4, lPd.data(), lPt.data(), Pd.data());
+  if (sg_window > 0) for (int i = 0; i < nk; ++i) { Ps_delta[i] = smooth_at(i, nk, lPd.data(), sg_coef, sg_window); Ps_theta[i] = smooth_at(i, nk, lPt.data(), sg_coef, sg_window); }
+  if (Pkmu && nmu > 0 && mu)
+    for (int i = 0; i < nk; ++i) for (int j = 0; j < nmu; ++j) {
+      const double d = sg_window > 0 ? sqrt(Ps_delta[i]) : dm[i], t = sg_window > 0 ? -sqrt(Ps_theta[i]) : tm[i];
+      const double v = bias * d - mu[j] * mu[j] * t;
+      Pkmu[(size_t)i * nmu + j] = v * v;
+    }
+  if (xi && r) {
+    const double* Pk = sg_window > 0 ? Ps_delta : Pd.data();
+    std::vector<Cx> F(nk / 2 + 1);
+    for (int m = 0; m <= nk / 2; ++m) F[m] = fftlog_forward(m, nk, kmodes, Pk, ell);
+    for (int nn = 0; nn < nk; ++nn) { xi[nk - 1 - nn] = fftlog_backward(nn, nk, kmodes, F.data(), ell); r[nk - 1 - nn] = 2.0 * M_PI / kmodes[nn]; }
+  }
   return DEB_OK;
 }

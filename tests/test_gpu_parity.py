@@ -329,3 +329,10 @@ def test_class_golden_curve_batched(gpu_lib, tables, batch_size):
     m = (kc >= 1e-5) & (kc <= 10.0)
     np.testing.assert_allclose(np.interp(kc[m], ks, out["pk"][0, :, 0]), Pc[m], rtol=0.005)
     print("batch", batch_size, "kernel_ms", out["kernel_ms"], "steps per batch", ns[:, 0].min(), "...", ns[:, 0].max())
+
+
+def test_spectra_epilogues_on_gpu(gpu_lib):
+    """power_multipoles, power_Kaiser, get_power_smoothed, get_xi_from_P computed by the CUDA library
+    (csrc/deb_spectra.cu) against the NumPy oracle (oracle/spectra.py, itself pinned against SciPy)."""
+    from test_spectra_cpu import check_product_spectra
+    check_product_spectra(gpu_lib)

@@ -1,11 +1,14 @@
-"""Spectra post-processing entry points (perturbations.py:1063-1224) -- host-side array functions of the solver
-output; checked against independent SciPy implementations and closed forms."""
+"""Spectra post-processing entry points (perturbations.py:1063-1224).  The NumPy oracle (oracle/spectra.py) is checked
+against independent SciPy implementations and closed forms; the product's kernels (csrc/deb_spectra.cuh behind
+discoeb_b200/spectra.py) are checked against the oracle -- here through the CPU build of the source (tests/emu), in
+tests/test_gpu_parity.py through the CUDA library."""
 import numpy as np
 import scipy.signal
 import scipy.special
 
 import helpers
-from discoeb_b200 import spectra as S
+import oracle.spectra as S
+from discoeb_b200 import spectra as G
 from discoeb_b200 import perturbations as P
 
 
@@ -17,7 +20,7 @@ def _case():
 
 def test_reexported_from_perturbations():
     for name in ("get_power", "get_power_smoothed", "power_Kaiser", "power_multipoles", "get_xi_from_P"):
-        assert getattr(P, name) is getattr(S, name)
+        assert getattr(P, name) is getattr(G, name)
 
 
 def test_lngamma_matches_scipy():
@@ -82,3 +85,39 @@ def test_fftlog_gaussian_pair():
     # quadrupole of a pure monopole-shaped input is a different Hankel transform: finite and of the right size
     xi2, _ = S.get_xi_from_P(k=k, Pk=Pk, ell=2)
     assert np.all(np.isfinite(xi2)) and np.abs(xi2[m]).max() < np.abs(xi[m]).max()
+
+
+def check_product_spectra(lib):
+    """discoeb_b200.spectra (library kernels) against the oracle on a wiggly synthetic spectrum and on a solver output."""
+    k = np.geomspace(1e-3, 1.0, 128)
+    p = dict(A_s=2.1e-9, n_s=0.96, k_p=0.05)
+    y = np.zeros((128, 20))
+    y[:, 4] = 1e3 * k ** 1.5 * (1 + 0.05 * np.sin(40 * np.log(k)))
+    y[:, 5] = -0.5 * y[:, 4]
+    for a, b in zip(G.power_multipoles(y=y, kmodes=k, b=1.7, param=p, lib=lib), S.power_multipoles(y=y, kmodes=k, b=1.7, param=p)):
+        np.testing.assert_allclose(a, b, rtol=1e-13)
+    for idx in (4, 5):
+        np.testing.assert_allclose(G.get_power_smoothed(k=k, y=y, dlogk=0.5, idx=idx, param=p, lib=lib),
+                                   S.get_power_smoothed(k=k, y=y, dlogk=0.5, idx=idx, param=p), rtol=1e-12)
+    for kw in (dict(nmu=9), dict(nmu=5, mu_sampling=False), dict(nmu=7, smooth_dlogk=0.5)):
+        a, mu_a = G.power_Kaiser(y=y, kmodes=k, bias=1.7, param=p, lib=lib, **kw)
+        b, mu_b = S.power_Kaiser(y=y, kmodes=k, bias=1.7, param=p, **kw)
+        np.testing.assert_allclose(mu_a, mu_b, rtol=0, atol=0)
+        np.testing.assert_allclose(a, b, rtol=1e-11)
+    for N in (512, 257):
+        kk = np.geomspace(1e-4, 1e2, N)
+        Pk = np.exp(-kk ** 2) + 1e-3 * kk ** -1.5
+        for ell in (0, 2, 4):
+            xa, ra = G.get_xi_from_P(k=kk, Pk=Pk, ell=ell, lib=lib)
+            xb, rb = S.get_xi_from_P(k=kk, Pk=Pk, ell=ell)
+            np.testing.assert_allclose(ra, rb, rtol=1e-15)
+            assert np.abs(xa - xb).max() <= 1e-10 * np.abs(xb).max(), (N, ell)
+    case, pp = _case()
+    yy = case["y"][:, -1, :]
+    for a, b in zip(G.power_multipoles(y=yy, kmodes=case["kmodes"], b=1.3, param=pp, lib=lib),
+                    S.power_multipoles(y=yy, kmodes=case["kmodes"], b=1.3, param=pp)):
+        np.testing.assert_allclose(a, b, rtol=1e-13)
+
+
+def test_product_spectra_source_matches_oracle(emu_lib):
+    check_product_spectra(emu_lib)
