@@ -289,6 +289,11 @@ struct Problem {
   // sharded launch with peer stores (deb_evolve_sharded_peer_f64): a rank integrates every `out_mul`-th k-mode and writes
   // the 20 fields, P(k) and the status words of local mode kidx to row kidx*out_mul + out_add (of out_nk) of the FULL-SIZE
   // buffers of all npeer ranks -- its own and, through NVLink peer mappings, everybody else's: the epilogue is the gather
+  // hybrid launch (small launches in steady state, deb_kernels.cu: launch_evolve): the team kernel takes the `hybrid_split`
+  // longest modes of the learned work list (one CTA per SM), the chain-lane kernel the rest on the warps that fit beside;
+  // both look at the list's verdict word (ticket[2]) and fall back / exit when the list was rejected
+  int hybrid_split;
+  unsigned int* ticket2;     // the lane kernel's own queue counter in hybrid launches
   int lockstep;              // chain-lane kernel: warps of a CTA advance stage by stage together (deb_lane.cuh)
   int stage_tables;          // chain-lane kernel, ncosmo == 1: the three RHS splines staged in shared memory by one bulk async copy
   int npeer, out_mul, out_add, out_nk;

@@ -168,6 +168,15 @@ int deb_evolve_sharded_f64(deb_comm* comm, int32_t world, int32_t rank, const de
   cudaStream_t st = (cudaStream_t)stream;
   const int nk = dims->nk, nloc = share(nk, world, rank), per = (nk + world - 1) / world, nc = dims->ncosmo, nout = dims->nout;
   const int has_pk = dims->power_idx >= 0 && pk_all;
+  if (world == 1) {       // nothing to deal or gather: the plain entry writes the full-size buffers directly
+    deb_dims one = *dims;
+    if (!has_pk) one.power_idx = -1;
+    char* w1 = (char*)workspace;
+    int32_t* na1 = (int32_t*)w1;
+    void* ews1 = w1 + al256((size_t)nc * nk * 4);
+    return deb_evolve_f64(&one, ctrl, scalars, tables, kmodes, aexp_out, y_all, pk_all, tau_out, status_all, nsteps_all, na1, ews1,
+                          workspace_bytes - al256((size_t)nc * nk * 4), stream);
+  }
   const size_t RL = 21 * (size_t)nout + 2;
   char* w = (char*)workspace;
   double* kloc = (double*)w; w += al256((size_t)per * 8);

@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(128) k_tau_out(Problem P, double* tau_out, dou
       for (int i = threadIdx.x; i < DEB_ORDER_MAX / 32; i += 128) bm[i] = 0u;
       __syncthreads();
       const int* h = P.order_hdr;
-      const bool hdr_ok = h && total <= DEB_ORDER_MAX && h[0] == DEB_ORDER_MAGIC && h[1] == total && h[2] == P.shape_hash;
+      const bool hdr_ok = h && total <= DEB_ORDER_MAX && h[0] == DEB_ORDER_MAGIC && h[1] == total && h[2] == P.shape_hash && h[3] >= 0 && h[3] <= total;
       if (hdr_ok) {
         for (int i = threadIdx.x; i < total; i += 128) {
           const unsigned int m = (unsigned int)h[8 + i];
@@ -245,7 +245,22 @@ static evolve_kernel_t pick_kernel(int n, bool many_modes, bool few_modes, int* 
 }
 
 int deb_launch_team(const Problem& P, cudaStream_t st, int nsm);      // deb_team.cu
-int deb_launch_lane(const Problem& P, cudaStream_t st, int nsm);      // deb_lane.cu
+int deb_learn_order(const Problem& P, cudaStream_t st);               // deb_team.cu
+int deb_lane_supported(const Problem& P);                             // deb_lane.cu
+int deb_launch_lane(const Problem& P, cudaStream_t st, int nsm, int hybrid_ctas = 0);      // deb_lane.cu
+
+// helper stream + events of the hybrid launch (one set per device, created on first use)
+struct HybridAux { cudaStream_t s2 = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+static HybridAux* hybrid_aux(int dev) {
+  static HybridAux aux[64];
+  if (dev < 0 || dev >= 64) return nullptr;
+  HybridAux& a = aux[dev];
+  if (!a.s2) {
+    if (cudaStreamCreateWithFlags(&a.s2, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  }
+  return &a;
+}
 
 // Kernel choice can be forced for tests and measurements: DEB_VARIANT = warp | helper | team
 static int variant_forced(const char* name) { const char* v = getenv("DEB_VARIANT"); return v && !strcmp(v, name); }
@@ -260,6 +275,36 @@ static int launch_evolve(const Problem& P, cudaStream_t st) {
     // (1536 modes: 45.0 vs 44.4 ms), ~7 per SM at n = 72 (1024 modes: 32.4 vs 33.0 ms)
     const long nm = (long)P.ncosmo * P.nk;
     const bool want = getenv("DEB_VARIANT") ? variant_forced("team") : nm <= (long)nsm * (P.n > 128 ? 8 : 6);
+    // Hybrid launch (opt-in, DEB_HYBRID=1; steady state only): with a learned work list the modes of more than 0.38 x the
+    // longest step count get team CTAs, one per SM -- a second team CTA on the SM costs the slowest mode 15-20 % per step --
+    // while the shorter modes run on chain-lane warps (4 per SM fit beside a team CTA: 32 k + 31 k registers, same
+    // shared-memory carve-out).  Two kernels on two streams; both read the list's verdict word, so a rejected list
+    // degrades to the plain team launch.  Measured (tools/time_hybrid.py, profiles/r2_hybrid.txt): 296 modes 19.70 ->
+    // 19.18 ms, 512 modes 21.81 -> 21.39 ms, 768 modes 24.5 -> 32.2 ms: the team CTA does keep its single-CTA step
+    // latency (31.5 us), but a chain-lane warp beside it needs 81 us per step, so the split only pays in a narrow range.
+    // Off by default.
+    const bool hybrid = want && !getenv("DEB_VARIANT") && getenv("DEB_HYBRID") && atoi(getenv("DEB_HYBRID")) && P.mode == 0 && P.order_hdr && P.n > 128 &&
+                        nm > (long)nsm && nm <= DEB_ORDER_MAX && deb_lane_supported(P);
+    if (hybrid) {
+      HybridAux* ax = hybrid_aux(dev);
+      if (ax) {
+        Problem Q = P;
+        Q.hybrid_split = nsm;
+        Q.ticket2 = P.ticket + 8;
+        CUDA_TRY(cudaMemsetAsync(Q.ticket2, 0, sizeof(unsigned int), st));
+        CUDA_TRY(cudaEventRecord(ax->fork, st));
+        CUDA_TRY(cudaStreamWaitEvent(ax->s2, ax->fork, 0));
+        int rc = deb_launch_team(Q, st, nsm);             // (its k_learn_order is issued below, after the join)
+        if (rc == DEB_OK) {
+          rc = deb_launch_lane(Q, ax->s2, nsm, nsm);
+          if (rc != DEB_OK) return rc;
+          CUDA_TRY(cudaEventRecord(ax->join, ax->s2));
+          CUDA_TRY(cudaStreamWaitEvent(st, ax->join, 0));
+          return deb_learn_order(P, st);
+        }
+        if (rc != DEB_E_UNSUPPORTED) return rc;
+      }
+    }
     if (want) {
       const int rc = deb_launch_team(P, st, nsm);
       if (rc != DEB_E_UNSUPPORTED) return rc;

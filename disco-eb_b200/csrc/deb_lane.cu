@@ -78,17 +78,27 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) k_evolve_lane(const __grid_c
   __syncthreads();
   init_lane_tab<NT>(P, *C, *T, threadIdx.x, 32 * WARPS);
   __syncthreads();
-  const int total = P.ncosmo * P.nk;
+  int total = P.ncosmo * P.nk;
+  // hybrid launch: this kernel takes positions hybrid_split.. of the learned work list (the shorter modes), the team kernel
+  // the first hybrid_split; with a rejected list the team kernel does everything and this one has nothing to do
+  const bool hybrid = P.hybrid_split > 0;
+  const int* order = hybrid ? P.order_hdr + 8 : nullptr;
+  unsigned int* queue = hybrid ? P.ticket2 : P.ticket;
+  int nteam = 0;
+  if (hybrid) { if (P.ticket[2] != 1u) return; nteam = P.order_hdr[3]; total -= nteam; }
   LaneSync SY;
   SY.cnt = 32 * WARPS; SY.on = (P.mode == 0 && P.lockstep) ? 1 : 0;
   for (;;) {
     unsigned int tk = 0;
-    if (lane == 0) tk = atomicAdd(P.ticket, 1u);
+    if (lane == 0) tk = atomicAdd(queue, 1u);
     tk = __shfl_sync(0xffffffffu, tk, 0);
     // largest k first, cosmologies interleaved; mode -1 = out of work: with lock-step on, the warp goes through the SAME
     // call (one copy of the code, the same barrier instructions) to attend the barriers until every warp is done
     int mode = -1;
-    if (tk < (unsigned int)total) { const int kd = tk / P.ncosmo, cs = tk - kd * P.ncosmo; mode = cs * P.nk + (P.nk - 1 - kd); }
+    if (tk < (unsigned int)total) {
+      if (hybrid) mode = order[nteam + tk];
+      else { const int kd = tk / P.ncosmo, cs = tk - kd * P.ncosmo; mode = cs * P.nk + (P.nk - 1 - kd); }
+    }
     if (mode < 0 && !SY.on) break;
     integrate_mode_lane<NT>(P, *C, *T, W, SY, mode, lane, stab);
     __syncwarp();
@@ -112,27 +122,49 @@ static LaneKernel pick_lane(int nt, int np) {
   }
 }
 
-// returns DEB_OK after launching, DEB_E_UNSUPPORTED when this variant does not serve the shape
-int deb_launch_lane(const Problem& P, cudaStream_t st, int nsm) {
+static LaneKernel pick_lane12(int nt, int np) {
+  switch (nt) {
+    case 1: return {k_evolve_lane<1, 12, 1>, lane_smem_bytes<1>(np, 12)};
+    case 2: return {k_evolve_lane<2, 12, 1>, lane_smem_bytes<2>(np, 12)};
+    case 3: return {k_evolve_lane<3, 12, 1>, lane_smem_bytes<3>(np, 12)};
+    case 4: return {k_evolve_lane<4, 12, 1>, lane_smem_bytes<4>(np, 12)};
+    default: return {nullptr, 0};
+  }
+}
+
+// can the chain-lane kernel serve this shape (used by the hybrid launch before it commits the team kernel to a subset)
+int deb_lane_supported(const Problem& P) {
+  const int nt = lane_nt(P.lmaxg, P.lmaxgp, P.lmaxr, P.lmaxnu);
+  return nt != 0 && LN_NSEG * P.nch <= 32 && P.nh <= 32 && P.n <= 34 + 32 * nt && pick_lane<4, 2>(nt, P.np).smem <= 160 * 1024;
+}
+
+// returns DEB_OK after launching, DEB_E_UNSUPPORTED when this variant does not serve the shape.  hybrid_ctas > 0: the
+// lane half of a hybrid launch (4-warp CTAs, as many as fit beside one team CTA per SM), queue counter P.ticket2.
+int deb_launch_lane(const Problem& P, cudaStream_t st, int nsm, int hybrid_ctas) {
   const int nt = lane_nt(P.lmaxg, P.lmaxgp, P.lmaxr, P.lmaxnu);
   if (nt == 0 || LN_NSEG * P.nch > 32 || P.nh > 32 || P.n > 34 + 32 * nt) return DEB_E_UNSUPPORTED;
   // 8 modes in flight per SM (255 registers each) as ONE CTA of 8 warps advancing in lock-step (LN_BAR): 225.7 -> 199.0 ms
   // on 16384 modes against free-running warps; two CTAs of 4 warps in lock-step: 206.2 ms (profiles/r2_lane_lockstep.txt)
-  int warps = 8;
-  if (const char* e = getenv("DEB_LANE_WARPS")) warps = atoi(e);
-  const LaneKernel lk = warps == 4 ? pick_lane<4, 2>(nt, P.np) : pick_lane<8, 1>(nt, P.np);
-  if (warps != 4) warps = 8;
+  // small hierarchies (NT <= 4: the stage vectors take <= 56 registers per lane) run 12 warps per SM under 168 registers
+  int warps = nt <= 4 ? 12 : 8;
+  if (hybrid_ctas > 0) warps = 4;
+  else if (const char* e = getenv("DEB_LANE_WARPS")) warps = atoi(e);
+  if (warps == 12 && nt > 4) warps = 8;
+  const LaneKernel lk = warps == 4 ? pick_lane<4, 2>(nt, P.np) : (warps == 12 ? pick_lane12(nt, P.np) : pick_lane<8, 1>(nt, P.np));
+  if (warps != 4 && warps != 12) warps = 8;
   if (!lk.fn) return DEB_E_UNSUPPORTED;
   int occ = 0;
   const size_t smem_max = ((lk.smem + 127) & ~(size_t)127) + 128 + (size_t)(6 * P.nth + 3 * P.nnu) * 8;
   const bool can_stage = smem_max <= 227 * 1024;
   CUDA_TRY(cudaFuncSetAttribute((const void*)lk.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(can_stage ? smem_max : lk.smem)));
+  CUDA_TRY(cudaFuncSetAttribute((const void*)lk.fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)lk.fn, 32 * warps, lk.smem));
   if (occ < 1) return DEB_E_UNSUPPORTED;
   const long total = (long)P.ncosmo * P.nk;
   long grid = (long)nsm * occ;
   if (grid * warps > total) grid = (total + warps - 1) / warps;
-  CUDA_TRY(cudaMemsetAsync(P.ticket, 0, sizeof(unsigned int), st));
+  if (hybrid_ctas > 0) grid = hybrid_ctas;
+  else CUDA_TRY(cudaMemsetAsync(P.ticket, 0, sizeof(unsigned int), st));
   Problem Q = P;
   Q.lockstep = getenv("DEB_LANE_LOCKSTEP") ? atoi(getenv("DEB_LANE_LOCKSTEP")) : 1;
   // staged tables: on whenever one cosmology serves the whole launch and the copy fits beside the modes (measured -0.4 %

@@ -82,11 +82,21 @@ __global__ void __launch_bounds__(32 * TEAM, MINB) k_evolve_team(const __grid_co
   // (the list is used only when this launch's pre-kernel verified it entry by entry: k_tau_out -> ticket[2])
   const bool ordered = P.order_hdr && P.ticket[2] == 1u;
   const int* order = P.order_hdr + 8;
+  // hybrid launch with an accepted list: CTA b < split integrates the b-th longest mode and nothing else (one CTA per SM:
+  // the second wave of CTAs leaves at once and makes room for the chain-lane CTAs that take the shorter modes)
+  const bool hybrid = ordered && P.hybrid_split > 0;
+  // (positions [0, nteam) of the list are the team's: the modes of more than 0.38 x the longest step count, see k_learn_order)
+  const int nteam = hybrid ? P.order_hdr[3] : 0;
   bool first = true;
   for (;;) {
     if (tid == 0) {
       unsigned int t;
-      if (ordered && first) t = (G & 1) ? (unsigned int)blockIdx.x : (unsigned int)((blockIdx.x & 1) * (G / 2) + (blockIdx.x >> 1));
+      if (hybrid) {
+        if ((int)blockIdx.x >= P.hybrid_split) t = (unsigned int)total;
+        else if (first) t = (unsigned int)blockIdx.x < (unsigned int)nteam ? (unsigned int)blockIdx.x : (unsigned int)total;
+        else { const unsigned int q = (unsigned int)P.hybrid_split + atomicAdd(P.ticket, 1u); t = q < (unsigned int)nteam ? q : (unsigned int)total; }
+      }
+      else if (ordered && first) t = (G & 1) ? (unsigned int)blockIdx.x : (unsigned int)((blockIdx.x & 1) * (G / 2) + (blockIdx.x >> 1));
       else t = (ordered ? (unsigned int)G : 0u) + atomicAdd(P.ticket, 1u);
       *s_tk = t;
     }
@@ -136,11 +146,24 @@ __global__ void __launch_bounds__(1024) k_learn_order(const int* __restrict__ ns
       __syncthreads();
     }
   for (int i = threadIdx.x; i < total; i += 1024) hdr[8 + i] = 2047 - (int)(key[i] & 2047u);
+  // hybrid launches: how many modes (from the front of the list) take more than 0.38 x the longest step count.  Those go to
+  // team CTAs (31 us per step with chain-lane warps beside them), the others to chain-lane warps (81 us per step measured
+  // next to a team CTA): both halves then finish together.
+  __shared__ int nlong;
+  if (threadIdx.x == 0) nlong = 0;
   __syncthreads();
-  if (threadIdx.x == 0) { hdr[1] = total; hdr[2] = shape_hash; __threadfence(); hdr[0] = DEB_ORDER_MAGIC; }
+  {
+    const unsigned int smax = (key[0] >> 11) & 0xfffffu;
+    int c = 0;
+    for (int i = threadIdx.x; i < total; i += 1024) c += (((key[i] >> 11) & 0xfffffu) * 100u > smax * 38u) ? 1 : 0;
+    atomicAdd(&nlong, c);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) { hdr[1] = total; hdr[2] = shape_hash; hdr[3] = nlong; __threadfence(); hdr[0] = DEB_ORDER_MAGIC; }
 }
 
 typedef void (*evolve_kernel_t)(const Problem);
+int deb_learn_order(const Problem& P, cudaStream_t st);
 
 template <int TEAM, int MINB>
 static evolve_kernel_t pick_team(int n) {
@@ -164,6 +187,8 @@ int deb_launch_team(const Problem& P, cudaStream_t st, int nsm) {
   const size_t smem = team_smem_bytes(P.np, team_segrows(P.lmaxg, P.lmaxgp, P.lmaxr, P.lmaxnu));
   int occ = 0;
   CUDA_TRY(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // (same shared-memory carve-out as the chain-lane kernel, so that CTAs of both can share an SM in hybrid launches)
+  CUDA_TRY(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)kern, 32 * team, smem));
   if (occ < 1) return DEB_E_UNSUPPORTED;
   const long total = (long)P.ncosmo * P.nk;
@@ -172,6 +197,12 @@ int deb_launch_team(const Problem& P, cudaStream_t st, int nsm) {
   CUDA_TRY(cudaMemsetAsync(P.ticket, 0, sizeof(unsigned int), st));
   kern<<<(unsigned)grid, 32 * team, smem, st>>>(P);
   CUDA_TRY(cudaGetLastError());
+  if (P.hybrid_split > 0) return DEB_OK;       // hybrid launch: the list is refreshed after BOTH kernels (deb_learn_order)
+  return deb_learn_order(P, st);
+}
+
+int deb_learn_order(const Problem& P, cudaStream_t st) {
+  const long total = (long)P.ncosmo * P.nk;
   if (P.order_hdr && P.mode == 0 && total <= DEB_ORDER_MAX && !getenv("DEB_NO_ORDER")) {
     k_learn_order<<<1, 1024, 0, st>>>(P.nsteps, (int)total, P.order_hdr, P.shape_hash);
     CUDA_TRY(cudaGetLastError());
