@@ -36,7 +36,7 @@ constexpr int LN_NSEG = 4;
 // line in the SM's instruction cache.  LN_BAR is a counted CTA barrier at the top of the Jacobian phase and of every
 // stage, executed by ALL threads of the CTA every time; `barrier.red.popc` returns how many threads still have work.  A
 // warp whose work queue ran dry keeps attending (it arrives at once and sleeps in the barrier) until that count is zero.
-struct LaneSync { unsigned cnt; int on; };
+struct LaneSync { unsigned cnt; int on; int every; };     // every: a stage barrier at stages 1, 1 + every, ... (1, 2, 4 or 8)
 #ifdef DEB_CPU_EMU
 #define LN_BAR(SY, stay)
 #else
@@ -459,7 +459,7 @@ DEB_DEV void integrate_mode_lane(const Problem& P, const CtaConst& C, const Lane
     double ts = t, invts = invt0;
 #pragma unroll 1
     for (int st = 1; st <= 8; ++st) {
-      LN_BAR(SY, !idle);
+      if (SY.every == 1 || (st & (SY.every - 1)) == 1) LN_BAR(SY, !idle);
       if (idle) continue;
       if (st > 1) {
         ts = st == 2 ? t + RD_CT2 * dt : st == 3 ? t + RD_CT3 * dt : st == 4 ? t + RD_CT4 * dt : st == 5 ? t + RD_CT5 * dt : t + dt;

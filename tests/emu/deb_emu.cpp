@@ -175,7 +175,7 @@ static void run_all_lane(const Problem& P) {
 #pragma omp parallel
   {
     std::vector<LaneWs<NT>> ws(1);
-    LaneSync sy; sy.cnt = 32; sy.on = 0;
+    LaneSync sy; sy.cnt = 32; sy.on = 0; sy.every = 1;
 #pragma omp for schedule(dynamic, 1)
     for (int m = 0; m < total; ++m) integrate_mode_lane<NT>(P, C, tab[0], ws[0], sy, total - 1 - m);
   }
