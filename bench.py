@@ -53,7 +53,7 @@ METRIC = "k-modes/sec (ms per P(k), N_k=512, in ms_per_step)"
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_evolve_team<3,4,2> launch on this workload (ncu --set full),
 # read from the committed summary so that the number and its evidence cannot drift apart
-NCU_SUMMARY = os.path.join(ROOT, "profiles", "r1_v24_k_evolve_team_ncu_summary.txt")
+NCU_SUMMARY = os.path.join(ROOT, "profiles", "r2_final_k_team_ncu_summary.txt")
 
 
 def ncu_dram_bytes_per_launch():

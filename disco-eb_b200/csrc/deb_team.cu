@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(32 * TEAM, MINB) k_evolve_team(const __grid_co
     long long t_start_ = 0;
     if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start_));
 #endif
-    integrate_mode_team<NE, TEAM>(P, *C, W, X, *box, mode, ltid);
+    integrate_mode_team<NE, TEAM>(P, *C, W, X, *box, mode, ltid, 0, nullptr);
     __syncthreads();
 #ifdef DEB_TEAM_TIMING
     if (tid == 0 && mode < 4096) {
@@ -120,6 +120,85 @@ __global__ void __launch_bounds__(32 * TEAM, MINB) k_evolve_team(const __grid_co
       g_mode_log[mode][0] = t_start_; g_mode_log[mode][1] = t_end_; g_mode_log[mode][2] = smid_; g_mode_log[mode][3] = s_tk[1];
     }
 #endif
+  }
+}
+
+// Two teams of four warps in ONE CTA per SM (instead of two CTAs of one team): same work per SM, one copy of the CTA
+// constants, and the two serial warps advance through the step code together (DuoSync, deb_team.cuh).  Team q of the CTA
+// synchronises on named barriers 1+5q .. 5+5q; barrier 0 is used by the whole CTA during set-up only.
+static __host__ __device__ size_t duo_team_bytes(int np, int segrows) {
+  return al16((warp_ws_doubles(np) + team_ws_doubles(segrows)) * sizeof(double)) + al16(sizeof(TeamBox));
+}
+static __host__ __device__ size_t duo_smem_bytes(int np, int segrows) {
+  return al16(sizeof(CtaConst)) + 4 * al16((size_t)np * sizeof(int)) + 2 * duo_team_bytes(np, segrows) + 64;
+}
+template <int NE>
+__global__ void __launch_bounds__(256, 1) k_evolve_duo(const __grid_constant__ Problem P) {
+  constexpr int TEAM = 4;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  CtaConst* C = reinterpret_cast<CtaConst*>(smem_raw);
+  size_t off = al16(sizeof(CtaConst));
+  int* tail = reinterpret_cast<int*>(smem_raw + off);
+  off += al16((size_t)P.np * sizeof(int));
+  int* eslot = reinterpret_cast<int*>(smem_raw + off);
+  off += al16((size_t)P.np * sizeof(int));
+  int* epos = reinterpret_cast<int*>(smem_raw + off);
+  off += al16((size_t)P.np * sizeof(int));
+  int* tailpos = reinterpret_cast<int*>(smem_raw + off);
+  off += al16((size_t)P.np * sizeof(int));
+  const int segrows = team_segrows(P.lmaxg, P.lmaxgp, P.lmaxr, P.lmaxnu);
+  const int tq = threadIdx.x >> 7, tid = threadIdx.x & 127;          // team of the CTA, thread of the team
+  const size_t per_team = duo_team_bytes(P.np, segrows);
+  double* wsb = reinterpret_cast<double*>(smem_raw + off + tq * per_team);
+  TeamBox* box = reinterpret_cast<TeamBox*>(smem_raw + off + tq * per_team + al16((warp_ws_doubles(P.np) + team_ws_doubles(segrows)) * sizeof(double)));
+  // [0..1] ticket of team 0 / 1, [2..3] role rotation, [4..5] the rendezvous counters
+  unsigned int* s_ctl = reinterpret_cast<unsigned int*>(smem_raw + off + 2 * per_team);
+  init_cta_const(P, *C, tail, threadIdx.x, 256);
+  if (threadIdx.x < 2) reinterpret_cast<int*>(s_ctl + 4)[threadIdx.x] = 0x7fffffff;
+  __syncthreads();
+  init_team_const(P, *C, eslot, epos, tailpos, threadIdx.x, 256);
+  WarpWs W;
+  carve(W, wsb, P.np);
+  TeamWs X;
+  carve_team(X, wsb + warp_ws_doubles(P.np), segrows, eslot, epos, tailpos);
+  // warp slot w issues from scheduler w % 4: the second team rotates its roles by two warps so that the two serial warps
+  // (and the two background warps) sit on different schedulers (see k_evolve_team)
+  if (tid == 0) {
+    unsigned int wslot;
+    asm volatile("mov.u32 %0, %%warpid;" : "=r"(wslot));
+    s_ctl[2 + tq] = ((wslot / TEAM) & 1u) * (TEAM / 2);
+  }
+  __syncthreads();
+  const int ltid = ((((tid >> 5) + TEAM - (int)s_ctl[2 + tq]) % TEAM) << 5) | (tid & 31);
+  const int bb = 1 + 5 * tq;
+  DuoSync duo;
+  duo.mine = reinterpret_cast<int*>(s_ctl + 4) + tq;
+  duo.other = reinterpret_cast<int*>(s_ctl + 4) + (tq ^ 1);
+  duo.v = 0; duo.every = P.lockstep; duo.attached = false;
+  duo.K = 1 + (P.lockstep ? (8 + P.lockstep - 1) / P.lockstep : 0);
+  const int total = P.ncosmo * P.nk;
+  // work list as in k_evolve_team, with G = 2 gridDim.x teams: the teams of CTA b start on positions b and G/2 + b of an
+  // accepted cost-ordered list (one long and one medium mode per SM), then everybody pulls from the ticket counter
+  const int G = 2 * gridDim.x;
+  const bool ordered = P.order_hdr && P.ticket[2] == 1u;
+  const int* order = P.order_hdr + 8;
+  bool first = true;
+  for (;;) {
+    if (tid == 0) {
+      unsigned int t;
+      if (ordered && first) t = (unsigned int)(tq * (G / 2) + blockIdx.x);
+      else t = (ordered ? (unsigned int)G : 0u) + atomicAdd(P.ticket, 1u);
+      s_ctl[tq] = t;
+    }
+    first = false;
+    asm volatile("bar.sync %0, 128;" ::"r"(bb) : "memory");
+    const unsigned int tk = s_ctl[tq];
+    if (tk >= (unsigned int)total) break;
+    const int kd = tk / P.ncosmo, cs = tk - kd * P.ncosmo;
+    const int mode = ordered ? order[tk] : cs * P.nk + (P.nk - 1 - kd);
+    integrate_mode_team<NE, TEAM, true>(P, *C, W, X, *box, mode, ltid, bb, &duo);
+    if ((ltid >> 5) == 0) duo.detach(ltid & 31);
+    asm volatile("bar.sync %0, 128;" ::"r"(bb) : "memory");
   }
 }
 
@@ -184,6 +263,30 @@ int deb_launch_team(const Problem& P, cudaStream_t st, int nsm) {
   if (team == 4) kern = minb >= 4 ? pick_team<4, 4>(P.n) : (minb == 3 ? pick_team<4, 3>(P.n) : pick_team<4, 2>(P.n));
   else if (team == 8) kern = pick_team<8, 2>(P.n);
   if (!kern) return DEB_E_UNSUPPORTED;
+  // two teams per CTA, serial warps in lock-step (k_evolve_duo): the default geometry; DEB_DUO=0 keeps two CTAs of one team
+  int duo = team == 4 && minb == 2 && P.hybrid_split == 0 && P.mode == 0;
+  long duo_min = 2L * nsm;
+  if (const char* e = getenv("DEB_DUO")) { duo = duo && atoi(e) != 0; if (atoi(e) == 2) duo_min = 2; }      // 2: at any size (tests)
+  if (duo) {
+    const int ne = (P.n + 127) / 128;
+    evolve_kernel_t dk = ne <= 1 ? k_evolve_duo<1> : (ne <= 2 ? k_evolve_duo<2> : (ne <= 3 ? k_evolve_duo<3> : nullptr));
+    const size_t dsmem = duo_smem_bytes(P.np, team_segrows(P.lmaxg, P.lmaxgp, P.lmaxr, P.lmaxnu));
+    const long total = (long)P.ncosmo * P.nk;
+    // (below two teams' worth of modes per SM the one-team CTAs spread over more SMs: measured equal or better there)
+    if (dk && dsmem <= 227 * 1024 && total >= duo_min) {
+      Problem Q = P;
+      Q.lockstep = 1;
+      if (const char* e = getenv("DEB_DUO_LOCKSTEP")) Q.lockstep = atoi(e);
+      if (Q.lockstep != 0 && Q.lockstep != 1 && Q.lockstep != 2 && Q.lockstep != 4 && Q.lockstep != 8) Q.lockstep = 1;
+      CUDA_TRY(cudaFuncSetAttribute((const void*)dk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem));
+      long grid = nsm;
+      if (grid > (total + 1) / 2) grid = (total + 1) / 2;
+      CUDA_TRY(cudaMemsetAsync(P.ticket, 0, sizeof(unsigned int), st));
+      dk<<<(unsigned)grid, 256, dsmem, st>>>(Q);
+      CUDA_TRY(cudaGetLastError());
+      return deb_learn_order(P, st);
+    }
+  }
   const size_t smem = team_smem_bytes(P.np, team_segrows(P.lmaxg, P.lmaxgp, P.lmaxr, P.lmaxnu));
   int occ = 0;
   CUDA_TRY(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -121,22 +121,30 @@ DEB_DEV void init_team_const(const Problem& P, const CtaConst& C, int* eslot, in
 #define DEB_TREGS(type, name, dims) type name##_all[NT] dims
 #define DEB_TUSE(name) auto& name = name##_all[tid]
 #define DEB_IF_WARP(w)
+#define DEB_DUO_TOP()
+#define DEB_DUO_STAGE(st)
 #define DEB_T_OR(name) ([&]() { int a_ = 0; for (int l_ = 0; l_ < NT; ++l_) a_ |= (name##_all[l_] != 0); return a_; }())
 #else
 #define DEB_TID_PARAM , const int tid
 #define DEB_T_BEGIN {
 #define DEB_T_END }
-#define DEB_T_BAR() __syncthreads()
+// (DUO: two teams share one CTA -- deb_team.cu, k_evolve_duo --, so a team's barriers are named ones, ids bb .. bb+4)
+#define DEB_T_BAR() do { if (DUO) asm volatile("bar.sync %0, %1;" ::"r"(bb), "n"(32 * TEAM) : "memory"); else __syncthreads(); } while (0)
 // barrier of the team without warp 1 (named barrier 1): warp 1 evaluates the next stage's background from the first
 // barrier of a stage to the last and must not hold up the solve
-#define DEB_T_BAR_BUT1() do { if (TEAM >= 3) { if (wid != 1) asm volatile("bar.sync 1, %0;" ::"n"(32 * TEAM - 32) : "memory"); } else __syncthreads(); } while (0)
+#define DEB_T_BAR_BUT1() do { if (TEAM >= 3) { if (wid != 1) DEB_NB_SYNC(1, 32 * TEAM - 32); } else DEB_T_BAR(); } while (0)
 // producer/consumer hand-off between two warps (PTX named barriers): the producer arrives and goes on, the consumer waits
-#define DEB_NB_ARRIVE(id, nthr) asm volatile("bar.arrive %0, %1;" ::"n"(id), "n"(nthr) : "memory")
-#define DEB_NB_SYNC(id, nthr) asm volatile("bar.sync %0, %1;" ::"n"(id), "n"(nthr) : "memory")
+#define DEB_NB_ARRIVE(id, nthr) do { if (DUO) asm volatile("bar.arrive %0, %1;" ::"r"(bb + (id)), "n"(nthr) : "memory"); \
+                                     else asm volatile("bar.arrive %0, %1;" ::"n"(id), "n"(nthr) : "memory"); } while (0)
+#define DEB_NB_SYNC(id, nthr) do { if (DUO) asm volatile("bar.sync %0, %1;" ::"r"(bb + (id)), "n"(nthr) : "memory"); \
+                                   else asm volatile("bar.sync %0, %1;" ::"n"(id), "n"(nthr) : "memory"); } while (0)
 #define DEB_TREGS(type, name, dims) type name dims
 #define DEB_TUSE(name)
 #define DEB_IF_WARP(w) if (wid == (w))
-#define DEB_T_OR(name) __syncthreads_or(name)
+#define DEB_T_OR(name) (DUO ? team_or_named(name, bb, 32 * TEAM) : __syncthreads_or(name))
+// the cross-team rendezvous of a two-team CTA (warp 0 of each team; see DuoSync)
+#define DEB_DUO_TOP() do { if (DUO) { DEB_IF_WARP(0) duo->top(lane); } } while (0)
+#define DEB_DUO_STAGE(st) do { if (DUO) { DEB_IF_WARP(0) duo->stage(st, lane); } } while (0)
 #endif
 
 // element e of the stage vector just solved: x0 for e = 0, otherwise r plus the deferred forward-sweep carry
@@ -241,8 +249,44 @@ DEB_DEV void team_jac_compute(const Problem& P, const CtaConst& C, const Cosmo& 
   DEB_LANES_END
 }
 
-template <int NE, int TEAM>
-DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W, const TeamWs& X, TeamBox& box, int mode DEB_TID_PARAM) {
+#ifndef DEB_CPU_EMU
+// Two teams in one CTA (k_evolve_duo): their serial warps rendezvous at the top of every step and at every `every`-th
+// stage so that both run the same stretch of the (170 KB, straight-line) step code at the same time and share its
+// instruction-cache lines -- the same remedy as the chain-lane kernel's lock-step, here between two warps only.
+// The rendezvous is a pair of counters in shared memory on a common virtual clock (K ticks per step, step tops at
+// multiples of K): a team posts the tick it reached and waits until the other has posted at least as much.  A team
+// between modes (work fetch, initial conditions) or out of work posts INT_MAX = "do not wait for me" and re-attaches at
+// the other's next step top.  No data travels through the counters; they are read and written with shared-memory atomics
+// by lane 0 only (compute-sanitizer's racecheck stays clean).
+struct DuoSync {
+  int* mine; int* other;
+  int v, K, every; bool attached;
+  __device__ __forceinline__ void post_wait(int lane) {
+    if (lane == 0) { atomicExch(mine, v); while (atomicOr(other, 0) < v) { } }
+    __syncwarp();
+  }
+  __device__ __forceinline__ void top(int lane) {
+    if (attached) v = (v / K + 1) * K;
+    else { const int a = __shfl_sync(0xffffffffu, lane == 0 ? atomicOr(other, 0) : 0, 0); v = ((a == 0x7fffffff ? v : a) + K - 1) / K * K; attached = true; }
+    post_wait(lane);
+  }
+  __device__ __forceinline__ void stage(int st, int lane) { if (every && ((st - 1) & (every - 1)) == 0) { ++v; post_wait(lane); } }
+  __device__ __forceinline__ void detach(int lane) { if (lane == 0) atomicExch(mine, 0x7fffffff); attached = false; }
+};
+// __syncthreads_or over one team of a two-team CTA (named barrier `id`, nthr threads)
+static __device__ __forceinline__ int team_or_named(int pred, int id, int nthr) {
+  int r;
+  asm volatile("{ .reg .pred p, q; setp.ne.s32 p, %1, 0; barrier.red.or.pred q, %2, %3, p; selp.s32 %0, 1, 0, q; }"
+               : "=r"(r) : "r"(pred), "r"(id), "r"(nthr) : "memory");
+  return r;
+}
+#define DEB_DUO_PARAM , const int bb, DuoSync* duo
+#else
+#define DEB_DUO_PARAM
+#endif
+
+template <int NE, int TEAM, bool DUO = false>
+DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W, const TeamWs& X, TeamBox& box, int mode DEB_TID_PARAM DEB_DUO_PARAM) {
   constexpr int NT = 32 * TEAM;
 #ifndef DEB_CPU_EMU
   const int lane = tid & 31, wid = tid >> 5;
@@ -344,6 +388,7 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
   DEB_T_BAR();
 
   while (t < t1 && nsteps < P.max_steps && status == 0) {
+    DEB_DUO_TOP();
     if (P.mode == 3) {
       if (nsteps >= DEB_LDG(P.rp_n + mode)) break;
       tnext = DEB_LDG(P.rp_tnext + (size_t)mode * P.rp_stride + nsteps);
@@ -609,6 +654,7 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
     double errnorm2 = 0.0;
 #pragma unroll 1
     for (int st = 1; st <= 8; ++st) {
+      DEB_DUO_STAGE(st);
       DEB_TICK3_START
       if (st > 1) {
         TeamBg& cur = box.bg[st & 1];                  // posted by warp 1 during stage st-1

@@ -139,6 +139,34 @@ def test_context_reuse_across_shapes(gpu_lib, tables, monkeypatch):
         assert np.array_equal(out["y"], ref[key]["y"]) and np.array_equal(out["nsteps"], ref[key]["nsteps"]), key
 
 
+def test_two_team_cta_is_bit_identical_to_one_team_cta(gpu_lib, tables, monkeypatch):
+    """k_evolve_duo (two teams per CTA, serial warps in lock-step; the default for launches of >= 2 modes per SM slot)
+    against k_evolve_team: the rendezvous moves no data, so every output bit and every step count must agree -- odd
+    mode counts (one team of the last CTA idle), several cosmologies, several output times, with and without a learned
+    work list, every lock-step spacing."""
+    from discoeb_b200 import _cabi
+    tab = tables["fiducial"]
+    monkeypatch.setenv("DEB_VARIANT", "team")
+    ctrl = _cabi.make_ctrl(rtol=1e-4, atol=1e-4)
+    def run(nk, ncosmo, dims5, nout):
+        lg, lp, lr, ln, nq = dims5
+        dims = _cabi.make_dims(ncosmo=ncosmo, nk=nk, nout=nout, lmaxg=lg, lmaxgp=lp, lmaxr=lr, lmaxnu=ln, nqmax=nq, nth=tab.nth,
+                               nnu=tab.nnu, max_steps=2048, power_idx=4)
+        ks = np.geomspace(1e-3, 1.0, nk)
+        sc = np.repeat(tab.scalars[None], ncosmo, 0); tb = np.repeat(tab.tables[None], ncosmo, 0)
+        return gpu_lib.evolve_host(dims, ctrl, sc, tb, ks, np.geomspace(0.05, 1.0, nout), want_pk=True)
+    for shape in ((37, 1, (31, 31, 31, 31, 5), 1), (12, 3, (11, 11, 11, 8, 3), 3), (5, 1, (5, 4, 6, 3, 4), 2), (64, 1, (16, 16, 16, 16, 3), 1)):
+        monkeypatch.setenv("DEB_DUO", "0")
+        ref = run(*shape)
+        assert np.all(ref["status"] == 0)
+        for ls in ("2", "0", "1", "4", "8"):
+            monkeypatch.setenv("DEB_DUO", "2"); monkeypatch.setenv("DEB_DUO_LOCKSTEP", ls)
+            for rep in range(2):          # second call: the learned work list is in use
+                out = run(*shape)
+                assert np.array_equal(out["status"], ref["status"]) and np.array_equal(out["nsteps"], ref["nsteps"]), (shape, ls, rep)
+                assert np.array_equal(out["y"], ref["y"]) and np.array_equal(out["pk"], ref["pk"]), (shape, ls, rep)
+
+
 def test_gpu_matches_cpu_build_of_same_source(gpu_lib, emu_lib, tables):
     """Same source, two compilers: any difference beyond round-off is a GPU-only defect
     (missing __syncwarp, shuffle misuse, shared-memory race)."""
