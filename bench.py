@@ -51,9 +51,9 @@ WORKLOAD = dict(name="config2: LCDM + 1 massive nu, lmax=31 (32 multipoles), nq=
 METRIC = "k-modes/sec (ms per P(k), N_k=512, in ms_per_step)"
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_evolve_team<3,4,2> launch on this workload (ncu --set full),
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_evolve_duo<3> launch on this workload (ncu --set full),
 # read from the committed summary so that the number and its evidence cannot drift apart
-NCU_SUMMARY = os.path.join(ROOT, "profiles", "r2_final_k_team_ncu_summary.txt")
+NCU_SUMMARY = os.path.join(ROOT, "profiles", "r2_final_k_duo_ncu_summary.txt")
 
 
 def ncu_dram_bytes_per_launch():
@@ -416,16 +416,16 @@ def run_ours(args, rank, world):
                                              "(deb_evolve_sharded_f64)" if world > 1 else "1 GPU"),
                                 state="steady state: the caller's workspace holds the work list learned from the previous call (DESIGN.md section 3)"),
                     roofline=dict(bound="fp64", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak,
-                                  traffic=ncu_dram_bytes_per_launch(), kernel="k_evolve_team<3,4,2> (one CTA of 4 warps per mode)",
+                                  traffic=ncu_dram_bytes_per_launch(), kernel="k_evolve_duo<3> (one 4-warp team per mode, two teams per CTA, one CTA per SM)",
                                   note="FP64 FMA pipe (the path is neither HBM- nor tensor-bound); peak measured on this GPU by "
                                        "deb_fp64_peak_tflops (dependent-free DFMA streams) x n_gpus; algorithmic flops = "
-                                       "(370 n + 3000) x attempted steps, n=265; traffic = dram bytes read+written per k_evolve_team "
+                                       "(370 n + 3000) x attempted steps, n=265; traffic = dram bytes read+written per k_evolve_duo "
                                        f"launch from {os.path.relpath(NCU_SUMMARY, ROOT)} (HBM is idle)"),
                     e2e=dict(value=nk_tot / (e2e * 1e-3), unit="k-modes/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
                              ms_per_step=e2e),
                     gpu_launches=launches * args.steps,
-                    gpu_launches_note=("k_tau_out, k_evolve_team, k_learn_order per pass" if world == 1 else
-                                       "k_take_modes, k_tau_out, k_evolve_team, k_learn_order, k_pack_rows, k_unpack_rows per pass per rank (+ NCCL's all-gather kernel)"),
+                    gpu_launches_note=("k_tau_out, k_evolve_duo, k_learn_order per pass" if world == 1 else
+                                       "k_take_modes, k_tau_out, k_evolve_duo, k_learn_order, k_pack_rows, k_unpack_rows per pass per rank (+ NCCL's all-gather kernel)"),
                     clocks=clocks)
         if parity is not None:
             line["parity"] = parity
