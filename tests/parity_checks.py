@@ -18,6 +18,8 @@ Tolerances (float64; north_star asks for 1e-5 relative on transfer functions / P
   50*rtol on the matter transfer functions, and at least half of all modes must be of the
   first kind.
 """
+import os
+
 import numpy as np
 
 import helpers
@@ -179,7 +181,7 @@ def check_adaptive(lib, tables, name):
 # tools/make_golden_tangent.py).  Bars: replay of the oracle's step sequence 1e-6 (north_star: 1e-5) of each
 # field's tangent scale; free-running, modes whose step counts equal the oracle's: 1e-5 for <= 100 steps.
 # ---------------------------------------------------------------------------------------------------
-TANGENT_CASES = ("default_n72", "w0wa_n43", "fisher_n265", "kscaled_n72")
+TANGENT_CASES = ("default_n72", "w0wa_n43", "fisher_n265", "kscaled_n72", "config5_n265")
 
 
 def load_tangent_case(name):
@@ -233,6 +235,67 @@ def check_tangent_replay(lib, name, tol=1e-6):
                 worst = max(worst, e)
                 assert e < tol, (name, full, m, d, e)
     return worst
+
+
+# The tangent oracle pinned against the REFERENCE's functions (tools/make_reference_tangent.py): central differences with
+# a Richardson step of the reference's ICs -> Rodas5Transformed.step along the recorded step sequence -> interpolation ->
+# convert_to_output_variables -> get_power, run through tools/refshim.  Bar: 2e-6 of the field's tangent scale plus ten
+# times the Richardson error estimate (differences of ~1e-4 relative steps resolve 1e-8 .. 1e-7 on well-scaled fields; a
+# few tiny, cancellation-dominated fields are limited by the differencing, not by the tangent).
+REFERENCE_TANGENT_CASES = ("default_n72", "w0wa_n43", "fisher_n265")
+
+
+def load_reference_tangent(name):
+    fn = os.path.join(helpers.GOLD, f"reference_tangent_{name}.npz")
+    if not os.path.exists(fn):
+        import pytest
+        pytest.skip(f"{os.path.basename(fn)} not generated")
+    z = np.load(fn, allow_pickle=False)
+    return {k: z[k] for k in z.files}
+
+
+def reference_tangent_diffs(name, dy, dyfull=None, dpk=None):
+    """``dy[direction, mode, nout, 20]`` (fixture direction order) against the differenced reference; asserts the bar and
+    returns the worst scaled deviation over the fields whose Richardson estimate is below 1e-8 of their scale."""
+    case, ref = load_tangent_case(name), load_reference_tangent(name)
+    worst = 0.0
+    for im, m in enumerate(ref["modes"]):
+        for idd, d in enumerate(ref["dir_index"]):
+            for got, key, prim in ((dy, "dy", case["y"][m]), (dyfull, "dyfull", case["yfull"][m])):
+                if got is None:
+                    continue
+                fd, err = ref[key][im, idd], ref[key + "_err"][im, idd]
+                ax = tuple(range(prim.ndim - 1))
+                # the scale of tangent_scaled_diff, kept per field
+                fmax = np.maximum(np.abs(prim).max(axis=ax), 1e-300); dmax = np.abs(fd).max(axis=ax)
+                sc = np.maximum(dmax, fmax * np.median(dmax / fmax))
+                nine = 9 if prim.shape[-1] == 20 else 4
+                sc[nine] = max(sc[nine], sc[nine + 2], sc[nine + 4])
+                if prim.shape[-1] != 20:          # raw state: a multipole is measured against its hierarchy
+                    sc = np.maximum(sc, helpers.hierarchy_scales(fd, case["dims"]))
+                dev = np.abs(got[d, m] - fd)
+                assert np.all(dev <= 2e-6 * sc + 10.0 * err), (name, key, int(m), int(d), float((dev / sc).max()))
+                ok = err.max(axis=ax) < 1e-8 * sc           # fields the differencing resolves well
+                if np.any(ok):
+                    worst = max(worst, float((dev.max(axis=ax) / sc)[ok].max()))
+            if dpk is not None:
+                rel = np.abs(dpk[d, m] / ref["dpk4"][im, idd] - 1.0)
+                assert np.all(rel <= 2e-6 + 10.0 * np.abs(ref["dpk4_err"][im, idd] / ref["dpk4"][im, idd])), (name, "dpk", int(m), int(d), rel)
+    return worst
+
+
+def check_tangent_replay_vs_reference(lib, name):
+    """The kernel's tangent replay against the differenced reference directly."""
+    case = load_tangent_case(name)
+    ctrl = _cabi.make_ctrl(rtol=float(case["rtol"]), atol=float(case["rtol"]))
+    got = {}
+    for full in (False, True):
+        dims = tangent_dims(case, return_full=full)
+        _, dy, _, _ = lib.debug_replay_tangent(dims, ctrl, case["scalars"][None], case["tables"][None], case["kmodes"], case["aexp_out"],
+                                               case["d_scalars"][:, None], case["d_tables"][:, None], case["rp_tnext"],
+                                               case["rp_dtnext"], case["rp_keep"], case["nsteps"], d_kmodes=case.get("d_kmodes"))
+        got[full] = dy[:, 0]
+    return reference_tangent_diffs(name, got[False], got[True])
 
 
 def check_tangent_adaptive(lib, name):

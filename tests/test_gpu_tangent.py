@@ -16,6 +16,13 @@ def test_tangent_replay_of_oracle_step_sequence(gpu_lib, name):
     print(name, "worst scaled tangent deviation", worst)
 
 
+@pytest.mark.parametrize("name", pc.REFERENCE_TANGENT_CASES)
+def test_tangent_replay_against_the_differenced_reference(gpu_lib, name):
+    """The CUDA tangent kernel against central differences (+ Richardson) of the REFERENCE's own step function, run from
+    its sources by tools/make_reference_tangent.py (tests/golden/reference_tangent_*.npz)."""
+    pc.check_tangent_replay_vs_reference(gpu_lib, name)
+
+
 @pytest.mark.parametrize("name", ("default_n72", "w0wa_n43", "kscaled_n72"))
 def test_tangent_adaptive_against_oracle(gpu_lib, name):
     pc.check_tangent_adaptive(gpu_lib, name)

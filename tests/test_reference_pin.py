@@ -119,3 +119,25 @@ def test_lane_kernel_source_replays_reference_step_sequence(emu_lib, tables, nam
     monkeypatch.setenv("DEB_EMU_LANE", "1")
     pc.check_reference_step(emu_lib, tables, name)
     pc.check_replay(emu_lib, tables, name)
+
+
+# ---- forward tangents: the complex-step oracle against the differenced reference (tools/make_reference_tangent.py) ----
+@pytest.mark.parametrize("name", pc.REFERENCE_TANGENT_CASES)
+def test_tangent_oracle_vs_differenced_reference(name):
+    case = pc.load_tangent_case(name)
+    ref = pc.load_reference_tangent(name)
+    worst = pc.reference_tangent_diffs(name, case["dy"], case["dyfull"], case["dpk4"])
+    # the pieces in front of the solve: initial conditions, start time, output times
+    for im, m in enumerate(ref["modes"]):
+        for idd, d in enumerate(ref["dir_index"]):
+            s0 = np.abs(case["dy0"][d, m]).max()
+            assert np.all(np.abs(ref["dy0"][im, idd] - case["dy0"][d, m]) <= 1e-7 * s0 + 10 * ref["dy0_err"][im, idd]), (name, m, d)
+            if case["dtau_start"][d, m] != 0.0:
+                assert abs(ref["dtau_start"][im, idd] / case["dtau_start"][d, m] - 1) < 1e-6, (name, m, d)
+                np.testing.assert_allclose(ref["dtau_out"][im, idd], case["dtau_out"][d], rtol=1e-7)
+    print(name, "worst scaled deviation on the well-resolved fields:", worst)
+
+
+@pytest.mark.parametrize("name", pc.REFERENCE_TANGENT_CASES)
+def test_kernel_source_tangent_vs_differenced_reference(emu_lib, name):
+    pc.check_tangent_replay_vs_reference(emu_lib, name)

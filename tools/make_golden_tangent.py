@@ -64,6 +64,10 @@ CASES = {
     "w0wa_n43": (dict(w_DE_0=-0.9, w_DE_a=0.1), (5, 4, 6, 3, 4), [2e-3, 0.2], [0.5], 1e-3, ("w_DE_a", "Omegab")),
     "fisher_n265": ({}, (31, 31, 31, 31, 5), [0.01, 0.3], [0.5, 1.0], 1e-4, ("Omegam",)),
     "fisher_n265x2": ({}, (31, 31, 31, 31, 5), [0.02], [0.5, 1.0], 1e-4, ("Omegab", "H0")),      # seeds for the full-size property test
+    # BASELINE config 5 (Fisher Jacobian: n=265, a_out = [0.5, 1], 7 directions): every 32nd mode of the 512-mode grid,
+    # the ~600-step k=10 mode included
+    "config5_n265": ({}, (31, 31, 31, 31, 5), list(np.geomspace(1e-4, 10.0, 512)[31::32]), [0.5, 1.0], 1e-4,
+                     ("Omegam", "Omegab", "w_DE_0", "w_DE_a", "H0", "n_s", "A_s")),
     # wavenumbers that move with the parameter (k = const x h, nb_discoeb_rsd_eyes_plot.ipynb cell 5): d k / d H0 = k / H0;
     # the second direction moves k alone (all other seeds zero)
     "kscaled_n72": ({}, (11, 11, 11, 8, 3), [2e-3, 0.1], [0.3, 1.0], 1e-4, ("H0", "n_s")),
