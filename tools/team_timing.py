@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "disco-eb_b200")); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import helpers
 from discoeb_b200 import _cabi
-lib = _cabi.default_library()
+lib = _cabi.Library(os.path.join(ROOT, 'disco-eb_b200', 'csrc', '_obj', 'libdeb_timing.so')) if os.path.exists(os.path.join(ROOT, 'disco-eb_b200', 'csrc', '_obj', 'libdeb_timing.so')) else _cabi.default_library()
 tab = helpers.load_tables("fiducial")
 nk = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 kmax = float(sys.argv[2]) if len(sys.argv) > 2 else 10.0
