@@ -53,7 +53,12 @@ static int nccl_load() {
 #define NCCL_TRY(x) do { ncclResult_t r_ = (x); if (r_ != 0) { \
   fprintf(stderr, "[discoeb_b200] NCCL error %s at %s:%d\n", g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "?", __FILE__, __LINE__); return DEB_E_CUDA; } } while (0)
 
-struct deb_comm { ncclComm_t nccl; int world, rank; };
+// (the host entry keeps its device arena, stream and events on the communicator: nothing is allocated per call, and the
+//  work list learned by one call -- it lives in the workspace part of the arena -- serves the next one)
+struct deb_comm {
+  ncclComm_t nccl; int world, rank;
+  char* arena = nullptr; size_t arena_bytes = 0; cudaStream_t st = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr;
+};
 
 // local share of rank r: modes r, r + W, ...
 static inline int share(int nk, int world, int rank) { return nk > rank ? (nk - rank + world - 1) / world : 0; }
@@ -141,6 +146,10 @@ int deb_comm_create_on(int32_t device, int32_t world, int32_t rank, const void* 
 void deb_comm_destroy(deb_comm* c) {
   if (!c) return;
   if (c->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl);
+  if (c->e0) cudaEventDestroy(c->e0);
+  if (c->e1) cudaEventDestroy(c->e1);
+  if (c->st) cudaStreamDestroy(c->st);
+  if (c->arena) cudaFree(c->arena);
   delete c;
 }
 
@@ -233,15 +242,24 @@ int deb_evolve_sharded_host_f64(deb_comm* comm, int32_t device, const deb_dims* 
   const size_t b_sc = al256(nc * DEB_NSCAL * 8), b_tb = al256(nc * tl * 8), b_k = al256(nk * 8), b_a = al256(nout * 8),
                b_y = al256(nc * nk * nout * 20 * 8), b_pk = al256(nc * nk * nout * 8), b_tau = al256(nc * nout * 8), b_i = al256(nc * nk * 4),
                b_ws = al256(deb_sharded_workspace_bytes(dims, comm->world));
-  char* d = nullptr;
-  cudaStream_t st = nullptr;
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
   int rc = DEB_OK;
-  if (cudaMalloc((void**)&d, b_sc + b_tb + b_k + b_a + b_y + b_pk + b_tau + 2 * b_i + b_ws) != cudaSuccess ||
-      cudaStreamCreate(&st) != cudaSuccess || cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) rc = DEB_E_CUDA;
+  const size_t need = b_sc + b_tb + b_k + b_a + b_y + b_pk + b_tau + 2 * b_i + b_ws;
+  if (!comm->st && (cudaStreamCreate(&comm->st) != cudaSuccess || cudaEventCreate(&comm->e0) != cudaSuccess ||
+                    cudaEventCreate(&comm->e1) != cudaSuccess)) return DEB_E_CUDA;
+  if (need > comm->arena_bytes) {
+    if (comm->arena) { cudaStreamSynchronize(comm->st); cudaFree(comm->arena); comm->arena = nullptr; comm->arena_bytes = 0; }
+    if (cudaMalloc((void**)&comm->arena, need) != cudaSuccess) return DEB_E_CUDA;
+    comm->arena_bytes = need;
+    // (a fresh arena starts zeroed: the workspace must never present a stale work-list header)
+    if (cudaMemsetAsync(comm->arena, 0, need, comm->st) != cudaSuccess) return DEB_E_CUDA;
+  }
+  // the workspace sits at the FRONT of the arena (fixed offset whatever the call shape, like ctx_evolve's)
+  char* d = comm->arena;
+  cudaStream_t st = comm->st;
+  cudaEvent_t e0 = comm->e0, e1 = comm->e1;
   if (rc == DEB_OK) {
-    char* p_sc = d; char* p_tb = p_sc + b_sc; char* p_k = p_tb + b_tb; char* p_a = p_k + b_k; char* p_y = p_a + b_a; char* p_pk = p_y + b_y;
-    char* p_tau = p_pk + b_pk; char* p_st = p_tau + b_tau; char* p_ns = p_st + b_i; char* p_ws = p_ns + b_i;
+    char* p_ws = d; char* p_sc = p_ws + b_ws; char* p_tb = p_sc + b_sc; char* p_k = p_tb + b_tb; char* p_a = p_k + b_k; char* p_y = p_a + b_a;
+    char* p_pk = p_y + b_y; char* p_tau = p_pk + b_pk; char* p_st = p_tau + b_tau; char* p_ns = p_st + b_i;
     cudaMemcpyAsync(p_sc, scalars, nc * DEB_NSCAL * 8, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(p_tb, tables, nc * tl * 8, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(p_k, kmodes, nk * 8, cudaMemcpyHostToDevice, st);
@@ -261,10 +279,6 @@ int deb_evolve_sharded_host_f64(deb_comm* comm, int32_t device, const deb_dims* 
     if (cudaStreamSynchronize(st) != cudaSuccess && rc == DEB_OK) rc = DEB_E_CUDA;
     if (rc == DEB_OK && elapsed_ms) cudaEventElapsedTime(elapsed_ms, e0, e1);
   }
-  if (e0) cudaEventDestroy(e0);
-  if (e1) cudaEventDestroy(e1);
-  if (st) cudaStreamDestroy(st);
-  if (d) cudaFree(d);
   return rc;
 }
 

@@ -167,6 +167,30 @@ def test_two_team_cta_is_bit_identical_to_one_team_cta(gpu_lib, tables, monkeypa
                 assert np.array_equal(out["y"], ref["y"]) and np.array_equal(out["pk"], ref["pk"]), (shape, ls, rep)
 
 
+def test_sharded_host_entry_keeps_its_arena_across_shapes(gpu_lib, tables, monkeypatch):
+    """deb_evolve_sharded_host_f64 keeps its device arena, stream and learned work list on the communicator: alternating
+    call shapes (growing and shrinking) on one communicator must reproduce the plain host entry bit for bit."""
+    from discoeb_b200 import _cabi
+    from discoeb_b200.distributed import NativeComm
+    tab = tables["fiducial"]
+    monkeypatch.setenv("DEB_VARIANT", "team")
+    ctrl = _cabi.make_ctrl(rtol=1e-3, atol=1e-3)
+    comm = NativeComm(1, 0, lambda ident: ident, device=0, lib=gpu_lib)
+    try:
+        for nk, ncosmo in ((40, 1), (41, 1), (40, 1), (300, 1), (20, 2), (300, 1), (40, 1)):
+            dims = _cabi.make_dims(ncosmo=ncosmo, nk=nk, nout=2, lmaxg=11, lmaxgp=11, lmaxr=11, lmaxnu=8, nqmax=3, nth=tab.nth,
+                                   nnu=tab.nnu, max_steps=2048, power_idx=4)
+            ks = np.geomspace(1e-3, 0.3, nk)
+            sc = np.repeat(tab.scalars[None], ncosmo, 0); tb = np.repeat(tab.tables[None], ncosmo, 0)
+            a = gpu_lib.evolve_sharded_host(comm, dims, ctrl, sc, tb, ks, np.array([0.5, 1.0]), want_pk=True)
+            b = gpu_lib.evolve_host(dims, ctrl, sc, tb, ks, np.array([0.5, 1.0]), want_pk=True)
+            assert np.all(a["status"] == 0), (nk, ncosmo)
+            for key in ("y", "pk", "tau_out", "nsteps"):
+                assert np.array_equal(a[key], b[key]), (nk, ncosmo, key)
+    finally:
+        comm.close()
+
+
 def test_gpu_matches_cpu_build_of_same_source(gpu_lib, emu_lib, tables):
     """Same source, two compilers: any difference beyond round-off is a GPU-only defect
     (missing __syncwarp, shuffle misuse, shared-memory race)."""
