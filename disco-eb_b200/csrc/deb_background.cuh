@@ -26,8 +26,10 @@ namespace bg {
 
 #ifdef DEB_CPU_EMU
 #define BG_DEV inline
+#define BG_HD inline
 #else
 #define BG_DEV __device__ __forceinline__
+#define BG_HD __host__ __device__ inline
 #endif
 
 constexpr int NBGIN = 16;     // doubles per cosmology in the input block (order below)
@@ -136,6 +138,31 @@ BG_DEV double spline_eval(const double* x, const double* y, const double* S, int
   const double h = x[i + 1] - x[i], t = (xn - x[i]) / h, A = 1.0 - t, B = t;
   return A * y[i] + B * y[i + 1] + ((A * A * A - A) * S[i] + (B * B * B - B) * S[i + 1]) * (h * h) / 6.0;
 }
+// first and second derivative at knot i of the spline itself, with the interval the reference's searchsorted picks for
+// x_new = x[i] (spline_interpolation.py:203-260: idx = clip(searchsorted(x, x_i) - 1, 0, n-2) = i-1, the interval to the LEFT)
+BG_DEV void spline_knot_derivs(const double* x, const double* y, const double* S, int n, int i, double* d1, double* d2) {
+  int k = i - 1;
+  if (k < 0) k = 0;
+  if (k > n - 2) k = n - 2;
+  const double h = x[k + 1] - x[k], dv = x[i] - x[k];
+  const double b = (y[k + 1] - y[k]) / h - h * (S[k + 1] + 2.0 * S[k]) / 6.0, c = S[k] / 2.0, d = (S[k + 1] - S[k]) / (6.0 * h);
+  *d1 = b + 2.0 * c * dv + 3.0 * d * dv * dv;
+  *d2 = 2.0 * c + 6.0 * d * dv;
+}
+// integral of the spline from x[0] to xn given the cumulative knot integrals (spline_interpolation.py:95-104, 155-189)
+BG_DEV double spline_interval_integral(const double* x, const double* y, const double* S, int k, double dv) {
+  const double h = x[k + 1] - x[k];
+  const double b = (y[k + 1] - y[k]) / h - h * (S[k + 1] + 2.0 * S[k]) / 6.0, c = S[k] / 2.0, d = (S[k + 1] - S[k]) / (6.0 * h);
+  return y[k] * dv + b * (dv * dv) / 2.0 + c * (dv * dv * dv) / 3.0 + d * (dv * dv * dv * dv) / 4.0;
+}
+BG_DEV double spline_integral_from_start(const double* x, const double* y, const double* S, const double* icum, int n, double xn) {
+  int lo = 0, hi = n;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (x[mid] < xn) lo = mid + 1; else hi = mid; }
+  int k = lo - 1;
+  if (k < 0) k = 0;
+  if (k > n - 2) k = n - 2;
+  return icum[k] + spline_interval_integral(x, y, S, k, xn - x[k]);
+}
 // natural cubic spline second derivatives by the Thomas algorithm (spline_interpolation.py:45-86); cp, dp: scratch [n]
 BG_DEV void spline_build(const double* x, const double* y, double* S, int n, double* cp, double* dp) {
   S[0] = 0.0; S[n - 1] = 0.0;
@@ -198,15 +225,17 @@ BG_DEV double romb_dtauda(const BgP& p, double lo, double hi) {
 }
 
 // neutrino density and pressure of one massive flavour in units of a massless one (background.py:48-72)
-BG_DEV void nu_background(double a, double amnu, const double* q, const double* w, double* rho, double* pres) {
-  double r = 0.0, pn = 0.0;
+BG_DEV void nu_background(double a, double amnu, const double* q, const double* w, double* rho, double* pres, double* ppseudo = nullptr) {
+  double r = 0.0, pn = 0.0, pp = 0.0;
   for (int i = 0; i < NNUQ; ++i) {
     const double aq = a * amnu / q[i];
     const double v = 1.0 / sqrt(1.0 + aq * aq);
     r += w[i] * (1.0 / v);
     pn += w[i] * (v / 3.0);
+    pp += w[i] * (v * v * v / 3.0);
   }
   *rho = r; *pres = pn;
+  if (ppseudo) *ppseudo = pp;
 }
 
 // adaptive sampling of the scale factor (thermodynamics_recfast.py:324-360): point i of N
@@ -545,11 +574,20 @@ struct BgWork {
   double cp[5][NTH_MAX > NNU ? NTH_MAX : NNU], dp[5][NTH_MAX > NNU ? NTH_MAX : NNU];      // Thomas scratch, 5 splines at a time
   double ag[NTH_MAX + 1], tau[NTH_MAX], dtau[NTH_MAX], y6[NTH_MAX * 6];
   double la[NTH_MAX], xe[NTH_MAX], cs2a[NTH_MAX];
+  double ppy[NNU];                                              // log pseudo-pressure of the neutrino table (extras only)
+  double tba[NTH_MAX], opS[NTH_MAX], icum[NTH_MAX];             // a T_m, opacity spline, its cumulative integral (extras only)
   BgP p;
 };
 
+// Everything else the reference's evolve_background leaves in `param` (background.py:238-246, 250-251, 167, 306-342;
+// thermodynamics_recfast.py:460-478), per cosmology, in this order; rows of nth doubles unless noted:
+enum BgExtra { BX_XEHI, BX_XEHEI, BX_XEHEII, BX_CS2, BX_TM, BX_XEPRIME_RECF, BX_XEPRIME, BX_OPAC, BX_OPTICAL_DEPTH, BX_GVIS, BX_GVISPRIME,
+               BX_GVISPPRIME, BX_CS2A_OF_TAU_S, BX_TEMPBA_OF_TAU_S, BX_NROWS };       // then log ppseudo_nu [NNU] and its S [NNU]
+BG_HD size_t extras_len(int nth) { return (size_t)BX_NROWS * nth + 2 * NNU; }
+
 // tables of one cosmology in the layout of deb_spline (include/discoeb_b200.h): 7 splines x (x, y, S)
-BG_DEV void background_one(const double* in, const double* q8, const double* w8, int nth, double* scal, double* tab, BgWork& W, int tid, int nthr) {
+BG_DEV void background_one(const double* in, const double* q8, const double* w8, int nth, double* scal, double* tab, BgWork& W, int tid, int nthr,
+                           double* ext = nullptr) {
   const Consts c = make_consts();
   BgP& p = W.p;
   double* t_cs2a = tab;                     // x, y, S each nth
@@ -564,9 +602,10 @@ BG_DEV void background_one(const double* in, const double* q8, const double* w8,
   // ---- neutrino density / pressure tables on 512 log-spaced knots (background.py:157-167) ----
   for (int i = tid; i < NNU; i += nthr) {
     const double a = geom_point(AMIN * 0.9, AMAX * 1.1, i, NNU, true);
-    double r, pr;
-    nu_background(a, p.amnu, q8, w8, &r, &pr);
+    double r, pr, pp;
+    nu_background(a, p.amnu, q8, w8, &r, &pr, &pp);
     W.nx[i] = log(a); W.ry[i] = log(r); W.py[i] = log(pr);
+    if (ext) W.ppy[i] = log(pp);
   }
   BG_SYNC();
   if (tid == 0) spline_build(W.nx, W.ry, W.rS, NNU, W.cp[0], W.dp[0]);
@@ -604,6 +643,13 @@ BG_DEV void background_one(const double* in, const double* q8, const double* w8,
     const double Tm = y[2], daTmda = Tm + a * y[5];
     const double cs2 = BGC_KB / BGC_MH / (BGC_C * BGC_C) / mu * Tm * (4.0 - daTmda / Tm) / 3.0;
     W.la[i] = log(a); W.xe[i] = xe; W.cs2a[i] = a * cs2;
+    if (ext) {
+      ext[BX_XEHI * nth + i] = y[0]; ext[BX_XEHEI * nth + i] = y[1]; ext[BX_XEHEII * nth + i] = he2.v;
+      ext[BX_CS2 * nth + i] = cs2; ext[BX_TM * nth + i] = Tm;
+      // d x_e / d tau as RECFAST knows it (thermodynamics_recfast.py:477): d/da of the three species times a' (background.py:83-92)
+      ext[BX_XEPRIME_RECF * nth + i] = (y[3] + p.fHe * y[4] + he2.d[0]) / dtauda(p, a);
+      W.tba[i] = a * Tm;
+    }
   }
   BG_SYNC();
   // ---- the five thermo splines (background.py:240-255), one thread each ----
@@ -627,6 +673,56 @@ BG_DEV void background_one(const double* in, const double* q8, const double* w8,
   for (int i = tid; i < NNU; i += nthr) {
     t_lrn[i] = W.nx[i]; t_lrn[NNU + i] = W.ry[i]; t_lrn[2 * NNU + i] = W.rS[i];
     t_lpn[i] = W.nx[i]; t_lpn[NNU + i] = W.py[i]; t_lpn[2 * NNU + i] = W.pS[i];
+  }
+  if (ext) {
+    // ---- the rest of evolve_background's outputs (background.py:250-251, 167, 306-342) ----
+    BG_SYNC();
+    double* logpp = ext + (size_t)BX_NROWS * nth;
+    if (tid == 0) spline_build(W.tau, W.cs2a, ext + BX_CS2A_OF_TAU_S * nth, nth, W.cp[0], W.dp[0]);
+    if (tid == (nthr > 1 ? 1 : 0)) spline_build(W.tau, W.tba, ext + BX_TEMPBA_OF_TAU_S * nth, nth, W.cp[1], W.dp[1]);
+    if (tid == (nthr > 2 ? 2 : 0)) spline_build(W.nx, W.ppy, logpp + NNU, NNU, W.cp[2], W.dp[2]);
+    for (int i = tid; i < NNU; i += nthr) logpp[i] = W.ppy[i];
+    // optical depth and visibility on the knots: opacity x_e sigma_T n_e / a^2 with x_e frozen at full ionisation before
+    // a = 1e-4, its natural spline over tau, the spline's derivatives and its integral from tau to the last knot, shifted to
+    // vanish today
+    const double akthom = 2.3038921003709498e-9 * (1.0 - p.YHe) * p.Omegab * p.H0 * p.H0;
+    const double tau_pre = spline_eval(t_toa, t_toa + nth, t_toa + 2 * nth, nth, 1e-4);
+    const double xe_full = 1.0 + p.YHe / (1.0 - p.YHe);
+    double* opac = ext + BX_OPAC * nth;
+    for (int i = tid; i < nth; i += nthr) {
+      const bool pre = W.tau[i] <= tau_pre;
+      double d1, d2;
+      spline_knot_derivs(W.tau, W.xe, t_xot + 2 * nth, nth, i, &d1, &d2);
+      ext[BX_XEPRIME * nth + i] = pre ? 0.0 : d1;
+      const double a = W.ag[i + 1];
+      opac[i] = (pre ? xe_full : W.xe[i]) * akthom / (a * a);
+    }
+    BG_SYNC();
+    if (tid == 0) {
+      spline_build(W.tau, opac, W.opS, nth, W.cp[3], W.dp[3]);
+      double acc = 0.0;
+      W.icum[0] = 0.0;
+      for (int k = 0; k < nth - 1; ++k) { acc += spline_interval_integral(W.tau, opac, W.opS, k, W.tau[k + 1] - W.tau[k]); W.icum[k + 1] = acc; }
+    }
+    BG_SYNC();
+    {
+      const double itot = W.icum[nth - 1];
+      const double tau0 = spline_eval(t_toa, t_toa + nth, t_toa + 2 * nth, nth, 1.0);
+      const double today = itot - spline_integral_from_start(W.tau, opac, W.opS, W.icum, nth, tau0);
+      for (int i = tid; i < nth; i += nthr) {
+        double o1, o2;
+        spline_knot_derivs(W.tau, opac, W.opS, nth, i, &o1, &o2);
+        // (the reference evaluates the integral at the knot through the interval to its left, like the derivatives)
+        int k = i - 1;
+        if (k < 0) k = 0;
+        const double od = (itot - (W.icum[k] + spline_interval_integral(W.tau, opac, W.opS, k, W.tau[i] - W.tau[k]))) - today;
+        const double em = exp(-od), op = opac[i];
+        ext[BX_OPTICAL_DEPTH * nth + i] = od;
+        ext[BX_GVIS * nth + i] = op * em;
+        ext[BX_GVISPRIME * nth + i] = (o1 + op * op) * em;
+        ext[BX_GVISPPRIME * nth + i] = (o2 + 3.0 * op * o1 + op * op * op) * em;
+      }
+    }
   }
   if (tid == 0) {
     // scalars in the order of deb_scalar (include/discoeb_b200.h)

@@ -84,6 +84,14 @@ class Library:
         bgf.argtypes = [C.c_int32, C.c_int32, C.c_int32, _dp, _dp, _dp, C.POINTER(C.c_float)]
         bgf.restype = C.c_int
         self._background_host = bgf
+        bgx = getattr(self.lib, prefix + "background_host_ex_f64")
+        bgx.argtypes = [C.c_int32, C.c_int32, C.c_int32, _dp, _dp, _dp, _dp, C.POINTER(C.c_float)]
+        bgx.restype = C.c_int
+        self._background_host_ex = bgx
+        bgl = getattr(self.lib, prefix + "background_extras_len")
+        bgl.argtypes = [C.c_int32]
+        bgl.restype = C.c_size_t
+        self._background_extras_len = bgl
         spf = getattr(self.lib, prefix + "spectra_host_f64")
         spf.argtypes = [C.c_int32, C.c_int32, C.c_int32, _dp, _dp, C.c_double, C.c_double, C.c_double, C.c_double, _dp, C.c_int32, _dp, C.c_int32] + [_dp] * 8
         spf.restype = C.c_int
@@ -119,16 +127,22 @@ class Library:
     def nvar(lmaxg, lmaxgp, lmaxr, lmaxnu, nqmax):
         return 7 + (lmaxg + 1) + (lmaxgp + 1) + (lmaxr + 1) + nqmax * (lmaxnu + 1) + 2
 
-    def background_host(self, bg_in, nth: int, device: int = 0, nnu: int = 512):
-        """Table producer (deb_background_host_f64): bg_in[nc, 16] -> (scalars[nc, 24], tables[nc, 3 (5 nth + 2 nnu)], kernel ms)."""
+    def background_host(self, bg_in, nth: int, device: int = 0, nnu: int = 512, extras: bool = False):
+        """Table producer (deb_background_host[_ex]_f64): bg_in[nc, 16] -> (scalars[nc, 24], tables[nc, 3 (5 nth + 2 nnu)], kernel ms)
+        and, with ``extras=True``, a fourth item: extras[nc, deb_background_extras_len(nth)] (include/discoeb_b200.h)."""
         bg_in = np.ascontiguousarray(bg_in, dtype=np.float64)
         nc = bg_in.shape[0]
         scal = np.zeros((nc, 24), dtype=np.float64)
         tab = np.zeros((nc, 3 * (5 * nth + 2 * nnu)), dtype=np.float64)
         kms = C.c_float(0.0)
-        self._check(self._background_host(C.c_int32(device), C.c_int32(nc), C.c_int32(nth), _d(bg_in), _d(scal), _d(tab), C.byref(kms)),
-                    "background_host_f64")
-        return scal, tab, kms.value
+        if not extras:
+            self._check(self._background_host(C.c_int32(device), C.c_int32(nc), C.c_int32(nth), _d(bg_in), _d(scal), _d(tab), C.byref(kms)),
+                        "background_host_f64")
+            return scal, tab, kms.value
+        ext = np.zeros((nc, int(self._background_extras_len(C.c_int32(nth)))), dtype=np.float64)
+        self._check(self._background_host_ex(C.c_int32(device), C.c_int32(nc), C.c_int32(nth), _d(bg_in), _d(scal), _d(tab), _d(ext),
+                                             C.byref(kms)), "background_host_ex_f64")
+        return scal, tab, kms.value, ext
 
     def spectra_host(self, y, k, As, ns, kp, bias, sg_coef, mu, ell, want_xi, device: int = 0):
         """deb_spectra_host_f64 -> dict(P0, P2, P4, Pkmu, Ps_delta, Ps_theta, xi, r) (entries None when not requested)."""

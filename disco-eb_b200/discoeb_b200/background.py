@@ -41,6 +41,38 @@ class TableSpline:
         A, B = 1 - t, t
         return A * self.y[i] + B * self.y[i + 1] + ((A ** 3 - A) * self.S[i] + (B ** 3 - B) * self.S[i + 1]) * h ** 2 / 6.0
 
+    # the other members of the reference's spline_interpolation (spline_interpolation.py:155-260), so that a ``param``
+    # returned by evolve_background serves the reference's callers of these splines too
+    def _local(self, xn):
+        xn = np.atleast_1d(np.asarray(xn, dtype=np.float64))
+        n = self.x.shape[0]
+        i = np.clip(np.searchsorted(self.x, xn) - 1, 0, n - 2)
+        h = self.x[i + 1] - self.x[i]
+        b = (self.y[i + 1] - self.y[i]) / h - h * (self.S[i + 1] + 2 * self.S[i]) / 6.0
+        return xn, i, xn - self.x[i], b, self.S[i] / 2.0, (self.S[i + 1] - self.S[i]) / (6.0 * h)
+
+    def derivative12(self, xn):
+        xn, i, dv, b, c, d = self._local(xn)
+        d1, d2 = b + 2 * c * dv + 3 * d * dv ** 2, 2 * c + 6 * d * dv
+        return (d1[0], d2[0]) if xn.shape[0] == 1 else (d1, d2)
+
+    def derivative(self, xn):
+        return self.derivative12(xn)[0]
+
+    def derivative2(self, xn):
+        return self.derivative12(xn)[1]
+
+    def integral(self, xn):
+        """Integral from x[0] to xn (``integrate_from_start``, the default) or from xn to x[-1]."""
+        xn, i, dv, b, c, d = self._local(xn)
+        h = np.diff(self.x)
+        bb = np.diff(self.y) / h - h * (self.S[1:] + 2 * self.S[:-1]) / 6.0
+        full = self.y[:-1] * h + bb * h ** 2 / 2 + (self.S[:-1] / 2.0) * h ** 3 / 3 + ((self.S[1:] - self.S[:-1]) / (6.0 * h)) * h ** 4 / 4
+        icum = np.concatenate([[0.0], np.cumsum(full)])
+        fwd = icum[i] + self.y[i] * dv + b * dv ** 2 / 2 + c * dv ** 3 / 3 + d * dv ** 4 / 4
+        res = fwd if getattr(self, "integrate_from_start", True) else icum[-1] - fwd
+        return res[0] if xn.shape[0] == 1 else res
+
 
 def pack_background_input(param):
     v = np.zeros(NBGIN)
@@ -77,6 +109,26 @@ def background_tables(params, *, num_thermo: int = 256, device: int = 0, lib=Non
     return (scal, tab, dict(kernel_ms=ms)) if return_info else (scal, tab)
 
 
+EXTRA_ROWS = ("xeHI", "xeHeI", "xeHeII", "cs2", "Tm", "xeprime_recf", "xeprime", "opac", "optical_depth", "gvis", "gvisprime", "gvispprime")
+
+
+def unpack_extras(out, ext, nth, nnu=NNU):
+    """The rest of the reference's ``param`` (background.py:238-251, 167, 306-342) from the extras block of
+    ``deb_background_ex_f64`` (row order: include/discoeb_b200.h)."""
+    for j, key in enumerate(EXTRA_ROWS):
+        out[key] = ext[j * nth:(j + 1) * nth]
+    r = len(EXTRA_ROWS)
+    tau, aexp = out["tau"], out["aexp"]
+    out["cs2a_of_tau_spline"] = TableSpline(tau, aexp * out["cs2"], ext[r * nth:(r + 1) * nth])
+    out["tempba_of_tau_spline"] = TableSpline(tau, aexp * out["Tm"], ext[(r + 1) * nth:(r + 2) * nth])
+    o = (r + 2) * nth
+    out["logppseudonu_of_loga_spline"] = TableSpline(out["logrhonu_of_loga_spline"].x, ext[o:o + nnu], ext[o + nnu:o + 2 * nnu])
+    out["a"] = np.exp(out["logrhonu_of_loga_spline"].x)           # the knots of the neutrino tables (background.py:158-160)
+    out["adotrad"] = float(np.sqrt((out["grhog"] + out["grhor"] * (out["Neff"] + out["Nmnu"])) / 3.0))
+    out["fHe"] = out["YHe"] / (3.97146570884 * (1.0 - out["YHe"]))      # thermodynamics_recfast.py:41, 457
+    return out
+
+
 def unpack_param(param, scal, tab, nth, nnu=NNU):
     out = dict(param)
     for i, key in enumerate(SCALAR_KEYS):
@@ -99,5 +151,7 @@ def evolve_background(*, param, thermo_module: str = "RECFAST", num_thermo: int 
     hot path's tests use).  ``rtol/atol/order`` are accepted and, as in the reference, unused by the RECFAST branch."""
     if thermo_module != "RECFAST":
         raise NotImplementedError("discoeb_b200.evolve_background implements thermo_module='RECFAST' only")
-    scal, tab = background_tables([param], num_thermo=num_thermo, device=device, lib=lib)
-    return unpack_param(param, scal[0], tab[0], num_thermo)
+    lib = lib or _cabi.default_library()
+    bg_in = np.ascontiguousarray(pack_background_input(param)[None])
+    scal, tab, _, ext = lib.background_host(bg_in, num_thermo, device=device, extras=True)
+    return unpack_extras(unpack_param(param, scal[0], tab[0], num_thermo), ext[0], num_thermo)

@@ -233,6 +233,22 @@ int deb_background_f64(int32_t ncosmo, int32_t nth, const double* bg_in, double*
 int deb_background_host_f64(int32_t device, int32_t ncosmo, int32_t nth, const double* bg_in, double* scalars,
                             double* tables, float* kernel_ms);
 
+/* The rest of what evolve_background leaves in `param` (not read by evolve_perturbations; for callers of the reference
+ * that use the thermal history or the visibility function): background.py:238-246 (x_HII, x_HeII, x_HeIII fractions, c_s^2,
+ * T_m), :250-251 (second derivatives of the a c_s^2 and a T_m splines over tau), :167 (log pseudo-pressure table of the
+ * massive neutrinos), :306-342 (opacity, optical depth from today, visibility g and its first two derivatives, x_e' from
+ * the spline and from RECFAST's own right-hand side, thermodynamics_recfast.py:477).
+ *   extras [ncosmo, deb_background_extras_len(nth)], rows of nth doubles in this order:
+ *     xeHI, xeHeI, xeHeII, cs2, Tm, xeprime_recf, xeprime, opac, optical_depth, gvis, gvisprime, gvispprime,
+ *     S of cs2a_of_tau_spline, S of tempba_of_tau_spline (x = tau, y = aexp cs2 / aexp Tm), then
+ *     log ppseudo_nu [512] and its second derivatives [512] on the knots of the logrhonu table.
+ * extras = NULL makes the _ex entries identical to the plain ones. */
+size_t deb_background_extras_len(int32_t nth);
+int deb_background_ex_f64(int32_t ncosmo, int32_t nth, const double* bg_in, double* scalars, double* tables, double* extras,
+                          void* workspace, size_t workspace_bytes, void* stream);
+int deb_background_host_ex_f64(int32_t device, int32_t ncosmo, int32_t nth, const double* bg_in, double* scalars,
+                               double* tables, double* extras, float* kernel_ms);
+
 /* ---- multi-GPU: one k grid dealt round-robin over the ranks of one box ---------------------------
  * The reference has no multi-device code; its vmap over k (perturbations.py:980-987) is what gets sharded: rank r integrates
  * modes r, r + W, ... (cost rises steeply with k) and EVERY rank ends with the full-size y_all[ncosmo, nk, nout, 20],

@@ -322,8 +322,15 @@ extern "C" int emu_debug_replay_tangent_host_f64(const deb_dims* dims, const deb
 }
 
 // table producer (deb_background.cuh) on the CPU: one cosmology per OpenMP thread
+extern "C" int emu_background_host_ex_f64(int32_t device, int32_t ncosmo, int32_t nth, const double* bg_in, double* scalars, double* tables,
+                                          double* extras, float* kernel_ms);
 extern "C" int emu_background_host_f64(int32_t device, int32_t ncosmo, int32_t nth, const double* bg_in, double* scalars, double* tables,
                                        float* kernel_ms) {
+  return emu_background_host_ex_f64(device, ncosmo, nth, bg_in, scalars, tables, nullptr, kernel_ms);
+}
+extern "C" size_t emu_background_extras_len(int32_t nth) { return deb::bg::extras_len(nth); }
+extern "C" int emu_background_host_ex_f64(int32_t device, int32_t ncosmo, int32_t nth, const double* bg_in, double* scalars, double* tables,
+                                          double* extras, float* kernel_ms) {
   (void)device;
   using namespace deb::bg;
   if (ncosmo < 1 || nth < 16 || nth > NTH_MAX) return DEB_E_ARG;
@@ -334,7 +341,8 @@ extern "C" int emu_background_host_f64(int32_t device, int32_t ncosmo, int32_t n
   for (int c = 0; c < ncosmo; ++c) {
     std::vector<BgWork> W(1);
     for (int i = 0; i < DEB_NSCAL; ++i) scalars[(size_t)c * DEB_NSCAL + i] = 0.0;
-    background_one(bg_in + (size_t)c * NBGIN, q, w, nth, scalars + (size_t)c * DEB_NSCAL, tables + (size_t)c * tl, W[0], 0, 1);
+    background_one(bg_in + (size_t)c * NBGIN, q, w, nth, scalars + (size_t)c * DEB_NSCAL, tables + (size_t)c * tl, W[0], 0, 1,
+                   extras ? extras + (size_t)c * extras_len(nth) : nullptr);
   }
   if (kernel_ms) *kernel_ms = 0.0f;
   return DEB_OK;

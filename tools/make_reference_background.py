@@ -34,12 +34,19 @@ def fiducial(**over):
     return p
 
 
+# everything else evolve_background leaves in param (background.py:238-342): species fractions, sound speed, matter
+# temperature, the tau-splines of a c_s^2 and a T_m, the pseudo-pressure table, optical depth and visibility
+EXTRA_ARRAYS = ("xeHI", "xeHeI", "xeHeII", "cs2", "Tm", "xeprime_recf", "xeprime", "opac", "optical_depth", "gvis", "gvisprime", "gvispprime")
+EXTRA_SPLINES = ("cs2a_of_tau_spline", "tempba_of_tau_spline", "logppseudonu_of_loga_spline")
+
+
 def main():
     cases = {"fiducial": fiducial(), "w0wa": fiducial(w_DE_0=-0.9, w_DE_a=0.1), "massless": fiducial(Nmnu=0, Neff=3.046),
              "fisher": fiducial(Omegam=0.32, Omegab=0.05, H0=67.0, n_s=0.96, w_DE_0=-0.9999, cs2_DE=0.9999)}
     for i, d in enumerate(config4_draws(3)):
         cases[f"config4_{i}"] = fiducial(**d)
     out = {"names": np.array(list(cases))}
+    ext = {"names": np.array(list(cases))}
     for name, p in cases.items():
         inp = pack_background_input(p)
         q = evolve_background(param=dict(p), thermo_module="RECFAST")
@@ -49,8 +56,16 @@ def main():
             out[f"{name}_{sp}_x"] = np.asarray(q[sp]._x_)
             out[f"{name}_{sp}_y"] = np.asarray(q[sp]._y_)
             out[f"{name}_{sp}_S"] = np.asarray(q[sp]._S_full_)
+        for key in EXTRA_ARRAYS:
+            ext[f"{name}_{key}"] = np.asarray(q[key], dtype=np.float64)
+        for sp in EXTRA_SPLINES:
+            ext[f"{name}_{sp}_y"] = np.asarray(q[sp]._y_)
+            ext[f"{name}_{sp}_S"] = np.asarray(q[sp]._S_full_)
+        ext[f"{name}_taumax"] = float(q["taumax"]); ext[f"{name}_adotrad"] = float(q["adotrad"]); ext[f"{name}_Omegamnu"] = float(q["Omegamnu"])
         print(name, "OmegaDE", float(q["OmegaDE"]), "xe[120]", float(np.asarray(q["xe"])[120]), flush=True)
-    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "reference_background.npz"), **out)
+    if "--extras-only" not in sys.argv:
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", "reference_background.npz"), **out)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "reference_background_extras.npz"), **ext)
 
 
 if __name__ == "__main__":
