@@ -576,6 +576,75 @@ DEB_DEV void carve(WarpWs& W, double* base, int np) {
 // row r of the block-diagonal head matrix, addressable by ABSOLUTE head column lo <= c < hi
 DEB_DEV double* hrow(const WarpWs& W, int r, int lo) { return W.lu() + (r * LDB - lo); }
 
+// Gauss-Jordan with partial pivoting on all diagonal blocks of the head at once (lane = row, <= 8 columns per block), used
+// by the team and chain-lane kernels (expects W, C, nhb, lane and the lane registers pcol, rscale, pkey, pivl, fmul in scope; the
+// rows were assembled in shared memory, hrow).  The rows live in REGISTERS for the eight pivot steps and the pivot row
+// travels by shuffles: a step is one dependency chain (key, 8-way search, reciprocal, update) without the load - store -
+// load round trips through shared memory between steps (team kernel: 10.8 k -> 8.3 k cycles per Jacobian).  Same
+// operations on the same operands as the in-memory form: the factors are bit-identical.  The pivot row is left unscaled
+// until the end; afterwards S[:, j] is column perm[j] of the accumulated row operations: x_j = (S b_perm)[perm[j]].
+#define DEB_GJ_ROWP(r) (hrow(W, (r), C.blo[(r)]) + C.blo[(r)])      /* first of the 8 slots of row r (deb_lane.cuh redefines both) */
+#define DEB_GJ_PERM(j) W.perm()[(j)]
+#define DEB_GJ_ELIM(i, BT) if ((i) != (BT)) { const double p_ = DEB_SHFL(g##i, pivl); if (gact) g##i = g##i - fmul * p_; }
+#define DEB_GJ_STEP(BT) \
+      DEB_LANES_BEGIN \
+        DEB_USE(pcol); DEB_USE(pkey); DEB_USE(g##BT); \
+        const int lo = C.blo[lane], hi = C.bhi[lane]; \
+        pkey = (lane < nhb && lo + BT < hi && pcol < 0) ? hi32abs(g##BT) + 1u : 0u; \
+      DEB_LANES_END \
+      DEB_LANES_BEGIN \
+        DEB_USE(pcol); DEB_USE(rscale); DEB_USE(pkey); DEB_USE(pivl); DEB_USE(fmul); DEB_USE(gact); DEB_USE(g##BT); \
+        const int lo = C.blo[lane], hi = C.bhi[lane], j = lo + BT; \
+        /* pivot = first row of the block holding the largest key: a scan of the (at most 8) block rows by shuffles */ \
+        int piv = lane; unsigned best = 0u; \
+        _Pragma("unroll") \
+        for (int i = 0; i < 8; ++i) { \
+          const int src = (lo + i < hi) ? lo + i : lane; \
+          const unsigned kk = DEB_SHFL(pkey, src); \
+          if (lo + i < hi && kk > best) { best = kk; piv = lo + i; } \
+        } \
+        pivl = piv; fmul = 0.0; gact = 0; \
+        const double pv = DEB_SHFL(g##BT, piv); \
+        if (lane < nhb && j < hi) { \
+          const double ipv = DEB_RCP(pv); \
+          if (lane == piv) { pcol = j; rscale = ipv; DEB_GJ_PERM(j) = piv; } \
+          else { fmul = g##BT * ipv; gact = 1; } \
+        } \
+      DEB_LANES_END \
+      DEB_LANES_BEGIN \
+        DEB_USE(pivl); DEB_USE(fmul); DEB_USE(gact); \
+        DEB_USE(g0); DEB_USE(g1); DEB_USE(g2); DEB_USE(g3); DEB_USE(g4); DEB_USE(g5); DEB_USE(g6); DEB_USE(g7); \
+        const int lo = C.blo[lane], hi = C.bhi[lane]; \
+        DEB_GJ_ELIM(0, BT) DEB_GJ_ELIM(1, BT) DEB_GJ_ELIM(2, BT) DEB_GJ_ELIM(3, BT) \
+        DEB_GJ_ELIM(4, BT) DEB_GJ_ELIM(5, BT) DEB_GJ_ELIM(6, BT) DEB_GJ_ELIM(7, BT) \
+        if (lane < nhb && lo + BT < hi) { if (gact) g##BT = -fmul; else if (lane == pivl) g##BT = 1.0; } \
+      DEB_LANES_END
+#define DEB_GJ_ALL(cond) \
+      DEB_REGS(double, g0, ); DEB_REGS(double, g1, ); DEB_REGS(double, g2, ); DEB_REGS(double, g3, ); \
+      DEB_REGS(double, g4, ); DEB_REGS(double, g5, ); DEB_REGS(double, g6, ); DEB_REGS(double, g7, ); \
+      DEB_REGS(int, gact, ); \
+      DEB_LANES_BEGIN \
+        DEB_USE(g0); DEB_USE(g1); DEB_USE(g2); DEB_USE(g3); DEB_USE(g4); DEB_USE(g5); DEB_USE(g6); DEB_USE(g7); \
+        g0 = g1 = g2 = g3 = g4 = g5 = g6 = g7 = 0.0; \
+        if (lane < nhb) { \
+          const double* rb = DEB_GJ_ROWP(lane); \
+          g0 = rb[0]; g1 = rb[1]; g2 = rb[2]; g3 = rb[3]; g4 = rb[4]; g5 = rb[5]; g6 = rb[6]; g7 = rb[7]; \
+        } \
+      DEB_LANES_END \
+      if (cond) { \
+        DEB_GJ_STEP(0) DEB_GJ_STEP(1) DEB_GJ_STEP(2) DEB_GJ_STEP(3) DEB_GJ_STEP(4) DEB_GJ_STEP(5) DEB_GJ_STEP(6) DEB_GJ_STEP(7) \
+      } \
+      /* scale the rows; right-hand sides of the two Woodbury solves are gathered in pivot order below */ \
+      DEB_LANES_BEGIN \
+        DEB_USE(rscale); \
+        DEB_USE(g0); DEB_USE(g1); DEB_USE(g2); DEB_USE(g3); DEB_USE(g4); DEB_USE(g5); DEB_USE(g6); DEB_USE(g7); \
+        if (lane < nhb) { \
+          double* rb = DEB_GJ_ROWP(lane); \
+          rb[0] = g0 * rscale; rb[1] = g1 * rscale; rb[2] = g2 * rscale; rb[3] = g3 * rscale; \
+          rb[4] = g4 * rscale; rb[5] = g5 * rscale; rb[6] = g6 * rscale; rb[7] = g7 * rscale; \
+        } \
+      DEB_LANES_END
+
 // background coefficients at scale factor a (perturbations.py:176-218, background.py:110-121)
 template <class T> struct Bg {
   T a, H, opac, cs2, pbo, wq1, wq, ca2;
@@ -1335,6 +1404,8 @@ DEB_DEV void integrate_mode(const Problem& P, const CtaConst& C, WarpWs& W, Help
     //      (step t eliminates the t-th column of each block; lanes = rows; pivot search is a masked warp max).
     //      The pivot row is left unscaled until the end, so each step is one race-free phase; afterwards
     //      S[:, j] is column perm[j] of the accumulated row operations: x_j = (S b_perm)[perm[j]].
+    // (the one-warp kernels keep the rows in shared memory: they run at the register limit, and the eight row registers of
+    //  DEB_GJ_ALL cost more in spills than the round trips -- n = 111: +5 %, tangent kernel: +40 %; team and lane kernels use it)
     for (int bt = 0; bt < 8; ++bt) {
       DEB_LANES_BEGIN
         DEB_USE(pcol); DEB_USE(pkey);

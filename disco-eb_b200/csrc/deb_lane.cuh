@@ -366,58 +366,17 @@ DEB_DEV void integrate_mode_lane(const Problem& P, const CtaConst& C, const Lane
         }
       DEB_LANES_END
     }
-    for (int bt_ = 0; bt_ < 8; ++bt_) {
-      DEB_LANES_BEGIN
-        DEB_USE(pcol); DEB_USE(pkey);
-        const int lo = C.blo[lane], hi = C.bhi[lane];
-        pkey = (lane < nhb && lo + bt_ < hi && pcol < 0) ? hi32abs(lrow(W, lane, lo)[lo + bt_]) + 1u : 0u;
-      DEB_LANES_END
-      DEB_LANES_BEGIN
-        DEB_USE(pcol); DEB_USE(rscale); DEB_USE(pkey); DEB_USE(pivl); DEB_USE(fmul);
-        const int lo = C.blo[lane], hi = C.bhi[lane], j = lo + bt_;
-        int piv = lane; unsigned best = 0u;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int src = (lo + i < hi) ? lo + i : lane;
-          const unsigned kk = DEB_SHFL(pkey, src);
-          if (lo + i < hi && kk > best) { best = kk; piv = lo + i; }
-        }
-        pivl = piv; fmul = 0.0;
-        if (lane < nhb && j < hi) {
-          const double ipv = DEB_RCP(lrow(W, piv, lo)[j]);
-          if (lane == piv) { pcol = j; rscale = ipv; W.perm_[j] = piv; }
-          else fmul = lrow(W, lane, lo)[j] * ipv;
-        }
-      DEB_LANES_END
-      DEB_LANES_BEGIN
-        DEB_USE(pivl); DEB_USE(fmul);
-        const int lo = C.blo[lane], hi = C.bhi[lane], j = lo + bt_;
-        if (lane < nhb && j < hi) {
-          double* row = lrow(W, lane, lo);
-          if (lane == pivl) row[j] = 1.0;
-          else {
-            const double* rb = row + lo;
-            const double* pb = lrow(W, pivl, lo) + lo;
-            const double f = fmul;
-            double ra[8], pa[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { ra[i] = rb[i]; pa[i] = (i == bt_) ? 0.0 : pb[i]; }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) row[lo + i] = (i == bt_) ? -f : ra[i] - f * pa[i];
-          }
-        }
-      DEB_LANES_END
-    }
+    // (register-resident Gauss-Jordan of deb_core.cuh on this workspace's row storage)
+#undef DEB_GJ_ROWP
+#undef DEB_GJ_PERM
+#define DEB_GJ_ROWP(r) (lrow(W, (r), C.blo[(r)]) + C.blo[(r)])
+#define DEB_GJ_PERM(j) W.perm_[(j)]
+    DEB_GJ_ALL(true)
+#undef DEB_GJ_ROWP
+#undef DEB_GJ_PERM
+#define DEB_GJ_ROWP(r) (hrow(W, (r), C.blo[(r)]) + C.blo[(r)])
+#define DEB_GJ_PERM(j) W.perm()[(j)]
     DEB_LANES_BEGIN
-      DEB_USE(rscale);
-      if (lane < nhb) {
-        double* rb = lrow(W, lane, C.blo[lane]) + C.blo[lane];
-        double ra[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) ra[i] = rb[i];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) rb[i] = ra[i] * rscale;
-      }
       W.xb_[lane] = 0.0;
       if (lane < 8) W.xb_[NHMAX + lane] = 0.0;
     DEB_LANES_END

@@ -563,59 +563,8 @@ DEB_DEV void integrate_mode_team(const Problem& P, const CtaConst& C, WarpWs& W,
           }
         }
       DEB_LANES_END
-#pragma unroll 1
-      for (int bt = 0; bt < (DEB_KEEP(64) ? 8 : 0); ++bt) {
-        DEB_LANES_BEGIN
-          DEB_USE(pcol); DEB_USE(pkey);
-          const int lo = C.blo[lane], hi = C.bhi[lane];
-          pkey = (lane < nhb && lo + bt < hi && pcol < 0) ? hi32abs(hrow(W, lane, lo)[lo + bt]) + 1u : 0u;
-        DEB_LANES_END
-        DEB_LANES_BEGIN
-          DEB_USE(pcol); DEB_USE(rscale); DEB_USE(pkey); DEB_USE(pivl); DEB_USE(fmul);
-          const int lo = C.blo[lane], hi = C.bhi[lane], j = lo + bt;
-          int piv = lane; unsigned best = 0u;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int src = (lo + i < hi) ? lo + i : lane;
-            const unsigned kk = DEB_SHFL(pkey, src);
-            if (lo + i < hi && kk > best) { best = kk; piv = lo + i; }
-          }
-          pivl = piv; fmul = 0.0;
-          if (lane < nhb && j < hi) {
-            const double ipv = DEB_RCP(hrow(W, piv, lo)[j]);
-            if (lane == piv) { pcol = j; rscale = ipv; W.perm()[j] = piv; }
-            else fmul = hrow(W, lane, lo)[j] * ipv;
-          }
-        DEB_LANES_END
-        DEB_LANES_BEGIN
-          DEB_USE(pivl); DEB_USE(fmul);
-          const int lo = C.blo[lane], hi = C.bhi[lane], j = lo + bt;
-          if (lane < nhb && j < hi) {
-            double* row = hrow(W, lane, lo);
-            if (lane == pivl) row[j] = 1.0;
-            else {
-              const double* rb = row + lo;
-              const double* pb = hrow(W, pivl, lo) + lo;
-              const double f = fmul;
-              double ra[8], pa[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) { ra[i] = rb[i]; pa[i] = (i == bt) ? 0.0 : pb[i]; }
-#pragma unroll
-              for (int i = 0; i < 8; ++i) row[lo + i] = (i == bt) ? -f : ra[i] - f * pa[i];
-            }
-          }
-        DEB_LANES_END
-      }
+      DEB_GJ_ALL(DEB_KEEP(64))
       DEB_LANES_BEGIN
-        DEB_USE(rscale);
-        if (lane < nhb) {
-          double* rb = hrow(W, lane, C.blo[lane]) + C.blo[lane];
-          double ra[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) ra[i] = rb[i];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) rb[i] = ra[i] * rscale;
-        }
         W.xb()[lane] = 0.0;
       DEB_LANES_END
       DEB_LANES_BEGIN
