@@ -310,11 +310,12 @@ static int launch_evolve(const Problem& P, cudaStream_t st) {
       if (rc != DEB_E_UNSUPPORTED) return rc;
     }
   }
-  // throughput launches (more modes than the 8 per SM the register file holds) of the large hierarchies: the
-  // register-resident chain-lane kernel (deb_lane.cuh), +11 % over the cyclic one-warp kernel at n = 265
-  // (profiles/r2_lane_*); at n = 72 the cyclic layout with 12 modes per SM stays ahead
+  // throughput launches (more modes than the team kernel takes): the register-resident chain-lane kernel (deb_lane.cuh),
+  // +11 % over the cyclic one-warp kernel at n = 265 before its lock-step (profiles/r2_lane_*), and with the lock-step
+  // ahead at the small hierarchies too: n = 72 / 111, 1024 ... 16384 modes: 7 ... 26 % faster (tools/time_lane_small_n.py,
+  // profiles/r2_lane_small_n.txt)
   if (P.batch_size == 0 && P.ntan == 0 && P.mode == 0 &&
-      (variant_forced("lane") || (!getenv("DEB_VARIANT") && P.n > 128 && (long)P.ncosmo * P.nk > (long)nsm * 8))) {
+      (variant_forced("lane") || (!getenv("DEB_VARIANT") && (long)P.ncosmo * P.nk > (long)nsm * (P.n > 128 ? 8 : 6)))) {
     const int rc = deb_launch_lane(P, st, nsm);
     if (rc != DEB_E_UNSUPPORTED) return rc;
   }

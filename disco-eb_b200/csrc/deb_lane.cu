@@ -146,7 +146,9 @@ int deb_launch_lane(const Problem& P, cudaStream_t st, int nsm, int hybrid_ctas)
   // 8 modes in flight per SM (255 registers each) as ONE CTA of 8 warps advancing in lock-step (LN_BAR): 225.7 -> 199.0 ms
   // on 16384 modes against free-running warps; two CTAs of 4 warps in lock-step: 206.2 ms (profiles/r2_lane_lockstep.txt)
   // small hierarchies (NT <= 4: the stage vectors take <= 56 registers per lane) run 12 warps per SM under 168 registers
-  int warps = nt <= 4 ? 12 : 8;
+  // 12 warps per CTA pay for NT <= 3 (n = 72) once the launch is deep (>= 48 modes per SM: 8192 modes 58.0 vs 64.8 ms,
+  // 4096 modes 39.2 vs 37.5 ms); at NT = 4 (n = 111) eight warps stay ahead at every size (profiles/r2_lane_small_n.txt)
+  int warps = (nt <= 3 && (long)P.ncosmo * P.nk >= 48L * nsm) ? 12 : 8;
   if (hybrid_ctas > 0) warps = 4;
   else if (const char* e = getenv("DEB_LANE_WARPS")) warps = atoi(e);
   if (warps == 12 && nt > 4) warps = 8;
