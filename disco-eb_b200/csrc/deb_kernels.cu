@@ -272,9 +272,10 @@ static int launch_evolve(const Problem& P, cudaStream_t st) {
   if (P.batch_size == 0 && P.ntan == 0) {
     // launches that cannot fill the GPU: one CTA (4 warps) per mode, deb_team.cuh.  Measured crossover against the
     // one-warp kernels (tools/time_crossover.py, profiles/r1_v19_crossover.txt): ~10 modes per SM at n = 265
-    // (1536 modes: 45.0 vs 44.4 ms), ~7 per SM at n = 72 (1024 modes: 32.4 vs 33.0 ms)
+    // (1536 modes: 45.0 vs 44.4 ms), ~7 per SM at n = 72 (1024 modes: 32.4 vs 33.0 ms); round 2 against the chain-lane kernel
+    // (tools/time_team_lane_crossover.py, profiles/r2_team_lane_crossover.txt): 8 per SM at n = 265, 7 at n = 72 / 111
     const long nm = (long)P.ncosmo * P.nk;
-    const bool want = getenv("DEB_VARIANT") ? variant_forced("team") : nm <= (long)nsm * (P.n > 128 ? 8 : 6);
+    const bool want = getenv("DEB_VARIANT") ? variant_forced("team") : nm <= (long)nsm * (P.n > 128 ? 8 : 7);
     // Hybrid launch (opt-in, DEB_HYBRID=1; steady state only): with a learned work list the modes of more than 0.38 x the
     // longest step count get team CTAs, one per SM -- a second team CTA on the SM costs the slowest mode 15-20 % per step --
     // while the shorter modes run on chain-lane warps (4 per SM fit beside a team CTA: 32 k + 31 k registers, same
@@ -315,7 +316,7 @@ static int launch_evolve(const Problem& P, cudaStream_t st) {
   // ahead at the small hierarchies too: n = 72 / 111, 1024 ... 16384 modes: 7 ... 26 % faster (tools/time_lane_small_n.py,
   // profiles/r2_lane_small_n.txt)
   if (P.batch_size == 0 && P.ntan == 0 && P.mode == 0 &&
-      (variant_forced("lane") || (!getenv("DEB_VARIANT") && (long)P.ncosmo * P.nk > (long)nsm * (P.n > 128 ? 8 : 6)))) {
+      (variant_forced("lane") || (!getenv("DEB_VARIANT") && (long)P.ncosmo * P.nk > (long)nsm * (P.n > 128 ? 8 : 7)))) {
     const int rc = deb_launch_lane(P, st, nsm);
     if (rc != DEB_E_UNSUPPORTED) return rc;
   }
