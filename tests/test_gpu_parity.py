@@ -167,6 +167,32 @@ def test_two_team_cta_is_bit_identical_to_one_team_cta(gpu_lib, tables, monkeypa
                 assert np.array_equal(out["y"], ref["y"]) and np.array_equal(out["pk"], ref["pk"]), (shape, ls, rep)
 
 
+@pytest.mark.parametrize("dims5,nk", [((11, 11, 11, 8, 3), 600), ((16, 16, 16, 16, 3), 450), ((5, 4, 6, 3, 4), 500)])
+def test_deep_launch_of_small_hierarchies_takes_the_lane_kernel(gpu_lib, tables, monkeypatch, dims5, nk):
+    """Beyond the team kernel's range (7 modes per SM at n <= 128) the library takes the chain-lane kernel at every n since
+    round 2: three cosmologies x nk modes by the default choice against the cyclic one-warp kernel (free-running: identical
+    step counts on most modes, solver-tolerance agreement on the rest), every mode processed."""
+    from discoeb_b200 import _cabi
+    lg, lp, lr, ln, nq = dims5
+    tabs = [tables["fiducial"], tables["w0wa"], tables["fiducial"]]
+    sc = np.stack([t.scalars for t in tabs]); tb = np.stack([t.tables for t in tabs])
+    ctrl = _cabi.make_ctrl(rtol=1e-4, atol=1e-4)
+    dims = _cabi.make_dims(ncosmo=3, nk=nk, nout=2, lmaxg=lg, lmaxgp=lp, lmaxr=lr, lmaxnu=ln, nqmax=nq, nth=tabs[0].nth, nnu=tabs[0].nnu,
+                           max_steps=4096, power_idx=4)
+    ks = np.geomspace(1e-4, 5.0, nk)
+    a = gpu_lib.evolve_host(dims, ctrl, sc, tb, ks, np.array([0.3, 1.0]), want_pk=True)
+    monkeypatch.setenv("DEB_VARIANT", "warp")
+    b = gpu_lib.evolve_host(dims, ctrl, sc, tb, ks, np.array([0.3, 1.0]), want_pk=True)
+    assert np.all(a["status"] == 0) and np.all(b["status"] == 0)
+    rel = np.abs(a["pk"] / b["pk"] - 1)
+    # (P(k) ~ delta^2; at lmax = 11 and rtol 1e-4 ANY two kernels differ by up to ~2e-2 on the worst long mode -- team vs
+    #  cyclic 1.69e-2, lane vs cyclic 1.68e-2 on this launch, all three equally far from a tight-tolerance run:
+    #  tools/dbg_small_n_variants.py -- so the bar is the variants' own spread, and most modes must agree far better)
+    assert np.median(rel) < 1e-8 and np.mean(rel > 1e-3) < 0.05 and rel.max() < 0.05, (np.median(rel), np.mean(rel > 1e-3), rel.max())
+    assert np.mean(a["nsteps"] == b["nsteps"]) > 0.5
+    assert np.array_equal(a["pk"][0], a["pk"][2]) and not np.array_equal(a["pk"][0], a["pk"][1])      # cosmologies kept apart
+
+
 def test_sharded_host_entry_keeps_its_arena_across_shapes(gpu_lib, tables, monkeypatch):
     """deb_evolve_sharded_host_f64 keeps its device arena, stream and learned work list on the communicator: alternating
     call shapes (growing and shrinking) on one communicator must reproduce the plain host entry bit for bit."""
