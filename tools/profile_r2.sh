@@ -6,8 +6,8 @@ TAG=${1:-r2_final}
 mkdir -p gpurun_out
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_bench_under_ncu.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_evolve_duo -c 1 -f -o gpurun_out/${TAG}_team \
-    python tools/run_once.py 2 512 > gpurun_out/${TAG}_team.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_evolve_duo --launch-skip 1 -c 1 -f -o gpurun_out/${TAG}_team \
+    python tools/run_once.py 3 512 > gpurun_out/${TAG}_team.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_evolve_lane -c 1 -f -o gpurun_out/${TAG}_lane \
     python tools/run_once.py 1 4096 > gpurun_out/${TAG}_lane.log 2>&1
 ncu --set full --clock-control none -k regex:k_background -c 1 -f -o gpurun_out/${TAG}_background \
