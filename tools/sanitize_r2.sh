@@ -19,8 +19,8 @@ from discoeb_b200 import _cabi
 from discoeb_b200.background import config4_draws, pack_background_input
 base = dict(Omegam=0.3099, Omegab=0.0488911, w_DE_0=-0.99, w_DE_a=0.0, cs2_DE=1.0, Omegak=0.0, A_s=2.1064e-09, n_s=0.96822, H0=67.742, Tcmb=2.7255, YHe=0.248, Neff=2.046, Nmnu=1, mnu=0.06)
 bg = np.stack([pack_background_input({**base, **d}) for d in config4_draws(3)])
-s, t, ms = _cabi.default_library().background_host(bg, 256)
-print('status ok', np.isfinite(t).all())
+s, t, ms, ex = _cabi.default_library().background_host(bg, 256, extras=True)
+print('status ok', np.isfinite(t).all(), np.isfinite(ex[:, 256*7:256*8]).all())
 " 2>&1 | grep -E "SUMMARY|hazard|Error|error|status|Barrier" | head -20 >> $OUT
 done
 cat $OUT
