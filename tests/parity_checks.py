@@ -411,6 +411,12 @@ def check_edge_shapes(lib, tables):
                              max_steps=4096, power_idx=4)
     out31 = lib.evolve_host(dims31, ctrl, tab.scalars[None], tab.tables[None], np.array([0.02]), np.array([1.0]), want_pk=True)
     assert abs(out["pk"][0, 0, 0] / out31["pk"][0, 0, 0] - 1) < 1e-3          # the cut-off does not matter at k = 0.02
+    # step budget exhausted (diffrax: max_steps reached with throw=False): status 1, exactly max_steps attempts, on every variant's
+    # layout (2 modes: team; the short mode still finishes)
+    dims = _cabi.make_dims(ncosmo=1, nk=2, nout=1, lmaxg=11, lmaxgp=11, lmaxr=11, lmaxnu=8, nqmax=3, nth=tab.nth, nnu=tab.nnu,
+                           max_steps=25)
+    outm = lib.evolve_host(dims, ctrl, tab.scalars[None], tab.tables[None], np.array([1e-4, 1.0]), np.array([1.0]))
+    assert outm["status"][0].tolist() == [0, 1] and outm["nsteps"][0, 1] == 25 and outm["nsteps"][0, 0] < 25
     # non-finite input
     dims = _cabi.make_dims(ncosmo=1, nk=2, nout=1, lmaxg=11, lmaxgp=11, lmaxr=11, lmaxnu=8, nqmax=3, nth=tab.nth, nnu=tab.nnu,
                            max_steps=256)
