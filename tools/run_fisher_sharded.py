@@ -28,6 +28,14 @@ def as_param(scal, tab):
 param = as_param(z["scalars"], z["tables"])
 dparams = [as_param(z["d_scalars"][d], z["d_tables"][d]) for d in range(7)]
 
+def allgather(buf):
+    """the gather evolve_perturbations_jvp_sharded asks its caller for: equal-size float64 buffers from every rank, in rank order"""
+    t = torch.from_numpy(np.ascontiguousarray(buf)).cuda()
+    outs = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(outs, t)
+    return [o.cpu().numpy() for o in outs]
+
+
 def barrier():
     if world > 1:
         dist.barrier()
@@ -39,7 +47,8 @@ for dm in ((11, 11, 11, 8, 3), (31, 31, 31, 31, 5)):
     for rep in range(3):
         barrier(); t = time.perf_counter()
         y, dy, pk, dpk, k = evolve_perturbations_jvp_sharded(param=dict(param), dparam=dparams, aexp_out=[0.5, 1.0], kmin=1e-4, kmax=10.0,
-                                                             num_k=512, device=local, **kw)
+                                                             num_k=512, device=local, rank=rank, world=world,
+                                                             allgather=allgather if world > 1 else None, **kw)
         barrier()
         dt = torch.tensor([time.perf_counter() - t], dtype=torch.float64, device="cuda")
         if world > 1:
