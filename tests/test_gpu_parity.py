@@ -187,7 +187,7 @@ def test_deep_launch_of_small_hierarchies_takes_the_lane_kernel(gpu_lib, tables,
     rel = np.abs(a["pk"] / b["pk"] - 1)
     # (P(k) ~ delta^2; at lmax = 11 and rtol 1e-4 ANY two kernels differ by up to ~2e-2 on the worst long mode -- team vs
     #  cyclic 1.69e-2, lane vs cyclic 1.68e-2 on this launch, all three equally far from a tight-tolerance run:
-    #  tools/dbg_small_n_variants.py -- so the bar is the variants' own spread, and most modes must agree far better)
+    #  tools/compare_variants_small_n.py -- so the bar is the variants' own spread, and most modes must agree far better)
     assert np.median(rel) < 1e-8 and np.mean(rel > 1e-3) < 0.05 and rel.max() < 0.05, (np.median(rel), np.mean(rel > 1e-3), rel.max())
     assert np.mean(a["nsteps"] == b["nsteps"]) > 0.5
     assert np.array_equal(a["pk"][0], a["pk"][2]) and not np.array_equal(a["pk"][0], a["pk"][1])      # cosmologies kept apart

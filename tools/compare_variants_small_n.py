@@ -1,3 +1,6 @@
+"""At n = 72 and rtol 1e-4: how far the kernel variants (lane, cyclic one-warp, team) are from each other and from a
+tight-tolerance run on a deep multi-cosmology launch -- the spread that sets the bar of
+tests/test_gpu_parity.py::test_deep_launch_of_small_hierarchies_takes_the_lane_kernel (run under gpurun)."""
 import os, sys
 import numpy as np
 ROOT = "/root/repo"
