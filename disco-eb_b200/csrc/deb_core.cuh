@@ -294,6 +294,7 @@ struct Problem {
   // both look at the list's verdict word (ticket[2]) and fall back / exit when the list was rejected
   int hybrid_split;
   unsigned int* ticket2;     // the lane kernel's own queue counter in hybrid launches
+  int duo_nosolo;            // two-team CTAs: 1 = every long mode keeps a partner team (measurement switch DEB_DUO_SOLO=0)
   int lockstep;              // chain-lane kernel: warps of a CTA advance stage by stage together (deb_lane.cuh)
   int stage_tables;          // chain-lane kernel, ncosmo == 1: the three RHS splines staged in shared memory by one bulk async copy
   int npeer, out_mul, out_add, out_nk;

@@ -182,12 +182,26 @@ __global__ void __launch_bounds__(256, 1) k_evolve_duo(const __grid_constant__ P
   const int G = 2 * gridDim.x;
   const bool ordered = P.order_hdr && P.ticket[2] == 1u;
   const int* order = P.order_hdr + 8;
+  // The nsolo longest modes (CTAs 0 .. nsolo-1) keep their SM to themselves: team 1 of those CTAs leaves at once, and its
+  // static positions G/2 .. G/2+nsolo-1 are served first by the ticket counter.  Any nsolo in [0, G/2] keeps the map
+  // position <-> (CTA, team, ticket) one-to-one; the value only moves work around (results do not depend on it).
+  int nsolo = 0;
+  if (ordered) {
+    nsolo = P.order_hdr[4];
+    const int cap = (int)gridDim.x / 4;              // never give up more than a quarter of the second teams
+    nsolo = nsolo < 0 ? 0 : (nsolo > cap ? cap : nsolo);
+    if (total < G) nsolo = 0;                        // (not every team has a first mode: nothing to rearrange)
+    if (total > 2 * G) nsolo = 0;                    // deeper launches are bound by the sum of the work, not by the longest mode:
+                                                     // the slots given up cost more there (768 modes 21.7 -> 22.6 ms, 512 modes 20.1 -> 19.5)
+  }
+  if (P.duo_nosolo) nsolo = 0;
   bool first = true;
   for (;;) {
     if (tid == 0) {
       unsigned int t;
-      if (ordered && first) t = (unsigned int)(tq * (G / 2) + blockIdx.x);
-      else t = (ordered ? (unsigned int)G : 0u) + atomicAdd(P.ticket, 1u);
+      if (ordered && first) t = (tq == 1 && (int)blockIdx.x < nsolo) ? (unsigned int)total : (unsigned int)(tq * (G / 2) + blockIdx.x);
+      else if (ordered) { const unsigned int q = atomicAdd(P.ticket, 1u); t = q < (unsigned int)nsolo ? (unsigned int)(G / 2) + q : (unsigned int)G + (q - (unsigned int)nsolo); }
+      else t = atomicAdd(P.ticket, 1u);
       s_ctl[tq] = t;
     }
     first = false;
@@ -228,17 +242,24 @@ __global__ void __launch_bounds__(1024) k_learn_order(const int* __restrict__ ns
   // hybrid launches: how many modes (from the front of the list) take more than 0.38 x the longest step count.  Those go to
   // team CTAs (31 us per step with chain-lane warps beside them), the others to chain-lane warps (81 us per step measured
   // next to a team CTA): both halves then finish together.
-  __shared__ int nlong;
-  if (threadIdx.x == 0) nlong = 0;
+  // two-team CTAs: how many modes are within 5.5 % of the longest step count.  A team beside a working partner needs
+  // ~33 us per step, alone on its SM 31.3: these modes -- the ones the launch waits for -- get an SM without a partner
+  // (k_evolve_duo), everything else has slack.
+  __shared__ int nlong, nsolo;
+  if (threadIdx.x == 0) { nlong = 0; nsolo = 0; }
   __syncthreads();
   {
     const unsigned int smax = (key[0] >> 11) & 0xfffffu;
-    int c = 0;
-    for (int i = threadIdx.x; i < total; i += 1024) c += (((key[i] >> 11) & 0xfffffu) * 100u > smax * 38u) ? 1 : 0;
-    atomicAdd(&nlong, c);
+    int c = 0, c2 = 0;
+    for (int i = threadIdx.x; i < total; i += 1024) {
+      const unsigned int ns = (key[i] >> 11) & 0xfffffu;
+      c += (ns * 100u > smax * 38u) ? 1 : 0;
+      c2 += (ns * 1000u > smax * 945u) ? 1 : 0;
+    }
+    atomicAdd(&nlong, c); atomicAdd(&nsolo, c2);
   }
   __syncthreads();
-  if (threadIdx.x == 0) { hdr[1] = total; hdr[2] = shape_hash; hdr[3] = nlong; __threadfence(); hdr[0] = DEB_ORDER_MAGIC; }
+  if (threadIdx.x == 0) { hdr[1] = total; hdr[2] = shape_hash; hdr[3] = nlong; hdr[4] = nsolo; __threadfence(); hdr[0] = DEB_ORDER_MAGIC; }
 }
 
 typedef void (*evolve_kernel_t)(const Problem);
@@ -277,6 +298,8 @@ int deb_launch_team(const Problem& P, cudaStream_t st, int nsm) {
       Problem Q = P;
       Q.lockstep = 1;
       if (const char* e = getenv("DEB_DUO_LOCKSTEP")) Q.lockstep = atoi(e);
+      Q.duo_nosolo = 0;
+      if (const char* e = getenv("DEB_DUO_SOLO")) Q.duo_nosolo = atoi(e) == 0;
       if (Q.lockstep != 0 && Q.lockstep != 1 && Q.lockstep != 2 && Q.lockstep != 4 && Q.lockstep != 8) Q.lockstep = 1;
       CUDA_TRY(cudaFuncSetAttribute((const void*)dk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem));
       long grid = nsm;

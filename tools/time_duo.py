@@ -8,14 +8,14 @@ import helpers
 from discoeb_b200 import _cabi
 tab = helpers.load_tables("fiducial")
 lib = _cabi.default_library()
-variants = [("solo", {"DEB_DUO": "0"})] + [(f"duo_ls{e}", {"DEB_DUO": "1", "DEB_DUO_LOCKSTEP": str(e)}) for e in (0, 8, 4, 2, 1)]
+variants = [("solo", {"DEB_DUO": "0"}), ("duo_partnered", {"DEB_DUO": "1", "DEB_DUO_SOLO": "0"})] + [(f"duo_ls{e}", {"DEB_DUO": "1", "DEB_DUO_LOCKSTEP": str(e)}) for e in (0, 2, 1)]
 for nk in [int(a) for a in sys.argv[1:]] or [256, 512, 1024]:
     ks = np.geomspace(1e-4, 10.0, nk)
     dims = _cabi.make_dims(ncosmo=1, nk=nk, nout=1, lmaxg=31, lmaxgp=31, lmaxr=31, lmaxnu=31, nqmax=5, nth=tab.nth, nnu=tab.nnu, max_steps=2048, power_idx=4)
     ctrl = _cabi.make_ctrl(rtol=1e-4, atol=1e-4)
     row, base = dict(modes=nk), None
     for name, env in variants:
-        for k_ in ("DEB_DUO", "DEB_DUO_LOCKSTEP"): os.environ.pop(k_, None)
+        for k_ in ("DEB_DUO", "DEB_DUO_LOCKSTEP", "DEB_DUO_SOLO"): os.environ.pop(k_, None)
         os.environ.update(env)
         ts = []
         for _ in range(8):
